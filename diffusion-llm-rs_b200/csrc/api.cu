@@ -1,0 +1,1167 @@
+// api.cu — the C ABI (include/dllm_b200.h): context, host-pointer entry points that stage
+// through device buffers, device-pointer entry points that only enqueue, the quantized weight
+// object, the layer stack behind DiffusionModel, p_sample / sample, and the KV cache entry.
+// There is no CPU path anywhere in this file: every compute call launches CUDA kernels.
+#include <math.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "wlayout.cuh"
+
+#define CTX_CHECK(ctx)                    \
+    do {                                  \
+        if (!(ctx)) return DLLM_ERR_NULL; \
+        (ctx)->err[0] = 0;                \
+    } while (0)
+
+#define ARG_CHECK(ctx, cond, code, ...)                  \
+    do {                                                 \
+        if (!(cond)) DLLM_FAIL(ctx, code, __VA_ARGS__);  \
+    } while (0)
+
+static inline bool pack_width_ok(int bits) { return bits == 1 || bits == 2 || bits == 4 || bits == 8; }
+
+// ==========================================================================================
+// context
+// ==========================================================================================
+extern "C" {
+
+const char *dllm_version(void) { return "dllm_b200 0.1.0 (sm_100a)"; }
+
+int32_t dllm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int32_t ctx_init(int32_t device, void *stream, bool adopt, dllm_ctx **out) {
+    if (!out) return DLLM_ERR_NULL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return DLLM_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) return DLLM_ERR_NO_DEVICE;
+    dllm_ctx *ctx = new (std::nothrow) dllm_ctx();
+    if (!ctx) return DLLM_ERR_OOM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DLLM_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return DLLM_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) {   // kernels are sm_100a only: fail loudly, never fall back
+        delete ctx;
+        return DLLM_ERR_NO_DEVICE;
+    }
+    if (adopt) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->owns_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DLLM_ERR_CUDA; }
+        ctx->owns_stream = true;
+    }
+    bool ok = cudaMalloc(&ctx->d_partials, sizeof(float) * 2 * kMaxPartials) == cudaSuccess &&
+              cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_params, sizeof(float) * 16) == cudaSuccess &&
+              cudaMallocHost(&ctx->h_params, sizeof(float) * 16) == cudaSuccess &&
+              cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)) == cudaSuccess;
+    if (!ok) { dllm_ctx_destroy(ctx); return DLLM_ERR_CUDA; }
+    *out = ctx;
+    return DLLM_OK;
+}
+
+int32_t dllm_ctx_create(int32_t device, dllm_ctx **out) { return ctx_init(device, nullptr, false, out); }
+int32_t dllm_ctx_create_on_stream(int32_t device, void *cuda_stream, dllm_ctx **out) {
+    return ctx_init(device, cuda_stream, true, out);
+}
+
+int32_t dllm_tp_finalize(dllm_ctx *ctx);
+
+void dllm_ctx_destroy(dllm_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    dllm_tp_finalize(ctx);
+    for (auto &b : ctx->ws) if (b.p) cudaFree(b.p);
+    for (auto &b : ctx->act) if (b.p) cudaFree(b.p);
+    if (ctx->lin_ws.p) cudaFree(ctx->lin_ws.p);
+    if (ctx->lin_flags.p) cudaFree(ctx->lin_flags.p);
+    if (ctx->d_partials) cudaFree(ctx->d_partials);
+    if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+    if (ctx->d_params) cudaFree(ctx->d_params);
+    if (ctx->h_params) cudaFreeHost(ctx->h_params);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int32_t dllm_ctx_sync(dllm_ctx *ctx) {
+    CTX_CHECK(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DLLM_OK;
+}
+void *dllm_ctx_stream(dllm_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+const char *dllm_last_error(const dllm_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+uint64_t dllm_launch_count(const dllm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int32_t dllm_sm_count(const dllm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+int32_t dllm_malloc(dllm_ctx *ctx, size_t bytes, void **dptr) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, dptr, DLLM_ERR_NULL, "null out pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+    return DLLM_OK;
+}
+int32_t dllm_free(dllm_ctx *ctx, void *dptr) {
+    CTX_CHECK(ctx);
+    if (dptr) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(dptr)); }
+    return DLLM_OK;
+}
+int32_t dllm_memcpy_h2d(dllm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    CTX_CHECK(ctx);
+    if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return DLLM_OK;
+}
+int32_t dllm_memcpy_d2h(dllm_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    CTX_CHECK(ctx);
+    if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DLLM_OK;
+}
+int32_t dllm_host_alloc(size_t bytes, void **hptr) {
+    if (!hptr) return DLLM_ERR_NULL;
+    return cudaMallocHost(hptr, bytes ? bytes : 1) == cudaSuccess ? DLLM_OK : DLLM_ERR_OOM;
+}
+int32_t dllm_host_free(void *hptr) {
+    if (hptr && cudaFreeHost(hptr) != cudaSuccess) return DLLM_ERR_CUDA;
+    return DLLM_OK;
+}
+
+}  // extern "C"
+
+// staging helpers ---------------------------------------------------------------------------
+static int32_t stage_in(dllm_ctx *ctx, int slot, const void *host, size_t bytes, void **dev) {
+    DLLM_TRY(ensure_buf(ctx, ctx->ws[slot], bytes ? bytes : 16));
+    *dev = ctx->ws[slot].p;
+    if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return DLLM_OK;
+}
+static int32_t stage_out_buf(dllm_ctx *ctx, int slot, size_t bytes, void **dev) {
+    DLLM_TRY(ensure_buf(ctx, ctx->ws[slot], bytes ? bytes : 16));
+    *dev = ctx->ws[slot].p;
+    return DLLM_OK;
+}
+static int32_t copy_out(dllm_ctx *ctx, void *host, const void *dev, size_t bytes) {
+    if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return DLLM_OK;
+}
+static int32_t sync(dllm_ctx *ctx) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DLLM_OK;
+}
+
+extern "C" {
+
+// ==========================================================================================
+// quantizer B
+// ==========================================================================================
+int32_t dllm_quantize_tensor_dev(dllm_ctx *ctx, const float *x_dev, size_t n, uint8_t bits, int32_t packed,
+                                 uint8_t *codes_dev, float *params_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, bits >= 1 && bits <= 8, DLLM_ERR_INVALID_PARAMS, "Bits must be between 1 and 8 (got %d)", (int)bits);
+    ARG_CHECK(ctx, !packed || pack_width_ok(bits), DLLM_ERR_INVALID_PARAMS, "packed codes need bits in {1,2,4,8}");
+    ARG_CHECK(ctx, params_dev && (n == 0 || (x_dev && codes_dev)), DLLM_ERR_NULL, "null device pointer");
+    DLLM_TRY(k_minmax(ctx, x_dev, n, bits, params_dev));
+    return k_encode_b(ctx, x_dev, n, bits, packed ? bits : 0, params_dev, 0.f, 0.f, codes_dev);
+}
+
+int32_t dllm_dequantize_tensor_dev(dllm_ctx *ctx, const uint8_t *codes_dev, size_t n, uint8_t bits, int32_t packed,
+                                   const float *params_dev, float *out_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, !packed || pack_width_ok(bits), DLLM_ERR_INVALID_PARAMS, "packed codes need bits in {1,2,4,8}");
+    ARG_CHECK(ctx, params_dev && (n == 0 || (codes_dev && out_dev)), DLLM_ERR_NULL, "null device pointer");
+    return k_decode_ab(ctx, codes_dev, n, packed ? bits : 0, params_dev, 0.f, 0.f, out_dev);
+}
+
+int32_t dllm_quantize_tensor(dllm_ctx *ctx, const float *x, size_t n, uint8_t bits, uint8_t *codes, float *scale,
+                             float *zero_point) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, bits >= 1 && bits <= 8, DLLM_ERR_INVALID_PARAMS, "Bits must be between 1 and 8 (got %d)", (int)bits);
+    ARG_CHECK(ctx, scale && zero_point && (n == 0 || (x && codes)), DLLM_ERR_NULL, "null pointer");
+    void *dx, *dc;
+    DLLM_TRY(stage_in(ctx, 0, x, n * sizeof(float), &dx));
+    DLLM_TRY(stage_out_buf(ctx, 1, n, &dc));
+    DLLM_TRY(dllm_quantize_tensor_dev(ctx, (const float *)dx, n, bits, 0, (uint8_t *)dc, ctx->d_params));
+    DLLM_TRY(copy_out(ctx, codes, dc, n));
+    DLLM_TRY(copy_out(ctx, ctx->h_params, ctx->d_params, 4 * sizeof(float)));
+    DLLM_TRY(sync(ctx));
+    *scale = ctx->h_params[0];
+    *zero_point = ctx->h_params[1];
+    return DLLM_OK;
+}
+
+int32_t dllm_dequantize_tensor(dllm_ctx *ctx, const uint8_t *codes, size_t n, float scale, float zero_point,
+                               float *out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, n == 0 || (codes && out), DLLM_ERR_NULL, "null pointer");
+    void *dc, *dout;
+    DLLM_TRY(stage_in(ctx, 1, codes, n, &dc));
+    DLLM_TRY(stage_out_buf(ctx, 0, n * sizeof(float), &dout));
+    DLLM_TRY(k_decode_ab(ctx, (const uint8_t *)dc, n, 0, nullptr, scale, zero_point, (float *)dout));
+    DLLM_TRY(copy_out(ctx, out, dout, n * sizeof(float)));
+    return sync(ctx);
+}
+
+int32_t dllm_quantize_codes(dllm_ctx *ctx, const float *x, size_t n, uint8_t bits, float scale, float zero_point,
+                            uint8_t *codes) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, bits >= 1 && bits <= 8, DLLM_ERR_INVALID_PARAMS, "Bits must be between 1 and 8 (got %d)", (int)bits);
+    ARG_CHECK(ctx, n == 0 || (x && codes), DLLM_ERR_NULL, "null pointer");
+    void *dx, *dc;
+    DLLM_TRY(stage_in(ctx, 0, x, n * sizeof(float), &dx));
+    DLLM_TRY(stage_out_buf(ctx, 1, n, &dc));
+    DLLM_TRY(k_encode_b(ctx, (const float *)dx, n, bits, 0, nullptr, scale, zero_point, (uint8_t *)dc));
+    DLLM_TRY(copy_out(ctx, codes, dc, n));
+    return sync(ctx);
+}
+
+float dllm_compression_ratio(size_t numel, size_t data_len, uint8_t bits) {
+    const size_t original = numel * 4;                         // quantization.rs:121
+    const size_t compressed = (data_len * (size_t)bits + 7) / 8;  // :122
+    return (float)original / (float)compressed;
+}
+
+// ==========================================================================================
+// quantizer A
+// ==========================================================================================
+static bool a_range(int32_t qtype, float *lo, float *hi) {
+    switch (qtype) {   // quantization/src/quantize.rs:139-144
+        case DLLM_QT_INT8: *lo = -128.f; *hi = 127.f; return true;
+        case DLLM_QT_INT4: *lo = -8.f; *hi = 7.f; return true;
+        case DLLM_QT_BINARY: *lo = 0.f; *hi = 1.f; return true;
+        case DLLM_QT_FLOAT8: *lo = -127.f; *hi = 127.f; return true;
+    }
+    return false;
+}
+
+int32_t dllm_quantize_a(dllm_ctx *ctx, const float *x, size_t n, int32_t qtype, float scale, int32_t zero_point,
+                        uint8_t *codes) {
+    CTX_CHECK(ctx);
+    float lo, hi;
+    ARG_CHECK(ctx, a_range(qtype, &lo, &hi), DLLM_ERR_INVALID_PARAMS, "unknown QuantizationType %d", qtype);
+    ARG_CHECK(ctx, n == 0 || (x && codes), DLLM_ERR_NULL, "null pointer");
+    void *dx, *dc;
+    DLLM_TRY(stage_in(ctx, 0, x, n * sizeof(float), &dx));
+    DLLM_TRY(stage_out_buf(ctx, 1, n, &dc));
+    DLLM_TRY(k_encode_a(ctx, (const float *)dx, n, scale, (float)zero_point, lo, hi, (uint8_t *)dc));
+    DLLM_TRY(copy_out(ctx, codes, dc, n));
+    return sync(ctx);
+}
+
+int32_t dllm_dequantize_a(dllm_ctx *ctx, const uint8_t *codes, size_t n, float scale, int32_t zero_point,
+                          float *out) {
+    return dllm_dequantize_tensor(ctx, codes, n, scale, (float)zero_point, out);  // same form, quantize.rs:179-181
+}
+
+int32_t dllm_minmax(dllm_ctx *ctx, const float *x, size_t n, float *min_out, float *max_out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, min_out && max_out && (n == 0 || x), DLLM_ERR_NULL, "null pointer");
+    void *dx;
+    DLLM_TRY(stage_in(ctx, 0, x, n * sizeof(float), &dx));
+    DLLM_TRY(k_minmax(ctx, (const float *)dx, n, 0, ctx->d_params));
+    DLLM_TRY(copy_out(ctx, ctx->h_params, ctx->d_params, 4 * sizeof(float)));
+    DLLM_TRY(sync(ctx));
+    *min_out = ctx->h_params[2];
+    *max_out = ctx->h_params[3];
+    return DLLM_OK;
+}
+
+static int32_t f32_as_i32_sat(float v) {
+    if (v != v) return 0;
+    if (v <= -2147483648.0f) return INT32_MIN;
+    if (v >= 2147483648.0f) return INT32_MAX;
+    return (int32_t)v;
+}
+
+int32_t dllm_calibrate_params(float min, float max, size_t total_samples, uint8_t bits, int32_t symmetric,
+                              float *scale, int32_t *zero_point) {
+    if (!scale || !zero_point) return DLLM_ERR_NULL;
+    if (total_samples == 0) return DLLM_ERR_CALIBRATION_REQUIRED;        // calibrate.rs:73-75
+    if (bits > 31) return DLLM_ERR_INVALID_PARAMS;
+    volatile float num_levels = (float)(1u << bits);                     // :77
+    volatile float range = max - min;                                    // :78
+    if (range <= 1.1920929e-07f) { *scale = 1.0f; *zero_point = 0; return DLLM_OK; }
+    if (symmetric) {
+        volatile float max_abs = fmaxf(fabsf(max), fabsf(min));          // :91
+        volatile float t = max_abs * 2.0f;
+        *scale = t / (num_levels - 1.0f);                                // :92
+        volatile float h = num_levels / 2.0f;
+        *zero_point = f32_as_i32_sat(h - 1.0f);                          // :98
+    } else {
+        volatile float s = range / (num_levels - 1.0f);                  // :94
+        *scale = s;
+        volatile float q = -min / s;
+        *zero_point = f32_as_i32_sat(roundf(q));                         // :100
+    }
+    return DLLM_OK;
+}
+
+// ==========================================================================================
+// quantizers C and D
+// ==========================================================================================
+float dllm_bitquantizer_scale(uint8_t bits) {
+    if (bits > 30) return 0.f;
+    return 1.0f / (float)(int32_t)((1u << bits) - 1u);   // prefill-kvquant-rs/lib.rs:105
+}
+
+int32_t dllm_quantize_c(dllm_ctx *ctx, const float *x, size_t n, uint8_t bits, float scale, float zero_point,
+                        uint8_t *codes) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, bits <= 30, DLLM_ERR_INVALID_PARAMS, "bits %d overflows `1 << bits`", (int)bits);
+    ARG_CHECK(ctx, n == 0 || (x && codes), DLLM_ERR_NULL, "null pointer");
+    void *dx, *dc;
+    DLLM_TRY(stage_in(ctx, 0, x, n * sizeof(float), &dx));
+    DLLM_TRY(stage_out_buf(ctx, 1, n, &dc));
+    DLLM_TRY(k_encode_cd(ctx, (const float *)dx, n, bits, 0, scale, zero_point, (uint8_t *)dc));
+    DLLM_TRY(copy_out(ctx, codes, dc, n));
+    return sync(ctx);
+}
+
+int32_t dllm_dequantize_cd(dllm_ctx *ctx, const uint8_t *codes, size_t n, float scale, float zero_point, float *out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, n == 0 || (codes && out), DLLM_ERR_NULL, "null pointer");
+    void *dc, *dout;
+    DLLM_TRY(stage_in(ctx, 1, codes, n, &dc));
+    DLLM_TRY(stage_out_buf(ctx, 0, n * sizeof(float), &dout));
+    DLLM_TRY(k_decode_cd(ctx, (const uint8_t *)dc, n, 0, scale, zero_point, nullptr, nullptr, 0, (float *)dout));
+    DLLM_TRY(copy_out(ctx, out, dout, n * sizeof(float)));
+    return sync(ctx);
+}
+
+int32_t dllm_kvquant_quantize_vectors(dllm_ctx *ctx, const float *embeddings, size_t nvec, size_t elems_per_vec,
+                                      const uint8_t *cfg_bits, size_t ncfg, const uint8_t *bits, size_t nbits,
+                                      uint8_t *codes) {
+    CTX_CHECK(ctx);
+    if (nbits == 0 || nvec == 0) return DLLM_OK;   // zip with an empty cycle yields nothing (lib.rs:132)
+    ARG_CHECK(ctx, embeddings && cfg_bits && bits && codes, DLLM_ERR_NULL, "null pointer");
+    // validate first: the reference panics on the first out-of-range vector (lib.rs:133)
+    for (size_t v = 0; v < nvec; ++v) {
+        const size_t qi = (size_t)bits[v % nbits] / 2;
+        ARG_CHECK(ctx, qi < ncfg, DLLM_ERR_INDEX, "quantizers[%zu] out of bounds (len %zu)", qi, ncfg);
+        ARG_CHECK(ctx, bits[v % nbits] <= 30 && cfg_bits[qi] <= 30, DLLM_ERR_INVALID_PARAMS, "bits overflow");
+    }
+    const size_t n = nvec * elems_per_vec;
+    void *dx, *dc;
+    DLLM_TRY(stage_in(ctx, 0, embeddings, n * sizeof(float), &dx));
+    DLLM_TRY(stage_out_buf(ctx, 1, n, &dc));
+    if (nbits == 1) {   // one bit width: a single launch over all vectors
+        const float s = dllm_bitquantizer_scale(cfg_bits[bits[0] / 2]);
+        DLLM_TRY(k_encode_cd(ctx, (const float *)dx, n, bits[0], 0, s, 0.0f, (uint8_t *)dc));
+    } else {
+        for (size_t v = 0; v < nvec; ++v) {
+            const uint8_t b = bits[v % nbits];
+            const float s = dllm_bitquantizer_scale(cfg_bits[b / 2]);
+            DLLM_TRY(k_encode_cd(ctx, (const float *)dx + v * elems_per_vec, elems_per_vec, b, 0, s, 0.0f,
+                                 (uint8_t *)dc + v * elems_per_vec));
+        }
+    }
+    DLLM_TRY(copy_out(ctx, codes, dc, n));
+    return sync(ctx);
+}
+
+int32_t dllm_quantize_d_rows_dev(dllm_ctx *ctx, const float *x_dev, size_t rows, size_t dim, uint8_t bits,
+                                 int32_t packed, uint8_t *codes_dev, float *scales_dev, float *zero_points_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, bits <= 31, DLLM_ERR_INVALID_PARAMS, "bits %d overflows `1u32 << bits`", (int)bits);
+    ARG_CHECK(ctx, !packed || pack_width_ok(bits), DLLM_ERR_INVALID_PARAMS, "packed codes need bits in {1,2,4,8}");
+    ARG_CHECK(ctx, rows * dim == 0 || (x_dev && codes_dev && scales_dev && zero_points_dev), DLLM_ERR_NULL, "null device pointer");
+    return k_quant_d_rows(ctx, x_dev, rows, dim, nullptr, 1, bits, packed ? bits : 0, codes_dev, scales_dev,
+                          zero_points_dev);
+}
+
+int32_t dllm_dequantize_d_rows_dev(dllm_ctx *ctx, const uint8_t *codes_dev, size_t rows, size_t dim, uint8_t bits,
+                                   int32_t packed, const float *scales_dev, const float *zero_points_dev,
+                                   float *out_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, !packed || pack_width_ok(bits), DLLM_ERR_INVALID_PARAMS, "packed codes need bits in {1,2,4,8}");
+    ARG_CHECK(ctx, rows * dim == 0 || (codes_dev && scales_dev && zero_points_dev && out_dev), DLLM_ERR_NULL, "null device pointer");
+    return k_decode_cd(ctx, codes_dev, rows * dim, packed ? bits : 0, 0.f, 0.f, scales_dev, zero_points_dev, dim, out_dev);
+}
+
+int32_t dllm_quantize_d_rows(dllm_ctx *ctx, const float *x, size_t rows, size_t dim, const uint8_t *bits,
+                             size_t nbits, uint8_t *codes, float *scales, float *zero_points) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, nbits > 0 && bits, DLLM_ERR_INVALID_PARAMS, "empty bits list (`i %% 0` panics, fusion_ann.rs:58)");
+    for (size_t i = 0; i < nbits; ++i)
+        ARG_CHECK(ctx, bits[i] <= 31, DLLM_ERR_INVALID_PARAMS, "bits %d overflows `1u32 << bits`", (int)bits[i]);
+    const size_t n = rows * dim;
+    ARG_CHECK(ctx, n == 0 || (x && codes && scales && zero_points), DLLM_ERR_NULL, "null pointer");
+    if (rows == 0) return DLLM_OK;
+    void *dx, *dc, *dsz, *dtab;
+    DLLM_TRY(stage_in(ctx, 0, x, n * sizeof(float), &dx));
+    DLLM_TRY(stage_out_buf(ctx, 1, n, &dc));
+    DLLM_TRY(stage_out_buf(ctx, 2, 2 * rows * sizeof(float), &dsz));
+    DLLM_TRY(stage_in(ctx, 3, bits, nbits, &dtab));
+    float *ds = (float *)dsz, *dz = ds + rows;
+    DLLM_TRY(k_quant_d_rows(ctx, (const float *)dx, rows, dim, nbits > 1 ? (const uint8_t *)dtab : nullptr,
+                            (int)nbits, bits[0], 0, (uint8_t *)dc, ds, dz));
+    DLLM_TRY(copy_out(ctx, codes, dc, n));
+    DLLM_TRY(copy_out(ctx, scales, ds, rows * sizeof(float)));
+    DLLM_TRY(copy_out(ctx, zero_points, dz, rows * sizeof(float)));
+    return sync(ctx);
+}
+
+int32_t dllm_dequantize_d_rows(dllm_ctx *ctx, const uint8_t *codes, size_t rows, size_t dim, const float *scales,
+                               const float *zero_points, float *out) {
+    CTX_CHECK(ctx);
+    const size_t n = rows * dim;
+    ARG_CHECK(ctx, n == 0 || (codes && scales && zero_points && out), DLLM_ERR_NULL, "null pointer");
+    if (n == 0) return DLLM_OK;
+    void *dc, *dout, *dsz;
+    DLLM_TRY(stage_in(ctx, 1, codes, n, &dc));
+    DLLM_TRY(stage_out_buf(ctx, 2, 2 * rows * sizeof(float), &dsz));
+    float *ds = (float *)dsz, *dz = ds + rows;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds, scales, rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dz, zero_points, rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    DLLM_TRY(stage_out_buf(ctx, 0, n * sizeof(float), &dout));
+    DLLM_TRY(k_decode_cd(ctx, (const uint8_t *)dc, n, 0, 0.f, 0.f, ds, dz, dim, (float *)dout));
+    DLLM_TRY(copy_out(ctx, out, dout, n * sizeof(float)));
+    return sync(ctx);
+}
+
+// ==========================================================================================
+// pack / unpack
+// ==========================================================================================
+size_t dllm_packed_len(size_t n, uint8_t bits) { return (n * (size_t)bits + 7) / 8; }
+
+int32_t dllm_pack_dev(dllm_ctx *ctx, const uint8_t *codes_dev, size_t n, uint8_t bits, uint8_t *packed_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, pack_width_ok(bits), DLLM_ERR_INVALID_PARAMS, "pack width %d not in {1,2,4,8}", (int)bits);
+    return k_pack(ctx, codes_dev, n, bits, packed_dev);
+}
+int32_t dllm_unpack_dev(dllm_ctx *ctx, const uint8_t *packed_dev, size_t n, uint8_t bits, uint8_t *codes_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, pack_width_ok(bits), DLLM_ERR_INVALID_PARAMS, "pack width %d not in {1,2,4,8}", (int)bits);
+    return k_unpack(ctx, packed_dev, n, bits, codes_dev);
+}
+int32_t dllm_pack(dllm_ctx *ctx, const uint8_t *codes, size_t n, uint8_t bits, uint8_t *packed) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, pack_width_ok(bits), DLLM_ERR_INVALID_PARAMS, "pack width %d not in {1,2,4,8}", (int)bits);
+    ARG_CHECK(ctx, n == 0 || (codes && packed), DLLM_ERR_NULL, "null pointer");
+    void *dc, *dp;
+    DLLM_TRY(stage_in(ctx, 1, codes, n, &dc));
+    DLLM_TRY(stage_out_buf(ctx, 2, dllm_packed_len(n, bits), &dp));
+    DLLM_TRY(k_pack(ctx, (const uint8_t *)dc, n, bits, (uint8_t *)dp));
+    DLLM_TRY(copy_out(ctx, packed, dp, dllm_packed_len(n, bits)));
+    return sync(ctx);
+}
+int32_t dllm_unpack(dllm_ctx *ctx, const uint8_t *packed, size_t n, uint8_t bits, uint8_t *codes) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, pack_width_ok(bits), DLLM_ERR_INVALID_PARAMS, "pack width %d not in {1,2,4,8}", (int)bits);
+    ARG_CHECK(ctx, n == 0 || (codes && packed), DLLM_ERR_NULL, "null pointer");
+    void *dc, *dp;
+    DLLM_TRY(stage_in(ctx, 2, packed, dllm_packed_len(n, bits), &dp));
+    DLLM_TRY(stage_out_buf(ctx, 1, n, &dc));
+    DLLM_TRY(k_unpack(ctx, (const uint8_t *)dp, n, bits, (uint8_t *)dc));
+    DLLM_TRY(copy_out(ctx, codes, dc, n));
+    return sync(ctx);
+}
+
+// ==========================================================================================
+// quantized weight
+// ==========================================================================================
+static int32_t qweight_alloc(dllm_ctx *ctx, size_t K, size_t N, uint8_t bits, size_t group, dllm_qweight **out) {
+    ARG_CHECK(ctx, out, DLLM_ERR_NULL, "null out pointer");
+    *out = nullptr;
+    ARG_CHECK(ctx, bits >= 1 && bits <= 8, DLLM_ERR_INVALID_PARAMS, "Bits must be between 1 and 8 (got %d)", (int)bits);
+    ARG_CHECK(ctx, K > 0 && N > 0, DLLM_ERR_SHAPE, "empty weight [%zu, %zu]", K, N);
+    ARG_CHECK(ctx, group == 0 || (group % WL_TILE_K == 0 && K % group == 0), DLLM_ERR_SHAPE,
+              "group %zu must be a multiple of %d that divides K=%zu", group, WL_TILE_K, K);
+    dllm_qweight *w = new (std::nothrow) dllm_qweight();
+    if (!w) return DLLM_ERR_OOM;
+    w->K = K; w->N = N; w->bits = bits; w->device = ctx->device;
+    w->k_blocks = (K + WL_TILE_K - 1) / WL_TILE_K;
+    w->n_tiles = (N + WL_TILE_N - 1) / WL_TILE_N;
+    w->per_tensor = group == 0;
+    w->group = group == 0 ? w->k_blocks * WL_TILE_K : group;
+    const int cb = wl_container_bits(bits);
+    w->tile_bytes = wl_tile_bytes(cb);
+    const size_t G = w->per_tensor ? 1 : K / group;
+    const size_t Npad = w->n_tiles * WL_TILE_N;
+    cudaError_t e = cudaMalloc(&w->d_packed, w->n_tiles * w->k_blocks * w->tile_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_scales, G * Npad * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_zps, G * Npad * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        dllm_qweight_destroy(w);
+        DLLM_FAIL(ctx, DLLM_ERR_OOM, "cudaMalloc failed for a [%zu,%zu] %d-bit weight", K, N, (int)bits);
+    }
+    *out = w;
+    return DLLM_OK;
+}
+
+static int32_t qweight_set_bias(dllm_ctx *ctx, dllm_qweight *w, const float *bias, bool bias_on_device) {
+    if (!bias) return DLLM_OK;
+    CUDA_TRY(ctx, cudaMalloc(&w->d_bias, w->N * sizeof(float)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(w->d_bias, bias, w->N * sizeof(float),
+                                  bias_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    return DLLM_OK;
+}
+
+int32_t dllm_qweight_quantize_dev(dllm_ctx *ctx, const float *w_dev, size_t K, size_t N, uint8_t bits, size_t group,
+                                  const float *bias_dev, dllm_qweight **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, w_dev, DLLM_ERR_NULL, "null weight pointer");
+    dllm_qweight *w = nullptr;
+    DLLM_TRY(qweight_alloc(ctx, K, N, bits, group, &w));
+    int32_t rc;
+    if (w->per_tensor) {
+        rc = k_minmax(ctx, w_dev, K * N, bits, ctx->d_params);
+        if (rc == DLLM_OK) rc = k_wparams_broadcast(ctx, ctx->d_params, N, w->d_scales, w->d_zps);
+        if (rc == DLLM_OK) {
+            cudaMemcpyAsync(ctx->h_params, ctx->d_params, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            w->tensor_scale = ctx->h_params[0];
+            w->tensor_zp = ctx->h_params[1];
+        }
+    } else {
+        rc = k_wparams_grouped(ctx, w_dev, K, N, group, bits, w->d_scales, w->d_zps);
+    }
+    if (rc == DLLM_OK) rc = k_wpack_from_f32(ctx, w_dev, w);
+    if (rc == DLLM_OK) rc = qweight_set_bias(ctx, w, bias_dev, true);
+    if (rc != DLLM_OK) { dllm_qweight_destroy(w); return rc; }
+    *out = w;
+    return DLLM_OK;
+}
+
+int32_t dllm_qweight_quantize(dllm_ctx *ctx, const float *w_host, size_t K, size_t N, uint8_t bits, size_t group,
+                              const float *bias, dllm_qweight **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, w_host, DLLM_ERR_NULL, "null weight pointer");
+    ARG_CHECK(ctx, K > 0 && N > 0, DLLM_ERR_SHAPE, "empty weight [%zu, %zu]", K, N);
+    void *dw, *db = nullptr;
+    DLLM_TRY(stage_in(ctx, 0, w_host, K * N * sizeof(float), &dw));
+    if (bias) DLLM_TRY(stage_in(ctx, 3, bias, N * sizeof(float), &db));
+    DLLM_TRY(dllm_qweight_quantize_dev(ctx, (const float *)dw, K, N, bits, group, (const float *)db, out));
+    return sync(ctx);
+}
+
+int32_t dllm_qweight_from_codes(dllm_ctx *ctx, const uint8_t *codes, const float *scales, const float *zero_points,
+                                size_t K, size_t N, uint8_t bits, size_t group, const float *bias,
+                                dllm_qweight **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, codes && scales && zero_points, DLLM_ERR_NULL, "null pointer");
+    dllm_qweight *w = nullptr;
+    DLLM_TRY(qweight_alloc(ctx, K, N, bits, group, &w));
+    const size_t Npad = w->n_tiles * WL_TILE_N;
+    int32_t rc = DLLM_OK;
+    void *dc = nullptr;
+    do {
+        if ((rc = stage_in(ctx, 1, codes, K * N, &dc)) != DLLM_OK) break;
+        if (w->per_tensor) {
+            ctx->h_params[0] = scales[0];
+            ctx->h_params[1] = zero_points[0];
+            w->tensor_scale = scales[0];
+            w->tensor_zp = zero_points[0];
+            cudaMemcpyAsync(ctx->d_params, ctx->h_params, 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            if ((rc = k_wparams_broadcast(ctx, ctx->d_params, N, w->d_scales, w->d_zps)) != DLLM_OK) break;
+        } else {
+            const size_t G = K / group;
+            cudaMemsetAsync(w->d_scales, 0, G * Npad * sizeof(float), ctx->stream);
+            cudaMemsetAsync(w->d_zps, 0, G * Npad * sizeof(float), ctx->stream);
+            cudaMemcpy2DAsync(w->d_scales, Npad * sizeof(float), scales, N * sizeof(float), N * sizeof(float), G,
+                              cudaMemcpyHostToDevice, ctx->stream);
+            cudaMemcpy2DAsync(w->d_zps, Npad * sizeof(float), zero_points, N * sizeof(float), N * sizeof(float), G,
+                              cudaMemcpyHostToDevice, ctx->stream);
+        }
+        if ((rc = k_wpack_from_codes(ctx, (const uint8_t *)dc, w)) != DLLM_OK) break;
+        if ((rc = qweight_set_bias(ctx, w, bias, false)) != DLLM_OK) break;
+        rc = sync(ctx);
+    } while (0);
+    if (rc != DLLM_OK) { dllm_qweight_destroy(w); return rc; }
+    *out = w;
+    return DLLM_OK;
+}
+
+int32_t dllm_qweight_export(dllm_ctx *ctx, const dllm_qweight *w, uint8_t *codes, float *scales, float *zero_points) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, w, DLLM_ERR_NULL, "null weight");
+    const size_t Npad = w->n_tiles * WL_TILE_N;
+    if (codes) {
+        void *dc;
+        DLLM_TRY(stage_out_buf(ctx, 1, w->K * w->N, &dc));
+        DLLM_TRY(k_wexport_codes(ctx, w, (uint8_t *)dc));
+        DLLM_TRY(copy_out(ctx, codes, dc, w->K * w->N));
+    }
+    const size_t G = w->per_tensor ? 1 : w->K / w->group;
+    if (w->per_tensor) {
+        if (scales) CUDA_TRY(ctx, cudaMemcpyAsync(scales, w->d_scales, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (zero_points) CUDA_TRY(ctx, cudaMemcpyAsync(zero_points, w->d_zps, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        if (scales) CUDA_TRY(ctx, cudaMemcpy2DAsync(scales, w->N * sizeof(float), w->d_scales, Npad * sizeof(float), w->N * sizeof(float), G, cudaMemcpyDeviceToHost, ctx->stream));
+        if (zero_points) CUDA_TRY(ctx, cudaMemcpy2DAsync(zero_points, w->N * sizeof(float), w->d_zps, Npad * sizeof(float), w->N * sizeof(float), G, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return sync(ctx);
+}
+
+int32_t dllm_qweight_info(const dllm_qweight *w, size_t *K, size_t *N, uint8_t *bits, size_t *group,
+                          size_t *packed_bytes) {
+    if (!w) return DLLM_ERR_NULL;
+    if (K) *K = w->K;
+    if (N) *N = w->N;
+    if (bits) *bits = (uint8_t)w->bits;
+    if (group) *group = w->per_tensor ? 0 : w->group;
+    if (packed_bytes) *packed_bytes = w->n_tiles * w->k_blocks * w->tile_bytes;
+    return DLLM_OK;
+}
+
+void dllm_qweight_destroy(dllm_qweight *w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    if (w->d_packed) cudaFree(w->d_packed);
+    if (w->d_scales) cudaFree(w->d_scales);
+    if (w->d_zps) cudaFree(w->d_zps);
+    if (w->d_bias) cudaFree(w->d_bias);
+    delete w;
+}
+
+// ==========================================================================================
+// quantized linear
+// ==========================================================================================
+static int resolve_path(const dllm_qweight *w, size_t M, int32_t path) {
+    if (path == DLLM_PATH_AUTO) return k_umma_supported(w, M) ? DLLM_PATH_UMMA : DLLM_PATH_SIMT;
+    return path;
+}
+
+int32_t dllm_qlinear_forward_dev(dllm_ctx *ctx, const dllm_qweight *w, const float *x_dev, size_t M, float *y_dev,
+                                 int32_t path) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, w, DLLM_ERR_NULL, "null weight");
+    ARG_CHECK(ctx, M == 0 || (x_dev && y_dev), DLLM_ERR_NULL, "null device pointer");
+    ARG_CHECK(ctx, path >= DLLM_PATH_AUTO && path <= DLLM_PATH_UMMA, DLLM_ERR_INVALID_PARAMS, "unknown path %d", path);
+    if (M == 0) return DLLM_OK;
+    const int p = resolve_path(w, M, path);
+    if (p == DLLM_PATH_SIMT) return k_qlinear_simt(ctx, w, x_dev, M, y_dev);
+    ARG_CHECK(ctx, k_umma_supported(w, M), DLLM_ERR_UNSUPPORTED, "tcgen05 path does not support this shape");
+    DLLM_TRY(ensure_buf(ctx, ctx->act[0], M * w->K * 2));
+    DLLM_TRY(k_f32_to_bf16(ctx, x_dev, M * w->K, ctx->act[0].p));
+    return k_qlinear_umma(ctx, w, ctx->act[0].p, M, y_dev, nullptr);
+}
+
+int32_t dllm_qlinear_forward(dllm_ctx *ctx, const dllm_qweight *w, const float *x, size_t M, float *y, int32_t path) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, w, DLLM_ERR_NULL, "null weight");
+    ARG_CHECK(ctx, M == 0 || (x && y), DLLM_ERR_NULL, "null pointer");
+    if (M == 0) return DLLM_OK;
+    void *dx, *dy;
+    DLLM_TRY(stage_in(ctx, 4, x, M * w->K * sizeof(float), &dx));
+    DLLM_TRY(stage_out_buf(ctx, 5, M * w->N * sizeof(float), &dy));
+    DLLM_TRY(dllm_qlinear_forward_dev(ctx, w, (const float *)dx, M, (float *)dy, path));
+    DLLM_TRY(copy_out(ctx, y, dy, M * w->N * sizeof(float)));
+    return sync(ctx);
+}
+
+int32_t dllm_dequant_matmul(dllm_ctx *ctx, const uint8_t *codes, const float *scales, const float *zero_points,
+                            size_t K, size_t N, uint8_t bits, size_t group, const float *bias, const float *x,
+                            size_t M, float *y, int32_t path) {
+    dllm_qweight *w = nullptr;
+    DLLM_TRY(dllm_qweight_from_codes(ctx, codes, scales, zero_points, K, N, bits, group, bias, &w));
+    int32_t rc = dllm_qlinear_forward(ctx, w, x, M, y, path);
+    dllm_qweight_destroy(w);
+    return rc;
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// model: stack of quantized linears + schedule (diffuse-llm-rs/src/lib.rs:748-813, 554-593)
+// ==========================================================================================
+struct dllm_model {
+    size_t hidden = 0;
+    std::vector<dllm_qweight *> layers;
+    std::vector<int> parallel;   // 0 replicated, 1 column-parallel, 2 row-parallel
+    size_t T = 0;
+    std::vector<float> betas, alpha_bars;
+    float *d_coef_table[2] = {nullptr, nullptr};   // [T][4] for guard_t0 = 0 / 1 (c1, c2, std, degenerate)
+    int *d_rowmap = nullptr;     // per-row timestep for the host-pointer p_sample
+    size_t rowmap_cap = 0;
+    int device = 0;
+};
+
+static int32_t beta_schedule_host(int32_t kind, size_t T, float beta_start, float beta_end, float *betas) {
+    if (T == 0 || !betas) return DLLM_ERR_INVALID_PARAMS;
+    const float PI_F = 3.14159265358979323846f;
+    for (size_t t = 0; t < T; ++t) {
+        // volatile temporaries: one f32 rounding per reference operation, whatever the host compiler flags
+        switch (kind) {
+            case DLLM_BETA_LINEAR: {   // lib.rs:560-563
+                volatile float d = beta_end - beta_start;
+                volatile float p = d * (float)t;
+                volatile float q = p / (float)(T - 1);
+                betas[t] = beta_start + q;
+                break;
+            }
+            case DLLM_BETA_QUADRATIC: {   // lib.rs:569-573
+                volatile float tn = (float)t / (float)(T - 1);
+                volatile float d = beta_end - beta_start;
+                volatile float p = d * tn;
+                volatile float q = p * tn;
+                betas[t] = beta_start + q;
+                break;
+            }
+            case DLLM_BETA_COSINE: {   // lib.rs:578-587
+                const float s = 0.008f;
+                volatile float tn = (float)t / (float)T;
+                volatile float a = tn + s;
+                volatile float b = a / (1.0f + s);
+                volatile float c = b * PI_F;
+                volatile float d = c / 2.0f;
+                volatile float ct = cosf(d);
+                volatile float ft = ct * ct;
+                volatile float a0 = s / (1.0f + s);
+                volatile float c0 = a0 * PI_F;
+                volatile float d0 = c0 / 2.0f;
+                volatile float cz = cosf(d0);
+                volatile float f0 = cz * cz;
+                volatile float r = ft / f0;
+                betas[t] = fminf(1.0f - r, 0.999f);
+                break;
+            }
+            default: return DLLM_ERR_INVALID_PARAMS;
+        }
+    }
+    return DLLM_OK;
+}
+
+// coefficients of p_sample for timestep t: lib.rs:1160-1192, 1208-1209 (alphas read as alpha_t)
+static void p_sample_coeffs_host(const dllm_model *m, size_t t, int guard_t0, float out[4]) {
+    const size_t ti = t < m->T - 1 ? t : m->T - 1;
+    const float ab_t = m->alpha_bars[ti];
+    const float beta_t = m->betas[ti];
+    volatile float alpha_t = 1.0f - beta_t;
+    const float ab_prev = ti > 0 ? m->alpha_bars[ti - 1] : 1.0f;
+    volatile float one_m_abt = 1.0f - ab_t;
+    volatile float one_m_abp = 1.0f - ab_prev;
+    volatile float n1 = sqrtf(ab_prev) * beta_t;
+    volatile float n2 = sqrtf(alpha_t) * one_m_abp;
+    volatile float c1 = n1 / one_m_abt, c2 = n2 / one_m_abt;
+    volatile float ratio = one_m_abp / one_m_abt;
+    volatile float var = ratio * beta_t;
+    out[0] = c1; out[1] = c2; out[2] = sqrtf(var);
+    out[3] = (guard_t0 && one_m_abt == 0.0f) ? 1.0f : 0.0f;
+}
+
+// tensor-parallel hooks (tp.cu)
+int32_t tp_allreduce(dllm_ctx *ctx, float *buf, size_t n);
+int32_t tp_allgather_cols(dllm_ctx *ctx, const float *in, size_t M, size_t n_local, float *out);
+
+static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x_dev, size_t tokens, float *out_dev,
+                                    int32_t path) {
+    const size_t L = m->layers.size();
+    // widest activation of the stack
+    size_t maxw = m->hidden;
+    for (auto *w : m->layers) { if (w->N > maxw) maxw = w->N; if (w->K > maxw) maxw = w->K; }
+    bool all_umma = path != DLLM_PATH_SIMT;
+    for (auto *w : m->layers) all_umma = all_umma && k_umma_supported(w, tokens);
+    bool any_parallel = false;
+    for (int p : m->parallel) any_parallel = any_parallel || p != 0;
+    if (path == DLLM_PATH_UMMA && !all_umma) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "tcgen05 path does not support this stack");
+
+    if (all_umma && !any_parallel) {
+        // bf16 activations between layers; the last layer writes f32
+        DLLM_TRY(ensure_buf(ctx, ctx->act[0], tokens * maxw * 2));
+        DLLM_TRY(ensure_buf(ctx, ctx->act[1], tokens * maxw * 2));
+        DLLM_TRY(k_f32_to_bf16(ctx, x_dev, tokens * m->layers[0]->K, ctx->act[0].p));
+        void *cur = ctx->act[0].p, *nxt = ctx->act[1].p;
+        for (size_t l = 0; l < L; ++l) {
+            const bool last = l + 1 == L;
+            DLLM_TRY(k_qlinear_umma(ctx, m->layers[l], cur, tokens, last ? out_dev : nullptr, last ? nullptr : nxt));
+            void *t = cur; cur = nxt; nxt = t;
+        }
+        return DLLM_OK;
+    }
+    // f32 activations between layers (SIMT path, or tensor-parallel stacks with NCCL at the boundaries)
+    DLLM_TRY(ensure_buf(ctx, ctx->act[0], tokens * maxw * 4 * (size_t)ctx->tp_world));
+    DLLM_TRY(ensure_buf(ctx, ctx->act[1], tokens * maxw * 4 * (size_t)ctx->tp_world));
+    DLLM_TRY(ensure_buf(ctx, ctx->act[2], tokens * maxw * 2));
+    const float *cur = x_dev;
+    float *bufs[2] = {(float *)ctx->act[0].p, (float *)ctx->act[1].p};
+    int flip = 0;
+    for (size_t l = 0; l < L; ++l) {
+        const bool last = l + 1 == L;
+        dllm_qweight *w = m->layers[l];
+        const int par = m->parallel[l];
+        float *dst = (last && par == 0) ? out_dev : bufs[flip];
+        const bool umma = path != DLLM_PATH_SIMT && k_umma_supported(w, tokens);
+        if (umma) {
+            DLLM_TRY(k_f32_to_bf16(ctx, cur, tokens * w->K, ctx->act[2].p));
+            DLLM_TRY(k_qlinear_umma(ctx, w, ctx->act[2].p, tokens, dst, nullptr));
+        } else {
+            DLLM_TRY(k_qlinear_simt(ctx, w, cur, tokens, dst));
+        }
+        if (par == 2) {           // row-parallel: partial sums over the K shards -> all-reduce
+            DLLM_TRY(tp_allreduce(ctx, dst, tokens * w->N));
+            if (last) { CUDA_TRY(ctx, cudaMemcpyAsync(out_dev, dst, tokens * w->N * 4, cudaMemcpyDeviceToDevice, ctx->stream)); }
+        } else if (par == 1 && (last || m->parallel[l + 1] != 2)) {
+            // column-parallel whose consumer needs the full width: all-gather the column shards
+            float *full = last ? out_dev : bufs[flip ^ 1];
+            DLLM_TRY(tp_allgather_cols(ctx, dst, tokens, w->N, full));
+            dst = full;
+            if (!last) flip ^= 1;
+        }
+        cur = dst;
+        flip ^= 1;
+    }
+    return DLLM_OK;
+}
+
+extern "C" {
+
+int32_t dllm_beta_schedule(int32_t kind, size_t T, float beta_start, float beta_end, float *betas) {
+    return beta_schedule_host(kind, T, beta_start, beta_end, betas);
+}
+
+uint8_t dllm_progressive_bits(size_t num_steps, size_t t, uint8_t decode_bits, uint8_t min_decode_bits,
+                              int32_t *is_prefill) {
+    if (is_prefill) *is_prefill = t > num_steps / 2;                       // lib.rs:886
+    volatile float progress = (float)(num_steps - t) / (float)(num_steps / 2);   // :895
+    volatile float a = (float)decode_bits * (1.0f - progress);
+    volatile float b = (float)min_decode_bits * progress;
+    volatile float target = a + b;                                         // :896-897
+    float v = target;
+    if (v != v || v <= 0.0f) return 0;
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+
+int32_t dllm_model_create(dllm_ctx *ctx, size_t hidden, dllm_qweight *const *layers, size_t n_layers,
+                          size_t num_timesteps, int32_t beta_kind, float beta_start, float beta_end,
+                          dllm_model **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, out && layers, DLLM_ERR_NULL, "null pointer");
+    *out = nullptr;
+    ARG_CHECK(ctx, n_layers > 0 && hidden > 0, DLLM_ERR_INVALID_PARAMS, "empty model");
+    ARG_CHECK(ctx, num_timesteps > 0, DLLM_ERR_INVALID_PARAMS, "num_timesteps must be > 0 (lib.rs:547 panics)");
+    for (size_t l = 0; l < n_layers; ++l) ARG_CHECK(ctx, layers[l], DLLM_ERR_NULL, "layer %zu is null", l);
+    ARG_CHECK(ctx, layers[0]->K == hidden, DLLM_ERR_SHAPE, "first layer K=%zu != hidden=%zu", layers[0]->K, hidden);
+    dllm_model *m = new (std::nothrow) dllm_model();
+    if (!m) return DLLM_ERR_OOM;
+    m->hidden = hidden;
+    m->layers.assign(layers, layers + n_layers);
+    m->parallel.assign(n_layers, 0);
+    m->T = num_timesteps;
+    m->device = ctx->device;
+    m->betas.resize(num_timesteps);
+    int32_t rc = beta_schedule_host(beta_kind, num_timesteps, beta_start, beta_end, m->betas.data());
+    if (rc != DLLM_OK) { delete m; DLLM_FAIL(ctx, rc, "unknown beta schedule %d", beta_kind); }
+    m->alpha_bars.resize(num_timesteps);
+    m->alpha_bars[0] = 1.0f;                                              // lib.rs:1162-1165
+    for (size_t i = 1; i < num_timesteps; ++i) {
+        volatile float a = 1.0f - m->betas[i - 1];
+        volatile float p = m->alpha_bars[i - 1] * a;
+        m->alpha_bars[i] = p;
+    }
+    // coefficient tables for every timestep, resident on the device: no host work per step
+    std::vector<float> tab(num_timesteps * 4);
+    for (int g = 0; g < 2; ++g) {
+        for (size_t t = 0; t < num_timesteps; ++t) p_sample_coeffs_host(m, t, g, tab.data() + 4 * t);
+        if (cudaMalloc(&m->d_coef_table[g], tab.size() * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(m->d_coef_table[g], tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError();
+            dllm_model_destroy(m);
+            DLLM_FAIL(ctx, DLLM_ERR_CUDA, "coefficient table upload failed");
+        }
+    }
+    *out = m;
+    return DLLM_OK;
+}
+
+void dllm_model_destroy(dllm_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (int g = 0; g < 2; ++g) if (m->d_coef_table[g]) cudaFree(m->d_coef_table[g]);
+    if (m->d_rowmap) cudaFree(m->d_rowmap);
+    delete m;   // layers are owned by the caller
+}
+
+int32_t dllm_model_set_parallel(dllm_ctx *ctx, dllm_model *m, const int32_t *parallel, size_t n_layers) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m && parallel, DLLM_ERR_NULL, "null pointer");
+    ARG_CHECK(ctx, n_layers == m->layers.size(), DLLM_ERR_SHAPE, "expected %zu entries", m->layers.size());
+    for (size_t l = 0; l < n_layers; ++l) {
+        ARG_CHECK(ctx, parallel[l] >= 0 && parallel[l] <= 2, DLLM_ERR_INVALID_PARAMS, "parallel[%zu]=%d", l, parallel[l]);
+        m->parallel[l] = parallel[l];
+    }
+    return DLLM_OK;
+}
+
+int32_t dllm_model_forward_dev(dllm_ctx *ctx, dllm_model *m, const float *x_dev, size_t batch, size_t feat,
+                               float *noise_pred_dev, int32_t path) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    ARG_CHECK(ctx, feat % m->hidden == 0, DLLM_ERR_SHAPE, "feature dim %zu is not a multiple of hidden %zu", feat, m->hidden);
+    if (batch * feat == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_dev && noise_pred_dev, DLLM_ERR_NULL, "null device pointer");
+    return model_forward_tokens(ctx, m, x_dev, batch * (feat / m->hidden), noise_pred_dev, path);
+}
+
+int32_t dllm_model_forward(dllm_ctx *ctx, dllm_model *m, const float *x, const size_t *t, size_t batch, size_t feat,
+                           float *noise_pred, int32_t path) {
+    CTX_CHECK(ctx);
+    (void)t;   // SimpleDiffusionModel::forward ignores the timestep (lib.rs:806 `_t`)
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    const size_t n = batch * feat;
+    ARG_CHECK(ctx, n == 0 || (x && noise_pred), DLLM_ERR_NULL, "null pointer");
+    if (n == 0) return DLLM_OK;
+    void *dx, *dy;
+    DLLM_TRY(stage_in(ctx, 4, x, n * sizeof(float), &dx));
+    DLLM_TRY(stage_out_buf(ctx, 5, n * sizeof(float), &dy));
+    DLLM_TRY(dllm_model_forward_dev(ctx, m, (const float *)dx, batch, feat, (float *)dy, path));
+    DLLM_TRY(copy_out(ctx, noise_pred, dy, n * sizeof(float)));
+    return sync(ctx);
+}
+
+static int32_t upload_rowmap(dllm_ctx *ctx, dllm_model *m, const size_t *t, size_t batch) {
+    if (batch > m->rowmap_cap) {
+        if (m->d_rowmap) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(m->d_rowmap); m->d_rowmap = nullptr; }
+        CUDA_TRY(ctx, cudaMalloc(&m->d_rowmap, batch * sizeof(int)));
+        m->rowmap_cap = batch;
+    }
+    std::vector<int> rows(batch);
+    for (size_t b = 0; b < batch; ++b) rows[b] = (int)(t[b] < m->T - 1 ? t[b] : m->T - 1);   // lib.rs:1174 clamp
+    CUDA_TRY(ctx, cudaMemcpyAsync(m->d_rowmap, rows.data(), batch * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // `rows` is a stack temporary
+    return DLLM_OK;
+}
+
+int32_t dllm_p_sample(dllm_ctx *ctx, dllm_model *m, const float *x_t, const float *noise_pred, const float *z,
+                      const size_t *t, size_t batch, size_t feat, int32_t guard_t0, float *x_prev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    const size_t n = batch * feat;
+    if (n == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_t && noise_pred && t && x_prev, DLLM_ERR_NULL, "null pointer");
+    const bool add_noise = z != nullptr && t[0] > 0;      // lib.rs:1199-1205
+    void *dx, *dp, *dz = nullptr, *dout;
+    DLLM_TRY(stage_in(ctx, 4, x_t, n * sizeof(float), &dx));
+    DLLM_TRY(stage_in(ctx, 5, noise_pred, n * sizeof(float), &dp));
+    if (add_noise) DLLM_TRY(stage_in(ctx, 6, z, n * sizeof(float), &dz));
+    DLLM_TRY(stage_out_buf(ctx, 7, n * sizeof(float), &dout));
+    DLLM_TRY(upload_rowmap(ctx, m, t, batch));
+    DLLM_TRY(k_p_sample(ctx, (const float *)dx, (const float *)dp, (const float *)dz, m->d_coef_table[guard_t0 ? 1 : 0],
+                        m->d_rowmap, 0, batch, feat, (float *)dout));
+    DLLM_TRY(copy_out(ctx, x_prev, dout, n * sizeof(float)));
+    return sync(ctx);
+}
+
+int32_t dllm_denoise_step_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, const float *z_dev, size_t t, size_t batch,
+                              size_t feat, int32_t guard_t0, int32_t path) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    const size_t n = batch * feat;
+    if (n == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_dev, DLLM_ERR_NULL, "null device pointer");
+    void *dpred;
+    DLLM_TRY(stage_out_buf(ctx, 7, n * sizeof(float), &dpred));
+    DLLM_TRY(dllm_model_forward_dev(ctx, m, x_dev, batch, feat, (float *)dpred, path));   // lib.rs:924
+    // p_sample in place: every element is read once before it is written (lib.rs:925)
+    const int row = (int)(t < m->T - 1 ? t : m->T - 1);
+    return k_p_sample(ctx, x_dev, (const float *)dpred, t > 0 ? z_dev : nullptr, m->d_coef_table[guard_t0 ? 1 : 0],
+                      nullptr, row, batch, feat, x_dev);
+}
+
+int32_t dllm_sample(dllm_ctx *ctx, dllm_model *m, const float *x0, const float *noises, size_t batch, size_t feat,
+                    size_t num_steps, int32_t guard_t0, int32_t path, float *x_out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    const size_t n = batch * feat;
+    if (n == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x0 && x_out, DLLM_ERR_NULL, "null pointer");
+    void *dx, *dz = nullptr;
+    DLLM_TRY(stage_in(ctx, 4, x0, n * sizeof(float), &dx));          // lib.rs:875-878 (noise injected)
+    if (noises) DLLM_TRY(stage_out_buf(ctx, 6, n * sizeof(float), &dz));
+    for (size_t t = num_steps; t-- > 0;) {                           // lib.rs:881 `(0..num_steps).rev()`
+        if (noises && t > 0)
+            CUDA_TRY(ctx, cudaMemcpyAsync(dz, noises + t * n, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        DLLM_TRY(dllm_denoise_step_dev(ctx, m, (float *)dx, noises ? (const float *)dz : nullptr, t, batch, feat,
+                                       guard_t0, path));
+    }
+    DLLM_TRY(copy_out(ctx, x_out, dx, n * sizeof(float)));
+    return sync(ctx);
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// KV cache entry
+// ==========================================================================================
+struct dllm_kv {
+    size_t L = 0, S = 0, H = 0;
+    int bits = 8, scheme = DLLM_KV_TENSOR_B;
+    bool packed = false;
+    size_t code_bytes = 0;            // per tensor
+    uint8_t *d_codes[2] = {nullptr, nullptr};
+    float *d_params[2] = {nullptr, nullptr};   // B: {scale, zp, min, max}
+    float *d_rows[2] = {nullptr, nullptr};     // D: [rows] scales then [rows] zps
+    float c_scale = 0.f;
+    int device = 0;
+};
+
+static int32_t kv_quantize_one(dllm_ctx *ctx, dllm_kv *kv, int which, const float *src_dev) {
+    const size_t rows = kv->L * kv->S, n = rows * kv->H;
+    const int pack = kv->packed ? kv->bits : 0;
+    switch (kv->scheme) {
+        case DLLM_KV_TENSOR_B:
+            DLLM_TRY(k_minmax(ctx, src_dev, n, kv->bits, kv->d_params[which]));
+            return k_encode_b(ctx, src_dev, n, kv->bits, pack, kv->d_params[which], 0.f, 0.f, kv->d_codes[which]);
+        case DLLM_KV_ROW_D:
+            return k_quant_d_rows(ctx, src_dev, rows, kv->H, nullptr, 1, kv->bits, pack, kv->d_codes[which],
+                                  kv->d_rows[which], kv->d_rows[which] + rows);
+        case DLLM_KV_FIXED_C:
+            return k_encode_cd(ctx, src_dev, n, kv->bits, pack, kv->c_scale, 0.0f, kv->d_codes[which]);
+    }
+    return DLLM_ERR_INVALID_PARAMS;
+}
+
+static int32_t kv_dequantize_one(dllm_ctx *ctx, const dllm_kv *kv, int which, float *dst_dev) {
+    const size_t rows = kv->L * kv->S, n = rows * kv->H;
+    const int pack = kv->packed ? kv->bits : 0;
+    switch (kv->scheme) {
+        case DLLM_KV_TENSOR_B:
+            return k_decode_ab(ctx, kv->d_codes[which], n, pack, kv->d_params[which], 0.f, 0.f, dst_dev);
+        case DLLM_KV_ROW_D:
+            return k_decode_cd(ctx, kv->d_codes[which], n, pack, 0.f, 0.f, kv->d_rows[which], kv->d_rows[which] + rows, kv->H, dst_dev);
+        case DLLM_KV_FIXED_C:
+            return k_decode_cd(ctx, kv->d_codes[which], n, pack, kv->c_scale, 0.0f, nullptr, nullptr, 0, dst_dev);
+    }
+    return DLLM_ERR_INVALID_PARAMS;
+}
+
+extern "C" {
+
+void dllm_kv_destroy(dllm_kv *kv) {
+    if (!kv) return;
+    cudaSetDevice(kv->device);
+    for (int i = 0; i < 2; ++i) {
+        if (kv->d_codes[i]) cudaFree(kv->d_codes[i]);
+        if (kv->d_params[i]) cudaFree(kv->d_params[i]);
+        if (kv->d_rows[i]) cudaFree(kv->d_rows[i]);
+    }
+    delete kv;
+}
+
+int32_t dllm_kv_update_dev(dllm_ctx *ctx, dllm_kv *kv, const float *keys_dev, const float *values_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kv, DLLM_ERR_NULL, "null kv entry");
+    if (kv->L * kv->S * kv->H == 0) return DLLM_OK;
+    ARG_CHECK(ctx, keys_dev && values_dev, DLLM_ERR_NULL, "null device pointer");
+    DLLM_TRY(kv_quantize_one(ctx, kv, 0, keys_dev));
+    return kv_quantize_one(ctx, kv, 1, values_dev);
+}
+
+int32_t dllm_kv_quantize_dev(dllm_ctx *ctx, const float *keys_dev, const float *values_dev, size_t layers, size_t seq,
+                             size_t hidden, uint8_t bits, int32_t scheme, dllm_kv **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, out, DLLM_ERR_NULL, "null out pointer");
+    *out = nullptr;
+    ARG_CHECK(ctx, scheme >= DLLM_KV_TENSOR_B && scheme <= DLLM_KV_FIXED_C, DLLM_ERR_INVALID_PARAMS, "unknown scheme %d", scheme);
+    if (scheme == DLLM_KV_TENSOR_B)
+        ARG_CHECK(ctx, bits >= 1 && bits <= 8, DLLM_ERR_INVALID_PARAMS, "Bits must be between 1 and 8 (got %d)", (int)bits);
+    ARG_CHECK(ctx, bits <= 30, DLLM_ERR_INVALID_PARAMS, "bits %d overflows", (int)bits);
+    dllm_kv *kv = new (std::nothrow) dllm_kv();
+    if (!kv) return DLLM_ERR_OOM;
+    kv->L = layers; kv->S = seq; kv->H = hidden; kv->bits = bits; kv->scheme = scheme; kv->device = ctx->device;
+    const size_t rows = layers * seq, n = rows * hidden;
+    kv->packed = pack_width_ok(bits) && bits != 8 && hidden % 8 == 0 && (hidden * bits / 8) % 4 == 0 &&
+                 (scheme != DLLM_KV_ROW_D || hidden <= 16384);
+    kv->code_bytes = kv->packed ? n * bits / 8 : n;
+    kv->c_scale = dllm_bitquantizer_scale(bits);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMalloc(&kv->d_codes[i], kv->code_bytes ? kv->code_bytes : 16);
+        if (e == cudaSuccess) e = cudaMalloc(&kv->d_params[i], 4 * sizeof(float));
+        if (e == cudaSuccess && scheme == DLLM_KV_ROW_D) e = cudaMalloc(&kv->d_rows[i], (2 * rows + 4) * sizeof(float));
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); dllm_kv_destroy(kv); DLLM_FAIL(ctx, DLLM_ERR_OOM, "cudaMalloc failed for the KV entry"); }
+    int32_t rc = dllm_kv_update_dev(ctx, kv, keys_dev, values_dev);
+    if (rc != DLLM_OK) { dllm_kv_destroy(kv); return rc; }
+    *out = kv;
+    return DLLM_OK;
+}
+
+int32_t dllm_kv_quantize(dllm_ctx *ctx, const float *keys, const float *values, size_t layers, size_t seq,
+                         size_t hidden, uint8_t bits, int32_t scheme, dllm_kv **out) {
+    CTX_CHECK(ctx);
+    const size_t n = layers * seq * hidden;
+    ARG_CHECK(ctx, n == 0 || (keys && values), DLLM_ERR_NULL, "null pointer");
+    void *dk, *dv;
+    DLLM_TRY(stage_in(ctx, 4, keys, n * sizeof(float), &dk));
+    DLLM_TRY(stage_in(ctx, 5, values, n * sizeof(float), &dv));
+    DLLM_TRY(dllm_kv_quantize_dev(ctx, (const float *)dk, (const float *)dv, layers, seq, hidden, bits, scheme, out));
+    return sync(ctx);
+}
+
+int32_t dllm_kv_dequantize_dev(dllm_ctx *ctx, const dllm_kv *kv, float *keys_dev, float *values_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kv, DLLM_ERR_NULL, "null kv entry");
+    if (kv->L * kv->S * kv->H == 0) return DLLM_OK;
+    if (keys_dev) DLLM_TRY(kv_dequantize_one(ctx, kv, 0, keys_dev));
+    if (values_dev) DLLM_TRY(kv_dequantize_one(ctx, kv, 1, values_dev));
+    return DLLM_OK;
+}
+
+int32_t dllm_kv_dequantize(dllm_ctx *ctx, const dllm_kv *kv, float *keys, float *values) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kv, DLLM_ERR_NULL, "null kv entry");
+    const size_t n = kv->L * kv->S * kv->H;
+    if (n == 0) return DLLM_OK;
+    void *dk, *dv;
+    DLLM_TRY(stage_out_buf(ctx, 4, n * sizeof(float), &dk));
+    DLLM_TRY(stage_out_buf(ctx, 5, n * sizeof(float), &dv));
+    DLLM_TRY(dllm_kv_dequantize_dev(ctx, kv, keys ? (float *)dk : nullptr, values ? (float *)dv : nullptr));
+    if (keys) DLLM_TRY(copy_out(ctx, keys, dk, n * sizeof(float)));
+    if (values) DLLM_TRY(copy_out(ctx, values, dv, n * sizeof(float)));
+    return sync(ctx);
+}
+
+int32_t dllm_kv_export(dllm_ctx *ctx, const dllm_kv *kv, uint8_t *key_codes, uint8_t *value_codes, float *key_scales,
+                       float *key_zps, float *value_scales, float *value_zps) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kv, DLLM_ERR_NULL, "null kv entry");
+    const size_t rows = kv->L * kv->S, n = rows * kv->H;
+    uint8_t *codes[2] = {key_codes, value_codes};
+    float *sc[2] = {key_scales, value_scales}, *zp[2] = {key_zps, value_zps};
+    for (int i = 0; i < 2; ++i) {
+        if (codes[i] && n) {
+            if (kv->packed) {
+                void *du;
+                DLLM_TRY(stage_out_buf(ctx, 1, n, &du));
+                DLLM_TRY(k_unpack(ctx, kv->d_codes[i], n, kv->bits, (uint8_t *)du));
+                DLLM_TRY(copy_out(ctx, codes[i], du, n));
+                DLLM_TRY(sync(ctx));
+            } else {
+                DLLM_TRY(copy_out(ctx, codes[i], kv->d_codes[i], n));
+            }
+        }
+        if (kv->scheme == DLLM_KV_TENSOR_B) {
+            DLLM_TRY(copy_out(ctx, ctx->h_params, kv->d_params[i], 4 * sizeof(float)));
+            DLLM_TRY(sync(ctx));
+            if (sc[i]) sc[i][0] = ctx->h_params[0];
+            if (zp[i]) zp[i][0] = ctx->h_params[1];
+        } else if (kv->scheme == DLLM_KV_ROW_D) {
+            if (sc[i]) DLLM_TRY(copy_out(ctx, sc[i], kv->d_rows[i], rows * sizeof(float)));
+            if (zp[i]) DLLM_TRY(copy_out(ctx, zp[i], kv->d_rows[i] + rows, rows * sizeof(float)));
+        } else {
+            if (sc[i]) sc[i][0] = kv->c_scale;
+            if (zp[i]) zp[i][0] = 0.0f;
+        }
+    }
+    return sync(ctx);
+}
+
+size_t dllm_kv_memory_usage(const dllm_kv *kv) {
+    if (!kv) return 0;
+    const size_t len = kv->L * kv->S * kv->H;                 // quantized.keys.data.len()
+    return 2 * ((len * (size_t)kv->bits + 7) / 8);           // lib.rs:284-285 for keys + values
+}
+
+}  // extern "C"

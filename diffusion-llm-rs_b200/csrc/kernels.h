@@ -1,0 +1,56 @@
+// kernels.h — host launchers of the CUDA kernels (internal; the public surface is include/dllm_b200.h)
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+struct dllm_ctx;
+struct dllm_qweight;
+
+// ---- quant_kernels.cu ----
+// out_dev[4] = {scale_B, zp_B, min, max}; bits == 0 computes min/max only
+int32_t k_minmax(dllm_ctx *ctx, const float *x_dev, size_t n, int bits, float *out_dev);
+// pack: 0 = one code per u8; 1/2/4/8 = bit-packed
+int32_t k_encode_b(dllm_ctx *ctx, const float *x_dev, size_t n, int bits, int pack, const float *params_dev,
+                   float scale, float zp, uint8_t *out_dev);
+int32_t k_encode_a(dllm_ctx *ctx, const float *x_dev, size_t n, float scale, float zp, float lo, float hi,
+                   uint8_t *out_dev);
+int32_t k_encode_cd(dllm_ctx *ctx, const float *x_dev, size_t n, int bits, int pack, float scale, float zp,
+                    uint8_t *out_dev);
+int32_t k_decode_ab(dllm_ctx *ctx, const uint8_t *in_dev, size_t n, int pack, const float *params_dev,
+                    float scale, float zp, float *out_dev);
+int32_t k_decode_cd(dllm_ctx *ctx, const uint8_t *in_dev, size_t n, int pack, float scale, float zp,
+                    const float *row_scales, const float *row_zps, size_t dim, float *out_dev);
+int32_t k_pack(dllm_ctx *ctx, const uint8_t *codes_dev, size_t n, int bits, uint8_t *packed_dev);
+int32_t k_unpack(dllm_ctx *ctx, const uint8_t *packed_dev, size_t n, int bits, uint8_t *codes_dev);
+int32_t k_quant_d_rows(dllm_ctx *ctx, const float *x_dev, size_t rows, size_t dim, const uint8_t *bits_tab_dev,
+                       int nbits, int uniform_bits, int pack, uint8_t *out_dev, float *scales_dev, float *zps_dev);
+
+// ---- weight_kernels.cu ----
+// per-(group, column) quantizer-B parameters of W[K,N] (row-major f32)
+int32_t k_wparams_grouped(dllm_ctx *ctx, const float *w_dev, size_t K, size_t N, size_t group, int bits,
+                          float *scales_dev, float *zps_dev);
+// fill scales/zps [1, N] from the per-tensor params {scale, zp} on the device
+int32_t k_wparams_broadcast(dllm_ctx *ctx, const float *params_dev, size_t N, float *scales_dev, float *zps_dev);
+// quantize (from f32) or adopt (from u8 codes) into the tile-major packed layout of qw
+int32_t k_wpack_from_f32(dllm_ctx *ctx, const float *w_dev, dllm_qweight *qw);
+int32_t k_wpack_from_codes(dllm_ctx *ctx, const uint8_t *codes_dev, dllm_qweight *qw);
+int32_t k_wexport_codes(dllm_ctx *ctx, const dllm_qweight *qw, uint8_t *codes_dev);
+
+// ---- gemv_simt.cu ----
+// y[M,N] = x[M,K] · dequant(W) + b, f32 CUDA cores, any M (tiled by 8 rows)
+int32_t k_qlinear_simt(dllm_ctx *ctx, const dllm_qweight *qw, const float *x_dev, size_t M, float *y_dev);
+
+// ---- umma_gemm.cu ----
+// tcgen05 path.  x_bf16_dev: [M, K] bf16 row-major.  out_f32 / out_bf16: either may be null.
+int32_t k_qlinear_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M,
+                       float *y_f32_dev, void *y_bf16_dev);
+bool k_umma_supported(const dllm_qweight *qw, size_t M);
+
+// ---- sample_kernels.cu ----
+int32_t k_f32_to_bf16(dllm_ctx *ctx, const float *in_dev, size_t n, void *out_bf16_dev);
+int32_t k_bf16_to_f32(dllm_ctx *ctx, const void *in_bf16_dev, size_t n, float *out_dev);
+// x_prev = (c1*x + c2*pred) + sd*z per row (coefficients per batch row on the device)
+// coefficient table rows are {c1, c2, std, degenerate}; row of batch element b = rowmap ? rowmap[b] : row
+int32_t k_p_sample(dllm_ctx *ctx, const float *x_dev, const float *pred_dev, const float *z_dev,
+                   const float *coef_table_dev, const int *rowmap_dev, int row, size_t batch, size_t feat,
+                   float *out_dev);

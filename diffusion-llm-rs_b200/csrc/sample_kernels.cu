@@ -1,0 +1,79 @@
+// sample_kernels.cu — elementwise kernels of the denoising step: activation casts for the
+// tcgen05 path and the fused p_sample update (diffuse-llm-rs/src/lib.rs:1152-1215).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+f32_to_bf16_kernel(const float *__restrict__ in, size_t n, __nv_bfloat16 *__restrict__ out) {
+    const size_t n4 = n >> 2;
+    const float4 *i4 = reinterpret_cast<const float4 *>(in);
+    uint2 *o4 = reinterpret_cast<uint2 *>(out);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = ldg_stream_f4(i4 + i);
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        o4[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (size_t j = n4 << 2; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+}
+
+__global__ void __launch_bounds__(256)
+bf16_to_f32_kernel(const __nv_bfloat16 *__restrict__ in, size_t n, float *__restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = __bfloat162float(in[i]);
+}
+
+// x_prev = (c1 * x_t + c2 * noise_pred) + std * z       lib.rs:1195-1196, 1212
+// two products and an add, then a product and an add: no FMA contraction (Rust does not contract)
+__global__ void __launch_bounds__(256)
+p_sample_kernel(const float *x /* may alias out */, const float *__restrict__ pred, const float *__restrict__ z,
+                const float *__restrict__ coef_table, const int *__restrict__ rowmap, int row, size_t batch,
+                size_t feat, float *out) {
+    const size_t total = batch * feat;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / feat;
+        const float *coef = coef_table + 4 * (size_t)(rowmap ? __ldg(rowmap + b) : row);
+        const float c1 = __ldg(coef), c2 = __ldg(coef + 1), sd = __ldg(coef + 2);
+        const float degenerate = __ldg(coef + 3);
+        const float xv = x[i];
+        if (degenerate != 0.f) { out[i] = xv; continue; }
+        const float mean = __fadd_rn(__fmul_rn(c1, xv), __fmul_rn(c2, pred[i]));
+        const float nz = z ? z[i] : 0.f;
+        out[i] = __fadd_rn(mean, __fmul_rn(sd, nz));
+    }
+}
+
+inline int grid1d(const dllm_ctx *ctx, size_t items) {
+    size_t b = (items + 255) / 256, cap = (size_t)ctx->sm_count * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+int32_t k_f32_to_bf16(dllm_ctx *ctx, const float *in_dev, size_t n, void *out_bf16_dev) {
+    if (n == 0) return DLLM_OK;
+    if (!aligned16(in_dev) || (reinterpret_cast<uintptr_t>(out_bf16_dev) & 7u))
+        DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "f32->bf16 cast needs aligned device buffers");
+    f32_to_bf16_kernel<<<grid1d(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(in_dev, n, (__nv_bfloat16 *)out_bf16_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
+
+int32_t k_bf16_to_f32(dllm_ctx *ctx, const void *in_bf16_dev, size_t n, float *out_dev) {
+    if (n == 0) return DLLM_OK;
+    bf16_to_f32_kernel<<<grid1d(ctx, n), 256, 0, ctx->stream>>>((const __nv_bfloat16 *)in_bf16_dev, n, out_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
+
+int32_t k_p_sample(dllm_ctx *ctx, const float *x_dev, const float *pred_dev, const float *z_dev,
+                   const float *coef_table_dev, const int *rowmap_dev, int row, size_t batch, size_t feat,
+                   float *out_dev) {
+    if (batch * feat == 0) return DLLM_OK;
+    p_sample_kernel<<<grid1d(ctx, batch * feat), 256, 0, ctx->stream>>>(x_dev, pred_dev, z_dev, coef_table_dev,
+                                                                        rowmap_dev, row, batch, feat, out_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}

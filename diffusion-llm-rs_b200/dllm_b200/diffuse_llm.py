@@ -1,0 +1,292 @@
+"""Mirror of diffuse_llm_rs::diffuse_llm (diffuse-llm-rs/src/lib.rs): the layer interface
+(`DiffusionModel`), the quantized layer stack that implements it on the GPU, the phase-aware KV
+cache entry, and the denoising loop (`DiffuseLLM::sample`, `p_sample`)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .quantization import QuantizedKVCacheEntry
+from .runtime import Context, QWeight, default_context
+
+
+class BetaSchedule(Enum):
+    """lib.rs:109-117"""
+    Linear = L.BETA_LINEAR
+    Quadratic = L.BETA_QUADRATIC
+    Cosine = L.BETA_COSINE
+
+
+@dataclass
+class QuantizationConfig:
+    """phase-aware KV precision, lib.rs:85-105"""
+    prefill_bits: int = 8
+    decode_bits: int = 4
+    progressive_precision: bool = True
+    min_decode_bits: int = 2
+
+
+@dataclass
+class DiffusionConfig:
+    """lib.rs:52-81, defaults :476-493"""
+    num_timesteps: int = 1000
+    hidden_size: int = 768
+    num_layers: int = 12
+    num_attention_heads: int = 12
+    vocab_size: int = 50257
+    max_sequence_length: int = 1024
+    beta_start: float = 0.0001
+    beta_end: float = 0.02
+    beta_schedule: BetaSchedule = BetaSchedule.Linear
+    use_kv_cache: bool = True
+    kv_quant_bits: int = 4
+    max_cache_size: int = 2 * 1024 * 1024 * 1024
+    use_phase_aware_quant: bool = True
+    quant_config: QuantizationConfig = field(default_factory=QuantizationConfig)
+
+    def create_beta_schedule(self):
+        """lib.rs:554-593 (f32, host arithmetic inside the library)"""
+        betas = np.empty(self.num_timesteps, np.float32)
+        L.check(L.lib().dllm_beta_schedule(self.beta_schedule.value, self.num_timesteps, self.beta_start,
+                                           self.beta_end, betas.ctypes.data))
+        return betas
+
+
+class KVCacheEntry:
+    """lib.rs:122-313: f32 K/V plus up to two quantized copies (prefill / decode bits)."""
+
+    def __init__(self, keys, values, prefill_bits: int, decode_bits: int, ctx: Context | None = None):
+        self._ctx = ctx or default_context()
+        self.keys = np.ascontiguousarray(keys, np.float32)
+        self.values = np.ascontiguousarray(values, np.float32)
+        self.prefill_quant_bits, self.decode_quant_bits = prefill_bits, decode_bits
+        self.is_prefill_phase = True
+        self.seq_len = self.keys.shape[1]
+        self.prefill_quantized = self._q(prefill_bits) if prefill_bits > 0 else None    # :145-153
+        self.decode_quantized = self._q(decode_bits) if decode_bits > 0 else None       # :155-163
+
+    def _q(self, bits):
+        if self.keys.size == 0:
+            return None
+        return QuantizedKVCacheEntry(self.keys, self.values, bits, self._ctx)
+
+    def _active(self):
+        return self.prefill_quantized if self.is_prefill_phase else self.decode_quantized
+
+    def get_keys(self):
+        q = self._active()
+        return q.dequantize_keys() if q is not None else self.keys.copy()
+
+    def get_values(self):
+        q = self._active()
+        return q.dequantize_values() if q is not None else self.values.copy()
+
+    def set_phase(self, is_prefill: bool):
+        self.transition_phase(is_prefill)
+
+    def get_current_quant_bits(self) -> int:
+        return self.prefill_quant_bits if self.is_prefill_phase else self.decode_quant_bits
+
+    def transition_phase(self, is_prefill: bool):
+        if self.is_prefill_phase == is_prefill:
+            return
+        self.is_prefill_phase = is_prefill
+        if not is_prefill and self.decode_quant_bits > 0 and self.decode_quantized is None:   # :228-235
+            self.decode_quantized = self._q(self.decode_quant_bits)
+
+    def update(self, new_keys, new_values):
+        """:246-276 — re-quantizes at both precisions"""
+        self.keys = np.ascontiguousarray(new_keys, np.float32)
+        self.values = np.ascontiguousarray(new_values, np.float32)
+        self.seq_len = self.keys.shape[1]
+        if self.prefill_quant_bits > 0:
+            self.prefill_quantized = self._q(self.prefill_quant_bits)
+        if self.decode_quant_bits > 0:
+            self.decode_quantized = self._q(self.decode_quant_bits)
+
+    def memory_usage(self) -> int:
+        total = 0
+        for q in (self.prefill_quantized, self.decode_quantized):    # :283-296
+            if q is not None:
+                total += q.memory_usage()
+        return total if total else self.keys.size * 4 + self.values.size * 4
+
+    def len(self) -> int:
+        return self.seq_len
+
+    def is_empty(self) -> bool:
+        return self.seq_len == 0
+
+
+class DiffusionModel:
+    """trait DiffusionModel: Send + Sync (lib.rs:748-772)"""
+
+    def forward(self, x, t):
+        raise NotImplementedError
+
+    def forward_with_cache(self, x, t, keys, values):
+        raise NotImplementedError
+
+    def update_kv_cache(self, x, t, cache: KVCacheEntry):
+        raise NotImplementedError
+
+
+class QuantizedDiffusionModel(DiffusionModel):
+    """A stack of quantized linears `x·W+b` (each one the reference's SimpleDiffusionModel op,
+    lib.rs:806-813) resident in HBM; forward runs on the GPU.  x [batch, hidden*seq] is viewed as
+    [batch*seq, hidden] tokens; the stack's output width equals its input width."""
+
+    def __init__(self, layers: Sequence[QWeight], hidden: int, config: DiffusionConfig | None = None,
+                 ctx: Context | None = None, path: int = L.PATH_AUTO):
+        self._ctx = ctx or default_context()
+        self.layers = list(layers)
+        self.hidden = hidden
+        self.config = config or DiffusionConfig(hidden_size=hidden)
+        self.path = path
+        arr = (C.c_void_p * len(self.layers))(*[w.h for w in self.layers])
+        h = C.c_void_p()
+        self._ctx._ck(self._ctx._lib.dllm_model_create(
+            self._ctx.h, hidden, arr, len(self.layers), self.config.num_timesteps,
+            self.config.beta_schedule.value, self.config.beta_start, self.config.beta_end, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_f32(cls, weights: Sequence[np.ndarray], biases: Sequence[Optional[np.ndarray]], bits: int,
+                 group: int = 128, **kw):
+        ctx = kw.get("ctx") or default_context()
+        layers = [QWeight.quantize(ctx, w, bits, group, b) for w, b in zip(weights, biases)]
+        return cls(layers, weights[0].shape[0], **kw)
+
+    def forward(self, x, t=None):
+        x = np.ascontiguousarray(x, np.float32)
+        batch, feat = x.shape
+        out = np.empty_like(x)
+        tt = np.ascontiguousarray(t if t is not None else np.zeros(batch), np.uint64)
+        with self._ctx.lock:
+            self._ctx._ck(self._ctx._lib.dllm_model_forward(self._ctx.h, self.h, x.ctypes.data, tt.ctypes.data, batch,
+                                                            feat, out.ctypes.data, self.path))
+        return out
+
+    def forward_dev(self, x_dev: int, batch: int, feat: int, out_dev: int):
+        self._ctx._ck(self._ctx._lib.dllm_model_forward_dev(self._ctx.h, self.h, x_dev, batch, feat, out_dev, self.path))
+
+    def forward_with_cache(self, x, t, keys, values):
+        return self.forward(x, t)            # lib.rs:815-824: the cache is ignored
+
+    def update_kv_cache(self, x, t, cache: KVCacheEntry):
+        return cache.keys.copy(), cache.values.copy()   # lib.rs:826-835
+
+    def denoise_step_dev(self, x_dev: int, z_dev: Optional[int], t: int, batch: int, feat: int, guard_t0=True):
+        self._ctx._ck(self._ctx._lib.dllm_denoise_step_dev(self._ctx.h, self.h, x_dev, z_dev, t, batch, feat,
+                                                           int(guard_t0), self.path))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._ctx.sync()
+            self._ctx._lib.dllm_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SimpleDiffusionModel(QuantizedDiffusionModel):
+    """lib.rs:775-813: one linear layer, weights N(0,1)*0.02, zero bias — held quantized in HBM."""
+
+    def __init__(self, input_dim: int, output_dim: int, bits: int = 4, group: int = 128, seed: int | None = None,
+                 weights=None, bias=None, **kw):
+        rng = np.random.default_rng(seed)
+        self.weights = (np.asarray(weights, np.float32) if weights is not None
+                        else (rng.standard_normal((input_dim, output_dim)) * 0.02).astype(np.float32))   # :792-796
+        self.bias = np.asarray(bias, np.float32) if bias is not None else np.zeros(output_dim, np.float32)  # :798
+        ctx = kw.get("ctx") or default_context()
+        g = group if (group and input_dim % group == 0) else 0
+        layer = QWeight.quantize(ctx, self.weights, bits, g, self.bias)
+        super().__init__([layer], input_dim, **kw)
+
+
+class DiffuseLLM:
+    """The sampler half of lib.rs (`impl DiffuseLLM`, :853-955, :1100-1215)."""
+
+    def __init__(self, config: DiffusionConfig | None = None, ctx: Context | None = None):
+        self.config = config or DiffusionConfig()
+        self._ctx = ctx or default_context()
+        self.kv_cache = {}
+
+    # -- p_sample: lib.rs:1152-1215, noise injected --
+    def p_sample(self, model: QuantizedDiffusionModel, x_t, t, noise_pred, noise=None, guard_t0=True):
+        x_t = np.ascontiguousarray(x_t, np.float32)
+        noise_pred = np.ascontiguousarray(noise_pred, np.float32)
+        batch, feat = x_t.shape
+        tt = np.ascontiguousarray(t, np.uint64)
+        z = np.ascontiguousarray(noise, np.float32) if noise is not None else None
+        out = np.empty_like(x_t)
+        with self._ctx.lock:
+            self._ctx._ck(self._ctx._lib.dllm_p_sample(self._ctx.h, model.h, x_t.ctypes.data, noise_pred.ctypes.data,
+                                                       z.ctypes.data if z is not None else None, tt.ctypes.data,
+                                                       batch, feat, int(guard_t0), out.ctypes.data))
+        return out
+
+    def init_kv_cache(self, batch_size: int) -> KVCacheEntry:
+        """lib.rs:958-975: empty [layers, 0, hidden] cache with phase-aware bits"""
+        shape = (self.config.num_layers, 0, self.config.hidden_size)
+        q = self.config.quant_config
+        pre, dec = (q.prefill_bits, q.decode_bits) if self.config.use_phase_aware_quant else (self.config.kv_quant_bits,) * 2
+        return KVCacheEntry(np.zeros(shape, np.float32), np.zeros(shape, np.float32), pre, dec, self._ctx)
+
+    def sample(self, model: DiffusionModel, shape, num_steps: Optional[int] = None, cache_id: Optional[str] = None,
+               x0=None, noises=None, guard_t0: bool = True):
+        """lib.rs:853-927.  The reference draws x0 and the per-step noise from an unseeded
+        thread_rng (:875-878, :1201); here they are injected (`x0` [batch, hidden*seq], `noises`
+        [num_steps, batch, feat], slice t used at timestep t>0) or drawn from numpy when omitted."""
+        batch, seq_len = shape
+        num_steps = num_steps if num_steps is not None else self.config.num_timesteps
+        feat = self.config.hidden_size * seq_len
+        rng = np.random.default_rng()
+        x = np.ascontiguousarray(x0, np.float32) if x0 is not None else rng.standard_normal((batch, feat)).astype(np.float32)
+        if noises is None:
+            noises = rng.standard_normal((num_steps, batch, feat)).astype(np.float32)
+        noises = np.ascontiguousarray(noises, np.float32)
+        use_cache = self.config.use_kv_cache and cache_id is not None
+
+        if not use_cache and isinstance(model, QuantizedDiffusionModel):
+            # whole loop on the device: one H2D of x0, per-step noise slices, one D2H of the result
+            out = np.empty_like(x)
+            with self._ctx.lock:
+                self._ctx._ck(self._ctx._lib.dllm_sample(self._ctx.h, model.h, x.ctypes.data, noises.ctypes.data, batch,
+                                                         feat, num_steps, int(guard_t0), model.path, out.ctypes.data))
+            return out
+
+        cache = None
+        if use_cache:
+            cache = self.kv_cache.get(cache_id) or self.init_kv_cache(batch)
+            cache.set_phase(True)
+        qc = self.config.quant_config
+        for t in range(num_steps - 1, -1, -1):
+            t_array = np.full(batch, t, np.uint64)
+            if cache is not None:
+                is_prefill = C.c_int32()
+                target = self._ctx._lib.dllm_progressive_bits(num_steps, t, qc.decode_bits, qc.min_decode_bits,
+                                                              C.byref(is_prefill))              # :886-897
+                cache.set_phase(bool(is_prefill.value))
+                if (self.config.use_phase_aware_quant and qc.progressive_precision and not is_prefill.value
+                        and target != cache.decode_quant_bits):
+                    cache.decode_quant_bits = int(target)
+                    cache.decode_quantized = None                                             # :900-903
+                new_k, new_v = model.update_kv_cache(x, t_array, cache)                        # :907
+                pred = model.forward_with_cache(x, t_array, cache.get_keys(), cache.get_values())  # :910-915
+                cache.update(new_k, new_v)                                                     # :918
+            else:
+                pred = model.forward(x, t_array)                                               # :924
+            x = self.p_sample(model, x, t_array, pred, noises[t] if t > 0 else None, guard_t0)  # :921/:925
+        if cache is not None:
+            self.kv_cache[cache_id] = cache                                                    # :929-936
+        return x

@@ -1,0 +1,296 @@
+/*
+ * dllm_b200.h — C ABI of libdllm_b200.so: the B200-native (sm_100a) quantized-linear /
+ * quantize / KV-quant hot path of zetareticula/diffusion-llm-rs.
+ *
+ * The reference has no FFI of its own (no extern "C", no -sys crate): its
+ * seams are Rust traits and free functions.  Every entry point below names the reference
+ * item it replaces (file:line under the reference root) — INTEGRATION.md shows the Rust
+ * `extern "C"` block and the trait impls a maintainer adds on top.
+ *
+ * Conventions
+ *  - every function returns an int32 status (DLLM_OK == 0).  Reference panics / assert!s
+ *    and QuantizationError variants map onto the DLLM_ERR_* codes; the message is
+ *    available from dllm_last_error(ctx).  Nothing throws or aborts across the boundary.
+ *  - pointers without a `_dev` suffix in the function name are HOST pointers owned by the
+ *    caller (the reference's `&[f32]` / `Vec<u8>`); the call copies in, runs the CUDA
+ *    kernels and copies out before returning.  `*_dev` entry points take DEVICE pointers,
+ *    enqueue on the context's stream and return without synchronising.
+ *  - a dllm_ctx binds one CUDA device and one stream; use one ctx per thread (the Rust
+ *    wrapper keeps it behind a Mutex to satisfy `Send + Sync`).
+ *  - there is NO CPU fallback: without a CUDA device dllm_ctx_create fails with
+ *    DLLM_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef DLLM_B200_H
+#define DLLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLLM_API __attribute__((visibility("default")))
+
+/* ---- status codes ---- */
+enum {
+    DLLM_OK = 0,
+    /* quantization/src/error.rs:19-40 (QuantizationError) */
+    DLLM_ERR_INVALID_PARAMS = 1,       /* InvalidParams; also assert!(1..=8 bits) quantization.rs:39 */
+    DLLM_ERR_UNSUPPORTED = 2,          /* UnsupportedOperation */
+    DLLM_ERR_SHAPE = 3,                /* ShapeMismatch */
+    DLLM_ERR_CALIBRATION_REQUIRED = 4, /* CalibrationRequired, calibrate.rs:73-75 */
+    DLLM_ERR_IO = 5,
+    DLLM_ERR_SERIALIZATION = 6,
+    DLLM_ERR_INVALID_DATA_FORMAT = 7,
+    DLLM_ERR_INDEX = 8,                /* Vec index out of bounds panic, prefill-kvquant-rs/lib.rs:133 */
+    /* runtime */
+    DLLM_ERR_CUDA = 100,
+    DLLM_ERR_NO_DEVICE = 101,
+    DLLM_ERR_NCCL = 102,
+    DLLM_ERR_OOM = 103,
+    DLLM_ERR_NULL = 104
+};
+
+/* QuantizationType, quantization/src/quantize.rs:62-78 */
+enum { DLLM_QT_INT8 = 0, DLLM_QT_INT4 = 1, DLLM_QT_BINARY = 2, DLLM_QT_FLOAT8 = 3 };
+/* BetaSchedule, diffuse-llm-rs/src/lib.rs:109-117 */
+enum { DLLM_BETA_LINEAR = 0, DLLM_BETA_QUADRATIC = 1, DLLM_BETA_COSINE = 2 };
+/* KV quantization scheme: which reference quantizer a cache entry uses */
+enum {
+    DLLM_KV_TENSOR_B = 0, /* QuantizedKVCacheEntry::new: one scale/zp per tensor, quantization.rs:140-157 */
+    DLLM_KV_ROW_D = 1,    /* per-token row, prefill_kv.rs:104-121 */
+    DLLM_KV_FIXED_C = 2   /* fixed scale 1/(2^bits-1), prefill-kvquant-rs/lib.rs:39-46 */
+};
+/* which kernel a quantized linear runs on */
+enum {
+    DLLM_PATH_AUTO = 0,
+    DLLM_PATH_SIMT = 1,  /* f32 CUDA-core dequant-GEMV (exact f32 dequant, f32 accumulate) */
+    DLLM_PATH_UMMA = 2   /* tcgen05 / TMEM path: bf16 operands dequantized on the fly, f32 accumulate */
+};
+
+typedef struct dllm_ctx dllm_ctx;
+typedef struct dllm_qweight dllm_qweight; /* one quantized [K,N] weight resident in HBM */
+typedef struct dllm_model dllm_model;     /* stack of quantized linears behind DiffusionModel */
+typedef struct dllm_kv dllm_kv;           /* quantized K/V cache entry resident in HBM */
+
+/* ======================= context ======================= */
+DLLM_API const char *dllm_version(void);
+DLLM_API int32_t dllm_device_count(void);
+DLLM_API int32_t dllm_ctx_create(int32_t device, dllm_ctx **out);
+/* adopt an existing cudaStream_t (e.g. the caller's framework stream); not owned */
+DLLM_API int32_t dllm_ctx_create_on_stream(int32_t device, void *cuda_stream, dllm_ctx **out);
+DLLM_API void dllm_ctx_destroy(dllm_ctx *ctx);
+DLLM_API int32_t dllm_ctx_sync(dllm_ctx *ctx);
+DLLM_API void *dllm_ctx_stream(dllm_ctx *ctx);
+DLLM_API const char *dllm_last_error(const dllm_ctx *ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+DLLM_API uint64_t dllm_launch_count(const dllm_ctx *ctx);
+DLLM_API int32_t dllm_sm_count(const dllm_ctx *ctx);
+
+/* device / pinned-host memory helpers for callers without a CUDA runtime binding */
+DLLM_API int32_t dllm_malloc(dllm_ctx *ctx, size_t bytes, void **dptr);
+DLLM_API int32_t dllm_free(dllm_ctx *ctx, void *dptr);
+DLLM_API int32_t dllm_memcpy_h2d(dllm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+DLLM_API int32_t dllm_memcpy_d2h(dllm_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+DLLM_API int32_t dllm_host_alloc(size_t bytes, void **hptr);
+DLLM_API int32_t dllm_host_free(void *hptr);
+
+/* ======================= quantizer B =======================
+ * diffuse_llm_rs::quantization::quantize_tensor(&[f32], bits) -> (Vec<u8>, f32, f32)
+ *   diffuse-llm-rs/src/quantization.rs:38-68.   bits outside 1..=8 -> DLLM_ERR_INVALID_PARAMS. */
+DLLM_API int32_t dllm_quantize_tensor(dllm_ctx *ctx, const float *x, size_t n, uint8_t bits,
+                                      uint8_t *codes, float *scale, float *zero_point);
+/* dequantize_tensor(&[u8], scale, zp) -> Vec<f32>, quantization.rs:81-85 */
+DLLM_API int32_t dllm_dequantize_tensor(dllm_ctx *ctx, const uint8_t *codes, size_t n, float scale,
+                                        float zero_point, float *out);
+/* device-resident forms.  params_dev: float[4] = {scale, zero_point, min, max} written by the
+ * quantize call and read by the dequantize call (no host round trip).
+ * packed != 0: codes are bit-packed (bits in {1,2,4,8}, layout of dllm_pack). */
+DLLM_API int32_t dllm_quantize_tensor_dev(dllm_ctx *ctx, const float *x_dev, size_t n, uint8_t bits,
+                                          int32_t packed, uint8_t *codes_dev, float *params_dev);
+DLLM_API int32_t dllm_dequantize_tensor_dev(dllm_ctx *ctx, const uint8_t *codes_dev, size_t n,
+                                            uint8_t bits, int32_t packed, const float *params_dev,
+                                            float *out_dev);
+/* the code step alone with caller-supplied (scale, zp): quantization.rs:59-65 and
+ * AdaptiveQuantizer::quantize quantization.rs:220-234 (its CKMS sketch stays on the host) */
+DLLM_API int32_t dllm_quantize_codes(dllm_ctx *ctx, const float *x, size_t n, uint8_t bits,
+                                     float scale, float zero_point, uint8_t *codes);
+/* QuantizedTensor::compression_ratio, quantization.rs:120-124 (host arithmetic) */
+DLLM_API float dllm_compression_ratio(size_t numel, size_t data_len, uint8_t bits);
+
+/* ======================= quantizer A =======================
+ * quantization::DefaultQuantizer::{quantize,dequantize} + quant_utils::{quantize,dequantize}
+ *   quantization/src/quantize.rs:93-215, types.rs:71-81.  Through the reference's public API
+ *   scale == 1.0 and zero_point == 0 (quantize.rs:98-108); both are parameters here. */
+DLLM_API int32_t dllm_quantize_a(dllm_ctx *ctx, const float *x, size_t n, int32_t qtype, float scale,
+                                 int32_t zero_point, uint8_t *codes);
+DLLM_API int32_t dllm_dequantize_a(dllm_ctx *ctx, const uint8_t *codes, size_t n, float scale,
+                                   int32_t zero_point, float *out);
+/* CalibrationData::update's min/max fold on the device (calibrate.rs:42-46): out = {min, max} */
+DLLM_API int32_t dllm_minmax(dllm_ctx *ctx, const float *x, size_t n, float *min_out, float *max_out);
+/* CalibrationData::compute_params, calibrate.rs:72-110 (host arithmetic) */
+DLLM_API int32_t dllm_calibrate_params(float min, float max, size_t total_samples, uint8_t bits,
+                                       int32_t symmetric, float *scale, int32_t *zero_point);
+
+/* ======================= quantizer C =======================
+ * prefill_kvquant_rs::kvquant::BitQuantizer, prefill-kvquant-rs/lib.rs:34-53 */
+DLLM_API float dllm_bitquantizer_scale(uint8_t bits); /* 1/((1<<bits)-1), lib.rs:105 */
+DLLM_API int32_t dllm_quantize_c(dllm_ctx *ctx, const float *x, size_t n, uint8_t bits, float scale,
+                                 float zero_point, uint8_t *codes);
+/* BitQuantizer::dequantize `x as f32 * scale + zp` — shared by C and D (lib.rs:49-51,
+ * diffusion_prefill/src/prefill_kv.rs:62-66) */
+DLLM_API int32_t dllm_dequantize_cd(dllm_ctx *ctx, const uint8_t *codes, size_t n, float scale,
+                                    float zero_point, float *out);
+/* PrefillKVQuant::quantize_vectors, lib.rs:127-146: vector v uses bits[v % nbits] and the
+ * quantizer at index bits/2 of the Vec built from cfg_bits (DLLM_ERR_INDEX when out of range) */
+DLLM_API int32_t dllm_kvquant_quantize_vectors(dllm_ctx *ctx, const float *embeddings, size_t nvec,
+                                               size_t elems_per_vec, const uint8_t *cfg_bits,
+                                               size_t ncfg, const uint8_t *bits, size_t nbits,
+                                               uint8_t *codes);
+
+/* ======================= quantizer D (per-token rows) =======================
+ * KVCache::compress_vector / FusionANN::quantize: diffusion_prefill/src/prefill_kv.rs:104-121,
+ * fusion_ann.rs:53-88.  Row r uses bits[r % nbits] (fusion_ann.rs:58). */
+DLLM_API int32_t dllm_quantize_d_rows(dllm_ctx *ctx, const float *x, size_t rows, size_t dim,
+                                      const uint8_t *bits, size_t nbits, uint8_t *codes,
+                                      float *scales, float *zero_points);
+DLLM_API int32_t dllm_dequantize_d_rows(dllm_ctx *ctx, const uint8_t *codes, size_t rows, size_t dim,
+                                        const float *scales, const float *zero_points, float *out);
+/* fused per-token KV quantize, device resident, one bit width for all rows.
+ * packed != 0: row r's codes occupy dim*bits/8 bytes (bits in {1,2,4,8}, dim*bits % 8 == 0). */
+DLLM_API int32_t dllm_quantize_d_rows_dev(dllm_ctx *ctx, const float *x_dev, size_t rows, size_t dim,
+                                          uint8_t bits, int32_t packed, uint8_t *codes_dev,
+                                          float *scales_dev, float *zero_points_dev);
+DLLM_API int32_t dllm_dequantize_d_rows_dev(dllm_ctx *ctx, const uint8_t *codes_dev, size_t rows,
+                                            size_t dim, uint8_t bits, int32_t packed,
+                                            const float *scales_dev, const float *zero_points_dev,
+                                            float *out_dev);
+
+/* ======================= pack / unpack =======================
+ * The reference stores one code per u8 and only *accounts* for packed sizes
+ * ((len*bits+7)/8, quantization.rs:122, lib.rs:284-285).  This build defines the layout:
+ * element i -> bits [(i*bits)%8 ..) of byte (i*bits)/8, LSB first; bits in {1,2,4,8}. */
+DLLM_API size_t dllm_packed_len(size_t n, uint8_t bits);
+DLLM_API int32_t dllm_pack(dllm_ctx *ctx, const uint8_t *codes, size_t n, uint8_t bits, uint8_t *packed);
+DLLM_API int32_t dllm_unpack(dllm_ctx *ctx, const uint8_t *packed, size_t n, uint8_t bits, uint8_t *codes);
+DLLM_API int32_t dllm_pack_dev(dllm_ctx *ctx, const uint8_t *codes_dev, size_t n, uint8_t bits,
+                               uint8_t *packed_dev);
+DLLM_API int32_t dllm_unpack_dev(dllm_ctx *ctx, const uint8_t *packed_dev, size_t n, uint8_t bits,
+                                 uint8_t *codes_dev);
+
+/* ======================= quantized linear =======================
+ * The layer op is SimpleDiffusionModel::forward  `x.dot(&W) + &b`
+ * (diffuse-llm-rs/src/lib.rs:806-813) with W = dequantize_tensor(codes) (quantization.rs:81-85).
+ * W is [K,N] row-major like the reference's Array2 ([input_dim, output_dim], lib.rs:777).
+ * group == 0: one (scale, zp) for the whole tensor (reference behaviour);
+ * group  > 0: quantizer B per `group` consecutive k of each column (BASELINE.json configs[0];
+ *             QuantizationConfig::group_size = 128, quantization/src/types.rs:126); K % group == 0.
+ * bits in {2,4,8} are stored bit-packed in a tile-major layout private to the library. */
+DLLM_API int32_t dllm_qweight_quantize(dllm_ctx *ctx, const float *w, size_t K, size_t N, uint8_t bits,
+                                       size_t group, const float *bias /* [N] or NULL */,
+                                       dllm_qweight **out);
+DLLM_API int32_t dllm_qweight_quantize_dev(dllm_ctx *ctx, const float *w_dev, size_t K, size_t N,
+                                           uint8_t bits, size_t group, const float *bias_dev,
+                                           dllm_qweight **out);
+/* adopt codes produced elsewhere (one code per u8, [K,N]); scales/zps are [K/group, N] (or [1]) */
+DLLM_API int32_t dllm_qweight_from_codes(dllm_ctx *ctx, const uint8_t *codes, const float *scales,
+                                         const float *zero_points, size_t K, size_t N, uint8_t bits,
+                                         size_t group, const float *bias, dllm_qweight **out);
+/* read back in the canonical layout (parity checks / serialisation) */
+DLLM_API int32_t dllm_qweight_export(dllm_ctx *ctx, const dllm_qweight *w, uint8_t *codes,
+                                     float *scales, float *zero_points);
+DLLM_API int32_t dllm_qweight_info(const dllm_qweight *w, size_t *K, size_t *N, uint8_t *bits,
+                                   size_t *group, size_t *packed_bytes);
+DLLM_API void dllm_qweight_destroy(dllm_qweight *w);
+
+/* y[M,N] = x[M,K] · dequant(W) + b.  path: DLLM_PATH_* */
+DLLM_API int32_t dllm_qlinear_forward(dllm_ctx *ctx, const dllm_qweight *w, const float *x, size_t M,
+                                      float *y, int32_t path);
+DLLM_API int32_t dllm_qlinear_forward_dev(dllm_ctx *ctx, const dllm_qweight *w, const float *x_dev,
+                                          size_t M, float *y_dev, int32_t path);
+/* `quantization` crate extension named by BASELINE.json north_star ("quantize/dequantize/matmul"):
+ * one-shot dequant-matmul from canonical codes. */
+DLLM_API int32_t dllm_dequant_matmul(dllm_ctx *ctx, const uint8_t *codes, const float *scales,
+                                     const float *zero_points, size_t K, size_t N, uint8_t bits,
+                                     size_t group, const float *bias, const float *x, size_t M,
+                                     float *y, int32_t path);
+
+/* ======================= model / denoising loop =======================
+ * DiffusionModel::forward(x[batch, feat], t[batch]) -> [batch, feat]  (lib.rs:748-772): x is
+ * viewed as [batch*feat/hidden, hidden] tokens and sent through the stack of linears; the
+ * stack's last N equals its first K (output shape == input shape, lib.rs:759). */
+DLLM_API int32_t dllm_model_create(dllm_ctx *ctx, size_t hidden, dllm_qweight *const *layers,
+                                   size_t n_layers, size_t num_timesteps, int32_t beta_kind,
+                                   float beta_start, float beta_end, dllm_model **out);
+DLLM_API void dllm_model_destroy(dllm_model *m);
+DLLM_API int32_t dllm_model_forward(dllm_ctx *ctx, dllm_model *m, const float *x, const size_t *t,
+                                    size_t batch, size_t feat, float *noise_pred, int32_t path);
+DLLM_API int32_t dllm_model_forward_dev(dllm_ctx *ctx, dllm_model *m, const float *x_dev, size_t batch,
+                                        size_t feat, float *noise_pred_dev, int32_t path);
+/* create_beta_schedule, lib.rs:554-593 (host arithmetic, f32) */
+DLLM_API int32_t dllm_beta_schedule(int32_t kind, size_t T, float beta_start, float beta_end, float *betas);
+/* p_sample, lib.rs:1152-1215, noise injected (z may be NULL; ignored when t[0]==0).
+ * guard_t0 != 0: rows with 1 - alpha_bar_t == 0 keep x_prev = x_t (DESIGN.md "p_sample"). */
+DLLM_API int32_t dllm_p_sample(dllm_ctx *ctx, dllm_model *m, const float *x_t, const float *noise_pred,
+                               const float *z, const size_t *t, size_t batch, size_t feat,
+                               int32_t guard_t0, float *x_prev);
+/* one denoise step on the device: noise_pred = forward(x); x <- p_sample(x, t, noise_pred, z) */
+DLLM_API int32_t dllm_denoise_step_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, const float *z_dev,
+                                       size_t t, size_t batch, size_t feat, int32_t guard_t0,
+                                       int32_t path);
+/* DiffuseLLM::sample without cache, lib.rs:853-927.  x0: initial noise [batch, feat];
+ * noises: [num_steps, batch, feat], slice t used at timestep t (slice 0 unused).  Host pointers. */
+DLLM_API int32_t dllm_sample(dllm_ctx *ctx, dllm_model *m, const float *x0, const float *noises,
+                             size_t batch, size_t feat, size_t num_steps, int32_t guard_t0,
+                             int32_t path, float *x_out);
+/* progressive decode precision, lib.rs:886-897 (host arithmetic) */
+DLLM_API uint8_t dllm_progressive_bits(size_t num_steps, size_t t, uint8_t decode_bits,
+                                       uint8_t min_decode_bits, int32_t *is_prefill);
+
+/* ======================= KV cache =======================
+ * QuantizedKVCacheEntry::new(keys, values, bits) / dequantize_keys / dequantize_values
+ * (quantization.rs:129-176) over [layers, seq, hidden] f32, plus the per-token (D) and
+ * fixed-scale (C) schemes of the prefill crates.  Codes are bit-packed when bits in {1,2,4,8}. */
+DLLM_API int32_t dllm_kv_quantize(dllm_ctx *ctx, const float *keys, const float *values, size_t layers,
+                                  size_t seq, size_t hidden, uint8_t bits, int32_t scheme,
+                                  dllm_kv **out);
+DLLM_API int32_t dllm_kv_quantize_dev(dllm_ctx *ctx, const float *keys_dev, const float *values_dev,
+                                      size_t layers, size_t seq, size_t hidden, uint8_t bits,
+                                      int32_t scheme, dllm_kv **out);
+/* re-quantize into an existing entry (KVCacheEntry::update, lib.rs:246-276) */
+DLLM_API int32_t dllm_kv_update_dev(dllm_ctx *ctx, dllm_kv *kv, const float *keys_dev,
+                                    const float *values_dev);
+DLLM_API int32_t dllm_kv_dequantize(dllm_ctx *ctx, const dllm_kv *kv, float *keys, float *values);
+DLLM_API int32_t dllm_kv_dequantize_dev(dllm_ctx *ctx, const dllm_kv *kv, float *keys_dev,
+                                        float *values_dev);
+/* one-code-per-u8 view + parameters, for parity checks against the reference layout.
+ * scales/zps hold 1 entry (B, C) or layers*seq entries (D) per tensor. */
+DLLM_API int32_t dllm_kv_export(dllm_ctx *ctx, const dllm_kv *kv, uint8_t *key_codes,
+                                uint8_t *value_codes, float *key_scales, float *key_zps,
+                                float *value_scales, float *value_zps);
+/* KVCacheEntry::memory_usage accounting, lib.rs:279-302: (len*bits+7)/8 per tensor */
+DLLM_API size_t dllm_kv_memory_usage(const dllm_kv *kv);
+DLLM_API void dllm_kv_destroy(dllm_kv *kv);
+
+/* ======================= multi-GPU (one process per GPU) =======================
+ * Tensor parallel linears: column-parallel (split N) followed by row-parallel (split K) with
+ * one NCCL collective per pair at the layer boundary.  Rank 0 creates the id,
+ * the launcher broadcasts its 128 bytes (e.g. torch.distributed), every rank calls tp_init. */
+DLLM_API int32_t dllm_tp_unique_id(uint8_t id_out[128]);
+DLLM_API int32_t dllm_tp_init(dllm_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t world);
+DLLM_API int32_t dllm_tp_finalize(dllm_ctx *ctx);
+/* sum-all-reduce of a device f32 buffer over the TP group (row-parallel partial sums) */
+DLLM_API int32_t dllm_tp_allreduce_dev(dllm_ctx *ctx, float *buf_dev, size_t n);
+/* all-gather of column shards: in [M, N/world] per rank -> out [M, N] */
+DLLM_API int32_t dllm_tp_allgather_cols_dev(dllm_ctx *ctx, const float *in_dev, size_t M,
+                                            size_t n_local, float *out_dev);
+/* model whose layers alternate column-/row-parallel shards held by this rank:
+ * parallel[i] in {0 replicated, 1 column (split N), 2 row (split K)} */
+DLLM_API int32_t dllm_model_set_parallel(dllm_ctx *ctx, dllm_model *m, const int32_t *parallel,
+                                         size_t n_layers);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLLM_B200_H */

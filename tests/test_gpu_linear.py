@@ -1,0 +1,227 @@
+"""GPU parity of the quantized weight object and the dequant-matmul paths against the oracle.
+
+Tolerances (BASELINE.json north_star):
+  * weight quantization / repack / export: bit-exact;
+  * SIMT path (f32 dequant exactly as the reference, f32 accumulate): max|y - y64| <= 2e-5 * (|x|·|W|)
+    — f32 summation-order noise only;
+  * tcgen05 path (bf16 operands, f32 accumulate): max|y - y64| <= 1e-2 * max|y64|  and
+    relative Frobenius error <= 1e-2.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import dllm_b200
+    c = dllm_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import pyoracle
+    return pyoracle
+
+
+def beq(a, b):
+    a, b = np.asarray(a, F), np.asarray(b, F)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def make_w(rng, K, N, std=0.02):
+    return (rng.standard_normal((K, N)) * std).astype(F)     # lib.rs:792-796 init
+
+
+# ---------------------------------------------------------------- weight object
+@pytest.mark.parametrize("bits", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("shape", [(128, 128), (256, 200), (512, 384), (1024, 130)])
+def test_grouped_weight_quantize_bit_exact(ctx, O, bits, shape):
+    from dllm_b200 import QWeight
+    K, N = shape
+    rng = np.random.default_rng(K + N + bits)
+    w = make_w(rng, K, N)
+    qw = QWeight.quantize(ctx, w, bits, 128)
+    codes, scales, zps = qw.export()
+    c0, s0, z0 = O.quantize_weight_grouped(w, bits, 128)
+    assert beq(scales, s0) and beq(zps, z0)
+    assert np.array_equal(codes, c0)
+    qw.close()
+
+
+@pytest.mark.parametrize("bits", [2, 4, 8])
+@pytest.mark.parametrize("shape", [(64, 128), (100, 50), (333, 257)])
+def test_per_tensor_weight_quantize_bit_exact(ctx, O, bits, shape):
+    """group == 0: the reference's per-tensor quantize_tensor over the whole [K,N] array."""
+    from dllm_b200 import QWeight
+    K, N = shape
+    rng = np.random.default_rng(K * N + bits)
+    w = make_w(rng, K, N)
+    qw = QWeight.quantize(ctx, w, bits, 0)
+    codes, scales, zps = qw.export()
+    c0, s0, z0 = O.quantize_tensor(w, bits)
+    assert beq(scales[0, 0], s0) and beq(zps[0, 0], z0)
+    assert np.array_equal(codes.ravel(), c0)
+    qw.close()
+
+
+@pytest.mark.parametrize("bits", [2, 4, 8])
+def test_from_codes_roundtrip(ctx, O, bits):
+    from dllm_b200 import QWeight
+    rng = np.random.default_rng(bits)
+    K, N = 384, 200
+    codes = rng.integers(0, 1 << bits, (K, N)).astype(np.uint8)
+    scales = (rng.random((K // 128, N)) * 0.01 + 0.001).astype(F)
+    zps = rng.integers(0, 1 << bits, (K // 128, N)).astype(F)
+    qw = QWeight.from_codes(ctx, codes, scales, zps, bits, 128)
+    c1, s1, z1 = qw.export()
+    assert np.array_equal(c1, codes) and beq(s1, scales) and beq(z1, zps)
+    assert qw.packed_bytes == ((N + 127) // 128) * 128 * K * (2 if bits <= 2 else 4 if bits <= 4 else 8) // 8
+    qw.close()
+
+
+def test_weight_argument_errors(ctx):
+    import dllm_b200
+    from dllm_b200 import QWeight
+    w = np.zeros((128, 16), F)
+    with pytest.raises(dllm_b200.InvalidParams):
+        QWeight.quantize(ctx, w, 0, 128)
+    with pytest.raises(dllm_b200.InvalidParams):
+        QWeight.quantize(ctx, w, 9, 128)
+    with pytest.raises(dllm_b200.ShapeMismatch):
+        QWeight.quantize(ctx, w, 4, 96)            # group must be a multiple of 64
+    with pytest.raises(dllm_b200.ShapeMismatch):
+        QWeight.quantize(ctx, np.zeros((192, 16), F), 4, 128)   # K % group != 0
+
+
+# ---------------------------------------------------------------- linear, SIMT path
+def ref_linear(O, x, w, bits, group, bias):
+    if group:
+        c, s, z = O.quantize_weight_grouped(w, bits, group)
+        wd = O.dequantize_weight_grouped(c, s, z, group)
+    else:
+        c, s, z = O.quantize_tensor(w, bits)
+        wd = O.dequantize_tensor(c, s, z).reshape(w.shape)
+    y64 = O.linear_f64(x, wd, bias)
+    bound = np.abs(x).astype(np.float64) @ np.abs(wd).astype(np.float64)
+    return wd, y64, bound
+
+
+@pytest.mark.parametrize("bits", [2, 4, 8])
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 7, 8, 16, 33])
+def test_qlinear_simt_matches_oracle(ctx, O, bits, M):
+    from dllm_b200 import QWeight, PATH_SIMT
+    rng = np.random.default_rng(M * 10 + bits)
+    K, N = 1024, 384
+    w = make_w(rng, K, N)
+    x = rng.standard_normal((M, K)).astype(F)
+    bias = rng.standard_normal(N).astype(F)
+    qw = QWeight.quantize(ctx, w, bits, 128, bias)
+    y = qw.forward(x, PATH_SIMT)
+    wd, y64, bound = ref_linear(O, x, w, bits, 128, bias)
+    assert np.all(np.abs(y - y64) <= 2e-5 * bound + 1e-6)
+    # and it agrees with the oracle's own f32 sequential linear to f32 noise
+    y32 = O.linear_f32(x, wd, bias)
+    assert np.allclose(y, y32, rtol=0, atol=2e-5 * bound.max())
+    qw.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 10), (200, 130), (4096, 256)])
+def test_qlinear_simt_ragged_shapes_and_per_tensor(ctx, O, shape):
+    from dllm_b200 import QWeight, PATH_SIMT
+    K, N = shape
+    rng = np.random.default_rng(K + N)
+    w = make_w(rng, K, N)
+    x = rng.standard_normal((5, K)).astype(F)
+    qw = QWeight.quantize(ctx, w, 4, 0)            # per-tensor (reference behaviour), K, N ragged
+    y = qw.forward(x, PATH_SIMT)
+    _, y64, bound = ref_linear(O, x, w, 4, 0, None)
+    assert np.all(np.abs(y - y64) <= 2e-5 * bound + 1e-6)
+    qw.close()
+
+
+def test_dequant_matmul_example_config0(ctx, O):
+    """BASELINE.json configs[0]: 4-bit group-quantize + dequant-matmul, 4096x4096 weight, 8 tokens."""
+    import dllm_b200
+    rng = np.random.default_rng(42)
+    K = N = 4096
+    w = make_w(rng, K, N)
+    x = rng.standard_normal((8, K)).astype(F)
+    c, s, z = O.quantize_weight_grouped(w, 4, 128)
+    y = dllm_b200.dequant_matmul(ctx, c, s, z, x, 4, 128, None, dllm_b200.PATH_SIMT)
+    wd = O.dequantize_weight_grouped(c, s, z, 128)
+    y32 = O.linear_f32(x, wd, None, threads=8)
+    bound = float((np.abs(x).astype(np.float64) @ np.abs(wd).astype(np.float64)).max())
+    assert np.max(np.abs(y - y32)) <= 4e-5 * bound
+
+
+# ---------------------------------------------------------------- linear, tcgen05 path
+def umma_check(y, y64):
+    err = np.abs(y - y64)
+    assert err.max() <= 1e-2 * np.abs(y64).max(), (err.max(), np.abs(y64).max())
+    assert np.linalg.norm(y - y64) <= 1e-2 * np.linalg.norm(y64)
+
+
+@pytest.mark.parametrize("bits", [4, 2, 8])
+@pytest.mark.parametrize("M", [1, 8, 16, 128, 300])
+def test_qlinear_umma_matches_oracle(ctx, O, bits, M):
+    from dllm_b200 import QWeight, PATH_UMMA
+    rng = np.random.default_rng(M + bits)
+    K, N = 1024, 512
+    w = make_w(rng, K, N)
+    x = rng.standard_normal((M, K)).astype(F)
+    bias = rng.standard_normal(N).astype(F)
+    qw = QWeight.quantize(ctx, w, bits, 128, bias)
+    y = qw.forward(x, PATH_UMMA)
+    _, y64, _ = ref_linear(O, x, w, bits, 128, bias)
+    umma_check(y, y64)
+    qw.close()
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 130, 512), (2048, 2048, 256), (4096, 1024, 8192 // 8)])
+def test_qlinear_umma_shapes(ctx, O, shape):
+    from dllm_b200 import QWeight, PATH_UMMA
+    K, N, M = shape
+    rng = np.random.default_rng(K + N + M)
+    w = make_w(rng, K, N)
+    x = rng.standard_normal((M, K)).astype(F)
+    qw = QWeight.quantize(ctx, w, 4, 128)
+    y = qw.forward(x, PATH_UMMA)
+    c, s, z = O.quantize_weight_grouped(w, 4, 128)
+    wd = O.dequantize_weight_grouped(c, s, z, 128)
+    y64 = x.astype(np.float64) @ wd.astype(np.float64)
+    umma_check(y, y64)
+    qw.close()
+
+
+def test_qlinear_umma_vs_simt_full_width(ctx):
+    """Full BASELINE width (K=N=14336, 4-bit, M=16): both device paths agree to bf16 tolerance.
+    (The CPU oracle needs minutes at this size; the two GPU paths share only the packed weights.)"""
+    import torch
+    from dllm_b200 import QWeight, PATH_SIMT, PATH_UMMA
+    K = N = 14336
+    M = 16
+    g = torch.Generator(device="cuda").manual_seed(1)
+    w = torch.randn(K, N, device="cuda", generator=g) * 0.02
+    x = torch.randn(M, K, device="cuda", generator=g)
+    y1 = torch.empty(M, N, device="cuda")
+    y2 = torch.empty(M, N, device="cuda")
+    torch.cuda.synchronize()
+    qw = QWeight.quantize_dev(ctx, w.data_ptr(), K, N, 4, 128)
+    qw.forward_dev(x.data_ptr(), M, y1.data_ptr(), PATH_SIMT)
+    qw.forward_dev(x.data_ptr(), M, y2.data_ptr(), PATH_UMMA)
+    ctx.sync()
+    assert float((y1 - y2).abs().max()) <= 1e-2 * float(y1.abs().max())
+    # linearity property of the SIMT path: f(2x) == 2 f(x) exactly in f32 (power-of-two scaling)
+    x2 = x * 2
+    y3 = torch.empty_like(y1)
+    torch.cuda.synchronize()
+    qw.forward_dev(x2.data_ptr(), M, y3.data_ptr(), PATH_SIMT)
+    ctx.sync()
+    assert torch.equal(y3, y1 * 2)
+    qw.close()
