@@ -1,7 +1,478 @@
-// placeholder until the tcgen05 kernel lands
+// umma_gemm.cu — tcgen05 / TMEM dequant-GEMM (K5) and skinny dequant-GEMV (K4 fast path).
+//
+//   y[M,N] = x[M,K] · dequant(W) + b            (diffuse-llm-rs/src/lib.rs:812 composed with
+//                                                 dequantize_tensor, quantization.rs:81-85)
+//
+// Formulated "weights-as-A":   D[n, tok] += A[n, k] · B[tok, k]^T
+//   A (128 output columns x 64 k per step): 2/4/8-bit codes streamed from HBM with one bulk
+//      async copy per tile (tile-major layout, wlayout.cuh), dequantized IN REGISTERS to bf16
+//      ((q - zp) * scale, per group of 128 k) by the dequant warps and written straight into
+//      TENSOR MEMORY with tcgen05.st — the dequantized weights never touch shared memory or HBM.
+//   B (NTOK tokens x 64 k): bf16 activations, TMA-loaded (SWIZZLE_128B, K-major) into smem.
+//   D: f32 accumulators in TMEM (double buffered), read back with tcgen05.ld by the epilogue warps.
+// tcgen05.mma.cta_group::1.kind::f16 with A from TMEM ("TS" form), M=128, N=NTOK, K=16.
+//
+// Warp roles (512 threads, one persistent CTA per SM):
+//   warp 0      TMA / bulk-copy producer (one elected lane)
+//   warp 1      TMEM allocator + MMA issuer (one elected lane)
+//   warps 4-11  two dequant groups of 4 warps (warp%4 = TMEM lane quarter); group g takes the
+//               pipeline stages with stage%2 == g
+//   warps 12-15 epilogue: TMEM -> registers -> (+bias) -> global (f32 and/or bf16), coalesced
+// Pipelines: full[s] (TMA bytes landed) -> afull[s] (A slot written to TMEM) -> MMA ->
+//   tcgen05.commit -> empty[s];  tmem_full[a] / tmem_empty[a] between MMA and epilogue.
+// Work items = (output tile, K segment); skinny shapes split K so that every SM streams weights
+// (partials reduced in a fixed order by a second tiny kernel: deterministic).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.h"
-bool k_umma_supported(const dllm_qweight *, size_t) { return false; }
-int32_t k_qlinear_umma(dllm_ctx *ctx, const dllm_qweight *, const void *, size_t, float *, void *) {
-    DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "tcgen05 path not built");
+#include "wlayout.cuh"
+
+namespace {
+
+constexpr int kNumThreads = 512;
+constexpr int kStages = 8;
+constexpr int kAccStages = 2;
+constexpr int kACols = 32;            // TMEM columns of one A slot: 64 k of bf16 = 32 x 32-bit
+constexpr int kTmemCols = 512;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]      (kind::f16: bf16 operands, f32 accumulate)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// smem matrix descriptor of a K-major, SWIZZLE_128B bf16 tile (rows of 128 bytes, 8-row groups of
+// 1024 bytes): start>>4 | LBO(=1)<<16 | SBO(=1024>>4)<<32 | version(=1)<<46 | layout(=2: SW128)<<61
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), K-major A and B, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// dequantize one k-block (64 k) of one output column to 32 packed bf16 pairs: (q - zp) * scale.
+// q - zp is exact in bf16 (small integers); the product rounds once (the scale is bf16-rounded).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf2_sub_mul(uint32_t a, uint32_t zb, uint32_t s2) {
+    __nv_bfloat162 d = __hsub2(*reinterpret_cast<__nv_bfloat162 *>(&a), *reinterpret_cast<__nv_bfloat162 *>(&zb));
+    __nv_bfloat162 r = __hmul2(d, *reinterpret_cast<__nv_bfloat162 *>(&s2));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+
+template <int CB>
+__device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, float scale, float zp, uint32_t *out) {
+    constexpr int CH = CB / 2;
+    __nv_bfloat162 sb = __float2bfloat162_rn(scale);
+    const uint32_t s2 = *reinterpret_cast<uint32_t *>(&sb);
+    if (CB == 4 || CB == 2) {
+        // magic: 0x4300 | q is the bf16 number 128 + q (exact for q < 128); subtract bf16(128 + zp)
+        __nv_bfloat162 zb2 = __float2bfloat162_rn(128.0f + zp);
+        const uint32_t zb = *reinterpret_cast<uint32_t *>(&zb2);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const uint4 c = wpk[j * 128 + n_local];
+            const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int wd = 0; wd < 4; ++wd) {
+                if (CB == 4) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        out[j * 16 + wd * 4 + i] = bf2_sub_mul(((w[wd] >> (4 * i)) & 0x000f000fu) | 0x43004300u, zb, s2);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        out[wd * 8 + i] = bf2_sub_mul(((w[wd] >> (2 * i)) & 0x00030003u) | 0x43004300u, zb, s2);
+                }
+            }
+        }
+    } else {
+        // 8-bit: q and zp up to 255 — exact in f32, (q - zp) exact in bf16 after the subtraction
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const uint4 c = wpk[j * 128 + n_local];
+            const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int wd = 0; wd < 4; ++wd) {
+                // 0x4B000000 | byte == 8388608.0f + q
+                const float q0 = __uint_as_float(__byte_perm(w[wd], 0x4B000000u, 0x7650)) - 8388608.0f;
+                const float q1 = __uint_as_float(__byte_perm(w[wd], 0x4B000000u, 0x7651)) - 8388608.0f;
+                const float q2 = __uint_as_float(__byte_perm(w[wd], 0x4B000000u, 0x7652)) - 8388608.0f;
+                const float q3 = __uint_as_float(__byte_perm(w[wd], 0x4B000000u, 0x7653)) - 8388608.0f;
+                __nv_bfloat162 d01 = __floats2bfloat162_rn(q0 - zp, q1 - zp);
+                __nv_bfloat162 d23 = __floats2bfloat162_rn(q2 - zp, q3 - zp);
+                __nv_bfloat162 r01 = __hmul2(d01, sb), r23 = __hmul2(d23, sb);
+                out[j * 8 + wd * 2 + 0] = *reinterpret_cast<uint32_t *>(&r01);
+                out[j * 8 + wd * 2 + 1] = *reinterpret_cast<uint32_t *>(&r23);
+            }
+        }
+    }
+}
+
+struct UmmaArgs {
+    const uint8_t *packed;
+    const float *scales, *zps, *bias;
+    float *y_f32;              // final f32 output [M,N] (splits == 1) or null
+    __nv_bfloat16 *y_bf16;     // final bf16 output [M,N] (splits == 1) or null
+    float *partial;            // [splits][M][Npad] when splits > 1
+    uint32_t M, N, Npad, k_blocks, n_tiles, m_tiles, splits, group_kb, tile_bytes;
+};
+
+template <int NTOK>
+struct SmemLayout {
+    static constexpr int kXBytes = NTOK * 128;
+    static constexpr int kWBytesMax = 8192;
+    static constexpr int kStageBytes = kXBytes + kWBytesMax;
+    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
+};
+
+template <int CB, int NTOK>
+__global__ void __launch_bounds__(kNumThreads, 1)
+umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
+    using SL = SmemLayout<NTOK>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SL::kBarOffset);
+    uint64_t *full = bars, *afull = bars + kStages, *empty = bars + 2 * kStages;
+    uint64_t *tfull = bars + 3 * kStages, *tempty = tfull + kAccStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t wbytes = a.tile_bytes;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(afull + s, 4); mbar_init(empty + s, 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_col0 = 0;                          // 2 x NTOK accumulator columns
+    const uint32_t a_col0 = kAccStages * NTOK;            // then kStages x 32 columns of A slots
+
+    const uint32_t n_items = a.n_tiles * a.m_tiles * a.splits;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const uint32_t tile = w / a.splits, seg = w - tile * a.splits;
+                const uint32_t nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+                const uint32_t kb0 = a.k_blocks * seg / a.splits, kb1 = a.k_blocks * (seg + 1) / a.splits;
+                const uint8_t *wsrc = a.packed + ((size_t)nt * a.k_blocks) * wbytes;
+                for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                    mbar_wait(empty + s, ph ^ 1);
+                    uint8_t *stage = smem + s * SL::kStageBytes;
+                    mbar_arrive_expect_tx(full + s, SL::kXBytes + wbytes);
+                    tma_load_2d(stage, &tmap_x, full + s, (int)(kb * WL_TILE_K), (int)(mt * NTOK));
+                    bulk_load(stage + SL::kXBytes, wsrc + (size_t)kb * wbytes, wbytes, full + s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(NTOK);
+            uint32_t it = 0, item = 0;
+            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
+                const uint32_t tile = w / a.splits, seg = w - tile * a.splits;
+                const uint32_t kb0 = a.k_blocks * seg / a.splits, kb1 = a.k_blocks * (seg + 1) / a.splits;
+                const uint32_t acc = item % kAccStages, aph = (item / kAccStages) & 1;
+                mbar_wait(tempty + acc, aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc_col0 + acc * NTOK;
+                for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                    mbar_wait(full + s, ph);      // TMA bytes of the B tile are visible to this thread
+                    mbar_wait(afull + s, ph);     // A slot s has been written to TMEM
+                    tc_fence_after();
+                    const uint64_t bdesc = make_b_desc(smem_u32(smem + s * SL::kStageBytes));
+                    const uint32_t a_tmem = tmem_base + a_col0 + s * kACols;
+#pragma unroll
+                    for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                        umma_ts(d_tmem, a_tmem + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (kb > kb0 || k4 > 0) ? 1u : 0u);
+                    umma_commit(empty + s);       // frees smem stage s and TMEM A slot s
+                }
+                umma_commit(tfull + acc);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===================== dequant warps =====================
+        const int grp = (warp - 4) >> 2;          // 0 / 1
+        const int quarter = warp & 3;             // TMEM lanes [32*quarter, +32)
+        const int n_local = quarter * 32 + lane;
+        uint32_t it = 0;
+        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const uint32_t tile = w / a.splits, seg = w - tile * a.splits;
+            const uint32_t nt = tile % a.n_tiles;
+            const uint32_t kb0 = a.k_blocks * seg / a.splits, kb1 = a.k_blocks * (seg + 1) / a.splits;
+            const float *sc = a.scales + (size_t)nt * 128 + n_local;
+            const float *zc = a.zps + (size_t)nt * 128 + n_local;
+            uint32_t cur_g = 0xffffffffu;
+            float scale = 0.f, zp = 0.f;
+            for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                if ((int)(s & 1) != grp) continue;
+                const uint32_t g = kb / a.group_kb;
+                if (g != cur_g) { scale = __ldg(sc + (size_t)g * a.Npad); zp = __ldg(zc + (size_t)g * a.Npad); cur_g = g; }
+                mbar_wait(full + s, ph);
+                const uint4 *wpk = reinterpret_cast<const uint4 *>(smem + s * SL::kStageBytes + SL::kXBytes);
+                uint32_t vals[32];
+                dequant_kblock<CB>(wpk, n_local, scale, zp, vals);
+                tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0 + s * kACols, vals);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull + s);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;
+        uint32_t item = 0;
+        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
+            const uint32_t tile = w / a.splits, seg = w - tile * a.splits;
+            const uint32_t nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+            const uint32_t acc = item % kAccStages, aph = (item / kAccStages) & 1;
+            const uint32_t n = nt * 128 + quarter * 32 + lane;
+            const bool n_ok = n < a.N;
+            const float bias = (a.splits == 1 && a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
+            mbar_wait(tfull + acc, aph);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col0 + acc * NTOK;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NTOK; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_acc + c0, v);
+                tmem_ld_wait();
+                const uint32_t m_base = mt * NTOK + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t m = m_base + j;
+                    if (m < a.M && n_ok) {
+                        const float val = __uint_as_float(v[j]) + bias;
+                        if (a.splits > 1) {
+                            a.partial[((size_t)seg * a.M + m) * a.Npad + n] = val;
+                        } else {
+                            if (a.y_f32) a.y_f32[(size_t)m * a.N + n] = val;
+                            if (a.y_bf16) a.y_bf16[(size_t)m * a.N + n] = __float2bfloat16_rn(val);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// y[m][n] = sum_seg partial[seg][m][n] + bias[n]  (fixed order => deterministic)
+__global__ void umma_splitk_reduce_kernel(const float *__restrict__ part, int splits, size_t M, size_t N, size_t Npad,
+                                          const float *__restrict__ bias, float *__restrict__ y_f32,
+                                          __nv_bfloat16 *__restrict__ y_bf16) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * N) return;
+    const size_t m = idx / N, n = idx - m * N;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += part[((size_t)s * M + m) * Npad + n];
+    if (bias) v += __ldg(bias + n);
+    if (y_f32) y_f32[idx] = v;
+    if (y_bf16) y_bf16[idx] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+template <int CB, int NTOK>
+int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, size_t M, float *y_f32, void *y_bf16) {
+    using SL = SmemLayout<NTOK>;
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)qw->K, (cuuint64_t)M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)qw->K * 2};
+    const cuuint32_t box[2] = {WL_TILE_K, (cuuint32_t)NTOK};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(x_bf16), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+
+    UmmaArgs a;
+    a.packed = qw->d_packed; a.scales = qw->d_scales; a.zps = qw->d_zps; a.bias = qw->d_bias;
+    a.M = (uint32_t)M; a.N = (uint32_t)qw->N; a.Npad = (uint32_t)(qw->n_tiles * 128);
+    a.k_blocks = (uint32_t)qw->k_blocks; a.n_tiles = (uint32_t)qw->n_tiles;
+    a.m_tiles = (uint32_t)((M + NTOK - 1) / NTOK);
+    a.group_kb = (uint32_t)(qw->group / WL_TILE_K);
+    a.tile_bytes = (uint32_t)qw->tile_bytes;
+    // K segments: enough work items to occupy every SM, at least 4 k-blocks per segment
+    const uint32_t tiles = a.n_tiles * a.m_tiles;
+    uint32_t splits = 1;
+    if (tiles < (uint32_t)ctx->sm_count) {
+        splits = ((uint32_t)ctx->sm_count + tiles - 1) / tiles;
+        const uint32_t max_splits = a.k_blocks >= 4 ? a.k_blocks / 4 : 1;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    a.splits = splits;
+    a.y_f32 = y_f32; a.y_bf16 = (__nv_bfloat16 *)y_bf16; a.partial = nullptr;
+    if (splits > 1) {
+        DLLM_TRY(ensure_buf(ctx, ctx->lin_ws, (size_t)splits * M * a.Npad * sizeof(float)));
+        a.partial = (float *)ctx->lin_ws.p;
+    }
+    const uint32_t n_items = tiles * splits;
+    const int grid = (int)(n_items < (uint32_t)ctx->sm_count ? n_items : (uint32_t)ctx->sm_count);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
+        attr_set = true;
+    }
+    umma_qlinear_kernel<CB, NTOK><<<grid, kNumThreads, SL::kTotal, ctx->stream>>>(tmap, a);
+    LAUNCH_CHECK(ctx);
+    if (splits > 1) {
+        const size_t total = M * qw->N;
+        umma_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+            a.partial, (int)splits, M, qw->N, a.Npad, qw->d_bias, y_f32, (__nv_bfloat16 *)y_bf16);
+        LAUNCH_CHECK(ctx);
+    }
+    return DLLM_OK;
+}
+
+template <int CB>
+int32_t launch_umma_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const void *x, size_t M, float *y_f32, void *y_bf16) {
+    if (M <= 16) return launch_umma<CB, 16>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 32) return launch_umma<CB, 32>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 64) return launch_umma<CB, 64>(ctx, qw, x, M, y_f32, y_bf16);
+    return launch_umma<CB, 128>(ctx, qw, x, M, y_f32, y_bf16);
+}
+
+}  // namespace
+
+bool k_umma_supported(const dllm_qweight *qw, size_t M) {
+    // TMA needs a 16-byte row pitch for x (K % 8 == 0); everything else is padded / masked
+    return qw && M >= 1 && M < (1u << 31) && qw->K % 8 == 0 && qw->group % WL_TILE_K == 0;
+}
+
+int32_t k_qlinear_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M, float *y_f32_dev,
+                       void *y_bf16_dev) {
+    if (!k_umma_supported(qw, M)) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "tcgen05 path: unsupported shape (K %% 8 != 0)");
+    if ((reinterpret_cast<uintptr_t>(x_bf16_dev) & 15u) != 0) DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "x must be 16-byte aligned");
+    switch (wl_container_bits(qw->bits)) {
+        case 2: return launch_umma_ntok<2>(ctx, qw, x_bf16_dev, M, y_f32_dev, y_bf16_dev);
+        case 4: return launch_umma_ntok<4>(ctx, qw, x_bf16_dev, M, y_f32_dev, y_bf16_dev);
+        default: return launch_umma_ntok<8>(ctx, qw, x_bf16_dev, M, y_f32_dev, y_bf16_dev);
+    }
 }

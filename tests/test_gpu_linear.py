@@ -30,8 +30,13 @@ def O():
 
 
 def beq(a, b):
+    """bit-for-bit f32 equality; NaNs must sit at the same places (their payload bits are not
+    part of the reference's semantics: x86 and the GPU produce different default NaNs)."""
     a, b = np.asarray(a, F), np.asarray(b, F)
-    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if a.shape != b.shape:
+        return False
+    na, nb = np.isnan(a), np.isnan(b)
+    return bool(np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb]))
 
 
 def make_w(rng, K, N, std=0.02):

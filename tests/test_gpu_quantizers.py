@@ -28,8 +28,13 @@ def O():
 
 
 def beq(a, b):
+    """bit-for-bit f32 equality; NaNs must sit at the same places (their payload bits are not
+    part of the reference's semantics: x86 and the GPU produce different default NaNs)."""
     a, b = np.asarray(a, F), np.asarray(b, F)
-    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if a.shape != b.shape:
+        return False
+    na, nb = np.isnan(a), np.isnan(b)
+    return bool(np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb]))
 
 
 def edge_cases(rng):
@@ -351,7 +356,8 @@ def test_kv_full_row_size_against_torch_restatement(ctx, bits):
     ctx.sync()
     mn, mx = x.min(dim=1).values, x.max(dim=1).values
     levels = float((1 << bits) - 1)
-    s_ref = (mx - mn) / levels
+    # tensor divisors everywhere: torch turns `tensor / python_scalar` into a multiply by the reciprocal
+    s_ref = (mx - mn) / torch.full_like(mx, levels)
     assert torch.equal(scales, s_ref) and torch.equal(zps, mn)
     q_ref = torch.clamp((x - mn[:, None]) / s_ref[:, None], 0.0, levels).trunc().to(torch.uint8)
     if bits == 8:
@@ -377,11 +383,11 @@ def test_tensor_quantize_large_against_torch_restatement(ctx):
     ctx.sync()
     mn, mx = x.min(), x.max()
     qmax = float((1 << bits) - 1)
-    scale = (mx - mn) / qmax
+    scale = (mx - mn) / torch.full_like(mx, qmax)      # true division (see above)
     zp = _torch_round_half_away(torch.clamp(0.0 - mn / scale, 0.0, qmax))
     assert torch.equal(params[0], scale) and torch.equal(params[1], zp)
     assert torch.equal(params[2], mn) and torch.equal(params[3], mx)
-    q = torch.clamp(_torch_round_half_away(x / scale + zp), 0, qmax).to(torch.uint8)
+    q = torch.clamp(_torch_round_half_away(x / scale.expand_as(x) + zp), 0, qmax).to(torch.uint8)
     assert torch.equal(codes, q[0::2] | (q[1::2] << 4))
     del q
     out = torch.empty_like(x)
