@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric on the B200-native path, next to the reference's CPU path.
+
+Default workload (BASELINE.json configs[2]): one denoising step of a synthetic 1B-class 4-bit model
+(120 quantized linears `x·W+b`, group 128), 256-token canvas x batch 32 = 8192 tokens, on one B200.
+  step  = DiffusionModel::forward through the stack (tcgen05 dequant-GEMM) + p_sample
+  value = denoise steps/s, inputs resident in HBM (CUDA events on the launching stream)
+  e2e   = the same step through the host-buffer C ABI call (dllm_denoise_step): x and noise copied
+          H2D from pinned memory and x_prev copied D2H inside the timed region, every step
+N > 1 (torchrun): independent denoising batches, one replica per GPU (data parallel, weak scaling,
+no data-path collective); `--parallelism tp` runs the tensor-parallel 7B-class config instead.
+
+Other workloads (not the driver's line): --workload gemv | kv   (BASELINE.json configs[1] / [4]).
+`--impl reference` times the oracle port of the reference's CPU path on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "diffusion-llm-rs_b200"))
+
+MODELS = {
+    # name: (hidden H, ffn F, layers L).  Per layer: 4 x [H,H], [H,F], [F,H]  
+    "1b": (2048, 8192, 20),       # 20 * (4*2048^2 + 2*2048*8192) = 1.007 G linear params
+    "7b": (4096, 11008, 32),      # 32 * (4*4096^2 + 2*4096*11008) = 5.03 G linear params
+    "tiny": (256, 512, 2),
+}
+BATCH, CANVAS = 32, 256
+
+
+def layer_shapes(name):
+    H, F, L = MODELS[name]
+    per = [(H, H)] * 4 + [(H, F), (F, H)]
+    return H, per * L
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, timed on the host cores on a bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_denoise_step_seconds(model, threads, sample_tokens):
+    """One denoise step = for every linear: dequantize_tensor (quantization.rs:81-85) + x.dot(W)+b
+    (lib.rs:812), then p_sample (lib.rs:1152-1215).  Times one linear of each distinct shape on
+    `sample_tokens` tokens and scales the matmul part to the 8192-token canvas x batch."""
+    import numpy as np
+    from oracle import pyoracle as O
+    H, shapes = layer_shapes(model)
+    tokens = BATCH * CANVAS
+    rng = np.random.default_rng(42)
+    total, detail = 0.0, []
+    for shp in sorted(set(shapes)):
+        K, N = shp
+        cnt = shapes.count(shp)
+        codes = rng.integers(0, 16, (K, N)).astype(np.uint8)
+        scales = np.full((K // 128, N), 0.01, np.float32)
+        zps = np.full((K // 128, N), 8.0, np.float32)
+        x = rng.standard_normal((sample_tokens, K)).astype(np.float32)
+        t0 = time.perf_counter()
+        w = O.dequantize_weight_grouped(codes, scales, zps, 128)
+        t1 = time.perf_counter()
+        O.linear_f32(x, w, None, threads=threads)
+        t2 = time.perf_counter()
+        est = cnt * ((t1 - t0) + (t2 - t1) * tokens / sample_tokens)
+        total += est
+        detail.append(f"{K}x{N}:dq{(t1 - t0) * 1e3:.0f}ms,mm{(t2 - t1) * 1e3:.0f}ms")
+    feat = CANVAS * H
+    xs = rng.standard_normal((BATCH, feat)).astype(np.float32)
+    betas = O.beta_schedule(O.BETA_LINEAR, 1000)
+    t0 = time.perf_counter()
+    O.p_sample(xs, xs, xs, np.full(BATCH, 500), betas, True)
+    total += time.perf_counter() - t0
+    return total, ";".join(detail)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 64
+    t_all = []
+    for i in range(args.warmup + args.steps):
+        secs, detail = cpu_denoise_step_seconds(args.model, threads, sample)
+        if i >= args.warmup:
+            t_all.append(secs)
+    secs = sum(t_all) / len(t_all)
+    val = 1.0 / secs
+    sample_desc = (f"oracle port (C, -O2, no FMA): per step one linear of each distinct shape on {sample} of "
+                   f"{BATCH * CANVAS} tokens ({detail}), matmul scaled x{BATCH * CANVAS // sample}, + full p_sample; "
+                   f"{threads} threads over output columns")
+    print(json.dumps({
+        "impl": "reference", "metric": "denoise_steps_per_sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(args, world):
+    H, shapes = layer_shapes(args.model)
+    params = sum(k * n for k, n in shapes)
+    return {"workload": f"diffuse-llm-rs single denoising step, synthetic {args.model.upper()}-class model "
+                        f"({len(shapes)} quantized linears, {params / 1e9:.2f} G params), 4-bit weights group 128, "
+                        f"{CANVAS}-token canvas, batch {BATCH}, single B200 (BASELINE.json configs[2])",
+            "hidden": H, "tokens_per_step": BATCH * CANVAS, "bits": 4, "group_size": 128,
+            "parallelism": "single" if world == 1 else (f"dp{world}" if args.parallelism == "dp" else f"tp{world}"),
+            "l2": "working set (0.5 GB packed weights + 2x67 MB activations per linear) exceeds the 126 MB L2",
+            "seed": 42}
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import dllm_b200
+    from dllm_b200 import QWeight, _lib as L
+    from dllm_b200.diffuse_llm import DiffusionConfig, QuantizedDiffusionModel
+    import ctypes as C
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    ctx = dllm_b200.Context(local_rank, stream=stream.cuda_stream)   # raises without an sm_100 GPU
+    H, shapes = layer_shapes(args.model)
+    feat, tokens = CANVAS * H, BATCH * CANVAS
+    gen = torch.Generator(device="cuda").manual_seed(42 + rank)
+
+    # synthetic weights N(0, 1/K) (unit gain through the stack; the reference's init is N(0,1)*0.02,
+    # lib.rs:792-796), quantized on the device with quantizer B per group of 128, zero bias (:798)
+    layers = []
+    for (K, N) in shapes:
+        w = torch.randn(K, N, device="cuda", generator=gen) * (1.0 / K ** 0.5)
+        torch.cuda.synchronize()
+        layers.append(QWeight.quantize_dev(ctx, w.data_ptr(), K, N, 4, 128))
+        ctx.sync()
+        del w
+    cfg = DiffusionConfig(num_timesteps=1000, hidden_size=H, use_kv_cache=False)
+    model = QuantizedDiffusionModel(layers, H, cfg, ctx, dllm_b200.PATH_AUTO)
+
+    x = torch.randn(BATCH, feat, device="cuda", generator=gen)
+    zs = [torch.randn(BATCH, feat, device="cuda", generator=gen) for _ in range(4)]
+    torch.cuda.synchronize()
+
+    def step(i):
+        t = 999 - (i % 999)
+        model.denoise_step_dev(x.data_ptr(), zs[i % 4].data_ptr(), t, BATCH, feat)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-in-HBM timing ----
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches
+    ctx._ck(ctx._lib.dllm_profile_begin(ctx.h))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+        e1.record(stream)
+    e1.synchronize()
+    barrier()
+    secs = e0.elapsed_time(e1) * 1e-3
+    nl, ms, fl, by = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
+    ctx._ck(ctx._lib.dllm_profile_end(ctx.h, C.byref(nl), C.byref(ms), C.byref(fl), C.byref(by)))
+    launches = ctx.launches - launches0
+    clocks = sampler.summary()
+    finite = bool(torch.isfinite(x).all())
+
+    # ---- end to end through the host-buffer C ABI call ----
+    xh = torch.randn(BATCH, feat).pin_memory()
+    zh = torch.randn(BATCH, feat).pin_memory()
+    e2e_steps = max(2, min(args.steps, 10))
+    for i in range(2):
+        ctx._ck(ctx._lib.dllm_denoise_step(ctx.h, model.h, xh.data_ptr(), zh.data_ptr(), 999 - i, BATCH, feat, 1, 0))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ctx._ck(ctx._lib.dllm_denoise_step(ctx.h, model.h, xh.data_ptr(), zh.data_ptr(), 990 - i, BATCH, feat, 1, 0))
+    e2e_secs = time.perf_counter() - t0     # the call synchronises before returning
+
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([secs, e2e_secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        secs, e2e_secs = float(tt[0]), float(tt[1])
+    value = world * args.steps / secs
+    e2e_value = world * e2e_steps / e2e_secs
+
+    if rank == 0:
+        pk, src = peaks()
+        achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        line = {
+            "metric": "denoise_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(args, world),
+            "tokens_per_sec": value * tokens,
+            "model_tflops": 2.0 * tokens * sum(k * n for k, n in shapes) * value / world / 1e12,
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 2 * BATCH * feat * 4,
+                    "d2h_bytes_per_step": BATCH * feat * 4, "steps": e2e_steps,
+                    "api": "dllm_denoise_step (host buffers, pinned)"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "umma_qlinear_kernel<4,128> (tcgen05 dequant-GEMM)", "bound": "tensor",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "launches": int(nl.value), "kernel_ms_per_step": ms.value / args.steps,
+                         "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                         "algorithmic_GBps": by.value / (ms.value * 1e-3) / 1e9 if ms.value > 0 else 0.0},
+            "clocks": clocks, "output_finite": finite,
+        }
+        if not args.no_cpu:
+            secs_cpu, detail = cpu_denoise_step_seconds(args.model, 1, 32)
+            line["cpu_baseline"] = {
+                "value": 1.0 / secs_cpu, "unit": "steps/s", "cores": 1, "kind": "port",
+                "sample": f"oracle port, 1 thread (the reference is serial): one linear of each distinct shape on 32 of "
+                          f"{tokens} tokens ({detail}), matmul scaled x{tokens // 32}, + full p_sample"}
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="1b", choices=sorted(MODELS))
+    ap.add_argument("--parallelism", default="dp", choices=["dp", "tp"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

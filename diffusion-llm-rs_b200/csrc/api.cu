@@ -90,6 +90,7 @@ void dllm_ctx_destroy(dllm_ctx *ctx) {
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->d_params) cudaFree(ctx->d_params);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
+    for (auto e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -103,6 +104,33 @@ void *dllm_ctx_stream(dllm_ctx *ctx) { return ctx ? (void *)ctx->stream : nullpt
 const char *dllm_last_error(const dllm_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 uint64_t dllm_launch_count(const dllm_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int32_t dllm_sm_count(const dllm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+int32_t dllm_profile_begin(dllm_ctx *ctx) {
+    CTX_CHECK(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof_on = true;
+    ctx->prof_n = 0;
+    ctx->prof_flops = ctx->prof_bytes = 0.0;
+    return DLLM_OK;
+}
+
+int32_t dllm_profile_end(dllm_ctx *ctx, uint64_t *n_launches, double *total_ms, double *total_flops,
+                         double *total_bytes) {
+    CTX_CHECK(ctx);
+    ctx->prof_on = false;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0.0;
+    for (size_t i = 0; i < ctx->prof_n; ++i) {
+        float t = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        ms += t;
+    }
+    if (n_launches) *n_launches = ctx->prof_n;
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = ctx->prof_flops;
+    if (total_bytes) *total_bytes = ctx->prof_bytes;
+    return DLLM_OK;
+}
 
 int32_t dllm_malloc(dllm_ctx *ctx, size_t bytes, void **dptr) {
     CTX_CHECK(ctx);
@@ -967,6 +995,21 @@ int32_t dllm_denoise_step_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, const 
     const int row = (int)(t < m->T - 1 ? t : m->T - 1);
     return k_p_sample(ctx, x_dev, (const float *)dpred, t > 0 ? z_dev : nullptr, m->d_coef_table[guard_t0 ? 1 : 0],
                       nullptr, row, batch, feat, x_dev);
+}
+
+int32_t dllm_denoise_step(dllm_ctx *ctx, dllm_model *m, float *x, const float *z, size_t t, size_t batch, size_t feat,
+                          int32_t guard_t0, int32_t path) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    const size_t n = batch * feat;
+    if (n == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x, DLLM_ERR_NULL, "null pointer");
+    void *dx, *dz = nullptr;
+    DLLM_TRY(stage_in(ctx, 4, x, n * sizeof(float), &dx));
+    if (z && t > 0) DLLM_TRY(stage_in(ctx, 6, z, n * sizeof(float), &dz));
+    DLLM_TRY(dllm_denoise_step_dev(ctx, m, (float *)dx, (const float *)dz, t, batch, feat, guard_t0, path));
+    DLLM_TRY(copy_out(ctx, x, dx, n * sizeof(float)));
+    return sync(ctx);
 }
 
 int32_t dllm_sample(dllm_ctx *ctx, dllm_model *m, const float *x0, const float *noises, size_t batch, size_t feat,

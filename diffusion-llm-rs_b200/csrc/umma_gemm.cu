@@ -440,8 +440,27 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
         attr_set = true;
     }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->prof_on) {   // bracket this launch with events on the launching stream
+        while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) {
+            cudaEvent_t e;
+            CUDA_TRY(ctx, cudaEventCreate(&e));
+            ctx->prof_ev.push_back(e);
+        }
+        ev0 = ctx->prof_ev[2 * ctx->prof_n];
+        ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
+        CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
     umma_qlinear_kernel<CB, NTOK><<<grid, kNumThreads, SL::kTotal, ctx->stream>>>(tmap, a);
     LAUNCH_CHECK(ctx);
+    if (ev1) {
+        CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
+        ctx->prof_n++;
+        ctx->prof_flops += 2.0 * (double)M * (double)qw->K * (double)qw->N;
+        // algorithmic bytes: packed codes + (scale, zp) per group and column + bf16 x + output
+        ctx->prof_bytes += (double)qw->K * qw->N * qw->bits / 8.0 + (double)(qw->K / qw->group) * qw->N * 8.0 +
+                           2.0 * M * qw->K + (y_f32 ? 4.0 : 0.0) * M * qw->N + (y_bf16 ? 2.0 : 0.0) * M * qw->N;
+    }
     if (splits > 1) {
         const size_t total = M * qw->N;
         umma_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(

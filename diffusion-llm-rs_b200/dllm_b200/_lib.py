@@ -82,6 +82,9 @@ SIGNATURES = {
     "dllm_last_error": (C.c_char_p, [c_vp]),
     "dllm_launch_count": (C.c_uint64, [c_vp]),
     "dllm_sm_count": (C.c_int32, [c_vp]),
+    "dllm_profile_begin": (C.c_int32, [c_vp]),
+    "dllm_profile_end": (C.c_int32, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]),
     "dllm_malloc": (C.c_int32, [c_vp, c_sz, C.POINTER(c_vp)]),
     "dllm_free": (C.c_int32, [c_vp, c_vp]),
     "dllm_memcpy_h2d": (C.c_int32, [c_vp, c_vp, c_vp, c_sz]),
@@ -132,6 +135,7 @@ SIGNATURES = {
     "dllm_beta_schedule": (C.c_int32, [C.c_int32, c_sz, C.c_float, C.c_float, c_vp]),
     "dllm_p_sample": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, C.c_int32, c_vp]),
     "dllm_denoise_step_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, C.c_int32]),
+    "dllm_denoise_step": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, C.c_int32]),
     "dllm_sample": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, C.c_int32, c_vp]),
     "dllm_progressive_bits": (C.c_uint8, [c_sz, c_sz, C.c_uint8, C.c_uint8, C.POINTER(C.c_int32)]),
     "dllm_kv_quantize": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_uint8, C.c_int32, C.POINTER(c_vp)]),

@@ -88,6 +88,13 @@ DLLM_API const char *dllm_last_error(const dllm_ctx *ctx);
 DLLM_API uint64_t dllm_launch_count(const dllm_ctx *ctx);
 DLLM_API int32_t dllm_sm_count(const dllm_ctx *ctx);
 
+/* per-launch CUDA-event timing of the dominant (tcgen05 linear) kernel on the context's stream.
+ * begin() arms it; end() synchronises and returns the number of bracketed launches, their summed
+ * duration, and the algorithmic flops / bytes they covered (SURVEY.md §8d formulas). */
+DLLM_API int32_t dllm_profile_begin(dllm_ctx *ctx);
+DLLM_API int32_t dllm_profile_end(dllm_ctx *ctx, uint64_t *n_launches, double *total_ms, double *total_flops,
+                                  double *total_bytes);
+
 /* device / pinned-host memory helpers for callers without a CUDA runtime binding */
 DLLM_API int32_t dllm_malloc(dllm_ctx *ctx, size_t bytes, void **dptr);
 DLLM_API int32_t dllm_free(dllm_ctx *ctx, void *dptr);
@@ -239,6 +246,10 @@ DLLM_API int32_t dllm_p_sample(dllm_ctx *ctx, dllm_model *m, const float *x_t, c
 DLLM_API int32_t dllm_denoise_step_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, const float *z_dev,
                                        size_t t, size_t batch, size_t feat, int32_t guard_t0,
                                        int32_t path);
+/* the same step with HOST buffers: x (in/out) and z are copied in, x_prev is copied out (one iteration
+ * of the loop body at lib.rs:924-925 as seen by a host caller) */
+DLLM_API int32_t dllm_denoise_step(dllm_ctx *ctx, dllm_model *m, float *x, const float *z, size_t t, size_t batch,
+                                   size_t feat, int32_t guard_t0, int32_t path);
 /* DiffuseLLM::sample without cache, lib.rs:853-927.  x0: initial noise [batch, feat];
  * noises: [num_steps, batch, feat], slice t used at timestep t (slice 0 unused).  Host pointers. */
 DLLM_API int32_t dllm_sample(dllm_ctx *ctx, dllm_model *m, const float *x0, const float *noises,

@@ -251,18 +251,38 @@ int32_t orc_unpack(const uint8_t *packed, size_t n, uint8_t bits, uint8_t *codes
 /* diffuse-llm-rs/src/lib.rs:812  x.dot(&self.weights) + &self.bias.  The reference's sgemm
  * (matrixmultiply) is un-vendored: its accumulation order is unpinned.  This is the plain
  * sequential-k f32 form; orc_linear_f64 is the truth tolerances are stated against. */
+static void linear_f32_cols(const float *x, const float *w, const float *bias,
+                            size_t M, size_t K, size_t N, size_t n_begin, size_t n_end, float *y) {
+    /* Cache-blocked, but every y[m][n] is still the plain sequential-k f32 sum
+     * ((0 + x0*w0) + x1*w1) + ... with separate multiply and add, then + bias: blocking only
+     * changes which (m, n) are in flight, not the order of any single accumulation. */
+    enum { MB = 8, NB = 128 };
+    float acc[MB][NB];
+    for (size_t n0 = n_begin; n0 < n_end; n0 += NB) {
+        const size_t nb = n_end - n0 < NB ? n_end - n0 : NB;
+        for (size_t m0 = 0; m0 < M; m0 += MB) {
+            const size_t mb = M - m0 < MB ? M - m0 : MB;
+            for (size_t mi = 0; mi < mb; ++mi)
+                for (size_t j = 0; j < nb; ++j) acc[mi][j] = 0.0f;
+            for (size_t k = 0; k < K; ++k) {
+                const float *wr = w + k * N + n0;
+                for (size_t mi = 0; mi < mb; ++mi) {
+                    const float xv = x[(m0 + mi) * K + k];
+                    float *a = acc[mi];
+                    for (size_t j = 0; j < nb; ++j) a[j] = a[j] + xv * wr[j];
+                }
+            }
+            for (size_t mi = 0; mi < mb; ++mi) {
+                float *yr = y + (m0 + mi) * N + n0;
+                for (size_t j = 0; j < nb; ++j) yr[j] = bias ? acc[mi][j] + bias[n0 + j] : acc[mi][j];
+            }
+        }
+    }
+}
+
 void orc_linear_f32(const float *x, const float *w, const float *bias,
                     size_t M, size_t K, size_t N, float *y) {
-    for (size_t m = 0; m < M; ++m) {
-        float *yr = y + m * N;
-        for (size_t nn = 0; nn < N; ++nn) yr[nn] = 0.0f;
-        for (size_t k = 0; k < K; ++k) {
-            const float xv = x[m * K + k];
-            const float *wr = w + k * N;
-            for (size_t nn = 0; nn < N; ++nn) yr[nn] = yr[nn] + xv * wr[nn];
-        }
-        if (bias) for (size_t nn = 0; nn < N; ++nn) yr[nn] = yr[nn] + bias[nn];
-    }
+    linear_f32_cols(x, w, bias, M, K, N, 0, N, y);
 }
 
 void orc_linear_f64(const float *x, const float *w, const float *bias,
@@ -279,23 +299,25 @@ void orc_linear_f64(const float *x, const float *w, const float *bias,
     }
 }
 
-struct lin_job { const float *x, *w, *bias; size_t m0, m1, K, N; float *y; };
+struct lin_job { const float *x, *w, *bias; size_t M, K, N, n0, n1; float *y; };
 static void *lin_worker(void *p) {
     struct lin_job *j = (struct lin_job *)p;
-    if (j->m1 > j->m0)
-        orc_linear_f32(j->x + j->m0 * j->K, j->w, j->bias, j->m1 - j->m0, j->K, j->N,
-                       j->y + j->m0 * j->N);
+    if (j->n1 > j->n0) linear_f32_cols(j->x, j->w, j->bias, j->M, j->K, j->N, j->n0, j->n1, j->y);
     return NULL;
 }
+/* threads split the OUTPUT COLUMNS (each streams its own panel of W); every y[m][n] keeps the
+ * same sequential-k sum, so the result is bit-identical to orc_linear_f32 */
 void orc_linear_f32_mt(const float *x, const float *w, const float *bias,
                        size_t M, size_t K, size_t N, float *y, int threads) {
     if (threads < 1) threads = 1;
-    if ((size_t)threads > M) threads = (int)(M ? M : 1);
+    size_t chunks = (N + 127) / 128;
+    if ((size_t)threads > chunks) threads = (int)(chunks ? chunks : 1);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
     struct lin_job *jobs = (struct lin_job *)malloc(sizeof(struct lin_job) * (size_t)threads);
     for (int t = 0; t < threads; ++t) {
-        jobs[t] = (struct lin_job){x, w, bias, M * (size_t)t / (size_t)threads,
-                                   M * (size_t)(t + 1) / (size_t)threads, K, N, y};
+        size_t c0 = chunks * (size_t)t / (size_t)threads, c1 = chunks * (size_t)(t + 1) / (size_t)threads;
+        size_t n0 = c0 * 128, n1 = c1 * 128 < N ? c1 * 128 : N;
+        jobs[t] = (struct lin_job){x, w, bias, M, K, N, n0, n1, y};
         pthread_create(&th[t], NULL, lin_worker, &jobs[t]);
     }
     for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);

@@ -98,7 +98,7 @@ void orc_linear_f32(const float *x, const float *w, const float *bias,
                     size_t M, size_t K, size_t N, float *y);   /* sequential-k f32 accumulate */
 void orc_linear_f64(const float *x, const float *w, const float *bias,
                     size_t M, size_t K, size_t N, double *y);  /* f64-accumulated truth */
-/* the same, multi-threaded over output rows (NOT reference behaviour; CPU-baseline "all cores") */
+/* the same, multi-threaded over output columns (NOT reference behaviour; "all cores" CPU arm) */
 void orc_linear_f32_mt(const float *x, const float *w, const float *bias,
                        size_t M, size_t K, size_t N, float *y, int threads);
 /* exact integer path: sum_k (qw - zw)(qx - zx) -> int64 (SURVEY.md §7 "int8 path") */

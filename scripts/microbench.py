@@ -40,6 +40,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--umma", action="store_true", help="also time the tcgen05 path")
+    ap.add_argument("--dense", action="store_true", help="only the dense (M=8192) tcgen05 shapes")
+    ap.add_argument("--gemv-only", action="store_true")
     args = ap.parse_args()
     hbm, tf, src = peaks()
     stream = torch.cuda.Stream()
@@ -56,6 +58,21 @@ def main():
         print(json.dumps(r), flush=True)
         out.append(r)
 
+    if args.dense:
+        M = 8192
+        for (K, N) in ((2048, 2048), (2048, 8192), (8192, 2048), (4096, 4096), (4096, 11008), (11008, 4096)):
+            w = torch.randn(K, N, device="cuda") * 0.02
+            for bits in (4, 8, 2):
+                qw = QWeight.quantize_dev(ctx, w.data_ptr(), K, N, bits, 128)
+                xin = torch.randn(M, K, device="cuda")
+                y = torch.empty(M, N, device="cuda")
+                torch.cuda.synchronize()
+                t = time_fn(stream, lambda: qw.forward_dev(xin.data_ptr(), M, y.data_ptr(), PATH_UMMA), 10)
+                report(f"dense_umma_{bits}b(+f32->bf16 cast)", t, K * N * bits // 8 + 6 * M * K + 4 * M * N, 2.0 * M * K * N, K=K, N=N, M=M)
+                qw.close()
+        return
+    if args.gemv_only:
+        args.quick = args.quick
     # ---- KV quantizers: rows x 4096 f32 ----
     rows, dim = ((1 << 16) if not args.quick else (1 << 14)), 4096
     n = rows * dim
