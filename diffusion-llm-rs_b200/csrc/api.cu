@@ -518,6 +518,7 @@ static int32_t qweight_alloc(dllm_ctx *ctx, size_t K, size_t N, uint8_t bits, si
     cudaError_t e = cudaMalloc(&w->d_packed, w->n_tiles * w->k_blocks * w->tile_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&w->d_scales, G * Npad * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&w->d_zps, G * Npad * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_dqparams, G * Npad * sizeof(uint2));
     if (e != cudaSuccess) {
         cudaGetLastError();
         dllm_qweight_destroy(w);
@@ -555,6 +556,7 @@ int32_t dllm_qweight_quantize_dev(dllm_ctx *ctx, const float *w_dev, size_t K, s
         rc = k_wparams_grouped(ctx, w_dev, K, N, group, bits, w->d_scales, w->d_zps);
     }
     if (rc == DLLM_OK) rc = k_wpack_from_f32(ctx, w_dev, w);
+    if (rc == DLLM_OK) rc = k_wdq_params(ctx, w);
     if (rc == DLLM_OK) rc = qweight_set_bias(ctx, w, bias_dev, true);
     if (rc != DLLM_OK) { dllm_qweight_destroy(w); return rc; }
     *out = w;
@@ -602,6 +604,7 @@ int32_t dllm_qweight_from_codes(dllm_ctx *ctx, const uint8_t *codes, const float
                               cudaMemcpyHostToDevice, ctx->stream);
         }
         if ((rc = k_wpack_from_codes(ctx, (const uint8_t *)dc, w)) != DLLM_OK) break;
+        if ((rc = k_wdq_params(ctx, w)) != DLLM_OK) break;
         if ((rc = qweight_set_bias(ctx, w, bias, false)) != DLLM_OK) break;
         rc = sync(ctx);
     } while (0);
@@ -648,6 +651,7 @@ void dllm_qweight_destroy(dllm_qweight *w) {
     if (w->d_packed) cudaFree(w->d_packed);
     if (w->d_scales) cudaFree(w->d_scales);
     if (w->d_zps) cudaFree(w->d_zps);
+    if (w->d_dqparams) cudaFree(w->d_dqparams);
     if (w->d_bias) cudaFree(w->d_bias);
     delete w;
 }

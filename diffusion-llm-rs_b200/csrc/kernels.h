@@ -34,6 +34,8 @@ int32_t k_wparams_broadcast(dllm_ctx *ctx, const float *params_dev, size_t N, fl
 // quantize (from f32) or adopt (from u8 codes) into the tile-major packed layout of qw
 int32_t k_wpack_from_f32(dllm_ctx *ctx, const float *w_dev, dllm_qweight *qw);
 int32_t k_wpack_from_codes(dllm_ctx *ctx, const uint8_t *codes_dev, dllm_qweight *qw);
+// derive the packed dequant operands of the tcgen05 path from scales / zps (call after they are final)
+int32_t k_wdq_params(dllm_ctx *ctx, dllm_qweight *qw);
 int32_t k_wexport_codes(dllm_ctx *ctx, const dllm_qweight *qw, uint8_t *codes_dev);
 
 // ---- gemv_simt.cu ----

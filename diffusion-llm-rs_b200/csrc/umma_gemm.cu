@@ -12,12 +12,13 @@
 //   D: f32 accumulators in TMEM (double buffered), read back with tcgen05.ld by the epilogue warps.
 // tcgen05.mma.cta_group::1.kind::f16 with A from TMEM ("TS" form), M=128, N=NTOK, K=16.
 //
-// Warp roles (512 threads, one persistent CTA per SM):
-//   warp 0      TMA / bulk-copy producer (one elected lane)
+// Warp roles (one persistent CTA per SM, (8 + 4*NDQ) warps):
+//   warp 0      TMA / bulk-copy producer (one elected lane): x tile (TMA), packed weight tile and the
+//               tile's 128 (zero-point, scale) dequant operands (bulk copies) per stage
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 4-11  two dequant groups of 4 warps (warp%4 = TMEM lane quarter); group g takes the
-//               pipeline stages with stage%2 == g
-//   warps 12-15 epilogue: TMEM -> registers -> (+bias) -> global (f32 and/or bf16), coalesced
+//   warps 4..   NDQ dequant groups of 4 warps (warp%4 = TMEM lane quarter); group g takes the
+//               pipeline stages with stage % NDQ == g
+//   last 4      epilogue: TMEM -> registers -> (+bias) -> global (f32 and/or bf16), coalesced
 // Pipelines: full[s] (TMA bytes landed) -> afull[s] (A slot written to TMEM) -> MMA ->
 //   tcgen05.commit -> empty[s];  tmem_full[a] / tmem_empty[a] between MMA and epilogue.
 // Work items = (output tile, K segment); skinny shapes split K so that every SM streams weights
@@ -31,7 +32,10 @@
 
 namespace {
 
-constexpr int kNumThreads = 512;
+#ifndef DLLM_NDQ
+#define DLLM_NDQ 4
+#endif
+constexpr int kNDQ = DLLM_NDQ;       // dequant groups of 4 warps
 constexpr int kStages = 8;
 constexpr int kAccStages = 2;
 constexpr int kACols = 32;            // TMEM columns of one A slot: 64 k of bf16 = 32 x 32-bit
@@ -142,15 +146,13 @@ __device__ __forceinline__ uint32_t bf2_sub_mul(uint32_t a, uint32_t zb, uint32_
     return *reinterpret_cast<uint32_t *>(&r);
 }
 
+// `zterm`/`s2` are the per-(group, column) operands prepared by wdq_params_kernel.
 template <int CB>
-__device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, float scale, float zp, uint32_t *out) {
+__device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, uint32_t zterm, uint32_t s2, uint32_t *out) {
     constexpr int CH = CB / 2;
-    __nv_bfloat162 sb = __float2bfloat162_rn(scale);
-    const uint32_t s2 = *reinterpret_cast<uint32_t *>(&sb);
     if (CB == 4 || CB == 2) {
-        // magic: 0x4300 | q is the bf16 number 128 + q (exact for q < 128); subtract bf16(128 + zp)
-        __nv_bfloat162 zb2 = __float2bfloat162_rn(128.0f + zp);
-        const uint32_t zb = *reinterpret_cast<uint32_t *>(&zb2);
+        // magic: 0x4300 | q is the bf16 number 128 + q (exact for q < 128); subtract bf16x2(128 + zp)
+        const uint32_t zb = zterm;
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             const uint4 c = wpk[j * 128 + n_local];
@@ -170,6 +172,8 @@ __device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, fl
         }
     } else {
         // 8-bit: q and zp up to 255 — exact in f32, (q - zp) exact in bf16 after the subtraction
+        const float zp = __uint_as_float(zterm);
+        const __nv_bfloat162 sb = *reinterpret_cast<const __nv_bfloat162 *>(&s2);
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             const uint4 c = wpk[j * 128 + n_local];
@@ -193,7 +197,8 @@ __device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, fl
 
 struct UmmaArgs {
     const uint8_t *packed;
-    const float *scales, *zps, *bias;
+    const uint2 *dqparams;     // [G][Npad] {zero-point term, bf16x2 scale}
+    const float *bias;
     float *y_f32;              // final f32 output [M,N] (splits == 1) or null
     __nv_bfloat16 *y_bf16;     // final bf16 output [M,N] (splits == 1) or null
     float *partial;            // [splits][M][Npad] when splits > 1
@@ -204,15 +209,18 @@ template <int NTOK>
 struct SmemLayout {
     static constexpr int kXBytes = NTOK * 128;
     static constexpr int kWBytesMax = 8192;
-    static constexpr int kStageBytes = kXBytes + kWBytesMax;
+    static constexpr int kPBytes = 128 * 8;                  // dequant operands of the tile's 128 columns
+    static constexpr int kStageBytes = kXBytes + kWBytesMax + kPBytes;
     static constexpr int kBarOffset = kStages * kStageBytes;
     static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
 };
 
-template <int CB, int NTOK>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int CB, int NTOK, int NDQ>
+__global__ void __launch_bounds__((8 + 4 * NDQ) * 32, 1)
 umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
     using SL = SmemLayout<NTOK>;
+    static_assert(kStages % NDQ == 0, "a stage must always belong to the same dequant group");
+    constexpr int kEpiWarp0 = 4 + 4 * NDQ;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SL::kBarOffset);
@@ -248,13 +256,17 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 const uint32_t nt = tile % a.n_tiles, mt = tile / a.n_tiles;
                 const uint32_t kb0 = a.k_blocks * seg / a.splits, kb1 = a.k_blocks * (seg + 1) / a.splits;
                 const uint8_t *wsrc = a.packed + ((size_t)nt * a.k_blocks) * wbytes;
+                const uint2 *psrc = a.dqparams + (size_t)nt * 128;
+                uint32_t g = kb0 / a.group_kb, g_left = a.group_kb - (kb0 - g * a.group_kb);
                 for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     mbar_wait(empty + s, ph ^ 1);
                     uint8_t *stage = smem + s * SL::kStageBytes;
-                    mbar_arrive_expect_tx(full + s, SL::kXBytes + wbytes);
+                    mbar_arrive_expect_tx(full + s, SL::kXBytes + wbytes + SL::kPBytes);
                     tma_load_2d(stage, &tmap_x, full + s, (int)(kb * WL_TILE_K), (int)(mt * NTOK));
                     bulk_load(stage + SL::kXBytes, wsrc + (size_t)kb * wbytes, wbytes, full + s);
+                    bulk_load(stage + SL::kXBytes + SL::kWBytesMax, psrc + (size_t)g * a.Npad, SL::kPBytes, full + s);
+                    if (--g_left == 0) { ++g; g_left = a.group_kb; }
                 }
             }
         }
@@ -285,37 +297,37 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 umma_commit(tfull + acc);
             }
         }
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4 && warp < kEpiWarp0) {
         // ===================== dequant warps =====================
-        const int grp = (warp - 4) >> 2;          // 0 / 1
+        const uint32_t grp = (uint32_t)(warp - 4) >> 2;
         const int quarter = warp & 3;             // TMEM lanes [32*quarter, +32)
         const int n_local = quarter * 32 + lane;
-        uint32_t it = 0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0;
+        uint32_t it = 0;                          // global k-block counter of this CTA (same in every role)
         for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
             const uint32_t tile = w / a.splits, seg = w - tile * a.splits;
-            const uint32_t nt = tile % a.n_tiles;
             const uint32_t kb0 = a.k_blocks * seg / a.splits, kb1 = a.k_blocks * (seg + 1) / a.splits;
-            const float *sc = a.scales + (size_t)nt * 128 + n_local;
-            const float *zc = a.zps + (size_t)nt * 128 + n_local;
-            uint32_t cur_g = 0xffffffffu;
-            float scale = 0.f, zp = 0.f;
-            for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
-                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                if ((int)(s & 1) != grp) continue;
-                const uint32_t g = kb / a.group_kb;
-                if (g != cur_g) { scale = __ldg(sc + (size_t)g * a.Npad); zp = __ldg(zc + (size_t)g * a.Npad); cur_g = g; }
+            const uint32_t nkb = kb1 - kb0;
+            // first k-block of this item that falls on one of this group's stages
+            uint32_t j = (grp + NDQ - (it % NDQ)) % NDQ;
+            for (; j < nkb; j += NDQ) {
+                const uint32_t i2 = it + j;
+                const uint32_t s = i2 % kStages, ph = (i2 / kStages) & 1;
                 mbar_wait(full + s, ph);
-                const uint4 *wpk = reinterpret_cast<const uint4 *>(smem + s * SL::kStageBytes + SL::kXBytes);
+                const uint8_t *stage = smem + s * SL::kStageBytes;
+                const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + SL::kXBytes);
+                const uint2 prm = reinterpret_cast<const uint2 *>(stage + SL::kXBytes + SL::kWBytesMax)[n_local];
                 uint32_t vals[32];
-                dequant_kblock<CB>(wpk, n_local, scale, zp, vals);
-                tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0 + s * kACols, vals);
+                dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
+                tmem_st32(lane_addr + s * kACols, vals);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(afull + s);
             }
+            it += nkb;
         }
-    } else if (warp >= 12) {
+    } else if (warp >= kEpiWarp0) {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;
         uint32_t item = 0;
@@ -396,7 +408,7 @@ PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-template <int CB, int NTOK>
+template <int CB, int NTOK, int NDQ>
 int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, size_t M, float *y_f32, void *y_bf16) {
     using SL = SmemLayout<NTOK>;
     PFN_encodeTiled enc = get_encode_fn();
@@ -412,7 +424,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
 
     UmmaArgs a;
-    a.packed = qw->d_packed; a.scales = qw->d_scales; a.zps = qw->d_zps; a.bias = qw->d_bias;
+    a.packed = qw->d_packed; a.dqparams = qw->d_dqparams; a.bias = qw->d_bias;
     a.M = (uint32_t)M; a.N = (uint32_t)qw->N; a.Npad = (uint32_t)(qw->n_tiles * 128);
     a.k_blocks = (uint32_t)qw->k_blocks; a.n_tiles = (uint32_t)qw->n_tiles;
     a.m_tiles = (uint32_t)((M + NTOK - 1) / NTOK);
@@ -437,7 +449,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     const int grid = (int)(n_items < (uint32_t)ctx->sm_count ? n_items : (uint32_t)ctx->sm_count);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, NDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
         attr_set = true;
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -451,7 +463,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
         CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    umma_qlinear_kernel<CB, NTOK><<<grid, kNumThreads, SL::kTotal, ctx->stream>>>(tmap, a);
+    umma_qlinear_kernel<CB, NTOK, NDQ><<<grid, (8 + 4 * NDQ) * 32, SL::kTotal, ctx->stream>>>(tmap, a);
     LAUNCH_CHECK(ctx);
     if (ev1) {
         CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
@@ -472,10 +484,10 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
 
 template <int CB>
 int32_t launch_umma_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const void *x, size_t M, float *y_f32, void *y_bf16) {
-    if (M <= 16) return launch_umma<CB, 16>(ctx, qw, x, M, y_f32, y_bf16);
-    if (M <= 32) return launch_umma<CB, 32>(ctx, qw, x, M, y_f32, y_bf16);
-    if (M <= 64) return launch_umma<CB, 64>(ctx, qw, x, M, y_f32, y_bf16);
-    return launch_umma<CB, 128>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 16) return launch_umma<CB, 16, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 32) return launch_umma<CB, 32, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 64) return launch_umma<CB, 64, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    return launch_umma<CB, 128, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
 }
 
 }  // namespace

@@ -74,6 +74,28 @@ wpack_kernel(const SRC *__restrict__ src, size_t K, size_t N, size_t Npad, size_
     }
 }
 
+// per (group, column): the two 32-bit operands the tcgen05 dequant needs, so that its inner loop is
+// one LDS.64 instead of two dependent global loads and two conversions.
+//   2/4-bit: x = bf16x2(128 + zp)   (subtracted from the magic-number form 128 + q, exact)
+//   8-bit  : x = f32 bits of zp
+//   y = bf16x2(scale)
+__global__ void wdq_params_kernel(const float *__restrict__ scales, const float *__restrict__ zps, size_t n, int cb,
+                                  uint2 *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float s = scales[i], z = zps[i];
+    __nv_bfloat162 sb = __float2bfloat162_rn(s);
+    uint2 o;
+    o.y = *reinterpret_cast<uint32_t *>(&sb);
+    if (cb == 8) {
+        o.x = __float_as_uint(z);
+    } else {
+        __nv_bfloat162 zb = __float2bfloat162_rn(128.0f + z);
+        o.x = *reinterpret_cast<uint32_t *>(&zb);
+    }
+    out[i] = o;
+}
+
 template <int CB>
 __global__ void __launch_bounds__(128)
 wexport_kernel(const uint8_t *__restrict__ packed, size_t K, size_t N, size_t k_blocks,
@@ -134,6 +156,15 @@ static int32_t wpack_any(dllm_ctx *ctx, const SRC *src, dllm_qweight *qw) {
 
 int32_t k_wpack_from_f32(dllm_ctx *ctx, const float *w_dev, dllm_qweight *qw) { return wpack_any<float>(ctx, w_dev, qw); }
 int32_t k_wpack_from_codes(dllm_ctx *ctx, const uint8_t *codes_dev, dllm_qweight *qw) { return wpack_any<uint8_t>(ctx, codes_dev, qw); }
+
+int32_t k_wdq_params(dllm_ctx *ctx, dllm_qweight *qw) {
+    const size_t G = qw->per_tensor ? 1 : qw->K / qw->group;
+    const size_t n = G * qw->n_tiles * 128;
+    wdq_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(qw->d_scales, qw->d_zps, n,
+                                                                            wl_container_bits(qw->bits), qw->d_dqparams);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
 
 int32_t k_wexport_codes(dllm_ctx *ctx, const dllm_qweight *qw, uint8_t *codes_dev) {
     const int cb = wl_container_bits(qw->bits);
