@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "diffusion-llm-rs_b200"))
 MODELS = {
     # name: (hidden H, ffn F, layers L).  Per layer: 4 x [H,H], [H,F], [F,H]  
     "1b": (2048, 8192, 20),       # 20 * (4*2048^2 + 2*2048*8192) = 1.007 G linear params
-    "7b": (4096, 11008, 32),      # 32 * (4*4096^2 + 2*4096*11008) = 5.03 G linear params
+    "7b": (4096, 14336, 32),      # 32 * (4*4096^2 + 2*4096*14336) = 5.91 G linear params; F/8 = 14*128
     "tiny": (256, 512, 2),
 }
 BATCH, CANVAS = 32, 256
@@ -184,15 +184,29 @@ def run_ours(args, rank, world, local_rank):
 
     # synthetic weights N(0, 1/K) (unit gain through the stack; the reference's init is N(0,1)*0.02,
     # lib.rs:792-796), quantized on the device with quantizer B per group of 128, zero bias (:798)
+    tp = world > 1 and args.parallelism == "tp"
+    from dllm_b200 import parallel as PAR
+    plan = PAR.tp_plan(shapes, world) if tp else [PAR.REPLICATED] * len(shapes)
+    wgen = torch.Generator(device="cuda").manual_seed(42 if tp else 42 + rank)   # TP: same full weights on every rank
     layers = []
-    for (K, N) in shapes:
-        w = torch.randn(K, N, device="cuda", generator=gen) * (1.0 / K ** 0.5)
+    for li, (K, N) in enumerate(shapes):
+        w = torch.randn(K, N, device="cuda", generator=wgen) * (1.0 / K ** 0.5)
+        if plan[li] == PAR.COLUMN:
+            w = w[:, N * rank // world: N * (rank + 1) // world].contiguous()
+        elif plan[li] == PAR.ROW:
+            w = w[K * rank // world: K * (rank + 1) // world, :].contiguous()
         torch.cuda.synchronize()
-        layers.append(QWeight.quantize_dev(ctx, w.data_ptr(), K, N, 4, 128))
+        layers.append(QWeight.quantize_dev(ctx, w.data_ptr(), w.shape[0], w.shape[1], 4, 128))
         ctx.sync()
         del w
     cfg = DiffusionConfig(num_timesteps=1000, hidden_size=H, use_kv_cache=False)
     model = QuantizedDiffusionModel(layers, H, cfg, ctx, dllm_b200.PATH_AUTO)
+    tpg = None
+    if tp:
+        tpg = PAR.TensorParallelGroup(ctx, rank, world)
+        tpg.init_nccl()
+        tpg.set_plan(model, plan)
+        gen = torch.Generator(device="cuda").manual_seed(4242)                 # TP: replicated activations
 
     x = torch.randn(BATCH, feat, device="cuda", generator=gen)
     zs = [torch.randn(BATCH, feat, device="cuda", generator=gen) for _ in range(4)]
@@ -249,8 +263,9 @@ def run_ours(args, rank, world, local_rank):
         tt = torch.tensor([secs, e2e_secs], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         secs, e2e_secs = float(tt[0]), float(tt[1])
-    value = world * args.steps / secs
-    e2e_value = world * e2e_steps / e2e_secs
+    # DP: every rank ran its own batch (weak scaling); TP: all ranks share one batch (strong scaling)
+    value = (1 if tp else world) * args.steps / secs
+    e2e_value = (1 if tp else world) * e2e_steps / e2e_secs
 
     if rank == 0:
         pk, src = peaks()
@@ -259,10 +274,10 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": "denoise_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args, world),
             "tokens_per_sec": value * tokens,
-            "model_tflops": 2.0 * tokens * sum(k * n for k, n in shapes) * value / world / 1e12,
+            "model_tflops_per_gpu": 2.0 * tokens * sum(k * n for k, n in shapes) * value / world / 1e12,
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 2 * BATCH * feat * 4,
                     "d2h_bytes_per_step": BATCH * feat * 4, "steps": e2e_steps,
                     "api": "dllm_denoise_step (host buffers, pinned)"},
@@ -281,6 +296,8 @@ def run_ours(args, rank, world, local_rank):
                 "sample": f"oracle port, 1 thread (the reference is serial): one linear of each distinct shape on 32 of "
                           f"{tokens} tokens ({detail}), matmul scaled x{tokens // 32}, + full p_sample"}
         print(json.dumps(line), flush=True)
+    if tpg is not None:
+        tpg.close()
     model.close()
     if world > 1:
         import torch.distributed as dist

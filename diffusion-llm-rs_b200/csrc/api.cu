@@ -811,37 +811,39 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
         }
         return DLLM_OK;
     }
-    // f32 activations between layers (SIMT path, or tensor-parallel stacks with NCCL at the boundaries)
-    DLLM_TRY(ensure_buf(ctx, ctx->act[0], tokens * maxw * 4 * (size_t)ctx->tp_world));
-    DLLM_TRY(ensure_buf(ctx, ctx->act[1], tokens * maxw * 4 * (size_t)ctx->tp_world));
+    // General path: f32 activations at the layer boundaries (SIMT layers, and tensor-parallel stacks
+    // where the NCCL collective sits at the boundary).  Width bookkeeping:
+    //   COLUMN (1): this rank holds W[:, N/p] -> y is the [tokens, N/p] shard; a following ROW layer
+    //               consumes it directly (its K shard), anything else needs the all-gather;
+    //   ROW    (2): input is the K shard, y is a partial sum over K -> all-reduce -> full [tokens, N].
+    const size_t wmul = (size_t)(ctx->tp_world > 1 ? ctx->tp_world : 1);
+    DLLM_TRY(ensure_buf(ctx, ctx->act[0], tokens * maxw * 4 * wmul));
+    DLLM_TRY(ensure_buf(ctx, ctx->act[1], tokens * maxw * 4 * wmul));
     DLLM_TRY(ensure_buf(ctx, ctx->act[2], tokens * maxw * 2));
-    const float *cur = x_dev;
     float *bufs[2] = {(float *)ctx->act[0].p, (float *)ctx->act[1].p};
-    int flip = 0;
+    const float *cur = x_dev;
+    int next_buf = 0;
     for (size_t l = 0; l < L; ++l) {
         const bool last = l + 1 == L;
         dllm_qweight *w = m->layers[l];
         const int par = m->parallel[l];
-        float *dst = (last && par == 0) ? out_dev : bufs[flip];
-        const bool umma = path != DLLM_PATH_SIMT && k_umma_supported(w, tokens);
-        if (umma) {
+        const bool gather = par == 1 && (last || m->parallel[l + 1] != 2);
+        float *dst = (last && !gather) ? out_dev : bufs[next_buf];
+        if (path != DLLM_PATH_SIMT && k_umma_supported(w, tokens)) {
             DLLM_TRY(k_f32_to_bf16(ctx, cur, tokens * w->K, ctx->act[2].p));
             DLLM_TRY(k_qlinear_umma(ctx, w, ctx->act[2].p, tokens, dst, nullptr));
         } else {
             DLLM_TRY(k_qlinear_simt(ctx, w, cur, tokens, dst));
         }
-        if (par == 2) {           // row-parallel: partial sums over the K shards -> all-reduce
+        if (par == 2) {
             DLLM_TRY(tp_allreduce(ctx, dst, tokens * w->N));
-            if (last) { CUDA_TRY(ctx, cudaMemcpyAsync(out_dev, dst, tokens * w->N * 4, cudaMemcpyDeviceToDevice, ctx->stream)); }
-        } else if (par == 1 && (last || m->parallel[l + 1] != 2)) {
-            // column-parallel whose consumer needs the full width: all-gather the column shards
-            float *full = last ? out_dev : bufs[flip ^ 1];
+        } else if (gather) {
+            float *full = last ? out_dev : bufs[next_buf ^ 1];
             DLLM_TRY(tp_allgather_cols(ctx, dst, tokens, w->N, full));
             dst = full;
-            if (!last) flip ^= 1;
         }
         cur = dst;
-        flip ^= 1;
+        next_buf = (dst == bufs[0]) ? 1 : 0;
     }
     return DLLM_OK;
 }
