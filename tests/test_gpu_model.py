@@ -179,3 +179,15 @@ def test_sample_with_phase_aware_cache(ctx, O):
     cache = llm.kv_cache["c"]
     assert not cache.is_prefill_phase and cache.decode_quant_bits == O.progressive_bits(6, 0)[0]
     model.close()
+
+
+def test_cpp_host_mirror_harness():
+    """The C++ mirror of the reference interface (host/dllm.hpp) run as the reference's own unit tests."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "diffusion-llm-rs_b200", "host", "host_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "HOST_TEST_OK" in out.stdout, out.stdout + out.stderr
