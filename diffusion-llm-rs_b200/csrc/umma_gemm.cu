@@ -19,12 +19,17 @@
 //   warps 4..   NDQ dequant groups of 4 warps (warp%4 = TMEM lane quarter); group g takes the
 //               pipeline stages with stage % NDQ == g
 //   last 4      epilogue: TMEM -> registers -> (+bias) -> global (f32 and/or bf16), coalesced
-// Pipelines: full[s] (TMA bytes landed) -> afull[s] (A slot written to TMEM) -> MMA ->
-//   tcgen05.commit -> empty[s];  tmem_full[a] / tmem_empty[a] between MMA and epilogue.
-// Work items = (output tile, K segment); skinny shapes split K so that every SM streams weights
-// (partials reduced in a fixed order by a second tiny kernel: deterministic).
+// Two rings: shared-memory stages (deep: they cover the HBM latency; KBS k-blocks per stage) and
+//   TMEM A slots (shallow: they cover dequant -> MMA).  full[s] (TMA bytes landed) ->
+//   afull[a] (A slot written) -> MMA -> tcgen05.commit -> sempty[s] + aempty[a];
+//   tmem_full / tmem_empty between MMA and epilogue.
+// Scheduling: dense shapes take whole output tiles round-robin; skinny shapes use stream-K — every CTA
+//   gets the same number of contiguous k-block units, so all 148 SMs stream weights for the same
+//   time; tiles cut by a CTA boundary emit f32 partials that a tiny fix-up kernel sums in CTA order
+//   (deterministic, no atomics).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -36,9 +41,8 @@ namespace {
 #define DLLM_NDQ 4
 #endif
 constexpr int kNDQ = DLLM_NDQ;       // dequant groups of 4 warps
-constexpr int kStages = 8;
 constexpr int kAccStages = 2;
-constexpr int kACols = 32;            // TMEM columns of one A slot: 64 k of bf16 = 32 x 32-bit
+constexpr int kACols = 32;            // TMEM columns of one dequantized k-block: 64 k of bf16 = 32 x 32-bit
 constexpr int kTmemCols = 512;
 
 // ------------------------------------------------------------------------------------------
@@ -82,6 +86,18 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
 }
 
+// one lane of a fully converged warp (keeps the surrounding code warp-uniform so that descriptors and
+// addresses live in uniform registers: no per-instruction R2UR waterfall in the MMA / TMA issue loops)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
@@ -199,41 +215,107 @@ struct UmmaArgs {
     const uint8_t *packed;
     const uint2 *dqparams;     // [G][Npad] {zero-point term, bf16x2 scale}
     const float *bias;
-    float *y_f32;              // final f32 output [M,N] (splits == 1) or null
-    __nv_bfloat16 *y_bf16;     // final bf16 output [M,N] (splits == 1) or null
-    float *partial;            // [splits][M][Npad] when splits > 1
-    uint32_t M, N, Npad, k_blocks, n_tiles, m_tiles, splits, group_kb, tile_bytes;
+    float *y_f32;              // final f32 output [M,N] or null
+    __nv_bfloat16 *y_bf16;     // final bf16 output [M,N] or null
+    float *partial;            // stream-K partial tiles: [2 * grid][NTOK][128] f32
+    uint32_t M, N, Npad, k_blocks, n_tiles, m_tiles, group_kb;
+    uint32_t stream_k;         // 0: whole tiles round-robin; 1: contiguous unit ranges per CTA
+    long long *trace;          // dbg & 128: per-stage clock64 stamps of CTA 0: [role 0..5][256]
+    uint32_t dbg;              // timing experiments only (DLLM_UMMA_DBG): 1 skip MMAs, 2 skip dequant math, 4 skip TMEM stores
+    uint64_t units;            // n_tiles * m_tiles * k_blocks
 };
 
-template <int NTOK>
-struct SmemLayout {
-    static constexpr int kXBytes = NTOK * 128;
-    static constexpr int kWBytesMax = 8192;
-    static constexpr int kPBytes = 128 * 8;                  // dequant operands of the tile's 128 columns
-    static constexpr int kStageBytes = kXBytes + kWBytesMax + kPBytes;
+// One piece of work of a CTA: k-blocks [kb0, kb1) of output tile `tile`.
+#define TRACE(role, idx) do { if ((a.dbg & 128) && blockIdx.x == 0 && (idx) < 256) a.trace[(role) * 256 + (idx)] = clock64(); } while (0)
+
+struct Item {
+    uint32_t tile, kb0, kb1;
+    int32_t slot;              // -1: complete tile, written directly; else partial slot index
+};
+
+// Every warp role walks the same item sequence.
+struct ItemIter {
+    uint32_t stream_k, KB, tiles, cur_tile, first;
+    uint64_t u, u1;
+    __device__ ItemIter(const UmmaArgs &a) {
+        stream_k = a.stream_k; KB = a.k_blocks; tiles = a.n_tiles * a.m_tiles; first = 1;
+        if (stream_k) {
+            u = a.units * blockIdx.x / gridDim.x;
+            u1 = a.units * (blockIdx.x + 1) / gridDim.x;
+        } else {
+            cur_tile = blockIdx.x; u = u1 = 0;
+        }
+    }
+    __device__ bool next(Item &it) {
+        if (!stream_k) {
+            if (cur_tile >= tiles) return false;
+            it.tile = cur_tile; it.kb0 = 0; it.kb1 = KB; it.slot = -1;
+            cur_tile += gridDim.x;
+            return true;
+        }
+        if (u >= u1) return false;
+        it.tile = (uint32_t)(u / KB);
+        it.kb0 = (uint32_t)(u - (uint64_t)it.tile * KB);
+        const uint64_t left = u1 - u;
+        it.kb1 = (uint64_t)(KB - it.kb0) <= left ? KB : (uint32_t)(it.kb0 + left);
+        it.slot = (it.kb0 == 0 && it.kb1 == KB) ? -1 : (int32_t)(blockIdx.x * 2 + (first ? 0 : 1));
+        first = 0;
+        u += it.kb1 - it.kb0;
+        return true;
+    }
+};
+
+// Ring sizing.  Safety rule for the parity waits (verified by an exhaustive-interleaving model of the
+// protocol): the dequant group that owns stage `it` first waits for MMA(it - A) [the slot's previous
+// user], then for the stage's TMA bytes.  That wait is alias-free only if the barrier it tests cannot be
+// two phases behind, i.e. the number of distinct "slot free" barriers must be >= the number of dequant
+// groups -> kSlotBars = A * ceil(NDQ / A).  Dense tiles (NTOK >= 64) tie the two rings (S == A) so one
+// tcgen05.commit per stage frees both the smem stage and the TMEM slot.
+template <int CB, int NTOK, int KBS, int NDQ = 4>
+struct Cfg {
+    static constexpr int kXBytes = NTOK * 128;                       // one k-block of activations (bf16, SW128)
+    static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;   // one packed weight tile
+    static constexpr int kPBytes = 128 * 8;                          // dequant operands of 128 columns
+    static constexpr int kStageBytes = KBS * (kXBytes + kWBytes + kPBytes);
+    static constexpr int kSmemBudget = 220 * 1024;
+    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+    static constexpr int kSlotCols = KBS * kACols;
+    static constexpr int kSlotsRaw = (kTmemCols - kAccStages * NTOK) / kSlotCols;
+    static constexpr bool kTied = NTOK >= 64;
+    static constexpr int kTiedDepth = kStagesRaw < kSlotsRaw ? (kStagesRaw < 8 ? kStagesRaw : 8) : (kSlotsRaw < 8 ? kSlotsRaw : 8);
+    static constexpr int kStages = kTied ? kTiedDepth : (kStagesRaw > 24 ? 24 : kStagesRaw);   // smem ring depth
+    static constexpr int kSlots = kTied ? kTiedDepth : (kSlotsRaw > 8 ? 8 : kSlotsRaw);        // TMEM A ring depth
+    static constexpr int kSlotBars = kTied ? 0 : kSlots * ((NDQ + kSlots - 1) / kSlots);       // "slot free" barriers
     static constexpr int kBarOffset = kStages * kStageBytes;
-    static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
+    static constexpr int kNumBars = 2 * kStages + kSlots + kSlotBars + 2 * kAccStages;
+    static_assert(!kTied || kStages >= NDQ, "tied rings: need at least as many stages as dequant groups");
+    static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;     // + tmem slot + alignment slack
+    static_assert(kStageBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned stages");
+    static_assert(kStages >= 2 && kSlots >= 2, "pipeline too shallow");
+    static_assert(kAccStages * NTOK + kSlots * kSlotCols <= kTmemCols, "TMEM over-subscribed");
 };
 
-template <int CB, int NTOK, int NDQ>
+template <int CB, int NTOK, int KBS, int NDQ>
 __global__ void __launch_bounds__((8 + 4 * NDQ) * 32, 1)
 umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
-    using SL = SmemLayout<NTOK>;
-    static_assert(kStages % NDQ == 0, "a stage must always belong to the same dequant group");
+    using C = Cfg<CB, NTOK, KBS, NDQ>;
+    constexpr int S = C::kStages, A = C::kSlots, AB = C::kSlotBars;
     constexpr int kEpiWarp0 = 4 + 4 * NDQ;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SL::kBarOffset);
-    uint64_t *full = bars, *afull = bars + kStages, *empty = bars + 2 * kStages;
-    uint64_t *tfull = bars + 3 * kStages, *tempty = tfull + kAccStages;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kBarOffset);
+    uint64_t *full = bars, *sempty = bars + S, *afull = bars + 2 * S, *aempty = afull + A;
+    uint64_t *tfull = aempty + AB, *tempty = tfull + kAccStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kAccStages);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t wbytes = a.tile_bytes;
+    // warp index via shuffle: provably warp-uniform, so the role branches below are uniform branches
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
-        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(afull + s, 4); mbar_init(empty + s, 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(sempty + s, 1); }
+        for (int s = 0; s < A; ++s) mbar_init(afull + s, 4);
+        for (int s = 0; s < AB; ++s) mbar_init(aempty + s, 1);
         for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
         fence_barrier_init();
     }
@@ -242,59 +324,83 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t acc_col0 = 0;                          // 2 x NTOK accumulator columns
-    const uint32_t a_col0 = kAccStages * NTOK;            // then kStages x 32 columns of A slots
-
-    const uint32_t n_items = a.n_tiles * a.m_tiles * a.splits;
+    const uint32_t acc_col0 = 0;                          // kAccStages x NTOK accumulator columns
+    const uint32_t a_col0 = kAccStages * NTOK;            // then A slots of KBS x 32 columns
 
     if (warp == 0) {
-        // ===================== producer =====================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
-                const uint32_t tile = w / a.splits, seg = w - tile * a.splits;
-                const uint32_t nt = tile % a.n_tiles, mt = tile / a.n_tiles;
-                const uint32_t kb0 = a.k_blocks * seg / a.splits, kb1 = a.k_blocks * (seg + 1) / a.splits;
-                const uint8_t *wsrc = a.packed + ((size_t)nt * a.k_blocks) * wbytes;
+        // ===================== producer (warp-converged; one elected lane issues the copies) =====================
+        {
+            ItemIter iter(a);
+            Item item;
+            uint32_t it = 0;                               // stage counter of this CTA
+            while (iter.next(item)) {
+                const uint32_t nt = item.tile % a.n_tiles, mt = item.tile / a.n_tiles;
+                const uint8_t *wsrc = a.packed + ((size_t)nt * a.k_blocks) * C::kWBytes;
                 const uint2 *psrc = a.dqparams + (size_t)nt * 128;
-                uint32_t g = kb0 / a.group_kb, g_left = a.group_kb - (kb0 - g * a.group_kb);
-                for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
-                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                    mbar_wait(empty + s, ph ^ 1);
-                    uint8_t *stage = smem + s * SL::kStageBytes;
-                    mbar_arrive_expect_tx(full + s, SL::kXBytes + wbytes + SL::kPBytes);
-                    tma_load_2d(stage, &tmap_x, full + s, (int)(kb * WL_TILE_K), (int)(mt * NTOK));
-                    bulk_load(stage + SL::kXBytes, wsrc + (size_t)kb * wbytes, wbytes, full + s);
-                    bulk_load(stage + SL::kXBytes + SL::kWBytesMax, psrc + (size_t)g * a.Npad, SL::kPBytes, full + s);
-                    if (--g_left == 0) { ++g; g_left = a.group_kb; }
+                for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                    const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                    const uint32_t s = it % S, ph = (it / S) & 1;
+                    mbar_wait(sempty + s, ph ^ 1);
+                    uint8_t *stage = smem + s * C::kStageBytes;
+                    if (elect_one()) {
+                        TRACE(0, it);                              // producer: stage free, issuing loads
+                        if (a.dbg & 8) {   // timing experiment: weights only
+                            mbar_arrive_expect_tx(full + s, nk * C::kWBytes);
+                            bulk_load(stage + KBS * C::kXBytes, wsrc + (size_t)kb * C::kWBytes, nk * C::kWBytes, full + s);
+                        } else {
+                            mbar_arrive_expect_tx(full + s, nk * (C::kXBytes + C::kWBytes + C::kPBytes));
+                            bulk_load(stage + KBS * C::kXBytes, wsrc + (size_t)kb * C::kWBytes, nk * C::kWBytes, full + s);
+                            for (uint32_t sub = 0; sub < nk; ++sub) {
+                                tma_load_2d(stage + sub * C::kXBytes, &tmap_x, full + s, (int)((kb + sub) * WL_TILE_K), (int)(mt * NTOK));
+                                const uint32_t g = (kb + sub) / a.group_kb;
+                                bulk_load(stage + KBS * (C::kXBytes + C::kWBytes) + sub * C::kPBytes, psrc + (size_t)g * a.Npad,
+                                          C::kPBytes, full + s);
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (warp-converged; one elected lane issues) =====================
+        {
             constexpr uint32_t idesc = make_idesc(NTOK);
-            uint32_t it = 0, item = 0;
-            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
-                const uint32_t tile = w / a.splits, seg = w - tile * a.splits;
-                const uint32_t kb0 = a.k_blocks * seg / a.splits, kb1 = a.k_blocks * (seg + 1) / a.splits;
-                const uint32_t acc = item % kAccStages, aph = (item / kAccStages) & 1;
+            ItemIter iter(a);
+            Item item;
+            uint32_t it = 0, n_item = 0;
+            while (iter.next(item)) {
+                const uint32_t acc = n_item % kAccStages, aph = (n_item / kAccStages) & 1;
+                ++n_item;
                 mbar_wait(tempty + acc, aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc_col0 + acc * NTOK;
-                for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
-                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                    mbar_wait(full + s, ph);      // TMA bytes of the B tile are visible to this thread
-                    mbar_wait(afull + s, ph);     // A slot s has been written to TMEM
+                for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                    const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                    const uint32_t s = it % S, ph = (it / S) & 1;
+                    const uint32_t sl = it % A, aph2 = (it / A) & 1;
+                    if (lane == 0) TRACE(1, it);   // mma warp: starts waiting for stage it
+                    mbar_wait(full + s, ph);       // TMA bytes of the B tiles are visible to this warp
+                    mbar_wait(afull + sl, aph2);   // A slot has been written to TMEM
                     tc_fence_after();
-                    const uint64_t bdesc = make_b_desc(smem_u32(smem + s * SL::kStageBytes));
-                    const uint32_t a_tmem = tmem_base + a_col0 + s * kACols;
+                    if (lane == 0) TRACE(3, it);   // mma warp: A ready, issuing
+                    const uint32_t stage_addr = smem_u32(smem + s * C::kStageBytes);
+                    const uint32_t a_tmem = tmem_base + a_col0 + sl * C::kSlotCols;
+                    if (elect_one()) {
+                        for (uint32_t sub = 0; sub < nk && !(a.dbg & 1); ++sub) {
+                            const uint64_t bdesc = make_b_desc(stage_addr + sub * C::kXBytes);
 #pragma unroll
-                    for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
-                        umma_ts(d_tmem, a_tmem + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (kb > kb0 || k4 > 0) ? 1u : 0u);
-                    umma_commit(empty + s);       // frees smem stage s and TMEM A slot s
+                            for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                                umma_ts(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc,
+                                        (kb > item.kb0 || sub > 0 || k4 > 0) ? 1u : 0u);
+                        }
+                        umma_commit(sempty + s);       // smem stage free for the producer (tied rings: and the A slot)
+                        if constexpr (!C::kTied) umma_commit(aempty + it % AB);   // TMEM A slot free for the dequant warps
+                    }
+                    __syncwarp();
                 }
-                umma_commit(tfull + acc);
+                if (elect_one()) umma_commit(tfull + acc);
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < kEpiWarp0) {
@@ -303,41 +409,62 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
         const int quarter = warp & 3;             // TMEM lanes [32*quarter, +32)
         const int n_local = quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0;
-        uint32_t it = 0;                          // global k-block counter of this CTA (same in every role)
-        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
-            const uint32_t tile = w / a.splits, seg = w - tile * a.splits;
-            const uint32_t kb0 = a.k_blocks * seg / a.splits, kb1 = a.k_blocks * (seg + 1) / a.splits;
-            const uint32_t nkb = kb1 - kb0;
-            // first k-block of this item that falls on one of this group's stages
-            uint32_t j = (grp + NDQ - (it % NDQ)) % NDQ;
-            for (; j < nkb; j += NDQ) {
-                const uint32_t i2 = it + j;
-                const uint32_t s = i2 % kStages, ph = (i2 / kStages) & 1;
+        ItemIter iter(a);
+        Item item;
+        uint32_t it = 0;
+        while (iter.next(item)) {
+            for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                if (it % NDQ != grp) continue;    // group g owns the stages with it % NDQ == g
+                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                const uint32_t s = it % S, ph = (it / S) & 1;
+                const uint32_t sl = it % A;
+                // 1. the slot's previous user MMA(it - A) has completed (also orders us after every TMA
+                //    of stages <= it - A, which makes the next wait alias-free); 2. this stage's bytes landed
+                if (it >= (uint32_t)A) {
+                    if constexpr (C::kTied) {
+                        if (!(a.dbg & 32)) mbar_wait(sempty + s, ph ^ 1);
+                    } else {
+                        const uint32_t j = it - A;
+                        mbar_wait(aempty + j % AB, (j / AB) & 1);
+                    }
+                }
                 mbar_wait(full + s, ph);
-                const uint8_t *stage = smem + s * SL::kStageBytes;
-                const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + SL::kXBytes);
-                const uint2 prm = reinterpret_cast<const uint2 *>(stage + SL::kXBytes + SL::kWBytesMax)[n_local];
-                uint32_t vals[32];
-                dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
-                tmem_st32(lane_addr + s * kACols, vals);
+                if (!(a.dbg & 16)) tc_fence_after();
+                if (quarter == 0 && lane == 0) TRACE(4, it);   // dequant: inputs ready
+                const uint8_t *stage = smem + s * C::kStageBytes;
+                for (uint32_t sub = 0; sub < nk; ++sub) {
+                    const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + KBS * C::kXBytes + sub * C::kWBytes);
+                    const uint2 prm = reinterpret_cast<const uint2 *>(stage + KBS * (C::kXBytes + C::kWBytes) + sub * C::kPBytes)[n_local];
+                    uint32_t vals[32];
+                    if (!(a.dbg & 2)) dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) vals[q] = prm.x + q;
+                    }
+                    if (!(a.dbg & 4)) tmem_st32(lane_addr + sl * C::kSlotCols + sub * kACols, vals);
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(afull + s);
+                if (lane == 0) mbar_arrive(afull + sl);
+                if (quarter == 0 && lane == 0) TRACE(5, it);   // dequant: slot published
             }
-            it += nkb;
         }
     } else if (warp >= kEpiWarp0) {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;
-        uint32_t item = 0;
-        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
-            const uint32_t tile = w / a.splits, seg = w - tile * a.splits;
-            const uint32_t nt = tile % a.n_tiles, mt = tile / a.n_tiles;
-            const uint32_t acc = item % kAccStages, aph = (item / kAccStages) & 1;
+        ItemIter iter(a);
+        Item item;
+        uint32_t n_item = 0;
+        while (iter.next(item)) {
+            const uint32_t nt = item.tile % a.n_tiles, mt = item.tile / a.n_tiles;
+            const uint32_t acc = n_item % kAccStages, aph = (n_item / kAccStages) & 1;
+            ++n_item;
             const uint32_t n = nt * 128 + quarter * 32 + lane;
             const bool n_ok = n < a.N;
-            const float bias = (a.splits == 1 && a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
+            const bool direct = item.slot < 0;
+            const float bias = (direct && a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
+            float *part = direct ? nullptr : a.partial + (size_t)item.slot * (NTOK * 128) + quarter * 32 + lane;
             mbar_wait(tfull + acc, aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col0 + acc * NTOK;
@@ -347,18 +474,19 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 tmem_ld16(t_acc + c0, v);
                 tmem_ld_wait();
                 const uint32_t m_base = mt * NTOK + c0;
+                if (direct) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const uint32_t m = m_base + j;
-                    if (m < a.M && n_ok) {
-                        const float val = __uint_as_float(v[j]) + bias;
-                        if (a.splits > 1) {
-                            a.partial[((size_t)seg * a.M + m) * a.Npad + n] = val;
-                        } else {
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t m = m_base + j;
+                        if (m < a.M && n_ok && !(a.dbg & 64)) {
+                            const float val = __uint_as_float(v[j]) + bias;
                             if (a.y_f32) a.y_f32[(size_t)m * a.N + n] = val;
                             if (a.y_bf16) a.y_bf16[(size_t)m * a.N + n] = __float2bfloat16_rn(val);
                         }
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) part[(size_t)(c0 + j) * 128] = __uint_as_float(v[j]);
                 }
             }
             tc_fence_before();
@@ -375,18 +503,32 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
     }
 }
 
-// y[m][n] = sum_seg partial[seg][m][n] + bias[n]  (fixed order => deterministic)
-__global__ void umma_splitk_reduce_kernel(const float *__restrict__ part, int splits, size_t M, size_t N, size_t Npad,
-                                          const float *__restrict__ bias, float *__restrict__ y_f32,
-                                          __nv_bfloat16 *__restrict__ y_bf16) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M * N) return;
-    const size_t m = idx / N, n = idx - m * N;
-    float v = 0.f;
-    for (int s = 0; s < splits; ++s) v += part[((size_t)s * M + m) * Npad + n];
-    if (bias) v += __ldg(bias + n);
-    if (y_f32) y_f32[idx] = v;
-    if (y_bf16) y_bf16[idx] = __float2bfloat16_rn(v);
+// stream-K fix-up: tiles that were cut by a CTA boundary get y = sum of their partial tiles (in CTA
+// order: deterministic) + bias.  One block per output tile; complete tiles return immediately.
+template <int NTOK>
+__global__ void __launch_bounds__(256)
+umma_streamk_fixup_kernel(const UmmaArgs a, uint32_t grid_main) {
+    const uint32_t tile = blockIdx.x;
+    const uint64_t KB = a.k_blocks, U = a.units, G = grid_main;
+    const uint64_t t0 = (uint64_t)tile * KB, t1 = t0 + KB;
+    const uint32_t c_lo = (uint32_t)(((t0 + 1) * G - 1) / U);     // CTA owning the tile's first unit
+    const uint32_t c_hi = (uint32_t)((t1 * G - 1) / U);           // CTA owning its last unit
+    if (c_lo == c_hi) return;                                     // one CTA saw the whole tile: written directly
+    const uint32_t nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+    for (uint32_t e = threadIdx.x; e < NTOK * 128; e += blockDim.x) {
+        const uint32_t ml = e >> 7, nl = e & 127;
+        const uint32_t m = mt * NTOK + ml, n = nt * 128 + nl;
+        if (m >= a.M || n >= a.N) continue;
+        float v = 0.f;
+        for (uint32_t c = c_lo; c <= c_hi; ++c) {
+            const uint64_t u0 = U * c / G;
+            const uint32_t slot = c * 2 + (u0 >= t0 ? 0u : 1u);   // CTA starts inside this tile -> its first item
+            v += a.partial[(size_t)slot * (NTOK * 128) + e];
+        }
+        if (a.bias) v += __ldg(a.bias + n);
+        if (a.y_f32) a.y_f32[(size_t)m * a.N + n] = v;
+        if (a.y_bf16) a.y_bf16[(size_t)m * a.N + n] = __float2bfloat16_rn(v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -408,9 +550,9 @@ PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-template <int CB, int NTOK, int NDQ>
+template <int CB, int NTOK, int KBS, int NDQ>
 int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, size_t M, float *y_f32, void *y_bf16) {
-    using SL = SmemLayout<NTOK>;
+    using C = Cfg<CB, NTOK, KBS, NDQ>;
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     CUtensorMap tmap;
@@ -429,27 +571,33 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     a.k_blocks = (uint32_t)qw->k_blocks; a.n_tiles = (uint32_t)qw->n_tiles;
     a.m_tiles = (uint32_t)((M + NTOK - 1) / NTOK);
     a.group_kb = (uint32_t)(qw->group / WL_TILE_K);
-    a.tile_bytes = (uint32_t)qw->tile_bytes;
-    // K segments: enough work items to occupy every SM, at least 4 k-blocks per segment
     const uint32_t tiles = a.n_tiles * a.m_tiles;
-    uint32_t splits = 1;
-    if (tiles < (uint32_t)ctx->sm_count) {
-        splits = ((uint32_t)ctx->sm_count + tiles - 1) / tiles;
-        const uint32_t max_splits = a.k_blocks >= 4 ? a.k_blocks / 4 : 1;
-        if (splits > max_splits) splits = max_splits;
-        if (splits < 1) splits = 1;
-    }
-    a.splits = splits;
+    a.units = (uint64_t)tiles * a.k_blocks;
     a.y_f32 = y_f32; a.y_bf16 = (__nv_bfloat16 *)y_bf16; a.partial = nullptr;
-    if (splits > 1) {
-        DLLM_TRY(ensure_buf(ctx, ctx->lin_ws, (size_t)splits * M * a.Npad * sizeof(float)));
+    static const uint32_t dbg_flags = getenv("DLLM_UMMA_DBG") ? (uint32_t)atoi(getenv("DLLM_UMMA_DBG")) : 0u;
+    a.dbg = dbg_flags;
+    a.trace = nullptr;
+    if (a.dbg & 128) {
+        DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, 6 * 256 * sizeof(long long)));
+        a.trace = (long long *)ctx->lin_flags.p;
+        cudaMemsetAsync(a.trace, 0, 6 * 256 * sizeof(long long), ctx->stream);
+    }
+    // dense problems (>= 4 tiles per SM): whole tiles round-robin; otherwise stream-K over all SMs
+    const uint32_t sms = (uint32_t)ctx->sm_count;
+    a.stream_k = 0;
+    uint32_t grid = tiles < sms ? tiles : sms;
+    if (tiles < 4 * sms) {
+        const uint64_t g = a.units / (2 * KBS);     // at least two stages of work per CTA
+        const uint32_t gk = (uint32_t)(g > sms ? sms : g);
+        if (gk > grid || tiles > sms) { a.stream_k = 1; grid = gk; }
+    }
+    if (a.stream_k) {
+        DLLM_TRY(ensure_buf(ctx, ctx->lin_ws, (size_t)2 * grid * NTOK * 128 * sizeof(float)));
         a.partial = (float *)ctx->lin_ws.p;
     }
-    const uint32_t n_items = tiles * splits;
-    const int grid = (int)(n_items < (uint32_t)ctx->sm_count ? n_items : (uint32_t)ctx->sm_count);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, NDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, KBS, NDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
         attr_set = true;
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -463,7 +611,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
         CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    umma_qlinear_kernel<CB, NTOK, NDQ><<<grid, (8 + 4 * NDQ) * 32, SL::kTotal, ctx->stream>>>(tmap, a);
+    umma_qlinear_kernel<CB, NTOK, KBS, NDQ><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
     LAUNCH_CHECK(ctx);
     if (ev1) {
         CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
@@ -473,21 +621,35 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         ctx->prof_bytes += (double)qw->K * qw->N * qw->bits / 8.0 + (double)(qw->K / qw->group) * qw->N * 8.0 +
                            2.0 * M * qw->K + (y_f32 ? 4.0 : 0.0) * M * qw->N + (y_bf16 ? 2.0 : 0.0) * M * qw->N;
     }
-    if (splits > 1) {
-        const size_t total = M * qw->N;
-        umma_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
-            a.partial, (int)splits, M, qw->N, a.Npad, qw->d_bias, y_f32, (__nv_bfloat16 *)y_bf16);
+    if (a.dbg & 128) {   // dump the stage timeline of CTA 0 (timing experiments only)
+        std::vector<long long> h(6 * 256);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h.data(), a.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        FILE *f = fopen("gpurun_out/umma_trace.csv", "w");
+        if (f) {
+            fprintf(f, "it,prod_issue,mma_wait,mma_full,mma_aready,dq_start,dq_end\n");
+            for (int i = 0; i < 256; ++i)
+                fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld,%lld\n", i, h[i], h[256 + i], h[512 + i], h[768 + i], h[1024 + i], h[1280 + i]);
+            fclose(f);
+        }
+    }
+    if (a.stream_k) {
+        umma_streamk_fixup_kernel<NTOK><<<tiles, 256, 0, ctx->stream>>>(a, grid);
         LAUNCH_CHECK(ctx);
     }
     return DLLM_OK;
 }
 
+// skinny shapes are HBM-bound: KBS k-blocks per stage so that a stage carries >= 8 KB of codes
 template <int CB>
 int32_t launch_umma_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const void *x, size_t M, float *y_f32, void *y_bf16) {
-    if (M <= 16) return launch_umma<CB, 16, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
-    if (M <= 32) return launch_umma<CB, 32, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
-    if (M <= 64) return launch_umma<CB, 64, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
-    return launch_umma<CB, 128, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    constexpr int kSkinnyKBS = CB == 2 ? 4 : 2;
+    if (M <= 16) return launch_umma<CB, 16, kSkinnyKBS, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 32) return launch_umma<CB, 32, kSkinnyKBS, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 64) return launch_umma<CB, 64, 1, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    static const int dense_kbs = getenv("DLLM_DENSE_KBS") ? atoi(getenv("DLLM_DENSE_KBS")) : 1;
+    if (dense_kbs == 2) return launch_umma<CB, 128, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    return launch_umma<CB, 128, 1, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
 }
 
 }  // namespace

@@ -71,10 +71,10 @@ def main():
                 report(f"dense_umma_{bits}b(+f32->bf16 cast)", t, K * N * bits // 8 + 6 * M * K + 4 * M * N, 2.0 * M * K * N, K=K, N=N, M=M)
                 qw.close()
         return
-    if args.gemv_only:
-        args.quick = args.quick
-    # ---- KV quantizers: rows x 4096 f32 ----
     rows, dim = ((1 << 16) if not args.quick else (1 << 14)), 4096
+    if args.gemv_only:
+        rows = 0
+    # ---- KV quantizers: rows x 4096 f32 ----
     n = rows * dim
     x = torch.randn(rows, dim, device="cuda")
     codes = torch.empty(n, dtype=torch.uint8, device="cuda")
@@ -82,7 +82,7 @@ def main():
     params = torch.empty(4, device="cuda")
     deq = torch.empty_like(x)
     torch.cuda.synchronize()
-    for bits in (8, 4, 2):
+    for bits in ((8, 4, 2) if rows else ()):
         t = time_fn(stream, lambda: ctx.quantize_d_rows_dev(x.data_ptr(), rows, dim, bits, True, codes.data_ptr(), scales.data_ptr(), zps.data_ptr()), 10)
         report(f"kv_quant_rows_D_{bits}b", t, 4 * n + n * bits // 8 + 8 * rows, rows=rows, dim=dim)
         t = time_fn(stream, lambda: ctx.dequantize_d_rows_dev(codes.data_ptr(), rows, dim, bits, True, scales.data_ptr(), zps.data_ptr(), deq.data_ptr()), 10)
@@ -91,9 +91,10 @@ def main():
         report(f"quant_tensor_B_{bits}b(2 passes)", t, 8 * n + n * bits // 8, n=n)
         t = time_fn(stream, lambda: ctx.dequantize_tensor_dev(codes.data_ptr(), n, bits, True, params.data_ptr(), deq.data_ptr()), 10)
         report(f"dequant_tensor_B_{bits}b", t, 4 * n + n * bits // 8, n=n)
-    ctx.quantize_tensor_dev(x.data_ptr(), n, 8, False, codes.data_ptr(), params.data_ptr())
-    packed = torch.empty(n, dtype=torch.uint8, device="cuda")
-    for bits in (4, 1):
+    if rows:
+        ctx.quantize_tensor_dev(x.data_ptr(), n, 8, False, codes.data_ptr(), params.data_ptr())
+    packed = torch.empty(max(n, 16), dtype=torch.uint8, device="cuda")
+    for bits in ((4, 1) if rows else ()):
         t = time_fn(stream, lambda: ctx.pack_dev(codes.data_ptr(), n, bits, packed.data_ptr()), 10)
         report(f"pack_{bits}b", t, n + n * bits // 8, n=n)
         t = time_fn(stream, lambda: ctx.unpack_dev(packed.data_ptr(), n, bits, codes.data_ptr()), 10)
