@@ -38,7 +38,7 @@
 namespace {
 
 #ifndef DLLM_NDQ
-#define DLLM_NDQ 4
+#define DLLM_NDQ 3
 #endif
 constexpr int kNDQ = DLLM_NDQ;       // dequant groups of 4 warps
 constexpr int kAccStages = 2;
@@ -140,6 +140,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+template <int CH>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t *r) {
+    static_assert(CH == 16 || CH == 32 || CH == 64, "chunk");
+    if (CH == 16) tmem_ld16(taddr, r);
+    else if (CH == 32) tmem_ld32(taddr, r);
+    else { tmem_ld32(taddr, r); tmem_ld32(taddr + 32, r + 32); }   // two loads in flight, one wait
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // smem matrix descriptor of a K-major, SWIZZLE_128B bf16 tile (rows of 128 bytes, 8-row groups of
@@ -220,7 +238,7 @@ struct UmmaArgs {
     float *partial;            // stream-K partial tiles: [2 * grid][NTOK][128] f32
     uint32_t M, N, Npad, k_blocks, n_tiles, m_tiles, group_kb;
     uint32_t stream_k;         // 0: whole tiles round-robin; 1: contiguous unit ranges per CTA
-    long long *trace;          // dbg & 128: per-stage clock64 stamps of CTA 0: [role 0..5][256]
+    long long *trace;          // dbg & 128: per-stage clock64 stamps of CTA 0: [role 0..7][256]
     uint32_t dbg;              // timing experiments only (DLLM_UMMA_DBG): 1 skip MMAs, 2 skip dequant math, 4 skip TMEM stores
     uint64_t units;            // n_tiles * m_tiles * k_blocks
 };
@@ -265,33 +283,36 @@ struct ItemIter {
     }
 };
 
-// Ring sizing.  Safety rule for the parity waits (verified by an exhaustive-interleaving model of the
-// protocol): the dequant group that owns stage `it` first waits for MMA(it - A) [the slot's previous
-// user], then for the stage's TMA bytes.  That wait is alias-free only if the barrier it tests cannot be
-// two phases behind, i.e. the number of distinct "slot free" barriers must be >= the number of dequant
-// groups -> kSlotBars = A * ceil(NDQ / A).  Dense tiles (NTOK >= 64) tie the two rings (S == A) so one
-// tcgen05.commit per stage frees both the smem stage and the TMEM slot.
+// Ring sizing.  Three resources, two rings:
+//   W ring  (kWStages deep): packed weight tiles + their dequant operands in smem.  Filled by the weight
+//           producer, consumed by the dequant warps (generic-proxy reads), released by their arrival.
+//           It is deep and cheap (4-bit: 5 KB per k-block), so the dequant never waits on HBM latency.
+//   XA ring (kSlots deep): activation tiles in smem + the dequantized A tile in TMEM, k-block for
+//           k-block.  Both are released by the same tcgen05.commit once the stage's MMAs completed.
+// Safety rule for the parity waits (verified with an interleaving model of the protocol, scripts/
+// pipeline_model.py): the dequant group that owns stage `it` first waits for MMA(it - A) [previous user
+// of its TMEM slot], then for the stage's weight bytes.  Those waits cannot alias if the XA ring has
+// at least as many slots as there are dequant groups and the W ring is at least as deep as the XA ring.
 template <int CB, int NTOK, int KBS, int NDQ = 4>
 struct Cfg {
     static constexpr int kXBytes = NTOK * 128;                       // one k-block of activations (bf16, SW128)
     static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;   // one packed weight tile
     static constexpr int kPBytes = 128 * 8;                          // dequant operands of 128 columns
-    static constexpr int kStageBytes = KBS * (kXBytes + kWBytes + kPBytes);
-    static constexpr int kSmemBudget = 220 * 1024;
-    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+    static constexpr int kXStage = KBS * kXBytes;
+    static constexpr int kWStage = KBS * (kWBytes + kPBytes);
     static constexpr int kSlotCols = KBS * kACols;
     static constexpr int kSlotsRaw = (kTmemCols - kAccStages * NTOK) / kSlotCols;
-    static constexpr bool kTied = NTOK >= 64;
-    static constexpr int kTiedDepth = kStagesRaw < kSlotsRaw ? (kStagesRaw < 8 ? kStagesRaw : 8) : (kSlotsRaw < 8 ? kSlotsRaw : 8);
-    static constexpr int kStages = kTied ? kTiedDepth : (kStagesRaw > 24 ? 24 : kStagesRaw);   // smem ring depth
-    static constexpr int kSlots = kTied ? kTiedDepth : (kSlotsRaw > 8 ? 8 : kSlotsRaw);        // TMEM A ring depth
-    static constexpr int kSlotBars = kTied ? 0 : kSlots * ((NDQ + kSlots - 1) / kSlots);       // "slot free" barriers
-    static constexpr int kBarOffset = kStages * kStageBytes;
-    static constexpr int kNumBars = 2 * kStages + kSlots + kSlotBars + 2 * kAccStages;
-    static_assert(!kTied || kStages >= NDQ, "tied rings: need at least as many stages as dequant groups");
+    static constexpr int kSlots = kSlotsRaw > 8 ? 8 : kSlotsRaw;     // XA ring depth
+    static constexpr int kSmemBudget = 216 * 1024;
+    static constexpr int kWStagesRaw = (kSmemBudget - kSlots * kXStage) / kWStage;
+    static constexpr int kWStages = kWStagesRaw > 24 ? 24 : kWStagesRaw;     // W ring depth
+    static constexpr int kWOffset = kSlots * kXStage;
+    static constexpr int kBarOffset = kWOffset + kWStages * kWStage;
+    static constexpr int kNumBars = 2 * kWStages + 3 * kSlots + 2 * kAccStages;
     static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;     // + tmem slot + alignment slack
-    static_assert(kStageBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned stages");
-    static_assert(kStages >= 2 && kSlots >= 2, "pipeline too shallow");
+    static_assert(kXStage % 1024 == 0 && kWStage % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned stages");
+    static_assert(kSlots >= NDQ, "XA ring must have at least as many slots as dequant groups");
+    static_assert(kWStages >= kSlots, "W ring must be at least as deep as the XA ring");
     static_assert(kAccStages * NTOK + kSlots * kSlotCols <= kTmemCols, "TMEM over-subscribed");
 };
 
@@ -299,13 +320,15 @@ template <int CB, int NTOK, int KBS, int NDQ>
 __global__ void __launch_bounds__((8 + 4 * NDQ) * 32, 1)
 umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
     using C = Cfg<CB, NTOK, KBS, NDQ>;
-    constexpr int S = C::kStages, A = C::kSlots, AB = C::kSlotBars;
+    constexpr int SW = C::kWStages, A = C::kSlots;
     constexpr int kEpiWarp0 = 4 + 4 * NDQ;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_w = smem + C::kWOffset;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kBarOffset);
-    uint64_t *full = bars, *sempty = bars + S, *afull = bars + 2 * S, *aempty = afull + A;
-    uint64_t *tfull = aempty + AB, *tempty = tfull + kAccStages;
+    uint64_t *wfull = bars, *wempty = bars + SW;                     // W ring
+    uint64_t *xfull = bars + 2 * SW, *xaempty = xfull + A, *afull = xaempty + A;   // XA ring
+    uint64_t *tfull = afull + A, *tempty = tfull + kAccStages;       // accumulators
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kAccStages);
 
     // warp index via shuffle: provably warp-uniform, so the role branches below are uniform branches
@@ -313,9 +336,8 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
-        for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(sempty + s, 1); }
-        for (int s = 0; s < A; ++s) mbar_init(afull + s, 4);
-        for (int s = 0; s < AB; ++s) mbar_init(aempty + s, 1);
+        for (int s = 0; s < SW; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 4); }
+        for (int s = 0; s < A; ++s) { mbar_init(xfull + s, 1); mbar_init(xaempty + s, 1); mbar_init(afull + s, 4); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
         fence_barrier_init();
     }
@@ -328,80 +350,111 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
     const uint32_t a_col0 = kAccStages * NTOK;            // then A slots of KBS x 32 columns
 
     if (warp == 0) {
-        // ===================== producer (warp-converged; one elected lane issues the copies) =====================
-        {
-            ItemIter iter(a);
-            Item item;
-            uint32_t it = 0;                               // stage counter of this CTA
-            while (iter.next(item)) {
-                const uint32_t nt = item.tile % a.n_tiles, mt = item.tile / a.n_tiles;
-                const uint8_t *wsrc = a.packed + ((size_t)nt * a.k_blocks) * C::kWBytes;
-                const uint2 *psrc = a.dqparams + (size_t)nt * 128;
-                for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
-                    const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
-                    const uint32_t s = it % S, ph = (it / S) & 1;
-                    mbar_wait(sempty + s, ph ^ 1);
-                    uint8_t *stage = smem + s * C::kStageBytes;
-                    if (elect_one()) {
-                        TRACE(0, it);                              // producer: stage free, issuing loads
-                        if (a.dbg & 8) {   // timing experiment: weights only
-                            mbar_arrive_expect_tx(full + s, nk * C::kWBytes);
-                            bulk_load(stage + KBS * C::kXBytes, wsrc + (size_t)kb * C::kWBytes, nk * C::kWBytes, full + s);
-                        } else {
-                            mbar_arrive_expect_tx(full + s, nk * (C::kXBytes + C::kWBytes + C::kPBytes));
-                            bulk_load(stage + KBS * C::kXBytes, wsrc + (size_t)kb * C::kWBytes, nk * C::kWBytes, full + s);
-                            for (uint32_t sub = 0; sub < nk; ++sub) {
-                                tma_load_2d(stage + sub * C::kXBytes, &tmap_x, full + s, (int)((kb + sub) * WL_TILE_K), (int)(mt * NTOK));
-                                const uint32_t g = (kb + sub) / a.group_kb;
-                                bulk_load(stage + KBS * (C::kXBytes + C::kWBytes) + sub * C::kPBytes, psrc + (size_t)g * a.Npad,
-                                          C::kPBytes, full + s);
-                            }
-                        }
+        // ===================== activation producer (warp-converged; one elected lane issues TMA) =====================
+        ItemIter iter(a);
+        Item item;
+        uint32_t it = 0;                               // stage counter of this CTA
+        while (iter.next(item)) {
+            const uint32_t mt = item.tile / a.n_tiles;
+            for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                const uint32_t s = it % A, ph = (it / A) & 1;
+                mbar_wait(xaempty + s, ph ^ 1);
+                if (elect_one()) {
+                    TRACE(0, it);
+                    uint8_t *stage = smem + s * C::kXStage;
+                    if (!(a.dbg & 8)) {
+                        mbar_arrive_expect_tx(xfull + s, nk * C::kXBytes);
+                        for (uint32_t sub = 0; sub < nk; ++sub)
+                            tma_load_2d(stage + sub * C::kXBytes, &tmap_x, xfull + s, (int)((kb + sub) * WL_TILE_K), (int)(mt * NTOK));
+                    } else {
+                        mbar_arrive(xfull + s);        // timing experiment: no activation traffic
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== weight producer (runs ahead through the deep W ring) =====================
+        ItemIter iter(a);
+        Item item;
+        uint32_t it = 0;
+        while (iter.next(item)) {
+            const uint32_t nt = item.tile % a.n_tiles;
+            const uint8_t *wsrc = a.packed + ((size_t)nt * a.k_blocks) * C::kWBytes;
+            const uint2 *psrc = a.dqparams + (size_t)nt * 128;
+            for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                const uint32_t s = it % SW, ph = (it / SW) & 1;
+                mbar_wait(wempty + s, ph ^ 1);
+                if (elect_one()) {
+                    uint8_t *stage = smem_w + s * C::kWStage;
+                    mbar_arrive_expect_tx(wfull + s, nk * (C::kWBytes + C::kPBytes));
+                    bulk_load(stage, wsrc + (size_t)kb * C::kWBytes, nk * C::kWBytes, wfull + s);
+                    for (uint32_t sub = 0; sub < nk; ++sub) {
+                        const uint32_t g = (kb + sub) / a.group_kb;
+                        bulk_load(stage + KBS * C::kWBytes + sub * C::kPBytes, psrc + (size_t)g * a.Npad, C::kPBytes, wfull + s);
+                    }
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-converged; one elected lane issues) =====================
-        {
-            constexpr uint32_t idesc = make_idesc(NTOK);
-            ItemIter iter(a);
-            Item item;
-            uint32_t it = 0, n_item = 0;
-            while (iter.next(item)) {
-                const uint32_t acc = n_item % kAccStages, aph = (n_item / kAccStages) & 1;
-                ++n_item;
-                mbar_wait(tempty + acc, aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc_col0 + acc * NTOK;
-                for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
-                    const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
-                    const uint32_t s = it % S, ph = (it / S) & 1;
-                    const uint32_t sl = it % A, aph2 = (it / A) & 1;
-                    if (lane == 0) TRACE(1, it);   // mma warp: starts waiting for stage it
-                    mbar_wait(full + s, ph);       // TMA bytes of the B tiles are visible to this warp
-                    mbar_wait(afull + sl, aph2);   // A slot has been written to TMEM
+        constexpr uint32_t idesc = make_idesc(NTOK);
+        ItemIter iter(a);
+        Item item;
+        uint32_t it = 0, n_item = 0;
+        while (iter.next(item)) {
+            const uint32_t acc = n_item % kAccStages, aph = (n_item / kAccStages) & 1;
+            ++n_item;
+            mbar_wait(tempty + acc, aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc_col0 + acc * NTOK;
+            // Software-pipelined: the barriers of stage it+1 are polled after the first k-block of stage `it`
+            // has been issued, so the tensor pipe never drains while this warp sits in a try_wait.
+            bool ready = false;
+            for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                const uint32_t s = it % A, ph = (it / A) & 1;
+                if (!ready) {
+                    if (lane == 0) TRACE(1, it);
+                    mbar_wait(xfull + s, ph);      // activation tiles landed
+                    mbar_wait(afull + s, ph);      // A slot written to TMEM
                     tc_fence_after();
-                    if (lane == 0) TRACE(3, it);   // mma warp: A ready, issuing
-                    const uint32_t stage_addr = smem_u32(smem + s * C::kStageBytes);
-                    const uint32_t a_tmem = tmem_base + a_col0 + sl * C::kSlotCols;
-                    if (elect_one()) {
-                        for (uint32_t sub = 0; sub < nk && !(a.dbg & 1); ++sub) {
-                            const uint64_t bdesc = make_b_desc(stage_addr + sub * C::kXBytes);
-#pragma unroll
-                            for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
-                                umma_ts(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc,
-                                        (kb > item.kb0 || sub > 0 || k4 > 0) ? 1u : 0u);
-                        }
-                        umma_commit(sempty + s);       // smem stage free for the producer (tied rings: and the A slot)
-                        if constexpr (!C::kTied) umma_commit(aempty + it % AB);   // TMEM A slot free for the dequant warps
-                    }
-                    __syncwarp();
                 }
-                if (elect_one()) umma_commit(tfull + acc);
+                if (lane == 0) TRACE(3, it);
+                const uint32_t stage_addr = smem_u32(smem + s * C::kXStage);
+                const uint32_t a_tmem = tmem_base + a_col0 + s * C::kSlotCols;
+                const bool first = kb == item.kb0;
+                if (elect_one() && !(a.dbg & 1)) {             // k-block 0 of the stage
+                    const uint64_t bdesc = make_b_desc(stage_addr);
+#pragma unroll
+                    for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                        umma_ts(d_tmem, a_tmem + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (!first || k4 > 0) ? 1u : 0u);
+                }
+                __syncwarp();
+                ready = false;
+                if (kb + KBS < item.kb1) {                     // peek at the next stage while those MMAs run
+                    const uint32_t s2 = (it + 1) % A, ph2 = ((it + 1) / A) & 1;
+                    mbar_wait(xfull + s2, ph2);
+                    mbar_wait(afull + s2, ph2);
+                    tc_fence_after();
+                    ready = true;
+                }
+                if (elect_one()) {
+                    for (uint32_t sub = 1; sub < nk && !(a.dbg & 1); ++sub) {
+                        const uint64_t bdesc = make_b_desc(stage_addr + sub * C::kXBytes);
+#pragma unroll
+                        for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                            umma_ts(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, 1u);
+                    }
+                    umma_commit(xaempty + s);      // frees the activation stage and the TMEM A slot
+                }
                 __syncwarp();
             }
+            if (elect_one()) umma_commit(tfull + acc);
+            __syncwarp();
         }
     } else if (warp >= 4 && warp < kEpiWarp0) {
         // ===================== dequant warps =====================
@@ -416,25 +469,17 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
             for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
                 if (it % NDQ != grp) continue;    // group g owns the stages with it % NDQ == g
                 const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
-                const uint32_t s = it % S, ph = (it / S) & 1;
-                const uint32_t sl = it % A;
-                // 1. the slot's previous user MMA(it - A) has completed (also orders us after every TMA
-                //    of stages <= it - A, which makes the next wait alias-free); 2. this stage's bytes landed
-                if (it >= (uint32_t)A) {
-                    if constexpr (C::kTied) {
-                        if (!(a.dbg & 32)) mbar_wait(sempty + s, ph ^ 1);
-                    } else {
-                        const uint32_t j = it - A;
-                        mbar_wait(aempty + j % AB, (j / AB) & 1);
-                    }
-                }
-                mbar_wait(full + s, ph);
-                if (!(a.dbg & 16)) tc_fence_after();
-                if (quarter == 0 && lane == 0) TRACE(4, it);   // dequant: inputs ready
-                const uint8_t *stage = smem + s * C::kStageBytes;
+                const uint32_t sw = it % SW, wph = (it / SW) & 1;
+                const uint32_t sl = it % A, aph = (it / A) & 1;
+                // 1. previous user of the TMEM slot, MMA(it - A), completed; 2. this stage's weights landed
+                if (it >= (uint32_t)A) mbar_wait(xaempty + sl, aph ^ 1);
+                mbar_wait(wfull + sw, wph);
+                tc_fence_after();
+                if (quarter == 0 && lane == 0) TRACE(4, it);
+                const uint8_t *stage = smem_w + sw * C::kWStage;
                 for (uint32_t sub = 0; sub < nk; ++sub) {
-                    const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + KBS * C::kXBytes + sub * C::kWBytes);
-                    const uint2 prm = reinterpret_cast<const uint2 *>(stage + KBS * (C::kXBytes + C::kWBytes) + sub * C::kPBytes)[n_local];
+                    const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes);
+                    const uint2 prm = reinterpret_cast<const uint2 *>(stage + KBS * C::kWBytes + sub * C::kPBytes)[n_local];
                     uint32_t vals[32];
                     if (!(a.dbg & 2)) dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
                     else {
@@ -443,11 +488,13 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                     }
                     if (!(a.dbg & 4)) tmem_st32(lane_addr + sl * C::kSlotCols + sub * kACols, vals);
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(wempty + sw);   // all smem reads of this warp are done (values are in registers)
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(afull + sl);
-                if (quarter == 0 && lane == 0) TRACE(5, it);   // dequant: slot published
+                if (quarter == 0 && lane == 0) TRACE(5, it);
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -467,31 +514,42 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
             float *part = direct ? nullptr : a.partial + (size_t)item.slot * (NTOK * 128) + quarter * 32 + lane;
             mbar_wait(tfull + acc, aph);
             tc_fence_after();
+            if (quarter == 0 && lane == 0) TRACE(6, n_item - 1);   // epilogue: accumulator ready (indexed by item)
             const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col0 + acc * NTOK;
+            // wide TMEM loads (few round trips: tcgen05.ld competes with the MMA's accumulator traffic), and the
+            // accumulator is handed back to the MMA warp as soon as its last column is in registers
+            constexpr int CH = NTOK >= 64 ? 64 : NTOK;
 #pragma unroll 1
-            for (int c0 = 0; c0 < NTOK; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(t_acc + c0, v);
+            for (int c0 = 0; c0 < NTOK; c0 += CH) {
+                uint32_t v[CH];
+                tmem_ld_chunk<CH>(t_acc + c0, v);
                 tmem_ld_wait();
+                if (c0 + CH >= NTOK) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty + acc);
+                }
                 const uint32_t m_base = mt * NTOK + c0;
                 if (direct) {
+                    if (!n_ok || (a.dbg & 64)) continue;
+                    if (a.y_f32) {
+                        float *yp = a.y_f32 + (size_t)m_base * a.N + n;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t m = m_base + j;
-                        if (m < a.M && n_ok && !(a.dbg & 64)) {
-                            const float val = __uint_as_float(v[j]) + bias;
-                            if (a.y_f32) a.y_f32[(size_t)m * a.N + n] = val;
-                            if (a.y_bf16) a.y_bf16[(size_t)m * a.N + n] = __float2bfloat16_rn(val);
-                        }
+                        for (int j = 0; j < CH; ++j)
+                            if (m_base + j < a.M) yp[(size_t)j * a.N] = __uint_as_float(v[j]) + bias;
+                    }
+                    if (a.y_bf16) {
+                        __nv_bfloat16 *yp = a.y_bf16 + (size_t)m_base * a.N + n;
+#pragma unroll
+                        for (int j = 0; j < CH; ++j)
+                            if (m_base + j < a.M) yp[(size_t)j * a.N] = __float2bfloat16_rn(__uint_as_float(v[j]) + bias);
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) part[(size_t)(c0 + j) * 128] = __uint_as_float(v[j]);
+                    for (int j = 0; j < CH; ++j) part[(size_t)(c0 + j) * 128] = __uint_as_float(v[j]);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + acc);
+            if (quarter == 0 && lane == 0) TRACE(7, n_item - 1);   // epilogue: accumulator released
         }
     }
 
@@ -578,9 +636,9 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     a.dbg = dbg_flags;
     a.trace = nullptr;
     if (a.dbg & 128) {
-        DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, 6 * 256 * sizeof(long long)));
+        DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, 8 * 256 * sizeof(long long)));
         a.trace = (long long *)ctx->lin_flags.p;
-        cudaMemsetAsync(a.trace, 0, 6 * 256 * sizeof(long long), ctx->stream);
+        cudaMemsetAsync(a.trace, 0, 8 * 256 * sizeof(long long), ctx->stream);
     }
     // dense problems (>= 4 tiles per SM): whole tiles round-robin; otherwise stream-K over all SMs
     const uint32_t sms = (uint32_t)ctx->sm_count;
@@ -622,14 +680,14 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
                            2.0 * M * qw->K + (y_f32 ? 4.0 : 0.0) * M * qw->N + (y_bf16 ? 2.0 : 0.0) * M * qw->N;
     }
     if (a.dbg & 128) {   // dump the stage timeline of CTA 0 (timing experiments only)
-        std::vector<long long> h(6 * 256);
+        std::vector<long long> h(8 * 256);
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h.data(), a.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         FILE *f = fopen("gpurun_out/umma_trace.csv", "w");
         if (f) {
-            fprintf(f, "it,prod_issue,mma_wait,mma_full,mma_aready,dq_start,dq_end\n");
+            fprintf(f, "it,prod_issue,mma_wait,mma_full,mma_aready,dq_start,dq_end,epi_start,epi_end\n");
             for (int i = 0; i < 256; ++i)
-                fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld,%lld\n", i, h[i], h[256 + i], h[512 + i], h[768 + i], h[1024 + i], h[1280 + i]);
+                fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", i, h[i], h[256 + i], h[512 + i], h[768 + i], h[1024 + i], h[1280 + i], h[1536 + i], h[1792 + i]);
             fclose(f);
         }
     }
@@ -640,16 +698,13 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     return DLLM_OK;
 }
 
-// skinny shapes are HBM-bound: KBS k-blocks per stage so that a stage carries >= 8 KB of codes
+// two k-blocks (128 k = one quantization group) per pipeline stage
 template <int CB>
 int32_t launch_umma_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const void *x, size_t M, float *y_f32, void *y_bf16) {
-    constexpr int kSkinnyKBS = CB == 2 ? 4 : 2;
-    if (M <= 16) return launch_umma<CB, 16, kSkinnyKBS, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
-    if (M <= 32) return launch_umma<CB, 32, kSkinnyKBS, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
-    if (M <= 64) return launch_umma<CB, 64, 1, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
-    static const int dense_kbs = getenv("DLLM_DENSE_KBS") ? atoi(getenv("DLLM_DENSE_KBS")) : 1;
-    if (dense_kbs == 2) return launch_umma<CB, 128, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
-    return launch_umma<CB, 128, 1, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 16) return launch_umma<CB, 16, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 32) return launch_umma<CB, 32, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 64) return launch_umma<CB, 64, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    return launch_umma<CB, 128, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
 }
 
 }  // namespace
