@@ -77,6 +77,11 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -237,6 +242,7 @@ struct UmmaArgs {
     __nv_bfloat16 *y_bf16;     // final bf16 output [M,N] or null
     float *partial;            // stream-K partial tiles: [2 * grid][NTOK][128] f32
     uint32_t M, N, Npad, k_blocks, n_tiles, m_tiles, group_kb;
+    uint32_t x3d;              // activation tensor map is the 3-D {64, M, K/64} view (K % 64 == 0)
     uint32_t stream_k;         // 0: whole tiles round-robin; 1: contiguous unit ranges per CTA
     long long *trace;          // dbg & 128: per-stage clock64 stamps of CTA 0: [role 0..7][256]
     uint32_t dbg;              // timing experiments only (DLLM_UMMA_DBG): 1 skip MMAs, 2 skip dequant math, 4 skip TMEM stores
@@ -305,7 +311,7 @@ struct Cfg {
     static constexpr int kSlots = kSlotsRaw > 8 ? 8 : kSlotsRaw;     // XA ring depth
     static constexpr int kSmemBudget = 216 * 1024;
     static constexpr int kWStagesRaw = (kSmemBudget - kSlots * kXStage) / kWStage;
-    static constexpr int kWStages = kWStagesRaw > 24 ? 24 : kWStagesRaw;     // W ring depth
+    static constexpr int kWStages = (kWStagesRaw > 24 ? 24 : kWStagesRaw) & ~1;   // W ring depth (even: two producer warps alternate)
     static constexpr int kWOffset = kSlots * kXStage;
     static constexpr int kBarOffset = kWOffset + kWStages * kWStage;
     static constexpr int kNumBars = 2 * kWStages + 3 * kSlots + 2 * kAccStages;
@@ -364,9 +370,15 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                     TRACE(0, it);
                     uint8_t *stage = smem + s * C::kXStage;
                     if (!(a.dbg & 8)) {
-                        mbar_arrive_expect_tx(xfull + s, nk * C::kXBytes);
-                        for (uint32_t sub = 0; sub < nk; ++sub)
-                            tma_load_2d(stage + sub * C::kXBytes, &tmap_x, xfull + s, (int)((kb + sub) * WL_TILE_K), (int)(mt * NTOK));
+                        if (a.x3d) {
+                            // one TMA for all KBS k-blocks: box {64 k, NTOK tokens, KBS k-blocks}; k-blocks past K are zero-filled
+                            mbar_arrive_expect_tx(xfull + s, KBS * C::kXBytes);
+                            tma_load_3d(stage, &tmap_x, xfull + s, 0, (int)(mt * NTOK), (int)kb);
+                        } else {
+                            mbar_arrive_expect_tx(xfull + s, nk * C::kXBytes);
+                            for (uint32_t sub = 0; sub < nk; ++sub)
+                                tma_load_2d(stage + sub * C::kXBytes, &tmap_x, xfull + s, (int)((kb + sub) * WL_TILE_K), (int)(mt * NTOK));
+                        }
                     } else {
                         mbar_arrive(xfull + s);        // timing experiment: no activation traffic
                     }
@@ -374,8 +386,9 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 __syncwarp();
             }
         }
-    } else if (warp == 2) {
-        // ===================== weight producer (runs ahead through the deep W ring) =====================
+    } else if (warp == 2 || warp == 3) {
+        // ===================== weight producers (two warps alternate stages; they run ahead through the deep W ring) =====================
+        const uint32_t me = (uint32_t)(warp - 2);
         ItemIter iter(a);
         Item item;
         uint32_t it = 0;
@@ -384,10 +397,12 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
             const uint8_t *wsrc = a.packed + ((size_t)nt * a.k_blocks) * C::kWBytes;
             const uint2 *psrc = a.dqparams + (size_t)nt * 128;
             for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                if ((it & 1) != me) continue;
                 const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
                 const uint32_t s = it % SW, ph = (it / SW) & 1;
                 mbar_wait(wempty + s, ph ^ 1);
                 if (elect_one()) {
+                    TRACE(2, it);                      // weight producer: W stage free, issuing loads
                     uint8_t *stage = smem_w + s * C::kWStage;
                     mbar_arrive_expect_tx(wfull + s, nk * (C::kWBytes + C::kPBytes));
                     bulk_load(stage, wsrc + (size_t)kb * C::kWBytes, nk * C::kWBytes, wfull + s);
@@ -614,17 +629,32 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)qw->K, (cuuint64_t)M};
-    const cuuint64_t gstride[1] = {(cuuint64_t)qw->K * 2};
-    const cuuint32_t box[2] = {WL_TILE_K, (cuuint32_t)NTOK};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(x_bf16), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const bool x3d = qw->K % WL_TILE_K == 0;
+    CUresult r;
+    if (x3d) {
+        // {64 k (contiguous), M tokens (pitch K*2), K/64 k-blocks (pitch 128 B)}: one box = KBS k-block tiles, each
+        // NTOK x 64 in the SWIZZLE_128B K-major layout the UMMA descriptor expects
+        const cuuint64_t gdim[3] = {WL_TILE_K, (cuuint64_t)M, (cuuint64_t)(qw->K / WL_TILE_K)};
+        const cuuint64_t gstride[2] = {(cuuint64_t)qw->K * 2, (cuuint64_t)WL_TILE_K * 2};
+        const cuuint32_t box[3] = {WL_TILE_K, (cuuint32_t)NTOK, (cuuint32_t)KBS};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(x_bf16), gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t gdim[2] = {(cuuint64_t)qw->K, (cuuint64_t)M};
+        const cuuint64_t gstride[1] = {(cuuint64_t)qw->K * 2};
+        const cuuint32_t box[2] = {WL_TILE_K, (cuuint32_t)NTOK};
+        const cuuint32_t estr[2] = {1, 1};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(x_bf16), gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
 
     UmmaArgs a;
     a.packed = qw->d_packed; a.dqparams = qw->d_dqparams; a.bias = qw->d_bias;
+    a.x3d = x3d ? 1u : 0u;
     a.M = (uint32_t)M; a.N = (uint32_t)qw->N; a.Npad = (uint32_t)(qw->n_tiles * 128);
     a.k_blocks = (uint32_t)qw->k_blocks; a.n_tiles = (uint32_t)qw->n_tiles;
     a.m_tiles = (uint32_t)((M + NTOK - 1) / NTOK);
