@@ -86,6 +86,7 @@ void dllm_ctx_destroy(dllm_ctx *ctx) {
     for (auto &b : ctx->act) if (b.p) cudaFree(b.p);
     if (ctx->lin_ws.p) cudaFree(ctx->lin_ws.p);
     if (ctx->lin_flags.p) cudaFree(ctx->lin_flags.p);
+    if (ctx->gemv_tickets.p) cudaFree(ctx->gemv_tickets.p);
     if (ctx->d_partials) cudaFree(ctx->d_partials);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->d_params) cudaFree(ctx->d_params);
@@ -519,6 +520,7 @@ static int32_t qweight_alloc(dllm_ctx *ctx, size_t K, size_t N, uint8_t bits, si
     if (e == cudaSuccess) e = cudaMalloc(&w->d_scales, G * Npad * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&w->d_zps, G * Npad * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&w->d_dqparams, G * Npad * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_gparams, G * Npad * sizeof(uint2));
     if (e != cudaSuccess) {
         cudaGetLastError();
         dllm_qweight_destroy(w);
@@ -652,6 +654,7 @@ void dllm_qweight_destroy(dllm_qweight *w) {
     if (w->d_scales) cudaFree(w->d_scales);
     if (w->d_zps) cudaFree(w->d_zps);
     if (w->d_dqparams) cudaFree(w->d_dqparams);
+    if (w->d_gparams) cudaFree(w->d_gparams);
     if (w->d_bias) cudaFree(w->d_bias);
     delete w;
 }
@@ -660,7 +663,10 @@ void dllm_qweight_destroy(dllm_qweight *w) {
 // quantized linear
 // ==========================================================================================
 static int resolve_path(const dllm_qweight *w, size_t M, int32_t path) {
-    if (path == DLLM_PATH_AUTO) return k_umma_supported(w, M) ? DLLM_PATH_UMMA : DLLM_PATH_SIMT;
+    if (path == DLLM_PATH_AUTO) {
+        if (k_gemv_supported(w, M)) return DLLM_PATH_GEMV;
+        return k_umma_supported(w, M) ? DLLM_PATH_UMMA : DLLM_PATH_SIMT;
+    }
     return path;
 }
 
@@ -669,10 +675,14 @@ int32_t dllm_qlinear_forward_dev(dllm_ctx *ctx, const dllm_qweight *w, const flo
     CTX_CHECK(ctx);
     ARG_CHECK(ctx, w, DLLM_ERR_NULL, "null weight");
     ARG_CHECK(ctx, M == 0 || (x_dev && y_dev), DLLM_ERR_NULL, "null device pointer");
-    ARG_CHECK(ctx, path >= DLLM_PATH_AUTO && path <= DLLM_PATH_UMMA, DLLM_ERR_INVALID_PARAMS, "unknown path %d", path);
+    ARG_CHECK(ctx, path >= DLLM_PATH_AUTO && path <= DLLM_PATH_GEMV, DLLM_ERR_INVALID_PARAMS, "unknown path %d", path);
     if (M == 0) return DLLM_OK;
     const int p = resolve_path(w, M, path);
     if (p == DLLM_PATH_SIMT) return k_qlinear_simt(ctx, w, x_dev, M, y_dev);
+    if (p == DLLM_PATH_GEMV) {
+        ARG_CHECK(ctx, k_gemv_supported(w, M), DLLM_ERR_UNSUPPORTED, "GEMV path needs 1 <= M <= 16 (got %zu)", M);
+        return k_qlinear_gemv(ctx, w, x_dev, M, y_dev);
+    }
     ARG_CHECK(ctx, k_umma_supported(w, M), DLLM_ERR_UNSUPPORTED, "tcgen05 path does not support this shape");
     DLLM_TRY(ensure_buf(ctx, ctx->act[0], M * w->K * 2));
     DLLM_TRY(k_f32_to_bf16(ctx, x_dev, M * w->K, ctx->act[0].p));
@@ -792,7 +802,11 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
     // widest activation of the stack
     size_t maxw = m->hidden;
     for (auto *w : m->layers) { if (w->N > maxw) maxw = w->N; if (w->K > maxw) maxw = w->K; }
-    bool all_umma = path != DLLM_PATH_SIMT;
+    // few tokens: every layer is HBM-bound -> the GEMV kernel (f32 activations at the boundaries)
+    bool use_gemv = path == DLLM_PATH_AUTO || path == DLLM_PATH_GEMV;
+    for (auto *w : m->layers) use_gemv = use_gemv && k_gemv_supported(w, tokens);
+    if (path == DLLM_PATH_GEMV && !use_gemv) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path needs 1 <= tokens <= 16");
+    bool all_umma = path != DLLM_PATH_SIMT && !use_gemv;
     for (auto *w : m->layers) all_umma = all_umma && k_umma_supported(w, tokens);
     bool any_parallel = false;
     for (int p : m->parallel) any_parallel = any_parallel || p != 0;
@@ -829,7 +843,9 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
         const int par = m->parallel[l];
         const bool gather = par == 1 && (last || m->parallel[l + 1] != 2);
         float *dst = (last && !gather) ? out_dev : bufs[next_buf];
-        if (path != DLLM_PATH_SIMT && k_umma_supported(w, tokens)) {
+        if (use_gemv) {
+            DLLM_TRY(k_qlinear_gemv(ctx, w, cur, tokens, dst));
+        } else if (path != DLLM_PATH_SIMT && k_umma_supported(w, tokens)) {
             DLLM_TRY(k_f32_to_bf16(ctx, cur, tokens * w->K, ctx->act[2].p));
             DLLM_TRY(k_qlinear_umma(ctx, w, ctx->act[2].p, tokens, dst, nullptr));
         } else {

@@ -1,0 +1,664 @@
+// gemv_mma.cu — HBM-bound dequant-GEMV / skinny GEMM for 1..16 tokens (K4 fast path).
+//
+//   y[M,N] = x[M,K] · dequant(W) + b,  M <= 16     (diffuse-llm-rs/src/lib.rs:812 composed with
+//                                                    dequantize_tensor, quantization.rs:81-85)
+//
+// At M <= 16 the op moves K·N·bits/8 bytes of codes for 2·M·K·N flops: it is bound by how fast the
+// packed weights stream out of HBM, so the kernel is organised around the copy engine, not the math:
+//
+//   * one persistent CTA per SM; the k-blocks of all tiles are dealt out in equal contiguous ranges
+//     (k-segment-major stream-K), so every SM streams the same number of bytes;
+//   * a producer warp keeps a deep shared-memory ring (up to 32 stages, > 100 KB in flight per SM) full
+//     with `cp.async.bulk` copies — one 2/4/8 KB packed tile (wlayout.cuh: contiguous in HBM) plus the
+//     tile's 128 scales and zero-points per stage, completion on an mbarrier;
+//   * the CTA's slice of the activations is staged ONCE into shared memory (bf16, fragment order) and
+//     stays resident: no activation traffic in the steady state;
+//   * NG groups of 8 consumer warps take the stages round-robin.  A warp owns 16 output columns of the
+//     128-column tile: it reads its codes with conflict-free LDS.32 and turns them into exact fp16
+//     (q - zp) pairs in registers — 0x6400 | q is the half 1024 + q, 0x6400 | (q << 4) is 1024 + 16 q, so a
+//     32-bit word of eight 4-bit codes costs one shift, four LOP3 and four HSUB2 / HFMA2 — and feeds them to
+//     mma.sync.m16n8k16 (f16 operands, f32 accumulate) with the activations as the B operand.  The group's
+//     scale is applied in f32 to the k-block's partial sum (more accurate than scaling the 16-bit operand).
+//     Tensor cores are used only so that the FMA work costs one instruction per 256 weights: what bounds the
+//     kernel after the copy engine is the ~1.1 CUDA-core instructions per weight of the unpack;
+//   * tiles cut by a range boundary are reduced by the LAST CTA to arrive at the tile (atomic ticket,
+//     no spinning), always in CTA order: results are deterministic and there is no fix-up launch.
+//
+// Numerics: (q - zp) exact, x rounded to fp16 (saturated at +-65504), f32 accumulate, f32 scale.
+// Zero-points must be the integers quantizer B produces (quantization.rs:55-56).
+// Timeline instrumentation (globaltimer stamps per CTA / per stage) compiles in with -DDLLM_GEMV_TRACE.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "wlayout.cuh"
+
+namespace {
+
+constexpr int kGroupWarps = 8;                 // 8 warps x 16 output columns = one 128-column tile
+constexpr int kRedStride = 132;                // padded row of the cross-group reduction buffer (floats)
+constexpr int kSmemBudget = 220 * 1024;      // of the 227 KB a CTA may use
+constexpr int kXBudget = 112 * 1024;           // resident activation slice per CTA
+constexpr int kMaxStages = 32;
+constexpr int kMaxContrib = 160;              // a CTA contributes at most once to a tile, so grid <= kMaxContrib suffices
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "GW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GW_DONE;\n\t"
+        "bra GW_LOOP;\n\t"
+        "GW_DONE:\n\t"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// same wait, returning a zero the compiler cannot see through: adding it to the shared-memory addresses of the
+// loads that follow makes them data-dependent on the wait (they are plain asm loads, free to be scheduled otherwise)
+__device__ __forceinline__ uint32_t mbar_wait_token(uint64_t *bar, uint32_t parity) {
+    uint32_t z;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "GT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "@p bra GT_DONE;\n\t"
+        "bra GT_LOOP;\n\t"
+        "GT_DONE:\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "}\n" : "=r"(z) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return z;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 16-byte asynchronous copy (LDGSTS) whose completion is reported to an mbarrier by cp_async_arrive
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void consumer_bar(int threads) { asm volatile("bar.sync 1, %0;" :: "r"(threads) : "memory"); }
+// D(16 columns x 8 tokens, f32) += A(16 columns x 16 k, f16) · B(16 k x 8 tokens, f16)
+__device__ __forceinline__ void mma_f16(float *d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// (a & mask) | magic in ONE LOP3 (with two immediates the compiler emits two)
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t magic) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2sub(uint32_t a, uint32_t b) {
+    __half2 r = __hsub2(*reinterpret_cast<__half2 *>(&a), *reinterpret_cast<__half2 *>(&b));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+__device__ __forceinline__ uint32_t h2fma(uint32_t a, uint32_t b, uint32_t c) {
+    __half2 r = __hfma2(*reinterpret_cast<__half2 *>(&a), *reinterpret_cast<__half2 *>(&b), *reinterpret_cast<__half2 *>(&c));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    __half2 r = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+
+// k (inside a 64-k block) of element e (0..7) of the 16-byte activation unit that lane quad-index t
+// consumes in round u (0..1); the code words of wlayout.cuh decide it (see consume_stage)
+template <int CB>
+__host__ __device__ __forceinline__ int gemv_kmap(int u, int t, int e) {
+    if (CB == 4) return 32 * u + 8 * t + e;
+    if (CB == 2) return 16 * t + 8 * u + e;
+    return 32 * u + 16 * (e >> 2) + 4 * t + (e & 3);
+}
+
+struct GemvArgs {
+    const uint8_t *packed;
+    const uint2 *gparams;            // [G][Npad] {f32 scale, half2(1024 + zp)}
+    const float *bias;
+    const uint8_t *xb;               // prepared activations: [k_blocks][2 rounds][MT tokens][4 t][8 e] fp16
+    float *y;                        // [M, N]
+    float *partial;                  // [grid * max_items][MT][128]
+    unsigned int *tickets;           // [n_tiles], zero between launches
+    uint32_t M, N, Npad, k_blocks, n_tiles;
+    uint32_t group_magic;            // ceil(2^32 / k-blocks per quantization group): kb / group_kb == umulhi(kb, magic) for kb < 2^16 (0: identity)
+    uint32_t S, P;                   // k segments, CTAs per segment (grid = S * P)
+    uint32_t max_items;              // partial slots per CTA
+    uint32_t stages;                 // ring depth (multiple of NG)
+    uint32_t x_off, red_off, bar_off;   // shared-memory carve-up (bytes)
+    unsigned long long *trace;       // -DDLLM_GEMV_TRACE: per CTA [32] globaltimer stamps, then [4][256] stage stamps of CTA 0
+};
+
+// the k-segment and unit range of one CTA; units of a segment are ordered (tile, k-block)
+struct Range {
+    uint32_t kb_s0, kbs;             // segment = k-blocks [kb_s0, kb_s0 + kbs)
+    uint64_t units, u0, u1;          // units of the segment; this CTA's range
+    __device__ Range(const GemvArgs &a, uint32_t cta) {
+        const uint32_t seg = cta / a.P, j = cta - seg * a.P;
+        kb_s0 = (uint32_t)((uint64_t)a.k_blocks * seg / a.S);
+        kbs = (uint32_t)((uint64_t)a.k_blocks * (seg + 1) / a.S) - kb_s0;
+        units = (uint64_t)a.n_tiles * kbs;
+        u0 = units * j / a.P;
+        u1 = units * (j + 1) / a.P;
+    }
+};
+
+struct Item {
+    uint32_t nt, kb0, kb1, ordinal;
+};
+
+struct ItemIter {
+    uint64_t u, u1;
+    uint32_t kb_s0, kbs, first_nt;
+    __device__ ItemIter(const Range &r) : u(r.u0), u1(r.u1), kb_s0(r.kb_s0), kbs(r.kbs) { first_nt = kbs ? (uint32_t)(r.u0 / kbs) : 0; }
+    __device__ bool next(Item &it) {
+        if (u >= u1) return false;
+        it.nt = (uint32_t)(u / kbs);
+        const uint32_t off = (uint32_t)(u - (uint64_t)it.nt * kbs);
+        const uint64_t left = u1 - u;
+        const uint32_t len = (uint64_t)(kbs - off) <= left ? kbs - off : (uint32_t)left;
+        it.kb0 = kb_s0 + off;
+        it.kb1 = it.kb0 + len;
+        it.ordinal = it.nt - first_nt;
+        u += len;
+        return true;
+    }
+};
+
+// one 64-k block of a 128-column tile, consumed by the 8 warps of one group.
+// Shared-memory addresses, each already offset to this lane's element (lane = 4 g + t, output columns
+// r0 = 16 w + g and r0 + 8):
+//   cw : word t of chunk 0 of column r0 of the packed codes (wlayout.cuh): + 2048 per chunk, + 128 for column r0 + 8
+//   pw : {f32 scale, half2(1024 + zp)} of column r0: + 64 for column r0 + 8
+//   xw : the lane's 16-byte unit of token g in round 0 of the fp16 activations: + 64 MT per round, + 512 for token g + 8
+template <int CB, int MT>
+__device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_t xw, int g, float (*ya)[4]) {
+    constexpr int NB = MT > 8 ? 2 : 1;           // 8-token MMA column blocks
+    constexpr uint32_t kMagic = 0x64006400u;     // half2(1024, 1024)
+    const uint2 p0 = lds64(pw), p1 = lds64(pw + 64);
+    float d[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) d[nb][0] = d[nb][1] = d[nb][2] = d[nb][3] = 0.f;
+
+    // activations of both rounds first: independent of everything else
+    uint4 b[2][NB];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            b[u][nb] = make_uint4(0, 0, 0, 0);
+            if (g + 8 * nb < MT) b[u][nb] = lds128(xw + u * (MT * 64) + nb * 512);
+        }
+
+    if (CB == 4) {
+        // word = codes 0..7 at nibbles {0,4,1,5,2,6,3,7}: (w & 0x000f000f) = codes (0,1), (w & 0x00f000f0) = 16 x codes (2,3),
+        // the same of w >> 8 = codes (4,5), (6,7).   1024 + q - (1024 + zp) and (1024 + 16 q) / 16 - (64 + zp) are exact.
+        const uint32_t kSixteenth = 0x2C002C00u, k960 = 0x63806380u;     // half2(1/16), half2(960)
+        const uint32_t zh0 = h2sub(k960, p0.y), zh1 = h2sub(k960, p1.y);   // -(64 + zp)
+        uint32_t q[2][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { q[u][0] = lds32(cw + u * 2048); q[u][1] = lds32(cw + u * 2048 + 128); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t v0 = h ? q[u][0] >> 8 : q[u][0], v1 = h ? q[u][1] >> 8 : q[u][1];
+                const uint32_t a0 = h2sub(and_or(v0, 0x000f000fu, kMagic), p0.y);
+                const uint32_t a1 = h2sub(and_or(v1, 0x000f000fu, kMagic), p1.y);
+                const uint32_t a2 = h2fma(and_or(v0, 0x00f000f0u, kMagic), kSixteenth, zh0);
+                const uint32_t a3 = h2fma(and_or(v1, 0x00f000f0u, kMagic), kSixteenth, zh1);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
+            }
+        }
+    } else if (CB == 2) {
+        // one word = 16 codes, code i at field (i >> 1) + 8 (i & 1): (w >> 2p) & 0x00030003 = codes (2p, 2p + 1)
+        const uint32_t q0 = lds32(cw), q1 = lds32(cw + 128);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = 4 * u + 2 * h;
+                const uint32_t a0 = h2sub(and_or(q0 >> (2 * p), 0x00030003u, kMagic), p0.y);
+                const uint32_t a1 = h2sub(and_or(q1 >> (2 * p), 0x00030003u, kMagic), p1.y);
+                const uint32_t a2 = h2sub(and_or(q0 >> (2 * p + 2), 0x00030003u, kMagic), p0.y);
+                const uint32_t a3 = h2sub(and_or(q1 >> (2 * p + 2), 0x00030003u, kMagic), p1.y);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
+            }
+        }
+    } else {
+        // 16-k chunks, word t = 4 codes in byte order; PRMT with 0x64 bytes builds half2(1024 + q_i, 1024 + q_j)
+        uint32_t q[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { q[c][0] = lds32(cw + c * 2048); q[c][1] = lds32(cw + c * 2048 + 128); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = 2 * u + h;
+                const uint32_t a0 = h2sub(__byte_perm(q[c][0], kMagic, 0x5150), p0.y);
+                const uint32_t a1 = h2sub(__byte_perm(q[c][1], kMagic, 0x5150), p1.y);
+                const uint32_t a2 = h2sub(__byte_perm(q[c][0], kMagic, 0x5352), p0.y);
+                const uint32_t a3 = h2sub(__byte_perm(q[c][1], kMagic, 0x5352), p1.y);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
+            }
+        }
+    }
+    // dequantize_tensor's `* scale` (quantization.rs:83), applied to the k-block's partial sum in f32
+    const float s0 = __uint_as_float(p0.x), s1 = __uint_as_float(p1.x);
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+        ya[nb][0] = fmaf(s0, d[nb][0], ya[nb][0]);
+        ya[nb][1] = fmaf(s0, d[nb][1], ya[nb][1]);
+        ya[nb][2] = fmaf(s1, d[nb][2], ya[nb][2]);
+        ya[nb][3] = fmaf(s1, d[nb][3], ya[nb][3]);
+    }
+}
+
+template <int CB, int MT, int NG, int NP, int KBS>
+__global__ void __launch_bounds__((NG * kGroupWarps + NP) * 32, 1)
+gemv_mma_kernel(const GemvArgs a) {
+    constexpr int NB = MT > 8 ? 2 : 1;
+    constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
+    constexpr int kStage = KBS * (kWBytes + 1024);   // KBS code tiles, then KBS x (128 scales + 128 zero-points)
+    constexpr int kXTile = MT * 128;             // activations of one k-block
+    constexpr int kConsumers = NG * kGroupWarps * 32;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *ring = smem;
+    uint8_t *xs = smem + a.x_off;
+    float *red = reinterpret_cast<float *>(smem + a.red_off);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.bar_off);
+    uint64_t *empty = full + a.stages;
+    uint64_t *xfull = empty + a.stages;
+    uint32_t *last_flag = reinterpret_cast<uint32_t *>(xfull + 1);   // [0] last arriver?  [1] contributors  [2..] their slots
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const Range rg(a, blockIdx.x);
+#ifdef DLLM_GEMV_TRACE
+#define STRACE(role, idx) do { if (blockIdx.x == 0 && (idx) < 256) { unsigned long long _t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(_t)); a.trace[gridDim.x * 32 + (role) * 256 + (idx)] = _t; } } while (0)
+#define GTRACE(slot) do { if ((slot) < 32) { unsigned long long _t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(_t)); a.trace[blockIdx.x * 32 + (slot)] = _t; } } while (0)
+#else
+#define STRACE(role, idx) do { } while (0)
+#define GTRACE(slot) do { } while (0)
+#endif
+    if (threadIdx.x == 0) GTRACE(0);
+
+    if (threadIdx.x == 0) {
+        // full: one arrival per lane of the owning producer warp, triggered when that lane's cp.async copies landed
+        for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(full + s, 32); mbar_init(empty + s, kGroupWarps); }
+        mbar_init(xfull, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp >= NG * kGroupWarps) {
+        // ===================== producers: NP warps take the stages round-robin =====================
+        // (the mbarrier / bulk-copy instructions of ONE warp cost ~100 cycles each and do not overlap, so a
+        //  single producer warp caps the SM at a fraction of its HBM share; NP warps and KBS tiles per copy
+        //  lift that cap)
+        const uint32_t me = (uint32_t)(warp - NG * kGroupWarps);
+        if (me == 0 && rg.u0 < rg.u1 && elect_one()) {   // the CTA's activation slice, once
+            const uint32_t xbytes = rg.kbs * kXTile;
+            mbar_arrive_expect_tx(xfull, xbytes);
+            const uint8_t *src = a.xb + (size_t)rg.kb_s0 * kXTile;
+            for (uint32_t off = 0; off < xbytes; off += 16384)
+                bulk_load(xs + off, src + off, xbytes - off < 16384 ? xbytes - off : 16384, xfull);
+        }
+        __syncwarp();
+        ItemIter iter(rg);
+        Item item;
+        uint32_t it0 = 0, my_it = me, my_s = me, my_ph = 0;
+        while (iter.next(item)) {
+            const uint32_t it1 = it0 + (item.kb1 - item.kb0 + KBS - 1) / KBS;
+            const uint8_t *wsrc = a.packed + (size_t)item.nt * a.k_blocks * kWBytes;
+            const uint2 *psrc = a.gparams + (size_t)item.nt * 128;
+            for (; my_it < it1; my_it += NP) {
+                const uint32_t kb = item.kb0 + (my_it - it0) * KBS;
+                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                mbar_wait(empty + my_s, my_ph ^ 1);
+                if (lane == 0) STRACE(0, my_it);
+                uint8_t *st = ring + (size_t)my_s * kStage;
+                // Everything rides on 16-byte cp.async (LDGSTS) of the warp's 32 lanes; each lane's arrival on the
+                // stage's mbarrier fires when its copies have landed.  (cp.async.bulk was measured no faster, and
+                // its issue costs the single elected thread ~100 cycles per copy.)
+                const uint8_t *src = wsrc + (size_t)kb * kWBytes;
+#pragma unroll 8
+                for (uint32_t i = lane; i < nk * (kWBytes / 16); i += 32) cp_async16(st + i * 16, src + (size_t)i * 16);
+#pragma unroll
+                for (int sub = 0; sub < KBS; ++sub) {
+                    if ((uint32_t)sub < nk) {
+                        const uint2 *pg = psrc + (size_t)(a.group_magic ? __umulhi(kb + sub, a.group_magic) : kb + sub) * a.Npad;
+                        cp_async16(st + KBS * kWBytes + sub * 1024 + lane * 16, pg + lane * 2);
+                        cp_async16(st + KBS * kWBytes + sub * 1024 + 512 + lane * 16, pg + 64 + lane * 2);
+                    }
+                }
+                cp_async_arrive(full + my_s);
+                if (lane == 0) STRACE(1, my_it);
+                __syncwarp();
+                my_s += NP;
+                if (my_s >= a.stages) { my_s -= a.stages; my_ph ^= 1; }
+            }
+            it0 = it1;
+        }
+    } else {
+        // ===================== consumers =====================
+        const int grp = warp / kGroupWarps, w = warp % kGroupWarps;
+        const int g = lane >> 2, t = lane & 3;
+        const int ctid = threadIdx.x;            // consumer warps come first: 0 .. kConsumers-1
+        float ya[NB][4];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) ya[nb][0] = ya[nb][1] = ya[nb][2] = ya[nb][3] = 0.f;
+        // per-lane shared-memory addresses (see consume_kblock)
+        const uint32_t ring_cw = smem_u32(ring) + ((16 * w + g) * 4 + t) * 4;
+        const uint32_t ring_pw = smem_u32(ring) + KBS * kWBytes + (16 * w + g) * 8;
+        const uint32_t xs_lane = smem_u32(xs) + g * 64 + 16 * t;
+        if (ctid == 0) GTRACE(1);
+        if (rg.u0 < rg.u1) mbar_wait(xfull, 0);
+        if (ctid == 0) GTRACE(2);
+        uint32_t n_item = 0;
+        ItemIter iter(rg);
+        Item item;
+        // stage counter `it` of the CTA; this group owns the stages with it % NG == grp.  (my_it, my_s, my_ph)
+        // walk this group's stages only — no per-stage bookkeeping for the other groups' stages
+        uint32_t it0 = 0, my_it = (uint32_t)grp, my_s = (uint32_t)grp, my_ph = 0;
+        while (iter.next(item)) {
+            const uint32_t it1 = it0 + (item.kb1 - item.kb0 + KBS - 1) / KBS;
+            const uint32_t xitem = xs_lane + (item.kb0 - rg.kb_s0) * kXTile;
+            for (; my_it < it1; my_it += NG) {
+                const uint32_t kbo = (my_it - it0) * KBS;           // k-block offset inside the item
+                const uint32_t nk = item.kb1 - item.kb0 - kbo < (uint32_t)KBS ? item.kb1 - item.kb0 - kbo : (uint32_t)KBS;
+                const uint32_t so = my_s * kStage + mbar_wait_token(full + my_s, my_ph);
+                if (ctid == 0 && my_it == 0) GTRACE(3);
+                if (w == 0 && lane == 0) STRACE(2, my_it);
+#pragma unroll
+                for (int sub = 0; sub < KBS; ++sub)
+                    if ((uint32_t)sub < nk)
+                        consume_kblock<CB, MT>(ring_cw + so + sub * kWBytes, ring_pw + so + sub * 1024, xitem + (kbo + sub) * kXTile, g, ya);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + my_s);
+                if (w == 0 && lane == 0) STRACE(3, my_it);
+                my_s += NG;
+                if (my_s >= a.stages) { my_s -= a.stages; my_ph ^= 1; }
+            }
+            it0 = it1;
+            if (ctid == 0) GTRACE(4 + 2 * n_item);
+            // ---------- tile (or tile part) done: reduce over the consumer groups, then write ----------
+            float *mine = red + (size_t)grp * (MT * kRedStride);
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const int tok = 8 * nb + 2 * t;
+                if (tok < MT) { mine[tok * kRedStride + 16 * w + g] = ya[nb][0]; mine[tok * kRedStride + 16 * w + g + 8] = ya[nb][2]; }
+                if (tok + 1 < MT) { mine[(tok + 1) * kRedStride + 16 * w + g] = ya[nb][1]; mine[(tok + 1) * kRedStride + 16 * w + g + 8] = ya[nb][3]; }
+                ya[nb][0] = ya[nb][1] = ya[nb][2] = ya[nb][3] = 0.f;
+            }
+            consumer_bar(kConsumers);
+            // contributors of this tile: per segment the CTAs whose range touches its units
+            const bool whole = a.S == 1 && item.kb0 == rg.kb_s0 && item.kb1 == rg.kb_s0 + rg.kbs;
+            float *dst = whole ? nullptr : a.partial + ((size_t)blockIdx.x * a.max_items + item.ordinal) * (MT * 128);
+            for (int e = ctid; e < MT * 128; e += kConsumers) {
+                const int tok = e >> 7, nl = e & 127;
+                float v = 0.f;
+#pragma unroll
+                for (int q = 0; q < NG; ++q) v += red[(size_t)q * (MT * kRedStride) + tok * kRedStride + nl];
+                if (whole) {
+                    const uint32_t n = item.nt * 128 + nl;
+                    if ((uint32_t)tok < a.M && n < a.N) a.y[(size_t)tok * a.N + n] = v + (a.bias ? __ldg(a.bias + n) : 0.f);
+                } else {
+                    dst[e] = v;
+                }
+            }
+            if (!whole) {
+                __threadfence();
+                consumer_bar(kConsumers);
+                if (ctid == 0) {
+                    // contributors of this tile, in the fixed order (segment, CTA): their partial slots
+                    uint32_t cnt = 0;
+                    for (uint32_t sg = 0; sg < a.S; ++sg) {
+                        const uint32_t k0 = (uint32_t)((uint64_t)a.k_blocks * sg / a.S);
+                        const uint32_t kn = (uint32_t)((uint64_t)a.k_blocks * (sg + 1) / a.S) - k0;
+                        const uint64_t U = (uint64_t)a.n_tiles * kn, a0 = (uint64_t)item.nt * kn, a1 = a0 + kn;
+                        const uint32_t j_lo = (uint32_t)(((a0 + 1) * a.P - 1) / U), j_hi = (uint32_t)((a1 * a.P - 1) / U);
+                        for (uint32_t j = j_lo; j <= j_hi; ++j) {
+                            const uint32_t first_nt = (uint32_t)((U * j / a.P) / kn);
+                            if (cnt < kMaxContrib) last_flag[2 + cnt] = (sg * a.P + j) * a.max_items + (item.nt - first_nt);
+                            ++cnt;
+                        }
+                    }
+                    const uint32_t old = atomicAdd(a.tickets + item.nt, 1u);
+                    const uint32_t last = old + 1 == cnt ? 1u : 0u;
+                    if (last) a.tickets[item.nt] = 0;      // every contributor has arrived: re-arm for the next launch
+                    last_flag[0] = last;
+                    last_flag[1] = cnt;
+                }
+                consumer_bar(kConsumers);
+                if (last_flag[0]) {
+                    __threadfence();
+                    const uint32_t cnt = last_flag[1];
+                    for (int e = ctid; e < MT * 128; e += kConsumers) {
+                        const int tok = e >> 7, nl = e & 127;
+                        const uint32_t n = item.nt * 128 + nl;
+                        if ((uint32_t)tok >= a.M || n >= a.N) continue;
+                        float v = 0.f;
+                        for (uint32_t c = 0; c < cnt; ++c) v += __ldcg(a.partial + (size_t)last_flag[2 + c] * (MT * 128) + e);
+                        a.y[(size_t)tok * a.N + n] = v + (a.bias ? __ldg(a.bias + n) : 0.f);
+                    }
+                }
+            }
+            consumer_bar(kConsumers);            // `red` and `last_flag` are reused by the next item
+            if (ctid == 0) GTRACE(5 + 2 * n_item);
+            ++n_item;
+        }
+    }
+}
+
+// x[M,K] f32 -> fp16 in the order the consumer lanes read it: [k-block][round u][token][t][e]
+template <int CB>
+__global__ void __launch_bounds__(256)
+gemv_xprep_kernel(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t k_blocks, uint32_t MT, uint4 *__restrict__ xb) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte unit per thread
+    const uint32_t total = k_blocks * 2 * MT * 4;
+    if (idx >= total) return;
+    const uint32_t t = idx & 3, tok = (idx >> 2) % MT, u = ((idx >> 2) / MT) & 1, kb = (idx >> 2) / (MT * 2);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t k = kb * WL_TILE_K + (uint32_t)gemv_kmap<CB>((int)u, (int)t, e);
+        v[e] = (tok < M && k < K) ? __ldg(x + (size_t)tok * K + k) : 0.f;
+    }
+    uint4 o;
+    o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]);
+    xb[idx] = o;
+}
+
+template <int CB, int MT>
+int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
+    // NP == NG: a ring slot must always be filled by the same producer warp and drained by the same consumer
+    // group (the stage count is a multiple of both) — parity waits of different warps on one slot could alias
+    constexpr int NG = 3, NP = 3, KBS = 2;
+    static_assert(NG % NP == 0 || NP % NG == 0, "ring depth is a multiple of max(NG, NP) only");
+    constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
+    constexpr int kStage = KBS * (kWBytes + 1024);
+    constexpr int kXTile = MT * 128;
+    const uint32_t k_blocks = (uint32_t)qw->k_blocks, n_tiles = (uint32_t)qw->n_tiles;
+    const uint32_t sms = (uint32_t)ctx->sm_count;
+
+    // k segments: the fewest such that a CTA's activation slice leaves room for a ring of >= 8 stages
+    const uint32_t red_bytes = NG * MT * kRedStride * 4;
+    uint32_t S = 1;
+    for (;; ++S) {
+        const uint64_t xb = (uint64_t)((k_blocks + S - 1) / S) * kXTile;
+        if (S >= k_blocks || (xb <= (uint64_t)kXBudget && xb + red_bytes + 1024 + 8ull * kStage <= (uint64_t)kSmemBudget)) break;
+    }
+    uint32_t P = sms / S;
+    if (P == 0) { P = 1; }
+    // small problems: at least 4 k-blocks per CTA
+    const uint64_t total_units = (uint64_t)n_tiles * k_blocks;
+    while (P > 1 && total_units / ((uint64_t)S * P) < 4) --P;
+    while (S * P > (uint32_t)kMaxContrib) --P;
+    const uint32_t grid = S * P;
+
+    GemvArgs a;
+    a.packed = qw->d_packed; a.gparams = qw->d_gparams; a.bias = qw->d_bias;
+    a.y = y;
+    a.M = (uint32_t)M; a.N = (uint32_t)qw->N; a.Npad = n_tiles * 128; a.k_blocks = k_blocks; a.n_tiles = n_tiles;
+    const uint32_t group_kb = qw->per_tensor ? k_blocks : (uint32_t)(qw->group / WL_TILE_K);
+    if (k_blocks >= 65536) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path: K too large");
+    a.group_magic = group_kb == 1 ? 0u : (uint32_t)(((1ull << 32) + group_kb - 1) / group_kb);   // 0: one k-block per group
+    a.S = S; a.P = P;
+    a.trace = nullptr;
+#ifdef DLLM_GEMV_TRACE
+    DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, ((size_t)grid * 32 + 1024) * 8));
+    a.trace = (unsigned long long *)ctx->lin_flags.p;
+    cudaMemsetAsync(a.trace, 0, ((size_t)grid * 32 + 1024) * 8, ctx->stream);
+#endif
+    const uint32_t kbs_max = (k_blocks + S - 1) / S, kbs_min = k_blocks / S;
+    const uint64_t len_max = ((uint64_t)n_tiles * kbs_max + P - 1) / P;
+    a.max_items = (uint32_t)(len_max / (kbs_min ? kbs_min : 1)) + 2;
+
+    const uint32_t xbytes = kbs_max * kXTile;
+    uint32_t stages = (uint32_t)((kSmemBudget - xbytes - red_bytes - 1024) / kStage);
+    if (stages > (uint32_t)kMaxStages) stages = kMaxStages;
+    stages -= stages % (NG > NP ? NG : NP);
+    if (stages < 2 * NG || stages <= (uint32_t)NP) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path: shared-memory ring too small");
+    a.stages = stages;
+    a.x_off = stages * kStage;
+    a.red_off = a.x_off + ((xbytes + 127) & ~127u);
+    a.bar_off = a.red_off + ((red_bytes + 127) & ~127u);
+    const size_t smem_bytes = a.bar_off + (2 * stages + 1) * 8 + (2 + kMaxContrib) * 4;
+
+    DLLM_TRY(ensure_buf(ctx, ctx->act[2], (size_t)k_blocks * kXTile));
+    DLLM_TRY(ensure_buf(ctx, ctx->lin_ws, (size_t)grid * a.max_items * MT * 128 * sizeof(float)));
+    if (ctx->gemv_tickets.cap < n_tiles * sizeof(unsigned int)) {
+        DLLM_TRY(ensure_buf(ctx, ctx->gemv_tickets, n_tiles * sizeof(unsigned int)));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->gemv_tickets.p, 0, ctx->gemv_tickets.cap, ctx->stream));
+    }
+    a.xb = (const uint8_t *)ctx->act[2].p;
+    a.partial = (float *)ctx->lin_ws.p;
+    a.tickets = (unsigned int *)ctx->gemv_tickets.p;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_mma_kernel<CB, MT, NG, NP, KBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const uint32_t units16 = k_blocks * 2 * MT * 4;
+    gemv_xprep_kernel<CB><<<(units16 + 255) / 256, 256, 0, ctx->stream>>>(x, (uint32_t)M, (uint32_t)qw->K, k_blocks, MT, (uint4 *)ctx->act[2].p);
+    LAUNCH_CHECK(ctx);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->prof_on) {
+        while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) {
+            cudaEvent_t e;
+            CUDA_TRY(ctx, cudaEventCreate(&e));
+            ctx->prof_ev.push_back(e);
+        }
+        ev0 = ctx->prof_ev[2 * ctx->prof_n];
+        ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
+        CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    gemv_mma_kernel<CB, MT, NG, NP, KBS><<<grid, (NG * kGroupWarps + NP) * 32, smem_bytes, ctx->stream>>>(a);
+    LAUNCH_CHECK(ctx);
+    if (ev1) {
+        CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
+        ctx->prof_n++;
+        ctx->prof_flops += 2.0 * (double)M * (double)qw->K * (double)qw->N;
+        ctx->prof_bytes += (double)qw->K * qw->N * qw->bits / 8.0 + (double)(qw->K / qw->group) * qw->N * 8.0 +
+                           4.0 * M * qw->K + 4.0 * M * qw->N;
+    }
+#ifdef DLLM_GEMV_TRACE
+    {   // dump the per-CTA timeline (timing experiments only)
+        std::vector<unsigned long long> h((size_t)grid * 32 + 1024);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h.data(), a.trace, h.size() * 8, cudaMemcpyDeviceToHost);
+        FILE *f = fopen("gpurun_out/gemv_trace.csv", "w");
+        if (f) {
+            unsigned long long t0 = ~0ull;
+            for (uint32_t c = 0; c < grid; ++c) if (h[c * 32] && h[c * 32] < t0) t0 = h[c * 32];
+            fprintf(f, "cta,start,cons_start,x_ready,first_full,then (item_done, flush_done)...  [ns since the first CTA started]\n");
+            for (uint32_t c = 0; c < grid; ++c) {
+                fprintf(f, "%u", c);
+                for (int i = 0; i < 32; ++i) fprintf(f, ",%lld", h[c * 32 + i] ? (long long)(h[c * 32 + i] - t0) : -1ll);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+        f = fopen("gpurun_out/gemv_stages.csv", "w");
+        if (f) {
+            unsigned long long t0 = h[0];
+            fprintf(f, "it,prod_empty_ok,prod_issued,cons_full_ok,cons_done  [ns since CTA 0 started]\n");
+            for (int i = 0; i < 256; ++i) {
+                fprintf(f, "%d", i);
+                for (int r = 0; r < 4; ++r) { unsigned long long v = h[(size_t)grid * 32 + r * 256 + i]; fprintf(f, ",%lld", v ? (long long)(v - t0) : -1ll); }
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
+#endif
+    return DLLM_OK;
+}
+
+template <int CB>
+int32_t launch_gemv_mt(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
+    if (M <= 1) return launch_gemv_mma<CB, 1>(ctx, qw, x, M, y);
+    if (M <= 2) return launch_gemv_mma<CB, 2>(ctx, qw, x, M, y);
+    if (M <= 4) return launch_gemv_mma<CB, 4>(ctx, qw, x, M, y);
+    if (M <= 8) return launch_gemv_mma<CB, 8>(ctx, qw, x, M, y);
+    return launch_gemv_mma<CB, 16>(ctx, qw, x, M, y);
+}
+
+}  // namespace
+
+bool k_gemv_supported(const dllm_qweight *qw, size_t M) {
+    return qw && M >= 1 && M <= 16 && (qw->per_tensor || qw->group % WL_TILE_K == 0);
+}
+
+int32_t k_qlinear_gemv(dllm_ctx *ctx, const dllm_qweight *qw, const float *x_dev, size_t M, float *y_dev) {
+    if (!k_gemv_supported(qw, M)) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path: 1 <= M <= 16 required");
+    switch (wl_container_bits(qw->bits)) {
+        case 2: return launch_gemv_mt<2>(ctx, qw, x_dev, M, y_dev);
+        case 4: return launch_gemv_mt<4>(ctx, qw, x_dev, M, y_dev);
+        default: return launch_gemv_mt<8>(ctx, qw, x_dev, M, y_dev);
+    }
+}

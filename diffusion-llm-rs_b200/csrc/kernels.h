@@ -42,6 +42,11 @@ int32_t k_wexport_codes(dllm_ctx *ctx, const dllm_qweight *qw, uint8_t *codes_de
 // y[M,N] = x[M,K] · dequant(W) + b, f32 CUDA cores, any M (tiled by 8 rows)
 int32_t k_qlinear_simt(dllm_ctx *ctx, const dllm_qweight *qw, const float *x_dev, size_t M, float *y_dev);
 
+// ---- gemv_mma.cu ----
+// HBM-bound path for 1..16 tokens: bulk-copy ring + mma.sync on in-register dequantized bf16 codes
+int32_t k_qlinear_gemv(dllm_ctx *ctx, const dllm_qweight *qw, const float *x_dev, size_t M, float *y_dev);
+bool k_gemv_supported(const dllm_qweight *qw, size_t M);
+
 // ---- umma_gemm.cu ----
 // tcgen05 path.  x_bf16_dev: [M, K] bf16 row-major.  out_f32 / out_bf16: either may be null.
 int32_t k_qlinear_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M,

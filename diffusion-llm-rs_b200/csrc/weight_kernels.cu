@@ -79,8 +79,9 @@ wpack_kernel(const SRC *__restrict__ src, size_t K, size_t N, size_t Npad, size_
 //   2/4-bit: x = bf16x2(128 + zp)   (subtracted from the magic-number form 128 + q, exact)
 //   8-bit  : x = f32 bits of zp
 //   y = bf16x2(scale)
+// and for the GEMV path (fp16 operands): {f32 scale, half2(1024 + zp)} — 0x6400 | q is the half 1024 + q
 __global__ void wdq_params_kernel(const float *__restrict__ scales, const float *__restrict__ zps, size_t n, int cb,
-                                  uint2 *__restrict__ out) {
+                                  uint2 *__restrict__ out, uint2 *__restrict__ gout) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float s = scales[i], z = zps[i];
@@ -94,6 +95,8 @@ __global__ void wdq_params_kernel(const float *__restrict__ scales, const float 
         o.x = *reinterpret_cast<uint32_t *>(&zb);
     }
     out[i] = o;
+    __half2 zh = __float2half2_rn(1024.0f + z);
+    gout[i] = make_uint2(__float_as_uint(s), *reinterpret_cast<uint32_t *>(&zh));
 }
 
 template <int CB>
@@ -161,7 +164,7 @@ int32_t k_wdq_params(dllm_ctx *ctx, dllm_qweight *qw) {
     const size_t G = qw->per_tensor ? 1 : qw->K / qw->group;
     const size_t n = G * qw->n_tiles * 128;
     wdq_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(qw->d_scales, qw->d_zps, n,
-                                                                            wl_container_bits(qw->bits), qw->d_dqparams);
+                                                                            wl_container_bits(qw->bits), qw->d_dqparams, qw->d_gparams);
     LAUNCH_CHECK(ctx);
     return DLLM_OK;
 }

@@ -9,9 +9,9 @@ behaviour).  Everything computes on the GPU through the C ABI; there is no CPU f
 """
 from . import _lib
 from ._lib import (DllmError, QuantizationError, InvalidParams, UnsupportedOperation, ShapeMismatch,
-                   CalibrationRequired, ReferencePanic, NoDevice, PATH_AUTO, PATH_SIMT, PATH_UMMA)
+                   CalibrationRequired, ReferencePanic, NoDevice, PATH_AUTO, PATH_SIMT, PATH_UMMA, PATH_GEMV)
 from .runtime import Context, QWeight, dequant_matmul, default_context
 
 __all__ = ["Context", "QWeight", "dequant_matmul", "default_context", "DllmError", "QuantizationError",
            "InvalidParams", "UnsupportedOperation", "ShapeMismatch", "CalibrationRequired", "ReferencePanic",
-           "NoDevice", "PATH_AUTO", "PATH_SIMT", "PATH_UMMA"]
+           "NoDevice", "PATH_AUTO", "PATH_SIMT", "PATH_UMMA", "PATH_GEMV"]

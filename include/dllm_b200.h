@@ -66,7 +66,8 @@ enum {
 enum {
     DLLM_PATH_AUTO = 0,
     DLLM_PATH_SIMT = 1,  /* f32 CUDA-core dequant-GEMV (exact f32 dequant, f32 accumulate) */
-    DLLM_PATH_UMMA = 2   /* tcgen05 / TMEM path: bf16 operands dequantized on the fly, f32 accumulate */
+    DLLM_PATH_UMMA = 2,  /* tcgen05 / TMEM path: bf16 operands dequantized on the fly, f32 accumulate */
+    DLLM_PATH_GEMV = 3   /* 1..16 tokens, HBM-bound: bulk-copy ring + mma.sync on exact bf16 (q - zp), f32 scale and accumulate */
 };
 
 typedef struct dllm_ctx dllm_ctx;

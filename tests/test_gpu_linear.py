@@ -165,6 +165,95 @@ def test_dequant_matmul_example_config0(ctx, O):
     assert np.max(np.abs(y - y32)) <= 4e-5 * bound
 
 
+# ---------------------------------------------------------------- linear, HBM-bound GEMV path (1..16 tokens)
+def gemv_check(y, y64, bound):
+    """x is rounded to bf16 (relative 2^-9 per element), (q - zp) is exact, scale and accumulation are
+    f32: the error of every output is bounded by 2^-9 * sum|x||w| plus f32 summation noise."""
+    err = np.abs(y - y64)
+    assert np.all(err <= (2.0 ** -9 + 5e-5) * bound + 1e-6), float((err / (bound + 1e-30)).max())
+    assert np.linalg.norm(y - y64) <= 1e-2 * np.linalg.norm(y64)
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 7, 8, 9, 16])
+def test_qlinear_gemv_matches_oracle(ctx, O, bits, M):
+    from dllm_b200 import QWeight, PATH_GEMV
+    rng = np.random.default_rng(M * 100 + bits)
+    K, N = 1024, 384
+    w = make_w(rng, K, N)
+    x = rng.standard_normal((M, K)).astype(F)
+    bias = rng.standard_normal(N).astype(F)
+    qw = QWeight.quantize(ctx, w, bits, 128, bias)
+    y = qw.forward(x, PATH_GEMV)
+    _, y64, bound = ref_linear(O, x, w, bits, 128, bias)
+    gemv_check(y, y64, bound)
+    qw.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 10, 5), (200, 130, 5), (4096, 256, 3), (8192, 512, 16), (14336, 256, 16),
+                                   (14336, 128, 8), (2048, 4096, 1)])
+@pytest.mark.parametrize("group", [0, 128])
+def test_qlinear_gemv_shapes(ctx, O, shape, group):
+    """ragged K / N (padding), per-tensor parameters (group 0, the reference's own scheme), and K large
+    enough that the activations are split into k segments (several CTAs reduce into one tile)."""
+    from dllm_b200 import QWeight, PATH_GEMV
+    K, N, M = shape
+    if group and K % group:
+        pytest.skip("grouped weights need K % group == 0")
+    rng = np.random.default_rng(K + N + M)
+    w = make_w(rng, K, N)
+    x = rng.standard_normal((M, K)).astype(F)
+    qw = QWeight.quantize(ctx, w, 4, group)
+    y = qw.forward(x, PATH_GEMV)
+    _, y64, bound = ref_linear(O, x, w, 4, group, None)
+    gemv_check(y, y64, bound)
+    y2 = qw.forward(x, PATH_GEMV)              # tickets re-armed; fixed reduction order
+    assert beq(y, y2)
+    qw.close()
+
+
+def test_qlinear_auto_path_small_m_is_gemv(ctx, O):
+    from dllm_b200 import QWeight, PATH_AUTO, PATH_GEMV
+    rng = np.random.default_rng(5)
+    w = make_w(rng, 512, 256)
+    x = rng.standard_normal((4, 512)).astype(F)
+    qw = QWeight.quantize(ctx, w, 4, 128)
+    assert beq(qw.forward(x, PATH_AUTO), qw.forward(x, PATH_GEMV))
+    import dllm_b200
+    with pytest.raises(dllm_b200.QuantizationError):
+        qw.forward(rng.standard_normal((17, 512)).astype(F), PATH_GEMV)
+    qw.close()
+
+
+@pytest.mark.parametrize("bits,M", [(4, 1), (4, 16), (2, 4), (8, 8)])
+def test_qlinear_gemv_full_width(ctx, bits, M):
+    """Full BASELINE width (K=N=14336): the GEMV path against the f32-faithful SIMT path, run-to-run
+    determinism, and exact linearity under power-of-two scaling."""
+    import torch
+    from dllm_b200 import QWeight, PATH_SIMT, PATH_GEMV
+    K = N = 14336
+    g = torch.Generator(device="cuda").manual_seed(bits * 100 + M)
+    w = torch.randn(K, N, device="cuda", generator=g) * 0.02
+    x = torch.randn(M, K, device="cuda", generator=g)
+    y1, y2, y3, y4 = (torch.empty(M, N, device="cuda") for _ in range(4))
+    torch.cuda.synchronize()
+    qw = QWeight.quantize_dev(ctx, w.data_ptr(), K, N, bits, 128)
+    qw.forward_dev(x.data_ptr(), M, y1.data_ptr(), PATH_SIMT)
+    qw.forward_dev(x.data_ptr(), M, y2.data_ptr(), PATH_GEMV)
+    qw.forward_dev(x.data_ptr(), M, y3.data_ptr(), PATH_GEMV)
+    x2 = x * 4
+    torch.cuda.synchronize()
+    qw.forward_dev(x2.data_ptr(), M, y4.data_ptr(), PATH_GEMV)
+    ctx.sync()
+    assert float((y1 - y2).abs().max()) <= 4e-3 * float(y1.abs().max())
+    assert float(torch.linalg.norm(y1 - y2)) <= 3e-3 * float(torch.linalg.norm(y1))
+    assert torch.equal(y2, y3)
+    # power-of-two scaling commutes with every rounding of the path except for the handful of activations that are
+    # fp16-subnormal (|x| < 6.1e-5) before the scaling
+    assert float((y4 - y2 * 4).abs().max()) <= 1e-5 * float(y2.abs().max())
+    qw.close()
+
+
 # ---------------------------------------------------------------- linear, tcgen05 path
 def umma_check(y, y64):
     err = np.abs(y - y64)
