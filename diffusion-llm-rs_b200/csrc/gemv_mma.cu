@@ -47,9 +47,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -64,9 +61,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "GW_DONE:\n\t"
         "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// producer-side wait: the thread may stay suspended for up to `ns` before the try_wait returns false — a producer
+// that polls a barrier in a tight loop steals issue slots from the consumer warps (measured: 27% of all issued
+// instructions), and it is never latency-critical: it runs a whole ring ahead
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "GR_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra GR_DONE;\n\t"
+        "bra GR_LOOP;\n\t"
+        "GR_DONE:\n\t"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
 // same wait, returning a zero the compiler cannot see through: adding it to the shared-memory addresses of the
 // loads that follow makes them data-dependent on the wait (they are plain asm loads, free to be scheduled otherwise)
-__device__ __forceinline__ uint32_t mbar_wait_token(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ uint32_t mbar_wait_token(uint32_t bar, uint32_t parity) {
     uint32_t z;
     asm volatile(
         "{\n\t"
@@ -77,7 +91,7 @@ __device__ __forceinline__ uint32_t mbar_wait_token(uint64_t *bar, uint32_t pari
         "bra GT_LOOP;\n\t"
         "GT_DONE:\n\t"
         "mov.u32 %0, 0;\n\t"
-        "}\n" : "=r"(z) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" : "=r"(z) : "r"(bar), "r"(parity) : "memory");
     return z;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
@@ -118,7 +132,14 @@ __device__ __forceinline__ bool elect_one() {
         "}\n" : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void consumer_bar(int threads) { asm volatile("bar.sync 1, %0;" :: "r"(threads) : "memory"); }
+// named barriers: kBarConsumers — among the consumer warps; kBarPartial — consumers arrive once a partial tile is
+// in global memory, the epilogue warp waits for it; kBarFinal — the epilogue warp arrives with its verdict on the
+// CTA's last tile, the consumers wait for it (they have nothing else left to do and help with that reduction)
+// kBarEpiFree — the epilogue warp is ready for the next partial tile (a named barrier must not collect the arrivals of
+// two tiles at once, so the consumers wait for it before they arrive on kBarPartial again)
+constexpr int kBarConsumers = 1, kBarPartial = 2, kBarFinal = 3, kBarEpiFree = 4;
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 // D(16 columns x 8 tokens, f32) += A(16 columns x 16 k, f16) · B(16 k x 8 tokens, f16)
 __device__ __forceinline__ void mma_f16(float *d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -210,9 +231,11 @@ struct ItemIter {
 // r0 = 16 w + g and r0 + 8):
 //   cw : word t of chunk 0 of column r0 of the packed codes (wlayout.cuh): + 2048 per chunk, + 128 for column r0 + 8
 //   pw : {f32 scale, half2(1024 + zp)} of column r0: + 64 for column r0 + 8
-//   xw : the lane's 16-byte unit of token g in round 0 of the fp16 activations: + 64 MT per round, + 512 for token g + 8
+//   xw : the lane's 16-byte unit of token min(g, MT - 1) in round 0 of the fp16 activations: + 64 MT per round, + 512 for
+//        token g + 8.  (Lanes with g >= MT feed MMA columns of tokens that do not exist and are never stored; they
+//        re-read the last token instead of zeroing registers.)
 template <int CB, int MT>
-__device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_t xw, int g, float (*ya)[4]) {
+__device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_t xw, float (*ya)[4]) {
     constexpr int NB = MT > 8 ? 2 : 1;           // 8-token MMA column blocks
     constexpr uint32_t kMagic = 0x64006400u;     // half2(1024, 1024)
     const uint2 p0 = lds64(pw), p1 = lds64(pw + 64);
@@ -226,8 +249,7 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
     for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
-            b[u][nb] = make_uint4(0, 0, 0, 0);
-            if (g + 8 * nb < MT) b[u][nb] = lds128(xw + u * (MT * 64) + nb * 512);
+            b[u][nb] = lds128(xw + u * (MT * 64) + nb * 512);
         }
 
     if (CB == 4) {
@@ -297,13 +319,36 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
     }
 }
 
-template <int CB, int MT, int NG, int NP, int KBS>
-__global__ void __launch_bounds__((NG * kGroupWarps + NP) * 32, 1)
+// y tile = sum of the partial tiles of all contributors (fixed order) + bias; `nthreads` threads, this one is `tid`
+template <int MT>
+__device__ __forceinline__ void reduce_tile(const GemvArgs &a, uint32_t cnt, const uint32_t *slots, uint32_t nt, int tid, int nthreads) {
+    for (int e4 = tid; e4 < MT * 32; e4 += nthreads) {                 // 4 consecutive columns of one token
+        const int tok = e4 >> 5, nl = (e4 & 31) * 4;
+        const uint32_t n = nt * 128 + nl;
+        if ((uint32_t)tok >= a.M || n >= a.N) continue;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (uint32_t c = 0; c < cnt; ++c) {
+            const float4 pv = __ldcg(reinterpret_cast<const float4 *>(a.partial + (size_t)slots[c] * (MT * 128)) + e4);
+            v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+        }
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (n + i < a.N) a.y[(size_t)tok * a.N + n + i] = vv[i] + (a.bias ? __ldg(a.bias + n + i) : 0.f);
+    }
+}
+
+// XR: the CTA's slice of the activations is resident in shared memory (small M·K); otherwise every stage carries the
+// activations of its k-blocks (they come from L2: the prepared x is at most a few hundred KB)
+template <int CB, int MT, int NG, int NP, int KBS, bool XR>
+__global__ void __launch_bounds__((NG * kGroupWarps + NP + 1) * 32, 1)
 gemv_mma_kernel(const GemvArgs a) {
     constexpr int NB = MT > 8 ? 2 : 1;
     constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
-    constexpr int kStage = KBS * (kWBytes + 1024);   // KBS code tiles, then KBS x (128 scales + 128 zero-points)
     constexpr int kXTile = MT * 128;             // activations of one k-block
+    // a stage: KBS code tiles, KBS x 128 {scale, zero-point} pairs, and (unless XR) KBS activation tiles
+    constexpr int kStage = KBS * (kWBytes + 1024 + (XR ? 0 : kXTile));
     constexpr int kConsumers = NG * kGroupWarps * 32;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *ring = smem;
@@ -312,7 +357,8 @@ gemv_mma_kernel(const GemvArgs a) {
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.bar_off);
     uint64_t *empty = full + a.stages;
     uint64_t *xfull = empty + a.stages;
-    uint32_t *last_flag = reinterpret_cast<uint32_t *>(xfull + 1);   // [0] last arriver?  [1] contributors  [2..] their slots
+    uint32_t *verdict = reinterpret_cast<uint32_t *>(xfull + 1);     // [0] this CTA arrived last at its final tile  [1] contributors
+    uint32_t *slots = verdict + 2;                                   // partial slots of the contributors of one tile
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const Range rg(a, blockIdx.x);
@@ -333,13 +379,13 @@ gemv_mma_kernel(const GemvArgs a) {
     }
     __syncthreads();
 
-    if (warp >= NG * kGroupWarps) {
+    if (warp >= NG * kGroupWarps && warp < NG * kGroupWarps + NP) {
         // ===================== producers: NP warps take the stages round-robin =====================
         // (the mbarrier / bulk-copy instructions of ONE warp cost ~100 cycles each and do not overlap, so a
         //  single producer warp caps the SM at a fraction of its HBM share; NP warps and KBS tiles per copy
         //  lift that cap)
         const uint32_t me = (uint32_t)(warp - NG * kGroupWarps);
-        if (me == 0 && rg.u0 < rg.u1 && elect_one()) {   // the CTA's activation slice, once
+        if (XR && me == 0 && rg.u0 < rg.u1 && elect_one()) {   // the CTA's activation slice, once
             const uint32_t xbytes = rg.kbs * kXTile;
             mbar_arrive_expect_tx(xfull, xbytes);
             const uint8_t *src = a.xb + (size_t)rg.kb_s0 * kXTile;
@@ -357,7 +403,7 @@ gemv_mma_kernel(const GemvArgs a) {
             for (; my_it < it1; my_it += NP) {
                 const uint32_t kb = item.kb0 + (my_it - it0) * KBS;
                 const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
-                mbar_wait(empty + my_s, my_ph ^ 1);
+                mbar_wait_relaxed(empty + my_s, my_ph ^ 1, 2000);
                 if (lane == 0) STRACE(0, my_it);
                 uint8_t *st = ring + (size_t)my_s * kStage;
                 // Everything rides on 16-byte cp.async (LDGSTS) of the warp's 32 lanes; each lane's arrival on the
@@ -374,6 +420,11 @@ gemv_mma_kernel(const GemvArgs a) {
                         cp_async16(st + KBS * kWBytes + sub * 1024 + 512 + lane * 16, pg + 64 + lane * 2);
                     }
                 }
+                if (!XR) {
+                    const uint8_t *xsrc = a.xb + (size_t)kb * kXTile;
+#pragma unroll 4
+                    for (uint32_t i = lane; i < nk * (kXTile / 16); i += 32) cp_async16(st + KBS * (kWBytes + 1024) + i * 16, xsrc + (size_t)i * 16);
+                }
                 cp_async_arrive(full + my_s);
                 if (lane == 0) STRACE(1, my_it);
                 __syncwarp();
@@ -382,7 +433,7 @@ gemv_mma_kernel(const GemvArgs a) {
             }
             it0 = it1;
         }
-    } else {
+    } else if (warp < NG * kGroupWarps) {
         // ===================== consumers =====================
         const int grp = warp / kGroupWarps, w = warp % kGroupWarps;
         const int g = lane >> 2, t = lane & 3;
@@ -390,41 +441,45 @@ gemv_mma_kernel(const GemvArgs a) {
         float ya[NB][4];
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) ya[nb][0] = ya[nb][1] = ya[nb][2] = ya[nb][3] = 0.f;
-        // per-lane shared-memory addresses (see consume_kblock)
-        const uint32_t ring_cw = smem_u32(ring) + ((16 * w + g) * 4 + t) * 4;
-        const uint32_t ring_pw = smem_u32(ring) + KBS * kWBytes + (16 * w + g) * 8;
-        const uint32_t xs_lane = smem_u32(xs) + g * 64 + 16 * t;
+        // per-lane shared-memory addresses (see consume_kblock), kept in registers (the empty asm stops the
+        // compiler from re-deriving them from the shared window base inside the loop)
+        const uint32_t r0 = 16 * w + g;
+        uint32_t cwa = smem_u32(ring) + (r0 * 4 + t) * 4 + grp * kStage;      // codes of this group's next stage
+        uint32_t dpw = KBS * kWBytes + r0 * 8 - (r0 * 4 + t) * 4;             // its parameters, relative to cwa
+        uint32_t xs_lane = (XR ? smem_u32(xs) : KBS * (kWBytes + 1024) - (r0 * 4 + t) * 4) + (g < MT ? g : MT - 1) * 64 + 16 * t;   // !XR: relative to cwa
+        uint32_t fa = smem_u32(full) + grp * 8;                               // its full barrier; empty = + 8 stages
+        const uint32_t ring_bytes = a.stages * kStage, bar_bytes = a.stages * 8;
+        asm volatile("" : "+r"(cwa), "+r"(dpw), "+r"(xs_lane), "+r"(fa));
         if (ctid == 0) GTRACE(1);
-        if (rg.u0 < rg.u1) mbar_wait(xfull, 0);
+        if (XR && rg.u0 < rg.u1) mbar_wait(xfull, 0);
         if (ctid == 0) GTRACE(2);
-        uint32_t n_item = 0;
+        uint32_t n_item = 0, last_nt = 0;
+        bool last_whole = true;
         ItemIter iter(rg);
         Item item;
-        // stage counter `it` of the CTA; this group owns the stages with it % NG == grp.  (my_it, my_s, my_ph)
-        // walk this group's stages only — no per-stage bookkeeping for the other groups' stages
+        // stage counter `it` of the CTA; this group owns the stages with it % NG == grp and walks only those
         uint32_t it0 = 0, my_it = (uint32_t)grp, my_s = (uint32_t)grp, my_ph = 0;
         while (iter.next(item)) {
-            const uint32_t it1 = it0 + (item.kb1 - item.kb0 + KBS - 1) / KBS;
-            const uint32_t xitem = xs_lane + (item.kb0 - rg.kb_s0) * kXTile;
+            const uint32_t len = item.kb1 - item.kb0;
+            const uint32_t it1 = it0 + (len + KBS - 1) / KBS;
+            uint32_t xa = XR ? xs_lane + (item.kb0 - rg.kb_s0 + (my_it - it0) * KBS) * kXTile : 0u;
             for (; my_it < it1; my_it += NG) {
-                const uint32_t kbo = (my_it - it0) * KBS;           // k-block offset inside the item
-                const uint32_t nk = item.kb1 - item.kb0 - kbo < (uint32_t)KBS ? item.kb1 - item.kb0 - kbo : (uint32_t)KBS;
-                const uint32_t so = my_s * kStage + mbar_wait_token(full + my_s, my_ph);
+                const uint32_t c = cwa + mbar_wait_token(fa, my_ph);
                 if (ctid == 0 && my_it == 0) GTRACE(3);
                 if (w == 0 && lane == 0) STRACE(2, my_it);
-#pragma unroll
-                for (int sub = 0; sub < KBS; ++sub)
-                    if ((uint32_t)sub < nk)
-                        consume_kblock<CB, MT>(ring_cw + so + sub * kWBytes, ring_pw + so + sub * 1024, xitem + (kbo + sub) * kXTile, g, ya);
+                const uint32_t xk = XR ? xa : c + xs_lane;
+                consume_kblock<CB, MT>(c, c + dpw, xk, ya);
+                if (KBS == 2 && !(my_it + 1 == it1 && (len & 1)))               // the item's last stage may hold one k-block
+                    consume_kblock<CB, MT>(c + kWBytes, c + dpw + 1024, xk + kXTile, ya);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty + my_s);
+                if (lane == 0) mbar_arrive_addr(fa + bar_bytes);
                 if (w == 0 && lane == 0) STRACE(3, my_it);
-                my_s += NG;
-                if (my_s >= a.stages) { my_s -= a.stages; my_ph ^= 1; }
+                xa += NG * KBS * kXTile; cwa += NG * kStage; fa += NG * 8; my_s += NG;
+                if (my_s >= a.stages) { my_s -= a.stages; cwa -= ring_bytes; fa -= bar_bytes; my_ph ^= 1; }
             }
             it0 = it1;
             if (ctid == 0) GTRACE(4 + 2 * n_item);
-            // ---------- tile (or tile part) done: reduce over the consumer groups, then write ----------
+            // ---------- tile (or tile part) done: sum the consumer groups, store, hand over to the epilogue warp ----------
             float *mine = red + (size_t)grp * (MT * kRedStride);
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
@@ -433,8 +488,7 @@ gemv_mma_kernel(const GemvArgs a) {
                 if (tok + 1 < MT) { mine[(tok + 1) * kRedStride + 16 * w + g] = ya[nb][1]; mine[(tok + 1) * kRedStride + 16 * w + g + 8] = ya[nb][3]; }
                 ya[nb][0] = ya[nb][1] = ya[nb][2] = ya[nb][3] = 0.f;
             }
-            consumer_bar(kConsumers);
-            // contributors of this tile: per segment the CTAs whose range touches its units
+            named_bar_sync(kBarConsumers, kConsumers);
             const bool whole = a.S == 1 && item.kb0 == rg.kb_s0 && item.kb1 == rg.kb_s0 + rg.kbs;
             float *dst = whole ? nullptr : a.partial + ((size_t)blockIdx.x * a.max_items + item.ordinal) * (MT * 128);
             for (int e = ctid; e < MT * 128; e += kConsumers) {
@@ -449,46 +503,64 @@ gemv_mma_kernel(const GemvArgs a) {
                     dst[e] = v;
                 }
             }
+            named_bar_sync(kBarConsumers, kConsumers);                  // `red` may be overwritten by the next tile
+            // the partial tile is in global memory: the epilogue warp publishes it (fence + ticket) and, if this CTA
+            // was the last contributor, reduces the tile — while the consumers are already on the next tile
             if (!whole) {
-                __threadfence();
-                consumer_bar(kConsumers);
-                if (ctid == 0) {
-                    // contributors of this tile, in the fixed order (segment, CTA): their partial slots
-                    uint32_t cnt = 0;
-                    for (uint32_t sg = 0; sg < a.S; ++sg) {
-                        const uint32_t k0 = (uint32_t)((uint64_t)a.k_blocks * sg / a.S);
-                        const uint32_t kn = (uint32_t)((uint64_t)a.k_blocks * (sg + 1) / a.S) - k0;
-                        const uint64_t U = (uint64_t)a.n_tiles * kn, a0 = (uint64_t)item.nt * kn, a1 = a0 + kn;
-                        const uint32_t j_lo = (uint32_t)(((a0 + 1) * a.P - 1) / U), j_hi = (uint32_t)((a1 * a.P - 1) / U);
-                        for (uint32_t j = j_lo; j <= j_hi; ++j) {
-                            const uint32_t first_nt = (uint32_t)((U * j / a.P) / kn);
-                            if (cnt < kMaxContrib) last_flag[2 + cnt] = (sg * a.P + j) * a.max_items + (item.nt - first_nt);
-                            ++cnt;
-                        }
-                    }
-                    const uint32_t old = atomicAdd(a.tickets + item.nt, 1u);
-                    const uint32_t last = old + 1 == cnt ? 1u : 0u;
-                    if (last) a.tickets[item.nt] = 0;      // every contributor has arrived: re-arm for the next launch
-                    last_flag[0] = last;
-                    last_flag[1] = cnt;
-                }
-                consumer_bar(kConsumers);
-                if (last_flag[0]) {
-                    __threadfence();
-                    const uint32_t cnt = last_flag[1];
-                    for (int e = ctid; e < MT * 128; e += kConsumers) {
-                        const int tok = e >> 7, nl = e & 127;
-                        const uint32_t n = item.nt * 128 + nl;
-                        if ((uint32_t)tok >= a.M || n >= a.N) continue;
-                        float v = 0.f;
-                        for (uint32_t c = 0; c < cnt; ++c) v += __ldcg(a.partial + (size_t)last_flag[2 + c] * (MT * 128) + e);
-                        a.y[(size_t)tok * a.N + n] = v + (a.bias ? __ldg(a.bias + n) : 0.f);
-                    }
-                }
+                named_bar_sync(kBarEpiFree, kConsumers + 32);
+                named_bar_arrive(kBarPartial, kConsumers + 32);
             }
-            consumer_bar(kConsumers);            // `red` and `last_flag` are reused by the next item
             if (ctid == 0) GTRACE(5 + 2 * n_item);
             ++n_item;
+            last_whole = whole;
+            last_nt = item.nt;
+        }
+        if (n_item != 0 && !last_whole) {
+            // the CTA's last tile: wait for the verdict; if this CTA arrived last, all consumer threads reduce it
+            named_bar_sync(kBarFinal, kConsumers + 32);
+            if (verdict[0]) reduce_tile<MT>(a, verdict[1], slots, last_nt, ctid, kConsumers);
+        }
+    } else {
+        // ===================== epilogue warp =====================
+        ItemIter iter(rg);
+        Item item;
+        bool more = iter.next(item);
+        while (more) {
+            const Item cur = item;
+            more = iter.next(item);
+            const bool whole = a.S == 1 && cur.kb0 == rg.kb_s0 && cur.kb1 == rg.kb_s0 + rg.kbs;
+            if (whole) continue;
+            named_bar_arrive(kBarEpiFree, kConsumers + 32);
+            named_bar_sync(kBarPartial, kConsumers + 32);
+            uint32_t cnt = 0, last = 0;
+            if (lane == 0) {
+                __threadfence();                       // cumulative: publishes the consumers' stores ordered before the barrier
+                // contributors of this tile, in the fixed order (segment, CTA): their partial slots
+                for (uint32_t sg = 0; sg < a.S; ++sg) {
+                    const uint32_t k0 = (uint32_t)((uint64_t)a.k_blocks * sg / a.S);
+                    const uint32_t kn = (uint32_t)((uint64_t)a.k_blocks * (sg + 1) / a.S) - k0;
+                    const uint64_t U = (uint64_t)a.n_tiles * kn, a0 = (uint64_t)cur.nt * kn, a1 = a0 + kn;
+                    const uint32_t j_lo = (uint32_t)(((a0 + 1) * a.P - 1) / U), j_hi = (uint32_t)((a1 * a.P - 1) / U);
+                    for (uint32_t j = j_lo; j <= j_hi; ++j) {
+                        const uint32_t first_nt = (uint32_t)((U * j / a.P) / kn);
+                        if (cnt < kMaxContrib) slots[cnt] = (sg * a.P + j) * a.max_items + (cur.nt - first_nt);
+                        ++cnt;
+                    }
+                }
+                const uint32_t old = atomicAdd(a.tickets + cur.nt, 1u);
+                last = old + 1 == cnt ? 1u : 0u;
+                if (last) a.tickets[cur.nt] = 0;       // every contributor has arrived: re-arm for the next launch
+                __threadfence();
+                verdict[0] = last;
+                verdict[1] = cnt;
+            }
+            cnt = __shfl_sync(0xffffffffu, cnt, 0);
+            last = __shfl_sync(0xffffffffu, last, 0);  // (the shuffle also orders lane 0's shared-memory writes before the reads)
+            if (!more) {
+                named_bar_arrive(kBarFinal, kConsumers + 32);           // the consumers take it from here
+            } else if (last) {
+                reduce_tile<MT>(a, cnt, slots, cur.nt, lane, 32);
+            }
         }
     }
 }
@@ -512,24 +584,27 @@ gemv_xprep_kernel(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t 
     xb[idx] = o;
 }
 
-template <int CB, int MT>
+template <int CB, int MT, bool XR>
 int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
     // NP == NG: a ring slot must always be filled by the same producer warp and drained by the same consumer
     // group (the stage count is a multiple of both) — parity waits of different warps on one slot could alias
     constexpr int NG = 3, NP = 3, KBS = 2;
     static_assert(NG % NP == 0 || NP % NG == 0, "ring depth is a multiple of max(NG, NP) only");
     constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
-    constexpr int kStage = KBS * (kWBytes + 1024);
     constexpr int kXTile = MT * 128;
+    constexpr int kStage = KBS * (kWBytes + 1024 + (XR ? 0 : kXTile));
     const uint32_t k_blocks = (uint32_t)qw->k_blocks, n_tiles = (uint32_t)qw->n_tiles;
     const uint32_t sms = (uint32_t)ctx->sm_count;
 
-    // k segments: the fewest such that a CTA's activation slice leaves room for a ring of >= 8 stages
+    // XR: the whole activation block stays resident (one k segment).  The segment machinery (S > 1: a CTA keeps only
+    // its k segment's slice) remains for activations that are too large for that but were asked to stay resident.
     const uint32_t red_bytes = NG * MT * kRedStride * 4;
     uint32_t S = 1;
-    for (;; ++S) {
-        const uint64_t xb = (uint64_t)((k_blocks + S - 1) / S) * kXTile;
-        if (S >= k_blocks || (xb <= (uint64_t)kXBudget && xb + red_bytes + 1024 + 8ull * kStage <= (uint64_t)kSmemBudget)) break;
+    if (XR) {
+        for (;; ++S) {
+            const uint64_t xb = (uint64_t)((k_blocks + S - 1) / S) * kXTile;
+            if (S >= k_blocks || (xb <= (uint64_t)kXBudget && xb + red_bytes + 1024 + 8ull * kStage <= (uint64_t)kSmemBudget)) break;
+        }
     }
     uint32_t P = sms / S;
     if (P == 0) { P = 1; }
@@ -557,7 +632,7 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     const uint64_t len_max = ((uint64_t)n_tiles * kbs_max + P - 1) / P;
     a.max_items = (uint32_t)(len_max / (kbs_min ? kbs_min : 1)) + 2;
 
-    const uint32_t xbytes = kbs_max * kXTile;
+    const uint32_t xbytes = XR ? kbs_max * kXTile : 0u;
     uint32_t stages = (uint32_t)((kSmemBudget - xbytes - red_bytes - 1024) / kStage);
     if (stages > (uint32_t)kMaxStages) stages = kMaxStages;
     stages -= stages % (NG > NP ? NG : NP);
@@ -580,7 +655,7 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
 
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_mma_kernel<CB, MT, NG, NP, KBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_mma_kernel<CB, MT, NG, NP, KBS, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const uint32_t units16 = k_blocks * 2 * MT * 4;
@@ -597,7 +672,7 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
         ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
         CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    gemv_mma_kernel<CB, MT, NG, NP, KBS><<<grid, (NG * kGroupWarps + NP) * 32, smem_bytes, ctx->stream>>>(a);
+    gemv_mma_kernel<CB, MT, NG, NP, KBS, XR><<<grid, (NG * kGroupWarps + NP + 1) * 32, smem_bytes, ctx->stream>>>(a);
     LAUNCH_CHECK(ctx);
     if (ev1) {
         CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
@@ -639,13 +714,22 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     return DLLM_OK;
 }
 
+// the prepared activations of up to kXResident bytes stay resident in shared memory; larger ones ride the ring
+constexpr size_t kXResident = 64 * 1024;
+
+template <int CB, int MT>
+int32_t launch_gemv_x(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
+    if (qw->k_blocks * (size_t)(MT * 128) <= kXResident) return launch_gemv_mma<CB, MT, true>(ctx, qw, x, M, y);
+    return launch_gemv_mma<CB, MT, false>(ctx, qw, x, M, y);
+}
+
 template <int CB>
 int32_t launch_gemv_mt(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
-    if (M <= 1) return launch_gemv_mma<CB, 1>(ctx, qw, x, M, y);
-    if (M <= 2) return launch_gemv_mma<CB, 2>(ctx, qw, x, M, y);
-    if (M <= 4) return launch_gemv_mma<CB, 4>(ctx, qw, x, M, y);
-    if (M <= 8) return launch_gemv_mma<CB, 8>(ctx, qw, x, M, y);
-    return launch_gemv_mma<CB, 16>(ctx, qw, x, M, y);
+    if (M <= 1) return launch_gemv_x<CB, 1>(ctx, qw, x, M, y);
+    if (M <= 2) return launch_gemv_x<CB, 2>(ctx, qw, x, M, y);
+    if (M <= 4) return launch_gemv_x<CB, 4>(ctx, qw, x, M, y);
+    if (M <= 8) return launch_gemv_x<CB, 8>(ctx, qw, x, M, y);
+    return launch_gemv_x<CB, 16>(ctx, qw, x, M, y);
 }
 
 }  // namespace
