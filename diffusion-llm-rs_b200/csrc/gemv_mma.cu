@@ -50,17 +50,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "GW_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra GW_DONE;\n\t"
-        "bra GW_LOOP;\n\t"
-        "GW_DONE:\n\t"
-        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 // producer-side wait: the thread may stay suspended for up to `ns` before the try_wait returns false — a producer
 // that polls a barrier in a tight loop steals issue slots from the consumer warps (measured: 27% of all issued
 // instructions), and it is never latency-critical: it runs a whole ring ahead
@@ -137,7 +126,7 @@ __device__ __forceinline__ bool elect_one() {
 // CTA's last tile, the consumers wait for it (they have nothing else left to do and help with that reduction)
 // kBarEpiFree — the epilogue warp is ready for the next partial tile (a named barrier must not collect the arrivals of
 // two tiles at once, so the consumers wait for it before they arrive on kBarPartial again)
-constexpr int kBarConsumers = 1, kBarPartial = 2, kBarFinal = 3, kBarEpiFree = 4;
+constexpr int kBarConsumers = 1, kBarPartial = 2, kBarFinal = 3, kBarEpiFree = 4, kBarXReady = 5;
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 // D(16 columns x 8 tokens, f32) += A(16 columns x 16 k, f16) · B(16 k x 8 tokens, f16)
@@ -177,7 +166,9 @@ struct GemvArgs {
     const uint8_t *packed;
     const uint2 *gparams;            // [G][Npad] {f32 scale, half2(1024 + zp)}
     const float *bias;
-    const uint8_t *xb;               // prepared activations: [k_blocks][2 rounds][MT tokens][4 t][8 e] fp16
+    const uint8_t *xb;               // !XR: prepared activations [k_blocks][2 rounds][MT tokens][4 t][8 e] fp16
+    const float *x;                  // XR: the f32 activations [M, K]; every CTA prepares its own slice in shared memory
+    uint32_t K;
     float *y;                        // [M, N]
     float *partial;                  // [grid * max_items][MT][128]
     unsigned int *tickets;           // [n_tiles], zero between launches
@@ -187,6 +178,7 @@ struct GemvArgs {
     uint32_t max_items;              // partial slots per CTA
     uint32_t stages;                 // ring depth (multiple of NG)
     uint32_t x_off, red_off, bar_off;   // shared-memory carve-up (bytes)
+    uint32_t bulk;                   // code tiles by one cp.async.bulk per stage (default) or by per-lane cp.async (DLLM_GEMV_BULK=0)
     unsigned long long *trace;       // -DDLLM_GEMV_TRACE: per CTA [32] globaltimer stamps, then [4][256] stage stamps of CTA 0
 };
 
@@ -319,6 +311,27 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
     }
 }
 
+// One 16-byte unit of the prepared activations: the 8 fp16 values of token `tok` that lane quad-index t consumes in
+// round u of k-block kb (gemv_kmap).  They are two runs of 4 consecutive k; `vec` = K % 4 == 0 and x is 16-byte aligned.
+template <int CB>
+__device__ __forceinline__ uint4 gemv_x_unit(const float *__restrict__ x, uint32_t M, uint32_t K, bool vec, uint32_t kb, uint32_t u, uint32_t tok, uint32_t t) {
+    float v[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t k = kb * WL_TILE_K + (uint32_t)gemv_kmap<CB>((int)u, (int)t, 4 * h);
+        if (tok < M && vec && k + 3 < K) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(x + (size_t)tok * K + k));
+            v[4 * h] = f.x; v[4 * h + 1] = f.y; v[4 * h + 2] = f.z; v[4 * h + 3] = f.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[4 * h + e] = (tok < M && k + e < K) ? __ldg(x + (size_t)tok * K + k + e) : 0.f;
+        }
+    }
+    uint4 o;
+    o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]);
+    return o;
+}
+
 // y tile = sum of the partial tiles of all contributors (fixed order) + bias; `nthreads` threads, this one is `tid`
 template <int MT>
 __device__ __forceinline__ void reduce_tile(const GemvArgs &a, uint32_t cnt, const uint32_t *slots, uint32_t nt, int tid, int nthreads) {
@@ -337,6 +350,19 @@ __device__ __forceinline__ void reduce_tile(const GemvArgs &a, uint32_t cnt, con
         for (int i = 0; i < 4; ++i)
             if (n + i < a.N) a.y[(size_t)tok * a.N + n + i] = vv[i] + (a.bias ? __ldg(a.bias + n + i) : 0.f);
     }
+}
+
+// XR: consumers + epilogue warp convert the CTA's k-segment of x to fp16 in shared memory (the producers are
+// already streaming weights meanwhile), then meet at kBarXReady
+template <int CB, int MT>
+__device__ __forceinline__ void prepare_x_slice(const GemvArgs &a, const Range &rg, uint8_t *xs, int tid, int nthreads) {
+    const bool vec = (a.K & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+    const uint32_t total = rg.u0 < rg.u1 ? rg.kbs * 2 * MT * 4 : 0;
+    for (uint32_t idx = tid; idx < total; idx += nthreads) {
+        const uint32_t t = idx & 3, tok = (idx >> 2) % MT, u = ((idx >> 2) / MT) & 1, kb = (idx >> 2) / (MT * 2);
+        reinterpret_cast<uint4 *>(xs)[idx] = gemv_x_unit<CB>(a.x, a.M, a.K, vec, rg.kb_s0 + kb, u, tok, t);
+    }
+    named_bar_sync(kBarXReady, nthreads);
 }
 
 // XR: the CTA's slice of the activations is resident in shared memory (small M·K); otherwise every stage carries the
@@ -373,7 +399,7 @@ gemv_mma_kernel(const GemvArgs a) {
 
     if (threadIdx.x == 0) {
         // full: one arrival per lane of the owning producer warp, triggered when that lane's cp.async copies landed
-        for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(full + s, 32); mbar_init(empty + s, kGroupWarps); }
+        for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(full + s, 33); mbar_init(empty + s, kGroupWarps); }
         mbar_init(xfull, 1);
         fence_barrier_init();
     }
@@ -385,14 +411,6 @@ gemv_mma_kernel(const GemvArgs a) {
         //  single producer warp caps the SM at a fraction of its HBM share; NP warps and KBS tiles per copy
         //  lift that cap)
         const uint32_t me = (uint32_t)(warp - NG * kGroupWarps);
-        if (XR && me == 0 && rg.u0 < rg.u1 && elect_one()) {   // the CTA's activation slice, once
-            const uint32_t xbytes = rg.kbs * kXTile;
-            mbar_arrive_expect_tx(xfull, xbytes);
-            const uint8_t *src = a.xb + (size_t)rg.kb_s0 * kXTile;
-            for (uint32_t off = 0; off < xbytes; off += 16384)
-                bulk_load(xs + off, src + off, xbytes - off < 16384 ? xbytes - off : 16384, xfull);
-        }
-        __syncwarp();
         ItemIter iter(rg);
         Item item;
         uint32_t it0 = 0, my_it = me, my_s = me, my_ph = 0;
@@ -406,12 +424,23 @@ gemv_mma_kernel(const GemvArgs a) {
                 mbar_wait_relaxed(empty + my_s, my_ph ^ 1, 2000);
                 if (lane == 0) STRACE(0, my_it);
                 uint8_t *st = ring + (size_t)my_s * kStage;
-                // Everything rides on 16-byte cp.async (LDGSTS) of the warp's 32 lanes; each lane's arrival on the
-                // stage's mbarrier fires when its copies have landed.  (cp.async.bulk was measured no faster, and
-                // its issue costs the single elected thread ~100 cycles per copy.)
+                // The KBS code tiles are contiguous in HBM: one cp.async.bulk (complete_tx on the stage's mbarrier).
+                // Scales / zero-points (and the activations, when they are not resident) ride on 16-byte cp.async of
+                // the warp's 32 lanes; each lane's arrival on the same mbarrier fires when its copies have landed.
+                // (Measured on 14336^2 4-bit: bulk 33.2 us, all-cp.async 34.6 us — the latter costs the producer
+                // warps 16 more issue slots per lane and stage.)
                 const uint8_t *src = wsrc + (size_t)kb * kWBytes;
+                if (a.bulk) {
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(full + my_s, nk * kWBytes);
+                        bulk_load(st, src, nk * kWBytes, full + my_s);
+                    }
+                    __syncwarp();
+                } else {
 #pragma unroll 8
-                for (uint32_t i = lane; i < nk * (kWBytes / 16); i += 32) cp_async16(st + i * 16, src + (size_t)i * 16);
+                    for (uint32_t i = lane; i < nk * (kWBytes / 16); i += 32) cp_async16(st + i * 16, src + (size_t)i * 16);
+                    if (lane == 0) mbar_arrive_addr(smem_u32(full + my_s));
+                }
 #pragma unroll
                 for (int sub = 0; sub < KBS; ++sub) {
                     if ((uint32_t)sub < nk) {
@@ -451,7 +480,7 @@ gemv_mma_kernel(const GemvArgs a) {
         const uint32_t ring_bytes = a.stages * kStage, bar_bytes = a.stages * 8;
         asm volatile("" : "+r"(cwa), "+r"(dpw), "+r"(xs_lane), "+r"(fa));
         if (ctid == 0) GTRACE(1);
-        if (XR && rg.u0 < rg.u1) mbar_wait(xfull, 0);
+        if (XR) prepare_x_slice<CB, MT>(a, rg, xs, ctid, kConsumers + 32);
         if (ctid == 0) GTRACE(2);
         uint32_t n_item = 0, last_nt = 0;
         bool last_whole = true;
@@ -522,6 +551,7 @@ gemv_mma_kernel(const GemvArgs a) {
         }
     } else {
         // ===================== epilogue warp =====================
+        if (XR) prepare_x_slice<CB, MT>(a, rg, xs, kConsumers + lane, kConsumers + 32);
         ItemIter iter(rg);
         Item item;
         bool more = iter.next(item);
@@ -573,15 +603,8 @@ gemv_xprep_kernel(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t 
     const uint32_t total = k_blocks * 2 * MT * 4;
     if (idx >= total) return;
     const uint32_t t = idx & 3, tok = (idx >> 2) % MT, u = ((idx >> 2) / MT) & 1, kb = (idx >> 2) / (MT * 2);
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const uint32_t k = kb * WL_TILE_K + (uint32_t)gemv_kmap<CB>((int)u, (int)t, e);
-        v[e] = (tok < M && k < K) ? __ldg(x + (size_t)tok * K + k) : 0.f;
-    }
-    uint4 o;
-    o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]);
-    xb[idx] = o;
+    const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    xb[idx] = gemv_x_unit<CB>(x, M, K, vec, kb, u, tok, t);
 }
 
 template <int CB, int MT, bool XR>
@@ -612,6 +635,8 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     const uint64_t total_units = (uint64_t)n_tiles * k_blocks;
     while (P > 1 && total_units / ((uint64_t)S * P) < 4) --P;
     while (S * P > (uint32_t)kMaxContrib) --P;
+    static const int grid_cap = getenv("DLLM_GEMV_GRID") ? atoi(getenv("DLLM_GEMV_GRID")) : 0;   // experiments only
+    if (grid_cap > 0) while (P > 1 && S * P > (uint32_t)grid_cap) --P;
     const uint32_t grid = S * P;
 
     GemvArgs a;
@@ -622,6 +647,8 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     if (k_blocks >= 65536) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path: K too large");
     a.group_magic = group_kb == 1 ? 0u : (uint32_t)(((1ull << 32) + group_kb - 1) / group_kb);   // 0: one k-block per group
     a.S = S; a.P = P;
+    static const uint32_t bulk_mode = getenv("DLLM_GEMV_BULK") ? (uint32_t)atoi(getenv("DLLM_GEMV_BULK")) : 1u;
+    a.bulk = bulk_mode;
     a.trace = nullptr;
 #ifdef DLLM_GEMV_TRACE
     DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, ((size_t)grid * 32 + 1024) * 8));
@@ -643,24 +670,30 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     a.bar_off = a.red_off + ((red_bytes + 127) & ~127u);
     const size_t smem_bytes = a.bar_off + (2 * stages + 1) * 8 + (2 + kMaxContrib) * 4;
 
-    DLLM_TRY(ensure_buf(ctx, ctx->act[2], (size_t)k_blocks * kXTile));
+    if (!XR) DLLM_TRY(ensure_buf(ctx, ctx->act[2], (size_t)k_blocks * kXTile));
     DLLM_TRY(ensure_buf(ctx, ctx->lin_ws, (size_t)grid * a.max_items * MT * 128 * sizeof(float)));
     if (ctx->gemv_tickets.cap < n_tiles * sizeof(unsigned int)) {
         DLLM_TRY(ensure_buf(ctx, ctx->gemv_tickets, n_tiles * sizeof(unsigned int)));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->gemv_tickets.p, 0, ctx->gemv_tickets.cap, ctx->stream));
     }
     a.xb = (const uint8_t *)ctx->act[2].p;
+    a.x = x; a.K = (uint32_t)qw->K;
     a.partial = (float *)ctx->lin_ws.p;
     a.tickets = (unsigned int *)ctx->gemv_tickets.p;
 
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_mma_kernel<CB, MT, NG, NP, KBS, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        // the activation-prep kernel runs right before: same shared-memory carve-out, so the SMs are not
+        // re-partitioned (L1 vs shared) between the two launches
+        CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_xprep_kernel<CB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    const uint32_t units16 = k_blocks * 2 * MT * 4;
-    gemv_xprep_kernel<CB><<<(units16 + 255) / 256, 256, 0, ctx->stream>>>(x, (uint32_t)M, (uint32_t)qw->K, k_blocks, MT, (uint4 *)ctx->act[2].p);
-    LAUNCH_CHECK(ctx);
+    if (!XR) {
+        const uint32_t units16 = k_blocks * 2 * MT * 4;
+        gemv_xprep_kernel<CB><<<(units16 + 255) / 256, 256, 0, ctx->stream>>>(x, (uint32_t)M, (uint32_t)qw->K, k_blocks, MT, (uint4 *)ctx->act[2].p);
+        LAUNCH_CHECK(ctx);
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->prof_on) {
         while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) {

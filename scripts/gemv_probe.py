@@ -43,5 +43,21 @@ nl, ms, fl, by = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
 ctx._ck(ctx._lib.dllm_profile_end(ctx.h, C.byref(nl), C.byref(ms), C.byref(fl), C.byref(by)))
 kus = ms.value / nl.value * 1e3
 byts = K * N * bits / 8 + (K // 128) * N * 8 + 4 * M * (K + N)
+# CUDA-graph replay of 4 x npool back-to-back calls: what a captured decode loop pays per linear (no host in the way)
+g = torch.cuda.CUDAGraph()
+ncap = 4 * npool
+with torch.cuda.graph(g, stream=stream):
+    for i in range(ncap):
+        run(i)
+with torch.cuda.stream(stream):
+    g.replay()
+    stream.synchronize()
+    e0.record(stream)
+    for _ in range(10):
+        g.replay()
+    e1.record(stream)
+    e1.synchronize()
+gus = e0.elapsed_time(e1) / (10 * ncap) * 1e3
+print(f"graph replay: {gus:.1f} us/call  {byts / gus / 1e3:.0f} GB/s")
 print(f"dbg={os.environ.get('DLLM_GEMV_DBG', '0')} K={K} N={N} bits={bits} M={M} path={path}: {us:.1f} us/call  "
       f"kernel-only {kus:.1f} us  {byts / kus / 1e3:.0f} GB/s", flush=True)
