@@ -10,7 +10,9 @@ Default workload (BASELINE.json configs[2]): one denoising step of a synthetic 1
 N > 1 (torchrun): independent denoising batches, one replica per GPU (data parallel, weak scaling,
 no data-path collective); `--parallelism tp` runs the tensor-parallel 7B-class config instead.
 
-Other workloads (not the driver's line): --workload gemv | kv   (BASELINE.json configs[1] / [4]).
+The line also carries the GB/s half of the metric as extras ("gemv": 4-bit 14336^2 dequant-GEMV from a CUDA graph,
+"kv_quant": per-token KV quantize / dequantize), each with its fraction of the measured HBM bandwidth; the full
+sweeps of BASELINE.json configs[1] / [4] are scripts/microbench.py.
 `--impl reference` times the oracle port of the reference's CPU path on the host cores.
 """
 import argparse
@@ -147,6 +149,78 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample_desc},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+def secondary_metrics(ctx, stream, pk):
+    """The GB/s half of BASELINE.json's metric, on rank 0 after the timed denoise steps: the 4-bit dequant-GEMV
+    (configs[1] shape K=N=14336, group 128) replayed from a CUDA graph over a pool of weights larger than L2, and
+    the per-token KV quantizer (configs[4] row shape, 4096 hidden).  Algorithmic bytes / CUDA-event
+    time, as a fraction of the measured HBM copy bandwidth."""
+    import torch
+    import dllm_b200
+    from dllm_b200 import QWeight
+    out = {}
+    hbm = pk["hbm_gbs"]
+    K = N = 14336
+    w = torch.randn(K, N, device="cuda") * 0.02
+    torch.cuda.synchronize()
+    pool = [QWeight.quantize_dev(ctx, w.data_ptr(), K, N, 4, 128) for _ in range(4)]   # 4 x 103 MB > 126 MB L2
+    ctx.sync()
+    del w
+    gemv = {"kernel": "gemv_mma_kernel<4> (cp.async/bulk ring + mma.sync on in-register dequantized fp16)",
+            "K": K, "N": N, "bits": 4, "group": 128, "timing": "CUDA-graph replay of 16 calls x 10, 4-weight pool (412 MB)"}
+    for M in (1, 16):
+        x = torch.randn(M, K, device="cuda")
+        y = torch.empty(M, N, device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            for i in range(4):
+                pool[i].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
+            stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for i in range(16):
+                pool[i % 4].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            g.replay()
+            stream.synchronize()
+            e0.record(stream)
+            for _ in range(10):
+                g.replay()
+            e1.record(stream)
+            e1.synchronize()
+        us = e0.elapsed_time(e1) / 160 * 1e3
+        byts = K * N // 2 + (K // 128) * N * 8 + 4 * M * K + 4 * M * N
+        gemv[f"M{M}"] = {"us_per_call": round(us, 2), "GBps": round(byts / us / 1e3, 1), "hbm_frac": round(byts / us / 1e3 / hbm, 3)}
+        del g
+    for p in pool:
+        p.close()
+    out["gemv"] = gemv
+    rows, dim = 1 << 16, 4096
+    x = torch.randn(rows, dim, device="cuda")
+    codes = torch.empty(rows * dim // 2, dtype=torch.uint8, device="cuda")
+    sc, zp = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    deq = torch.empty_like(x)
+    torch.cuda.synchronize()
+    kv = {"rows": rows, "dim": dim, "bits": 4, "scheme": "per-token row (prefill_kv.rs:104-121), packed"}
+    for name, fn in (("quantize", lambda: ctx.quantize_d_rows_dev(x.data_ptr(), rows, dim, 4, True, codes.data_ptr(), sc.data_ptr(), zp.data_ptr())),
+                     ("dequantize", lambda: ctx.dequantize_d_rows_dev(codes.data_ptr(), rows, dim, 4, True, sc.data_ptr(), zp.data_ptr(), deq.data_ptr()))):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                fn()
+            stream.synchronize()
+            e0.record(stream)
+            for _ in range(10):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+        us = e0.elapsed_time(e1) / 10 * 1e3
+        byts = 4 * rows * dim + rows * dim // 2 + 8 * rows
+        kv[name] = {"us": round(us, 1), "GBps": round(byts / us / 1e3, 1), "hbm_frac": round(byts / us / 1e3 / hbm, 3)}
+    out["kv_quant"] = kv
+    return out
 
 
 def workload_config(args, world):
@@ -289,6 +363,22 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_GBps": by.value / (ms.value * 1e-3) / 1e9 if ms.value > 0 else 0.0},
             "clocks": clocks, "output_finite": finite,
         }
+        traffic = None
+        try:   # DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_umma_traffic.json")))
+            if tj.get("model") == args.model:
+                traffic = tj["dram_bytes_per_launch"]
+                line["roofline"]["traffic_source"] = tj.get("source")
+        except Exception:
+            pass
+        line["roofline"]["traffic"] = traffic
+        if not args.no_secondary and world == 1:
+            try:
+                model.close()
+                model = None
+                line.update(secondary_metrics(ctx, stream, pk))
+            except Exception as e:  # noqa: BLE001  (the headline line must survive a failure of the extras)
+                line["secondary_error"] = str(e)[:200]
         if not args.no_cpu:
             secs_cpu, detail = cpu_denoise_step_seconds(args.model, 1, 32)
             line["cpu_baseline"] = {
@@ -298,7 +388,8 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if tpg is not None:
         tpg.close()
-    model.close()
+    if model is not None:
+        model.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -313,6 +404,7 @@ def main():
     ap.add_argument("--model", default="1b", choices=sorted(MODELS))
     ap.add_argument("--parallelism", default="dp", choices=["dp", "tp"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the GEMV / KV-quant GB/s extras")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

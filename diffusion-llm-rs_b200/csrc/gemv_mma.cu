@@ -768,7 +768,8 @@ int32_t launch_gemv_mt(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, si
 }  // namespace
 
 bool k_gemv_supported(const dllm_qweight *qw, size_t M) {
-    return qw && M >= 1 && M <= 16 && (qw->per_tensor || qw->group % WL_TILE_K == 0);
+    // fp16 operands: integer zero-points (subtracted exactly) and scales in fp16's full-precision range
+    return qw && M >= 1 && M <= 16 && (qw->per_tensor || qw->group % WL_TILE_K == 0) && qw->int_zps;
 }
 
 int32_t k_qlinear_gemv(dllm_ctx *ctx, const dllm_qweight *qw, const float *x_dev, size_t M, float *y_dev) {

@@ -170,7 +170,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), K-major A and B, N>>3 at 17, M>>4 at 24
+// instruction descriptor: c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), K-major A and B, N>>3 at 17, M>>4 at 24.
+// (Measured: kind::f16 traps with cudaErrorIllegalInstruction when the A and B formats differ, so fp16 weights —
+// whose unpack is cheaper, see gemv_mma.cu — would need fp16 activations too; the stack keeps bf16 for its range.)
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
@@ -185,6 +187,12 @@ __device__ __forceinline__ uint32_t bf2_sub_mul(uint32_t a, uint32_t zb, uint32_
     return *reinterpret_cast<uint32_t *>(&r);
 }
 
+// (a & mask) | magic in ONE LOP3 (with two immediates the compiler emits two; +3.5% on the whole denoise step)
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t magic) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
+    return d;
+}
 // `zterm`/`s2` are the per-(group, column) operands prepared by wdq_params_kernel.
 template <int CB>
 __device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, uint32_t zterm, uint32_t s2, uint32_t *out) {
@@ -201,11 +209,11 @@ __device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, ui
                 if (CB == 4) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        out[j * 16 + wd * 4 + i] = bf2_sub_mul(((w[wd] >> (4 * i)) & 0x000f000fu) | 0x43004300u, zb, s2);
+                        out[j * 16 + wd * 4 + i] = bf2_sub_mul(and_or(w[wd] >> (4 * i), 0x000f000fu, 0x43004300u), zb, s2);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        out[wd * 8 + i] = bf2_sub_mul(((w[wd] >> (2 * i)) & 0x00030003u) | 0x43004300u, zb, s2);
+                        out[wd * 8 + i] = bf2_sub_mul(and_or(w[wd] >> (2 * i), 0x00030003u, 0x43004300u), zb, s2);
                 }
             }
         }
@@ -741,7 +749,7 @@ int32_t launch_umma_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const void *x, s
 
 bool k_umma_supported(const dllm_qweight *qw, size_t M) {
     // TMA needs a 16-byte row pitch for x (K % 8 == 0); everything else is padded / masked
-    return qw && M >= 1 && M < (1u << 31) && qw->K % 8 == 0 && qw->group % WL_TILE_K == 0;
+    return qw && M >= 1 && M < (1u << 31) && qw->K % 8 == 0 && qw->group % WL_TILE_K == 0 && qw->int_zps;
 }
 
 int32_t k_qlinear_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M, float *y_f32_dev,

@@ -80,11 +80,18 @@ wpack_kernel(const SRC *__restrict__ src, size_t K, size_t N, size_t Npad, size_
 //   8-bit  : x = f32 bits of zp
 //   y = bf16x2(scale)
 // and for the GEMV path (fp16 operands): {f32 scale, half2(1024 + zp)} — 0x6400 | q is the half 1024 + q
+// flags (OR-ed): 1 = some zero-point is not an integer in [0, 255] (the 16-bit-operand kernels subtract it exactly
+// only if it is: quantizer B always produces such, hand-made parameters may not); 2 = some scale is outside the range
+// in which an fp16 copy keeps full precision and (q - zp) * scale cannot overflow
 __global__ void wdq_params_kernel(const float *__restrict__ scales, const float *__restrict__ zps, size_t n, int cb,
-                                  uint2 *__restrict__ out, uint2 *__restrict__ gout) {
+                                  uint2 *__restrict__ out, uint2 *__restrict__ gout, unsigned int *__restrict__ flags) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float s = scales[i], z = zps[i];
+    unsigned int f = 0;
+    if (!(z >= 0.f && z <= 255.f && z == rintf(z))) f |= 1u;
+    if (s != 0.f && !(fabsf(s) >= 6.2e-5f && fabsf(s) <= 200.f)) f |= 2u;
+    if (f) atomicOr(flags, f);
     __nv_bfloat162 sb = __float2bfloat162_rn(s);
     uint2 o;
     o.y = *reinterpret_cast<uint32_t *>(&sb);
@@ -163,9 +170,16 @@ int32_t k_wpack_from_codes(dllm_ctx *ctx, const uint8_t *codes_dev, dllm_qweight
 int32_t k_wdq_params(dllm_ctx *ctx, dllm_qweight *qw) {
     const size_t G = qw->per_tensor ? 1 : qw->K / qw->group;
     const size_t n = G * qw->n_tiles * 128;
+    unsigned int *flags = reinterpret_cast<unsigned int *>(ctx->d_params + 8);
+    CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, sizeof(unsigned int), ctx->stream));
     wdq_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(qw->d_scales, qw->d_zps, n,
-                                                                            wl_container_bits(qw->bits), qw->d_dqparams, qw->d_gparams);
+                                                                            wl_container_bits(qw->bits), qw->d_dqparams, qw->d_gparams, flags);
     LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_params + 8, flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned int f = *reinterpret_cast<unsigned int *>(ctx->h_params + 8);
+    qw->int_zps = (f & 1u) == 0;
+    qw->f16_scales = (f & 2u) == 0;
     return DLLM_OK;
 }
 
