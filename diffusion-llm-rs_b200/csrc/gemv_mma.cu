@@ -111,6 +111,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// programmatic dependent launch: `launch_dependents` lets the next kernel of the stream start its prologue while this
+// one runs; `wait` blocks until the previous kernel of the stream has completed and its memory is visible
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -396,6 +400,9 @@ gemv_mma_kernel(const GemvArgs a) {
 #define GTRACE(slot) do { } while (0)
 #endif
     if (threadIdx.x == 0) GTRACE(0);
+    // The next kernel of the stream (typically the next layer's GEMV) may start now: its producers prefetch weights —
+    // which depend on nothing — into their ring while this kernel still runs; everything else of it waits (pdl_wait).
+    pdl_launch_dependents();
 
     if (threadIdx.x == 0) {
         // full: one arrival per lane of the owning producer warp, triggered when that lane's cp.async copies landed
@@ -411,6 +418,7 @@ gemv_mma_kernel(const GemvArgs a) {
         //  single producer warp caps the SM at a fraction of its HBM share; NP warps and KBS tiles per copy
         //  lift that cap)
         const uint32_t me = (uint32_t)(warp - NG * kGroupWarps);
+        if (!XR) pdl_wait();                    // the prepared activations come from the kernel before this one
         ItemIter iter(rg);
         Item item;
         uint32_t it0 = 0, my_it = me, my_s = me, my_ph = 0;
@@ -480,6 +488,8 @@ gemv_mma_kernel(const GemvArgs a) {
         const uint32_t ring_bytes = a.stages * kStage, bar_bytes = a.stages * 8;
         asm volatile("" : "+r"(cwa), "+r"(dpw), "+r"(xs_lane), "+r"(fa));
         if (ctid == 0) GTRACE(1);
+        // activations, partial-tile workspace, tickets and y belong to the stream's previous kernels until they are done
+        pdl_wait();
         if (XR) prepare_x_slice<CB, MT>(a, rg, xs, ctid, kConsumers + 32);
         if (ctid == 0) GTRACE(2);
         uint32_t n_item = 0, last_nt = 0;
@@ -551,6 +561,7 @@ gemv_mma_kernel(const GemvArgs a) {
         }
     } else {
         // ===================== epilogue warp =====================
+        pdl_wait();
         if (XR) prepare_x_slice<CB, MT>(a, rg, xs, kConsumers + lane, kConsumers + 32);
         ItemIter iter(rg);
         Item item;
@@ -705,7 +716,22 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
         ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
         CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    gemv_mma_kernel<CB, MT, NG, NP, KBS, XR><<<grid, (NG * kGroupWarps + NP + 1) * 32, smem_bytes, ctx->stream>>>(a);
+    {
+        // programmatic stream serialization: this kernel may be scheduled before the stream's previous kernel has
+        // finished (it waits in-kernel where it depends on it, see pdl_wait)
+        static const bool no_pdl = getenv("DLLM_GEMV_NO_PDL") != nullptr;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3((NG * kGroupWarps + NP + 1) * 32);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = no_pdl ? 0 : 1;
+        CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, gemv_mma_kernel<CB, MT, NG, NP, KBS, XR>, a));
+    }
     LAUNCH_CHECK(ctx);
     if (ev1) {
         CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));

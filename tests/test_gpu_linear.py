@@ -225,6 +225,30 @@ def test_qlinear_auto_path_small_m_is_gemv(ctx, O):
     qw.close()
 
 
+def test_fractional_zero_points_take_the_f32_path(ctx, O):
+    """Hand-made parameters with non-integer zero-points (quantizer B never produces them): the 16-bit-operand
+    kernels subtract the zero-point exactly only when it is an integer, so AUTO must fall back to the f32-faithful
+    SIMT kernel and an explicit request for the other paths must fail loudly."""
+    import dllm_b200
+    from dllm_b200 import QWeight, PATH_AUTO, PATH_SIMT, PATH_GEMV, PATH_UMMA
+    rng = np.random.default_rng(11)
+    K, N = 256, 128
+    codes = rng.integers(0, 16, (K, N)).astype(np.uint8)
+    scales = (rng.random((K // 128, N)) * 0.01 + 0.001).astype(F)
+    zps = (rng.integers(0, 15, (K // 128, N)) + 0.5).astype(F)
+    qw = QWeight.from_codes(ctx, codes, scales, zps, 4, 128)
+    x = rng.standard_normal((4, K)).astype(F)
+    y = qw.forward(x, PATH_AUTO)
+    assert beq(y, qw.forward(x, PATH_SIMT))
+    wd = O.dequantize_weight_grouped(codes, scales, zps, 128)
+    bound = np.abs(x).astype(np.float64) @ np.abs(wd).astype(np.float64)
+    assert np.all(np.abs(y - O.linear_f64(x, wd, None)) <= 2e-5 * bound + 1e-6)
+    for path in (PATH_GEMV, PATH_UMMA):
+        with pytest.raises(dllm_b200.UnsupportedOperation):
+            qw.forward(x, path)
+    qw.close()
+
+
 @pytest.mark.parametrize("bits,M", [(4, 1), (4, 16), (2, 4), (8, 8)])
 def test_qlinear_gemv_full_width(ctx, bits, M):
     """Full BASELINE width (K=N=14336): the GEMV path against the f32-faithful SIMT path, run-to-run
