@@ -228,7 +228,10 @@ def workload_config(args, world):
     params = sum(k * n for k, n in shapes)
     return {"workload": f"diffuse-llm-rs single denoising step, synthetic {args.model.upper()}-class model "
                         f"({len(shapes)} quantized linears, {params / 1e9:.2f} G params), 4-bit weights group 128, "
-                        f"{CANVAS}-token canvas, batch {BATCH}, single B200 (BASELINE.json configs[2])",
+                        f"{CANVAS}-token canvas, batch {BATCH}, " +
+                        ("single B200 (BASELINE.json configs[2])" if world == 1 else
+                         f"one replica per B200, {world} GPUs (configs[2], data parallel)" if args.parallelism == "dp" else
+                         f"tensor-parallel across {world} B200 over NVLink (the step of BASELINE.json configs[3])"),
             "hidden": H, "tokens_per_step": BATCH * CANVAS, "bits": 4, "group_size": 128,
             "parallelism": "single" if world == 1 else (f"dp{world}" if args.parallelism == "dp" else f"tp{world}"),
             "l2": "working set (0.5 GB packed weights + 2x67 MB activations per linear) exceeds the 126 MB L2",

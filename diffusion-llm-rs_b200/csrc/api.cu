@@ -794,6 +794,7 @@ static void p_sample_coeffs_host(const dllm_model *m, size_t t, int guard_t0, fl
 
 // tensor-parallel hooks (tp.cu)
 int32_t tp_allreduce(dllm_ctx *ctx, float *buf, size_t n);
+int32_t tp_allreduce_bf16(dllm_ctx *ctx, void *buf, size_t n);
 int32_t tp_allgather_cols(dllm_ctx *ctx, const float *in, size_t M, size_t n_local, float *out);
 
 static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x_dev, size_t tokens, float *out_dev,
@@ -812,8 +813,13 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
     for (int p : m->parallel) any_parallel = any_parallel || p != 0;
     if (path == DLLM_PATH_UMMA && !all_umma) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "tcgen05 path does not support this stack");
 
-    if (all_umma && !any_parallel) {
-        // bf16 activations between layers; the last layer writes f32
+    // tensor-parallel stacks whose column-parallel layers all feed a row-parallel one need no all-gather
+    bool no_gather = true;
+    for (size_t l = 0; l < L; ++l)
+        if (m->parallel[l] == 1 && (l + 1 == L || m->parallel[l + 1] != 2)) no_gather = false;
+    if (all_umma && (!any_parallel || no_gather)) {
+        // bf16 activations between layers; the last layer writes f32.  Row-parallel layers leave partial sums:
+        // one NCCL all-reduce at the layer boundary, on the bf16 tensor the next linear reads (f32 for the last).
         DLLM_TRY(ensure_buf(ctx, ctx->act[0], tokens * maxw * 2));
         DLLM_TRY(ensure_buf(ctx, ctx->act[1], tokens * maxw * 2));
         DLLM_TRY(k_f32_to_bf16(ctx, x_dev, tokens * m->layers[0]->K, ctx->act[0].p));
@@ -821,6 +827,10 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
         for (size_t l = 0; l < L; ++l) {
             const bool last = l + 1 == L;
             DLLM_TRY(k_qlinear_umma(ctx, m->layers[l], cur, tokens, last ? out_dev : nullptr, last ? nullptr : nxt));
+            if (m->parallel[l] == 2) {
+                if (last) DLLM_TRY(tp_allreduce(ctx, out_dev, tokens * m->layers[l]->N));
+                else DLLM_TRY(tp_allreduce_bf16(ctx, nxt, tokens * m->layers[l]->N));
+            }
             void *t = cur; cur = nxt; nxt = t;
         }
         return DLLM_OK;

@@ -25,6 +25,15 @@ int32_t tp_allreduce(dllm_ctx *ctx, float *buf, size_t n) {
     return DLLM_OK;
 }
 
+// bf16 partial sums of a row-parallel linear, reduced in place (half the NVLink bytes of the f32 form; the result
+// feeds the next tcgen05 linear, which reads bf16 anyway)
+int32_t tp_allreduce_bf16(dllm_ctx *ctx, void *buf, size_t n) {
+    if (ctx->tp_world <= 1 || n == 0) return DLLM_OK;
+    if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
+    NCCL_TRY(ctx, ncclAllReduce(buf, buf, n, ncclBfloat16, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return DLLM_OK;
+}
+
 namespace {
 // gathered [world][M][n_local] -> out [M][world*n_local]
 __global__ void interleave_cols_kernel(const float *__restrict__ gathered, size_t M, size_t n_local, int world,

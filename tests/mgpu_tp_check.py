@@ -31,7 +31,11 @@ def main():
     tpg = P.TensorParallelGroup(ctx, rank, world)
     tpg.init_nccl()
     ok = True
-    for path, tol in ((dllm_b200.PATH_SIMT, 1e-5), (dllm_b200.PATH_UMMA, 2e-2)):
+    x_full = x
+    # (path, tolerance, tokens): f32 SIMT; tcgen05 with bf16 all-reduce at the row-parallel boundaries; and the
+    # HBM-bound GEMV kernel (AUTO at <= 16 tokens) with f32 all-reduce
+    for path, tol, rows in ((dllm_b200.PATH_SIMT, 1e-5, 4), (dllm_b200.PATH_UMMA, 2e-2, 4), (dllm_b200.PATH_AUTO, 2e-3, 1)):
+        x = x_full[:rows, :hidden * (64 if rows == 4 else 8)]            # 256 tokens / 8 tokens
         layers = []
         for w, b, mode in zip(ws, bs, plan):
             wsh, bsh = P.shard_weight(w, b, mode, rank, world)
