@@ -106,6 +106,21 @@ const char *dllm_last_error(const dllm_ctx *ctx) { return ctx ? ctx->err : "null
 uint64_t dllm_launch_count(const dllm_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int32_t dllm_sm_count(const dllm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
+int32_t dllm_selftest_division(dllm_ctx *ctx, uint64_t cases, uint64_t seed, uint64_t *mismatches) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, mismatches, DLLM_ERR_NULL, "null out pointer");
+    unsigned long long *d = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d, sizeof(unsigned long long)));
+    cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream);
+    int32_t rc = k_selftest_division(ctx, cases, seed, d);
+    unsigned long long h = 0;
+    if (rc == DLLM_OK && cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = DLLM_ERR_CUDA;
+    if (rc == DLLM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = DLLM_ERR_CUDA;
+    cudaFree(d);
+    *mismatches = h;
+    return rc;
+}
+
 int32_t dllm_profile_begin(dllm_ctx *ctx) {
     CTX_CHECK(ctx);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -25,6 +25,9 @@ int32_t k_unpack(dllm_ctx *ctx, const uint8_t *packed_dev, size_t n, int bits, u
 int32_t k_quant_d_rows(dllm_ctx *ctx, const float *x_dev, size_t rows, size_t dim, const uint8_t *bits_tab_dev,
                        int nbits, int uniform_bits, int pack, uint8_t *out_dev, float *scales_dev, float *zps_dev);
 
+// div_row (hoisted-reciprocal division of the row quantizer) against __fdiv_rn: counts differing quotients
+int32_t k_selftest_division(dllm_ctx *ctx, unsigned long long cases, unsigned long long seed, unsigned long long *mismatches_dev);
+
 // ---- weight_kernels.cu ----
 // per-(group, column) quantizer-B parameters of W[K,N] (row-major f32)
 int32_t k_wparams_grouped(dllm_ctx *ctx, const float *w_dev, size_t K, size_t N, size_t group, int bits,

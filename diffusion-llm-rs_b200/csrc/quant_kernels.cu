@@ -8,6 +8,8 @@
 // All of them are streaming kernels: one coalesced 128-bit load per lane per step, codes
 // produced in registers (IEEE division via __fdiv_rn, no FMA contraction), narrow coalesced
 // stores.  Grids are multiples of the SM count.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -382,18 +384,59 @@ quant_d_rows_kernel(const float *__restrict__ x, size_t rows, size_t dim, const 
         const float zp = mn;                                        // :108
         if (threadIdx.x == 0) { scales[r] = scale; zps[r] = zp; }
         uint8_t *orow = out + (PACK ? r * (dim * PACK / 8) : r * dim);
+        // every numerator x - zp of the row lies in [0, max - min] (NaN elements stay NaN -> code 0): one divisor per
+        // row, reciprocal and range check hoisted (common.cuh); rows with inf / NaN / extreme scales take __fdiv_rn
+        const RowDivisor rd = make_row_divisor(scale, __fsub_rn(mx, mn));
+        const unsigned int ulevels = (unsigned int)levels;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const size_t i = (size_t)j * T + threadIdx.x;
             const bool act = i < d4;
             uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             if (act) {
-                c0 = code_cd(v[j].x, scale, zp, levels); c1 = code_cd(v[j].y, scale, zp, levels);
-                c2 = code_cd(v[j].z, scale, zp, levels); c3 = code_cd(v[j].w, scale, zp, levels);
+                if (rd.fast) {
+                    c0 = clamp_trunc_u8(div_row(rd, __fsub_rn(v[j].x, zp)), ulevels);
+                    c1 = clamp_trunc_u8(div_row(rd, __fsub_rn(v[j].y, zp)), ulevels);
+                    c2 = clamp_trunc_u8(div_row(rd, __fsub_rn(v[j].z, zp)), ulevels);
+                    c3 = clamp_trunc_u8(div_row(rd, __fsub_rn(v[j].w, zp)), ulevels);
+                } else {
+                    c0 = code_cd(v[j].x, scale, zp, levels); c1 = code_cd(v[j].y, scale, zp, levels);
+                    c2 = code_cd(v[j].z, scale, zp, levels); c3 = code_cd(v[j].w, scale, zp, levels);
+                }
             }
             store_codes4<PACK>(orow, i, c0, c1, c2, c3, act);
         }
     }
+}
+
+// Self-test of div_row against __fdiv_rn.  Case i: divisor d from a hash of i (random significand, exponent in
+// [-40, 40]); numerators around every code boundary: RN(c·d) + k ulps for c = 1..256, k = -4..4, plus random ones.
+// Counts quotients whose bits differ (zeros of either sign are equal) — there must be none.
+__global__ void selftest_division_kernel(unsigned long long cases, unsigned long long seed, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cases;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long z = (i + seed) * 0x9E3779B97F4A7C15ull;       // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const int ex = (int)((z >> 40) % 81) - 40;
+        const float d = __uint_as_float((uint32_t)(127 + ex) << 23 | (uint32_t)(z & 0x7fffffu));
+        const RowDivisor rd = make_row_divisor(d, 1.0f);
+        for (int c = 1; c <= 256; ++c) {
+            const float base = __fmul_rn((float)c, d);
+            for (int k = -4; k <= 4; ++k) {
+                const float n = __uint_as_float(__float_as_uint(base) + k);
+                const float a = div_row(rd, n), b = __fdiv_rn(n, d);
+                if (__float_as_uint(a) != __float_as_uint(b) && !(a == 0.f && b == 0.f)) ++bad;
+            }
+        }
+        // a random numerator with quotient in (0, 512)
+        const float n = __fmul_rn(d, (float)((z >> 8) & 0xffffff) * (512.0f / 16777216.0f));
+        const float a = div_row(rd, n), b = __fdiv_rn(n, d);
+        if (__float_as_uint(a) != __float_as_uint(b) && !(a == 0.f && b == 0.f)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // generic fallback: any dim, any alignment, one warp per row, two passes over the row
@@ -582,6 +625,12 @@ int32_t k_quant_d_rows(dllm_ctx *ctx, const float *x_dev, size_t rows, size_t di
     else if (d4 <= 128 * 4) launch_d_rows<128, 4>(ctx, x_dev, rows, dim, bits_tab_dev, nbits, uniform_bits, pack, out_dev, scales_dev, zps_dev);
     else if (d4 <= 256 * 4) launch_d_rows<256, 4>(ctx, x_dev, rows, dim, bits_tab_dev, nbits, uniform_bits, pack, out_dev, scales_dev, zps_dev);
     else launch_d_rows<256, 16>(ctx, x_dev, rows, dim, bits_tab_dev, nbits, uniform_bits, pack, out_dev, scales_dev, zps_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
+
+int32_t k_selftest_division(dllm_ctx *ctx, unsigned long long cases, unsigned long long seed, unsigned long long *mismatches_dev) {
+    selftest_division_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(cases, seed, mismatches_dev);
     LAUNCH_CHECK(ctx);
     return DLLM_OK;
 }

@@ -82,6 +82,7 @@ SIGNATURES = {
     "dllm_last_error": (C.c_char_p, [c_vp]),
     "dllm_launch_count": (C.c_uint64, [c_vp]),
     "dllm_sm_count": (C.c_int32, [c_vp]),
+    "dllm_selftest_division": (C.c_int32, [c_vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "dllm_profile_begin": (C.c_int32, [c_vp]),
     "dllm_profile_end": (C.c_int32, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]),

@@ -92,6 +92,10 @@ DLLM_API int32_t dllm_sm_count(const dllm_ctx *ctx);
 /* per-launch CUDA-event timing of the dominant (tcgen05 linear) kernel on the context's stream.
  * begin() arms it; end() synchronises and returns the number of bracketed launches, their summed
  * duration, and the algorithmic flops / bytes they covered (SURVEY.md §8d formulas). */
+/* self-test: the per-row quantizer divides by a row's scale with a hoisted reciprocal and exact-FMA corrections;
+ * compares that against IEEE division on `cases` divisors x 2305 numerators around every code boundary and returns
+ * the number of differing quotients (must be 0) */
+DLLM_API int32_t dllm_selftest_division(dllm_ctx *ctx, uint64_t cases, uint64_t seed, uint64_t *mismatches);
 DLLM_API int32_t dllm_profile_begin(dllm_ctx *ctx);
 DLLM_API int32_t dllm_profile_end(dllm_ctx *ctx, uint64_t *n_launches, double *total_ms, double *total_flops,
                                   double *total_bytes);

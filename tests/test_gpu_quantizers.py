@@ -337,6 +337,48 @@ def _torch_round_half_away(t):
     return r + ((t - r).abs() >= 0.5).to(t.dtype) * torch.sign(t)
 
 
+def test_row_division_matches_ieee_division(ctx):
+    """The per-token quantizer divides by the row's scale with a hoisted correctly-rounded reciprocal and two exact-FMA
+    corrections (common.cuh: div_row).  Brute force on the device: 2^20 random divisors x (every code boundary
+    1..256 x +-4 ulps + a random numerator) = 2.4e9 quotients, all bit-identical to IEEE division."""
+    import ctypes as C
+    bad = C.c_uint64(123)
+    ctx._ck(ctx._lib.dllm_selftest_division(ctx.h, 1 << 20, 42, C.byref(bad)))
+    assert bad.value == 0
+
+
+@pytest.mark.parametrize("dim", [512, 1000, 4096, 14000])
+def test_d_rows_many_rows_bit_exact(ctx, O, dim):
+    """Many rows (several per resident CTA, so the row loop and its register reuse are exercised): same codes, scales
+    and zero-points as the oracle, with the reference's degenerate rows (constant row -> 0/0 = NaN -> code 0), NaN and
+    inf entries, a cycling bit-width table (fusion_ann.rs:58) and every packed width."""
+    rng = np.random.default_rng(dim)
+    rows = 1000
+    x = rng.standard_normal((rows, dim)).astype(F)
+    x[1] = 0.75
+    x[2, 3] = np.nan
+    x[3, 1] = np.inf
+    x[997, dim - 1] = -np.inf
+    for bits in ([4], [1, 2, 4, 8], [2, 16]):
+        c0, s0, z0 = O.quantize_d_rows(x, bits)
+        c1, s1, z1 = ctx.quantize_d_rows(x, bits)
+        assert beq(s0, s1) and beq(z0, z1)
+        assert np.array_equal(c0, c1)
+    n = rows * dim
+    dx, dc, ds, dz = ctx.malloc(n * 4), ctx.malloc(n), ctx.malloc(rows * 4), ctx.malloc(rows * 4)
+    ctx.h2d(dx, x)
+    for bits in (1, 2, 4, 8):
+        if (dim * bits // 8) % 4 or dim * bits % 8:
+            continue                                   # packed rows must be whole 32-bit words
+        ctx.quantize_d_rows_dev(dx, rows, dim, bits, True, dc, ds, dz)
+        ctx.sync()
+        c0, s0, z0 = O.quantize_d_rows(x, [bits])
+        assert beq(ctx.d2h(ds, (rows,), F), s0) and beq(ctx.d2h(dz, (rows,), F), z0)
+        assert np.array_equal(ctx.d2h(dc, (n * bits // 8,), np.uint8), O.pack(c0, bits))
+    for p in (dx, dc, ds, dz):
+        ctx.free(p)
+
+
 @pytest.mark.parametrize("bits", [4, 8])
 def test_kv_full_row_size_against_torch_restatement(ctx, bits):
     """Per-token KV quantize at the BASELINE config-4 row width (hidden 4096) on 2^16 rows
