@@ -134,7 +134,14 @@ template <int SCHEME, int PACK>
 __global__ void __launch_bounds__(kThreads)
 encode_kernel(const float *__restrict__ x, size_t n, uint8_t *__restrict__ out, EncArgs a) {
     float s = a.scale, z = a.zp;
-    if (a.dev) { s = __ldg(a.dev); z = __ldg(a.dev + 1); }
+    // quantizer B with its parameters on the device ({scale, zp, min, max} from minmax_kernel): one divisor for the
+    // whole tensor and a known numerator range -> hoisted-reciprocal division (common.cuh), bit-identical quotients
+    RowDivisor rd;
+    rd.fast = false;
+    if (a.dev) {
+        s = __ldg(a.dev); z = __ldg(a.dev + 1);
+        if (SCHEME == 0) rd = make_row_divisor(s, fmaxf(fabsf(__ldg(a.dev + 2)), fabsf(__ldg(a.dev + 3))));
+    }
     const size_t n4 = n >> 2;
     const float4 *x4 = reinterpret_cast<const float4 *>(x);
     const size_t nth = (size_t)gridDim.x * blockDim.x;
@@ -144,8 +151,16 @@ encode_kernel(const float *__restrict__ x, size_t n, uint8_t *__restrict__ out, 
     for (size_t it = 0; it < iters; ++it, i += nth) {
         const bool act = i < n4;
         float4 v = act ? ldg_stream_f4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t c0 = encode_one<SCHEME>(v.x, s, z, a), c1 = encode_one<SCHEME>(v.y, s, z, a);
-        uint32_t c2 = encode_one<SCHEME>(v.z, s, z, a), c3 = encode_one<SCHEME>(v.w, s, z, a);
+        uint32_t c0, c1, c2, c3;
+        if (SCHEME == 0 && rd.fast) {          // code_b with the division replaced: round(x / scale + zp), clamp
+            c0 = (uint32_t)rs_clampi(rs_as_i32(roundf(__fadd_rn(div_row_checked(rd, v.x), z))), 0, a.ihi);
+            c1 = (uint32_t)rs_clampi(rs_as_i32(roundf(__fadd_rn(div_row_checked(rd, v.y), z))), 0, a.ihi);
+            c2 = (uint32_t)rs_clampi(rs_as_i32(roundf(__fadd_rn(div_row_checked(rd, v.z), z))), 0, a.ihi);
+            c3 = (uint32_t)rs_clampi(rs_as_i32(roundf(__fadd_rn(div_row_checked(rd, v.w), z))), 0, a.ihi);
+        } else {
+            c0 = encode_one<SCHEME>(v.x, s, z, a); c1 = encode_one<SCHEME>(v.y, s, z, a);
+            c2 = encode_one<SCHEME>(v.z, s, z, a); c3 = encode_one<SCHEME>(v.w, s, z, a);
+        }
         store_codes4<PACK>(out, i, c0, c1, c2, c3, act);
     }
 }
@@ -410,7 +425,7 @@ quant_d_rows_kernel(const float *__restrict__ x, size_t rows, size_t dim, const 
 }
 
 // Self-test of div_row against __fdiv_rn.  Case i: divisor d from a hash of i (random significand, exponent in
-// [-40, 40]); numerators around every code boundary: RN(c·d) + k ulps for c = 1..256, k = -4..4, plus random ones.
+// [-40, 40]); numerators around every code boundary: +-(RN(c·d) + k ulps) for c = 1..256, k = -4..4, plus random ones.
 // Counts quotients whose bits differ (zeros of either sign are equal) — there must be none.
 __global__ void selftest_division_kernel(unsigned long long cases, unsigned long long seed, unsigned long long *mismatches) {
     unsigned long long bad = 0;
@@ -429,6 +444,8 @@ __global__ void selftest_division_kernel(unsigned long long cases, unsigned long
                 const float n = __uint_as_float(__float_as_uint(base) + k);
                 const float a = div_row(rd, n), b = __fdiv_rn(n, d);
                 if (__float_as_uint(a) != __float_as_uint(b) && !(a == 0.f && b == 0.f)) ++bad;
+                const float a2 = div_row_checked(rd, -n), b2 = __fdiv_rn(-n, d);      // quantizer B sees negative numerators
+                if (__float_as_uint(a2) != __float_as_uint(b2) && !(a2 == 0.f && b2 == 0.f)) ++bad;
             }
         }
         // a random numerator with quotient in (0, 512)

@@ -340,7 +340,7 @@ def _torch_round_half_away(t):
 def test_row_division_matches_ieee_division(ctx):
     """The per-token quantizer divides by the row's scale with a hoisted correctly-rounded reciprocal and two exact-FMA
     corrections (common.cuh: div_row).  Brute force on the device: 2^20 random divisors x (every code boundary
-    1..256 x +-4 ulps + a random numerator) = 2.4e9 quotients, all bit-identical to IEEE division."""
+    1..256 x +-4 ulps, both signs, + a random numerator) = 4.8e9 quotients, all bit-identical to IEEE division."""
     import ctypes as C
     bad = C.c_uint64(123)
     ctx._ck(ctx._lib.dllm_selftest_division(ctx.h, 1 << 20, 42, C.byref(bad)))
