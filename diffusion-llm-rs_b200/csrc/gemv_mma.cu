@@ -14,18 +14,22 @@
 //   * the CTA's slice of the activations is staged ONCE into shared memory (bf16, fragment order) and
 //     stays resident: no activation traffic in the steady state;
 //   * NG groups of 8 consumer warps take the stages round-robin.  A warp owns 16 output columns of the
-//     128-column tile: it reads its codes with conflict-free LDS.32 and turns them into exact fp16
-//     (q - zp) pairs in registers — 0x6400 | q is the half 1024 + q, 0x6400 | (q << 4) is 1024 + 16 q, so a
-//     32-bit word of eight 4-bit codes costs one shift, four LOP3 and four HSUB2 / HFMA2 — and feeds them to
-//     mma.sync.m16n8k16 (f16 operands, f32 accumulate) with the activations as the B operand.  The group's
-//     scale is applied in f32 to the k-block's partial sum (more accurate than scaling the 16-bit operand).
-//     Tensor cores are used only so that the FMA work costs one instruction per 256 weights: what bounds the
-//     kernel after the copy engine is the ~1.1 CUDA-core instructions per weight of the unpack;
+//     128-column tile: it reads its codes with conflict-free LDS.32 and turns them into fp16 operands in
+//     registers with ONE LOP3 per pair — 0x6400 | q is the half 1024 + q, 0x6400 | (q << 4) is 1024 + 16 q (those
+//     k positions meet activations prepared as x / 16) — so a 32-bit word of eight 4-bit codes costs one shift
+//     and four LOP3, and feeds them to mma.sync.m16n8k16 (f16 operands, f32 accumulate) with the activations as
+//     the B operand.  Neither the magic 1024 nor the zero-point is subtracted per weight: per (k-block, token)
+//     the x preparation also stores T = sum of the fp16 operands and S = sum of x, split into fp16 parts, and ONE
+//     more MMA per k-block with A = {64 zp, 32768, ...} and B = {-S/64, -T/64, ...} removes 1024 T + zp S from the
+//     accumulator (sum x (1024 + q) - 1024 sum x - zp sum x = sum x (q - zp)).  The group's scale is applied in f32
+//     to the k-block's partial sum.  Tensor cores are used only so that the FMA work costs one instruction per 256
+//     weights: what bounds the kernel after the copy engine is the CUDA-core instructions of the unpack;
 //   * tiles cut by a range boundary are reduced by the LAST CTA to arrive at the tile (atomic ticket,
 //     no spinning), always in CTA order: results are deterministic and there is no fix-up launch.
 //
-// Numerics: (q - zp) exact, x rounded to fp16 (saturated at +-65504), f32 accumulate, f32 scale.
-// Zero-points must be the integers quantizer B produces (quantization.rs:55-56).
+// Numerics: codes and zero-points exact, x rounded to fp16 (saturated at +-65504), f32 accumulate, f32 scale; the
+// 1024-offset cancels inside the f32 accumulator of one k-block (|1024 sum_64 x| * 2^-24 per MMA: two orders of
+// magnitude below the fp16 rounding of x).  Zero-points must be the integers quantizer B produces (quantization.rs:55-56).
 // Timeline instrumentation (globaltimer stamps per CTA / per stage) compiles in with -DDLLM_GEMV_TRACE.
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -144,19 +148,6 @@ __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t m
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
     return d;
 }
-__device__ __forceinline__ uint32_t h2sub(uint32_t a, uint32_t b) {
-    __half2 r = __hsub2(*reinterpret_cast<__half2 *>(&a), *reinterpret_cast<__half2 *>(&b));
-    return *reinterpret_cast<uint32_t *>(&r);
-}
-__device__ __forceinline__ uint32_t h2fma(uint32_t a, uint32_t b, uint32_t c) {
-    __half2 r = __hfma2(*reinterpret_cast<__half2 *>(&a), *reinterpret_cast<__half2 *>(&b), *reinterpret_cast<__half2 *>(&c));
-    return *reinterpret_cast<uint32_t *>(&r);
-}
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-    __half2 r = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-    return *reinterpret_cast<uint32_t *>(&r);
-}
-
 // k (inside a 64-k block) of element e (0..7) of the 16-byte activation unit that lane quad-index t
 // consumes in round u (0..1); the code words of wlayout.cuh decide it (see consume_stage)
 template <int CB>
@@ -168,9 +159,9 @@ __host__ __device__ __forceinline__ int gemv_kmap(int u, int t, int e) {
 
 struct GemvArgs {
     const uint8_t *packed;
-    const uint2 *gparams;            // [G][Npad] {f32 scale, half2(1024 + zp)}
+    const uint2 *gparams;            // [G][Npad] {f32 scale, half2(64 zp, zp / 32)}
     const float *bias;
-    const uint8_t *xb;               // !XR: prepared activations [k_blocks][2 rounds][MT tokens][4 t][8 e] fp16
+    const uint8_t *xb;               // !XR: prepared activations [k_blocks] tiles of gemv_x_tile_bytes(MT)
     const float *x;                  // XR: the f32 activations [M, K]; every CTA prepares its own slice in shared memory
     uint32_t K;
     float *y;                        // [M, N]
@@ -222,16 +213,21 @@ struct ItemIter {
     }
 };
 
+// bytes of one k-block of prepared activations: [2 rounds][MT tokens][4 t] 16-byte units, then one 16-byte
+// correction entry per token (x_corr_entry)
+__host__ __device__ constexpr int gemv_x_tile_bytes(int MT) { return MT * 144; }
+
 // one 64-k block of a 128-column tile, consumed by the 8 warps of one group.
 // Shared-memory addresses, each already offset to this lane's element (lane = 4 g + t, output columns
 // r0 = 16 w + g and r0 + 8):
 //   cw : word t of chunk 0 of column r0 of the packed codes (wlayout.cuh): + 2048 per chunk, + 128 for column r0 + 8
-//   pw : {f32 scale, half2(1024 + zp)} of column r0: + 64 for column r0 + 8
+//   pw : {f32 scale, half2(64 zp, zp / 32)} of column r0: + 64 for column r0 + 8
 //   xw : the lane's 16-byte unit of token min(g, MT - 1) in round 0 of the fp16 activations: + 64 MT per round, + 512 for
 //        token g + 8.  (Lanes with g >= MT feed MMA columns of tokens that do not exist and are never stored; they
 //        re-read the last token instead of zeroing registers.)
+//   xc : word t of that token's correction entry: + 128 for token g + 8
 template <int CB, int MT>
-__device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_t xw, float (*ya)[4]) {
+__device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_t xw, uint32_t xc, uint32_t zmask, uint32_t cfill, float (*ya)[4]) {
     constexpr int NB = MT > 8 ? 2 : 1;           // 8-token MMA column blocks
     constexpr uint32_t kMagic = 0x64006400u;     // half2(1024, 1024)
     const uint2 p0 = lds64(pw), p1 = lds64(pw + 64);
@@ -241,18 +237,20 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
 
     // activations of both rounds first: independent of everything else
     uint4 b[2][NB];
+    uint32_t bc[NB];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
             b[u][nb] = lds128(xw + u * (MT * 64) + nb * 512);
         }
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) bc[nb] = lds32(xc + nb * 128);
 
     if (CB == 4) {
-        // word = codes 0..7 at nibbles {0,4,1,5,2,6,3,7}: (w & 0x000f000f) = codes (0,1), (w & 0x00f000f0) = 16 x codes (2,3),
-        // the same of w >> 8 = codes (4,5), (6,7).   1024 + q - (1024 + zp) and (1024 + 16 q) / 16 - (64 + zp) are exact.
-        const uint32_t kSixteenth = 0x2C002C00u, k960 = 0x63806380u;     // half2(1/16), half2(960)
-        const uint32_t zh0 = h2sub(k960, p0.y), zh1 = h2sub(k960, p1.y);   // -(64 + zp)
+        // word = codes 0..7 at nibbles {0,4,1,5,2,6,3,7}: (w & 0x000f000f) | magic = 1024 + codes (0,1),
+        // (w & 0x00f000f0) | magic = 1024 + 16 x codes (2,3) (their activations are stored as x / 16), the same of
+        // w >> 8 = codes (4,5), (6,7)
         uint32_t q[2][2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) { q[u][0] = lds32(cw + u * 2048); q[u][1] = lds32(cw + u * 2048 + 128); }
@@ -261,10 +259,10 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t v0 = h ? q[u][0] >> 8 : q[u][0], v1 = h ? q[u][1] >> 8 : q[u][1];
-                const uint32_t a0 = h2sub(and_or(v0, 0x000f000fu, kMagic), p0.y);
-                const uint32_t a1 = h2sub(and_or(v1, 0x000f000fu, kMagic), p1.y);
-                const uint32_t a2 = h2fma(and_or(v0, 0x00f000f0u, kMagic), kSixteenth, zh0);
-                const uint32_t a3 = h2fma(and_or(v1, 0x00f000f0u, kMagic), kSixteenth, zh1);
+                const uint32_t a0 = and_or(v0, 0x000f000fu, kMagic);
+                const uint32_t a1 = and_or(v1, 0x000f000fu, kMagic);
+                const uint32_t a2 = and_or(v0, 0x00f000f0u, kMagic);
+                const uint32_t a3 = and_or(v1, 0x00f000f0u, kMagic);
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
             }
@@ -277,10 +275,10 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int p = 4 * u + 2 * h;
-                const uint32_t a0 = h2sub(and_or(q0 >> (2 * p), 0x00030003u, kMagic), p0.y);
-                const uint32_t a1 = h2sub(and_or(q1 >> (2 * p), 0x00030003u, kMagic), p1.y);
-                const uint32_t a2 = h2sub(and_or(q0 >> (2 * p + 2), 0x00030003u, kMagic), p0.y);
-                const uint32_t a3 = h2sub(and_or(q1 >> (2 * p + 2), 0x00030003u, kMagic), p1.y);
+                const uint32_t a0 = and_or(q0 >> (2 * p), 0x00030003u, kMagic);
+                const uint32_t a1 = and_or(q1 >> (2 * p), 0x00030003u, kMagic);
+                const uint32_t a2 = and_or(q0 >> (2 * p + 2), 0x00030003u, kMagic);
+                const uint32_t a3 = and_or(q1 >> (2 * p + 2), 0x00030003u, kMagic);
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
             }
@@ -295,14 +293,22 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int c = 2 * u + h;
-                const uint32_t a0 = h2sub(__byte_perm(q[c][0], kMagic, 0x5150), p0.y);
-                const uint32_t a1 = h2sub(__byte_perm(q[c][1], kMagic, 0x5150), p1.y);
-                const uint32_t a2 = h2sub(__byte_perm(q[c][0], kMagic, 0x5352), p0.y);
-                const uint32_t a3 = h2sub(__byte_perm(q[c][1], kMagic, 0x5352), p1.y);
+                const uint32_t a0 = __byte_perm(q[c][0], kMagic, 0x5150);
+                const uint32_t a1 = __byte_perm(q[c][1], kMagic, 0x5150);
+                const uint32_t a2 = __byte_perm(q[c][0], kMagic, 0x5352);
+                const uint32_t a3 = __byte_perm(q[c][1], kMagic, 0x5352);
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
             }
         }
+    }
+    // the correction MMA: k slots (0,1) = (64 zp, zp / 32) x the fp16 parts of -S/64, slots 2..5 = (32768, 32768, 32, 2^-6) x
+    // the parts of -T/64 (x_corr_entry), the other slots zero: d -= zp S + 1024 T, i.e. d = sum x (q - zp)
+    // (quantization.rs:83's `- zp`)
+    {
+        const uint32_t ca0 = and_or(p0.y, zmask, cfill), ca1 = and_or(p1.y, zmask, cfill);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], ca0, ca1, 0u, 0u, bc[nb], 0u);
     }
     // dequantize_tensor's `* scale` (quantization.rs:83), applied to the k-block's partial sum in f32
     const float s0 = __uint_as_float(p0.x), s1 = __uint_as_float(p1.x);
@@ -315,10 +321,34 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
     }
 }
 
+// The correction entry of one (k-block, token): the B operand of consume_kblock's correction MMA, word t for lane
+// quad-index t.  s_all = sum of the 64 activations as the weights see them, s_fed = sum of the 64 fp16 operands as the
+// MMAs see them (equal unless CB == 4, where half of them are fed as x / 16).  |s / 64| <= 65504 always.  An f32 is
+// carried as fp16 parts that are rescaled to the magnitude of the leading part (hi, 2^11 (v - hi), 2^22 (v - hi - mid)),
+// so none of them is an fp16 subnormal and power-of-two scalings of x commute with the whole path; the A operand holds
+// the matching factors:   word 0: -S/64 as (hi, mid')   x (64 zp, zp / 32)
+//                         word 1: -T/64 as (hi, hi)     x (32768, 32768)
+//                         word 2: -T/64 as (mid', lo')  x (32, 2^-6)             word 3: zero
+__device__ __forceinline__ uint4 x_corr_entry(float s_all, float s_fed) {
+    const float vs = -s_all * 0.015625f, vt = -s_fed * 0.015625f;
+    const __half shi = __float2half_rn(vs);
+    const __half smid = __float2half_rn((vs - __half2float(shi)) * 2048.f);
+    const __half thi = __float2half_rn(vt);
+    const float r = (vt - __half2float(thi)) * 2048.f;
+    const __half tmid = __float2half_rn(r);
+    const __half tlo = __float2half_rn((r - __half2float(tmid)) * 2048.f);
+    return make_uint4((uint32_t)__half_as_ushort(shi) | ((uint32_t)__half_as_ushort(smid) << 16),
+                      (uint32_t)__half_as_ushort(thi) * 0x10001u,
+                      (uint32_t)__half_as_ushort(tmid) | ((uint32_t)__half_as_ushort(tlo) << 16), 0u);
+}
+
 // One 16-byte unit of the prepared activations: the 8 fp16 values of token `tok` that lane quad-index t consumes in
 // round u of k-block kb (gemv_kmap).  They are two runs of 4 consecutive k; `vec` = K % 4 == 0 and x is 16-byte aligned.
+// CB == 4: elements 2, 3, 6, 7 meet weights unpacked as 1024 + 16 q and are stored as x / 16 (exact but for fp16
+// subnormals).  s_all / s_fed accumulate the unit's share of x_corr_entry's sums, from the ROUNDED operands.
 template <int CB>
-__device__ __forceinline__ uint4 gemv_x_unit(const float *__restrict__ x, uint32_t M, uint32_t K, bool vec, uint32_t kb, uint32_t u, uint32_t tok, uint32_t t) {
+__device__ __forceinline__ uint4 gemv_x_unit(const float *__restrict__ x, uint32_t M, uint32_t K, bool vec, uint32_t kb, uint32_t u, uint32_t tok, uint32_t t,
+                                             float &s_all, float &s_fed) {
     float v[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -331,9 +361,48 @@ __device__ __forceinline__ uint4 gemv_x_unit(const float *__restrict__ x, uint32
             for (int e = 0; e < 4; ++e) v[4 * h + e] = (tok < M && k + e < K) ? __ldg(x + (size_t)tok * K + k + e) : 0.f;
         }
     }
-    uint4 o;
-    o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]);
-    return o;
+    uint32_t o[4];
+    float sa = 0.f, sf = 0.f;
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+        const bool sixteenth = CB == 4 && (e2 & 1);
+        const float pre = sixteenth ? 0.0625f : 1.0f;
+        const __half2 h2 = __floats2half2_rn(fminf(fmaxf(v[2 * e2], -65504.f), 65504.f) * pre, fminf(fmaxf(v[2 * e2 + 1], -65504.f), 65504.f) * pre);
+        const float2 f2 = __half22float2(h2);
+        const float pair = f2.x + f2.y;
+        sf += pair;
+        sa += sixteenth ? 16.f * pair : pair;
+        o[e2] = *reinterpret_cast<const uint32_t *>(&h2);
+    }
+    s_all = sa; s_fed = sf;
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// the units of the k-blocks [kb0, kb0 + n_kb) into `dst` (tile of k-block kb0 first), all threads of whole warps:
+// 8 consecutive lanes hold the 8 units (u, t) of one (k-block, token), so its sums are three shuffles away
+template <int CB, int MT>
+__device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t kb0, uint32_t n_kb,
+                                                uint8_t *dst, uint32_t tid, uint32_t nthreads) {
+    const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const uint32_t total = n_kb * MT * 8;
+    for (uint32_t base = tid & ~31u; base < total; base += nthreads) {
+        const uint32_t idx = base + (tid & 31);
+        const bool valid = idx < total;                                   // total % 8 == 0: a group of 8 lanes is all valid or all not
+        const uint32_t t = idx & 3, u = (idx >> 2) & 1, tok = (idx >> 3) % MT, kb = (idx >> 3) / MT;
+        float sa = 0.f, sf = 0.f;
+        uint4 unit = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) unit = gemv_x_unit<CB>(x, M, K, vec, kb0 + kb, u, tok, t, sa, sf);
+#pragma unroll
+        for (int m = 1; m < 8; m <<= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, m);
+            sf += __shfl_xor_sync(0xffffffffu, sf, m);
+        }
+        if (valid) {
+            uint8_t *tile = dst + (size_t)kb * gemv_x_tile_bytes(MT);
+            *reinterpret_cast<uint4 *>(tile + ((u * MT + tok) * 4 + t) * 16) = unit;
+            if ((idx & 7) == 0) *reinterpret_cast<uint4 *>(tile + MT * 128 + tok * 16) = x_corr_entry(sa, sf);
+        }
+    }
 }
 
 // y tile = sum of the partial tiles of all contributors (fixed order) + bias; `nthreads` threads, this one is `tid`
@@ -360,12 +429,7 @@ __device__ __forceinline__ void reduce_tile(const GemvArgs &a, uint32_t cnt, con
 // already streaming weights meanwhile), then meet at kBarXReady
 template <int CB, int MT>
 __device__ __forceinline__ void prepare_x_slice(const GemvArgs &a, const Range &rg, uint8_t *xs, int tid, int nthreads) {
-    const bool vec = (a.K & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
-    const uint32_t total = rg.u0 < rg.u1 ? rg.kbs * 2 * MT * 4 : 0;
-    for (uint32_t idx = tid; idx < total; idx += nthreads) {
-        const uint32_t t = idx & 3, tok = (idx >> 2) % MT, u = ((idx >> 2) / MT) & 1, kb = (idx >> 2) / (MT * 2);
-        reinterpret_cast<uint4 *>(xs)[idx] = gemv_x_unit<CB>(a.x, a.M, a.K, vec, rg.kb_s0 + kb, u, tok, t);
-    }
+    if (rg.u0 < rg.u1) prepare_x_tiles<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.kbs, xs, (uint32_t)tid, (uint32_t)nthreads);
     named_bar_sync(kBarXReady, nthreads);
 }
 
@@ -376,7 +440,7 @@ __global__ void __launch_bounds__((NG * kGroupWarps + NP + 1) * 32, 1)
 gemv_mma_kernel(const GemvArgs a) {
     constexpr int NB = MT > 8 ? 2 : 1;
     constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
-    constexpr int kXTile = MT * 128;             // activations of one k-block
+    constexpr int kXTile = gemv_x_tile_bytes(MT);   // activations of one k-block
     // a stage: KBS code tiles, KBS x 128 {scale, zero-point} pairs, and (unless XR) KBS activation tiles
     constexpr int kStage = KBS * (kWBytes + 1024 + (XR ? 0 : kXTile));
     constexpr int kConsumers = NG * kGroupWarps * 32;
@@ -486,7 +550,11 @@ gemv_mma_kernel(const GemvArgs a) {
         uint32_t xs_lane = (XR ? smem_u32(xs) : KBS * (kWBytes + 1024) - (r0 * 4 + t) * 4) + (g < MT ? g : MT - 1) * 64 + 16 * t;   // !XR: relative to cwa
         uint32_t fa = smem_u32(full) + grp * 8;                               // its full barrier; empty = + 8 stages
         const uint32_t ring_bytes = a.stages * kStage, bar_bytes = a.stages * 8;
-        asm volatile("" : "+r"(cwa), "+r"(dpw), "+r"(xs_lane), "+r"(fa));
+        // correction entry of the lane's token, relative to its activation unit; A-operand pattern of the correction MMA
+        uint32_t dxc = MT * 128 - (g < MT ? g : MT - 1) * 48 - 12 * t;
+        uint32_t zmask = t == 0 ? 0xffffffffu : 0u;
+        uint32_t cfill = t == 1 ? 0x78007800u : t == 2 ? 0x24005000u : 0u;                    // half2(32768, 32768), half2(32, 2^-6)
+        asm volatile("" : "+r"(cwa), "+r"(dpw), "+r"(xs_lane), "+r"(fa), "+r"(dxc), "+r"(zmask), "+r"(cfill));
         if (ctid == 0) GTRACE(1);
         // activations, partial-tile workspace, tickets and y belong to the stream's previous kernels until they are done
         pdl_wait();
@@ -507,9 +575,9 @@ gemv_mma_kernel(const GemvArgs a) {
                 if (ctid == 0 && my_it == 0) GTRACE(3);
                 if (w == 0 && lane == 0) STRACE(2, my_it);
                 const uint32_t xk = XR ? xa : c + xs_lane;
-                consume_kblock<CB, MT>(c, c + dpw, xk, ya);
+                consume_kblock<CB, MT>(c, c + dpw, xk, xk + dxc, zmask, cfill, ya);
                 if (KBS == 2 && !(my_it + 1 == it1 && (len & 1)))               // the item's last stage may hold one k-block
-                    consume_kblock<CB, MT>(c + kWBytes, c + dpw + 1024, xk + kXTile, ya);
+                    consume_kblock<CB, MT>(c + kWBytes, c + dpw + 1024, xk + kXTile, xk + kXTile + dxc, zmask, cfill, ya);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_addr(fa + bar_bytes);
                 if (w == 0 && lane == 0) STRACE(3, my_it);
@@ -606,16 +674,11 @@ gemv_mma_kernel(const GemvArgs a) {
     }
 }
 
-// x[M,K] f32 -> fp16 in the order the consumer lanes read it: [k-block][round u][token][t][e]
-template <int CB>
+// x[M,K] f32 -> the prepared activation tiles of all k-blocks (activations too large to stay resident)
+template <int CB, int MT>
 __global__ void __launch_bounds__(256)
-gemv_xprep_kernel(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t k_blocks, uint32_t MT, uint4 *__restrict__ xb) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte unit per thread
-    const uint32_t total = k_blocks * 2 * MT * 4;
-    if (idx >= total) return;
-    const uint32_t t = idx & 3, tok = (idx >> 2) % MT, u = ((idx >> 2) / MT) & 1, kb = (idx >> 2) / (MT * 2);
-    const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    xb[idx] = gemv_x_unit<CB>(x, M, K, vec, kb, u, tok, t);
+gemv_xprep_kernel(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t k_blocks, uint8_t *__restrict__ xb) {
+    prepare_x_tiles<CB, MT>(x, M, K, 0, k_blocks, xb, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 template <int CB, int MT, bool XR>
@@ -625,7 +688,7 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     constexpr int NG = 3, NP = 3, KBS = 2;
     static_assert(NG % NP == 0 || NP % NG == 0, "ring depth is a multiple of max(NG, NP) only");
     constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
-    constexpr int kXTile = MT * 128;
+    constexpr int kXTile = gemv_x_tile_bytes(MT);
     constexpr int kStage = KBS * (kWBytes + 1024 + (XR ? 0 : kXTile));
     const uint32_t k_blocks = (uint32_t)qw->k_blocks, n_tiles = (uint32_t)qw->n_tiles;
     const uint32_t sms = (uint32_t)ctx->sm_count;
@@ -697,12 +760,12 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
         CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_mma_kernel<CB, MT, NG, NP, KBS, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // the activation-prep kernel runs right before: same shared-memory carve-out, so the SMs are not
         // re-partitioned (L1 vs shared) between the two launches
-        CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_xprep_kernel<CB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_xprep_kernel<CB, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     if (!XR) {
         const uint32_t units16 = k_blocks * 2 * MT * 4;
-        gemv_xprep_kernel<CB><<<(units16 + 255) / 256, 256, 0, ctx->stream>>>(x, (uint32_t)M, (uint32_t)qw->K, k_blocks, MT, (uint4 *)ctx->act[2].p);
+        gemv_xprep_kernel<CB, MT><<<(units16 + 255) / 256, 256, 0, ctx->stream>>>(x, (uint32_t)M, (uint32_t)qw->K, k_blocks, (uint8_t *)ctx->act[2].p);
         LAUNCH_CHECK(ctx);
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -778,7 +841,7 @@ constexpr size_t kXResident = 64 * 1024;
 
 template <int CB, int MT>
 int32_t launch_gemv_x(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
-    if (qw->k_blocks * (size_t)(MT * 128) <= kXResident) return launch_gemv_mma<CB, MT, true>(ctx, qw, x, M, y);
+    if (qw->k_blocks * (size_t)gemv_x_tile_bytes(MT) <= kXResident) return launch_gemv_mma<CB, MT, true>(ctx, qw, x, M, y);
     return launch_gemv_mma<CB, MT, false>(ctx, qw, x, M, y);
 }
 
