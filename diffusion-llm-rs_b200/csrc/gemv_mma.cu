@@ -38,6 +38,10 @@
 #include "kernels.h"
 #include "wlayout.cuh"
 
+#ifndef DLLM_GEMV_EXP
+#define DLLM_GEMV_EXP 0
+#endif
+
 namespace {
 
 constexpr int kGroupWarps = 8;                 // 8 warps x 16 output columns = one 128-column tile
@@ -234,6 +238,14 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
     float d[NB][4];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) d[nb][0] = d[nb][1] = d[nb][2] = d[nb][3] = 0.f;
+#if DLLM_GEMV_EXP == 2      // timing experiment: two independent accumulation chains
+    float d2[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) d2[nb][0] = d2[nb][1] = d2[nb][2] = d2[nb][3] = 0.f;
+#define DLLM_EXP_ACC(u, nb) ((u) ? d2[nb] : d[nb])
+#else
+#define DLLM_EXP_ACC(u, nb) d[nb]
+#endif
 
     // activations of both rounds first: independent of everything else
     uint4 b[2][NB];
@@ -259,12 +271,19 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t v0 = h ? q[u][0] >> 8 : q[u][0], v1 = h ? q[u][1] >> 8 : q[u][1];
+#if DLLM_GEMV_EXP == 4      // timing experiment: no unpack
+                const uint32_t a0 = v0, a1 = v1, a2 = v0 + 1, a3 = v1 + 1;
+#else
                 const uint32_t a0 = and_or(v0, 0x000f000fu, kMagic);
                 const uint32_t a1 = and_or(v1, 0x000f000fu, kMagic);
                 const uint32_t a2 = and_or(v0, 0x00f000f0u, kMagic);
                 const uint32_t a3 = and_or(v1, 0x00f000f0u, kMagic);
+#endif
+#if DLLM_GEMV_EXP == 3      // timing experiment: half of the data MMAs (operands still computed)
+                if (h) { asm volatile("" :: "r"(a0), "r"(a1), "r"(a2), "r"(a3)); continue; }
+#endif
 #pragma unroll
-                for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
+                for (int nb = 0; nb < NB; ++nb) mma_f16(DLLM_EXP_ACC(u, nb), a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
             }
         }
     } else if (CB == 2) {
@@ -305,11 +324,17 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
     // the correction MMA: k slots (0,1) = (64 zp, zp / 32) x the fp16 parts of -S/64, slots 2..5 = (32768, 32768, 32, 2^-6) x
     // the parts of -T/64 (x_corr_entry), the other slots zero: d -= zp S + 1024 T, i.e. d = sum x (q - zp)
     // (quantization.rs:83's `- zp`)
+#if DLLM_GEMV_EXP != 1   // (1: timing experiment without the correction MMA — wrong results)
     {
         const uint32_t ca0 = and_or(p0.y, zmask, cfill), ca1 = and_or(p1.y, zmask, cfill);
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], ca0, ca1, 0u, 0u, bc[nb], 0u);
     }
+#endif
+#if DLLM_GEMV_EXP == 2
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) { d[nb][0] += d2[nb][0]; d[nb][1] += d2[nb][1]; d[nb][2] += d2[nb][2]; d[nb][3] += d2[nb][3]; }
+#endif
     // dequantize_tensor's `* scale` (quantization.rs:83), applied to the k-block's partial sum in f32
     const float s0 = __uint_as_float(p0.x), s1 = __uint_as_float(p1.x);
 #pragma unroll
@@ -344,12 +369,9 @@ __device__ __forceinline__ uint4 x_corr_entry(float s_all, float s_fed) {
 
 // One 16-byte unit of the prepared activations: the 8 fp16 values of token `tok` that lane quad-index t consumes in
 // round u of k-block kb (gemv_kmap).  They are two runs of 4 consecutive k; `vec` = K % 4 == 0 and x is 16-byte aligned.
-// CB == 4: elements 2, 3, 6, 7 meet weights unpacked as 1024 + 16 q and are stored as x / 16 (exact but for fp16
-// subnormals).  s_all / s_fed accumulate the unit's share of x_corr_entry's sums, from the ROUNDED operands.
+// The load and the conversion are separate so that a thread can have the loads of several units in flight.
 template <int CB>
-__device__ __forceinline__ uint4 gemv_x_unit(const float *__restrict__ x, uint32_t M, uint32_t K, bool vec, uint32_t kb, uint32_t u, uint32_t tok, uint32_t t,
-                                             float &s_all, float &s_fed) {
-    float v[8];
+__device__ __forceinline__ void gemv_x_load(const float *__restrict__ x, uint32_t M, uint32_t K, bool vec, uint32_t kb, uint32_t u, uint32_t tok, uint32_t t, float *v) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const uint32_t k = kb * WL_TILE_K + (uint32_t)gemv_kmap<CB>((int)u, (int)t, 4 * h);
@@ -361,6 +383,11 @@ __device__ __forceinline__ uint4 gemv_x_unit(const float *__restrict__ x, uint32
             for (int e = 0; e < 4; ++e) v[4 * h + e] = (tok < M && k + e < K) ? __ldg(x + (size_t)tok * K + k + e) : 0.f;
         }
     }
+}
+// CB == 4: elements 2, 3, 6, 7 meet weights unpacked as 1024 + 16 q and are stored as x / 16 (exact but for fp16
+// subnormals).  s_all / s_fed are the unit's share of x_corr_entry's sums, from the ROUNDED operands.
+template <int CB>
+__device__ __forceinline__ uint4 gemv_x_convert(const float *v, float &s_all, float &s_fed) {
     uint32_t o[4];
     float sa = 0.f, sf = 0.f;
 #pragma unroll
@@ -379,28 +406,42 @@ __device__ __forceinline__ uint4 gemv_x_unit(const float *__restrict__ x, uint32
 }
 
 // the units of the k-blocks [kb0, kb0 + n_kb) into `dst` (tile of k-block kb0 first), all threads of whole warps:
-// 8 consecutive lanes hold the 8 units (u, t) of one (k-block, token), so its sums are three shuffles away
-template <int CB, int MT>
+// 8 consecutive lanes hold the 8 units (u, t) of one (k-block, token), so its sums are three shuffles away.
+// UNR units per thread and pass, all loads issued before the first conversion: the pass costs one L2 round trip.
+template <int CB, int MT, int UNR>
 __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t kb0, uint32_t n_kb,
                                                 uint8_t *dst, uint32_t tid, uint32_t nthreads) {
     const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     const uint32_t total = n_kb * MT * 8;
-    for (uint32_t base = tid & ~31u; base < total; base += nthreads) {
-        const uint32_t idx = base + (tid & 31);
-        const bool valid = idx < total;                                   // total % 8 == 0: a group of 8 lanes is all valid or all not
-        const uint32_t t = idx & 3, u = (idx >> 2) & 1, tok = (idx >> 3) % MT, kb = (idx >> 3) / MT;
-        float sa = 0.f, sf = 0.f;
-        uint4 unit = make_uint4(0u, 0u, 0u, 0u);
-        if (valid) unit = gemv_x_unit<CB>(x, M, K, vec, kb0 + kb, u, tok, t, sa, sf);
+    for (uint32_t base = tid & ~31u; base < total; base += UNR * nthreads) {
+        float v[UNR][8];
 #pragma unroll
-        for (int m = 1; m < 8; m <<= 1) {
-            sa += __shfl_xor_sync(0xffffffffu, sa, m);
-            sf += __shfl_xor_sync(0xffffffffu, sf, m);
+        for (int j = 0; j < UNR; ++j) {
+            const uint32_t idx = base + j * nthreads + (tid & 31);
+            if (idx < total) {
+                gemv_x_load<CB>(x, M, K, vec, kb0 + (idx >> 3) / MT, (idx >> 2) & 1, (idx >> 3) % MT, idx & 3, v[j]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+            }
         }
-        if (valid) {
-            uint8_t *tile = dst + (size_t)kb * gemv_x_tile_bytes(MT);
-            *reinterpret_cast<uint4 *>(tile + ((u * MT + tok) * 4 + t) * 16) = unit;
-            if ((idx & 7) == 0) *reinterpret_cast<uint4 *>(tile + MT * 128 + tok * 16) = x_corr_entry(sa, sf);
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const uint32_t idx = base + j * nthreads + (tid & 31);
+            const bool valid = idx < total;                               // total % 8 == 0: a group of 8 lanes is all valid or all not
+            const uint32_t t = idx & 3, u = (idx >> 2) & 1, tok = (idx >> 3) % MT, kb = (idx >> 3) / MT;
+            float sa, sf;
+            const uint4 unit = gemv_x_convert<CB>(v[j], sa, sf);
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, m);
+                sf += __shfl_xor_sync(0xffffffffu, sf, m);
+            }
+            if (valid) {
+                uint8_t *tile = dst + (size_t)kb * gemv_x_tile_bytes(MT);
+                *reinterpret_cast<uint4 *>(tile + ((u * MT + tok) * 4 + t) * 16) = unit;
+                if ((idx & 7) == 0) *reinterpret_cast<uint4 *>(tile + MT * 128 + tok * 16) = x_corr_entry(sa, sf);
+            }
         }
     }
 }
@@ -429,7 +470,7 @@ __device__ __forceinline__ void reduce_tile(const GemvArgs &a, uint32_t cnt, con
 // already streaming weights meanwhile), then meet at kBarXReady
 template <int CB, int MT>
 __device__ __forceinline__ void prepare_x_slice(const GemvArgs &a, const Range &rg, uint8_t *xs, int tid, int nthreads) {
-    if (rg.u0 < rg.u1) prepare_x_tiles<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.kbs, xs, (uint32_t)tid, (uint32_t)nthreads);
+    if (rg.u0 < rg.u1) prepare_x_tiles<CB, MT, 3>(a.x, a.M, a.K, rg.kb_s0, rg.kbs, xs, (uint32_t)tid, (uint32_t)nthreads);
     named_bar_sync(kBarXReady, nthreads);
 }
 
@@ -557,16 +598,18 @@ gemv_mma_kernel(const GemvArgs a) {
         asm volatile("" : "+r"(cwa), "+r"(dpw), "+r"(xs_lane), "+r"(fa), "+r"(dxc), "+r"(zmask), "+r"(cfill));
         if (ctid == 0) GTRACE(1);
         // activations, partial-tile workspace, tickets and y belong to the stream's previous kernels until they are done
-        pdl_wait();
-        if (XR) prepare_x_slice<CB, MT>(a, rg, xs, ctid, kConsumers + 32);
-        if (ctid == 0) GTRACE(2);
+        // (the iterator's 64-bit divisions are done before the wait: nothing of it depends on the previous kernel)
         uint32_t n_item = 0, last_nt = 0;
         bool last_whole = true;
         ItemIter iter(rg);
         Item item;
+        bool have_item = iter.next(item);
+        pdl_wait();
+        if (XR) prepare_x_slice<CB, MT>(a, rg, xs, ctid, kConsumers + 32);
+        if (ctid == 0) GTRACE(2);
         // stage counter `it` of the CTA; this group owns the stages with it % NG == grp and walks only those
         uint32_t it0 = 0, my_it = (uint32_t)grp, my_s = (uint32_t)grp, my_ph = 0;
-        while (iter.next(item)) {
+        for (; have_item; have_item = iter.next(item)) {
             const uint32_t len = item.kb1 - item.kb0;
             const uint32_t it1 = it0 + (len + KBS - 1) / KBS;
             uint32_t xa = XR ? xs_lane + (item.kb0 - rg.kb_s0 + (my_it - it0) * KBS) * kXTile : 0u;
@@ -678,7 +721,7 @@ gemv_mma_kernel(const GemvArgs a) {
 template <int CB, int MT>
 __global__ void __launch_bounds__(256)
 gemv_xprep_kernel(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t k_blocks, uint8_t *__restrict__ xb) {
-    prepare_x_tiles<CB, MT>(x, M, K, 0, k_blocks, xb, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    prepare_x_tiles<CB, MT, 1>(x, M, K, 0, k_blocks, xb, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 template <int CB, int MT, bool XR>

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libdllm_b200.so")
+# DLLM_B200_LIB: another build of the same library (timing experiments: scripts/build_variants.sh)
+LIB_PATH = os.environ.get("DLLM_B200_LIB") or os.path.join(_PKG, "lib", "libdllm_b200.so")
 
 OK = 0
 ERR_INVALID_PARAMS, ERR_UNSUPPORTED, ERR_SHAPE, ERR_CALIBRATION_REQUIRED = 1, 2, 3, 4
