@@ -11,28 +11,28 @@
 //   * a producer warp keeps a deep shared-memory ring (up to 32 stages, > 100 KB in flight per SM) full
 //     with `cp.async.bulk` copies — one 2/4/8 KB packed tile (wlayout.cuh: contiguous in HBM) plus the
 //     tile's 128 scales and zero-points per stage, completion on an mbarrier;
-//   * the CTA's slice of the activations is staged ONCE into shared memory (bf16, fragment order) and
-//     stays resident: no activation traffic in the steady state;
+//   * the CTA's slice of the activations is staged ONCE into shared memory (signed-digit int8 columns in MMA fragment
+//     order, prepared inside the kernel by the consumer warps while the producers already stream weights) and stays
+//     resident: no activation traffic in the steady state;
 //   * NG groups of 8 consumer warps take the stages round-robin.  A warp owns 16 output columns of the
-//     128-column tile: it reads its codes with conflict-free LDS.32 and turns them into fp16 operands in
-//     registers with ONE LOP3 per pair — 0x6400 | q is the half 1024 + q, 0x6400 | (q << 4) is 1024 + 16 q (those
-//     k positions meet activations prepared as x / 16) — so a 32-bit word of eight 4-bit codes costs one shift
-//     and four LOP3, and feeds them to mma.sync.m16n8k16 (f16 operands, f32 accumulate) with the activations as
-//     the B operand.  Neither the magic 1024 nor the zero-point is subtracted per weight: per (k-block, token)
-//     the x preparation also stores T = sum of the fp16 operands and S = sum of x, split into fp16 parts, and ONE
-//     more MMA per k-block with A = {64 zp, 32768, ...} and B = {-S/64, -T/64, ...} removes 1024 T + zp S from the
-//     accumulator (sum x (1024 + q) - 1024 sum x - zp sum x = sum x (q - zp)).  The group's scale is applied in f32
-//     to the k-block's partial sum.  Tensor cores are used only so that the FMA work costs one instruction per 256
-//     weights: what bounds the kernel after the copy engine is the CUDA-core instructions of the unpack;
+//     128-column tile: it reads its codes with conflict-free LDS.32, spreads the nibbles to bytes (two ANDs and a shift
+//     per eight 4-bit codes; 8-bit codes are used as they are) and feeds them as the unsigned A operand of
+//     mma.sync.m16n8k32 (u8 x s8 -> s32) with the activations' digit columns as B — two MMAs per 64-k block, exact
+//     integer sums; zero-point, scale and the activation block's power-of-two step are applied to the k-block's partial
+//     sum in f32 (see "the int8 tensor path" below).  The legacy tensor path costs 8 cycles of a sub-core's pipe per
+//     instruction whatever the type, so the f16 m16n8k16 this replaces (5 per k-block with the zero-point correction)
+//     was what bounded the 4-bit kernel (measured with instruction-removal builds, scripts/build_variants.sh);
 //   * tiles cut by a range boundary are reduced by the LAST CTA to arrive at the tile (atomic ticket,
 //     no spinning), always in CTA order: results are deterministic and there is no fix-up launch.
 //
-// Numerics: codes and zero-points exact, x rounded to fp16 (saturated at +-65504), f32 accumulate, f32 scale; the
-// 1024-offset cancels inside the f32 accumulator of one k-block (|1024 sum_64 x| * 2^-24 per MMA: two orders of
-// magnitude below the fp16 rounding of x).  Zero-points must be the integers quantizer B produces (quantization.rs:55-56).
+// Numerics: codes, zero-points and all integer sums exact; x is rounded to 23-bit (1-2 tokens) or 15-bit (4-16 tokens)
+// block fixed point per 64 activations — |error| <= 2^-22 resp. 2^-14 of the block's max |x| per element — f32
+// scale and f32 accumulation across k-blocks.  Zero-points must be the integers quantizer B produces (quantization.rs:55-56).
 // Timeline instrumentation (globaltimer stamps per CTA / per stage) compiles in with -DDLLM_GEMV_TRACE.
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <stdio.h>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -49,6 +49,7 @@ constexpr int kRedStride = 132;                // padded row of the cross-group 
 constexpr int kSmemBudget = 220 * 1024;      // of the 227 KB a CTA may use
 constexpr int kXBudget = 112 * 1024;           // resident activation slice per CTA
 constexpr int kMaxStages = 32;
+constexpr int kPreTiles = 2;                   // partial tiles of other CTAs a CTA may prefetch for its final tile
 constexpr int kMaxContrib = 160;              // a CTA contributes at most once to a tile, so grid <= kMaxContrib suffices
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,29 +142,53 @@ __device__ __forceinline__ bool elect_one() {
 constexpr int kBarConsumers = 1, kBarPartial = 2, kBarFinal = 3, kBarEpiFree = 4, kBarXReady = 5;
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
-// D(16 columns x 8 tokens, f32) += A(16 columns x 16 k, f16) · B(16 k x 8 tokens, f16)
-__device__ __forceinline__ void mma_f16(float *d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+// D(16 weight columns x 8 activation columns, s32) = A(16 x 32 k, u8) · B(32 k x 8, s8) + C
+__device__ __forceinline__ void mma_u8s8(int *d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1, const int *c) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
 }
-// (a & mask) | magic in ONE LOP3 (with two immediates the compiler emits two)
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t magic) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
-    return d;
-}
-// k (inside a 64-k block) of element e (0..7) of the 16-byte activation unit that lane quad-index t
-// consumes in round u (0..1); the code words of wlayout.cuh decide it (see consume_stage)
+// ---- the int8 tensor path ---------------------------------------------------------------------------------------
+// mma.sync.m16n8k32 (u8 x s8 -> s32, SASS IMMA.16832) costs the same 8 cycles of a sub-core's tensor pipe as the f16
+// m16n8k16 (measured: scripts/ubench/mma_rate.cu) and covers twice the k.  A = the codes themselves as unsigned bytes (no
+// magic numbers, no zero-point subtraction per weight), B = the activations as signed-digit fixed point: per (k-block,
+// token) x ~ delta * (d0 * 256^(P-1) + ... + d_{P-1}), digits in [-128, 127], delta a power of two chosen from the block's
+// max |x|.  Every digit is its own B COLUMN of the same MMA (the weights are shared), so P digits cost nothing extra while
+// tokens * P <= 8.  The int32 sums are exact; the zero-point leaves as zp * sum(digits) per (k-block, column), the scale and
+// delta * 256^j are applied in f32 to the k-block's partial sum.
+//
+// Activation columns: P = 3 digits (|error| <= 2^-22 max|x| of the 64-element block per element: f32-grade) for 1-2
+// tokens, 2 digits (<= 2^-14 max|x|) for 4..16 tokens; column c = token * P + digit.
+__host__ __device__ constexpr int gemv_parts(int MT) { return MT <= 2 ? 3 : 2; }
+__host__ __device__ constexpr int gemv_cols(int MT) { return MT * gemv_parts(MT); }
+__host__ __device__ constexpr int gemv_nb(int MT) { return (gemv_cols(MT) + 7) / 8; }          // 8-column MMA blocks
+// bytes of one k-block of prepared activations: [columns][4 t] 16-byte units {u0 b0, u0 b1, u1 b0, u1 b1} (the B registers
+// of the k-block's two MMAs for lane quad-index t), then per column block [4 t] entries {factor(2t), factor(2t+1),
+// digit sum(2t), digit sum(2t+1)} (f32) for the accumulator columns lane t holds
+__host__ __device__ constexpr int gemv_x_tile_bytes(int MT) { return gemv_cols(MT) * 64 + gemv_nb(MT) * 64; }
+
+// k (inside a 64-k block) of byte j (0..3) of B register r (0..1) of MMA u (0..1) for lane quad-index t: whatever code
+// the unpack of wlayout.cuh's words puts at that position of the A fragment (see consume_kblock)
 template <int CB>
-__host__ __device__ __forceinline__ int gemv_kmap(int u, int t, int e) {
-    if (CB == 4) return 32 * u + 8 * t + e;
-    if (CB == 2) return 16 * t + 8 * u + e;
-    return 32 * u + 16 * (e >> 2) + 4 * t + (e & 3);
+__host__ __device__ __forceinline__ constexpr int gemv_kmap(int u, int t, int r, int j) {
+    // 4-bit: word t of chunk u = codes 32 u + 8 t + e at nibble (e >> 1) + 4 (e & 1); w & 0x0f0f0f0f = e {0,4,1,5}, (w >> 4) & .. = e {2,6,3,7}
+    if (CB == 4) return 32 * u + 8 * t + (r ? 2 : 0) + (j >> 1) + 4 * (j & 1);
+    // 2-bit: word t = codes 16 t + i at field (i >> 1) + 8 (i & 1); (w >> 2 s) & 0x03030303 = i {2s, 8+2s, 2s+1, 9+2s}, s = 2 u + r
+    if (CB == 2) return 16 * t + 2 * (2 * u + r) + (j >> 1) + 8 * (j & 1);
+    // 8-bit: word t of chunk c = codes 16 c + 4 t + i in byte order; c = 2 u + r
+    return 16 * (2 * u + r) + 4 * t + j;
 }
+
+#ifdef DLLM_GEMV_TRACE
+constexpr int kTraceSlots = 64;
+unsigned long long *g_trace_buf = nullptr;
+size_t g_trace_stride = 0, g_trace_launch = 0;
+uint32_t g_trace_grid = 0;
+#endif
 
 struct GemvArgs {
     const uint8_t *packed;
-    const uint2 *gparams;            // [G][Npad] {f32 scale, half2(64 zp, zp / 32)}
+    const uint2 *gparams;            // [G][Npad] {f32 scale, f32 zp}
     const float *bias;
     const uint8_t *xb;               // !XR: prepared activations [k_blocks] tiles of gemv_x_tile_bytes(MT)
     const float *x;                  // XR: the f32 activations [M, K]; every CTA prepares its own slice in shared memory
@@ -176,7 +201,7 @@ struct GemvArgs {
     uint32_t S, P;                   // k segments, CTAs per segment (grid = S * P)
     uint32_t max_items;              // partial slots per CTA
     uint32_t stages;                 // ring depth (multiple of NG)
-    uint32_t x_off, red_off, bar_off;   // shared-memory carve-up (bytes)
+    uint32_t x_off, red_off, bar_off, pre_off;   // shared-memory carve-up (bytes)
     uint32_t bulk;                   // code tiles by one cp.async.bulk per stage (default) or by per-lane cp.async (DLLM_GEMV_BULK=0)
     unsigned long long *trace;       // -DDLLM_GEMV_TRACE: per CTA [32] globaltimer stamps, then [4][256] stage stamps of CTA 0
 };
@@ -217,230 +242,196 @@ struct ItemIter {
     }
 };
 
-// bytes of one k-block of prepared activations: [2 rounds][MT tokens][4 t] 16-byte units, then one 16-byte
-// correction entry per token (x_corr_entry)
-__host__ __device__ constexpr int gemv_x_tile_bytes(int MT) { return MT * 144; }
-
 // one 64-k block of a 128-column tile, consumed by the 8 warps of one group.
 // Shared-memory addresses, each already offset to this lane's element (lane = 4 g + t, output columns
 // r0 = 16 w + g and r0 + 8):
 //   cw : word t of chunk 0 of column r0 of the packed codes (wlayout.cuh): + 2048 per chunk, + 128 for column r0 + 8
-//   pw : {f32 scale, half2(64 zp, zp / 32)} of column r0: + 64 for column r0 + 8
-//   xw : the lane's 16-byte unit of token min(g, MT - 1) in round 0 of the fp16 activations: + 64 MT per round, + 512 for
-//        token g + 8.  (Lanes with g >= MT feed MMA columns of tokens that do not exist and are never stored; they
-//        re-read the last token instead of zeroing registers.)
-//   xc : word t of that token's correction entry: + 128 for token g + 8
+//   pw : {f32 scale, f32 zp} of column r0: + 64 for column r0 + 8
+//   xw : the lane's 16-byte unit of activation column min(g, columns - 1): + 512 per column block.  (Lanes beyond the
+//        last column feed MMA columns that are never stored; they re-read the last one instead of zeroing registers.)
+//   xf : the lane's factor entry of column block 0: + 64 per column block
+// ya[nb] = the lane's f32 accumulators: columns 8 nb + 2 t, + 1 of weight column r0, then the same of r0 + 8.
 template <int CB, int MT>
-__device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_t xw, uint32_t xc, uint32_t zmask, uint32_t cfill, float (*ya)[4]) {
-    constexpr int NB = MT > 8 ? 2 : 1;           // 8-token MMA column blocks
-    constexpr uint32_t kMagic = 0x64006400u;     // half2(1024, 1024)
+__device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_t xw, uint32_t xf, float (*ya)[4]) {
+    constexpr int NB = gemv_nb(MT);
+    // s32 accumulators start at the bits of the float 1.5 * 2^23: while |sum| < 2^22 the integer sum IS the float
+    // 12582912 + sum, so no I2F (a quarter-rate instruction) is needed.  |sum| <= 64 * 128 * 255 < 2^21.
+    constexpr int kMagicBits = 0x4B400000;
+    constexpr float kMagic = 12582912.f;
+    const int cinit[4] = {kMagicBits, kMagicBits, kMagicBits, kMagicBits};
     const uint2 p0 = lds64(pw), p1 = lds64(pw + 64);
-    float d[NB][4];
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) d[nb][0] = d[nb][1] = d[nb][2] = d[nb][3] = 0.f;
-#if DLLM_GEMV_EXP == 2      // timing experiment: two independent accumulation chains
-    float d2[NB][4];
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) d2[nb][0] = d2[nb][1] = d2[nb][2] = d2[nb][3] = 0.f;
-#define DLLM_EXP_ACC(u, nb) ((u) ? d2[nb] : d[nb])
-#else
-#define DLLM_EXP_ACC(u, nb) d[nb]
-#endif
 
-    // activations of both rounds first: independent of everything else
-    uint4 b[2][NB];
-    uint32_t bc[NB];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-            b[u][nb] = lds128(xw + u * (MT * 64) + nb * 512);
-        }
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) bc[nb] = lds32(xc + nb * 128);
-
+    // A fragments of the k-block's two MMAs: rows r0 / r0 + 8, k positions as gemv_kmap says
+    uint32_t a[2][4];
     if (CB == 4) {
-        // word = codes 0..7 at nibbles {0,4,1,5,2,6,3,7}: (w & 0x000f000f) | magic = 1024 + codes (0,1),
-        // (w & 0x00f000f0) | magic = 1024 + 16 x codes (2,3) (their activations are stored as x / 16), the same of
-        // w >> 8 = codes (4,5), (6,7)
         uint32_t q[2][2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) { q[u][0] = lds32(cw + u * 2048); q[u][1] = lds32(cw + u * 2048 + 128); }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t v0 = h ? q[u][0] >> 8 : q[u][0], v1 = h ? q[u][1] >> 8 : q[u][1];
-#if DLLM_GEMV_EXP == 4      // timing experiment: no unpack
-                const uint32_t a0 = v0, a1 = v1, a2 = v0 + 1, a3 = v1 + 1;
-#else
-                const uint32_t a0 = and_or(v0, 0x000f000fu, kMagic);
-                const uint32_t a1 = and_or(v1, 0x000f000fu, kMagic);
-                const uint32_t a2 = and_or(v0, 0x00f000f0u, kMagic);
-                const uint32_t a3 = and_or(v1, 0x00f000f0u, kMagic);
-#endif
-#if DLLM_GEMV_EXP == 3      // timing experiment: half of the data MMAs (operands still computed)
-                if (h) { asm volatile("" :: "r"(a0), "r"(a1), "r"(a2), "r"(a3)); continue; }
-#endif
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) mma_f16(DLLM_EXP_ACC(u, nb), a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
-            }
+            a[u][0] = q[u][0] & 0x0f0f0f0fu; a[u][1] = q[u][1] & 0x0f0f0f0fu;
+            a[u][2] = (q[u][0] >> 4) & 0x0f0f0f0fu; a[u][3] = (q[u][1] >> 4) & 0x0f0f0f0fu;
         }
     } else if (CB == 2) {
-        // one word = 16 codes, code i at field (i >> 1) + 8 (i & 1): (w >> 2p) & 0x00030003 = codes (2p, 2p + 1)
         const uint32_t q0 = lds32(cw), q1 = lds32(cw + 128);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int p = 4 * u + 2 * h;
-                const uint32_t a0 = and_or(q0 >> (2 * p), 0x00030003u, kMagic);
-                const uint32_t a1 = and_or(q1 >> (2 * p), 0x00030003u, kMagic);
-                const uint32_t a2 = and_or(q0 >> (2 * p + 2), 0x00030003u, kMagic);
-                const uint32_t a3 = and_or(q1 >> (2 * p + 2), 0x00030003u, kMagic);
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
-            }
+            a[u][0] = (q0 >> (4 * u)) & 0x03030303u; a[u][1] = (q1 >> (4 * u)) & 0x03030303u;
+            a[u][2] = (q0 >> (4 * u + 2)) & 0x03030303u; a[u][3] = (q1 >> (4 * u + 2)) & 0x03030303u;
         }
     } else {
-        // 16-k chunks, word t = 4 codes in byte order; PRMT with 0x64 bytes builds half2(1024 + q_i, 1024 + q_j)
-        uint32_t q[4][2];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { q[c][0] = lds32(cw + c * 2048); q[c][1] = lds32(cw + c * 2048 + 128); }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = 2 * u + h;
-                const uint32_t a0 = __byte_perm(q[c][0], kMagic, 0x5150);
-                const uint32_t a1 = __byte_perm(q[c][1], kMagic, 0x5150);
-                const uint32_t a2 = __byte_perm(q[c][0], kMagic, 0x5352);
-                const uint32_t a3 = __byte_perm(q[c][1], kMagic, 0x5352);
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], a0, a1, a2, a3, h ? b[u][nb].z : b[u][nb].x, h ? b[u][nb].w : b[u][nb].y);
-            }
+            a[u][0] = lds32(cw + (2 * u) * 2048); a[u][1] = lds32(cw + (2 * u) * 2048 + 128);
+            a[u][2] = lds32(cw + (2 * u + 1) * 2048); a[u][3] = lds32(cw + (2 * u + 1) * 2048 + 128);
         }
     }
-    // the correction MMA: k slots (0,1) = (64 zp, zp / 32) x the fp16 parts of -S/64, slots 2..5 = (32768, 32768, 32, 2^-6) x
-    // the parts of -T/64 (x_corr_entry), the other slots zero: d -= zp S + 1024 T, i.e. d = sum x (q - zp)
-    // (quantization.rs:83's `- zp`)
-#if DLLM_GEMV_EXP != 1   // (1: timing experiment without the correction MMA — wrong results)
-    {
-        const uint32_t ca0 = and_or(p0.y, zmask, cfill), ca1 = and_or(p1.y, zmask, cfill);
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) mma_f16(d[nb], ca0, ca1, 0u, 0u, bc[nb], 0u);
-    }
-#endif
-#if DLLM_GEMV_EXP == 2
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) { d[nb][0] += d2[nb][0]; d[nb][1] += d2[nb][1]; d[nb][2] += d2[nb][2]; d[nb][3] += d2[nb][3]; }
-#endif
-    // dequantize_tensor's `* scale` (quantization.rs:83), applied to the k-block's partial sum in f32
+    // dequantize_tensor's `(q - zp) * scale` (quantization.rs:83): sum x q - zp sum x, then * scale, per k-block in f32
     const float s0 = __uint_as_float(p0.x), s1 = __uint_as_float(p1.x);
+    const float nz0 = -__uint_as_float(p0.y), nz1 = -__uint_as_float(p1.y);
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
-        ya[nb][0] = fmaf(s0, d[nb][0], ya[nb][0]);
-        ya[nb][1] = fmaf(s0, d[nb][1], ya[nb][1]);
-        ya[nb][2] = fmaf(s1, d[nb][2], ya[nb][2]);
-        ya[nb][3] = fmaf(s1, d[nb][3], ya[nb][3]);
+        const uint4 b = lds128(xw + nb * 512);
+        const uint4 f = lds128(xf + nb * 64);
+        int d[4];
+        mma_u8s8(d, a[0][0], a[0][1], a[0][2], a[0][3], b.x, b.y, cinit);
+        mma_u8s8(d, a[1][0], a[1][1], a[1][2], a[1][3], b.z, b.w, d);
+        const float fac0 = __uint_as_float(f.x), fac1 = __uint_as_float(f.y), sx0 = __uint_as_float(f.z), sx1 = __uint_as_float(f.w);
+        // every intermediate is an integer below 2^24: exact
+        const float e0 = fmaf(nz0, sx0, __int_as_float(d[0])) - kMagic, e1 = fmaf(nz0, sx1, __int_as_float(d[1])) - kMagic;
+        const float e2 = fmaf(nz1, sx0, __int_as_float(d[2])) - kMagic, e3 = fmaf(nz1, sx1, __int_as_float(d[3])) - kMagic;
+        ya[nb][0] = fmaf(s0 * fac0, e0, ya[nb][0]);
+        ya[nb][1] = fmaf(s0 * fac1, e1, ya[nb][1]);
+        ya[nb][2] = fmaf(s1 * fac0, e2, ya[nb][2]);
+        ya[nb][3] = fmaf(s1 * fac1, e3, ya[nb][3]);
     }
 }
 
-// The correction entry of one (k-block, token): the B operand of consume_kblock's correction MMA, word t for lane
-// quad-index t.  s_all = sum of the 64 activations as the weights see them, s_fed = sum of the 64 fp16 operands as the
-// MMAs see them (equal unless CB == 4, where half of them are fed as x / 16).  |s / 64| <= 65504 always.  An f32 is
-// carried as fp16 parts that are rescaled to the magnitude of the leading part (hi, 2^11 (v - hi), 2^22 (v - hi - mid)),
-// so none of them is an fp16 subnormal and power-of-two scalings of x commute with the whole path; the A operand holds
-// the matching factors:   word 0: -S/64 as (hi, mid')   x (64 zp, zp / 32)
-//                         word 1: -T/64 as (hi, hi)     x (32768, 32768)
-//                         word 2: -T/64 as (mid', lo')  x (32, 2^-6)             word 3: zero
-__device__ __forceinline__ uint4 x_corr_entry(float s_all, float s_fed) {
-    const float vs = -s_all * 0.015625f, vt = -s_fed * 0.015625f;
-    const __half shi = __float2half_rn(vs);
-    const __half smid = __float2half_rn((vs - __half2float(shi)) * 2048.f);
-    const __half thi = __float2half_rn(vt);
-    const float r = (vt - __half2float(thi)) * 2048.f;
-    const __half tmid = __float2half_rn(r);
-    const __half tlo = __float2half_rn((r - __half2float(tmid)) * 2048.f);
-    return make_uint4((uint32_t)__half_as_ushort(shi) | ((uint32_t)__half_as_ushort(smid) << 16),
-                      (uint32_t)__half_as_ushort(thi) * 0x10001u,
-                      (uint32_t)__half_as_ushort(tmid) | ((uint32_t)__half_as_ushort(tlo) << 16), 0u);
+// The 16 activations of lane quad-index t in one k-block are 4 runs of 4 consecutive k: k of run q's first element
+template <int CB>
+__host__ __device__ __forceinline__ constexpr int gemv_run_k0(int q, int t) {
+    return CB == 4 ? 32 * (q >> 1) + 8 * t + 4 * (q & 1) : CB == 2 ? 16 * t + 4 * q : 16 * q + 4 * t;
+}
+// position (4 * run + index) in those runs of the activation that byte j of B register r of MMA u needs
+template <int CB>
+__host__ __device__ __forceinline__ constexpr int gemv_run_pos(int u, int r, int j) {
+    const int k = gemv_kmap<CB>(u, 0, r, j);
+    for (int q = 0; q < 4; ++q)
+        if (k >= gemv_run_k0<CB>(q, 0) && k < gemv_run_k0<CB>(q, 0) + 4) return 4 * q + (k - gemv_run_k0<CB>(q, 0));
+    return -1;
 }
 
-// One 16-byte unit of the prepared activations: the 8 fp16 values of token `tok` that lane quad-index t consumes in
-// round u of k-block kb (gemv_kmap).  They are two runs of 4 consecutive k; `vec` = K % 4 == 0 and x is 16-byte aligned.
-// The load and the conversion are separate so that a thread can have the loads of several units in flight.
+// loads of one (k-block, token, t) work item: 16 floats in run order.  `vec` = K % 4 == 0 and x is 16-byte aligned.
+// The load and the conversion are separate so that a thread can have the loads of several items in flight.
 template <int CB>
-__device__ __forceinline__ void gemv_x_load(const float *__restrict__ x, uint32_t M, uint32_t K, bool vec, uint32_t kb, uint32_t u, uint32_t tok, uint32_t t, float *v) {
+__device__ __forceinline__ void gemv_x_load(const float *__restrict__ x, uint32_t M, uint32_t K, bool vec, uint32_t kb, uint32_t tok, uint32_t t, float *v) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint32_t k = kb * WL_TILE_K + (uint32_t)gemv_kmap<CB>((int)u, (int)t, 4 * h);
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t k = kb * WL_TILE_K + (uint32_t)gemv_run_k0<CB>(q, (int)t);
         if (tok < M && vec && k + 3 < K) {
             const float4 f = __ldg(reinterpret_cast<const float4 *>(x + (size_t)tok * K + k));
-            v[4 * h] = f.x; v[4 * h + 1] = f.y; v[4 * h + 2] = f.z; v[4 * h + 3] = f.w;
+            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
         } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[4 * h + e] = (tok < M && k + e < K) ? __ldg(x + (size_t)tok * K + k + e) : 0.f;
+            for (int e = 0; e < 4; ++e) v[4 * q + e] = (tok < M && k + e < K) ? __ldg(x + (size_t)tok * K + k + e) : 0.f;
         }
     }
 }
-// CB == 4: elements 2, 3, 6, 7 meet weights unpacked as 1024 + 16 q and are stored as x / 16 (exact but for fp16
-// subnormals).  s_all / s_fed are the unit's share of x_corr_entry's sums, from the ROUNDED operands.
-template <int CB>
-__device__ __forceinline__ uint4 gemv_x_convert(const float *v, float &s_all, float &s_fed) {
-    uint32_t o[4];
-    float sa = 0.f, sf = 0.f;
-#pragma unroll
-    for (int e2 = 0; e2 < 4; ++e2) {
-        const bool sixteenth = CB == 4 && (e2 & 1);
-        const float pre = sixteenth ? 0.0625f : 1.0f;
-        const __half2 h2 = __floats2half2_rn(fminf(fmaxf(v[2 * e2], -65504.f), 65504.f) * pre, fminf(fmaxf(v[2 * e2 + 1], -65504.f), 65504.f) * pre);
-        const float2 f2 = __half22float2(h2);
-        const float pair = f2.x + f2.y;
-        sf += pair;
-        sa += sixteenth ? 16.f * pair : pair;
-        o[e2] = *reinterpret_cast<const uint32_t *>(&h2);
-    }
-    s_all = sa; s_fed = sf;
-    return make_uint4(o[0], o[1], o[2], o[3]);
-}
 
-// the units of the k-blocks [kb0, kb0 + n_kb) into `dst` (tile of k-block kb0 first), all threads of whole warps:
-// 8 consecutive lanes hold the 8 units (u, t) of one (k-block, token), so its sums are three shuffles away.
-// UNR units per thread and pass, all loads issued before the first conversion: the pass costs one L2 round trip.
+// the work items of the k-blocks [kb0, kb0 + n_kb) into `dst` (tile of k-block kb0 first), all threads of whole warps:
+// 4 consecutive lanes (t = 0..3) hold the 64 activations of one (k-block, token), so its max |x| and digit sums are two
+// shuffles away.  UNR items per thread and pass, all loads issued before the first conversion.
 template <int CB, int MT, int UNR>
 __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t kb0, uint32_t n_kb,
                                                 uint8_t *dst, uint32_t tid, uint32_t nthreads) {
+    constexpr int P = gemv_parts(MT), NC = gemv_cols(MT), NB = gemv_nb(MT);
+    // |x / delta| <= 2^kTop: leaves the top digit within [-64, 64] and lets the float -> int conversion be one FFMA
+    // (x * (1/delta) + 1.5 * 2^23: the sum's low mantissa bits are the rounded integer; F2I is a quarter-rate instruction)
+    constexpr int kTop = P == 3 ? 22 : 14;
+    constexpr int kMagicBits = 0x4B400000;
     const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    const uint32_t total = n_kb * MT * 8;
+    const uint32_t total = n_kb * MT * 4;
     for (uint32_t base = tid & ~31u; base < total; base += UNR * nthreads) {
-        float v[UNR][8];
+        float v[UNR][16];
 #pragma unroll
         for (int j = 0; j < UNR; ++j) {
             const uint32_t idx = base + j * nthreads + (tid & 31);
             if (idx < total) {
-                gemv_x_load<CB>(x, M, K, vec, kb0 + (idx >> 3) / MT, (idx >> 2) & 1, (idx >> 3) % MT, idx & 3, v[j]);
+                gemv_x_load<CB>(x, M, K, vec, kb0 + (idx >> 2) / MT, (idx >> 2) % MT, idx & 3, v[j]);
             } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+                for (int e = 0; e < 16; ++e) v[j][e] = 0.f;
             }
         }
 #pragma unroll
         for (int j = 0; j < UNR; ++j) {
             const uint32_t idx = base + j * nthreads + (tid & 31);
-            const bool valid = idx < total;                               // total % 8 == 0: a group of 8 lanes is all valid or all not
-            const uint32_t t = idx & 3, u = (idx >> 2) & 1, tok = (idx >> 3) % MT, kb = (idx >> 3) / MT;
-            float sa, sf;
-            const uint4 unit = gemv_x_convert<CB>(v[j], sa, sf);
+            const bool valid = idx < total;                               // total % 4 == 0: a quad is all valid or all not
+            const uint32_t t = idx & 3, tok = (idx >> 2) % MT, kb = (idx >> 2) / MT;
+            // block scale: delta = 2^(E - kTop) with max|x| < 2^E
+            float m = 0.f;
 #pragma unroll
-            for (int m = 1; m < 8; m <<= 1) {
-                sa += __shfl_xor_sync(0xffffffffu, sa, m);
-                sf += __shfl_xor_sync(0xffffffffu, sf, m);
+            for (int e = 0; e < 16; ++e) m = fmaxf(m, fabsf(v[j][e]));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            m = fminf(m, 3.0e38f);
+            int E = (int)(__float_as_uint(m) >> 23) - 126;
+            E = E < -100 ? -100 : E;
+            const float inv = __int_as_float((127 + kTop - E) << 23), delta = __int_as_float((127 + E - kTop) << 23);
+            // signed digits (balanced, low to high: d = (int8)(r & 255), r = (r + 128) >> 8), packed straight into the B
+            // registers: word ur = register ur & 1 of MMA ur >> 1.  (Non-finite activations give unspecified finite digits.)
+            uint32_t w[P][4];
+            int sum[P];
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp) sum[pp] = 0;
+#pragma unroll
+            for (int ur = 0; ur < 4; ++ur) {
+                int r0[4], r1[4], r2[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int e = gemv_run_pos<CB>(ur >> 1, ur & 1, jj);
+                    r0[jj] = __float_as_int(fmaf(v[j][e], inv, 12582912.f));          // low byte = digit 0 (the magic's is 0)
+                    r1[jj] = (r0[jj] + (128 - kMagicBits)) >> 8;
+                    r2[jj] = (r1[jj] + 128) >> 8;
+                }
+                // digit `lvl` (0 = lowest) of the four elements -> one word; part 0 is the TOP digit
+#pragma unroll
+                for (int lvl = 0; lvl < P; ++lvl) {
+                    const int *r = lvl == 0 ? r0 : lvl == 1 ? r1 : r2;
+                    const uint32_t lo = __byte_perm((uint32_t)r[0], (uint32_t)r[1], 0x0040), hi = __byte_perm((uint32_t)r[2], (uint32_t)r[3], 0x0040);
+                    const uint32_t word = __byte_perm(lo, hi, 0x5410);
+                    w[P - 1 - lvl][ur] = word;
+                    sum[P - 1 - lvl] = __dp4a((int)word, 0x01010101, sum[P - 1 - lvl]);
+                }
+            }
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp) {
+                sum[pp] += __shfl_xor_sync(0xffffffffu, sum[pp], 1);
+                sum[pp] += __shfl_xor_sync(0xffffffffu, sum[pp], 2);
             }
             if (valid) {
                 uint8_t *tile = dst + (size_t)kb * gemv_x_tile_bytes(MT);
-                *reinterpret_cast<uint4 *>(tile + ((u * MT + tok) * 4 + t) * 16) = unit;
-                if ((idx & 7) == 0) *reinterpret_cast<uint4 *>(tile + MT * 128 + tok * 16) = x_corr_entry(sa, sf);
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp) {
+                    const uint32_t c = tok * P + pp;
+                    *reinterpret_cast<uint4 *>(tile + c * 64 + t * 16) = make_uint4(w[pp][0], w[pp][1], w[pp][2], w[pp][3]);
+                    if (t == 0) {
+                        // entry of column c: block c >> 3, lane quad-index (c & 7) >> 1, slot c & 1
+                        float *ent = reinterpret_cast<float *>(tile + NC * 64 + (c >> 3) * 64 + ((c & 7) >> 1) * 16) + (c & 1);
+                        float fac = delta;
+#pragma unroll
+                        for (int k2 = pp; k2 < P - 1; ++k2) fac *= 256.f;
+                        ent[0] = fac;
+                        ent[2] = (float)sum[pp];
+                    }
+                }
+                if (NC < 8 * NB && t == 0 && tok == MT - 1) {             // columns that do not exist: factor 0
+#pragma unroll
+                    for (int c = NC; c < 8 * NB; ++c) {
+                        float *ent = reinterpret_cast<float *>(tile + NC * 64 + (c >> 3) * 64 + ((c & 7) >> 1) * 16) + (c & 1);
+                        ent[0] = 0.f; ent[2] = 0.f;
+                    }
+                }
             }
         }
     }
@@ -466,11 +457,11 @@ __device__ __forceinline__ void reduce_tile(const GemvArgs &a, uint32_t cnt, con
     }
 }
 
-// XR: consumers + epilogue warp convert the CTA's k-segment of x to fp16 in shared memory (the producers are
+// XR: consumers + epilogue warp convert the CTA's k-segment of x to digit columns in shared memory (the producers are
 // already streaming weights meanwhile), then meet at kBarXReady
 template <int CB, int MT>
 __device__ __forceinline__ void prepare_x_slice(const GemvArgs &a, const Range &rg, uint8_t *xs, int tid, int nthreads) {
-    if (rg.u0 < rg.u1) prepare_x_tiles<CB, MT, 3>(a.x, a.M, a.K, rg.kb_s0, rg.kbs, xs, (uint32_t)tid, (uint32_t)nthreads);
+    if (rg.u0 < rg.u1) prepare_x_tiles<CB, MT, 2>(a.x, a.M, a.K, rg.kb_s0, rg.kbs, xs, (uint32_t)tid, (uint32_t)nthreads);
     named_bar_sync(kBarXReady, nthreads);
 }
 
@@ -479,7 +470,7 @@ __device__ __forceinline__ void prepare_x_slice(const GemvArgs &a, const Range &
 template <int CB, int MT, int NG, int NP, int KBS, bool XR>
 __global__ void __launch_bounds__((NG * kGroupWarps + NP + 1) * 32, 1)
 gemv_mma_kernel(const GemvArgs a) {
-    constexpr int NB = MT > 8 ? 2 : 1;
+    constexpr int NB = gemv_nb(MT), NC = gemv_cols(MT), NPART = gemv_parts(MT);
     constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
     constexpr int kXTile = gemv_x_tile_bytes(MT);   // activations of one k-block
     // a stage: KBS code tiles, KBS x 128 {scale, zero-point} pairs, and (unless XR) KBS activation tiles
@@ -492,8 +483,11 @@ gemv_mma_kernel(const GemvArgs a) {
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.bar_off);
     uint64_t *empty = full + a.stages;
     uint64_t *xfull = empty + a.stages;
-    uint32_t *verdict = reinterpret_cast<uint32_t *>(xfull + 1);     // [0] this CTA arrived last at its final tile  [1] contributors
-    uint32_t *slots = verdict + 2;                                   // partial slots of the contributors of one tile
+    // verdict: [0] this CTA arrived last at its final tile  [1] contributors  [2] the other contributors' partial tiles of the
+    // final tile were prefetched into `pre`  [3] the consumers have reached the final flush  [4] this CTA's place among the contributors
+    uint32_t *verdict = reinterpret_cast<uint32_t *>(xfull + 1);
+    uint32_t *slots = verdict + 8;                                   // partial slots of the contributors of one tile
+    float *pre = reinterpret_cast<float *>(smem + a.pre_off);        // [kPreTiles][MT * 128]
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const Range rg(a, blockIdx.x);
@@ -513,6 +507,7 @@ gemv_mma_kernel(const GemvArgs a) {
         // full: one arrival per lane of the owning producer warp, triggered when that lane's cp.async copies landed
         for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(full + s, 33); mbar_init(empty + s, kGroupWarps); }
         mbar_init(xfull, 1);
+        verdict[2] = 0; verdict[3] = 0;
         fence_barrier_init();
     }
     __syncthreads();
@@ -556,7 +551,9 @@ gemv_mma_kernel(const GemvArgs a) {
                 }
 #pragma unroll
                 for (int sub = 0; sub < KBS; ++sub) {
-                    if ((uint32_t)sub < nk) {
+                    // (a k-block of the same quantization group as the stage's first one shares its parameters: the
+                    //  consumers read the first slot, nothing is fetched twice)
+                    if ((uint32_t)sub < nk && !(sub > 0 && a.group_magic && __umulhi(kb + sub, a.group_magic) == __umulhi(kb, a.group_magic))) {
                         const uint2 *pg = psrc + (size_t)(a.group_magic ? __umulhi(kb + sub, a.group_magic) : kb + sub) * a.Npad;
                         cp_async16(st + KBS * kWBytes + sub * 1024 + lane * 16, pg + lane * 2);
                         cp_async16(st + KBS * kWBytes + sub * 1024 + 512 + lane * 16, pg + 64 + lane * 2);
@@ -588,14 +585,12 @@ gemv_mma_kernel(const GemvArgs a) {
         const uint32_t r0 = 16 * w + g;
         uint32_t cwa = smem_u32(ring) + (r0 * 4 + t) * 4 + grp * kStage;      // codes of this group's next stage
         uint32_t dpw = KBS * kWBytes + r0 * 8 - (r0 * 4 + t) * 4;             // its parameters, relative to cwa
-        uint32_t xs_lane = (XR ? smem_u32(xs) : KBS * (kWBytes + 1024) - (r0 * 4 + t) * 4) + (g < MT ? g : MT - 1) * 64 + 16 * t;   // !XR: relative to cwa
+        const uint32_t col = g < NC ? g : NC - 1;                             // (only 1-2 tokens have fewer than 8 columns)
+        uint32_t xs_lane = (XR ? smem_u32(xs) : KBS * (kWBytes + 1024) - (r0 * 4 + t) * 4) + col * 64 + 16 * t;   // !XR: relative to cwa
         uint32_t fa = smem_u32(full) + grp * 8;                               // its full barrier; empty = + 8 stages
         const uint32_t ring_bytes = a.stages * kStage, bar_bytes = a.stages * 8;
-        // correction entry of the lane's token, relative to its activation unit; A-operand pattern of the correction MMA
-        uint32_t dxc = MT * 128 - (g < MT ? g : MT - 1) * 48 - 12 * t;
-        uint32_t zmask = t == 0 ? 0xffffffffu : 0u;
-        uint32_t cfill = t == 1 ? 0x78007800u : t == 2 ? 0x24005000u : 0u;                    // half2(32768, 32768), half2(32, 2^-6)
-        asm volatile("" : "+r"(cwa), "+r"(dpw), "+r"(xs_lane), "+r"(fa), "+r"(dxc), "+r"(zmask), "+r"(cfill));
+        uint32_t dxf = NC * 64 - col * 64;                                    // the lane's factor entry, relative to its activation unit
+        asm volatile("" : "+r"(cwa), "+r"(dpw), "+r"(xs_lane), "+r"(fa), "+r"(dxf));
         if (ctid == 0) GTRACE(1);
         // activations, partial-tile workspace, tickets and y belong to the stream's previous kernels until they are done
         // (the iterator's 64-bit divisions are done before the wait: nothing of it depends on the previous kernel)
@@ -618,9 +613,12 @@ gemv_mma_kernel(const GemvArgs a) {
                 if (ctid == 0 && my_it == 0) GTRACE(3);
                 if (w == 0 && lane == 0) STRACE(2, my_it);
                 const uint32_t xk = XR ? xa : c + xs_lane;
-                consume_kblock<CB, MT>(c, c + dpw, xk, xk + dxc, zmask, cfill, ya);
-                if (KBS == 2 && !(my_it + 1 == it1 && (len & 1)))               // the item's last stage may hold one k-block
-                    consume_kblock<CB, MT>(c + kWBytes, c + dpw + 1024, xk + kXTile, xk + kXTile + dxc, zmask, cfill, ya);
+                consume_kblock<CB, MT>(c, c + dpw, xk, xk + dxf, ya);
+                if (KBS == 2 && !(my_it + 1 == it1 && (len & 1))) {             // the item's last stage may hold one k-block
+                    const uint32_t kb = item.kb0 + (my_it - it0) * KBS;
+                    const bool same = a.group_magic && __umulhi(kb + 1, a.group_magic) == __umulhi(kb, a.group_magic);
+                    consume_kblock<CB, MT>(c + kWBytes, c + dpw + (same ? 0u : 1024u), xk + kXTile, xk + kXTile + dxf, ya);
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_addr(fa + bar_bytes);
                 if (w == 0 && lane == 0) STRACE(3, my_it);
@@ -630,25 +628,57 @@ gemv_mma_kernel(const GemvArgs a) {
             it0 = it1;
             if (ctid == 0) GTRACE(4 + 2 * n_item);
             // ---------- tile (or tile part) done: sum the consumer groups, store, hand over to the epilogue warp ----------
+            // the digit columns of a token are summed here (fixed order), then the groups through shared memory
             float *mine = red + (size_t)grp * (MT * kRedStride);
+            if (NPART == 2) {
+                // columns 2 t, 2 t + 1 of block nb = the two digits of token 4 nb + t
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-                const int tok = 8 * nb + 2 * t;
-                if (tok < MT) { mine[tok * kRedStride + 16 * w + g] = ya[nb][0]; mine[tok * kRedStride + 16 * w + g + 8] = ya[nb][2]; }
-                if (tok + 1 < MT) { mine[(tok + 1) * kRedStride + 16 * w + g] = ya[nb][1]; mine[(tok + 1) * kRedStride + 16 * w + g + 8] = ya[nb][3]; }
-                ya[nb][0] = ya[nb][1] = ya[nb][2] = ya[nb][3] = 0.f;
+                for (int nb = 0; nb < NB; ++nb) {
+                    const int tok = 4 * nb + t;
+                    mine[tok * kRedStride + 16 * w + g] = ya[nb][0] + ya[nb][1];
+                    mine[tok * kRedStride + 16 * w + g + 8] = ya[nb][2] + ya[nb][3];
+                }
+            } else {
+                // columns 0..2 = token 0, 3..5 = token 1: lane t = 0 holds (0, 1), t = 1 (2, 3), t = 2 (4, 5)
+                const int src = (lane & ~3) + 1;
+                const float m00 = __shfl_sync(0xffffffffu, ya[0][0], src), m01 = __shfl_sync(0xffffffffu, ya[0][1], src);
+                const float m10 = __shfl_sync(0xffffffffu, ya[0][2], src), m11 = __shfl_sync(0xffffffffu, ya[0][3], src);
+                if (t == 0) {
+                    mine[16 * w + g] = (ya[0][0] + ya[0][1]) + m00;
+                    mine[16 * w + g + 8] = (ya[0][2] + ya[0][3]) + m10;
+                } else if (t == 2 && MT > 1) {
+                    mine[kRedStride + 16 * w + g] = m01 + (ya[0][0] + ya[0][1]);
+                    mine[kRedStride + 16 * w + g + 8] = m11 + (ya[0][2] + ya[0][3]);
+                }
             }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) ya[nb][0] = ya[nb][1] = ya[nb][2] = ya[nb][3] = 0.f;
             named_bar_sync(kBarConsumers, kConsumers);
             const bool whole = a.S == 1 && item.kb0 == rg.kb_s0 && item.kb1 == rg.kb_s0 + rg.kbs;
+            // The CTA's final tile part: the other contributors have usually published theirs long ago (they were at the
+            // start of their ranges), and the epilogue warp has then already copied their partial tiles into shared memory:
+            // the tile is finished right here, in the same fixed order, without a round trip through global memory.
+            const bool final_part = !whole && iter.u >= iter.u1;
+            bool prefetched = false;
+            if (final_part) {
+                if (ctid == 0) *reinterpret_cast<volatile uint32_t *>(verdict + 3) = 1;
+                named_bar_sync(kBarEpiFree, kConsumers + 32);            // the epilogue warp's prefetch attempt is over
+                prefetched = *reinterpret_cast<volatile uint32_t *>(verdict + 2) != 0;
+            }
             float *dst = whole ? nullptr : a.partial + ((size_t)blockIdx.x * a.max_items + item.ordinal) * (MT * 128);
             for (int e = ctid; e < MT * 128; e += kConsumers) {
                 const int tok = e >> 7, nl = e & 127;
                 float v = 0.f;
 #pragma unroll
                 for (int q = 0; q < NG; ++q) v += red[(size_t)q * (MT * kRedStride) + tok * kRedStride + nl];
+                const uint32_t n = item.nt * 128 + nl;
                 if (whole) {
-                    const uint32_t n = item.nt * 128 + nl;
                     if ((uint32_t)tok < a.M && n < a.N) a.y[(size_t)tok * a.N + n] = v + (a.bias ? __ldg(a.bias + n) : 0.f);
+                } else if (prefetched) {
+                    const uint32_t cnt = verdict[1], me = verdict[4];
+                    float acc = 0.f;                                    // the same order as reduce_tile: bit-identical results
+                    for (uint32_t c = 0; c < cnt; ++c) acc += c == me ? v : pre[(c < me ? c : c - 1) * (MT * 128) + e];
+                    if ((uint32_t)tok < a.M && n < a.N) a.y[(size_t)tok * a.N + n] = acc + (a.bias ? __ldg(a.bias + n) : 0.f);
                 } else {
                     dst[e] = v;
                 }
@@ -656,20 +686,24 @@ gemv_mma_kernel(const GemvArgs a) {
             named_bar_sync(kBarConsumers, kConsumers);                  // `red` may be overwritten by the next tile
             // the partial tile is in global memory: the epilogue warp publishes it (fence + ticket) and, if this CTA
             // was the last contributor, reduces the tile — while the consumers are already on the next tile
-            if (!whole) {
-                named_bar_sync(kBarEpiFree, kConsumers + 32);
+            if (prefetched) {
+                if (ctid == 0) a.tickets[item.nt] = 0;                  // the others' arrivals: re-arm for the next launch
+            } else if (!whole) {
+                if (!final_part) named_bar_sync(kBarEpiFree, kConsumers + 32);
                 named_bar_arrive(kBarPartial, kConsumers + 32);
             }
             if (ctid == 0) GTRACE(5 + 2 * n_item);
             ++n_item;
-            last_whole = whole;
+            last_whole = whole || prefetched;
             last_nt = item.nt;
         }
         if (n_item != 0 && !last_whole) {
             // the CTA's last tile: wait for the verdict; if this CTA arrived last, all consumer threads reduce it
             named_bar_sync(kBarFinal, kConsumers + 32);
+            if (ctid == 0) GTRACE(30);
             if (verdict[0]) reduce_tile<MT>(a, verdict[1], slots, last_nt, ctid, kConsumers);
         }
+        if (ctid == 0) GTRACE(31);
     } else {
         // ===================== epilogue warp =====================
         pdl_wait();
@@ -682,12 +716,11 @@ gemv_mma_kernel(const GemvArgs a) {
             more = iter.next(item);
             const bool whole = a.S == 1 && cur.kb0 == rg.kb_s0 && cur.kb1 == rg.kb_s0 + rg.kbs;
             if (whole) continue;
-            named_bar_arrive(kBarEpiFree, kConsumers + 32);
-            named_bar_sync(kBarPartial, kConsumers + 32);
-            uint32_t cnt = 0, last = 0;
+            if (more) named_bar_arrive(kBarEpiFree, kConsumers + 32);
+            uint32_t cnt = 0, last = 0, me = 0;
             if (lane == 0) {
-                __threadfence();                       // cumulative: publishes the consumers' stores ordered before the barrier
-                // contributors of this tile, in the fixed order (segment, CTA): their partial slots
+                // contributors of this tile, in the fixed order (segment, CTA): their partial slots.  (Computed while the
+                // consumers are still working on the tile: the 64-bit divisions are off the critical path.)
                 for (uint32_t sg = 0; sg < a.S; ++sg) {
                     const uint32_t k0 = (uint32_t)((uint64_t)a.k_blocks * sg / a.S);
                     const uint32_t kn = (uint32_t)((uint64_t)a.k_blocks * (sg + 1) / a.S) - k0;
@@ -696,9 +729,47 @@ gemv_mma_kernel(const GemvArgs a) {
                     for (uint32_t j = j_lo; j <= j_hi; ++j) {
                         const uint32_t first_nt = (uint32_t)((U * j / a.P) / kn);
                         if (cnt < kMaxContrib) slots[cnt] = (sg * a.P + j) * a.max_items + (cur.nt - first_nt);
+                        if (sg * a.P + j == blockIdx.x) me = cnt;
                         ++cnt;
                     }
                 }
+            }
+            if (!more) {
+                // the CTA's final tile part: once every other contributor has published (ticket == contributors - 1), copy
+                // their partial tiles into shared memory — while the consumers are still streaming.  Gives up as soon as
+                // the consumers arrive at the flush; they then take the ordinary path below.
+                cnt = __shfl_sync(0xffffffffu, cnt, 0);
+                me = __shfl_sync(0xffffffffu, me, 0);
+                bool ok = false;
+                if (cnt >= 2 && cnt - 1 <= (uint32_t)kPreTiles) {
+                    for (;;) {
+                        uint32_t tk = 0;
+                        if (lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(tk) : "l"(a.tickets + cur.nt) : "memory");
+                        tk = __shfl_sync(0xffffffffu, tk, 0);
+                        if (tk == cnt - 1) {
+                            uint32_t pi = 0;
+                            for (uint32_t c = 0; c < cnt; ++c) {
+                                if (c == me) continue;
+                                const float4 *src = reinterpret_cast<const float4 *>(a.partial + (size_t)slots[c] * (MT * 128));
+                                for (int e4 = lane; e4 < MT * 32; e4 += 32) reinterpret_cast<float4 *>(pre)[pi * (MT * 32) + e4] = __ldcg(src + e4);
+                                ++pi;
+                            }
+                            ok = true;
+                            break;
+                        }
+                        if (*reinterpret_cast<volatile uint32_t *>(verdict + 3)) break;
+                        __nanosleep(200);
+                    }
+                }
+                if (lane == 0) { verdict[1] = cnt; verdict[4] = me; *reinterpret_cast<volatile uint32_t *>(verdict + 2) = ok ? 1u : 0u; }
+                __syncwarp();
+                __threadfence_block();
+                named_bar_arrive(kBarEpiFree, kConsumers + 32);
+                if (ok) break;                                          // the consumers finish the tile
+            }
+            named_bar_sync(kBarPartial, kConsumers + 32);
+            if (lane == 0) {
+                __threadfence();                       // cumulative: publishes the consumers' stores ordered before the barrier
                 const uint32_t old = atomicAdd(a.tickets + cur.nt, 1u);
                 last = old + 1 == cnt ? 1u : 0u;
                 if (last) a.tickets[cur.nt] = 0;       // every contributor has arrived: re-arm for the next launch
@@ -738,12 +809,12 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
 
     // XR: the whole activation block stays resident (one k segment).  The segment machinery (S > 1: a CTA keeps only
     // its k segment's slice) remains for activations that are too large for that but were asked to stay resident.
-    const uint32_t red_bytes = NG * MT * kRedStride * 4;
+    const uint32_t red_bytes = NG * MT * kRedStride * 4, pre_bytes = kPreTiles * MT * 512;
     uint32_t S = 1;
     if (XR) {
         for (;; ++S) {
             const uint64_t xb = (uint64_t)((k_blocks + S - 1) / S) * kXTile;
-            if (S >= k_blocks || (xb <= (uint64_t)kXBudget && xb + red_bytes + 1024 + 8ull * kStage <= (uint64_t)kSmemBudget)) break;
+            if (S >= k_blocks || (xb <= (uint64_t)kXBudget && xb + red_bytes + pre_bytes + 1280 + 8ull * kStage <= (uint64_t)kSmemBudget)) break;
         }
     }
     uint32_t P = sms / S;
@@ -768,16 +839,24 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     a.bulk = bulk_mode;
     a.trace = nullptr;
 #ifdef DLLM_GEMV_TRACE
-    DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, ((size_t)grid * 32 + 1024) * 8));
-    a.trace = (unsigned long long *)ctx->lin_flags.p;
-    cudaMemsetAsync(a.trace, 0, ((size_t)grid * 32 + 1024) * 8, ctx->stream);
+    static const bool trace_chain = getenv("DLLM_GEMV_TRACE_CHAIN") != nullptr;     // one slot per launch, dumped by dllm_debug_gemv_trace_dump
+    const size_t trace_stride = (size_t)grid * 32 + 1024;
+    if (trace_chain) {
+        if (!g_trace_buf) { cudaMalloc(&g_trace_buf, kTraceSlots * trace_stride * 8); cudaMemset(g_trace_buf, 0, kTraceSlots * trace_stride * 8); }
+        g_trace_stride = trace_stride; g_trace_grid = grid;
+        a.trace = g_trace_buf + (size_t)(g_trace_launch++ % kTraceSlots) * trace_stride;
+    } else {
+        DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, trace_stride * 8));
+        a.trace = (unsigned long long *)ctx->lin_flags.p;
+        cudaMemsetAsync(a.trace, 0, trace_stride * 8, ctx->stream);
+    }
 #endif
     const uint32_t kbs_max = (k_blocks + S - 1) / S, kbs_min = k_blocks / S;
     const uint64_t len_max = ((uint64_t)n_tiles * kbs_max + P - 1) / P;
     a.max_items = (uint32_t)(len_max / (kbs_min ? kbs_min : 1)) + 2;
 
     const uint32_t xbytes = XR ? kbs_max * kXTile : 0u;
-    uint32_t stages = (uint32_t)((kSmemBudget - xbytes - red_bytes - 1024) / kStage);
+    uint32_t stages = (uint32_t)((kSmemBudget - xbytes - red_bytes - pre_bytes - 1280) / kStage);
     if (stages > (uint32_t)kMaxStages) stages = kMaxStages;
     stages -= stages % (NG > NP ? NG : NP);
     if (stages < 2 * NG || stages <= (uint32_t)NP) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path: shared-memory ring too small");
@@ -785,7 +864,8 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     a.x_off = stages * kStage;
     a.red_off = a.x_off + ((xbytes + 127) & ~127u);
     a.bar_off = a.red_off + ((red_bytes + 127) & ~127u);
-    const size_t smem_bytes = a.bar_off + (2 * stages + 1) * 8 + (2 + kMaxContrib) * 4;
+    a.pre_off = (a.bar_off + (2 * stages + 1) * 8 + (8 + kMaxContrib) * 4 + 15) & ~15u;
+    const size_t smem_bytes = a.pre_off + pre_bytes;
 
     if (!XR) DLLM_TRY(ensure_buf(ctx, ctx->act[2], (size_t)k_blocks * kXTile));
     DLLM_TRY(ensure_buf(ctx, ctx->lin_ws, (size_t)grid * a.max_items * MT * 128 * sizeof(float)));
@@ -847,7 +927,7 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
                            4.0 * M * qw->K + 4.0 * M * qw->N;
     }
 #ifdef DLLM_GEMV_TRACE
-    {   // dump the per-CTA timeline (timing experiments only)
+    if (!trace_chain) {   // dump the per-CTA timeline (timing experiments only)
         std::vector<unsigned long long> h((size_t)grid * 32 + 1024);
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h.data(), a.trace, h.size() * 8, cudaMemcpyDeviceToHost);
@@ -899,8 +979,36 @@ int32_t launch_gemv_mt(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, si
 
 }  // namespace
 
+#ifdef DLLM_GEMV_TRACE
+// timing experiments only: the per-CTA stamps of the last launches (one slot per launch; a replayed CUDA graph
+// overwrites the slots its launches were captured with), absolute globaltimer ns
+extern "C" __attribute__((visibility("default"))) int dllm_debug_gemv_trace_dump(const char *path) {
+    if (!g_trace_buf) return -1;
+    cudaDeviceSynchronize();
+    std::vector<unsigned long long> h(kTraceSlots * g_trace_stride);
+    cudaMemcpy(h.data(), g_trace_buf, h.size() * 8, cudaMemcpyDeviceToHost);
+    FILE *f = fopen(path, "w");
+    if (!f) return -2;
+    fprintf(f, "slot,cta,start,cons_start,x_ready,first_full,s4,s5,s6,s7,s8,s9,verdict,end,last\n");
+    const size_t n = g_trace_launch < (size_t)kTraceSlots ? g_trace_launch : (size_t)kTraceSlots;
+    for (size_t sl = 0; sl < n; ++sl)
+        for (uint32_t c = 0; c < g_trace_grid; ++c) {
+            const unsigned long long *r = h.data() + sl * g_trace_stride + (size_t)c * 32;
+            unsigned long long last = 0;
+            for (int i = 0; i < 32; ++i) if (r[i] > last) last = r[i];
+            fprintf(f, "%zu,%u", sl, c);
+            for (int i = 0; i < 10; ++i) fprintf(f, ",%llu", r[i]);
+            unsigned long long lastc = 0;
+            for (int i = 0; i < 30; ++i) if (r[i] > lastc) lastc = r[i];
+            fprintf(f, ",%llu,%llu,%llu\n", r[30], r[31], lastc);
+        }
+    fclose(f);
+    return 0;
+}
+#endif
+
 bool k_gemv_supported(const dllm_qweight *qw, size_t M) {
-    // fp16 operands: integer zero-points (subtracted exactly) and scales in fp16's full-precision range
+    // integer zero-points (subtracted exactly in the integer domain)
     return qw && M >= 1 && M <= 16 && (qw->per_tensor || qw->group % WL_TILE_K == 0) && qw->int_zps;
 }
 

@@ -79,8 +79,7 @@ wpack_kernel(const SRC *__restrict__ src, size_t K, size_t N, size_t Npad, size_
 //   2/4-bit: x = bf16x2(128 + zp)   (subtracted from the magic-number form 128 + q, exact)
 //   8-bit  : x = f32 bits of zp
 //   y = bf16x2(scale)
-// and for the GEMV path (fp16 operands): {f32 scale, half2(64 zp, zp / 32)} — the A entries of its zero-point
-// correction MMA (gemv_mma.cu; both are exact in fp16 for integer zp <= 255)
+// and for the GEMV path (int8 tensor path, gemv_mma.cu): {f32 scale, f32 zp}
 // flags (OR-ed): 1 = some zero-point is not an integer in [0, 255] (the 16-bit-operand kernels subtract it exactly
 // only if it is: quantizer B always produces such, hand-made parameters may not); 2 = some scale is outside the range
 // in which an fp16 copy keeps full precision and (q - zp) * scale cannot overflow
@@ -103,8 +102,7 @@ __global__ void wdq_params_kernel(const float *__restrict__ scales, const float 
         o.x = *reinterpret_cast<uint32_t *>(&zb);
     }
     out[i] = o;
-    __half2 zh = __floats2half2_rn(64.0f * z, z * 0.03125f);
-    gout[i] = make_uint2(__float_as_uint(s), *reinterpret_cast<uint32_t *>(&zh));
+    gout[i] = make_uint2(__float_as_uint(s), __float_as_uint(z));
 }
 
 template <int CB>
