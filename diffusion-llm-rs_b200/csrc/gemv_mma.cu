@@ -201,20 +201,24 @@ struct GemvArgs {
     uint32_t S, P;                   // k segments, CTAs per segment (grid = S * P)
     uint32_t max_items;              // partial slots per CTA
     uint32_t stages;                 // ring depth (multiple of NG)
+    uint32_t prefill;                // stages requested before the activations are resident (XR)
+    uint32_t warm;                   // run the activation preparation once before the dependency wait (instruction-cache warm-up)
     uint32_t x_off, red_off, bar_off, pre_off;   // shared-memory carve-up (bytes)
     uint32_t bulk;                   // code tiles by one cp.async.bulk per stage (default) or by per-lane cp.async (DLLM_GEMV_BULK=0)
     unsigned long long *trace;       // -DDLLM_GEMV_TRACE: per CTA [32] globaltimer stamps, then [4][256] stage stamps of CTA 0
 };
 
-// the k-segment and unit range of one CTA; units of a segment are ordered (tile, k-block)
+// the k-segment and unit range of one CTA; units of a segment are ordered (tile, k-block).
+// 32-bit arithmetic throughout (the launch checks units * (P + 1) < 2^32): a 64-bit division is ~150 instructions, and
+// this kernel must fit the 32 KB instruction cache to stay warm from one launch to the next.
 struct Range {
     uint32_t kb_s0, kbs;             // segment = k-blocks [kb_s0, kb_s0 + kbs)
-    uint64_t units, u0, u1;          // units of the segment; this CTA's range
+    uint32_t units, u0, u1;          // units of the segment; this CTA's range
     __device__ Range(const GemvArgs &a, uint32_t cta) {
         const uint32_t seg = cta / a.P, j = cta - seg * a.P;
-        kb_s0 = (uint32_t)((uint64_t)a.k_blocks * seg / a.S);
-        kbs = (uint32_t)((uint64_t)a.k_blocks * (seg + 1) / a.S) - kb_s0;
-        units = (uint64_t)a.n_tiles * kbs;
+        kb_s0 = a.k_blocks * seg / a.S;
+        kbs = a.k_blocks * (seg + 1) / a.S - kb_s0;
+        units = a.n_tiles * kbs;
         u0 = units * j / a.P;
         u1 = units * (j + 1) / a.P;
     }
@@ -225,15 +229,15 @@ struct Item {
 };
 
 struct ItemIter {
-    uint64_t u, u1;
+    uint32_t u, u1;
     uint32_t kb_s0, kbs, first_nt;
-    __device__ ItemIter(const Range &r) : u(r.u0), u1(r.u1), kb_s0(r.kb_s0), kbs(r.kbs) { first_nt = kbs ? (uint32_t)(r.u0 / kbs) : 0; }
+    __device__ ItemIter(const Range &r) : u(r.u0), u1(r.u1), kb_s0(r.kb_s0), kbs(r.kbs) { first_nt = kbs ? r.u0 / kbs : 0; }
     __device__ bool next(Item &it) {
         if (u >= u1) return false;
-        it.nt = (uint32_t)(u / kbs);
-        const uint32_t off = (uint32_t)(u - (uint64_t)it.nt * kbs);
-        const uint64_t left = u1 - u;
-        const uint32_t len = (uint64_t)(kbs - off) <= left ? kbs - off : (uint32_t)left;
+        it.nt = u / kbs;
+        const uint32_t off = u - it.nt * kbs;
+        const uint32_t left = u1 - u;
+        const uint32_t len = kbs - off <= left ? kbs - off : left;
         it.kb0 = kb_s0 + off;
         it.kb1 = it.kb0 + len;
         it.ordinal = it.nt - first_nt;
@@ -329,11 +333,11 @@ __device__ __forceinline__ void gemv_x_load(const float *__restrict__ x, uint32_
     for (int q = 0; q < 4; ++q) {
         const uint32_t k = kb * WL_TILE_K + (uint32_t)gemv_run_k0<CB>(q, (int)t);
         if (tok < M && vec && k + 3 < K) {
-            const float4 f = __ldg(reinterpret_cast<const float4 *>(x + (size_t)tok * K + k));
+            const float4 f = __ldcg(reinterpret_cast<const float4 *>(x + (size_t)tok * K + k));
             v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
         } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[4 * q + e] = (tok < M && k + e < K) ? __ldg(x + (size_t)tok * K + k + e) : 0.f;
+            for (int e = 0; e < 4; ++e) v[4 * q + e] = (tok < M && k + e < K) ? __ldcg(x + (size_t)tok * K + k + e) : 0.f;
         }
     }
 }
@@ -341,9 +345,14 @@ __device__ __forceinline__ void gemv_x_load(const float *__restrict__ x, uint32_
 // the work items of the k-blocks [kb0, kb0 + n_kb) into `dst` (tile of k-block kb0 first), all threads of whole warps:
 // 4 consecutive lanes (t = 0..3) hold the 64 activations of one (k-block, token), so its max |x| and digit sums are two
 // shuffles away.  UNR items per thread and pass, all loads issued before the first conversion.
+#ifdef DLLM_GEMV_TRACE
+#define XTRACE(slot) do { if (xtrace && tid == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(_t)); xtrace[slot] = _t; } } while (0)
+#else
+#define XTRACE(slot) do { } while (0)
+#endif
 template <int CB, int MT, int UNR>
 __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t kb0, uint32_t n_kb,
-                                                uint8_t *dst, uint32_t tid, uint32_t nthreads) {
+                                                uint8_t *dst, uint32_t tid, uint32_t nthreads, unsigned long long *xtrace = nullptr) {
     constexpr int P = gemv_parts(MT), NC = gemv_cols(MT), NB = gemv_nb(MT);
     // |x / delta| <= 2^kTop: leaves the top digit within [-64, 64] and lets the float -> int conversion be one FFMA
     // (x * (1/delta) + 1.5 * 2^23: the sum's low mantissa bits are the rounded integer; F2I is a quarter-rate instruction)
@@ -351,6 +360,7 @@ __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uin
     constexpr int kMagicBits = 0x4B400000;
     const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     const uint32_t total = n_kb * MT * 4;
+#pragma unroll 1
     for (uint32_t base = tid & ~31u; base < total; base += UNR * nthreads) {
         float v[UNR][16];
 #pragma unroll
@@ -363,8 +373,10 @@ __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uin
                 for (int e = 0; e < 16; ++e) v[j][e] = 0.f;
             }
         }
+        XTRACE(24);
 #pragma unroll
         for (int j = 0; j < UNR; ++j) {
+            if (base + j * nthreads >= total) break;                      // (warp-uniform) nothing left for this warp
             const uint32_t idx = base + j * nthreads + (tid & 31);
             const bool valid = idx < total;                               // total % 4 == 0: a quad is all valid or all not
             const uint32_t t = idx & 3, tok = (idx >> 2) % MT, kb = (idx >> 2) / MT;
@@ -375,6 +387,7 @@ __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uin
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
             m = fminf(m, 3.0e38f);
+            if (j == 0 && m >= 0.f) XTRACE(25);
             int E = (int)(__float_as_uint(m) >> 23) - 126;
             E = E < -100 ? -100 : E;
             const float inv = __int_as_float((127 + kTop - E) << 23), delta = __int_as_float((127 + E - kTop) << 23);
@@ -439,29 +452,41 @@ __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uin
 
 // y tile = sum of the partial tiles of all contributors (fixed order) + bias; `nthreads` threads, this one is `tid`
 template <int MT>
-__device__ __forceinline__ void reduce_tile(const GemvArgs &a, uint32_t cnt, const uint32_t *slots, uint32_t nt, int tid, int nthreads) {
+__device__ __noinline__ void reduce_tile(const float *__restrict__ partial, float *__restrict__ y, const float *__restrict__ bias, uint32_t M, uint32_t N,
+                                         uint32_t cnt, const uint32_t *slots, uint32_t nt, int tid, int nthreads) {
     for (int e4 = tid; e4 < MT * 32; e4 += nthreads) {                 // 4 consecutive columns of one token
         const int tok = e4 >> 5, nl = (e4 & 31) * 4;
         const uint32_t n = nt * 128 + nl;
-        if ((uint32_t)tok >= a.M || n >= a.N) continue;
+        if ((uint32_t)tok >= M || n >= N) continue;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 2
         for (uint32_t c = 0; c < cnt; ++c) {
-            const float4 pv = __ldcg(reinterpret_cast<const float4 *>(a.partial + (size_t)slots[c] * (MT * 128)) + e4);
+            const float4 pv = __ldcg(reinterpret_cast<const float4 *>(partial + (size_t)slots[c] * (MT * 128)) + e4);
             v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
         }
         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (n + i < a.N) a.y[(size_t)tok * a.N + n + i] = vv[i] + (a.bias ? __ldg(a.bias + n + i) : 0.f);
+            if (n + i < N) y[(size_t)tok * N + n + i] = vv[i] + (bias ? __ldg(bias + n + i) : 0.f);
     }
 }
 
 // XR: consumers + epilogue warp convert the CTA's k-segment of x to digit columns in shared memory (the producers are
 // already streaming weights meanwhile), then meet at kBarXReady
+// `warm`: the pass before the dependency wait.  It runs the same code on whatever the activation buffer holds at that
+// time and its output is overwritten by the real pass: its only purpose is that the real pass — which sits on the
+// critical path between two dependent kernels — finds its ~10 KB of instructions in the instruction cache (measured:
+// 4.2 us cold, whatever the code did, vs the load latency + ~1 us warm).  Loads are L2-only (ld.global.cg), so the real
+// pass cannot see lines cached by the warm-up.
 template <int CB, int MT>
-__device__ __forceinline__ void prepare_x_slice(const GemvArgs &a, const Range &rg, uint8_t *xs, int tid, int nthreads) {
-    if (rg.u0 < rg.u1) prepare_x_tiles<CB, MT, 2>(a.x, a.M, a.K, rg.kb_s0, rg.kbs, xs, (uint32_t)tid, (uint32_t)nthreads);
+__device__ __noinline__ void prepare_x_slice(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t kb0, uint32_t n_kb, uint8_t *xs,
+                                             int tid, int nthreads, bool warm, unsigned long long *xtrace) {
+    if (warm) xtrace = nullptr;
+    prepare_x_tiles<CB, MT, 1>(x, M, K, kb0, n_kb, xs, (uint32_t)tid, (uint32_t)nthreads, xtrace);
+    if (warm) return;
+#ifdef DLLM_GEMV_TRACE
+    if (tid == 0 && xtrace) { unsigned long long _t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(_t)); xtrace[26] = _t; }
+#endif
     named_bar_sync(kBarXReady, nthreads);
 }
 
@@ -522,6 +547,7 @@ gemv_mma_kernel(const GemvArgs a) {
         ItemIter iter(rg);
         Item item;
         uint32_t it0 = 0, my_it = me, my_s = me, my_ph = 0;
+        bool x_ready = false;
         while (iter.next(item)) {
             const uint32_t it1 = it0 + (item.kb1 - item.kb0 + KBS - 1) / KBS;
             const uint8_t *wsrc = a.packed + (size_t)item.nt * a.k_blocks * kWBytes;
@@ -529,6 +555,9 @@ gemv_mma_kernel(const GemvArgs a) {
             for (; my_it < it1; my_it += NP) {
                 const uint32_t kb = item.kb0 + (my_it - it0) * KBS;
                 const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                // only `prefill` stages are requested before the activations are in shared memory: the loads of the
+                // activation preparation would otherwise queue behind a whole ring of bulk copies on this SM's memory path
+                if (XR && !x_ready && my_it >= a.prefill) { mbar_wait_relaxed(xfull, 0, 1000); x_ready = true; }
                 mbar_wait_relaxed(empty + my_s, my_ph ^ 1, 2000);
                 if (lane == 0) STRACE(0, my_it);
                 uint8_t *st = ring + (size_t)my_s * kStage;
@@ -599,8 +628,13 @@ gemv_mma_kernel(const GemvArgs a) {
         ItemIter iter(rg);
         Item item;
         bool have_item = iter.next(item);
-        pdl_wait();
-        if (XR) prepare_x_slice<CB, MT>(a, rg, xs, ctid, kConsumers + 32);
+        // (ONE instance of the preparation code, executed twice: see prepare_x_slice)
+#pragma unroll 1
+        for (uint32_t pass = XR && a.warm ? 0u : 1u; pass < 2u; ++pass) {
+            if (pass == 1u) { pdl_wait(); if (ctid == 0) GTRACE(29); }
+            if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, ctid, kConsumers + 32, pass == 0u, a.trace ? a.trace + blockIdx.x * 32 : nullptr);
+        }
+        if (XR && ctid == 0) mbar_arrive_addr(smem_u32(xfull));
         if (ctid == 0) GTRACE(2);
         // stage counter `it` of the CTA; this group owns the stages with it % NG == grp and walks only those
         uint32_t it0 = 0, my_it = (uint32_t)grp, my_s = (uint32_t)grp, my_ph = 0;
@@ -677,6 +711,7 @@ gemv_mma_kernel(const GemvArgs a) {
                 } else if (prefetched) {
                     const uint32_t cnt = verdict[1], me = verdict[4];
                     float acc = 0.f;                                    // the same order as reduce_tile: bit-identical results
+#pragma unroll 1
                     for (uint32_t c = 0; c < cnt; ++c) acc += c == me ? v : pre[(c < me ? c : c - 1) * (MT * 128) + e];
                     if ((uint32_t)tok < a.M && n < a.N) a.y[(size_t)tok * a.N + n] = acc + (a.bias ? __ldg(a.bias + n) : 0.f);
                 } else {
@@ -701,13 +736,16 @@ gemv_mma_kernel(const GemvArgs a) {
             // the CTA's last tile: wait for the verdict; if this CTA arrived last, all consumer threads reduce it
             named_bar_sync(kBarFinal, kConsumers + 32);
             if (ctid == 0) GTRACE(30);
-            if (verdict[0]) reduce_tile<MT>(a, verdict[1], slots, last_nt, ctid, kConsumers);
+            if (verdict[0]) reduce_tile<MT>(a.partial, a.y, a.bias, a.M, a.N, verdict[1], slots, last_nt, ctid, kConsumers);
         }
         if (ctid == 0) GTRACE(31);
     } else {
         // ===================== epilogue warp =====================
-        pdl_wait();
-        if (XR) prepare_x_slice<CB, MT>(a, rg, xs, kConsumers + lane, kConsumers + 32);
+#pragma unroll 1
+        for (uint32_t pass = XR && a.warm ? 0u : 1u; pass < 2u; ++pass) {
+            if (pass == 1u) pdl_wait();
+            if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, kConsumers + lane, kConsumers + 32, pass == 0u, nullptr);
+        }
         ItemIter iter(rg);
         Item item;
         bool more = iter.next(item);
@@ -722,12 +760,12 @@ gemv_mma_kernel(const GemvArgs a) {
                 // contributors of this tile, in the fixed order (segment, CTA): their partial slots.  (Computed while the
                 // consumers are still working on the tile: the 64-bit divisions are off the critical path.)
                 for (uint32_t sg = 0; sg < a.S; ++sg) {
-                    const uint32_t k0 = (uint32_t)((uint64_t)a.k_blocks * sg / a.S);
-                    const uint32_t kn = (uint32_t)((uint64_t)a.k_blocks * (sg + 1) / a.S) - k0;
-                    const uint64_t U = (uint64_t)a.n_tiles * kn, a0 = (uint64_t)cur.nt * kn, a1 = a0 + kn;
-                    const uint32_t j_lo = (uint32_t)(((a0 + 1) * a.P - 1) / U), j_hi = (uint32_t)((a1 * a.P - 1) / U);
+                    const uint32_t k0 = a.k_blocks * sg / a.S;
+                    const uint32_t kn = a.k_blocks * (sg + 1) / a.S - k0;
+                    const uint32_t U = a.n_tiles * kn, a0 = cur.nt * kn, a1 = a0 + kn;
+                    const uint32_t j_lo = ((a0 + 1) * a.P - 1) / U, j_hi = (a1 * a.P - 1) / U;
                     for (uint32_t j = j_lo; j <= j_hi; ++j) {
-                        const uint32_t first_nt = (uint32_t)((U * j / a.P) / kn);
+                        const uint32_t first_nt = (U * j / a.P) / kn;
                         if (cnt < kMaxContrib) slots[cnt] = (sg * a.P + j) * a.max_items + (cur.nt - first_nt);
                         if (sg * a.P + j == blockIdx.x) me = cnt;
                         ++cnt;
@@ -782,7 +820,7 @@ gemv_mma_kernel(const GemvArgs a) {
             if (!more) {
                 named_bar_arrive(kBarFinal, kConsumers + 32);           // the consumers take it from here
             } else if (last) {
-                reduce_tile<MT>(a, cnt, slots, cur.nt, lane, 32);
+                reduce_tile<MT>(a.partial, a.y, a.bias, a.M, a.N, cnt, slots, cur.nt, lane, 32);
             }
         }
     }
@@ -832,7 +870,7 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     a.y = y;
     a.M = (uint32_t)M; a.N = (uint32_t)qw->N; a.Npad = n_tiles * 128; a.k_blocks = k_blocks; a.n_tiles = n_tiles;
     const uint32_t group_kb = qw->per_tensor ? k_blocks : (uint32_t)(qw->group / WL_TILE_K);
-    if (k_blocks >= 65536) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path: K too large");
+    if (k_blocks >= 65536 || (uint64_t)n_tiles * k_blocks * (kMaxContrib + 1) >= (1ull << 32)) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path: weight too large");
     a.group_magic = group_kb == 1 ? 0u : (uint32_t)(((1ull << 32) + group_kb - 1) / group_kb);   // 0: one k-block per group
     a.S = S; a.P = P;
     static const uint32_t bulk_mode = getenv("DLLM_GEMV_BULK") ? (uint32_t)atoi(getenv("DLLM_GEMV_BULK")) : 1u;
@@ -861,6 +899,10 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     stages -= stages % (NG > NP ? NG : NP);
     if (stages < 2 * NG || stages <= (uint32_t)NP) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path: shared-memory ring too small");
     a.stages = stages;
+    static const int prefill_env = getenv("DLLM_GEMV_PREFILL") ? atoi(getenv("DLLM_GEMV_PREFILL")) : -1;   // experiments only
+    a.prefill = prefill_env >= 0 ? (uint32_t)prefill_env : stages;
+    static const bool warm = getenv("DLLM_GEMV_WARM") != nullptr;                                         // experiments only
+    a.warm = warm ? 1u : 0u;
     a.x_off = stages * kStage;
     a.red_off = a.x_off + ((xbytes + 127) & ~127u);
     a.bar_off = a.red_off + ((red_bytes + 127) & ~127u);
@@ -989,7 +1031,7 @@ extern "C" __attribute__((visibility("default"))) int dllm_debug_gemv_trace_dump
     cudaMemcpy(h.data(), g_trace_buf, h.size() * 8, cudaMemcpyDeviceToHost);
     FILE *f = fopen(path, "w");
     if (!f) return -2;
-    fprintf(f, "slot,cta,start,cons_start,x_ready,first_full,s4,s5,s6,s7,s8,s9,verdict,end,last\n");
+    fprintf(f, "slot,cta,start,cons_start,x_ready,first_full,s4,s5,s6,s7,s8,s9,xl_issued,xl_landed,x_done,pdl,verdict,end,last\n");
     const size_t n = g_trace_launch < (size_t)kTraceSlots ? g_trace_launch : (size_t)kTraceSlots;
     for (size_t sl = 0; sl < n; ++sl)
         for (uint32_t c = 0; c < g_trace_grid; ++c) {
@@ -999,8 +1041,8 @@ extern "C" __attribute__((visibility("default"))) int dllm_debug_gemv_trace_dump
             fprintf(f, "%zu,%u", sl, c);
             for (int i = 0; i < 10; ++i) fprintf(f, ",%llu", r[i]);
             unsigned long long lastc = 0;
-            for (int i = 0; i < 30; ++i) if (r[i] > lastc) lastc = r[i];
-            fprintf(f, ",%llu,%llu,%llu\n", r[30], r[31], lastc);
+            for (int i = 0; i < 24; ++i) if (r[i] > lastc) lastc = r[i];
+            fprintf(f, ",%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", r[24], r[25], r[26], r[29], r[30], r[31], lastc);
         }
     fclose(f);
     return 0;
