@@ -108,10 +108,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+// The packed weights are read once per call: evict-first keeps them from washing everything else out of the L2 — the
+// activations, the partial tiles and, above all, this kernel's own INSTRUCTIONS (measured: the first instructions after
+// the dependency wait took 3-4 us to arrive, the time of an instruction fetch from HBM under full streaming load).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 // 16-byte asynchronous copy (LDGSTS) whose completion is reported to an mbarrier by cp_async_arrive
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -548,6 +556,7 @@ gemv_mma_kernel(const GemvArgs a) {
         Item item;
         uint32_t it0 = 0, my_it = me, my_s = me, my_ph = 0;
         bool x_ready = false;
+        const uint64_t w_policy = l2_evict_first_policy();
         while (iter.next(item)) {
             const uint32_t it1 = it0 + (item.kb1 - item.kb0 + KBS - 1) / KBS;
             const uint8_t *wsrc = a.packed + (size_t)item.nt * a.k_blocks * kWBytes;
@@ -570,7 +579,7 @@ gemv_mma_kernel(const GemvArgs a) {
                 if (a.bulk) {
                     if (elect_one()) {
                         mbar_arrive_expect_tx(full + my_s, nk * kWBytes);
-                        bulk_load(st, src, nk * kWBytes, full + my_s);
+                        bulk_load(st, src, nk * kWBytes, full + my_s, w_policy);
                     }
                     __syncwarp();
                 } else {
