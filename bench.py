@@ -164,38 +164,39 @@ def secondary_metrics(ctx, stream, pk):
     K = N = 14336
     w = torch.randn(K, N, device="cuda") * 0.02
     torch.cuda.synchronize()
-    pool = [QWeight.quantize_dev(ctx, w.data_ptr(), K, N, 4, 128) for _ in range(4)]   # 4 x 103 MB > 126 MB L2
-    ctx.sync()
-    del w
-    gemv = {"kernel": "gemv_mma_kernel<4> (cp.async/bulk ring + mma.sync on in-register dequantized fp16)",
-            "K": K, "N": N, "bits": 4, "group": 128, "timing": "CUDA-graph replay of 16 calls x 10, 4-weight pool (412 MB)"}
-    for M in (1, 16):
-        x = torch.randn(M, K, device="cuda")
-        y = torch.empty(M, N, device="cuda")
-        torch.cuda.synchronize()
-        with torch.cuda.stream(stream):
-            for i in range(4):
-                pool[i].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
-            stream.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=stream):
-            for i in range(16):
-                pool[i % 4].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            g.replay()
-            stream.synchronize()
-            e0.record(stream)
-            for _ in range(10):
+    gemv = {"kernel": "gemv_mma_kernel (bulk-copy ring + int8 mma.sync: codes as the u8 operand, activations as signed-digit columns)",
+            "K": K, "N": N, "group": 128, "timing": "CUDA-graph replay of 16 calls x 10 over a 4-weight pool (412 MB at 4 bits: every call streams from HBM)"}
+    for bits, Ms in ((4, (1, 4, 16)), (8, (1,))):
+        pool = [QWeight.quantize_dev(ctx, w.data_ptr(), K, N, bits, 128) for _ in range(4)]   # 4 x 103 MB > 126 MB L2
+        ctx.sync()
+        for M in Ms:
+            x = torch.randn(M, K, device="cuda")
+            y = torch.empty(M, N, device="cuda")
+            torch.cuda.synchronize()
+            with torch.cuda.stream(stream):
+                for i in range(4):
+                    pool[i].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
+                stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(16):
+                    pool[i % 4].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
                 g.replay()
-            e1.record(stream)
-            e1.synchronize()
-        us = e0.elapsed_time(e1) / 160 * 1e3
-        byts = K * N // 2 + (K // 128) * N * 8 + 4 * M * K + 4 * M * N
-        gemv[f"M{M}"] = {"us_per_call": round(us, 2), "GBps": round(byts / us / 1e3, 1), "hbm_frac": round(byts / us / 1e3 / hbm, 3)}
-        del g
-    for p in pool:
-        p.close()
+                stream.synchronize()
+                e0.record(stream)
+                for _ in range(10):
+                    g.replay()
+                e1.record(stream)
+                e1.synchronize()
+            us = e0.elapsed_time(e1) / 160 * 1e3
+            byts = K * N * bits // 8 + (K // 128) * N * 8 + 4 * M * K + 4 * M * N
+            gemv[f"b{bits}_M{M}"] = {"us_per_call": round(us, 2), "GBps": round(byts / us / 1e3, 1), "hbm_frac": round(byts / us / 1e3 / hbm, 3)}
+            del g
+        for p in pool:
+            p.close()
+    del w
     out["gemv"] = gemv
     rows, dim = 1 << 16, 4096
     x = torch.randn(rows, dim, device="cuda")
