@@ -717,6 +717,29 @@ int32_t dllm_qlinear_forward(dllm_ctx *ctx, const dllm_qweight *w, const float *
     return sync(ctx);
 }
 
+int32_t dllm_qlinear_forward_i8_dev(dllm_ctx *ctx, const dllm_qweight *w, const int8_t *xq_dev, size_t M, int32_t *y_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, w, DLLM_ERR_NULL, "null weight");
+    ARG_CHECK(ctx, M == 0 || (xq_dev && y_dev), DLLM_ERR_NULL, "null device pointer");
+    if (M == 0) return DLLM_OK;
+    ARG_CHECK(ctx, k_umma_i8_supported(w, M), DLLM_ERR_UNSUPPORTED,
+              "int8 path needs a per-tensor quantized weight (group_size 0) with K %% 64 == 0 and K <= 65536");
+    return k_qlinear_umma_i8(ctx, w, xq_dev, M, y_dev);
+}
+
+int32_t dllm_qlinear_forward_i8(dllm_ctx *ctx, const dllm_qweight *w, const int8_t *xq, size_t M, int32_t *y) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, w, DLLM_ERR_NULL, "null weight");
+    ARG_CHECK(ctx, M == 0 || (xq && y), DLLM_ERR_NULL, "null pointer");
+    if (M == 0) return DLLM_OK;
+    void *dx, *dy;
+    DLLM_TRY(stage_in(ctx, 4, xq, M * w->K, &dx));
+    DLLM_TRY(stage_out_buf(ctx, 5, M * w->N * sizeof(int32_t), &dy));
+    DLLM_TRY(dllm_qlinear_forward_i8_dev(ctx, w, (const int8_t *)dx, M, (int32_t *)dy));
+    DLLM_TRY(copy_out(ctx, y, dy, M * w->N * sizeof(int32_t)));
+    return sync(ctx);
+}
+
 int32_t dllm_dequant_matmul(dllm_ctx *ctx, const uint8_t *codes, const float *scales, const float *zero_points,
                             size_t K, size_t N, uint8_t bits, size_t group, const float *bias, const float *x,
                             size_t M, float *y, int32_t path) {

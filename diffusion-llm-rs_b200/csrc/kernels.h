@@ -55,6 +55,9 @@ bool k_gemv_supported(const dllm_qweight *qw, size_t M);
 int32_t k_qlinear_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M,
                        float *y_f32_dev, void *y_bf16_dev);
 bool k_umma_supported(const dllm_qweight *qw, size_t M);
+// exact int8 x u8-codes -> int32 linear on tcgen05 kind::i8 (per-tensor quantized weights)
+int32_t k_qlinear_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq_dev, size_t M, int32_t *y_i32_dev);
+bool k_umma_i8_supported(const dllm_qweight *qw, size_t M);
 
 // ---- sample_kernels.cu ----
 int32_t k_f32_to_bf16(dllm_ctx *ctx, const float *in_dev, size_t n, void *out_bf16_dev);

@@ -42,7 +42,6 @@ namespace {
 #endif
 constexpr int kNDQ = DLLM_NDQ;       // dequant groups of 4 warps
 constexpr int kAccStages = 2;
-constexpr int kACols = 32;            // TMEM columns of one dequantized k-block: 64 k of bf16 = 32 x 32-bit
 constexpr int kTmemCols = 512;
 
 // ------------------------------------------------------------------------------------------
@@ -121,6 +120,15 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}\n" :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]      (kind::i8: u8 x s8 operands, s32 accumulate: exact)
+__device__ __forceinline__ void umma_ts_i8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -134,6 +142,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
            "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
            "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
            "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -175,6 +191,10 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 // whose unpack is cheaper, see gemv_mma.cu — would need fp16 activations too; the stack keeps bf16 for its range.)
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// kind::i8: c = s32 (2<<4), a = u8 (0<<7: the codes as they are), b = s8 (1<<10), K-major A and B
+__host__ __device__ constexpr uint32_t make_idesc_i8(int n) {
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -242,6 +262,38 @@ __device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, ui
     }
 }
 
+// int8 mode: one k-block (64 k) of one output column as 16 words of four u8 codes in k order (the A operand of
+// kind::i8 reads its 32-byte K chunk from 8 consecutive TMEM columns of the row) — no zero-point, no scale: the integer
+// GEMM is exact and the zero-point leaves in the epilogue as zp * rowsum(x).
+template <int CB>
+__device__ __forceinline__ void unpack_kblock_u8(const uint4 *wpk, int n_local, uint32_t *out) {
+    constexpr int CH = CB / 2;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const uint4 c = wpk[j * 128 + n_local];
+        const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int wd = 0; wd < 4; ++wd) {
+            if (CB == 4) {
+                // codes 0..7 at nibbles {0,4,1,5,2,6,3,7}: w & 0x0f.. = bytes (c0,c4,c1,c5), (w >> 4) & 0x0f.. = (c2,c6,c3,c7)
+                const uint32_t lo = w[wd] & 0x0f0f0f0fu, hi = (w[wd] >> 4) & 0x0f0f0f0fu;
+                out[j * 8 + wd * 2 + 0] = __byte_perm(lo, hi, 0x6420);
+                out[j * 8 + wd * 2 + 1] = __byte_perm(lo, hi, 0x7531);
+            } else if (CB == 2) {
+                // code i at field (i >> 1) + 8 (i & 1): (w >> 2 s) & 0x03.. = bytes (2s, 8+2s, 2s+1, 9+2s)
+                const uint32_t r0 = w[wd] & 0x03030303u, r1 = (w[wd] >> 2) & 0x03030303u;
+                const uint32_t r2 = (w[wd] >> 4) & 0x03030303u, r3 = (w[wd] >> 6) & 0x03030303u;
+                out[wd * 4 + 0] = __byte_perm(r0, r1, 0x6420);
+                out[wd * 4 + 1] = __byte_perm(r2, r3, 0x6420);
+                out[wd * 4 + 2] = __byte_perm(r0, r1, 0x7531);
+                out[wd * 4 + 3] = __byte_perm(r2, r3, 0x7531);
+            } else {
+                out[j * 4 + wd] = w[wd];
+            }
+        }
+    }
+}
+
 struct UmmaArgs {
     const uint8_t *packed;
     const uint2 *dqparams;     // [G][Npad] {zero-point term, bf16x2 scale}
@@ -255,6 +307,8 @@ struct UmmaArgs {
     long long *trace;          // dbg & 128: per-stage clock64 stamps of CTA 0: [role 0..7][256]
     uint32_t dbg;              // timing experiments only (DLLM_UMMA_DBG): 1 skip MMAs, 2 skip dequant math, 4 skip TMEM stores
     uint64_t units;            // n_tiles * m_tiles * k_blocks
+    // int8 mode reuses three fields (a larger parameter block costs the bf16 instances registers: they start to spill):
+    //   y_f32 = the exact int32 output [M,N], partial = row sums of the int8 activations [M] (int32), x3d = the zero-point
 };
 
 // One piece of work of a CTA: k-blocks [kb0, kb1) of output tile `tile`.
@@ -307,16 +361,20 @@ struct ItemIter {
 // pipeline_model.py): the dequant group that owns stage `it` first waits for MMA(it - A) [previous user
 // of its TMEM slot], then for the stage's weight bytes.  Those waits cannot alias if the XA ring has
 // at least as many slots as there are dequant groups and the W ring is at least as deep as the XA ring.
-template <int CB, int NTOK, int KBS, int NDQ = 4>
+template <int CB, int NTOK, int KBS, int NDQ = 4, bool I8 = false>
 struct Cfg {
-    static constexpr int kXBytes = NTOK * 128;                       // one k-block of activations (bf16, SW128)
+    // one k-block of activations: bf16 = a SW128 tile of NTOK rows x 128 B; int8 = half of one (the stage's two k-blocks
+    // share the 128-byte rows of ONE tile)
+    static constexpr int kXBytes = I8 ? NTOK * 64 : NTOK * 128;
+    static constexpr int kACols = I8 ? 16 : 32;                      // TMEM columns of one k-block of A: 64 k x (1 | 2) B / 4
     static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;   // one packed weight tile
     static constexpr int kPBytes = 128 * 8;                          // dequant operands of 128 columns
     static constexpr int kXStage = KBS * kXBytes;
     static constexpr int kWStage = KBS * (kWBytes + kPBytes);
     static constexpr int kSlotCols = KBS * kACols;
     static constexpr int kSlotsRaw = (kTmemCols - kAccStages * NTOK) / kSlotCols;
-    static constexpr int kSlots = kSlotsRaw > 8 ? 8 : kSlotsRaw;     // XA ring depth
+    static constexpr int kSlotsCap = I8 ? 4 : 8;                     // (int8: A slots are half as wide; keep the W ring the deeper one)
+    static constexpr int kSlots = kSlotsRaw > kSlotsCap ? kSlotsCap : kSlotsRaw;     // XA ring depth
     static constexpr int kSmemBudget = 216 * 1024;
     static constexpr int kWStagesRaw = (kSmemBudget - kSlots * kXStage) / kWStage;
     static constexpr int kWStages = (kWStagesRaw > 24 ? 24 : kWStagesRaw) & ~1;   // W ring depth (even: two producer warps alternate)
@@ -325,15 +383,17 @@ struct Cfg {
     static constexpr int kNumBars = 2 * kWStages + 3 * kSlots + 2 * kAccStages;
     static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;     // + tmem slot + alignment slack
     static_assert(kXStage % 1024 == 0 && kWStage % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned stages");
+    static_assert(!I8 || KBS == 2, "int8 mode: one 128-byte-row tile per stage = two k-blocks");
     static_assert(kSlots >= NDQ, "XA ring must have at least as many slots as dequant groups");
     static_assert(kWStages >= kSlots, "W ring must be at least as deep as the XA ring");
     static_assert(kAccStages * NTOK + kSlots * kSlotCols <= kTmemCols, "TMEM over-subscribed");
 };
 
-template <int CB, int NTOK, int KBS, int NDQ>
+template <int CB, int NTOK, int KBS, int NDQ, bool I8>
 __global__ void __launch_bounds__((8 + 4 * NDQ) * 32, 1)
 umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
-    using C = Cfg<CB, NTOK, KBS, NDQ>;
+    using C = Cfg<CB, NTOK, KBS, NDQ, I8>;
+    constexpr int kACols = C::kACols;
     constexpr int SW = C::kWStages, A = C::kSlots;
     constexpr int kEpiWarp0 = 4 + 4 * NDQ;
     extern __shared__ uint8_t smem_raw[];
@@ -377,7 +437,11 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 if (elect_one()) {
                     TRACE(0, it);
                     uint8_t *stage = smem + s * C::kXStage;
-                    if (!(a.dbg & 8)) {
+                    if constexpr (I8) {
+                        // int8: one box {128 k, NTOK tokens} = both k-blocks of the stage; k past K is zero-filled
+                        mbar_arrive_expect_tx(xfull + s, KBS * C::kXBytes);
+                        tma_load_2d(stage, &tmap_x, xfull + s, (int)(kb * WL_TILE_K), (int)(mt * NTOK));
+                    } else if (!(a.dbg & 8)) {
                         if (a.x3d) {
                             // one TMA for all KBS k-blocks: box {64 k, NTOK tokens, KBS k-blocks}; k-blocks past K are zero-filled
                             mbar_arrive_expect_tx(xfull + s, KBS * C::kXBytes);
@@ -424,7 +488,7 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-converged; one elected lane issues) =====================
-        constexpr uint32_t idesc = make_idesc(NTOK);
+        constexpr uint32_t idesc = I8 ? make_idesc_i8(NTOK) : make_idesc(NTOK);
         ItemIter iter(a);
         Item item;
         uint32_t it = 0, n_item = 0;
@@ -452,9 +516,16 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 const bool first = kb == item.kb0;
                 if (elect_one() && !(a.dbg & 1)) {             // k-block 0 of the stage
                     const uint64_t bdesc = make_b_desc(stage_addr);
+                    if constexpr (I8) {
+                        // 32 k (= 32 bytes of the 128-byte row, 8 TMEM columns of A) per MMA: two per k-block
 #pragma unroll
-                    for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
-                        umma_ts(d_tmem, a_tmem + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (!first || k4 > 0) ? 1u : 0u);
+                        for (int k2 = 0; k2 < 2; ++k2)
+                            umma_ts_i8(d_tmem, a_tmem + k2 * 8, bdesc + (uint64_t)(k2 * 2), idesc, (!first || k2 > 0) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                            umma_ts(d_tmem, a_tmem + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (!first || k4 > 0) ? 1u : 0u);
+                    }
                 }
                 __syncwarp();
                 ready = false;
@@ -467,10 +538,17 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 }
                 if (elect_one()) {
                     for (uint32_t sub = 1; sub < nk && !(a.dbg & 1); ++sub) {
-                        const uint64_t bdesc = make_b_desc(stage_addr + sub * C::kXBytes);
+                        if constexpr (I8) {
+                            const uint64_t bdesc = make_b_desc(stage_addr);      // second half of the same 128-byte rows
 #pragma unroll
-                        for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
-                            umma_ts(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, 1u);
+                            for (int k2 = 0; k2 < 2; ++k2)
+                                umma_ts_i8(d_tmem, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, 1u);
+                        } else {
+                            const uint64_t bdesc = make_b_desc(stage_addr + sub * C::kXBytes);
+#pragma unroll
+                            for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                                umma_ts(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, 1u);
+                        }
                     }
                     umma_commit(xaempty + s);      // frees the activation stage and the TMEM A slot
                 }
@@ -504,6 +582,11 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                     const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes);
                     const uint2 prm = reinterpret_cast<const uint2 *>(stage + KBS * C::kWBytes + sub * C::kPBytes)[n_local];
                     uint32_t vals[32];
+                    if constexpr (I8) {
+                        unpack_kblock_u8<CB>(wpk, n_local, vals);
+                        tmem_st16(lane_addr + sl * C::kSlotCols + sub * kACols, vals);
+                        continue;
+                    }
                     if (!(a.dbg & 2)) dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
                     else {
 #pragma unroll
@@ -553,7 +636,16 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                     if (lane == 0) mbar_arrive(tempty + acc);
                 }
                 const uint32_t m_base = mt * NTOK + c0;
-                if (direct) {
+                if constexpr (I8) {
+                    // exact: sum x q - zp sum x  (dequantize_tensor's `- zp`, quantization.rs:83, in the integer domain)
+                    if (!n_ok) continue;
+                    int32_t *yp = reinterpret_cast<int32_t *>(a.y_f32) + (size_t)m_base * a.N + n;
+                    const int32_t *sx = reinterpret_cast<const int32_t *>(a.partial);
+                    const int32_t zp = (int32_t)a.x3d;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (m_base + j < a.M) yp[(size_t)j * a.N] = (int32_t)v[j] - zp * __ldg(sx + m_base + j);
+                } else if (direct) {
                     if (!n_ok || (a.dbg & 64)) continue;
                     if (a.y_f32) {
                         float *yp = a.y_f32 + (size_t)m_base * a.N + n;
@@ -633,7 +725,7 @@ PFN_encodeTiled get_encode_fn() {
 
 template <int CB, int NTOK, int KBS, int NDQ>
 int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, size_t M, float *y_f32, void *y_bf16) {
-    using C = Cfg<CB, NTOK, KBS, NDQ>;
+    using C = Cfg<CB, NTOK, KBS, NDQ, false>;
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     CUtensorMap tmap;
@@ -693,7 +785,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     }
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, KBS, NDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, KBS, NDQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
         attr_set = true;
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -707,7 +799,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
         CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    umma_qlinear_kernel<CB, NTOK, KBS, NDQ><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
+    umma_qlinear_kernel<CB, NTOK, KBS, NDQ, false><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
     LAUNCH_CHECK(ctx);
     if (ev1) {
         CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
@@ -745,7 +837,107 @@ int32_t launch_umma_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const void *x, s
     return launch_umma<CB, 128, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
 }
 
+// row sums of the int8 activations (one warp per token row; K % 4 == 0)
+__global__ void __launch_bounds__(256)
+rowsum_i8_kernel(const int8_t *__restrict__ x, uint32_t M, uint32_t K, int32_t *__restrict__ sx) {
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int *p = reinterpret_cast<const int *>(x + (size_t)row * K);
+    int acc = 0;
+    for (uint32_t i = lane; i < K / 4; i += 32) acc = __dp4a(__ldg(p + i), 0x01010101, acc);
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+    if (lane == 0) sx[row] = acc;
+}
+
+template <int CB, int NTOK>
+int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, size_t M, int32_t *y) {
+    constexpr int KBS = 2, NDQ = kNDQ;
+    using C = Cfg<CB, NTOK, KBS, NDQ, true>;
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    CUtensorMap tmap;
+    // [M tokens, K bytes] row-major; one box = 128 k x NTOK tokens in the SWIZZLE_128B K-major layout
+    const cuuint64_t gdim[2] = {(cuuint64_t)qw->K, (cuuint64_t)M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)qw->K};
+    const cuuint32_t box[2] = {2 * WL_TILE_K, (cuuint32_t)NTOK};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(xq), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+
+    DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, M * sizeof(int32_t)));
+    rowsum_i8_kernel<<<(unsigned)((M + 7) / 8), 256, 0, ctx->stream>>>(xq, (uint32_t)M, (uint32_t)qw->K, (int32_t *)ctx->lin_flags.p);
+    LAUNCH_CHECK(ctx);
+
+    UmmaArgs a;
+    a.packed = qw->d_packed; a.dqparams = qw->d_dqparams; a.bias = nullptr;
+    a.x3d = (uint32_t)(int32_t)qw->tensor_zp;           // (int8 mode: the zero-point)
+    a.M = (uint32_t)M; a.N = (uint32_t)qw->N; a.Npad = (uint32_t)(qw->n_tiles * 128);
+    a.k_blocks = (uint32_t)qw->k_blocks; a.n_tiles = (uint32_t)qw->n_tiles;
+    a.m_tiles = (uint32_t)((M + NTOK - 1) / NTOK);
+    a.group_kb = (uint32_t)(qw->group / WL_TILE_K);
+    const uint32_t tiles = a.n_tiles * a.m_tiles;
+    a.units = (uint64_t)tiles * a.k_blocks;
+    a.y_f32 = reinterpret_cast<float *>(y); a.y_bf16 = nullptr;
+    a.partial = reinterpret_cast<float *>(ctx->lin_flags.p);           // (int8 mode: the row sums)
+    a.dbg = 0; a.trace = nullptr;
+    a.stream_k = 0;                                      // whole tiles only: int32 accumulators never leave TMEM half-summed
+    const uint32_t sms = (uint32_t)ctx->sm_count;
+    const uint32_t grid = tiles < sms ? tiles : sms;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, KBS, NDQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+        attr_set = true;
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->prof_on) {
+        while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) {
+            cudaEvent_t e;
+            CUDA_TRY(ctx, cudaEventCreate(&e));
+            ctx->prof_ev.push_back(e);
+        }
+        ev0 = ctx->prof_ev[2 * ctx->prof_n];
+        ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
+        CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    umma_qlinear_kernel<CB, NTOK, KBS, NDQ, true><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
+    LAUNCH_CHECK(ctx);
+    if (ev1) {
+        CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
+        ctx->prof_n++;
+        ctx->prof_flops += 2.0 * (double)M * (double)qw->K * (double)qw->N;
+        ctx->prof_bytes += (double)qw->K * qw->N * qw->bits / 8.0 + 1.0 * M * qw->K + 4.0 * M * qw->N;
+    }
+    return DLLM_OK;
+}
+
+template <int CB>
+int32_t launch_umma_i8_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, size_t M, int32_t *y) {
+    if (M <= 16) return launch_umma_i8<CB, 16>(ctx, qw, xq, M, y);
+    if (M <= 32) return launch_umma_i8<CB, 32>(ctx, qw, xq, M, y);
+    if (M <= 64) return launch_umma_i8<CB, 64>(ctx, qw, xq, M, y);
+    return launch_umma_i8<CB, 128>(ctx, qw, xq, M, y);
+}
+
 }  // namespace
+
+// exact integer linear on the tcgen05 int8 path: per-tensor quantized weights (one integer zero-point), K % 64 == 0 (whole
+// k-blocks), K * 255 * 128 < 2^31 (no int32 overflow)
+bool k_umma_i8_supported(const dllm_qweight *qw, size_t M) {
+    return qw && M >= 1 && M < (1u << 31) && qw->per_tensor && qw->int_zps && qw->K % WL_TILE_K == 0 && qw->K <= 65536;
+}
+
+int32_t k_qlinear_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq_dev, size_t M, int32_t *y_i32_dev) {
+    if (!k_umma_i8_supported(qw, M)) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "int8 path: per-tensor quantized weight with K %% 64 == 0 and K <= 65536 required");
+    if ((reinterpret_cast<uintptr_t>(xq_dev) & 15u) != 0) DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "xq must be 16-byte aligned");
+    switch (wl_container_bits(qw->bits)) {
+        case 2: return launch_umma_i8_ntok<2>(ctx, qw, xq_dev, M, y_i32_dev);
+        case 4: return launch_umma_i8_ntok<4>(ctx, qw, xq_dev, M, y_i32_dev);
+        default: return launch_umma_i8_ntok<8>(ctx, qw, xq_dev, M, y_i32_dev);
+    }
+}
 
 bool k_umma_supported(const dllm_qweight *qw, size_t M) {
     // TMA needs a 16-byte row pitch for x (K % 8 == 0); everything else is padded / masked

@@ -127,6 +127,8 @@ SIGNATURES = {
     "dllm_qweight_destroy": (None, [c_vp]),
     "dllm_qlinear_forward": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_vp, C.c_int32]),
     "dllm_qlinear_forward_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_vp, C.c_int32]),
+    "dllm_qlinear_forward_i8": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dllm_qlinear_forward_i8_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_vp]),
     "dllm_dequant_matmul": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, C.c_uint8, c_sz, c_vp, c_vp, c_sz,
                                         c_vp, C.c_int32]),
     "dllm_model_create": (C.c_int32, [c_vp, c_sz, C.POINTER(c_vp), c_sz, c_sz, C.c_int32, C.c_float, C.c_float,

@@ -276,6 +276,20 @@ class QWeight:
     def forward_dev(self, x_dev: int, M: int, y_dev: int, path=L.PATH_AUTO):
         self.ctx._ck(self.ctx._lib.dllm_qlinear_forward_dev(self.ctx.h, self.h, x_dev, M, y_dev, path))
 
+    def forward_i8(self, xq):
+        """Exact integer linear for a per-tensor quantized weight: int8 xq[M,K] -> int32 y[M,N] = sum_k xq (q - zp)
+        (tcgen05 kind::i8; dequantize_tensor composed with the matmul is tensor_scale * x_scale * y)."""
+        xq = np.ascontiguousarray(xq, dtype=np.int8)
+        M, K = xq.shape
+        assert K == self.K
+        y = np.empty((M, self.N), np.int32)
+        with self.ctx.lock:
+            self.ctx._ck(self.ctx._lib.dllm_qlinear_forward_i8(self.ctx.h, self.h, _ptr(xq), M, _ptr(y)))
+        return y
+
+    def forward_i8_dev(self, xq_dev: int, M: int, y_dev: int):
+        self.ctx._ck(self.ctx._lib.dllm_qlinear_forward_i8_dev(self.ctx.h, self.h, xq_dev, M, y_dev))
+
     def close(self):
         if self.h:
             self.ctx.sync()

@@ -221,6 +221,15 @@ DLLM_API int32_t dllm_qlinear_forward(dllm_ctx *ctx, const dllm_qweight *w, cons
                                       float *y, int32_t path);
 DLLM_API int32_t dllm_qlinear_forward_dev(dllm_ctx *ctx, const dllm_qweight *w, const float *x_dev,
                                           size_t M, float *y_dev, int32_t path);
+/* Exact integer linear (BASELINE.json north_star: "int8 natively ... 0 for int8->int32"): for a weight quantized per
+ * tensor (group_size 0: one scale, one integer zero-point — quantize_tensor's own scheme, quantization.rs:38-68) and
+ * int8 activations xq[M,K],   y[M,N] (int32) = sum_k xq[m,k] * (q[k,n] - zp)   with no rounding anywhere (tcgen05
+ * kind::i8, u8 codes x s8 activations, s32 accumulators).  The float result of dequantize_tensor composed with the
+ * matmul is tensor_scale * x_scale * y.  K % 64 == 0, K <= 65536 (no int32 overflow); else DLLM_ERR_UNSUPPORTED. */
+DLLM_API int32_t dllm_qlinear_forward_i8(dllm_ctx *ctx, const dllm_qweight *w, const int8_t *xq, size_t M,
+                                         int32_t *y);
+DLLM_API int32_t dllm_qlinear_forward_i8_dev(dllm_ctx *ctx, const dllm_qweight *w, const int8_t *xq_dev,
+                                             size_t M, int32_t *y_dev);
 /* `quantization` crate extension named by BASELINE.json north_star ("quantize/dequantize/matmul"):
  * one-shot dequant-matmul from canonical codes. */
 DLLM_API int32_t dllm_dequant_matmul(dllm_ctx *ctx, const uint8_t *codes, const float *scales,

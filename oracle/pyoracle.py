@@ -326,3 +326,14 @@ def sample(x0, layers, hidden, num_steps, betas, noises, guard_t0=True, threads=
         z = noises[t] if (noises is not None and t > 0) else None
         x = p_sample(x, pred, z, np.full(batch, t), betas, guard_t0)
     return x
+
+
+def linear_i8(xq, codes, zp):
+    """Exact integer form of `x.dot(dequantize_tensor(codes))` (diffuse-llm-rs/src/lib.rs:812 composed with
+    quantization.rs:81-85, `(q - zp) * scale`) for a per-tensor quantized weight and int8 activations:
+    y[m,n] = sum_k xq[m,k] * (codes[k,n] - zp), in int64 (numpy), the scale factored out.  Checker for
+    dllm_qlinear_forward_i8 (tolerance 0)."""
+    zi = int(zp)
+    assert zi == zp, "per-tensor zero-points of quantize_tensor are integers (quantization.rs:55-56)"
+    return np.asarray(xq, dtype=np.int64) @ (np.asarray(codes, dtype=np.int64) - zi)
+

@@ -313,6 +313,56 @@ def test_qlinear_gemv_full_width(ctx, bits, M):
     qw.close()
 
 
+# ---------------------------------------------------------------- exact int8 linear (tcgen05 kind::i8)
+@pytest.mark.parametrize("bits", [2, 4, 8])
+@pytest.mark.parametrize("shape", [(64, 128, 1), (256, 130, 16), (1024, 384, 100), (4160, 256, 300), (2048, 1000, 33)])
+def test_qlinear_i8_exact(ctx, O, bits, shape):
+    """int8 activations x per-tensor quantized codes -> int32, tolerance 0 (BASELINE.json north_star): every output equals
+    the int64 oracle, for ragged N / token counts, K with an odd number of k-blocks, and activations that include -128."""
+    from dllm_b200 import QWeight
+    K, N, M = shape
+    rng = np.random.default_rng(K + N + M + bits)
+    w = make_w(rng, K, N)
+    qw = QWeight.quantize(ctx, w, bits, 0)
+    codes, scales, zps = qw.export()
+    c0, s0, z0 = O.quantize_tensor(w, bits)
+    assert np.array_equal(codes.reshape(-1), c0) and float(np.ravel(scales)[0]) == s0 and float(np.ravel(zps)[0]) == z0
+    xq = rng.integers(-128, 128, (M, K)).astype(np.int8)
+    xq[0, :7] = -128
+    xq[-1, -5:] = 127
+    y = qw.forward_i8(xq)
+    exp = O.linear_i8(xq, codes.reshape(K, N), z0)
+    assert y.dtype == np.int32 and np.array_equal(y.astype(np.int64), exp)
+    # composed with the scales it is the reference's float linear (f32-faithful path on the same integers)
+    from dllm_b200 import PATH_SIMT
+    yf = qw.forward(xq.astype(F), PATH_SIMT)
+    assert np.allclose(yf, s0 * exp, rtol=2e-5, atol=2e-5 * float(np.abs(s0 * exp).max()))
+    qw.close()
+
+
+def test_qlinear_i8_extremes_and_errors(ctx, O):
+    """All-maximum operands (the int32 accumulator's worst case for K = 4096), and the shapes the int8 path refuses."""
+    import dllm_b200
+    from dllm_b200 import QWeight
+    K, N, M = 4096, 128, 16
+    codes = np.full((K, N), 255, np.uint8)
+    codes[:, 1] = 0
+    qw = QWeight.from_codes(ctx, codes, np.array([0.01], F), np.array([3.0], F), 8, 0)
+    xq = np.full((M, K), -128, np.int8)
+    xq[1] = 127
+    assert np.array_equal(qw.forward_i8(xq).astype(np.int64), O.linear_i8(xq, codes, 3.0))
+    qw.close()
+    rng = np.random.default_rng(3)
+    grouped = QWeight.quantize(ctx, make_w(rng, 256, 128), 4, 128)
+    with pytest.raises(dllm_b200.UnsupportedOperation):
+        grouped.forward_i8(np.zeros((4, 256), np.int8))
+    grouped.close()
+    ragged = QWeight.quantize(ctx, make_w(rng, 200, 128), 4, 0)
+    with pytest.raises(dllm_b200.UnsupportedOperation):
+        ragged.forward_i8(np.zeros((4, 200), np.int8))
+    ragged.close()
+
+
 # ---------------------------------------------------------------- linear, tcgen05 path
 def umma_check(y, y64):
     err = np.abs(y - y64)
