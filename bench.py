@@ -198,6 +198,32 @@ def secondary_metrics(ctx, stream, pk):
             p.close()
     del w
     out["gemv"] = gemv
+    # exact int8 linear (tcgen05 kind::i8) on the three layer shapes of the 1B-class model at 8192 tokens
+    i8 = {"kernel": "umma_qlinear_kernel<.., int8> (tcgen05 kind::i8: u8 codes x s8 activations -> s32, exact)", "tokens": 8192, "bits": 4,
+          "scheme": "per-tensor quantized weight (quantization.rs:38-68), int8 activations"}
+    Mi = 8192
+    for (Ki, Ni) in ((2048, 2048), (2048, 8192), (8192, 2048)):
+        wi = torch.randn(Ki, Ni, device="cuda") * 0.02
+        torch.cuda.synchronize()
+        qt = QWeight.quantize_dev(ctx, wi.data_ptr(), Ki, Ni, 4, 0)
+        xq = torch.randint(-128, 128, (Mi, Ki), device="cuda", dtype=torch.int8)
+        yi = torch.empty(Mi, Ni, device="cuda", dtype=torch.int32)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                qt.forward_i8_dev(xq.data_ptr(), Mi, yi.data_ptr())
+            stream.synchronize()
+            e0.record(stream)
+            for _ in range(20):
+                qt.forward_i8_dev(xq.data_ptr(), Mi, yi.data_ptr())
+            e1.record(stream)
+            e1.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        i8[f"{Ki}x{Ni}"] = {"us": round(us, 1), "TOPs": round(2.0 * Mi * Ki * Ni / us / 1e6, 1)}
+        qt.close()
+        del wi, xq, yi
+    out["int8_linear"] = i8
     rows, dim = 1 << 16, 4096
     x = torch.randn(rows, dim, device="cuda")
     codes = torch.empty(rows * dim // 2, dtype=torch.uint8, device="cuda")

@@ -302,6 +302,20 @@ public:
     ~QWeight() { dllm_qweight_destroy(h_); }
     QWeight(const QWeight &) = delete;
     dllm_qweight *raw() const { return h_; }
+    // y[M,N] = x[M,K] . dequant(W) + b   (lib.rs:806-813)
+    std::vector<float> forward(Context &ctx, const std::vector<float> &x, size_t M, size_t N, int32_t path = DLLM_PATH_AUTO) const {
+        std::vector<float> y(M * N);
+        std::lock_guard<std::mutex> lk(ctx.mutex());
+        ctx.check(dllm_qlinear_forward(ctx.raw(), h_, x.data(), M, y.data(), path));
+        return y;
+    }
+    // exact: y[M,N] = sum_k xq[m,k] * (q[k,n] - zp) for a per-tensor quantized weight (group 0); no rounding anywhere
+    std::vector<int32_t> forward_i8(Context &ctx, const std::vector<int8_t> &xq, size_t M, size_t N) const {
+        std::vector<int32_t> y(M * N);
+        std::lock_guard<std::mutex> lk(ctx.mutex());
+        ctx.check(dllm_qlinear_forward_i8(ctx.raw(), h_, xq.data(), M, y.data()));
+        return y;
+    }
 
 private:
     dllm_qweight *h_ = nullptr;
