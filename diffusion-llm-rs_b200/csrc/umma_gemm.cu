@@ -90,6 +90,55 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on the two SMs of a TPC run ONE 256-row MMA.  Each CTA dequantizes its
+// own 128 output columns into its own tensor memory and loads HALF of the activation tile (the B operand is read from both
+// CTAs' shared memory), so the activation traffic per SM halves.  Barriers the leader (rank 0) waits on collect arrivals
+// from both CTAs; completions it produces (tcgen05.commit) are multicast to both.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p`'s twin in the leader CTA
+__device__ __forceinline__ uint32_t leader_addr(const void *p) {
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(a) : "r"(smem_u32(p)));
+    return a;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
+}
+// both CTAs load their half of the tile into their own shared memory; the bytes are reported to the LEADER's barrier
+__device__ __forceinline__ void tma_load_3d_pair(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs, 256 rows] (+)= A[tmem of both CTAs] * B[smem of both CTAs]
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // one lane of a fully converged warp (keeps the surrounding code warp-uniform so that descriptors and
 // addresses live in uniform registers: no per-instruction R2UR waterfall in the MMA / TMA issue loops)
 __device__ __forceinline__ bool elect_one() {
@@ -191,6 +240,10 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 // whose unpack is cheaper, see gemv_mma.cu — would need fp16 activations too; the stack keeps bf16 for its range.)
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// the same for the 256-row MMA of a CTA pair
+__host__ __device__ constexpr uint32_t make_idesc_pair(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 // kind::i8: c = s32 (2<<4), a = u8 (0<<7: the codes as they are), b = s8 (1<<10), K-major A and B
 __host__ __device__ constexpr uint32_t make_idesc_i8(int n) {
@@ -323,9 +376,15 @@ struct Item {
 struct ItemIter {
     uint32_t stream_k, KB, tiles, cur_tile, first;
     uint64_t u, u1;
-    __device__ ItemIter(const UmmaArgs &a) {
+    uint32_t stride;
+    // pair: the two CTAs of a cluster walk the same sequence of (token tile, PAIR of column tiles)
+    __device__ ItemIter(const UmmaArgs &a, bool pair = false) {
         stream_k = a.stream_k; KB = a.k_blocks; tiles = a.n_tiles * a.m_tiles; first = 1;
-        if (stream_k) {
+        stride = gridDim.x;
+        if (pair) {
+            tiles = ((a.n_tiles + 1) / 2) * a.m_tiles; stride = gridDim.x / 2;
+            cur_tile = blockIdx.x / 2; u = u1 = 0;
+        } else if (stream_k) {
             u = a.units * blockIdx.x / gridDim.x;
             u1 = a.units * (blockIdx.x + 1) / gridDim.x;
         } else {
@@ -336,7 +395,7 @@ struct ItemIter {
         if (!stream_k) {
             if (cur_tile >= tiles) return false;
             it.tile = cur_tile; it.kb0 = 0; it.kb1 = KB; it.slot = -1;
-            cur_tile += gridDim.x;
+            cur_tile += stride;
             return true;
         }
         if (u >= u1) return false;
@@ -355,17 +414,18 @@ struct ItemIter {
 //   W ring  (kWStages deep): packed weight tiles + their dequant operands in smem.  Filled by the weight
 //           producer, consumed by the dequant warps (generic-proxy reads), released by their arrival.
 //           It is deep and cheap (4-bit: 5 KB per k-block), so the dequant never waits on HBM latency.
-//   XA ring (kSlots deep): activation tiles in smem + the dequantized A tile in TMEM, k-block for
-//           k-block.  Both are released by the same tcgen05.commit once the stage's MMAs completed.
+//   X ring  (kXSlots deep): activation tiles in smem;  A ring (kSlots deep): the dequantized A tiles in TMEM, k-block
+//           for k-block.  Each is released by its own tcgen05.commit once the stage's MMAs completed.
 // Safety rule for the parity waits (verified with an interleaving model of the protocol, scripts/
 // pipeline_model.py): the dequant group that owns stage `it` first waits for MMA(it - A) [previous user
-// of its TMEM slot], then for the stage's weight bytes.  Those waits cannot alias if the XA ring has
-// at least as many slots as there are dequant groups and the W ring is at least as deep as the XA ring.
-template <int CB, int NTOK, int KBS, int NDQ = 4, bool I8 = false>
+// of its TMEM slot], then for the stage's weight bytes.  Those waits cannot alias if the A ring has
+// at least as many slots as there are dequant groups and the W ring is at least as deep as the A ring.
+template <int CB, int NTOK, int KBS, int NDQ = 4, bool I8 = false, bool PAIR = false>
 struct Cfg {
     // one k-block of activations: bf16 = a SW128 tile of NTOK rows x 128 B; int8 = half of one (the stage's two k-blocks
     // share the 128-byte rows of ONE tile)
-    static constexpr int kXBytes = I8 ? NTOK * 64 : NTOK * 128;
+    // (CTA pair: this CTA's half of the tile's tokens)
+    static constexpr int kXBytes = I8 ? NTOK * 64 : (PAIR ? NTOK * 64 : NTOK * 128);
     static constexpr int kACols = I8 ? 16 : 32;                      // TMEM columns of one k-block of A: 64 k x (1 | 2) B / 4
     static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;   // one packed weight tile
     static constexpr int kPBytes = 128 * 8;                          // dequant operands of 128 columns
@@ -376,33 +436,58 @@ struct Cfg {
     static constexpr int kSlotsCap = I8 ? 4 : 8;                     // (int8: A slots are half as wide; keep the W ring the deeper one)
     static constexpr int kSlots = kSlotsRaw > kSlotsCap ? kSlotsCap : kSlotsRaw;     // XA ring depth
     static constexpr int kSmemBudget = 216 * 1024;
-    static constexpr int kWStagesRaw = (kSmemBudget - kSlots * kXStage) / kWStage;
+    // The activation ring (shared memory, kXSlots) and the A ring (tensor memory, kSlots) have their own barriers and may
+    // differ in depth.  Measured (profiles/README.md, round-1 notes): a deeper activation ring (5-8 stages, at the price
+    // of W stages) does NOT help — the stage cadence (~900 cycles for 8 MMAs of 128x128x16) is the pace of the tensor
+    // pipe itself in this configuration (A from tensor memory + concurrent tcgen05.st of the next A slots), not the
+    // activation latency — so both rings stay 4 deep and the W ring keeps the rest of the shared memory.
+    static constexpr int kXSlots = kSlots;
+    static constexpr int kWStagesRaw = (kSmemBudget - kXSlots * kXStage) / kWStage;
     static constexpr int kWStages = (kWStagesRaw > 24 ? 24 : kWStagesRaw) & ~1;   // W ring depth (even: two producer warps alternate)
-    static constexpr int kWOffset = kSlots * kXStage;
+    static constexpr int kWOffset = kXSlots * kXStage;
     static constexpr int kBarOffset = kWOffset + kWStages * kWStage;
-    static constexpr int kNumBars = 2 * kWStages + 3 * kSlots + 2 * kAccStages;
+    static constexpr int kNumBars = 2 * kWStages + 2 * kXSlots + 2 * kSlots + 2 * kAccStages;
     static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;     // + tmem slot + alignment slack
     static_assert(kXStage % 1024 == 0 && kWStage % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned stages");
     static_assert(!I8 || KBS == 2, "int8 mode: one 128-byte-row tile per stage = two k-blocks");
     static_assert(kSlots >= NDQ, "XA ring must have at least as many slots as dequant groups");
-    static_assert(kWStages >= kSlots, "W ring must be at least as deep as the XA ring");
+    static_assert(kWStages >= kSlots, "W ring must be at least as deep as the A ring");
+    static_assert(kTotal <= 227 * 1024, "shared memory over-subscribed");
     static_assert(kAccStages * NTOK + kSlots * kSlotCols <= kTmemCols, "TMEM over-subscribed");
 };
 
-template <int CB, int NTOK, int KBS, int NDQ, bool I8>
-__global__ void __launch_bounds__((8 + 4 * NDQ) * 32, 1)
-umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
-    using C = Cfg<CB, NTOK, KBS, NDQ, I8>;
+template <int CB, int NTOK, int KBS, int NDQ, bool I8, bool PAIR>
+__device__ __forceinline__ void umma_qlinear_body(const CUtensorMap &tmap_x, const UmmaArgs &a) {
+    using C = Cfg<CB, NTOK, KBS, NDQ, I8, PAIR>;
     constexpr int kACols = C::kACols;
-    constexpr int SW = C::kWStages, A = C::kSlots;
+    static_assert(!PAIR || !I8, "the CTA-pair variant exists for the bf16 mode only");
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                 // 0 = leader: issues the MMAs
+    const uint32_t n_pairs = (a.n_tiles + 1) / 2;
+    // column / token tile of an item.  Pair mode: this CTA's column tile is 2 * pair + rank; an odd tile count leaves the
+    // last pair's second CTA without columns: it loads the last real tile again and its epilogue stores nothing
+    // Tile order: groups of kRasterM token tiles, column-tile-major inside a group, so that the CTAs running at the same
+    // time spread over ~kRasterM token tiles x ~10 column tiles.  (Column-tile-minor order made all SMs read the same
+    // activation lines at the same moment: the TMA latency of an activation stage was ~1.3 us, L2 hot-spotting.)
+    constexpr uint32_t kRasterM = 16;
+    const uint32_t n_cols = PAIR ? n_pairs : a.n_tiles;                   // column tiles (or pairs of them) per token tile
+    auto decode = [&](uint32_t tile, uint32_t &mt, uint32_t &nc) {
+        if (a.stream_k) { mt = tile / n_cols; nc = tile % n_cols; return; }
+        const uint32_t grp = tile / (kRasterM * n_cols), r = tile - grp * (kRasterM * n_cols);
+        const uint32_t left = a.m_tiles - grp * kRasterM, gsz = left < kRasterM ? left : kRasterM;
+        nc = r / gsz; mt = grp * kRasterM + (r - nc * gsz);
+    };
+    auto tile_mt = [&](const Item &it) -> uint32_t { uint32_t mt, nc; decode(it.tile, mt, nc); return mt; };
+    auto tile_nt = [&](const Item &it) -> uint32_t { uint32_t mt, nc; decode(it.tile, mt, nc); return PAIR ? 2 * nc + rank : nc; };
+    constexpr int SW = C::kWStages, A = C::kSlots, X = C::kXSlots;
     constexpr int kEpiWarp0 = 4 + 4 * NDQ;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_w = smem + C::kWOffset;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kBarOffset);
     uint64_t *wfull = bars, *wempty = bars + SW;                     // W ring
-    uint64_t *xfull = bars + 2 * SW, *xaempty = xfull + A, *afull = xaempty + A;   // XA ring
-    uint64_t *tfull = afull + A, *tempty = tfull + kAccStages;       // accumulators
+    uint64_t *xfull = bars + 2 * SW, *xempty = xfull + X;             // activation ring (shared memory)
+    uint64_t *afull = xempty + X, *aempty = afull + A;               // A ring (tensor memory)
+    uint64_t *tfull = aempty + A, *tempty = tfull + kAccStages;      // accumulators
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kAccStages);
 
     // warp index via shuffle: provably warp-uniform, so the role branches below are uniform branches
@@ -410,12 +495,19 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
+        // pair mode: afull / tempty of the LEADER collect the dequant / epilogue warps of both CTAs
         for (int s = 0; s < SW; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 4); }
-        for (int s = 0; s < A; ++s) { mbar_init(xfull + s, 1); mbar_init(xaempty + s, 1); mbar_init(afull + s, 4); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        for (int s = 0; s < X; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); }
+        for (int s = 0; s < A; ++s) { mbar_init(afull + s, PAIR ? 8 : 4); mbar_init(aempty + s, 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, PAIR ? 8 : 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    if constexpr (PAIR) {
+        cluster_sync_all();                                // barriers of both CTAs exist before anybody signals them
+        if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
+    } else {
+        if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -425,19 +517,24 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
 
     if (warp == 0) {
         // ===================== activation producer (warp-converged; one elected lane issues TMA) =====================
-        ItemIter iter(a);
+        ItemIter iter(a, PAIR);
         Item item;
         uint32_t it = 0;                               // stage counter of this CTA
+        const uint32_t xfull_leader = PAIR ? leader_addr(xfull) : 0u;
         while (iter.next(item)) {
-            const uint32_t mt = item.tile / a.n_tiles;
+            const uint32_t mt = tile_mt(item);
             for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
                 const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
-                const uint32_t s = it % A, ph = (it / A) & 1;
-                mbar_wait(xaempty + s, ph ^ 1);
+                const uint32_t s = it % X, ph = (it / X) & 1;
+                mbar_wait(xempty + s, ph ^ 1);
                 if (elect_one()) {
                     TRACE(0, it);
                     uint8_t *stage = smem + s * C::kXStage;
-                    if constexpr (I8) {
+                    if constexpr (PAIR) {
+                        // this CTA's half of the tokens; the leader's barrier expects the bytes of both halves
+                        if (rank == 0) mbar_arrive_expect_tx(xfull + s, 2 * KBS * C::kXBytes);
+                        tma_load_3d_pair(stage, &tmap_x, xfull_leader + s * 8, 0, (int)(mt * NTOK + rank * (NTOK / 2)), (int)kb);
+                    } else if constexpr (I8) {
                         // int8: one box {128 k, NTOK tokens} = both k-blocks of the stage; k past K is zero-filled
                         mbar_arrive_expect_tx(xfull + s, KBS * C::kXBytes);
                         tma_load_2d(stage, &tmap_x, xfull + s, (int)(kb * WL_TILE_K), (int)(mt * NTOK));
@@ -461,11 +558,11 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
     } else if (warp == 2 || warp == 3) {
         // ===================== weight producers (two warps alternate stages; they run ahead through the deep W ring) =====================
         const uint32_t me = (uint32_t)(warp - 2);
-        ItemIter iter(a);
+        ItemIter iter(a, PAIR);
         Item item;
         uint32_t it = 0;
         while (iter.next(item)) {
-            const uint32_t nt = item.tile % a.n_tiles;
+            const uint32_t nt = tile_nt(item) < a.n_tiles ? tile_nt(item) : a.n_tiles - 1;
             const uint8_t *wsrc = a.packed + ((size_t)nt * a.k_blocks) * C::kWBytes;
             const uint2 *psrc = a.dqparams + (size_t)nt * 128;
             for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
@@ -486,10 +583,10 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 __syncwarp();
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (warp-converged; one elected lane issues) =====================
-        constexpr uint32_t idesc = I8 ? make_idesc_i8(NTOK) : make_idesc(NTOK);
-        ItemIter iter(a);
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (warp-converged; one elected lane issues; pair mode: the leader CTA only) =====================
+        constexpr uint32_t idesc = I8 ? make_idesc_i8(NTOK) : (PAIR ? make_idesc_pair(NTOK) : make_idesc(NTOK));
+        ItemIter iter(a, PAIR);
         Item item;
         uint32_t it = 0, n_item = 0;
         while (iter.next(item)) {
@@ -503,16 +600,17 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
             bool ready = false;
             for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
                 const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
-                const uint32_t s = it % A, ph = (it / A) & 1;
+                const uint32_t s = it % X, ph = (it / X) & 1;          // activation stage
+                const uint32_t sa = it % A, pha = (it / A) & 1;        // A slot
                 if (!ready) {
                     if (lane == 0) TRACE(1, it);
                     mbar_wait(xfull + s, ph);      // activation tiles landed
-                    mbar_wait(afull + s, ph);      // A slot written to TMEM
+                    mbar_wait(afull + sa, pha);    // A slot written to TMEM
                     tc_fence_after();
                 }
                 if (lane == 0) TRACE(3, it);
                 const uint32_t stage_addr = smem_u32(smem + s * C::kXStage);
-                const uint32_t a_tmem = tmem_base + a_col0 + s * C::kSlotCols;
+                const uint32_t a_tmem = tmem_base + a_col0 + sa * C::kSlotCols;
                 const bool first = kb == item.kb0;
                 if (elect_one() && !(a.dbg & 1)) {             // k-block 0 of the stage
                     const uint64_t bdesc = make_b_desc(stage_addr);
@@ -521,6 +619,10 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
 #pragma unroll
                         for (int k2 = 0; k2 < 2; ++k2)
                             umma_ts_i8(d_tmem, a_tmem + k2 * 8, bdesc + (uint64_t)(k2 * 2), idesc, (!first || k2 > 0) ? 1u : 0u);
+                    } else if constexpr (PAIR) {
+#pragma unroll
+                        for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                            umma_ts_pair(d_tmem, a_tmem + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (!first || k4 > 0) ? 1u : 0u);
                     } else {
 #pragma unroll
                         for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
@@ -529,10 +631,11 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 }
                 __syncwarp();
                 ready = false;
-                if (kb + KBS < item.kb1) {                     // peek at the next stage while those MMAs run
-                    const uint32_t s2 = (it + 1) % A, ph2 = ((it + 1) / A) & 1;
+                if (kb + KBS < item.kb1 && !(a.dbg & 16)) {    // peek at the next stage while those MMAs run
+                    const uint32_t s2 = (it + 1) % X, ph2 = ((it + 1) / X) & 1;
+                    const uint32_t sa2 = (it + 1) % A, pha2 = ((it + 1) / A) & 1;
                     mbar_wait(xfull + s2, ph2);
-                    mbar_wait(afull + s2, ph2);
+                    mbar_wait(afull + sa2, pha2);
                     tc_fence_after();
                     ready = true;
                 }
@@ -546,15 +649,19 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                         } else {
                             const uint64_t bdesc = make_b_desc(stage_addr + sub * C::kXBytes);
 #pragma unroll
-                            for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
-                                umma_ts(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, 1u);
+                            for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4) {
+                                if constexpr (PAIR) umma_ts_pair(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, 1u);
+                                else umma_ts(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, 1u);
+                            }
                         }
                     }
-                    umma_commit(xaempty + s);      // frees the activation stage and the TMEM A slot
+                    // frees the activation stage and the TMEM A slot (pair mode: in both CTAs)
+                    if constexpr (PAIR) { umma_commit_pair(xempty + s); umma_commit_pair(aempty + sa); }
+                    else { umma_commit(xempty + s); umma_commit(aempty + sa); }
                 }
                 __syncwarp();
             }
-            if (elect_one()) umma_commit(tfull + acc);
+            if (elect_one()) { if constexpr (PAIR) umma_commit_pair(tfull + acc); else umma_commit(tfull + acc); }
             __syncwarp();
         }
     } else if (warp >= 4 && warp < kEpiWarp0) {
@@ -563,9 +670,10 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
         const int quarter = warp & 3;             // TMEM lanes [32*quarter, +32)
         const int n_local = quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0;
-        ItemIter iter(a);
+        ItemIter iter(a, PAIR);
         Item item;
         uint32_t it = 0;
+        const uint32_t afull_leader = PAIR ? leader_addr(afull) : 0u;
         while (iter.next(item)) {
             for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
                 if (it % NDQ != grp) continue;    // group g owns the stages with it % NDQ == g
@@ -573,7 +681,7 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 const uint32_t sw = it % SW, wph = (it / SW) & 1;
                 const uint32_t sl = it % A, aph = (it / A) & 1;
                 // 1. previous user of the TMEM slot, MMA(it - A), completed; 2. this stage's weights landed
-                if (it >= (uint32_t)A) mbar_wait(xaempty + sl, aph ^ 1);
+                if (it >= (uint32_t)A) mbar_wait(aempty + sl, aph ^ 1);
                 mbar_wait(wfull + sw, wph);
                 tc_fence_after();
                 if (quarter == 0 && lane == 0) TRACE(4, it);
@@ -599,18 +707,19 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(afull + sl);
+                if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(afull_leader + sl * 8); else mbar_arrive(afull + sl); }
                 if (quarter == 0 && lane == 0) TRACE(5, it);
             }
         }
     } else if (warp >= kEpiWarp0) {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;
-        ItemIter iter(a);
+        ItemIter iter(a, PAIR);
         Item item;
         uint32_t n_item = 0;
+        const uint32_t tempty_leader = PAIR ? leader_addr(tempty) : 0u;
         while (iter.next(item)) {
-            const uint32_t nt = item.tile % a.n_tiles, mt = item.tile / a.n_tiles;
+            const uint32_t nt = tile_nt(item), mt = tile_mt(item);
             const uint32_t acc = n_item % kAccStages, aph = (n_item / kAccStages) & 1;
             ++n_item;
             const uint32_t n = nt * 128 + quarter * 32 + lane;
@@ -633,7 +742,7 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 if (c0 + CH >= NTOK) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty + acc);
+                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(tempty_leader + acc * 8); else mbar_arrive(tempty + acc); }
                 }
                 const uint32_t m_base = mt * NTOK + c0;
                 if constexpr (I8) {
@@ -670,10 +779,31 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (PAIR) {
+        cluster_sync_all();                                // the partner may still signal barriers / read shared memory of this CTA
+        if (warp == 1) {
+            tc_fence_after();
+            tmem_dealloc_pair(tmem_base, kTmemCols);
+        }
+    } else {
+        if (warp == 1) {
+            tc_fence_after();
+            tmem_dealloc(tmem_base, kTmemCols);
+        }
     }
+}
+
+template <int CB, int NTOK, int KBS, int NDQ, bool I8>
+__global__ void __launch_bounds__((8 + 4 * NDQ) * 32, 1)
+umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
+    umma_qlinear_body<CB, NTOK, KBS, NDQ, I8, false>(tmap_x, a);
+}
+
+// the CTA-pair variant (bf16 mode, whole tiles): a cluster of two CTAs per (token tile, pair of column tiles)
+template <int CB, int NTOK, int KBS, int NDQ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((8 + 4 * NDQ) * 32, 1)
+umma_qlinear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
+    umma_qlinear_body<CB, NTOK, KBS, NDQ, false, true>(tmap_x, a);
 }
 
 // stream-K fix-up: tiles that were cut by a CTA boundary get y = sum of their partial tiles (in CTA
@@ -783,9 +913,28 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         DLLM_TRY(ensure_buf(ctx, ctx->lin_ws, (size_t)2 * grid * NTOK * 128 * sizeof(float)));
         a.partial = (float *)ctx->lin_ws.p;
     }
+    // CTA pairs (cta_group::2) for dense problems: two CTAs share every activation tile (half the L2 -> SM activation
+    // traffic per SM, which is what bounds the 1-CTA kernel: ~10 TB/s of L2 reads at 8192 tokens)
+    static const int pair_env = getenv("DLLM_UMMA_PAIR") ? atoi(getenv("DLLM_UMMA_PAIR")) : 0;
+    const uint32_t n_pairs = (a.n_tiles + 1) / 2;
+    const bool use_pair = pair_env != 0 && NTOK == 128 && !a.stream_k && x3d && !(a.dbg & 128) && n_pairs * a.m_tiles >= sms / 2;
+    using CP = Cfg<CB, NTOK, KBS, NDQ, false, true>;
+    CUtensorMap tmap_pair;
+    if (use_pair) {
+        const cuuint64_t gdim[3] = {WL_TILE_K, (cuuint64_t)M, (cuuint64_t)(qw->K / WL_TILE_K)};
+        const cuuint64_t gstride[2] = {(cuuint64_t)qw->K * 2, (cuuint64_t)WL_TILE_K * 2};
+        const cuuint32_t box[3] = {WL_TILE_K, (cuuint32_t)(NTOK / 2), (cuuint32_t)KBS};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        r = enc(&tmap_pair, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(x_bf16), gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, KBS, NDQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+        if (NTOK == 128)
+            CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_pair_kernel<CB, NTOK, KBS, NDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, CP::kTotal));
         attr_set = true;
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -799,7 +948,13 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
         CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    umma_qlinear_kernel<CB, NTOK, KBS, NDQ, false><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
+    if (use_pair) {
+        const uint32_t pair_tiles = n_pairs * a.m_tiles;
+        const uint32_t pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+        umma_qlinear_pair_kernel<CB, NTOK, KBS, NDQ><<<2 * pairs, (8 + 4 * NDQ) * 32, CP::kTotal, ctx->stream>>>(tmap_pair, a);
+    } else {
+        umma_qlinear_kernel<CB, NTOK, KBS, NDQ, false><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
+    }
     LAUNCH_CHECK(ctx);
     if (ev1) {
         CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));

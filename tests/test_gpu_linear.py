@@ -428,3 +428,22 @@ def test_qlinear_umma_vs_simt_full_width(ctx):
     ctx.sync()
     assert torch.equal(y3, y1 * 2)
     qw.close()
+
+
+def test_umma_cta_pair_variant_is_bit_identical():
+    """The CTA-pair (tcgen05 cta_group::2) variant of the dense kernel — opt-in with DLLM_UMMA_PAIR=1 — must produce the
+    1-CTA kernel's output bit for bit on a dense, ragged shape with an odd number of column tiles."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    script = os.path.join(os.path.dirname(__file__), "umma_pair_check.py")
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for pair in ("0", "1"):
+            out = os.path.join(d, f"y{pair}.npy")
+            env = dict(os.environ, DLLM_UMMA_PAIR=pair)
+            r = subprocess.run([sys.executable, script, out], capture_output=True, text=True, timeout=300, env=env)
+            assert "PAIR_CHECK_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+            outs.append(np.load(out))
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))

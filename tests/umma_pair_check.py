@@ -1,0 +1,32 @@
+"""Parity of the CTA-pair (cta_group::2) variant of the tcgen05 kernel on a dense shape (run with DLLM_UMMA_PAIR=1):
+the output must equal the 1-CTA kernel's bit for bit (same k order, same accumulation) and match the f64 reference."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "diffusion-llm-rs_b200"))
+import numpy as np
+import torch
+import dllm_b200
+from dllm_b200 import QWeight, PATH_UMMA
+
+ctx = dllm_b200.Context(0)
+g = torch.Generator(device="cuda").manual_seed(7)
+K, N, M = 384, 7000, 1300            # 55 column tiles (odd: the last pair is half empty; ragged N), 11 token tiles (ragged): dense mode
+w = torch.randn(K, N, device="cuda", generator=g) * 0.02
+x = torch.randn(M, K, device="cuda", generator=g)
+y = torch.empty(M, N, device="cuda")
+torch.cuda.synchronize()
+qw = QWeight.quantize_dev(ctx, w.data_ptr(), K, N, 4, 128)
+qw.forward_dev(x.data_ptr(), M, y.data_ptr(), PATH_UMMA)
+ctx.sync()
+codes, scales, zps = qw.export()
+wd = (torch.from_numpy(codes.astype(np.float64)) - torch.from_numpy(np.repeat(zps, 128, axis=0).astype(np.float64))) * \
+    torch.from_numpy(np.repeat(scales, 128, axis=0).astype(np.float64))
+ref = x.cpu().double() @ wd
+err = (y.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+assert err <= 1e-2, err
+out = sys.argv[1] if len(sys.argv) > 1 else None
+if out:
+    np.save(out, y.cpu().numpy())
+print(f"PAIR_CHECK_OK pair={os.environ.get('DLLM_UMMA_PAIR', '0')} rel_err={err:.2e}")
