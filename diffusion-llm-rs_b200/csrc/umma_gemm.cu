@@ -986,9 +986,12 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
 // two k-blocks (128 k = one quantization group) per pipeline stage
 template <int CB>
 int32_t launch_umma_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const void *x, size_t M, float *y_f32, void *y_bf16) {
+    static const int ntok_env = getenv("DLLM_UMMA_NTOK") ? atoi(getenv("DLLM_UMMA_NTOK")) : 0;     // experiments only
     if (M <= 16) return launch_umma<CB, 16, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
     if (M <= 32) return launch_umma<CB, 32, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
-    if (M <= 64) return launch_umma<CB, 64, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    if (M <= 64 || ntok_env == 64) return launch_umma<CB, 64, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
+    static const int kbs_env = getenv("DLLM_UMMA_KBS") ? atoi(getenv("DLLM_UMMA_KBS")) : 0;         // experiments only
+    if (kbs_env == 1) return launch_umma<CB, 128, 1, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
     return launch_umma<CB, 128, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
 }
 
