@@ -456,6 +456,268 @@ struct Cfg {
     static_assert(kAccStages * NTOK + kSlots * kSlotCols <= kTmemCols, "TMEM over-subscribed");
 };
 
+// ------------------------------------------------------------------------------------------
+// The bf16 kernel of the denoise step (the headline path).  It is kept as its own function, textually apart from the
+// generalized body below (int8 mode, CTA pairs, separate activation / A rings): folding those variants into one template
+// cost this instance ~4 % of the step rate through different register allocation and scheduling (measured A/B on one box:
+// 55.7 vs 53.5 steps/s), although every added branch was `if constexpr`.
+// ------------------------------------------------------------------------------------------
+template <int CB, int NTOK, int KBS, int NDQ>
+__global__ void __launch_bounds__((8 + 4 * NDQ) * 32, 1)
+umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
+    using C = Cfg<CB, NTOK, KBS, NDQ>;
+    constexpr int kACols = C::kACols;
+    constexpr int SW = C::kWStages, A = C::kSlots;
+    constexpr int kEpiWarp0 = 4 + 4 * NDQ;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_w = smem + C::kWOffset;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kBarOffset);
+    uint64_t *wfull = bars, *wempty = bars + SW;                     // W ring
+    uint64_t *xfull = bars + 2 * SW, *xaempty = xfull + A, *afull = xaempty + A;   // XA ring
+    uint64_t *tfull = afull + A, *tempty = tfull + kAccStages;       // accumulators
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kAccStages);
+
+    // warp index via shuffle: provably warp-uniform, so the role branches below are uniform branches
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        for (int s = 0; s < SW; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 4); }
+        for (int s = 0; s < A; ++s) { mbar_init(xfull + s, 1); mbar_init(xaempty + s, 1); mbar_init(afull + s, 4); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_col0 = 0;                          // kAccStages x NTOK accumulator columns
+    const uint32_t a_col0 = kAccStages * NTOK;            // then A slots of KBS x 32 columns
+
+    if (warp == 0) {
+        // ===================== activation producer (warp-converged; one elected lane issues TMA) =====================
+        ItemIter iter(a);
+        Item item;
+        uint32_t it = 0;                               // stage counter of this CTA
+        while (iter.next(item)) {
+            const uint32_t mt = item.tile / a.n_tiles;
+            for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                const uint32_t s = it % A, ph = (it / A) & 1;
+                mbar_wait(xaempty + s, ph ^ 1);
+                if (elect_one()) {
+                    TRACE(0, it);
+                    uint8_t *stage = smem + s * C::kXStage;
+                    if (!(a.dbg & 8)) {
+                        if (a.x3d) {
+                            // one TMA for all KBS k-blocks: box {64 k, NTOK tokens, KBS k-blocks}; k-blocks past K are zero-filled
+                            mbar_arrive_expect_tx(xfull + s, KBS * C::kXBytes);
+                            tma_load_3d(stage, &tmap_x, xfull + s, 0, (int)(mt * NTOK), (int)kb);
+                        } else {
+                            mbar_arrive_expect_tx(xfull + s, nk * C::kXBytes);
+                            for (uint32_t sub = 0; sub < nk; ++sub)
+                                tma_load_2d(stage + sub * C::kXBytes, &tmap_x, xfull + s, (int)((kb + sub) * WL_TILE_K), (int)(mt * NTOK));
+                        }
+                    } else {
+                        mbar_arrive(xfull + s);        // timing experiment: no activation traffic
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===================== weight producers (two warps alternate stages; they run ahead through the deep W ring) =====================
+        const uint32_t me = (uint32_t)(warp - 2);
+        ItemIter iter(a);
+        Item item;
+        uint32_t it = 0;
+        while (iter.next(item)) {
+            const uint32_t nt = item.tile % a.n_tiles;
+            const uint8_t *wsrc = a.packed + ((size_t)nt * a.k_blocks) * C::kWBytes;
+            const uint2 *psrc = a.dqparams + (size_t)nt * 128;
+            for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                if ((it & 1) != me) continue;
+                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                const uint32_t s = it % SW, ph = (it / SW) & 1;
+                mbar_wait(wempty + s, ph ^ 1);
+                if (elect_one()) {
+                    TRACE(2, it);                      // weight producer: W stage free, issuing loads
+                    uint8_t *stage = smem_w + s * C::kWStage;
+                    mbar_arrive_expect_tx(wfull + s, nk * (C::kWBytes + C::kPBytes));
+                    bulk_load(stage, wsrc + (size_t)kb * C::kWBytes, nk * C::kWBytes, wfull + s);
+                    for (uint32_t sub = 0; sub < nk; ++sub) {
+                        const uint32_t g = (kb + sub) / a.group_kb;
+                        bulk_load(stage + KBS * C::kWBytes + sub * C::kPBytes, psrc + (size_t)g * a.Npad, C::kPBytes, wfull + s);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-converged; one elected lane issues) =====================
+        constexpr uint32_t idesc = make_idesc(NTOK);
+        ItemIter iter(a);
+        Item item;
+        uint32_t it = 0, n_item = 0;
+        while (iter.next(item)) {
+            const uint32_t acc = n_item % kAccStages, aph = (n_item / kAccStages) & 1;
+            ++n_item;
+            mbar_wait(tempty + acc, aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc_col0 + acc * NTOK;
+            // Software-pipelined: the barriers of stage it+1 are polled after the first k-block of stage `it`
+            // has been issued, so the tensor pipe never drains while this warp sits in a try_wait.
+            bool ready = false;
+            for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                const uint32_t s = it % A, ph = (it / A) & 1;
+                if (!ready) {
+                    if (lane == 0) TRACE(1, it);
+                    mbar_wait(xfull + s, ph);      // activation tiles landed
+                    mbar_wait(afull + s, ph);      // A slot written to TMEM
+                    tc_fence_after();
+                }
+                if (lane == 0) TRACE(3, it);
+                const uint32_t stage_addr = smem_u32(smem + s * C::kXStage);
+                const uint32_t a_tmem = tmem_base + a_col0 + s * C::kSlotCols;
+                const bool first = kb == item.kb0;
+                if (elect_one() && !(a.dbg & 1)) {             // k-block 0 of the stage
+                    const uint64_t bdesc = make_b_desc(stage_addr);
+#pragma unroll
+                    for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                        umma_ts(d_tmem, a_tmem + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (!first || k4 > 0) ? 1u : 0u);
+                }
+                __syncwarp();
+                ready = false;
+                if (kb + KBS < item.kb1) {                     // peek at the next stage while those MMAs run
+                    const uint32_t s2 = (it + 1) % A, ph2 = ((it + 1) / A) & 1;
+                    mbar_wait(xfull + s2, ph2);
+                    mbar_wait(afull + s2, ph2);
+                    tc_fence_after();
+                    ready = true;
+                }
+                if (elect_one()) {
+                    for (uint32_t sub = 1; sub < nk && !(a.dbg & 1); ++sub) {
+                        const uint64_t bdesc = make_b_desc(stage_addr + sub * C::kXBytes);
+#pragma unroll
+                        for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                            umma_ts(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, 1u);
+                    }
+                    umma_commit(xaempty + s);      // frees the activation stage and the TMEM A slot
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(tfull + acc);
+            __syncwarp();
+        }
+    } else if (warp >= 4 && warp < kEpiWarp0) {
+        // ===================== dequant warps =====================
+        const uint32_t grp = (uint32_t)(warp - 4) >> 2;
+        const int quarter = warp & 3;             // TMEM lanes [32*quarter, +32)
+        const int n_local = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0;
+        ItemIter iter(a);
+        Item item;
+        uint32_t it = 0;
+        while (iter.next(item)) {
+            for (uint32_t kb = item.kb0; kb < item.kb1; kb += KBS, ++it) {
+                if (it % NDQ != grp) continue;    // group g owns the stages with it % NDQ == g
+                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                const uint32_t sw = it % SW, wph = (it / SW) & 1;
+                const uint32_t sl = it % A, aph = (it / A) & 1;
+                // 1. previous user of the TMEM slot, MMA(it - A), completed; 2. this stage's weights landed
+                if (it >= (uint32_t)A) mbar_wait(xaempty + sl, aph ^ 1);
+                mbar_wait(wfull + sw, wph);
+                tc_fence_after();
+                if (quarter == 0 && lane == 0) TRACE(4, it);
+                const uint8_t *stage = smem_w + sw * C::kWStage;
+                for (uint32_t sub = 0; sub < nk; ++sub) {
+                    const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes);
+                    const uint2 prm = reinterpret_cast<const uint2 *>(stage + KBS * C::kWBytes + sub * C::kPBytes)[n_local];
+                    uint32_t vals[32];
+                    if (!(a.dbg & 2)) dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) vals[q] = prm.x + q;
+                    }
+                    if (!(a.dbg & 4)) tmem_st32(lane_addr + sl * C::kSlotCols + sub * kACols, vals);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(wempty + sw);   // all smem reads of this warp are done (values are in registers)
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull + sl);
+                if (quarter == 0 && lane == 0) TRACE(5, it);
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;
+        ItemIter iter(a);
+        Item item;
+        uint32_t n_item = 0;
+        while (iter.next(item)) {
+            const uint32_t nt = item.tile % a.n_tiles, mt = item.tile / a.n_tiles;
+            const uint32_t acc = n_item % kAccStages, aph = (n_item / kAccStages) & 1;
+            ++n_item;
+            const uint32_t n = nt * 128 + quarter * 32 + lane;
+            const bool n_ok = n < a.N;
+            const bool direct = item.slot < 0;
+            const float bias = (direct && a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
+            float *part = direct ? nullptr : a.partial + (size_t)item.slot * (NTOK * 128) + quarter * 32 + lane;
+            mbar_wait(tfull + acc, aph);
+            tc_fence_after();
+            if (quarter == 0 && lane == 0) TRACE(6, n_item - 1);   // epilogue: accumulator ready (indexed by item)
+            const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col0 + acc * NTOK;
+            // wide TMEM loads (few round trips: tcgen05.ld competes with the MMA's accumulator traffic), and the
+            // accumulator is handed back to the MMA warp as soon as its last column is in registers
+            constexpr int CH = NTOK >= 64 ? 64 : NTOK;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NTOK; c0 += CH) {
+                uint32_t v[CH];
+                tmem_ld_chunk<CH>(t_acc + c0, v);
+                tmem_ld_wait();
+                if (c0 + CH >= NTOK) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty + acc);
+                }
+                const uint32_t m_base = mt * NTOK + c0;
+                if (direct) {
+                    if (!n_ok || (a.dbg & 64)) continue;
+                    if (a.y_f32) {
+                        float *yp = a.y_f32 + (size_t)m_base * a.N + n;
+#pragma unroll
+                        for (int j = 0; j < CH; ++j)
+                            if (m_base + j < a.M) yp[(size_t)j * a.N] = __uint_as_float(v[j]) + bias;
+                    }
+                    if (a.y_bf16) {
+                        __nv_bfloat16 *yp = a.y_bf16 + (size_t)m_base * a.N + n;
+#pragma unroll
+                        for (int j = 0; j < CH; ++j)
+                            if (m_base + j < a.M) yp[(size_t)j * a.N] = __float2bfloat16_rn(__uint_as_float(v[j]) + bias);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) part[(size_t)(c0 + j) * 128] = __uint_as_float(v[j]);
+                }
+            }
+            if (quarter == 0 && lane == 0) TRACE(7, n_item - 1);   // epilogue: accumulator released
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+
 template <int CB, int NTOK, int KBS, int NDQ, bool I8, bool PAIR>
 __device__ __forceinline__ void umma_qlinear_body(const CUtensorMap &tmap_x, const UmmaArgs &a) {
     using C = Cfg<CB, NTOK, KBS, NDQ, I8, PAIR>;
@@ -465,13 +727,14 @@ __device__ __forceinline__ void umma_qlinear_body(const CUtensorMap &tmap_x, con
     const uint32_t n_pairs = (a.n_tiles + 1) / 2;
     // column / token tile of an item.  Pair mode: this CTA's column tile is 2 * pair + rank; an odd tile count leaves the
     // last pair's second CTA without columns: it loads the last real tile again and its epilogue stores nothing
-    // Tile order: groups of kRasterM token tiles, column-tile-major inside a group, so that the CTAs running at the same
-    // time spread over ~kRasterM token tiles x ~10 column tiles.  (Column-tile-minor order made all SMs read the same
-    // activation lines at the same moment: the TMA latency of an activation stage was ~1.3 us, L2 hot-spotting.)
+    // Tile order: column-tile-minor (CTAs running together share a token tile's activations).  DLLM_UMMA_DBG bit 32 selects a
+    // rasterized order instead (groups of kRasterM token tiles, column-tile-major inside a group: the CTAs spread over
+    // ~16 token tiles x ~10 column tiles) — measured: no difference, so L2 hot-spotting is not what makes an activation
+    // stage take ~1.3 us from TMA issue to arrival.
     constexpr uint32_t kRasterM = 16;
     const uint32_t n_cols = PAIR ? n_pairs : a.n_tiles;                   // column tiles (or pairs of them) per token tile
     auto decode = [&](uint32_t tile, uint32_t &mt, uint32_t &nc) {
-        if (a.stream_k) { mt = tile / n_cols; nc = tile % n_cols; return; }
+        if (a.stream_k || !(a.dbg & 32)) { mt = tile / n_cols; nc = tile % n_cols; return; }
         const uint32_t grp = tile / (kRasterM * n_cols), r = tile - grp * (kRasterM * n_cols);
         const uint32_t left = a.m_tiles - grp * kRasterM, gsz = left < kRasterM ? left : kRasterM;
         nc = r / gsz; mt = grp * kRasterM + (r - nc * gsz);
@@ -486,8 +749,10 @@ __device__ __forceinline__ void umma_qlinear_body(const CUtensorMap &tmap_x, con
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kBarOffset);
     uint64_t *wfull = bars, *wempty = bars + SW;                     // W ring
     uint64_t *xfull = bars + 2 * SW, *xempty = xfull + X;             // activation ring (shared memory)
-    uint64_t *afull = xempty + X, *aempty = afull + A;               // A ring (tensor memory)
-    uint64_t *tfull = aempty + A, *tempty = tfull + kAccStages;      // accumulators
+    // A ring (tensor memory).  While both rings have the same depth one barrier (and one tcgen05.commit per stage) frees the
+    // activation stage and the A slot together: a second commit per stage costs ~3 % of the step rate (measured)
+    uint64_t *afull = xempty + X, *aempty = (X == A) ? xempty : afull + A;
+    uint64_t *tfull = afull + 2 * A, *tempty = tfull + kAccStages;   // accumulators (after the A ring's own `empty` barriers, used or not)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kAccStages);
 
     // warp index via shuffle: provably warp-uniform, so the role branches below are uniform branches
@@ -498,7 +763,7 @@ __device__ __forceinline__ void umma_qlinear_body(const CUtensorMap &tmap_x, con
         // pair mode: afull / tempty of the LEADER collect the dequant / epilogue warps of both CTAs
         for (int s = 0; s < SW; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 4); }
         for (int s = 0; s < X; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); }
-        for (int s = 0; s < A; ++s) { mbar_init(afull + s, PAIR ? 8 : 4); mbar_init(aempty + s, 1); }
+        for (int s = 0; s < A; ++s) { mbar_init(afull + s, PAIR ? 8 : 4); if (X != A) mbar_init(aempty + s, 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, PAIR ? 8 : 4); }
         fence_barrier_init();
     }
@@ -656,8 +921,8 @@ __device__ __forceinline__ void umma_qlinear_body(const CUtensorMap &tmap_x, con
                         }
                     }
                     // frees the activation stage and the TMEM A slot (pair mode: in both CTAs)
-                    if constexpr (PAIR) { umma_commit_pair(xempty + s); umma_commit_pair(aempty + sa); }
-                    else { umma_commit(xempty + s); umma_commit(aempty + sa); }
+                    if constexpr (PAIR) { umma_commit_pair(xempty + s); if constexpr (X != A) umma_commit_pair(aempty + sa); }
+                    else { umma_commit(xempty + s); if constexpr (X != A) umma_commit(aempty + sa); }
                 }
                 __syncwarp();
             }
@@ -793,9 +1058,10 @@ __device__ __forceinline__ void umma_qlinear_body(const CUtensorMap &tmap_x, con
     }
 }
 
+// the generalized body as a 1-CTA kernel (used by the int8 mode)
 template <int CB, int NTOK, int KBS, int NDQ, bool I8>
 __global__ void __launch_bounds__((8 + 4 * NDQ) * 32, 1)
-umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
+umma_qlinear_x_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
     umma_qlinear_body<CB, NTOK, KBS, NDQ, I8, false>(tmap_x, a);
 }
 
@@ -932,7 +1198,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     }
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, KBS, NDQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, KBS, NDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
         if (NTOK == 128)
             CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_pair_kernel<CB, NTOK, KBS, NDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, CP::kTotal));
         attr_set = true;
@@ -953,7 +1219,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         const uint32_t pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
         umma_qlinear_pair_kernel<CB, NTOK, KBS, NDQ><<<2 * pairs, (8 + 4 * NDQ) * 32, CP::kTotal, ctx->stream>>>(tmap_pair, a);
     } else {
-        umma_qlinear_kernel<CB, NTOK, KBS, NDQ, false><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
+        umma_qlinear_kernel<CB, NTOK, KBS, NDQ><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
     }
     LAUNCH_CHECK(ctx);
     if (ev1) {
@@ -1046,7 +1312,7 @@ int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, 
     const uint32_t grid = tiles < sms ? tiles : sms;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, KBS, NDQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_x_kernel<CB, NTOK, KBS, NDQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
         attr_set = true;
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1060,7 +1326,7 @@ int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, 
         ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
         CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    umma_qlinear_kernel<CB, NTOK, KBS, NDQ, true><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
+    umma_qlinear_x_kernel<CB, NTOK, KBS, NDQ, true><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
     LAUNCH_CHECK(ctx);
     if (ev1) {
         CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
