@@ -260,6 +260,16 @@ __device__ __forceinline__ uint32_t bf2_sub_mul(uint32_t a, uint32_t zb, uint32_
     return *reinterpret_cast<uint32_t *>(&r);
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
 // (a & mask) | magic in ONE LOP3 (with two immediates the compiler emits two; +3.5% on the whole denoise step)
 __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t magic) {
     uint32_t d;
@@ -270,12 +280,13 @@ __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t m
 template <int CB>
 __device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, uint32_t zterm, uint32_t s2, uint32_t *out) {
     constexpr int CH = CB / 2;
+    const uint32_t wbase = smem_u32(wpk) + (uint32_t)n_local * 16u;      // explicit ld.shared (the pointer form compiled to generic LD.E.128)
     if (CB == 4 || CB == 2) {
         // magic: 0x4300 | q is the bf16 number 128 + q (exact for q < 128); subtract bf16x2(128 + zp)
         const uint32_t zb = zterm;
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-            const uint4 c = wpk[j * 128 + n_local];
+            const uint4 c = lds128(wbase + (uint32_t)(j * 128) * 16u);
             const uint32_t w[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
             for (int wd = 0; wd < 4; ++wd) {
@@ -296,7 +307,7 @@ __device__ __forceinline__ void dequant_kblock(const uint4 *wpk, int n_local, ui
         const __nv_bfloat162 sb = *reinterpret_cast<const __nv_bfloat162 *>(&s2);
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-            const uint4 c = wpk[j * 128 + n_local];
+            const uint4 c = lds128(wbase + (uint32_t)(j * 128) * 16u);
             const uint32_t w[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
             for (int wd = 0; wd < 4; ++wd) {
@@ -635,7 +646,7 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
                 const uint8_t *stage = smem_w + sw * C::kWStage;
                 for (uint32_t sub = 0; sub < nk; ++sub) {
                     const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes);
-                    const uint2 prm = reinterpret_cast<const uint2 *>(stage + KBS * C::kWBytes + sub * C::kPBytes)[n_local];
+                    const uint2 prm = lds64(smem_u32(stage + KBS * C::kWBytes + sub * C::kPBytes) + (uint32_t)n_local * 8u);
                     uint32_t vals[32];
                     if (!(a.dbg & 2)) dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
                     else {
@@ -953,7 +964,7 @@ __device__ __forceinline__ void umma_qlinear_body(const CUtensorMap &tmap_x, con
                 const uint8_t *stage = smem_w + sw * C::kWStage;
                 for (uint32_t sub = 0; sub < nk; ++sub) {
                     const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes);
-                    const uint2 prm = reinterpret_cast<const uint2 *>(stage + KBS * C::kWBytes + sub * C::kPBytes)[n_local];
+                    const uint2 prm = lds64(smem_u32(stage + KBS * C::kWBytes + sub * C::kPBytes) + (uint32_t)n_local * 8u);
                     uint32_t vals[32];
                     if constexpr (I8) {
                         unpack_kblock_u8<CB>(wpk, n_local, vals);
