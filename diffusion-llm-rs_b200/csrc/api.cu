@@ -1109,6 +1109,7 @@ int32_t dllm_sample(dllm_ctx *ctx, dllm_model *m, const float *x0, const float *
 // ==========================================================================================
 struct dllm_kv {
     size_t L = 0, S = 0, H = 0;
+    size_t cap = 0;                   // tokens per layer the buffers have room for: layer l's rows start at l * cap (cap == S: contiguous)
     int bits = 8, scheme = DLLM_KV_TENSOR_B;
     bool packed = false;
     size_t code_bytes = 0;            // per tensor
@@ -1119,34 +1120,60 @@ struct dllm_kv {
     int device = 0;
 };
 
+static size_t kv_row_bytes(const dllm_kv *kv) { return kv->packed ? kv->H * kv->bits / 8 : kv->H; }
+
+// quantize tokens [s0, s0 + t) of every layer from src [L, t, H] (schemes with per-row or fixed parameters: a row's codes
+// depend on that row only, so tokens already in the cache never change)
+static int32_t kv_quantize_rows(dllm_ctx *ctx, dllm_kv *kv, int which, const float *src_dev, size_t s0, size_t t) {
+    const int pack = kv->packed ? kv->bits : 0;
+    const size_t rb = kv_row_bytes(kv), rows_cap = kv->L * kv->cap;
+    const bool contiguous = kv->cap == t && s0 == 0;
+    const size_t n_l = contiguous ? kv->L : 1, loops = contiguous ? 1 : kv->L;
+    for (size_t l = 0; l < loops; ++l) {
+        const float *src = src_dev + l * t * kv->H;
+        const size_t r0 = l * kv->cap + s0;
+        if (kv->scheme == DLLM_KV_ROW_D)
+            DLLM_TRY(k_quant_d_rows(ctx, src, n_l * t, kv->H, nullptr, 1, kv->bits, pack, kv->d_codes[which] + r0 * rb,
+                                    kv->d_rows[which] + r0, kv->d_rows[which] + rows_cap + r0));
+        else
+            DLLM_TRY(k_encode_cd(ctx, src, n_l * t * kv->H, kv->bits, pack, kv->c_scale, 0.0f, kv->d_codes[which] + r0 * rb));
+    }
+    return DLLM_OK;
+}
+
 static int32_t kv_quantize_one(dllm_ctx *ctx, dllm_kv *kv, int which, const float *src_dev) {
     const size_t rows = kv->L * kv->S, n = rows * kv->H;
     const int pack = kv->packed ? kv->bits : 0;
     switch (kv->scheme) {
         case DLLM_KV_TENSOR_B:
+            if (kv->cap != kv->S) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "per-tensor KV entries have no spare capacity");
             DLLM_TRY(k_minmax(ctx, src_dev, n, kv->bits, kv->d_params[which]));
             return k_encode_b(ctx, src_dev, n, kv->bits, pack, kv->d_params[which], 0.f, 0.f, kv->d_codes[which]);
         case DLLM_KV_ROW_D:
-            return k_quant_d_rows(ctx, src_dev, rows, kv->H, nullptr, 1, kv->bits, pack, kv->d_codes[which],
-                                  kv->d_rows[which], kv->d_rows[which] + rows);
         case DLLM_KV_FIXED_C:
-            return k_encode_cd(ctx, src_dev, n, kv->bits, pack, kv->c_scale, 0.0f, kv->d_codes[which]);
+            return kv_quantize_rows(ctx, kv, which, src_dev, 0, kv->S);
     }
     return DLLM_ERR_INVALID_PARAMS;
 }
 
+// dst [L, S, H] contiguous
 static int32_t kv_dequantize_one(dllm_ctx *ctx, const dllm_kv *kv, int which, float *dst_dev) {
-    const size_t rows = kv->L * kv->S, n = rows * kv->H;
     const int pack = kv->packed ? kv->bits : 0;
-    switch (kv->scheme) {
-        case DLLM_KV_TENSOR_B:
-            return k_decode_ab(ctx, kv->d_codes[which], n, pack, kv->d_params[which], 0.f, 0.f, dst_dev);
-        case DLLM_KV_ROW_D:
-            return k_decode_cd(ctx, kv->d_codes[which], n, pack, 0.f, 0.f, kv->d_rows[which], kv->d_rows[which] + rows, kv->H, dst_dev);
-        case DLLM_KV_FIXED_C:
-            return k_decode_cd(ctx, kv->d_codes[which], n, pack, kv->c_scale, 0.0f, nullptr, nullptr, 0, dst_dev);
+    const size_t rb = kv_row_bytes(kv), rows_cap = kv->L * kv->cap;
+    if (kv->scheme == DLLM_KV_TENSOR_B)
+        return k_decode_ab(ctx, kv->d_codes[which], kv->L * kv->S * kv->H, pack, kv->d_params[which], 0.f, 0.f, dst_dev);
+    const bool contiguous = kv->cap == kv->S;
+    const size_t n_l = contiguous ? kv->L : 1, loops = contiguous ? 1 : kv->L;
+    for (size_t l = 0; l < loops; ++l) {
+        const size_t r0 = l * kv->cap;
+        float *dst = dst_dev + l * kv->S * kv->H;
+        if (kv->scheme == DLLM_KV_ROW_D)
+            DLLM_TRY(k_decode_cd(ctx, kv->d_codes[which] + r0 * rb, n_l * kv->S * kv->H, pack, 0.f, 0.f, kv->d_rows[which] + r0,
+                                 kv->d_rows[which] + rows_cap + r0, kv->H, dst));
+        else
+            DLLM_TRY(k_decode_cd(ctx, kv->d_codes[which] + r0 * rb, n_l * kv->S * kv->H, pack, kv->c_scale, 0.0f, nullptr, nullptr, 0, dst));
     }
-    return DLLM_ERR_INVALID_PARAMS;
+    return DLLM_OK;
 }
 
 extern "C" {
@@ -1171,19 +1198,17 @@ int32_t dllm_kv_update_dev(dllm_ctx *ctx, dllm_kv *kv, const float *keys_dev, co
     return kv_quantize_one(ctx, kv, 1, values_dev);
 }
 
-int32_t dllm_kv_quantize_dev(dllm_ctx *ctx, const float *keys_dev, const float *values_dev, size_t layers, size_t seq,
-                             size_t hidden, uint8_t bits, int32_t scheme, dllm_kv **out) {
-    CTX_CHECK(ctx);
-    ARG_CHECK(ctx, out, DLLM_ERR_NULL, "null out pointer");
-    *out = nullptr;
+// an entry with room for `capacity` tokens per layer, holding `seq` of them (not yet quantized)
+static int32_t kv_alloc(dllm_ctx *ctx, size_t layers, size_t seq, size_t capacity, size_t hidden, uint8_t bits, int32_t scheme,
+                        dllm_kv **out) {
     ARG_CHECK(ctx, scheme >= DLLM_KV_TENSOR_B && scheme <= DLLM_KV_FIXED_C, DLLM_ERR_INVALID_PARAMS, "unknown scheme %d", scheme);
     if (scheme == DLLM_KV_TENSOR_B)
         ARG_CHECK(ctx, bits >= 1 && bits <= 8, DLLM_ERR_INVALID_PARAMS, "Bits must be between 1 and 8 (got %d)", (int)bits);
     ARG_CHECK(ctx, bits <= 30, DLLM_ERR_INVALID_PARAMS, "bits %d overflows", (int)bits);
     dllm_kv *kv = new (std::nothrow) dllm_kv();
     if (!kv) return DLLM_ERR_OOM;
-    kv->L = layers; kv->S = seq; kv->H = hidden; kv->bits = bits; kv->scheme = scheme; kv->device = ctx->device;
-    const size_t rows = layers * seq, n = rows * hidden;
+    kv->L = layers; kv->S = seq; kv->cap = capacity; kv->H = hidden; kv->bits = bits; kv->scheme = scheme; kv->device = ctx->device;
+    const size_t rows = layers * capacity, n = rows * hidden;
     kv->packed = pack_width_ok(bits) && bits != 8 && hidden % 8 == 0 && (hidden * bits / 8) % 4 == 0 &&
                  (scheme != DLLM_KV_ROW_D || hidden <= 16384);
     kv->code_bytes = kv->packed ? n * bits / 8 : n;
@@ -1195,11 +1220,58 @@ int32_t dllm_kv_quantize_dev(dllm_ctx *ctx, const float *keys_dev, const float *
         if (e == cudaSuccess && scheme == DLLM_KV_ROW_D) e = cudaMalloc(&kv->d_rows[i], (2 * rows + 4) * sizeof(float));
     }
     if (e != cudaSuccess) { cudaGetLastError(); dllm_kv_destroy(kv); DLLM_FAIL(ctx, DLLM_ERR_OOM, "cudaMalloc failed for the KV entry"); }
+    *out = kv;
+    return DLLM_OK;
+}
+
+int32_t dllm_kv_quantize_dev(dllm_ctx *ctx, const float *keys_dev, const float *values_dev, size_t layers, size_t seq,
+                             size_t hidden, uint8_t bits, int32_t scheme, dllm_kv **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, out, DLLM_ERR_NULL, "null out pointer");
+    *out = nullptr;
+    dllm_kv *kv = nullptr;
+    DLLM_TRY(kv_alloc(ctx, layers, seq, seq, hidden, bits, scheme, &kv));
     int32_t rc = dllm_kv_update_dev(ctx, kv, keys_dev, values_dev);
     if (rc != DLLM_OK) { dllm_kv_destroy(kv); return rc; }
     *out = kv;
     return DLLM_OK;
 }
+
+int32_t dllm_kv_create(dllm_ctx *ctx, size_t layers, size_t capacity, size_t hidden, uint8_t bits, int32_t scheme, dllm_kv **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, out, DLLM_ERR_NULL, "null out pointer");
+    *out = nullptr;
+    ARG_CHECK(ctx, scheme == DLLM_KV_ROW_D || scheme == DLLM_KV_FIXED_C, DLLM_ERR_UNSUPPORTED,
+              "only per-token (ROW_D) and fixed-scale (FIXED_C) entries can grow: a per-tensor scale changes every code");
+    return kv_alloc(ctx, layers, 0, capacity, hidden, bits, scheme, out);
+}
+
+int32_t dllm_kv_append_dev(dllm_ctx *ctx, dllm_kv *kv, const float *keys_new_dev, const float *values_new_dev, size_t t_new) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kv, DLLM_ERR_NULL, "null kv entry");
+    ARG_CHECK(ctx, kv->scheme == DLLM_KV_ROW_D || kv->scheme == DLLM_KV_FIXED_C, DLLM_ERR_UNSUPPORTED, "per-tensor KV entries cannot grow");
+    ARG_CHECK(ctx, kv->S + t_new <= kv->cap, DLLM_ERR_INDEX, "KV entry is full: %zu + %zu tokens > capacity %zu", kv->S, t_new, kv->cap);
+    if (t_new == 0 || kv->L * kv->H == 0) return DLLM_OK;
+    ARG_CHECK(ctx, keys_new_dev && values_new_dev, DLLM_ERR_NULL, "null device pointer");
+    DLLM_TRY(kv_quantize_rows(ctx, kv, 0, keys_new_dev, kv->S, t_new));
+    DLLM_TRY(kv_quantize_rows(ctx, kv, 1, values_new_dev, kv->S, t_new));
+    kv->S += t_new;
+    return DLLM_OK;
+}
+
+int32_t dllm_kv_append(dllm_ctx *ctx, dllm_kv *kv, const float *keys_new, const float *values_new, size_t t_new) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kv, DLLM_ERR_NULL, "null kv entry");
+    const size_t n = kv->L * t_new * kv->H;
+    ARG_CHECK(ctx, n == 0 || (keys_new && values_new), DLLM_ERR_NULL, "null pointer");
+    void *dk, *dv;
+    DLLM_TRY(stage_in(ctx, 4, keys_new, n * sizeof(float), &dk));
+    DLLM_TRY(stage_in(ctx, 5, values_new, n * sizeof(float), &dv));
+    DLLM_TRY(dllm_kv_append_dev(ctx, kv, (const float *)dk, (const float *)dv, t_new));
+    return sync(ctx);
+}
+
+size_t dllm_kv_seq_len(const dllm_kv *kv) { return kv ? kv->S : 0; }
 
 int32_t dllm_kv_quantize(dllm_ctx *ctx, const float *keys, const float *values, size_t layers, size_t seq,
                          size_t hidden, uint8_t bits, int32_t scheme, dllm_kv **out) {
@@ -1243,16 +1315,25 @@ int32_t dllm_kv_export(dllm_ctx *ctx, const dllm_kv *kv, uint8_t *key_codes, uin
     const size_t rows = kv->L * kv->S, n = rows * kv->H;
     uint8_t *codes[2] = {key_codes, value_codes};
     float *sc[2] = {key_scales, value_scales}, *zp[2] = {key_zps, value_zps};
+    const size_t rb = kv_row_bytes(kv), rows_cap = kv->L * kv->cap;
+    const bool contiguous = kv->cap == kv->S;
+    const size_t n_l = contiguous ? kv->L : 1, loops = contiguous ? 1 : kv->L;      // layers per copy, copies
     for (int i = 0; i < 2; ++i) {
         if (codes[i] && n) {
+            void *du = nullptr;
+            if (kv->packed) DLLM_TRY(stage_out_buf(ctx, 1, n, &du));
+            for (size_t l = 0; l < loops; ++l) {
+                const uint8_t *src = kv->d_codes[i] + l * kv->cap * rb;
+                const size_t cnt = n_l * kv->S * kv->H, off = l * kv->S * kv->H;
+                if (kv->packed) {
+                    DLLM_TRY(k_unpack(ctx, src, cnt, kv->bits, (uint8_t *)du + off));
+                } else {
+                    DLLM_TRY(copy_out(ctx, codes[i] + off, src, cnt));
+                }
+            }
             if (kv->packed) {
-                void *du;
-                DLLM_TRY(stage_out_buf(ctx, 1, n, &du));
-                DLLM_TRY(k_unpack(ctx, kv->d_codes[i], n, kv->bits, (uint8_t *)du));
                 DLLM_TRY(copy_out(ctx, codes[i], du, n));
                 DLLM_TRY(sync(ctx));
-            } else {
-                DLLM_TRY(copy_out(ctx, codes[i], kv->d_codes[i], n));
             }
         }
         if (kv->scheme == DLLM_KV_TENSOR_B) {
@@ -1261,8 +1342,11 @@ int32_t dllm_kv_export(dllm_ctx *ctx, const dllm_kv *kv, uint8_t *key_codes, uin
             if (sc[i]) sc[i][0] = ctx->h_params[0];
             if (zp[i]) zp[i][0] = ctx->h_params[1];
         } else if (kv->scheme == DLLM_KV_ROW_D) {
-            if (sc[i]) DLLM_TRY(copy_out(ctx, sc[i], kv->d_rows[i], rows * sizeof(float)));
-            if (zp[i]) DLLM_TRY(copy_out(ctx, zp[i], kv->d_rows[i] + rows, rows * sizeof(float)));
+            for (size_t l = 0; l < loops; ++l) {
+                const size_t cnt = n_l * kv->S, off = l * kv->S, r0 = l * kv->cap;
+                if (sc[i] && cnt) DLLM_TRY(copy_out(ctx, sc[i] + off, kv->d_rows[i] + r0, cnt * sizeof(float)));
+                if (zp[i] && cnt) DLLM_TRY(copy_out(ctx, zp[i] + off, kv->d_rows[i] + rows_cap + r0, cnt * sizeof(float)));
+            }
         } else {
             if (sc[i]) sc[i][0] = kv->c_scale;
             if (zp[i]) zp[i][0] = 0.0f;

@@ -146,6 +146,10 @@ SIGNATURES = {
     "dllm_kv_quantize_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_uint8, C.c_int32,
                                          C.POINTER(c_vp)]),
     "dllm_kv_update_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp]),
+    "dllm_kv_create": (C.c_int32, [c_vp, c_sz, c_sz, c_sz, C.c_uint8, C.c_int32, C.POINTER(c_vp)]),
+    "dllm_kv_append": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz]),
+    "dllm_kv_append_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz]),
+    "dllm_kv_seq_len": (c_sz, [c_vp]),
     "dllm_kv_dequantize": (C.c_int32, [c_vp, c_vp, c_vp, c_vp]),
     "dllm_kv_dequantize_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp]),
     "dllm_kv_export": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -59,6 +59,34 @@ class QuantizedKVCacheEntry:
         self.h = h
         self.scheme = scheme
 
+    @classmethod
+    def with_capacity(cls, layers: int, capacity: int, hidden: int, bits: int, scheme: int = L.KV_ROW_D, ctx: Context | None = None):
+        """An empty entry with room for `capacity` tokens per layer (per-token or fixed-scale schemes): `append` quantizes
+        only the new tokens, where the reference's KVCacheEntry::update (lib.rs:246-276) re-quantizes the whole cache."""
+        self = cls.__new__(cls)
+        self._ctx = ctx or default_context()
+        self.shape = [layers, 0, hidden]
+        self.bits = int(bits)
+        self.seq_len = 0
+        self.scheme = scheme
+        h = C.c_void_p()
+        with self._ctx.lock:
+            self._ctx._ck(self._ctx._lib.dllm_kv_create(self._ctx.h, layers, capacity, hidden, bits, scheme, C.byref(h)))
+        self.h = h
+        return self
+
+    def append(self, keys_new, values_new):
+        """keys_new / values_new: [layers, t_new, hidden]; they land after the tokens every layer already holds."""
+        keys_new = np.ascontiguousarray(keys_new, np.float32)
+        values_new = np.ascontiguousarray(values_new, np.float32)
+        assert keys_new.ndim == 3 and keys_new.shape == values_new.shape
+        assert keys_new.shape[0] == self.shape[0] and keys_new.shape[2] == self.shape[2]
+        with self._ctx.lock:
+            self._ctx._ck(self._ctx._lib.dllm_kv_append(self._ctx.h, self.h, keys_new.ctypes.data, values_new.ctypes.data,
+                                                        keys_new.shape[1]))
+            self.seq_len = int(self._ctx._lib.dllm_kv_seq_len(self.h))
+        self.shape[1] = self.seq_len
+
     def _export(self):
         n = int(np.prod(self.shape))
         rows = self.shape[0] * self.shape[1]

@@ -286,6 +286,20 @@ DLLM_API int32_t dllm_kv_quantize_dev(dllm_ctx *ctx, const float *keys_dev, cons
 /* re-quantize into an existing entry (KVCacheEntry::update, lib.rs:246-276) */
 DLLM_API int32_t dllm_kv_update_dev(dllm_ctx *ctx, dllm_kv *kv, const float *keys_dev,
                                     const float *values_dev);
+/* Append-only growth.  The reference re-quantizes the WHOLE cache on every update
+ * (KVCacheEntry::update, lib.rs:246-276, called from the sampling loop :913-918).  With per-token parameters (ROW_D,
+ * prefill_kv.rs:104-121) or a fixed scale (FIXED_C, prefill-kvquant-rs/lib.rs:39-53) a token's codes depend on that token
+ * only, so only the NEW tokens are quantized: keys_new / values_new are [layers, t_new, hidden] and land after the
+ * seq tokens each layer already holds.  The result is bit-identical to quantizing the concatenated tensor at once.
+ * dllm_kv_create: an empty entry with room for `capacity` tokens per layer; per-tensor entries (TENSOR_B) cannot grow
+ * (DLLM_ERR_UNSUPPORTED); appending beyond the capacity is DLLM_ERR_INDEX. */
+DLLM_API int32_t dllm_kv_create(dllm_ctx *ctx, size_t layers, size_t capacity, size_t hidden, uint8_t bits,
+                                int32_t scheme, dllm_kv **out);
+DLLM_API int32_t dllm_kv_append(dllm_ctx *ctx, dllm_kv *kv, const float *keys_new, const float *values_new,
+                                size_t t_new);
+DLLM_API int32_t dllm_kv_append_dev(dllm_ctx *ctx, dllm_kv *kv, const float *keys_new_dev,
+                                    const float *values_new_dev, size_t t_new);
+DLLM_API size_t dllm_kv_seq_len(const dllm_kv *kv);
 DLLM_API int32_t dllm_kv_dequantize(dllm_ctx *ctx, const dllm_kv *kv, float *keys, float *values);
 DLLM_API int32_t dllm_kv_dequantize_dev(dllm_ctx *ctx, const dllm_kv *kv, float *keys_dev,
                                         float *values_dev);

@@ -299,6 +299,51 @@ def test_kv_entry_row_and_fixed_schemes(ctx, O, scheme_bits):
     e.close()
 
 
+@pytest.mark.parametrize("scheme_bits", [(1, 4), (1, 8), (1, 2), (1, 3), (2, 4), (2, 8)])
+@pytest.mark.parametrize("hidden", [64, 512])
+def test_kv_entry_append_only(ctx, O, scheme_bits, hidden):
+    """Growing an entry token chunk by token chunk (only the new tokens are quantized) must give exactly the entry the
+    reference builds by re-quantizing the whole [layers, seq, hidden] tensor (lib.rs:246-276), and the oracle's codes."""
+    import dllm_b200
+    from dllm_b200 import _lib as L
+    from dllm_b200.quantization import QuantizedKVCacheEntry
+    scheme, bits = scheme_bits
+    rng = np.random.default_rng(100 * scheme + bits + hidden)
+    layers, seq = 3, 37
+    k = (rng.random((layers, seq, hidden)) if scheme == L.KV_FIXED_C else rng.standard_normal((layers, seq, hidden))).astype(F)
+    v = (rng.random((layers, seq, hidden)) if scheme == L.KV_FIXED_C else rng.standard_normal((layers, seq, hidden))).astype(F)
+    whole = QuantizedKVCacheEntry(k, v, bits, ctx, scheme=scheme)
+    grown = QuantizedKVCacheEntry.with_capacity(layers, 40, hidden, bits, scheme, ctx)
+    assert grown.seq_len == 0
+    s = 0
+    for t in (5, 1, 16, 0, 15):
+        grown.append(k[:, s:s + t], v[:, s:s + t])
+        s += t
+        assert grown.seq_len == s and grown.shape == [layers, s, hidden]
+    for a, b in zip(whole._export(), grown._export()):
+        assert beq(a, b)
+    assert beq(whole.dequantize_keys(), grown.dequantize_keys()) and beq(whole.dequantize_values(), grown.dequantize_values())
+    assert whole.memory_usage() == grown.memory_usage()
+    if scheme == L.KV_ROW_D:
+        c0, s0, z0 = O.quantize_d_rows(k.reshape(-1, hidden), [bits])
+        kc, _, ks, kz, _, _ = grown._export()
+        assert np.array_equal(kc, c0.ravel()) and beq(ks, s0) and beq(kz, z0)
+    with pytest.raises(dllm_b200.DllmError):                          # 37 + 4 > capacity 40
+        grown.append(k[:, :4], v[:, :4])
+    assert grown.seq_len == 37
+    grown.append(k[:, :3], v[:, :3])                                    # exactly full
+    assert grown.seq_len == 40
+    whole.close(); grown.close()
+
+
+def test_kv_entry_per_tensor_cannot_grow(ctx):
+    import dllm_b200
+    from dllm_b200 import _lib as L
+    from dllm_b200.quantization import QuantizedKVCacheEntry
+    with pytest.raises(dllm_b200.UnsupportedOperation):
+        QuantizedKVCacheEntry.with_capacity(2, 8, 64, 4, L.KV_TENSOR_B, ctx)
+
+
 def test_phase_aware_cache_entry(ctx, O):
     """KVCacheEntry, diffuse-llm-rs/src/lib.rs:122-313"""
     from dllm_b200.diffuse_llm import KVCacheEntry
