@@ -333,20 +333,28 @@ __host__ __device__ __forceinline__ constexpr int gemv_run_pos(int u, int r, int
     return -1;
 }
 
+// four consecutive activations of a token with every guard (ragged K, tokens beyond M, unaligned x): out of line, so the
+// common path below is four straight-line LDG.128 — the instructions between the dependency wait and the first load are
+// executed cold (~100 ns per 128-byte line of code), and the inline guards were most of them
+__device__ __noinline__ float4 gemv_x_load4_guarded(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t tok, uint32_t k) {
+    float4 f;
+    f.x = (tok < M && k < K) ? __ldcg(x + (size_t)tok * K + k) : 0.f;
+    f.y = (tok < M && k + 1 < K) ? __ldcg(x + (size_t)tok * K + k + 1) : 0.f;
+    f.z = (tok < M && k + 2 < K) ? __ldcg(x + (size_t)tok * K + k + 2) : 0.f;
+    f.w = (tok < M && k + 3 < K) ? __ldcg(x + (size_t)tok * K + k + 3) : 0.f;
+    return f;
+}
 // loads of one (k-block, token, t) work item: 16 floats in run order.  `vec` = K % 4 == 0 and x is 16-byte aligned.
 // The load and the conversion are separate so that a thread can have the loads of several items in flight.
 template <int CB>
 __device__ __forceinline__ void gemv_x_load(const float *__restrict__ x, uint32_t M, uint32_t K, bool vec, uint32_t kb, uint32_t tok, uint32_t t, float *v) {
+    const bool fast = vec && tok < M && (kb + 1) * WL_TILE_K <= K;          // the whole k-block exists
+    const float *row = x + (size_t)tok * K + (size_t)kb * WL_TILE_K;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const uint32_t k = kb * WL_TILE_K + (uint32_t)gemv_run_k0<CB>(q, (int)t);
-        if (tok < M && vec && k + 3 < K) {
-            const float4 f = __ldcg(reinterpret_cast<const float4 *>(x + (size_t)tok * K + k));
-            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[4 * q + e] = (tok < M && k + e < K) ? __ldcg(x + (size_t)tok * K + k + e) : 0.f;
-        }
+        const uint32_t kk = (uint32_t)gemv_run_k0<CB>(q, (int)t);
+        const float4 f = fast ? __ldcg(reinterpret_cast<const float4 *>(row + kk)) : gemv_x_load4_guarded(x, M, K, tok, kb * WL_TILE_K + kk);
+        v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
     }
 }
 
@@ -487,7 +495,7 @@ __device__ __noinline__ void reduce_tile(const float *__restrict__ partial, floa
 // 4.2 us cold, whatever the code did, vs the load latency + ~1 us warm).  Loads are L2-only (ld.global.cg), so the real
 // pass cannot see lines cached by the warm-up.
 template <int CB, int MT>
-__device__ __noinline__ void prepare_x_slice(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t kb0, uint32_t n_kb, uint8_t *xs,
+__device__ __forceinline__ void prepare_x_slice(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t kb0, uint32_t n_kb, uint8_t *xs,
                                              int tid, int nthreads, bool warm, unsigned long long *xtrace) {
     if (warm) xtrace = nullptr;
     prepare_x_tiles<CB, MT, 1>(x, M, K, kb0, n_kb, xs, (uint32_t)tid, (uint32_t)nthreads, xtrace);
@@ -637,12 +645,9 @@ gemv_mma_kernel(const GemvArgs a) {
         ItemIter iter(rg);
         Item item;
         bool have_item = iter.next(item);
-        // (ONE instance of the preparation code, executed twice: see prepare_x_slice)
-#pragma unroll 1
-        for (uint32_t pass = XR && a.warm ? 0u : 1u; pass < 2u; ++pass) {
-            if (pass == 1u) { pdl_wait(); if (ctid == 0) GTRACE(29); }
-            if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, ctid, kConsumers + 32, pass == 0u, a.trace ? a.trace + blockIdx.x * 32 : nullptr);
-        }
+        pdl_wait();
+        if (ctid == 0) GTRACE(29);
+        if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, ctid, kConsumers + 32, false, a.trace ? a.trace + blockIdx.x * 32 : nullptr);
         if (XR && ctid == 0) mbar_arrive_addr(smem_u32(xfull));
         if (ctid == 0) GTRACE(2);
         // stage counter `it` of the CTA; this group owns the stages with it % NG == grp and walks only those
@@ -750,11 +755,8 @@ gemv_mma_kernel(const GemvArgs a) {
         if (ctid == 0) GTRACE(31);
     } else {
         // ===================== epilogue warp =====================
-#pragma unroll 1
-        for (uint32_t pass = XR && a.warm ? 0u : 1u; pass < 2u; ++pass) {
-            if (pass == 1u) pdl_wait();
-            if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, kConsumers + lane, kConsumers + 32, pass == 0u, nullptr);
-        }
+        pdl_wait();
+        if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, kConsumers + lane, kConsumers + 32, false, nullptr);
         ItemIter iter(rg);
         Item item;
         bool more = iter.next(item);
