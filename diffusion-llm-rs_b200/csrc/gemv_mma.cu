@@ -210,15 +210,14 @@ struct GemvArgs {
     uint32_t max_items;              // partial slots per CTA
     uint32_t stages;                 // ring depth (multiple of NG)
     uint32_t prefill;                // stages requested before the activations are resident (XR)
-    uint32_t warm;                   // run the activation preparation once before the dependency wait (instruction-cache warm-up)
     uint32_t x_off, red_off, bar_off, pre_off;   // shared-memory carve-up (bytes)
     uint32_t bulk;                   // code tiles by one cp.async.bulk per stage (default) or by per-lane cp.async (DLLM_GEMV_BULK=0)
     unsigned long long *trace;       // -DDLLM_GEMV_TRACE: per CTA [32] globaltimer stamps, then [4][256] stage stamps of CTA 0
 };
 
 // the k-segment and unit range of one CTA; units of a segment are ordered (tile, k-block).
-// 32-bit arithmetic throughout (the launch checks units * (P + 1) < 2^32): a 64-bit division is ~150 instructions, and
-// this kernel must fit the 32 KB instruction cache to stay warm from one launch to the next.
+// 32-bit arithmetic throughout (the launch checks units * (P + 1) < 2^32): an inlined 64-bit division is ~150 instructions,
+// and the prologue of this kernel runs instruction-cache-cold on every launch.
 struct Range {
     uint32_t kb_s0, kbs;             // segment = k-blocks [kb_s0, kb_s0 + kbs)
     uint32_t units, u0, u1;          // units of the segment; this CTA's range
@@ -488,18 +487,13 @@ __device__ __noinline__ void reduce_tile(const float *__restrict__ partial, floa
 }
 
 // XR: consumers + epilogue warp convert the CTA's k-segment of x to digit columns in shared memory (the producers are
-// already streaming weights meanwhile), then meet at kBarXReady
-// `warm`: the pass before the dependency wait.  It runs the same code on whatever the activation buffer holds at that
-// time and its output is overwritten by the real pass: its only purpose is that the real pass — which sits on the
-// critical path between two dependent kernels — finds its ~10 KB of instructions in the instruction cache (measured:
-// 4.2 us cold, whatever the code did, vs the load latency + ~1 us warm).  Loads are L2-only (ld.global.cg), so the real
-// pass cannot see lines cached by the warm-up.
+// already streaming weights meanwhile), then meet at kBarXReady.  Inlined straight after the dependency wait: what this
+// code costs there is mostly the non-sequential control transfers of its first, instruction-cache-cold execution
+// (a call + a pass loop around it cost 1.3 us per launch).
 template <int CB, int MT>
 __device__ __forceinline__ void prepare_x_slice(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t kb0, uint32_t n_kb, uint8_t *xs,
-                                             int tid, int nthreads, bool warm, unsigned long long *xtrace) {
-    if (warm) xtrace = nullptr;
+                                             int tid, int nthreads, unsigned long long *xtrace) {
     prepare_x_tiles<CB, MT, 1>(x, M, K, kb0, n_kb, xs, (uint32_t)tid, (uint32_t)nthreads, xtrace);
-    if (warm) return;
 #ifdef DLLM_GEMV_TRACE
     if (tid == 0 && xtrace) { unsigned long long _t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(_t)); xtrace[26] = _t; }
 #endif
@@ -647,7 +641,7 @@ gemv_mma_kernel(const GemvArgs a) {
         bool have_item = iter.next(item);
         pdl_wait();
         if (ctid == 0) GTRACE(29);
-        if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, ctid, kConsumers + 32, false, a.trace ? a.trace + blockIdx.x * 32 : nullptr);
+        if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, ctid, kConsumers + 32, a.trace ? a.trace + blockIdx.x * 32 : nullptr);
         if (XR && ctid == 0) mbar_arrive_addr(smem_u32(xfull));
         if (ctid == 0) GTRACE(2);
         // stage counter `it` of the CTA; this group owns the stages with it % NG == grp and walks only those
@@ -756,7 +750,7 @@ gemv_mma_kernel(const GemvArgs a) {
     } else {
         // ===================== epilogue warp =====================
         pdl_wait();
-        if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, kConsumers + lane, kConsumers + 32, false, nullptr);
+        if (XR) prepare_x_slice<CB, MT>(a.x, a.M, a.K, rg.kb_s0, rg.u0 < rg.u1 ? rg.kbs : 0u, xs, kConsumers + lane, kConsumers + 32, nullptr);
         ItemIter iter(rg);
         Item item;
         bool more = iter.next(item);
@@ -912,8 +906,6 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     a.stages = stages;
     static const int prefill_env = getenv("DLLM_GEMV_PREFILL") ? atoi(getenv("DLLM_GEMV_PREFILL")) : -1;   // experiments only
     a.prefill = prefill_env >= 0 ? (uint32_t)prefill_env : stages;
-    static const bool warm = getenv("DLLM_GEMV_WARM") != nullptr;                                         // experiments only
-    a.warm = warm ? 1u : 0u;
     a.x_off = stages * kStage;
     a.red_off = a.x_off + ((xbytes + 127) & ~127u);
     a.bar_off = a.red_off + ((red_bytes + 127) & ~127u);
