@@ -424,6 +424,94 @@ quant_d_rows_kernel(const float *__restrict__ x, size_t rows, size_t dim, const 
     }
 }
 
+// The same quantizer with the rows streamed through a shared-memory ring by bulk copies (cp.async.bulk, one per row,
+// completion on an mbarrier): R rows per CTA are in flight while one is being reduced and encoded, instead of the load
+// of a row waiting for the stores of the previous one in every CTA.  Rows of >= 4 KB, dim % 4 == 0.
+template <int T, int NV, int PACK, int R>
+__global__ void __launch_bounds__(T)
+quant_d_rows_ring_kernel(const float *__restrict__ x, size_t rows, size_t dim, int bits, uint8_t *__restrict__ out,
+                         float *__restrict__ scales, float *__restrict__ zps) {
+    extern __shared__ __align__(16) float4 ring[];          // R rows of dim floats
+    __shared__ uint64_t bar[R];
+    __shared__ float smx[T / 32], smn[T / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t d4 = dim >> 2;
+    const uint32_t row_bytes = (uint32_t)(dim * sizeof(float));
+    auto bar_addr = [&](int sl) { return (uint32_t)__cvta_generic_to_shared(bar + sl); };
+    auto fill = [&](int sl, size_t r) {                     // one elected thread
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr(sl)), "r"(row_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(ring + (size_t)sl * d4)), "l"(x + r * dim), "r"(row_bytes), "r"(bar_addr(sl)) : "memory");
+    };
+    if (threadIdx.x == 0) {
+        for (int sl = 0; sl < R; ++sl) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr(sl)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int sl = 0; sl < R; ++sl) {
+            const size_t r = blockIdx.x + (size_t)sl * gridDim.x;
+            if (r < rows) fill(sl, r);
+        }
+    const float levels = (float)((1u << bits) - 1u);
+    const unsigned int ulevels = (unsigned int)levels;
+    size_t it = 0;
+    for (size_t r = blockIdx.x; r < rows; r += gridDim.x, ++it) {
+        const int sl = (int)(it % R);
+        const uint32_t ph = (uint32_t)((it / R) & 1);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tQR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra QR_DONE;\n\tbra QR_WAIT;\n\tQR_DONE:\n\t}\n"
+            :: "r"(bar_addr(sl)), "r"(ph) : "memory");
+        const float4 *x4 = ring + (size_t)sl * d4;
+        float4 v[NV];
+        float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const size_t i = (size_t)j * T + threadIdx.x;
+            if (i < d4) {
+                v[j] = x4[i];
+                mx = fmaxf(mx, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
+                mn = fminf(mn, fminf(fminf(v[j].x, v[j].y), fminf(v[j].z, v[j].w)));
+            }
+        }
+        mx = warp_max(mx);
+        mn = warp_min(mn);
+        __syncthreads();                                    // the row is in registers everywhere; the previous row's smx/smn readers are done
+        if (threadIdx.x == 0) {                             // refill the slot with the row R iterations ahead
+            const size_t rn = r + (size_t)R * gridDim.x;
+            if (rn < rows) fill(sl, rn);
+        }
+        if (lane == 0) { smx[w] = mx; smn[w] = mn; }
+        __syncthreads();
+        mx = smx[0]; mn = smn[0];
+#pragma unroll
+        for (int i = 1; i < T / 32; ++i) { mx = fmaxf(mx, smx[i]); mn = fminf(mn, smn[i]); }
+        const float scale = __fdiv_rn(__fsub_rn(mx, mn), levels);   // prefill_kv.rs:107
+        const float zp = mn;                                        // :108
+        if (threadIdx.x == 0) { scales[r] = scale; zps[r] = zp; }
+        uint8_t *orow = out + (PACK ? r * (dim * PACK / 8) : r * dim);
+        const RowDivisor rd = make_row_divisor(scale, __fsub_rn(mx, mn));
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const size_t i = (size_t)j * T + threadIdx.x;
+            const bool act = i < d4;
+            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            if (act) {
+                if (rd.fast) {
+                    c0 = clamp_trunc_u8(div_row(rd, __fsub_rn(v[j].x, zp)), ulevels);
+                    c1 = clamp_trunc_u8(div_row(rd, __fsub_rn(v[j].y, zp)), ulevels);
+                    c2 = clamp_trunc_u8(div_row(rd, __fsub_rn(v[j].z, zp)), ulevels);
+                    c3 = clamp_trunc_u8(div_row(rd, __fsub_rn(v[j].w, zp)), ulevels);
+                } else {
+                    c0 = code_cd(v[j].x, scale, zp, levels); c1 = code_cd(v[j].y, scale, zp, levels);
+                    c2 = code_cd(v[j].z, scale, zp, levels); c3 = code_cd(v[j].w, scale, zp, levels);
+                }
+            }
+            store_codes4<PACK>(orow, i, c0, c1, c2, c3, act);
+        }
+    }
+}
+
 // Self-test of div_row against __fdiv_rn.  Case i: divisor d from a hash of i (random significand, exponent in
 // [-40, 40]); numerators around every code boundary: +-(RN(c·d) + k ulps) for c = 1..256, k = -4..4, plus random ones.
 // Counts quotients whose bits differ (zeros of either sign are equal) — there must be none.
@@ -619,6 +707,21 @@ static void launch_d_rows(dllm_ctx *ctx, const float *x, size_t rows, size_t dim
     }
 }
 
+template <int PACK>
+static bool launch_d_rows_ring(dllm_ctx *ctx, const float *x, size_t rows, size_t dim, int bits, uint8_t *out, float *scales, float *zps) {
+    constexpr int T = 256, NV = 4, R = 3;
+    const size_t smem = (size_t)R * dim * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(quant_d_rows_ring_kernel<T, NV, PACK, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4) != cudaSuccess) return false;
+        attr_set = true;
+    }
+    const size_t per_sm = 4;
+    const size_t grid = rows < (size_t)ctx->sm_count * per_sm ? rows : (size_t)ctx->sm_count * per_sm;
+    quant_d_rows_ring_kernel<T, NV, PACK, R><<<(int)grid, T, smem, ctx->stream>>>(x, rows, dim, bits, out, scales, zps);
+    return true;
+}
+
 int32_t k_quant_d_rows(dllm_ctx *ctx, const float *x_dev, size_t rows, size_t dim, const uint8_t *bits_tab_dev,
                        int nbits, int uniform_bits, int pack, uint8_t *out_dev, float *scales_dev, float *zps_dev) {
     if (rows == 0) return DLLM_OK;
@@ -638,6 +741,18 @@ int32_t k_quant_d_rows(dllm_ctx *ctx, const float *x_dev, size_t rows, size_t di
         return DLLM_OK;
     }
     const size_t d4 = dim / 4;
+    // long rows with one bit width: the bulk-copy ring variant (more bytes in flight per SM)
+    static const bool no_ring = getenv("DLLM_KV_NO_RING") != nullptr;       // experiments only
+    if (!no_ring && bits_tab_dev == nullptr && dim >= 1024 && dim <= 4096 && rows >= 64) {
+        bool ok = false;
+        switch (pack) {
+            case 4: ok = launch_d_rows_ring<4>(ctx, x_dev, rows, dim, uniform_bits, out_dev, scales_dev, zps_dev); break;
+            case 2: ok = launch_d_rows_ring<2>(ctx, x_dev, rows, dim, uniform_bits, out_dev, scales_dev, zps_dev); break;
+            case 1: ok = launch_d_rows_ring<1>(ctx, x_dev, rows, dim, uniform_bits, out_dev, scales_dev, zps_dev); break;
+            default: ok = launch_d_rows_ring<0>(ctx, x_dev, rows, dim, uniform_bits, out_dev, scales_dev, zps_dev); break;
+        }
+        if (ok) { LAUNCH_CHECK(ctx); return DLLM_OK; }
+    }
     if (d4 <= 32 * 4) launch_d_rows<32, 4>(ctx, x_dev, rows, dim, bits_tab_dev, nbits, uniform_bits, pack, out_dev, scales_dev, zps_dev);
     else if (d4 <= 128 * 4) launch_d_rows<128, 4>(ctx, x_dev, rows, dim, bits_tab_dev, nbits, uniform_bits, pack, out_dev, scales_dev, zps_dev);
     else if (d4 <= 256 * 4) launch_d_rows<256, 4>(ctx, x_dev, rows, dim, bits_tab_dev, nbits, uniform_bits, pack, out_dev, scales_dev, zps_dev);
