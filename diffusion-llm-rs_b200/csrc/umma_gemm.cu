@@ -491,6 +491,10 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
 
     // warp index via shuffle: provably warp-uniform, so the role branches below are uniform branches
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    // programmatic dependent launch: the next kernel of the stream may be scheduled as SMs free up; its barrier / TMEM set-up
+    // and its weight prefetch (which depend on nothing) overlap this kernel's tail.  Everything that reads activations or
+    // writes outputs waits for this kernel's predecessors at griddepcontrol.wait.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
@@ -509,6 +513,7 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
 
     if (warp == 0) {
         // ===================== activation producer (warp-converged; one elected lane issues TMA) =====================
+        asm volatile("griddepcontrol.wait;" ::: "memory");     // the activations are the previous kernel's output
         ItemIter iter(a);
         Item item;
         uint32_t it = 0;                               // stage counter of this CTA
@@ -666,6 +671,7 @@ umma_qlinear_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a
         }
     } else if (warp >= kEpiWarp0) {
         // ===================== epilogue warps =====================
+        asm volatile("griddepcontrol.wait;" ::: "memory");     // outputs / partial tiles may still be read by the previous kernels
         const int quarter = warp & 3;
         ItemIter iter(a);
         Item item;
@@ -1230,7 +1236,18 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         const uint32_t pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
         umma_qlinear_pair_kernel<CB, NTOK, KBS, NDQ><<<2 * pairs, (8 + 4 * NDQ) * 32, CP::kTotal, ctx->stream>>>(tmap_pair, a);
     } else {
-        umma_qlinear_kernel<CB, NTOK, KBS, NDQ><<<grid, (8 + 4 * NDQ) * 32, C::kTotal, ctx->stream>>>(tmap, a);
+        static const bool no_pdl = getenv("DLLM_UMMA_NO_PDL") != nullptr;      // experiments only
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3((8 + 4 * NDQ) * 32);
+        cfg.dynamicSmemBytes = C::kTotal;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = no_pdl ? 0 : 1;
+        CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, umma_qlinear_kernel<CB, NTOK, KBS, NDQ>, tmap, a));
     }
     LAUNCH_CHECK(ctx);
     if (ev1) {
