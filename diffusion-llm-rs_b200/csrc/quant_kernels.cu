@@ -262,6 +262,33 @@ decode_kernel(const uint8_t *__restrict__ in, size_t n, float *__restrict__ out,
     }
 }
 
+// Per-row dequantize, `x * scale + zp` (prefill_kv.rs:123-131): a CTA walks whole rows — the row's scale / zero-point are
+// read once, and there is no per-element 64-bit division to find the row (the flat kernel above spends ~100 instructions
+// per float4 on it).  Lane i of a warp handles the float4 i, i + 32, ...: every store instruction writes 512 contiguous
+// bytes.  (A variant with 16 codes per thread from one wide load was 60 % slower: its stores were 64 bytes apart.)
+template <int PACK>
+__global__ void __launch_bounds__(256)
+decode_rows_kernel(const uint8_t *__restrict__ in, size_t rows, uint32_t dim, const float *__restrict__ row_scales,
+                   const float *__restrict__ row_zps, float *__restrict__ out) {
+    constexpr int B = PACK == 0 ? 8 : PACK;                 // bits per code in memory
+    const uint32_t d4 = dim >> 2;
+    const size_t row_bytes = (size_t)dim * B / 8;
+    for (size_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float s = __ldg(row_scales + r), z = __ldg(row_zps + r);
+        const uint8_t *irow = in + r * row_bytes;
+        float4 *orow = reinterpret_cast<float4 *>(out + r * dim);
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < d4; i += 256) {
+            uint32_t c0, c1, c2, c3;
+            load_codes4<PACK>(irow, i, c0, c1, c2, c3);
+            float4 v;
+            v.x = deq_cd((uint8_t)c0, s, z); v.y = deq_cd((uint8_t)c1, s, z);
+            v.z = deq_cd((uint8_t)c2, s, z); v.w = deq_cd((uint8_t)c3, s, z);
+            stg_stream_f4(orow + i, v);
+        }
+    }
+}
+
 template <int FORM>
 __global__ void decode_scalar_kernel(const uint8_t *__restrict__ in, size_t n, float *out, DecArgs a, int pack) {
     float s = a.scale, z = a.zp;
@@ -658,6 +685,22 @@ int32_t k_decode_ab(dllm_ctx *ctx, const uint8_t *in_dev, size_t n, int pack, co
 }
 int32_t k_decode_cd(dllm_ctx *ctx, const uint8_t *in_dev, size_t n, int pack, float scale, float zp,
                     const float *row_scales, const float *row_zps, size_t dim, float *out_dev) {
+    // whole rows of 16-code units with per-row parameters: the row-wise kernel
+    // (a row is a whole number of the 4 / 2 / 1-byte loads of load_codes4 and starts aligned to them)
+    if (row_scales && row_zps && dim >= 256 && dim % 16 == 0 && dim <= (1u << 24) && n % dim == 0 && n &&
+        (pack == 0 || pack == 8 || pack == 4 || pack == 2 || pack == 1) && aligned16(in_dev) && aligned16(out_dev)) {
+        const size_t rows = n / dim;
+        const size_t cap = (size_t)ctx->sm_count * 8;
+        const int grid = (int)(rows < cap ? rows : cap);
+        switch (pack) {
+            case 0: case 8: decode_rows_kernel<0><<<grid, 256, 0, ctx->stream>>>(in_dev, rows, (uint32_t)dim, row_scales, row_zps, out_dev); break;
+            case 4: decode_rows_kernel<4><<<grid, 256, 0, ctx->stream>>>(in_dev, rows, (uint32_t)dim, row_scales, row_zps, out_dev); break;
+            case 2: decode_rows_kernel<2><<<grid, 256, 0, ctx->stream>>>(in_dev, rows, (uint32_t)dim, row_scales, row_zps, out_dev); break;
+            default: decode_rows_kernel<1><<<grid, 256, 0, ctx->stream>>>(in_dev, rows, (uint32_t)dim, row_scales, row_zps, out_dev); break;
+        }
+        LAUNCH_CHECK(ctx);
+        return DLLM_OK;
+    }
     DecArgs a{scale, zp, nullptr, row_scales, row_zps, dim ? dim : 1};
     return launch_decode<1>(ctx, in_dev, n, out_dev, a, pack);
 }
