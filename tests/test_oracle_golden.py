@@ -265,3 +265,24 @@ def test_progressive_bits():
     assert O.progressive_bits(64, 32) == (2, False)      # progress = 1.0
     assert O.progressive_bits(64, 0) == (0, False)       # progress = 2.0 -> 0 bits
     assert O.progressive_bits(64, 48)[1] is True
+
+
+def test_linear_i8_oracle_against_plain_loops_and_the_float_oracle():
+    """oracle/pyoracle.py: linear_i8 (the checker of dllm_qlinear_forward_i8): equals a plain-Python integer loop on a small
+    case, and composed with the scale it is the f64 linear of the dequantized weight (quantization.rs:81-85, lib.rs:812)."""
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(12)
+    K, N, M = 24, 7, 5
+    w = (rng.standard_normal((K, N)) * 0.02).astype(np.float32)
+    codes, scale, zp = O.quantize_tensor(w, 4)
+    codes = codes.reshape(K, N)
+    xq = rng.integers(-128, 128, (M, K)).astype(np.int8)
+    y = O.linear_i8(xq, codes, zp)
+    exp = [[sum(int(xq[m, k]) * (int(codes[k, n]) - int(zp)) for k in range(K)) for n in range(N)] for m in range(M)]
+    assert y.dtype == np.int64 and y.tolist() == exp
+    wd = O.dequantize_tensor(codes.reshape(-1), scale, zp).reshape(K, N)
+    yf = O.linear_f64(xq.astype(np.float32), wd, None)
+    bound = np.abs(xq).astype(np.float64) @ np.abs(wd).astype(np.float64)      # wd carries one f32 rounding per weight
+    assert np.all(np.abs(yf - np.float64(scale) * y) <= 1e-6 * bound + 1e-12)
+    with pytest.raises(AssertionError):
+        O.linear_i8(xq, codes, 2.5)                       # quantize_tensor's zero-points are integers
