@@ -10,10 +10,15 @@
 #include "kernels.h"
 #include "wlayout.cuh"
 
-#define CTX_CHECK(ctx)                    \
-    do {                                  \
-        if (!(ctx)) return DLLM_ERR_NULL; \
-        (ctx)->err[0] = 0;                \
+// every entry point runs on the context's device, whatever the calling thread's current device is
+#define CTX_CHECK(ctx)                                                        \
+    do {                                                                      \
+        if (!(ctx)) return DLLM_ERR_NULL;                                     \
+        (ctx)->err[0] = 0;                                                    \
+        if (cudaSetDevice((ctx)->device) != cudaSuccess) {                    \
+            cudaGetLastError();                                               \
+            DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cudaSetDevice(%d) failed", (ctx)->device); \
+        }                                                                     \
     } while (0)
 
 #define ARG_CHECK(ctx, cond, code, ...)                  \
@@ -84,6 +89,7 @@ void dllm_ctx_destroy(dllm_ctx *ctx) {
     dllm_tp_finalize(ctx);
     for (auto &b : ctx->ws) if (b.p) cudaFree(b.p);
     for (auto &b : ctx->act) if (b.p) cudaFree(b.p);
+    if (ctx->tp_ws.p) cudaFree(ctx->tp_ws.p);
     if (ctx->lin_ws.p) cudaFree(ctx->lin_ws.p);
     if (ctx->lin_flags.p) cudaFree(ctx->lin_flags.p);
     if (ctx->gemv_tickets.p) cudaFree(ctx->gemv_tickets.p);
@@ -762,7 +768,9 @@ struct dllm_model {
     size_t T = 0;
     std::vector<float> betas, alpha_bars;
     float *d_coef_table[2] = {nullptr, nullptr};   // [T][4] for guard_t0 = 0 / 1 (c1, c2, std, degenerate)
+    float *d_noise_table = nullptr;                // [T][2] {sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t)} (add_noise)
     int *d_rowmap = nullptr;     // per-row timestep for the host-pointer p_sample
+    std::vector<int> h_rowmap;   // its host staging
     size_t rowmap_cap = 0;
     int device = 0;
 };
@@ -835,9 +843,31 @@ int32_t tp_allreduce(dllm_ctx *ctx, float *buf, size_t n);
 int32_t tp_allreduce_bf16(dllm_ctx *ctx, void *buf, size_t n);
 int32_t tp_allgather_cols(dllm_ctx *ctx, const float *in, size_t M, size_t n_local, float *out);
 
+// The widths that flow through the stack must chain: DiffusionModel::forward returns the input's shape (lib.rs:759),
+// and every intermediate buffer is sized from the layers' own K / N.  `world` ranks hold COLUMN (N split) / ROW (K split)
+// shards; a COLUMN shard feeds a following ROW layer directly, anything else sees the gathered / reduced full width.
+static int32_t validate_chain(dllm_ctx *ctx, const dllm_model *m, const int *parallel, size_t world) {
+    const size_t L = m->layers.size();
+    size_t width = m->hidden;          // width of the activation entering layer l
+    bool shard_in = false;             // ... which is this rank's column shard of the previous layer
+    for (size_t l = 0; l < L; ++l) {
+        const dllm_qweight *w = m->layers[l];
+        const int par = parallel ? parallel[l] : 0;
+        if (par == 2 && !shard_in) DLLM_FAIL(ctx, DLLM_ERR_SHAPE, "layer %zu is row-parallel but does not follow a column-parallel layer", l);
+        if (par != 2 && shard_in) DLLM_FAIL(ctx, DLLM_ERR_SHAPE, "layer %zu follows an un-gathered column shard but is not row-parallel", l);
+        if (w->K != width) DLLM_FAIL(ctx, DLLM_ERR_SHAPE, "layer %zu expects K=%zu but receives width %zu", l, w->K, width);
+        const bool feeds_row = par == 1 && l + 1 < L && (parallel ? parallel[l + 1] : 0) == 2;
+        shard_in = feeds_row;
+        width = (par == 1 && !feeds_row) ? w->N * world : w->N;
+    }
+    if (width != m->hidden) DLLM_FAIL(ctx, DLLM_ERR_SHAPE, "the stack's output width %zu != hidden %zu (output shape must equal input shape, lib.rs:759)", width, m->hidden);
+    return DLLM_OK;
+}
+
 static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x_dev, size_t tokens, float *out_dev,
                                     int32_t path) {
     const size_t L = m->layers.size();
+    DLLM_TRY(validate_chain(ctx, m, m->parallel.data(), (size_t)(ctx->tp_world > 1 ? ctx->tp_world : 1)));
     // widest activation of the stack
     size_t maxw = m->hidden;
     for (auto *w : m->layers) { if (w->N > maxw) maxw = w->N; if (w->K > maxw) maxw = w->K; }
@@ -921,6 +951,7 @@ int32_t dllm_beta_schedule(int32_t kind, size_t T, float beta_start, float beta_
 uint8_t dllm_progressive_bits(size_t num_steps, size_t t, uint8_t decode_bits, uint8_t min_decode_bits,
                               int32_t *is_prefill) {
     if (is_prefill) *is_prefill = t > num_steps / 2;                       // lib.rs:886
+    if (t > num_steps) return 0;       // `num_steps - t` underflows: the reference panics (debug) — 0 bits is "no valid width"
     volatile float progress = (float)(num_steps - t) / (float)(num_steps / 2);   // :895
     volatile float a = (float)decode_bits * (1.0f - progress);
     volatile float b = (float)min_decode_bits * progress;
@@ -948,6 +979,10 @@ int32_t dllm_model_create(dllm_ctx *ctx, size_t hidden, dllm_qweight *const *lay
     m->parallel.assign(n_layers, 0);
     m->T = num_timesteps;
     m->device = ctx->device;
+    if (ctx->tp_world <= 1) {   // shards of a tensor-parallel group are validated with their plan (set_parallel / forward)
+        int32_t vrc = validate_chain(ctx, m, nullptr, 1);
+        if (vrc != DLLM_OK) { delete m; return vrc; }
+    }
     m->betas.resize(num_timesteps);
     int32_t rc = beta_schedule_host(beta_kind, num_timesteps, beta_start, beta_end, m->betas.data());
     if (rc != DLLM_OK) { delete m; DLLM_FAIL(ctx, rc, "unknown beta schedule %d", beta_kind); }
@@ -969,6 +1004,20 @@ int32_t dllm_model_create(dllm_ctx *ctx, size_t hidden, dllm_qweight *const *lay
             DLLM_FAIL(ctx, DLLM_ERR_CUDA, "coefficient table upload failed");
         }
     }
+    {   // add_noise's two factors per timestep (lib.rs:1131-1132)
+        std::vector<float> nt(num_timesteps * 2);
+        for (size_t t = 0; t < num_timesteps; ++t) {
+            volatile float om = 1.0f - m->alpha_bars[t];
+            nt[2 * t] = sqrtf(m->alpha_bars[t]);
+            nt[2 * t + 1] = sqrtf(om);
+        }
+        if (cudaMalloc(&m->d_noise_table, nt.size() * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(m->d_noise_table, nt.data(), nt.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError();
+            dllm_model_destroy(m);
+            DLLM_FAIL(ctx, DLLM_ERR_CUDA, "noise table upload failed");
+        }
+    }
     *out = m;
     return DLLM_OK;
 }
@@ -977,6 +1026,7 @@ void dllm_model_destroy(dllm_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (int g = 0; g < 2; ++g) if (m->d_coef_table[g]) cudaFree(m->d_coef_table[g]);
+    if (m->d_noise_table) cudaFree(m->d_noise_table);
     if (m->d_rowmap) cudaFree(m->d_rowmap);
     delete m;   // layers are owned by the caller
 }
@@ -985,10 +1035,13 @@ int32_t dllm_model_set_parallel(dllm_ctx *ctx, dllm_model *m, const int32_t *par
     CTX_CHECK(ctx);
     ARG_CHECK(ctx, m && parallel, DLLM_ERR_NULL, "null pointer");
     ARG_CHECK(ctx, n_layers == m->layers.size(), DLLM_ERR_SHAPE, "expected %zu entries", m->layers.size());
+    std::vector<int> plan(n_layers);
     for (size_t l = 0; l < n_layers; ++l) {
         ARG_CHECK(ctx, parallel[l] >= 0 && parallel[l] <= 2, DLLM_ERR_INVALID_PARAMS, "parallel[%zu]=%d", l, parallel[l]);
-        m->parallel[l] = parallel[l];
+        plan[l] = parallel[l];
     }
+    DLLM_TRY(validate_chain(ctx, m, plan.data(), (size_t)(ctx->tp_world > 1 ? ctx->tp_world : 1)));
+    m->parallel = plan;
     return DLLM_OK;
 }
 
@@ -1024,10 +1077,11 @@ static int32_t upload_rowmap(dllm_ctx *ctx, dllm_model *m, const size_t *t, size
         CUDA_TRY(ctx, cudaMalloc(&m->d_rowmap, batch * sizeof(int)));
         m->rowmap_cap = batch;
     }
-    std::vector<int> rows(batch);
-    for (size_t b = 0; b < batch; ++b) rows[b] = (int)(t[b] < m->T - 1 ? t[b] : m->T - 1);   // lib.rs:1174 clamp
-    CUDA_TRY(ctx, cudaMemcpyAsync(m->d_rowmap, rows.data(), batch * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // `rows` is a stack temporary
+    // staged through the model's own host vector: it outlives the copy (every caller synchronises before it returns,
+    // and a ctx is used by one thread at a time), so no extra stream synchronisation is needed here
+    m->h_rowmap.resize(batch);
+    for (size_t b = 0; b < batch; ++b) m->h_rowmap[b] = (int)(t[b] < m->T - 1 ? t[b] : m->T - 1);   // lib.rs:1174 clamp
+    CUDA_TRY(ctx, cudaMemcpyAsync(m->d_rowmap, m->h_rowmap.data(), batch * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     return DLLM_OK;
 }
 
@@ -1048,6 +1102,33 @@ int32_t dllm_p_sample(dllm_ctx *ctx, dllm_model *m, const float *x_t, const floa
     DLLM_TRY(k_p_sample(ctx, (const float *)dx, (const float *)dp, (const float *)dz, m->d_coef_table[guard_t0 ? 1 : 0],
                         m->d_rowmap, 0, batch, feat, (float *)dout));
     DLLM_TRY(copy_out(ctx, x_prev, dout, n * sizeof(float)));
+    return sync(ctx);
+}
+
+int32_t dllm_add_noise_dev(dllm_ctx *ctx, dllm_model *m, const float *x_start_dev, const float *noise_dev, size_t t,
+                           size_t batch, size_t feat, float *noisy_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    if (batch * feat == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_start_dev && noise_dev && noisy_dev, DLLM_ERR_NULL, "null device pointer");
+    const int row = (int)(t < m->T - 1 ? t : m->T - 1);                       // lib.rs:1123
+    return k_add_noise(ctx, x_start_dev, noise_dev, m->d_noise_table, nullptr, row, batch, feat, noisy_dev);
+}
+
+int32_t dllm_add_noise(dllm_ctx *ctx, dllm_model *m, const float *x_start, const float *noise, const size_t *t,
+                       size_t batch, size_t feat, float *noisy) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    const size_t n = batch * feat;
+    if (n == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_start && noise && t && noisy, DLLM_ERR_NULL, "null pointer (the noise is an input: the reference's own draw is an unseeded thread_rng, lib.rs:1107-1109)");
+    void *dx, *dn, *dout;
+    DLLM_TRY(stage_in(ctx, 4, x_start, n * sizeof(float), &dx));
+    DLLM_TRY(stage_in(ctx, 5, noise, n * sizeof(float), &dn));
+    DLLM_TRY(stage_out_buf(ctx, 7, n * sizeof(float), &dout));
+    DLLM_TRY(upload_rowmap(ctx, m, t, batch));
+    DLLM_TRY(k_add_noise(ctx, (const float *)dx, (const float *)dn, m->d_noise_table, m->d_rowmap, 0, batch, feat, (float *)dout));
+    DLLM_TRY(copy_out(ctx, noisy, dout, n * sizeof(float)));
     return sync(ctx);
 }
 

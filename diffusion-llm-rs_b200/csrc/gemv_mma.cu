@@ -923,13 +923,17 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     a.partial = (float *)ctx->lin_ws.p;
     a.tickets = (unsigned int *)ctx->gemv_tickets.p;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_mma_kernel<CB, MT, NG, NP, KBS, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        // the activation-prep kernel runs right before: same shared-memory carve-out, so the SMs are not
-        // re-partitioned (L1 vs shared) between the two launches
-        CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_xprep_kernel<CB, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
+    {   // per (context's device, kernel instance): function attributes are per device
+        const void *key = reinterpret_cast<const void *>(gemv_xprep_kernel<CB, MT>);
+        bool done = false;
+        for (const void *k : ctx->smem_attr_done) done = done || k == key;
+        DLLM_TRY(ensure_smem_attr(ctx, gemv_mma_kernel<CB, MT, NG, NP, KBS, XR>, 227 * 1024));
+        if (!done) {
+            // the activation-prep kernel runs right before: same shared-memory carve-out, so the SMs are not
+            // re-partitioned (L1 vs shared) between the two launches
+            CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_xprep_kernel<CB, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            ctx->smem_attr_done.push_back(key);
+        }
     }
     if (!XR) {
         const uint32_t units16 = k_blocks * 2 * MT * 4;

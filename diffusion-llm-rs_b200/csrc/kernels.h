@@ -46,7 +46,7 @@ int32_t k_wexport_codes(dllm_ctx *ctx, const dllm_qweight *qw, uint8_t *codes_de
 int32_t k_qlinear_simt(dllm_ctx *ctx, const dllm_qweight *qw, const float *x_dev, size_t M, float *y_dev);
 
 // ---- gemv_mma.cu ----
-// HBM-bound path for 1..16 tokens: bulk-copy ring + mma.sync on in-register dequantized bf16 codes
+// HBM-bound path for 1..16 tokens: bulk-copy ring + int8 mma.sync (u8 codes x signed-digit activations)
 int32_t k_qlinear_gemv(dllm_ctx *ctx, const dllm_qweight *qw, const float *x_dev, size_t M, float *y_dev);
 bool k_gemv_supported(const dllm_qweight *qw, size_t M);
 
@@ -67,3 +67,6 @@ int32_t k_bf16_to_f32(dllm_ctx *ctx, const void *in_bf16_dev, size_t n, float *o
 int32_t k_p_sample(dllm_ctx *ctx, const float *x_dev, const float *pred_dev, const float *z_dev,
                    const float *coef_table_dev, const int *rowmap_dev, int row, size_t batch, size_t feat,
                    float *out_dev);
+// noisy = x * tab[t][0] + noise * tab[t][1] per batch row (add_noise, lib.rs:1131-1133); rows as in k_p_sample
+int32_t k_add_noise(dllm_ctx *ctx, const float *x_dev, const float *noise_dev, const float *tab_dev, const int *rowmap_dev,
+                    int row, size_t batch, size_t feat, float *out_dev);

@@ -754,11 +754,7 @@ template <int PACK>
 static bool launch_d_rows_ring(dllm_ctx *ctx, const float *x, size_t rows, size_t dim, int bits, uint8_t *out, float *scales, float *zps) {
     constexpr int T = 256, NV = 4, R = 3;
     const size_t smem = (size_t)R * dim * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(quant_d_rows_ring_kernel<T, NV, PACK, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4) != cudaSuccess) return false;
-        attr_set = true;
-    }
+    if (ensure_smem_attr(ctx, quant_d_rows_ring_kernel<T, NV, PACK, R>, 3 * 4096 * 4) != DLLM_OK) return false;
     const size_t per_sm = 4;
     const size_t grid = rows < (size_t)ctx->sm_count * per_sm ? rows : (size_t)ctx->sm_count * per_sm;
     quant_d_rows_ring_kernel<T, NV, PACK, R><<<(int)grid, T, smem, ctx->stream>>>(x, rows, dim, bits, out, scales, zps);

@@ -45,6 +45,19 @@ p_sample_kernel(const float *x /* may alias out */, const float *__restrict__ pr
     }
 }
 
+// noisy = x_start * sqrt(alpha_bar_t) + noise * sqrt(1 - alpha_bar_t)      lib.rs:1131-1133
+// (two products, one add: no contraction).  tab rows are {sqrt(alpha_bar), sqrt(1 - alpha_bar)} per timestep.
+__global__ void __launch_bounds__(256)
+add_noise_kernel(const float *__restrict__ x, const float *__restrict__ noise, const float *__restrict__ tab,
+                 const int *__restrict__ rowmap, int row, size_t batch, size_t feat, float *__restrict__ out) {
+    const size_t total = batch * feat;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / feat;
+        const float *c = tab + 2 * (size_t)(rowmap ? __ldg(rowmap + b) : row);
+        out[i] = __fadd_rn(__fmul_rn(x[i], __ldg(c)), __fmul_rn(noise[i], __ldg(c + 1)));
+    }
+}
+
 inline int grid1d(const dllm_ctx *ctx, size_t items) {
     size_t b = (items + 255) / 256, cap = (size_t)ctx->sm_count * 16;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -74,6 +87,15 @@ int32_t k_p_sample(dllm_ctx *ctx, const float *x_dev, const float *pred_dev, con
     if (batch * feat == 0) return DLLM_OK;
     p_sample_kernel<<<grid1d(ctx, batch * feat), 256, 0, ctx->stream>>>(x_dev, pred_dev, z_dev, coef_table_dev,
                                                                         rowmap_dev, row, batch, feat, out_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
+
+int32_t k_add_noise(dllm_ctx *ctx, const float *x_dev, const float *noise_dev, const float *tab_dev, const int *rowmap_dev,
+                    int row, size_t batch, size_t feat, float *out_dev) {
+    if (batch * feat == 0) return DLLM_OK;
+    add_noise_kernel<<<grid1d(ctx, batch * feat), 256, 0, ctx->stream>>>(x_dev, noise_dev, tab_dev, rowmap_dev, row, batch,
+                                                                         feat, out_dev);
     LAUNCH_CHECK(ctx);
     return DLLM_OK;
 }

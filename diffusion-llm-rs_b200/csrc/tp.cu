@@ -55,8 +55,9 @@ int32_t tp_allgather_cols(dllm_ctx *ctx, const float *in, size_t M, size_t n_loc
     }
     if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
     if (n == 0) return DLLM_OK;
-    DLLM_TRY(ensure_buf(ctx, ctx->ws[7], (size_t)ctx->tp_world * n * sizeof(float)));
-    float *gathered = (float *)ctx->ws[7].p;
+    // own scratch: ws[7] is the noise_pred buffer of dllm_denoise_step_dev, i.e. possibly `out` itself
+    DLLM_TRY(ensure_buf(ctx, ctx->tp_ws, (size_t)ctx->tp_world * n * sizeof(float)));
+    float *gathered = (float *)ctx->tp_ws.p;
     NCCL_TRY(ctx, ncclAllGather(in, gathered, n, ncclFloat32, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     size_t blocks = ((size_t)ctx->tp_world * n + 255) / 256, cap = (size_t)ctx->sm_count * 16;
     interleave_cols_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, ctx->stream>>>(gathered, M, n_local, ctx->tp_world, out);

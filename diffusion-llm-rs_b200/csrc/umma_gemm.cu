@@ -1213,13 +1213,8 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_kernel<CB, NTOK, KBS, NDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
-        if (NTOK == 128)
-            CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_pair_kernel<CB, NTOK, KBS, NDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, CP::kTotal));
-        attr_set = true;
-    }
+    DLLM_TRY(ensure_smem_attr(ctx, umma_qlinear_kernel<CB, NTOK, KBS, NDQ>, C::kTotal));
+    if (NTOK == 128) DLLM_TRY(ensure_smem_attr(ctx, umma_qlinear_pair_kernel<CB, NTOK, KBS, NDQ>, CP::kTotal));
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->prof_on) {   // bracket this launch with events on the launching stream
         while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) {
@@ -1338,11 +1333,7 @@ int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, 
     a.stream_k = 0;                                      // whole tiles only: int32 accumulators never leave TMEM half-summed
     const uint32_t sms = (uint32_t)ctx->sm_count;
     const uint32_t grid = tiles < sms ? tiles : sms;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(umma_qlinear_x_kernel<CB, NTOK, KBS, NDQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
-        attr_set = true;
-    }
+    DLLM_TRY(ensure_smem_attr(ctx, umma_qlinear_x_kernel<CB, NTOK, KBS, NDQ, true>, C::kTotal));
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->prof_on) {
         while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) {

@@ -42,7 +42,7 @@ template <int CB, typename SRC>  // SRC = float (quantize with B) or uint8_t (ad
 __global__ void __launch_bounds__(128)
 wpack_kernel(const SRC *__restrict__ src, size_t K, size_t N, size_t Npad, size_t group, int bits,
              size_t k_blocks, const float *__restrict__ scales, const float *__restrict__ zps,
-             uint8_t *__restrict__ packed) {
+             uint8_t *__restrict__ packed, unsigned int *__restrict__ flags) {
     constexpr int CH = CB / 2;          // chunks per column per tile
     constexpr int EPW = 32 / CB;        // codes per word
     const size_t nt = blockIdx.x, kb = blockIdx.y;
@@ -65,7 +65,10 @@ wpack_kernel(const SRC *__restrict__ src, size_t K, size_t N, size_t Npad, size_
                 uint32_t c = pad_code;
                 if (col_ok && k < K) {
                     if (sizeof(SRC) == 4) c = code_b((float)src[k * N + n], s, z, hi);
-                    else c = (uint32_t)src[k * N + n];
+                    else {
+                        c = (uint32_t)src[k * N + n];
+                        if (c > (uint32_t)hi) atomicOr(flags, 4u);   // a code that does not fit `bits`: rejected by the host, never truncated
+                    }
                 }
                 words[wd] |= (c & ((1u << CB) - 1u)) << wl_bitpos<CB>(i);
             }
@@ -80,9 +83,8 @@ wpack_kernel(const SRC *__restrict__ src, size_t K, size_t N, size_t Npad, size_
 //   8-bit  : x = f32 bits of zp
 //   y = bf16x2(scale)
 // and for the GEMV path (int8 tensor path, gemv_mma.cu): {f32 scale, f32 zp}
-// flags (OR-ed): 1 = some zero-point is not an integer in [0, 255] (the 16-bit-operand kernels subtract it exactly
-// only if it is: quantizer B always produces such, hand-made parameters may not); 2 = some scale is outside the range
-// in which an fp16 copy keeps full precision and (q - zp) * scale cannot overflow
+// flags (OR-ed): 1 = some zero-point is not an integer in [0, 255] (the tensor-core kernels subtract it exactly
+// only if it is: quantizer B always produces such, hand-made parameters may not — those weights run on the f32 SIMT path)
 __global__ void wdq_params_kernel(const float *__restrict__ scales, const float *__restrict__ zps, size_t n, int cb,
                                   uint2 *__restrict__ out, uint2 *__restrict__ gout, unsigned int *__restrict__ flags) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,7 +92,6 @@ __global__ void wdq_params_kernel(const float *__restrict__ scales, const float 
     const float s = scales[i], z = zps[i];
     unsigned int f = 0;
     if (!(z >= 0.f && z <= 255.f && z == rintf(z))) f |= 1u;
-    if (s != 0.f && !(fabsf(s) >= 6.2e-5f && fabsf(s) <= 200.f)) f |= 2u;
     if (f) atomicOr(flags, f);
     __nv_bfloat162 sb = __float2bfloat162_rn(s);
     uint2 o;
@@ -154,12 +155,20 @@ static int32_t wpack_any(dllm_ctx *ctx, const SRC *src, dllm_qweight *qw) {
     const size_t Npad = qw->n_tiles * 128;
     const int cb = wl_container_bits(qw->bits);
     dim3 grid((unsigned)qw->n_tiles, (unsigned)qw->k_blocks);
+    unsigned int *flags = reinterpret_cast<unsigned int *>(ctx->d_params + 9);
+    if (sizeof(SRC) == 1) CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, sizeof(unsigned int), ctx->stream));
     switch (cb) {
-        case 2: wpack_kernel<2, SRC><<<grid, 128, 0, ctx->stream>>>(src, qw->K, qw->N, Npad, qw->group, qw->bits, qw->k_blocks, qw->d_scales, qw->d_zps, qw->d_packed); break;
-        case 4: wpack_kernel<4, SRC><<<grid, 128, 0, ctx->stream>>>(src, qw->K, qw->N, Npad, qw->group, qw->bits, qw->k_blocks, qw->d_scales, qw->d_zps, qw->d_packed); break;
-        default: wpack_kernel<8, SRC><<<grid, 128, 0, ctx->stream>>>(src, qw->K, qw->N, Npad, qw->group, qw->bits, qw->k_blocks, qw->d_scales, qw->d_zps, qw->d_packed); break;
+        case 2: wpack_kernel<2, SRC><<<grid, 128, 0, ctx->stream>>>(src, qw->K, qw->N, Npad, qw->group, qw->bits, qw->k_blocks, qw->d_scales, qw->d_zps, qw->d_packed, flags); break;
+        case 4: wpack_kernel<4, SRC><<<grid, 128, 0, ctx->stream>>>(src, qw->K, qw->N, Npad, qw->group, qw->bits, qw->k_blocks, qw->d_scales, qw->d_zps, qw->d_packed, flags); break;
+        default: wpack_kernel<8, SRC><<<grid, 128, 0, ctx->stream>>>(src, qw->K, qw->N, Npad, qw->group, qw->bits, qw->k_blocks, qw->d_scales, qw->d_zps, qw->d_packed, flags); break;
     }
     LAUNCH_CHECK(ctx);
+    if (sizeof(SRC) == 1) {   // adopted codes: one that does not fit `bits` is a format error (InvalidDataFormat, error.rs:38)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_params + 9, flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*reinterpret_cast<unsigned int *>(ctx->h_params + 9) & 4u)
+            DLLM_FAIL(ctx, DLLM_ERR_INVALID_DATA_FORMAT, "a code exceeds 2^%d - 1", qw->bits);
+    }
     return DLLM_OK;
 }
 
@@ -178,7 +187,6 @@ int32_t k_wdq_params(dllm_ctx *ctx, dllm_qweight *qw) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     const unsigned int f = *reinterpret_cast<unsigned int *>(ctx->h_params + 8);
     qw->int_zps = (f & 1u) == 0;
-    qw->f16_scales = (f & 2u) == 0;
     return DLLM_OK;
 }
 

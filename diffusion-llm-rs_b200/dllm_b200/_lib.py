@@ -138,6 +138,8 @@ SIGNATURES = {
     "dllm_model_forward_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_sz, c_vp, C.c_int32]),
     "dllm_beta_schedule": (C.c_int32, [C.c_int32, c_sz, C.c_float, C.c_float, c_vp]),
     "dllm_p_sample": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, C.c_int32, c_vp]),
+    "dllm_add_noise": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_vp]),
+    "dllm_add_noise_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, c_vp]),
     "dllm_denoise_step_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, C.c_int32]),
     "dllm_denoise_step": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, C.c_int32]),
     "dllm_sample": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, C.c_int32, c_vp]),

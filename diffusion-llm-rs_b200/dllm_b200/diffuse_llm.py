@@ -235,6 +235,22 @@ class DiffuseLLM:
                                                        batch, feat, int(guard_t0), out.ctypes.data))
         return out
 
+    # -- add_noise: lib.rs:1100-1137, noise injected --
+    def add_noise(self, model: QuantizedDiffusionModel, x_start, t, noise):
+        """(noisy, noise) with noisy = x_start*sqrt(alpha_bar_t) + noise*sqrt(1 - alpha_bar_t).  The reference draws
+        the noise from an unseeded thread_rng when it is None (:1107-1109); here it must be supplied."""
+        x_start = np.ascontiguousarray(x_start, np.float32)
+        if noise is None:
+            raise L.InvalidParams(L.ERR_INVALID_PARAMS, "add_noise: supply the noise (the reference's own draw is unseeded)")
+        noise = np.ascontiguousarray(noise, np.float32)
+        batch, feat = x_start.shape
+        tt = np.ascontiguousarray(t, np.uint64)
+        out = np.empty_like(x_start)
+        with self._ctx.lock:
+            self._ctx._ck(self._ctx._lib.dllm_add_noise(self._ctx.h, model.h, x_start.ctypes.data, noise.ctypes.data,
+                                                        tt.ctypes.data, batch, feat, out.ctypes.data))
+        return out, noise
+
     def init_kv_cache(self, batch_size: int) -> KVCacheEntry:
         """lib.rs:958-975: empty [layers, 0, hidden] cache with phase-aware bits"""
         shape = (self.config.num_layers, 0, self.config.hidden_size)

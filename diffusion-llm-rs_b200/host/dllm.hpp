@@ -367,6 +367,14 @@ public:
                                  batch, feat, guard_t0 ? 1 : 0, out.data()));
         return out;
     }
+    // add_noise (lib.rs:1100-1137): returns the noisy input; the noise is the caller's (the second element of the reference's pair)
+    std::vector<float> add_noise(QuantizedDiffusionModel &m, const std::vector<float> &x_start, const std::vector<size_t> &t,
+                                 const std::vector<float> &noise, size_t batch, size_t feat) {
+        std::lock_guard<std::mutex> lk(ctx_.mutex());
+        std::vector<float> out(x_start.size());
+        ctx_.check(dllm_add_noise(ctx_.raw(), m.raw(), x_start.data(), noise.data(), t.data(), batch, feat, out.data()));
+        return out;
+    }
     std::vector<float> sample(QuantizedDiffusionModel &m, const std::vector<float> &x0, const std::vector<float> &noises,
                               size_t batch, size_t feat, size_t num_steps, bool guard_t0 = true) {
         std::lock_guard<std::mutex> lk(ctx_.mutex());

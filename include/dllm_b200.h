@@ -67,7 +67,8 @@ enum {
     DLLM_PATH_AUTO = 0,
     DLLM_PATH_SIMT = 1,  /* f32 CUDA-core dequant-GEMV (exact f32 dequant, f32 accumulate) */
     DLLM_PATH_UMMA = 2,  /* tcgen05 / TMEM path: bf16 operands dequantized on the fly, f32 accumulate */
-    DLLM_PATH_GEMV = 3   /* 1..16 tokens, HBM-bound: bulk-copy ring + mma.sync on exact bf16 (q - zp), f32 scale and accumulate */
+    DLLM_PATH_GEMV = 3   /* 1..16 tokens, HBM-bound: bulk-copy ring + int8 mma.sync (u8 codes x signed-digit block-fixed-point
+                            activations, exact int32 sums per 64-k block), f32 scale and accumulation across k-blocks */
 };
 
 typedef struct dllm_ctx dllm_ctx;
@@ -256,6 +257,13 @@ DLLM_API int32_t dllm_beta_schedule(int32_t kind, size_t T, float beta_start, fl
 DLLM_API int32_t dllm_p_sample(dllm_ctx *ctx, dllm_model *m, const float *x_t, const float *noise_pred,
                                const float *z, const size_t *t, size_t batch, size_t feat,
                                int32_t guard_t0, float *x_prev);
+/* DiffuseLLM::add_noise, lib.rs:1100-1137: noisy = x_start * sqrt(alpha_bar_t) + noise * sqrt(1 - alpha_bar_t), t[b] clamped
+ * to T-1 per batch row (:1123).  The noise is an input (the reference's own draw when `None` is an unseeded thread_rng,
+ * :1107-1109: parity unpinned); the returned pair's second element is that same noise.  _dev: one timestep for all rows. */
+DLLM_API int32_t dllm_add_noise(dllm_ctx *ctx, dllm_model *m, const float *x_start, const float *noise, const size_t *t,
+                                size_t batch, size_t feat, float *noisy);
+DLLM_API int32_t dllm_add_noise_dev(dllm_ctx *ctx, dllm_model *m, const float *x_start_dev, const float *noise_dev,
+                                    size_t t, size_t batch, size_t feat, float *noisy_dev);
 /* one denoise step on the device: noise_pred = forward(x); x <- p_sample(x, t, noise_pred, z) */
 DLLM_API int32_t dllm_denoise_step_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, const float *z_dev,
                                        size_t t, size_t batch, size_t feat, int32_t guard_t0,

@@ -2,7 +2,7 @@
  * dllm_oracle.c — CPU restatement of the reference hot path.  TEST INFRASTRUCTURE ONLY
  * (see dllm_oracle.h for the rules and the parity status).
  *
- * Build: gcc -O2 -ffp-contract=off -fno-fast-math (oracle/Makefile).  No FMA contraction,
+ * Build: gcc -O3 -mavx2 -ffp-contract=off -fno-fast-math (oracle/Makefile).  No FMA contraction,
  * no reassociation: Rust never contracts a*b+c and the f32 operation order below is the
  * reference's.  Rust semantics restated explicitly:
  *   f32::max/min      -> fmaxf/fminf (NaN-ignoring)
@@ -400,6 +400,22 @@ void orc_p_sample(const float *x_t, const float *noise_pred, const float *z,
             float mean = c1 * x_t[o] + c2 * noise_pred[o];    /* :1195-1196 */
             float nz = add_noise ? z[o] : 0.0f;
             x_prev[o] = mean + sd * nz;                       /* :1212 */
+        }
+    }
+}
+
+/* diffuse-llm-rs/src/lib.rs:1100-1137 (noise supplied by the caller: the reference's own draw is an unseeded thread_rng) */
+void orc_add_noise(const float *x_start, const float *noise, const size_t *t, size_t batch, size_t feat,
+                   const float *betas, size_t T, float *noisy) {
+    for (size_t b = 0; b < batch; ++b) {
+        const size_t ti = t[b] < T - 1 ? t[b] : T - 1;        /* :1123 */
+        const float ab = alpha_bar_at(betas, ti);             /* :1116-1124 */
+        const float sa = sqrtf(ab);                           /* :1131 */
+        const float sd = sqrtf(1.0f - ab);                    /* :1132 */
+        for (size_t i = 0; i < feat; ++i) {
+            const size_t o = b * feat + i;
+            const float mean = x_start[o] * sa;               /* :1131 */
+            noisy[o] = mean + noise[o] * sd;                  /* :1133 */
         }
     }
 }

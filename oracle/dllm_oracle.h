@@ -115,6 +115,9 @@ void orc_p_sample_coeffs(const float *betas, size_t T, size_t t, float *c1, floa
 void orc_p_sample(const float *x_t, const float *noise_pred, const float *z,
                   const size_t *t, size_t batch, size_t feat,
                   const float *betas, size_t T, int32_t guard_t0, float *x_prev);
+/* add_noise, lib.rs:1100-1137: noisy = x_start * sqrt(alpha_bar_t) + noise * sqrt(1 - alpha_bar_t), t clamped to T-1 per row */
+void orc_add_noise(const float *x_start, const float *noise, const size_t *t, size_t batch, size_t feat,
+                   const float *betas, size_t T, float *noisy);
 /* progressive decode bits, lib.rs:886-897. returns target bits; *is_prefill set. */
 uint8_t orc_progressive_bits(size_t num_steps, size_t t, uint8_t decode_bits, uint8_t min_bits,
                              int32_t *is_prefill);

@@ -294,6 +294,18 @@ def p_sample(x_t, noise_pred, z, t, betas, guard_t0=True):
     return out
 
 
+def add_noise(x_start, t, noise, betas):
+    """diffuse-llm-rs/src/lib.rs:1100-1137 with the noise supplied (the reference's own draw is unseeded)."""
+    x_start, noise, betas = _f32(x_start), _f32(noise), _f32(betas)
+    batch, feat = x_start.shape
+    tt = np.ascontiguousarray(t, dtype=np.uint64)
+    out = np.empty_like(x_start)
+    lib().orc_add_noise(_p(x_start, C.c_float), _p(noise, C.c_float), tt.ctypes.data_as(C.POINTER(C.c_size_t)),
+                        C.c_size_t(batch), C.c_size_t(feat), _p(betas, C.c_float), C.c_size_t(betas.size),
+                        _p(out, C.c_float))
+    return out
+
+
 def progressive_bits(num_steps, t, decode_bits=4, min_bits=2):
     pre = C.c_int32()
     b = lib().orc_progressive_bits(C.c_size_t(num_steps), C.c_size_t(t), C.c_uint8(decode_bits),

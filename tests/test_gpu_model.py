@@ -82,6 +82,37 @@ def test_p_sample_bit_exact(ctx, O):
         model.close()
 
 
+def test_add_noise_bit_exact(ctx, O):
+    """DiffuseLLM::add_noise (lib.rs:1100-1137) on the GPU == the oracle, bit for bit, for the three schedules,
+    per-row timesteps (clamped past T-1, :1123), and the device-pointer form."""
+    from dllm_b200.diffuse_llm import DiffuseLLM, DiffusionConfig, QuantizedDiffusionModel, BetaSchedule
+    rng = np.random.default_rng(5)
+    layers, _ = build_stack(ctx, O, rng, [128, 128])
+    for sched in (BetaSchedule.Linear, BetaSchedule.Quadratic, BetaSchedule.Cosine):
+        cfg = DiffusionConfig(num_timesteps=100, hidden_size=128, beta_schedule=sched)
+        model = QuantizedDiffusionModel(layers, 128, cfg, ctx)
+        llm = DiffuseLLM(cfg, ctx)
+        betas = O.beta_schedule(sched.value, 100)
+        x = rng.standard_normal((6, 384)).astype(F)
+        nz = rng.standard_normal((6, 384)).astype(F)
+        x[0, :4] = [np.nan, np.inf, -np.inf, 0.0]
+        for t in ([0] * 6, [99] * 6, [3, 9, 27, 81, 99, 250], [0, 1, 2, 3, 4, 5]):
+            noisy, noise_out = llm.add_noise(model, x, t, nz)
+            assert noise_out is not None and beq(noise_out, nz)
+            assert beq(noisy, O.add_noise(x, t, nz, betas))
+        with pytest.raises(Exception):
+            llm.add_noise(model, x, [1] * 6, None)
+        # device-pointer form, one timestep for the batch
+        n = x.size
+        dx, dn, do = ctx.malloc(n * 4), ctx.malloc(n * 4), ctx.malloc(n * 4)
+        ctx.h2d(dx, x); ctx.h2d(dn, nz)
+        ctx._ck(ctx._lib.dllm_add_noise_dev(ctx.h, model.h, dx, dn, 42, 6, 384, do))
+        assert beq(ctx.d2h(do, x.shape, F), O.add_noise(x, [42] * 6, nz, betas))
+        for p in (dx, dn, do):
+            ctx.free(p)
+        model.close()
+
+
 @pytest.mark.parametrize("bits", [4, 8])
 def test_stack_forward_simt(ctx, O, bits):
     from dllm_b200 import PATH_SIMT

@@ -259,6 +259,28 @@ def test_p_sample_guard_and_noise_rule():
     assert np.all(np.isnan(lit))
 
 
+def test_add_noise_matches_numpy_restatement():
+    # lib.rs:1100-1137: noisy = x*sqrt(ab_t) + noise*sqrt(1-ab_t), t clamped to T-1 per row, f32, no FMA
+    rng = np.random.default_rng(11)
+    T = 50
+    betas = O.beta_schedule(O.BETA_LINEAR, T)
+    ab = np.ones(T, F)
+    for i in range(1, T):
+        ab[i] = F(ab[i - 1] * F(F(1.0) - betas[i - 1]))
+    x = rng.standard_normal((5, 24)).astype(F)
+    nz = rng.standard_normal((5, 24)).astype(F)
+    t = [0, 1, 17, 49, 1000]
+    out = O.add_noise(x, t, nz, betas)
+    for b, tb in enumerate(t):
+        a = ab[min(tb, T - 1)]
+        sa, sd = np.sqrt(a, dtype=F), np.sqrt(F(F(1.0) - a), dtype=F)
+        exp = ((x[b] * sa).astype(F) + (nz[b] * sd).astype(F)).astype(F)
+        assert bits_equal(out[b], exp)
+    # t = 0: alpha_bar_0 = 1 -> the input comes back unchanged (x*1 + noise*0)
+    assert bits_equal(out[0], (x[0] + (nz[0] * F(0.0)).astype(F)).astype(F))
+    assert O.add_noise(np.zeros((0, 8), F), [], np.zeros((0, 8), F), betas).shape == (0, 8)
+
+
 def test_progressive_bits():
     # lib.rs:886-897 with defaults decode=4, min=2, num_steps=64
     assert O.progressive_bits(64, 63) == (int(F(4) * (F(1) - F(1 / 32)) + F(2) * F(1 / 32)), True)
