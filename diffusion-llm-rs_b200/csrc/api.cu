@@ -90,6 +90,11 @@ void dllm_ctx_destroy(dllm_ctx *ctx) {
     for (auto &b : ctx->ws) if (b.p) cudaFree(b.p);
     for (auto &b : ctx->act) if (b.p) cudaFree(b.p);
     if (ctx->tp_ws.p) cudaFree(ctx->tp_ws.p);
+    for (auto e : ctx->tp_ev) cudaEventDestroy(e);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    for (auto e : ctx->ev_step) if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->lin_ws.p) cudaFree(ctx->lin_ws.p);
     if (ctx->lin_flags.p) cudaFree(ctx->lin_flags.p);
     if (ctx->gemv_tickets.p) cudaFree(ctx->gemv_tickets.p);
@@ -110,6 +115,7 @@ int32_t dllm_ctx_sync(dllm_ctx *ctx) {
 void *dllm_ctx_stream(dllm_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 const char *dllm_last_error(const dllm_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 uint64_t dllm_launch_count(const dllm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t dllm_graph_replay_count(const dllm_ctx *ctx) { return ctx ? ctx->graph_replays : 0; }
 int32_t dllm_sm_count(const dllm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
 int32_t dllm_selftest_division(dllm_ctx *ctx, uint64_t cases, uint64_t seed, uint64_t *mismatches) {
@@ -769,6 +775,12 @@ struct dllm_model {
     std::vector<float> betas, alpha_bars;
     float *d_coef_table[2] = {nullptr, nullptr};   // [T][4] for guard_t0 = 0 / 1 (c1, c2, std, degenerate)
     float *d_noise_table = nullptr;                // [T][2] {sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t)} (add_noise)
+    // seeded loop: {int t; int pad; u64 seed} on the device, and one captured denoise step (CUDA graph) that reads it
+    void *d_state = nullptr;
+    cudaGraphExec_t step_graph = nullptr;
+    float *graph_x = nullptr;
+    size_t graph_batch = 0, graph_feat = 0, graph_launches = 0;
+    int graph_path = -1, graph_guard = -1;
     int *d_rowmap = nullptr;     // per-row timestep for the host-pointer p_sample
     std::vector<int> h_rowmap;   // its host staging
     size_t rowmap_cap = 0;
@@ -841,7 +853,83 @@ static void p_sample_coeffs_host(const dllm_model *m, size_t t, int guard_t0, fl
 // tensor-parallel hooks (tp.cu)
 int32_t tp_allreduce(dllm_ctx *ctx, float *buf, size_t n);
 int32_t tp_allreduce_bf16(dllm_ctx *ctx, void *buf, size_t n);
+int32_t tp_allreduce_on(dllm_ctx *ctx, void *buf, size_t n, bool bf16, cudaStream_t stream);
+int32_t tp_allreduce_minmax(dllm_ctx *ctx, float *params_dev);
 int32_t tp_allgather_cols(dllm_ctx *ctx, const float *in, size_t M, size_t n_local, float *out);
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// The tcgen05 stack under tensor parallelism with the collectives overlapped (one exchange per column->row
+// pair, at the layer boundary).  The tokens are cut into `chunks` pieces; a segment of layers ending in a row-parallel one
+// is run chunk by chunk, and each chunk's all-reduce (in place, on the bf16 tensor the next linear reads) goes to the
+// communication stream as soon as its GEMM is done — it runs under the NEXT chunk's GEMMs, which leave `sm_reserve` SMs
+// free for the collective's CTAs.  The first GEMM that reads a chunk waits for that chunk's all-reduce only.
+static int32_t forward_tp_overlapped(dllm_ctx *ctx, dllm_model *m, const float *x_dev, size_t tokens, float *out_dev, int chunks) {
+    const size_t L = m->layers.size();
+    size_t maxw = m->hidden;
+    for (auto *w : m->layers) { if (w->N > maxw) maxw = w->N; if (w->K > maxw) maxw = w->K; }
+    if (!ctx->comm_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    while (ctx->tp_ev.size() < (size_t)(2 * chunks)) {
+        cudaEvent_t e;
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->tp_ev.push_back(e);
+    }
+    // chunk boundaries on multiples of 256 tokens (the dense kernel's widest tile)
+    std::vector<size_t> c0(chunks + 1, tokens);
+    const size_t per = ((tokens + chunks - 1) / chunks + 255) / 256 * 256;
+    for (int c = 0; c <= chunks; ++c) c0[c] = (size_t)c * per < tokens ? (size_t)c * per : tokens;
+    // every chunk owns one region of each ping-pong buffer ([its tokens, width] dense inside): chunks never overlap,
+    // whatever the layers' widths are
+    const size_t region = per * maxw * 2;
+    DLLM_TRY(ensure_buf(ctx, ctx->act[0], region * chunks));
+    DLLM_TRY(ensure_buf(ctx, ctx->act[1], region * chunks));
+    for (int c = 0; c < chunks; ++c)
+        if (c0[c + 1] > c0[c])
+            DLLM_TRY(k_f32_to_bf16(ctx, x_dev + c0[c] * m->layers[0]->K, (c0[c + 1] - c0[c]) * m->layers[0]->K, (char *)ctx->act[0].p + c * region));
+    const int reserve = ctx->sm_reserve >= 0 ? ctx->sm_reserve : env_int("DLLM_TP_RESERVE_SMS", 8);
+    ctx->sm_limit = ctx->sm_count - reserve;
+    std::vector<char> pending(chunks, 0);          // chunk c's input is still being all-reduced on the comm stream
+    char *cur = (char *)ctx->act[0].p, *nxt = (char *)ctx->act[1].p;
+    int32_t rc = DLLM_OK;
+    size_t l0 = 0;
+    while (l0 < L && rc == DLLM_OK) {
+        size_t l1 = l0;                            // segment [l0, l1]: up to and including the next row-parallel layer
+        while (l1 + 1 < L && m->parallel[l1] != 2) ++l1;
+        const bool reduce = m->parallel[l1] == 2;
+        for (int c = 0; c < chunks && rc == DLLM_OK; ++c) {
+            const size_t t0 = c0[c], tn = c0[c + 1] - c0[c];
+            if (tn == 0) continue;
+            if (pending[c]) { rc = cudaStreamWaitEvent(ctx->stream, ctx->tp_ev[2 * c + 1], 0) == cudaSuccess ? DLLM_OK : DLLM_ERR_CUDA; pending[c] = 0; }
+            char *a = cur + c * region, *b = nxt + c * region;
+            for (size_t l = l0; l <= l1 && rc == DLLM_OK; ++l) {
+                const dllm_qweight *w = m->layers[l];
+                const bool last = l + 1 == L;
+                rc = k_qlinear_umma(ctx, w, a, tn, last ? out_dev + t0 * w->N : nullptr, last ? nullptr : b);
+                char *t = a; a = b; b = t;
+            }
+            if (rc == DLLM_OK && reduce) {
+                const dllm_qweight *w = m->layers[l1];
+                const bool last = l1 + 1 == L;
+                void *buf = last ? (void *)(out_dev + t0 * w->N) : (void *)a;      // `a` is the last layer's output after the swap
+                if (cudaEventRecord(ctx->tp_ev[2 * c], ctx->stream) != cudaSuccess ||
+                    cudaStreamWaitEvent(ctx->comm_stream, ctx->tp_ev[2 * c], 0) != cudaSuccess) { rc = DLLM_ERR_CUDA; break; }
+                rc = tp_allreduce_on(ctx, buf, tn * w->N, !last, ctx->comm_stream);
+                if (rc == DLLM_OK && cudaEventRecord(ctx->tp_ev[2 * c + 1], ctx->comm_stream) != cudaSuccess) rc = DLLM_ERR_CUDA;
+                pending[c] = 1;
+            }
+        }
+        if ((l1 - l0 + 1) % 2 == 1) { char *t = cur; cur = nxt; nxt = t; }     // where the segment's output lives
+        l0 = l1 + 1;
+    }
+    ctx->sm_limit = 0;
+    for (int c = 0; c < chunks; ++c)
+        if (pending[c] && cudaStreamWaitEvent(ctx->stream, ctx->tp_ev[2 * c + 1], 0) != cudaSuccess && rc == DLLM_OK) rc = DLLM_ERR_CUDA;
+    if (rc == DLLM_ERR_CUDA && !ctx->err[0]) DLLM_SET_ERR(ctx, "CUDA error in the overlapped tensor-parallel forward: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
 
 // The widths that flow through the stack must chain: DiffusionModel::forward returns the input's shape (lib.rs:759),
 // and every intermediate buffer is sized from the layers' own K / N.  `world` ranks hold COLUMN (N split) / ROW (K split)
@@ -885,6 +973,10 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
     bool no_gather = true;
     for (size_t l = 0; l < L; ++l)
         if (m->parallel[l] == 1 && (l + 1 == L || m->parallel[l + 1] != 2)) no_gather = false;
+    if (all_umma && any_parallel && no_gather && ctx->tp_world > 1) {
+        const int chunks = ctx->tp_chunks > 0 ? ctx->tp_chunks : env_int("DLLM_TP_CHUNKS", 2);
+        if (chunks > 1 && tokens >= (size_t)chunks * 512) return forward_tp_overlapped(ctx, m, x_dev, tokens, out_dev, chunks);
+    }
     if (all_umma && (!any_parallel || no_gather)) {
         // bf16 activations between layers; the last layer writes f32.  Row-parallel layers leave partial sums:
         // one NCCL all-reduce at the layer boundary, on the bf16 tensor the next linear reads (f32 for the last).
@@ -1027,6 +1119,8 @@ void dllm_model_destroy(dllm_model *m) {
     cudaSetDevice(m->device);
     for (int g = 0; g < 2; ++g) if (m->d_coef_table[g]) cudaFree(m->d_coef_table[g]);
     if (m->d_noise_table) cudaFree(m->d_noise_table);
+    if (m->d_state) cudaFree(m->d_state);
+    if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
     if (m->d_rowmap) cudaFree(m->d_rowmap);
     delete m;   // layers are owned by the caller
 }
@@ -1155,11 +1249,155 @@ int32_t dllm_denoise_step(dllm_ctx *ctx, dllm_model *m, float *x, const float *z
     const size_t n = batch * feat;
     if (n == 0) return DLLM_OK;
     ARG_CHECK(ctx, x, DLLM_ERR_NULL, "null pointer");
-    void *dx, *dz = nullptr;
-    DLLM_TRY(stage_in(ctx, 4, x, n * sizeof(float), &dx));
-    if (z && t > 0) DLLM_TRY(stage_in(ctx, 6, z, n * sizeof(float), &dz));
-    DLLM_TRY(dllm_denoise_step_dev(ctx, m, (float *)dx, (const float *)dz, t, batch, feat, guard_t0, path));
+    if (!ctx->copy_stream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+        for (auto &e : ctx->ev_step) CUDA_TRY(ctx, cudaEventCreate(&e));
+    }
+    const bool noise = z && t > 0;
+    void *dx = nullptr, *dz = nullptr, *dpred = nullptr;
+    // buffers first (growing one synchronises), then the copies: x on the compute stream — the forward needs it — and the
+    // noise on the copy stream, under the forward pass; p_sample waits for it
+    DLLM_TRY(ensure_buf(ctx, ctx->ws[4], n * sizeof(float)));
+    if (noise) DLLM_TRY(ensure_buf(ctx, ctx->ws[6], n * sizeof(float)));
+    DLLM_TRY(stage_out_buf(ctx, 7, n * sizeof(float), &dpred));
+    dx = ctx->ws[4].p;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_step[0], ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dx, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_step[1], ctx->stream));
+    if (noise) {
+        dz = ctx->ws[6].p;
+        CUDA_TRY(ctx, cudaMemcpyAsync(dz, z, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    }
+    DLLM_TRY(dllm_model_forward_dev(ctx, m, (const float *)dx, batch, feat, (float *)dpred, path));   // lib.rs:924
+    if (noise) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    const int row = (int)(t < m->T - 1 ? t : m->T - 1);
+    DLLM_TRY(k_p_sample(ctx, (const float *)dx, (const float *)dpred, (const float *)dz, m->d_coef_table[guard_t0 ? 1 : 0],
+                        nullptr, row, batch, feat, (float *)dx));                                       // lib.rs:925
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_step[2], ctx->stream));
     DLLM_TRY(copy_out(ctx, x, dx, n * sizeof(float)));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_step[3], ctx->stream));
+    DLLM_TRY(sync(ctx));
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ctx->step_ms[i], ctx->ev_step[i], ctx->ev_step[i + 1]);
+    return DLLM_OK;
+}
+
+int32_t dllm_last_step_breakdown(const dllm_ctx *ctx, float *h2d_ms, float *compute_ms, float *d2h_ms) {
+    if (!ctx) return DLLM_ERR_NULL;
+    if (h2d_ms) *h2d_ms = ctx->step_ms[0];
+    if (compute_ms) *compute_ms = ctx->step_ms[1];
+    if (d2h_ms) *d2h_ms = ctx->step_ms[2];
+    return DLLM_OK;
+}
+
+// ---- seeded loop: noise from the counter-based generator ("dllm_noise v1", csrc/noise.cuh), nothing uploaded per step ----
+int32_t dllm_noise_fill_dev(dllm_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t first, size_t n, float *out_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, n == 0 || out_dev, DLLM_ERR_NULL, "null device pointer");
+    return k_noise_fill(ctx, seed, stream, first, n, out_dev);
+}
+
+int32_t dllm_noise_fill(dllm_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t first, size_t n, float *out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, n == 0 || out, DLLM_ERR_NULL, "null pointer");
+    if (n == 0) return DLLM_OK;
+    void *d;
+    DLLM_TRY(stage_out_buf(ctx, 6, n * sizeof(float), &d));
+    DLLM_TRY(k_noise_fill(ctx, seed, stream, first, n, (float *)d));
+    DLLM_TRY(copy_out(ctx, out, d, n * sizeof(float)));
+    return sync(ctx);
+}
+
+// forward + p_sample with in-kernel noise; `state` != null: t and seed are read on the device (graph replay)
+static int32_t step_seeded(dllm_ctx *ctx, dllm_model *m, float *x_dev, const void *state, size_t t, uint64_t seed, size_t batch,
+                           size_t feat, int32_t guard_t0, int32_t path) {
+    const size_t n = batch * feat;
+    void *dpred;
+    DLLM_TRY(stage_out_buf(ctx, 7, n * sizeof(float), &dpred));
+    DLLM_TRY(dllm_model_forward_dev(ctx, m, x_dev, batch, feat, (float *)dpred, path));   // lib.rs:924
+    return k_p_sample_seeded(ctx, x_dev, (const float *)dpred, m->d_coef_table[guard_t0 ? 1 : 0], state, (int)t, seed,
+                             (int)m->T, n, x_dev);                                        // lib.rs:925, in place
+}
+
+int32_t dllm_denoise_step_seeded_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, uint64_t seed, size_t t, size_t batch,
+                                     size_t feat, int32_t guard_t0, int32_t path) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    if (batch * feat == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_dev, DLLM_ERR_NULL, "null device pointer");
+    ARG_CHECK(ctx, t <= 0x7fffffffu, DLLM_ERR_INVALID_PARAMS, "timestep out of range");
+    return step_seeded(ctx, m, x_dev, nullptr, t, seed, batch, feat, guard_t0, path);
+}
+
+int32_t dllm_sample_seeded_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, uint64_t seed, size_t batch, size_t feat,
+                               size_t num_steps, int32_t guard_t0, int32_t path, int32_t use_graph) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    if (batch * feat == 0 || num_steps == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_dev, DLLM_ERR_NULL, "null device pointer");
+    ARG_CHECK(ctx, num_steps <= 0x7fffffffu, DLLM_ERR_INVALID_PARAMS, "num_steps out of range");
+    // the first step runs eagerly: it sizes every workspace and sets the kernels' attributes (nothing may allocate while a
+    // stream is being captured)
+    size_t t = num_steps - 1;                                           // lib.rs:881 `(0..num_steps).rev()`
+    DLLM_TRY(step_seeded(ctx, m, x_dev, nullptr, t, seed, batch, feat, guard_t0, path));
+    // graphs: one captured step replayed with t in device memory.  Not under tensor parallelism (NCCL calls stay eager) and
+    // not while launches are being bracketed with profiling events.
+    const bool graph = use_graph && ctx->tp_world <= 1 && !ctx->prof_on && num_steps >= 3;
+    if (!graph) {
+        while (t-- > 0) DLLM_TRY(step_seeded(ctx, m, x_dev, nullptr, t, seed, batch, feat, guard_t0, path));
+        return DLLM_OK;
+    }
+    if (!m->d_state) CUDA_TRY(ctx, cudaMalloc(&m->d_state, 16));
+    struct { int t; int pad; unsigned long long seed; } st = {(int)(num_steps - 2), 0, (unsigned long long)seed};
+    CUDA_TRY(ctx, cudaMemcpyAsync(m->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, ctx->stream));   // pageable source: staged before the call returns
+    const bool cached = m->step_graph && m->graph_x == x_dev && m->graph_batch == batch && m->graph_feat == feat &&
+                        m->graph_path == path && m->graph_guard == (guard_t0 ? 1 : 0);
+    if (!cached) {
+        if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; }
+        const uint64_t l0 = ctx->launches;
+        CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int32_t rc = step_seeded(ctx, m, x_dev, m->d_state, 0, 0, batch, feat, guard_t0, path);
+        if (rc == DLLM_OK) rc = k_sample_state_step(ctx, m->d_state);
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        if (rc != DLLM_OK || e != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            if (rc != DLLM_OK) return rc;
+            DLLM_FAIL(ctx, DLLM_ERR_CUDA, "stream capture of the denoise step failed: %s", cudaGetErrorString(e));
+        }
+        e = cudaGraphInstantiate(&m->step_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { m->step_graph = nullptr; DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+        m->graph_launches = (size_t)(ctx->launches - l0);
+        ctx->launches = l0;                                             // captured, not launched
+        m->graph_x = x_dev; m->graph_batch = batch; m->graph_feat = feat; m->graph_path = path; m->graph_guard = guard_t0 ? 1 : 0;
+    }
+    for (size_t s = 0; s + 1 < num_steps; ++s) {
+        CUDA_TRY(ctx, cudaGraphLaunch(m->step_graph, ctx->stream));
+        ctx->launches += m->graph_launches;
+        ctx->graph_replays++;
+    }
+    return DLLM_OK;
+}
+
+int32_t dllm_sample_seeded(dllm_ctx *ctx, dllm_model *m, const float *x0, uint64_t seed, size_t batch, size_t feat,
+                           size_t num_steps, int32_t guard_t0, int32_t path, int32_t use_graph, float *x_out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    const size_t n = batch * feat;
+    if (n == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_out, DLLM_ERR_NULL, "null pointer");
+    void *dx;
+    if (x0) {
+        DLLM_TRY(stage_in(ctx, 4, x0, n * sizeof(float), &dx));
+    } else {                                                            // lib.rs:875-878: x ~ N(0,1), here stream `num_steps`
+        DLLM_TRY(stage_out_buf(ctx, 4, n * sizeof(float), &dx));
+        DLLM_TRY(k_noise_fill(ctx, seed, (unsigned long long)num_steps, 0, n, (float *)dx));
+    }
+    DLLM_TRY(dllm_sample_seeded_dev(ctx, m, (float *)dx, seed, batch, feat, num_steps, guard_t0, path, use_graph));
+    DLLM_TRY(copy_out(ctx, x_out, dx, n * sizeof(float)));
     return sync(ctx);
 }
 
@@ -1313,6 +1551,35 @@ int32_t dllm_kv_quantize_dev(dllm_ctx *ctx, const float *keys_dev, const float *
     dllm_kv *kv = nullptr;
     DLLM_TRY(kv_alloc(ctx, layers, seq, seq, hidden, bits, scheme, &kv));
     int32_t rc = dllm_kv_update_dev(ctx, kv, keys_dev, values_dev);
+    if (rc != DLLM_OK) { dllm_kv_destroy(kv); return rc; }
+    *out = kv;
+    return DLLM_OK;
+}
+
+// This rank's slice [layers, seq_local, hidden] of K and V whose token rows are sharded over the ranks of the context's group
+// (dllm_tp_init): per-token (ROW_D) and fixed-scale (FIXED_C) entries need nothing from the other ranks; a per-tensor entry
+// (TENSOR_B: QuantizedKVCacheEntry::new quantizes each tensor with ONE scale / zero-point, quantization.rs:140-157) takes the
+// min / max over all ranks first — two floats per tensor on NVLink — so every rank encodes with the
+// parameters of the WHOLE tensor and the concatenated codes are bit-identical to a single-GPU quantization.
+int32_t dllm_kv_quantize_sharded_dev(dllm_ctx *ctx, const float *keys_dev, const float *values_dev, size_t layers, size_t seq_local,
+                                     size_t hidden, uint8_t bits, int32_t scheme, dllm_kv **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, out, DLLM_ERR_NULL, "null out pointer");
+    *out = nullptr;
+    if (scheme != DLLM_KV_TENSOR_B || ctx->tp_world <= 1)
+        return dllm_kv_quantize_dev(ctx, keys_dev, values_dev, layers, seq_local, hidden, bits, scheme, out);
+    dllm_kv *kv = nullptr;
+    DLLM_TRY(kv_alloc(ctx, layers, seq_local, seq_local, hidden, bits, scheme, &kv));
+    const size_t n = layers * seq_local * hidden;
+    const float *src[2] = {keys_dev, values_dev};
+    int32_t rc = DLLM_OK;
+    for (int i = 0; i < 2 && rc == DLLM_OK; ++i) {
+        if (n && !src[i]) { rc = DLLM_ERR_NULL; break; }
+        rc = k_minmax(ctx, src[i], n, bits, kv->d_params[i]);                 // an empty shard leaves {+inf, -inf}: neutral
+        if (rc == DLLM_OK) rc = tp_allreduce_minmax(ctx, kv->d_params[i]);
+        if (rc == DLLM_OK) rc = k_params_from_minmax(ctx, bits, kv->d_params[i]);
+        if (rc == DLLM_OK && n) rc = k_encode_b(ctx, src[i], n, bits, kv->packed ? bits : 0, kv->d_params[i], 0.f, 0.f, kv->d_codes[i]);
+    }
     if (rc != DLLM_OK) { dllm_kv_destroy(kv); return rc; }
     *out = kv;
     return DLLM_OK;

@@ -70,3 +70,13 @@ int32_t k_p_sample(dllm_ctx *ctx, const float *x_dev, const float *pred_dev, con
 // noisy = x * tab[t][0] + noise * tab[t][1] per batch row (add_noise, lib.rs:1131-1133); rows as in k_p_sample
 int32_t k_add_noise(dllm_ctx *ctx, const float *x_dev, const float *noise_dev, const float *tab_dev, const int *rowmap_dev,
                     int row, size_t batch, size_t feat, float *out_dev);
+// "dllm_noise v1" (noise.cuh): out[j] = element i0 + j of stream `stream` under `seed`
+int32_t k_noise_fill(dllm_ctx *ctx, unsigned long long seed, unsigned long long stream, unsigned long long i0, size_t n,
+                     float *out_dev);
+// p_sample with the step's noise generated in the kernel (stream = t); state_dev (may be null) = {int t; int pad; u64 seed}
+// read on the device instead of the t / seed arguments (CUDA-graph replay); k_sample_state_step decrements its t
+int32_t k_p_sample_seeded(dllm_ctx *ctx, const float *x_dev, const float *pred_dev, const float *coef_table_dev,
+                          const void *state_dev, int t, unsigned long long seed, int T, size_t total, float *out_dev);
+int32_t k_sample_state_step(dllm_ctx *ctx, void *state_dev);
+// quantizer B's {scale, zp} recomputed on the device from params[2..3] = {min, max} (after a cross-GPU min / max all-reduce)
+int32_t k_params_from_minmax(dllm_ctx *ctx, int bits, float *params_dev);

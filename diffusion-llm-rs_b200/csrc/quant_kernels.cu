@@ -602,9 +602,22 @@ inline int grid_for(const dllm_ctx *ctx, size_t work_items, int per_sm) {
 
 }  // namespace
 
+__global__ void params_from_minmax_kernel(int bits, float *params) {
+    float scale, zp;
+    params_b(params[2], params[3], bits, &scale, &zp);
+    params[0] = scale;
+    params[1] = zp;
+}
+
 // ==========================================================================================
 // launchers
 // ==========================================================================================
+int32_t k_params_from_minmax(dllm_ctx *ctx, int bits, float *params_dev) {
+    params_from_minmax_kernel<<<1, 1, 0, ctx->stream>>>(bits, params_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
+
 int32_t k_minmax(dllm_ctx *ctx, const float *x_dev, size_t n, int bits, float *out_dev) {
     int grid = grid_for(ctx, (n + 15) / 16, 8);
     if (grid > kMaxPartials) grid = kMaxPartials;

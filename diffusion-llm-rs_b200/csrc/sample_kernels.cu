@@ -2,8 +2,57 @@
 // tcgen05 path and the fused p_sample update (diffuse-llm-rs/src/lib.rs:1152-1215).
 #include "common.cuh"
 #include "kernels.h"
+#include "noise.cuh"
 
 namespace {
+
+// out[i] = element i0 + i of stream `stream` ("dllm_noise v1", noise.cuh); two elements (one Box-Muller pair) per thread
+__global__ void __launch_bounds__(256)
+noise_fill_kernel(unsigned long long seed, unsigned long long stream, unsigned long long i0, size_t n, float *__restrict__ out) {
+    const uint64_t key = dn_key(seed, stream);
+    const uint64_t first_pair = i0 >> 1, last = i0 + n;                      // elements [i0, last)
+    const uint64_t n_pairs = ((last + 1) >> 1) - first_pair;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (uint64_t)gridDim.x * blockDim.x) {
+        float z0, z1;
+        dn_normal_pair(key, first_pair + p, &z0, &z1);
+        const uint64_t e0 = 2 * (first_pair + p);
+        if (e0 >= i0 && e0 < last) out[e0 - i0] = z0;
+        if (e0 + 1 >= i0 && e0 + 1 < last) out[e0 + 1 - i0] = z1;
+    }
+}
+
+// one denoise step's update with the noise generated in the kernel (no z tensor in HBM):
+//   x_prev = (c1 * x_t + c2 * noise_pred) + std * z,   z = element i of stream t under `seed`, z = 0 when t == 0
+// t and seed come from device memory when `state` is given ({int t; pad; u64 seed}: the CUDA-graph replay of the step
+// reads them there, and `advance` != 0 makes the last thread decrement t for the next replay).
+struct SampleState { int t; int pad; unsigned long long seed; };
+__global__ void __launch_bounds__(256)
+p_sample_seeded_kernel(const float *x /* may alias out */, const float *__restrict__ pred, const float *__restrict__ coef_table,
+                       const SampleState *__restrict__ state, int t_arg, unsigned long long seed_arg, int T, size_t total,
+                       float *out) {
+    const int t = state ? state->t : t_arg;
+    const unsigned long long seed = state ? state->seed : seed_arg;
+    const float *coef = coef_table + 4 * (size_t)(t < T - 1 ? t : T - 1);                    // lib.rs:1174 clamp
+    const float c1 = __ldg(coef), c2 = __ldg(coef + 1), sd = __ldg(coef + 2), degenerate = __ldg(coef + 3);
+    const uint64_t key = dn_key(seed, (uint64_t)t);
+    const size_t n_pairs = (total + 1) >> 1;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (size_t)gridDim.x * blockDim.x) {
+        float z0 = 0.f, z1 = 0.f;
+        if (t > 0) dn_normal_pair(key, p, &z0, &z1);                                         // lib.rs:1199-1205
+        const size_t i = 2 * p;
+        const bool two = i + 1 < total;
+        float xv0 = x[i], xv1 = two ? x[i + 1] : 0.f;
+        if (degenerate != 0.f) { out[i] = xv0; if (two) out[i + 1] = xv1; continue; }
+        const float m0 = __fadd_rn(__fmul_rn(c1, xv0), __fmul_rn(c2, pred[i]));
+        out[i] = __fadd_rn(m0, __fmul_rn(sd, z0));
+        if (two) {
+            const float m1 = __fadd_rn(__fmul_rn(c1, xv1), __fmul_rn(c2, pred[i + 1]));
+            out[i + 1] = __fadd_rn(m1, __fmul_rn(sd, z1));
+        }
+    }
+}
+
+__global__ void sample_state_step_kernel(SampleState *state) { state->t -= 1; }
 
 __global__ void __launch_bounds__(256)
 f32_to_bf16_kernel(const float *__restrict__ in, size_t n, __nv_bfloat16 *__restrict__ out) {
@@ -96,6 +145,29 @@ int32_t k_add_noise(dllm_ctx *ctx, const float *x_dev, const float *noise_dev, c
     if (batch * feat == 0) return DLLM_OK;
     add_noise_kernel<<<grid1d(ctx, batch * feat), 256, 0, ctx->stream>>>(x_dev, noise_dev, tab_dev, rowmap_dev, row, batch,
                                                                          feat, out_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
+
+int32_t k_noise_fill(dllm_ctx *ctx, unsigned long long seed, unsigned long long stream, unsigned long long i0, size_t n,
+                     float *out_dev) {
+    if (n == 0) return DLLM_OK;
+    noise_fill_kernel<<<grid1d(ctx, (n + 1) / 2 + 1), 256, 0, ctx->stream>>>(seed, stream, i0, n, out_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
+
+int32_t k_p_sample_seeded(dllm_ctx *ctx, const float *x_dev, const float *pred_dev, const float *coef_table_dev,
+                          const void *state_dev, int t, unsigned long long seed, int T, size_t total, float *out_dev) {
+    if (total == 0) return DLLM_OK;
+    p_sample_seeded_kernel<<<grid1d(ctx, (total + 1) / 2), 256, 0, ctx->stream>>>(x_dev, pred_dev, coef_table_dev,
+                                                                                 (const SampleState *)state_dev, t, seed, T, total, out_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
+
+int32_t k_sample_state_step(dllm_ctx *ctx, void *state_dev) {
+    sample_state_step_kernel<<<1, 1, 0, ctx->stream>>>((SampleState *)state_dev);
     LAUNCH_CHECK(ctx);
     return DLLM_OK;
 }

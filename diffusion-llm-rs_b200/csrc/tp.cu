@@ -19,7 +19,7 @@
 static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
 
 int32_t tp_allreduce(dllm_ctx *ctx, float *buf, size_t n) {
-    if (ctx->tp_world <= 1 || n == 0) return DLLM_OK;
+    if (ctx->tp_world <= 1 || n == 0 || ctx->tp_skip_comm) return DLLM_OK;
     if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
     NCCL_TRY(ctx, ncclAllReduce(buf, buf, n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return DLLM_OK;
@@ -28,9 +28,28 @@ int32_t tp_allreduce(dllm_ctx *ctx, float *buf, size_t n) {
 // bf16 partial sums of a row-parallel linear, reduced in place (half the NVLink bytes of the f32 form; the result
 // feeds the next tcgen05 linear, which reads bf16 anyway)
 int32_t tp_allreduce_bf16(dllm_ctx *ctx, void *buf, size_t n) {
-    if (ctx->tp_world <= 1 || n == 0) return DLLM_OK;
+    if (ctx->tp_world <= 1 || n == 0 || ctx->tp_skip_comm) return DLLM_OK;
     if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
     NCCL_TRY(ctx, ncclAllReduce(buf, buf, n, ncclBfloat16, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return DLLM_OK;
+}
+
+// the same all-reduces on an explicit stream (the overlapped tensor-parallel forward issues them on ctx->comm_stream)
+int32_t tp_allreduce_on(dllm_ctx *ctx, void *buf, size_t n, bool bf16, cudaStream_t stream) {
+    if (ctx->tp_world <= 1 || n == 0 || ctx->tp_skip_comm) return DLLM_OK;
+    if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
+    NCCL_TRY(ctx, ncclAllReduce(buf, buf, n, bf16 ? ncclBfloat16 : ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, stream));
+    return DLLM_OK;
+}
+
+// params_dev = {scale, zp, min, max} of this rank's shard -> min / max over all ranks of the group (two 1-float all-reduces)
+int32_t tp_allreduce_minmax(dllm_ctx *ctx, float *params_dev) {
+    if (ctx->tp_world <= 1) return DLLM_OK;
+    if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
+    NCCL_TRY(ctx, ncclGroupStart());
+    NCCL_TRY(ctx, ncclAllReduce(params_dev + 2, params_dev + 2, 1, ncclFloat32, ncclMin, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    NCCL_TRY(ctx, ncclAllReduce(params_dev + 3, params_dev + 3, 1, ncclFloat32, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    NCCL_TRY(ctx, ncclGroupEnd());
     return DLLM_OK;
 }
 
@@ -99,6 +118,17 @@ int32_t dllm_tp_finalize(dllm_ctx *ctx) {
     }
     ctx->tp_rank = 0;
     ctx->tp_world = 1;
+    return DLLM_OK;
+}
+
+int32_t dllm_tp_configure(dllm_ctx *ctx, int32_t chunks, int32_t reserve_sms, int32_t skip_comm) {
+    if (!ctx) return DLLM_ERR_NULL;
+    ctx->err[0] = 0;
+    if (chunks < 0 || chunks > 16 || reserve_sms < -1 || reserve_sms > ctx->sm_count / 2)
+        DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "chunks in 0..16 (0 = default), reserve_sms in -1..%d (-1 = default)", ctx->sm_count / 2);
+    ctx->tp_chunks = chunks;
+    ctx->sm_reserve = reserve_sms;
+    ctx->tp_skip_comm = skip_comm != 0;
     return DLLM_OK;
 }
 

@@ -1089,6 +1089,403 @@ umma_qlinear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaA
     umma_qlinear_body<CB, NTOK, KBS, NDQ, false, true>(tmap_x, a);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair kernel with 256-token tiles ("pair2"): the dense kernel of the denoise step.
+//
+// What bounded the 1-CTA kernel: per 128 x 128 x 128 stage it moves 32 KB of activations and 10 KB of
+// weights from L2 into the SM, dequantizes 16 K weights and pays one barrier hand-off chain, all for 512 cycles of MMA.
+// Here a CLUSTER OF TWO CTAs owns 256 output columns x `ntok` (<= 256) tokens: each CTA dequantizes its own 128 columns
+// into its own tensor memory ONCE per stage and the leader issues tcgen05.mma.cta_group::2 (M = 256) against TWO token
+// halves, so a stage carries up to 1024 cycles of MMA per SM for the same dequant work, the same weight bytes and the same
+// hand-offs — and each CTA loads only HALF of the activation tile (the B operand is read from both CTAs' shared memory).
+// Per flop: activation bytes / 2, weight bytes / 2, dequant / 2, hand-offs / 2.
+//
+// Tensor memory (512 columns per CTA): two 128-column accumulators (token halves h = 0, 1; each CTA holds its 128 rows)
+// + 4 A slots of 64 columns.  The accumulators are single-buffered, but the halves are committed / drained / re-armed
+// separately: while the epilogue drains half 0 the tensor pipe still runs the last stage's half-1 MMAs, and the next
+// tile's first half-0 MMAs run while half 1 is drained — the drain hides behind 512 cycles of MMAs on either side.
+// Token <-> accumulator column: CTA r loads tokens [r*ntok/2, (r+1)*ntok/2) of the tile as ONE box; half h of the tile is
+// rows [h*q, (h+1)*q) of BOTH CTAs' boxes (q = ntok/4), i.e. column c of half h is token r*ntok/2 + h*q + i with
+// r = c / q, i = c % q.  ntok is a run-time multiple of 32 (MMA N = ntok/2 is a multiple of 16), chosen per problem so
+// that the tile count fills the 74 CTA pairs evenly (e.g. 8192 tokens x 2048 columns: 224-token tiles = 4 full waves).
+// ------------------------------------------------------------------------------------------
+struct Pair2Args {
+    const uint8_t *packed;
+    const uint2 *dqparams;
+    const float *bias;
+    float *y_f32;
+    __nv_bfloat16 *y_bf16;
+    uint32_t M, N, Npad, k_blocks, n_tiles, n_pairs, m_tiles, group_kb;
+    uint32_t ntok;             // tokens per pair tile: multiple of 32, <= 256
+    uint32_t tiles;            // n_pairs * m_tiles
+    uint32_t dbg;              // timing experiments only (DLLM_UMMA_DBG): 1 skip MMAs, 2 skip dequant math, 8 skip activation loads, 64 skip stores
+    long long *trace;          // dbg & 128: clock64 stamps of cluster 0's leader CTA: [role 0..7][256]
+};
+#define TRACE2(role, idx) do { if ((a.dbg & 128) && blockIdx.x == 0 && (idx) < 256) a.trace[(role) * 256 + (idx)] = clock64(); } while (0)
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+
+template <int CB>
+struct CfgP2 {
+    static constexpr int KBS = 2;
+    static constexpr int kXSlabMax = 128 * 128;                      // one k-block of this CTA's half of the tokens (<= 128 rows x 128 B)
+    static constexpr int kXStage = KBS * kXSlabMax;
+    static constexpr int kACols = 32, kSlotCols = KBS * kACols;
+    static constexpr int kSlots = 4;                                 // X ring (shared memory) and A ring (tensor memory): same depth, one commit frees both
+    static constexpr int kAccCols = 256;                             // two 128-column halves
+    static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
+    static constexpr int kPBytes = 128 * 8;
+    static constexpr int kWStage = KBS * (kWBytes + kPBytes);
+    // output staging: one accumulator half of this CTA as bf16, [2 parts][q <= 64 tokens][128 columns] = 32 KB, written
+    // by the epilogue warps and stored with two bulk tensor copies (the direct 2-byte stores cost 29 % of the kernel)
+    static constexpr int kOutBytes = 2 * 64 * 128 * 2;
+    static constexpr int kSmemBudget = 220 * 1024;
+    static constexpr int kWStagesRaw = (kSmemBudget - kSlots * kXStage - kOutBytes) / kWStage;
+    static constexpr int kWStages = kWStagesRaw > 12 ? 12 : kWStagesRaw;   // 1024 cycles of MMAs per stage: a few stages cover the L2 latency
+    static constexpr int kOutOffset = kSlots * kXStage;
+    static constexpr int kWOffset = kOutOffset + kOutBytes;
+    static constexpr int kBarOffset = kWOffset + kWStages * kWStage;
+    static constexpr int kNumBars = 2 * kWStages + 3 * kSlots + 4;
+    static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;
+    static_assert(kXStage % 1024 == 0 && kWStage % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned stages");
+    static_assert(kWStages >= kSlots, "W ring must be at least as deep as the A ring");
+    static_assert(kTotal <= 227 * 1024, "shared memory over-subscribed");
+    static_assert(kAccCols + kSlots * kSlotCols <= kTmemCols, "TMEM over-subscribed");
+};
+
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time; test_wait never does)
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+template <int CB, int NDQ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((12 + 4 * NDQ) * 32, 1)
+umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const Pair2Args a) {
+    using C = CfgP2<CB>;
+    constexpr int KBS = C::KBS, kACols = C::kACols;
+    constexpr int SW = C::kWStages, A = C::kSlots;
+    constexpr int kEpiWarp0 = 4 + 4 * NDQ;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_w = smem + C::kWOffset;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kBarOffset);
+    uint64_t *wfull = bars, *wempty = bars + SW;                          // W ring
+    uint64_t *xfull = bars + 2 * SW, *xempty = xfull + A, *afull = xempty + A;   // X ring + A ring (xempty frees both)
+    uint64_t *tfull = afull + A, *tempty = tfull + 2;                     // accumulator halves
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                              // 0 = leader: issues the MMAs
+    const uint32_t ntok = a.ntok, half_rows = ntok >> 1, q = ntok >> 2, nh = ntok >> 1;   // rows per CTA, rows per CTA per half, MMA N
+    const uint32_t slab = half_rows * 128u;                               // bytes of one k-block of activations in this CTA
+    const uint32_t KB = a.k_blocks, n_pairs_grid = gridDim.x >> 1, tile0 = blockIdx.x >> 1;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        if (a.y_f32 == nullptr) prefetch_tmap(&tmap_y);
+        for (int s = 0; s < SW; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 4); }
+        for (int s = 0; s < A; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); mbar_init(afull + s, 8); }   // afull: dequant warps of both CTAs
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 16); }                            // tempty: the 8 epilogue warps of both CTAs
+        fence_barrier_init();
+    }
+    cluster_sync_all();                                                   // barriers of both CTAs exist before anybody signals them
+    if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_col0 = C::kAccCols;
+    if (warp == 0) {
+        // ===================== activation producer: this CTA's half of the tile's tokens, bytes reported to the leader =====================
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const uint32_t xfull_leader = leader_addr(xfull);
+        uint32_t it = 0;
+        for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
+            const uint32_t mt = tile / a.n_pairs;
+            for (uint32_t kb = 0; kb < KB; kb += KBS, ++it) {
+                const uint32_t s = it % A, ph = (it / A) & 1;
+                mbar_wait(xempty + s, ph ^ 1);
+                if (elect_one()) {
+                    if (!(a.dbg & 8)) {
+                        if (rank == 0) mbar_arrive_expect_tx(xfull + s, 2 * KBS * slab);
+                        // box {64 k, ntok/2 tokens, KBS k-blocks}; tokens past M and k-blocks past K are zero-filled
+                        tma_load_3d_pair(smem + s * C::kXStage, &tmap_x, xfull_leader + s * 8, 0, (int)(mt * ntok + rank * half_rows), (int)kb);
+                    } else if (rank == 0) {
+                        mbar_arrive(xfull + s);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===================== weight producers: this CTA's own 128 columns =====================
+        const uint32_t me = (uint32_t)(warp - 2);
+        uint32_t it = 0;
+        for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
+            const uint32_t nc = tile % a.n_pairs;
+            const uint32_t nt = 2 * nc + rank < a.n_tiles ? 2 * nc + rank : a.n_tiles - 1;    // odd tile count: the last pair's second CTA re-reads the last tile (stores nothing)
+            const uint8_t *wsrc = a.packed + ((size_t)nt * KB) * C::kWBytes;
+            const uint2 *psrc = a.dqparams + (size_t)nt * 128;
+            for (uint32_t kb = 0; kb < KB; kb += KBS, ++it) {
+                if ((it & 1) != me) continue;
+                const uint32_t nk = KB - kb < (uint32_t)KBS ? KB - kb : (uint32_t)KBS;
+                const uint32_t s = it % SW, ph = (it / SW) & 1;
+                mbar_wait(wempty + s, ph ^ 1);
+                if (elect_one()) {
+                    uint8_t *stage = smem_w + s * C::kWStage;
+                    mbar_arrive_expect_tx(wfull + s, nk * (C::kWBytes + C::kPBytes));
+                    bulk_load(stage, wsrc + (size_t)kb * C::kWBytes, nk * C::kWBytes, wfull + s);
+                    for (uint32_t sub = 0; sub < nk; ++sub) {
+                        const uint32_t g = (kb + sub) / a.group_kb;
+                        bulk_load(stage + KBS * C::kWBytes + sub * C::kPBytes, psrc + (size_t)g * a.Npad, C::kPBytes, wfull + s);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (leader CTA; one elected lane): per stage, half 0 then half 1 =====================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((nh >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        uint32_t it = 0, n_item = 0;
+        for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
+            const uint32_t tph = n_item & 1;
+            ++n_item;
+            bool ready = false;
+            for (uint32_t kb = 0; kb < KB; kb += KBS, ++it) {
+                const uint32_t nk = KB - kb < (uint32_t)KBS ? KB - kb : (uint32_t)KBS;
+                const uint32_t s = it % A, ph = (it / A) & 1;
+                if (!ready) {
+                    mbar_wait(xfull + s, ph);          // both CTAs' activation halves landed
+                    mbar_wait(afull + s, ph);          // both CTAs' A slots written to tensor memory
+                    tc_fence_after();
+                }
+                const uint32_t stage_addr = smem_u32(smem + s * C::kXStage);
+                const uint32_t a_tmem = tmem_base + a_col0 + s * C::kSlotCols;
+                const bool first = kb == 0, last = kb + KBS >= KB;
+                if (lane == 0) TRACE2(1, it);
+                // ---- token half 0 ----
+                if (first) { mbar_wait(tempty + 0, tph ^ 1); tc_fence_after(); }      // previous tile's half 0 drained (both CTAs)
+                if (elect_one()) {
+                    if (!(a.dbg & 1)) {
+                        for (uint32_t sub = 0; sub < nk; ++sub) {
+                            const uint64_t bdesc = make_b_desc(stage_addr + sub * slab);
+#pragma unroll
+                            for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                                umma_ts_pair(tmem_base, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
+                        }
+                    }
+                    if (last) umma_commit_pair(tfull + 0);
+                }
+                __syncwarp();
+                // peek at the next stage while those MMAs run (never blocks: half 1 must be issued first)
+                ready = false;
+                if (!last) {
+                    const uint32_t s2 = (it + 1) % A, ph2 = ((it + 1) / A) & 1;
+                    if (mbar_try(xfull + s2, ph2) && mbar_try(afull + s2, ph2)) { tc_fence_after(); ready = true; }
+                }
+                // ---- token half 1 ----
+                if (first) { mbar_wait(tempty + 1, tph ^ 1); tc_fence_after(); }
+                if (lane == 0) TRACE2(2, it);
+                if (elect_one()) {
+                    if (!(a.dbg & 1)) {
+                        for (uint32_t sub = 0; sub < nk; ++sub) {
+                            const uint64_t bdesc = make_b_desc(stage_addr + sub * slab + q * 128u);
+#pragma unroll
+                            for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                                umma_ts_pair(tmem_base + 128, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
+                        }
+                    }
+                    if (last) umma_commit_pair(tfull + 1);
+                    umma_commit_pair(xempty + s);      // frees the activation stage and the A slot in both CTAs
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4 && warp < kEpiWarp0) {
+        // ===================== dequant warps: own 128 columns -> own tensor memory; arrive at the leader =====================
+        const uint32_t grp = (uint32_t)(warp - 4) >> 2;
+        const int quarter = warp & 3;
+        const int n_local = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0;
+        const uint32_t afull_leader = leader_addr(afull);
+        uint32_t it = 0;
+        for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
+            for (uint32_t kb = 0; kb < KB; kb += KBS, ++it) {
+                if (it % NDQ != grp) continue;
+                const uint32_t nk = KB - kb < (uint32_t)KBS ? KB - kb : (uint32_t)KBS;
+                const uint32_t sw = it % SW, wph = (it / SW) & 1;
+                const uint32_t sl = it % A, aph = (it / A) & 1;
+                if (it >= (uint32_t)A) mbar_wait(xempty + sl, aph ^ 1);     // MMAs of the slot's previous user completed
+                mbar_wait(wfull + sw, wph);
+                tc_fence_after();
+                if (quarter == 0 && lane == 0) TRACE2(0, it);
+                const uint8_t *stage = smem_w + sw * C::kWStage;
+                for (uint32_t sub = 0; sub < nk; ++sub) {
+                    const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes);
+                    const uint2 prm = lds64(smem_u32(stage + KBS * C::kWBytes + sub * C::kPBytes) + (uint32_t)n_local * 8u);
+                    uint32_t vals[32];
+                    if (!(a.dbg & 2)) dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) vals[e] = prm.x + e;
+                    }
+                    tmem_st32(lane_addr + sl * C::kSlotCols + sub * kACols, vals);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(wempty + sw);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(afull_leader + sl * 8);
+                if (quarter == 0 && lane == 0) TRACE2(3, it);
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue warps: drain half 0, re-arm it, drain half 1, re-arm it =====================
+        // Eight warps: warp%4 = TMEM lane quarter, `part` = which CTA's token rows (accumulator columns [part*q, (part+1)*q) of a
+        // half).  Two phases per half.  Phase 1 is on the tensor pipe's critical path (the accumulator half is single-
+        // buffered): the warp's q <= 64 columns are pulled into registers as packed bf16 (<= 32 registers) and the half is
+        // handed back to the MMA warp BEFORE anything is stored.  Phase 2, the stores, then overlaps the next MMAs.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int quarter = warp & 3;
+        const uint32_t part = (uint32_t)(warp - kEpiWarp0) >> 2;
+        const uint32_t tempty_leader = leader_addr(tempty);
+        const size_t ldy = a.N;
+        uint32_t n_item = 0;
+        for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
+            const uint32_t mt = tile / a.n_pairs, nc = tile % a.n_pairs;
+            const uint32_t tph = n_item & 1;
+            const uint32_t nt = 2 * nc + rank;
+            const uint32_t n = nt * 128 + quarter * 32 + lane;
+            const bool n_ok = nt < a.n_tiles && n < a.N && !(a.dbg & 64);
+            const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
+#pragma unroll 1
+            for (uint32_t h = 0; h < 2; ++h) {
+                mbar_wait(tfull + h, tph);
+                tc_fence_after();
+                if (warp == kEpiWarp0 && lane == 0) TRACE2(4 + h, n_item);
+                const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + part * q;
+                const uint32_t tok0 = mt * ntok + part * half_rows + h * q;     // token of this warp's first column
+                const uint32_t n_tok = tok0 >= a.M ? 0u : (a.M - tok0 < q ? a.M - tok0 : q);   // valid rows among its q
+                if (a.y_f32 == nullptr) {
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int g2 = 0; g2 < 4; ++g2) {
+                        const uint32_t c = (uint32_t)(g2 * 16);
+                        if (c + 16 <= q) {
+                            uint32_t v[16];
+                            tmem_ld16(t_acc + c, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[2 * j]) + bias, __uint_as_float(v[2 * j + 1]) + bias);
+                                pk[g2 * 8 + j] = *reinterpret_cast<uint32_t *>(&b2);
+                            }
+                        } else if (c + 8 <= q) {
+                            uint32_t v[8];
+                            tmem_ld8(t_acc + c, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[2 * j]) + bias, __uint_as_float(v[2 * j + 1]) + bias);
+                                pk[g2 * 8 + j] = *reinterpret_cast<uint32_t *>(&b2);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader + h * 8);   // this warp's columns are out: 16 such arrivals free the half
+                    if (warp == kEpiWarp0 && lane == 0) TRACE2(6 + h, n_item);
+                    // phase 2: registers -> staging [part][token][128 columns] -> two bulk tensor stores (rows past M and columns past
+                    // N are clipped by the TMA unit).  The staging buffer is reused per half: wait until the previous store has
+                    // read it.
+                    if (!(a.dbg & 64)) {
+                        if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        named_bar_sync(1, 256);
+                        const uint32_t sbase = smem_u32(smem + C::kOutOffset) + (part * q) * 256u + (uint32_t)(quarter * 32 + lane) * 2u;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            if ((uint32_t)(g * 8) < q) {
+#pragma unroll
+                                for (int j = 0; j < 8; j += 2) {
+                                    const uint32_t w = pk[(g * 8 + j) >> 1];
+                                    sts_u16(sbase + (uint32_t)(g * 8 + j) * 256u, w);
+                                    sts_u16(sbase + (uint32_t)(g * 8 + j + 1) * 256u, w >> 16);
+                                }
+                            }
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        named_bar_sync(1, 256);
+                        if (warp == kEpiWarp0 && lane == 0 && nt < a.n_tiles) {
+                            const uint32_t src = smem_u32(smem + C::kOutOffset);
+                            const int tokA = (int)(mt * ntok + h * q);
+                            tma_store_2d(&tmap_y, src, (int)(nt * 128), tokA);
+                            tma_store_2d(&tmap_y, src + q * 256u, (int)(nt * 128), tokA + (int)half_rows);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                } else {
+                    // f32 (and optionally bf16) output: the stack's last layer only.  Columns are stored as they are read.
+#pragma unroll 1
+                    for (uint32_t c0 = 0; c0 < q; c0 += 8) {
+                        uint32_t v[8];
+                        tmem_ld8(t_acc + c0, v);
+                        tmem_ld_wait();
+                        if (c0 + 8 >= q) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(tempty_leader + h * 8);
+                        }
+                        if (!n_ok) continue;
+                        const size_t o = (size_t)(tok0 + c0) * ldy + n;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (c0 + j < n_tok) {
+                                const float f = __uint_as_float(v[j]) + bias;
+                                a.y_f32[o + (size_t)j * ldy] = f;
+                                if (a.y_bf16) a.y_bf16[o + (size_t)j * ldy] = __float2bfloat16_rn(f);
+                            }
+                        }
+                    }
+                }
+            }
+            ++n_item;
+        }
+        if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // output writes complete before the CTA exits
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                // the partner may still signal barriers / read shared memory of this CTA
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+}
+
 // stream-K fix-up: tiles that were cut by a CTA boundary get y = sum of their partial tiles (in CTA
 // order: deterministic) + bias.  One block per output tile; complete tiles return immediately.
 template <int NTOK>
@@ -1184,7 +1581,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         cudaMemsetAsync(a.trace, 0, 8 * 256 * sizeof(long long), ctx->stream);
     }
     // dense problems (>= 4 tiles per SM): whole tiles round-robin; otherwise stream-K over all SMs
-    const uint32_t sms = (uint32_t)ctx->sm_count;
+    const uint32_t sms = (uint32_t)(ctx->sm_limit > 0 && ctx->sm_limit < ctx->sm_count ? ctx->sm_limit : ctx->sm_count);
     a.stream_k = 0;
     uint32_t grid = tiles < sms ? tiles : sms;
     if (tiles < 4 * sms) {
@@ -1200,7 +1597,7 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     // traffic per SM, which is what bounds the 1-CTA kernel: ~10 TB/s of L2 reads at 8192 tokens)
     static const int pair_env = getenv("DLLM_UMMA_PAIR") ? atoi(getenv("DLLM_UMMA_PAIR")) : 0;
     const uint32_t n_pairs = (a.n_tiles + 1) / 2;
-    const bool use_pair = pair_env != 0 && NTOK == 128 && !a.stream_k && x3d && !(a.dbg & 128) && n_pairs * a.m_tiles >= sms / 2;
+    const bool use_pair = pair_env == 1 && NTOK == 128 && !a.stream_k && x3d && !(a.dbg & 128) && n_pairs * a.m_tiles >= sms / 2;
     using CP = Cfg<CB, NTOK, KBS, NDQ, false, true>;
     CUtensorMap tmap_pair;
     if (use_pair) {
@@ -1272,10 +1669,145 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
     return DLLM_OK;
 }
 
+
+// tokens per pair tile: the candidate that needs the fewest token-columns of MMA time on sms/2 CTA pairs (full waves count;
+// ties go to the wider tile: fewer weight passes)
+static uint32_t pair2_pick_ntok(size_t M, uint32_t n_pairs, uint32_t pairs_hw) {
+    uint32_t best = 0;
+    uint64_t best_cost = ~0ull;
+    for (uint32_t ntok = 256; ntok >= 128; ntok -= 32) {
+        const uint64_t m_tiles = (M + ntok - 1) / ntok, tiles = m_tiles * n_pairs;
+        const uint64_t waves = (tiles + pairs_hw - 1) / pairs_hw;
+        const uint64_t cost = waves * (ntok + 6);          // + a few columns' worth of per-tile set-up / drain
+        if (cost < best_cost) { best_cost = cost; best = ntok; }
+    }
+    return best;
+}
+
+static int pair2_mode() {
+    // DLLM_UMMA_PAIR: unset / 2 = the 256-token CTA-pair kernel for dense problems (default), 0 = 1-CTA kernel only,
+    // 1 = the 128-token pair variant of round 1 (experiments)
+    static const int m = getenv("DLLM_UMMA_PAIR") ? atoi(getenv("DLLM_UMMA_PAIR")) : 2;
+    return m;
+}
+
+// dense problems only (whole tiles, K % 64 == 0, enough tiles for the 74 pairs); everything else stays on the 1-CTA kernel
+static bool pair2_applicable(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, const float *y_f32, const void *y_bf16) {
+    if (pair2_mode() != 2 || qw->K % WL_TILE_K != 0 || M < 1024) return false;
+    if (wl_container_bits(qw->bits) == 8) return false;        // 8-bit tiles leave too few W stages beside the output staging
+    // bf16 output leaves through a bulk tensor store: 16-byte aligned rows
+    if (!y_f32 && (qw->N % 8 != 0 || (reinterpret_cast<uintptr_t>(y_bf16) & 15u) != 0)) return false;
+    const uint32_t n_pairs = (uint32_t)((qw->n_tiles + 1) / 2);
+    const uint32_t pairs_hw = (uint32_t)(ctx->sm_limit > 0 && ctx->sm_limit < ctx->sm_count ? ctx->sm_limit : ctx->sm_count) / 2;
+    const uint32_t ntok = pair2_pick_ntok(M, n_pairs, pairs_hw);
+    return (uint64_t)((M + ntok - 1) / ntok) * n_pairs >= pairs_hw / 2;
+}
+
+template <int CB>
+int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, size_t M, float *y_f32, void *y_bf16) {
+    using C = CfgP2<CB>;
+    constexpr int NDQ = kNDQ;
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    Pair2Args a;
+    a.packed = qw->d_packed; a.dqparams = qw->d_dqparams; a.bias = qw->d_bias;
+    a.y_f32 = y_f32; a.y_bf16 = (__nv_bfloat16 *)y_bf16;
+    a.M = (uint32_t)M; a.N = (uint32_t)qw->N; a.Npad = (uint32_t)(qw->n_tiles * 128);
+    a.k_blocks = (uint32_t)qw->k_blocks; a.n_tiles = (uint32_t)qw->n_tiles; a.n_pairs = (a.n_tiles + 1) / 2;
+    a.group_kb = (uint32_t)(qw->group / WL_TILE_K);
+    const uint32_t pairs_hw = (uint32_t)(ctx->sm_limit > 0 && ctx->sm_limit < ctx->sm_count ? ctx->sm_limit : ctx->sm_count) / 2;
+    static const int ntok_env = getenv("DLLM_UMMA_NTOK2") ? atoi(getenv("DLLM_UMMA_NTOK2")) : 0;     // experiments only
+    a.ntok = (ntok_env >= 32 && ntok_env <= 256 && ntok_env % 32 == 0) ? (uint32_t)ntok_env : pair2_pick_ntok(M, a.n_pairs, pairs_hw);
+    a.m_tiles = (uint32_t)((M + a.ntok - 1) / a.ntok);
+    a.tiles = a.n_pairs * a.m_tiles;
+    static const uint32_t dbg_flags = getenv("DLLM_UMMA_DBG") ? (uint32_t)atoi(getenv("DLLM_UMMA_DBG")) : 0u;
+    a.dbg = dbg_flags;
+    a.trace = nullptr;
+    if (a.dbg & 128) {
+        DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, 8 * 256 * sizeof(long long)));
+        a.trace = (long long *)ctx->lin_flags.p;
+        cudaMemsetAsync(a.trace, 0, 8 * 256 * sizeof(long long), ctx->stream);
+    }
+
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {WL_TILE_K, (cuuint64_t)M, (cuuint64_t)(qw->K / WL_TILE_K)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)qw->K * 2, (cuuint64_t)WL_TILE_K * 2};
+    const cuuint32_t box[3] = {WL_TILE_K, a.ntok / 2, (cuuint32_t)C::KBS};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(x_bf16), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    // bf16 output [M, N] row-major: box {128 columns, ntok/4 tokens} = one part of an accumulator half in the staging buffer
+    CUtensorMap tmap_y = tmap;
+    if (!y_f32) {
+        const cuuint64_t ydim[2] = {(cuuint64_t)qw->N, (cuuint64_t)M};
+        const cuuint64_t ystride[1] = {(cuuint64_t)qw->N * 2};
+        const cuuint32_t ybox[2] = {128, a.ntok / 4};
+        const cuuint32_t yestr[2] = {1, 1};
+        r = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y_bf16, ydim, ystride, ybox, yestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
+    }
+    DLLM_TRY(ensure_smem_attr(ctx, umma_qlinear_pair2_kernel<CB, NDQ>, C::kTotal));
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->prof_on) {
+        while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) {
+            cudaEvent_t e;
+            CUDA_TRY(ctx, cudaEventCreate(&e));
+            ctx->prof_ev.push_back(e);
+        }
+        ev0 = ctx->prof_ev[2 * ctx->prof_n];
+        ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
+        CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    const uint32_t pairs = a.tiles < pairs_hw ? a.tiles : pairs_hw;
+    static const bool no_pdl = getenv("DLLM_UMMA_NO_PDL") != nullptr;      // experiments only
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3((12 + 4 * NDQ) * 32);
+    cfg.dynamicSmemBytes = C::kTotal;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, umma_qlinear_pair2_kernel<CB, NDQ>, tmap, tmap_y, a));
+    LAUNCH_CHECK(ctx);
+    if (a.dbg & 128) {   // dump the timeline of cluster 0's leader (timing experiments only)
+        std::vector<long long> hst(8 * 256);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(hst.data(), a.trace, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        FILE *f = fopen("gpurun_out/pair2_trace.csv", "w");
+        if (f) {
+            fprintf(f, "i,dq_start(stage),mma_h0(stage),mma_h1(stage),dq_end(stage),epi_h0_ready(tile),epi_h1_ready(tile),epi_h0_released(tile),epi_h1_released(tile)\n");
+            for (int i = 0; i < 256; ++i) {
+                fprintf(f, "%d", i);
+                for (int r = 0; r < 8; ++r) fprintf(f, ",%lld", hst[r * 256 + i]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
+    if (ev1) {
+        CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
+        ctx->prof_n++;
+        ctx->prof_flops += 2.0 * (double)M * (double)qw->K * (double)qw->N;
+        ctx->prof_bytes += (double)qw->K * qw->N * qw->bits / 8.0 + (double)(qw->K / qw->group) * qw->N * 8.0 +
+                           2.0 * M * qw->K + (y_f32 ? 4.0 : 0.0) * M * qw->N + (y_bf16 ? 2.0 : 0.0) * M * qw->N;
+    }
+    return DLLM_OK;
+}
+
 // two k-blocks (128 k = one quantization group) per pipeline stage
 template <int CB>
 int32_t launch_umma_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const void *x, size_t M, float *y_f32, void *y_bf16) {
     static const int ntok_env = getenv("DLLM_UMMA_NTOK") ? atoi(getenv("DLLM_UMMA_NTOK")) : 0;     // experiments only
+    if constexpr (CB != 8) {
+        if (pair2_applicable(ctx, qw, M, y_f32, y_bf16)) return launch_umma_pair2<CB>(ctx, qw, x, M, y_f32, y_bf16);
+    }
     if (M <= 16) return launch_umma<CB, 16, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
     if (M <= 32) return launch_umma<CB, 32, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
     if (M <= 64 || ntok_env == 64) return launch_umma<CB, 64, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);

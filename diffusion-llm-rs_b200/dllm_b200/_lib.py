@@ -83,6 +83,7 @@ SIGNATURES = {
     "dllm_last_error": (C.c_char_p, [c_vp]),
     "dllm_launch_count": (C.c_uint64, [c_vp]),
     "dllm_sm_count": (C.c_int32, [c_vp]),
+    "dllm_graph_replay_count": (C.c_uint64, [c_vp]),
     "dllm_selftest_division": (C.c_int32, [c_vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "dllm_profile_begin": (C.c_int32, [c_vp]),
     "dllm_profile_end": (C.c_int32, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -142,11 +143,19 @@ SIGNATURES = {
     "dllm_add_noise_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, c_vp]),
     "dllm_denoise_step_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, C.c_int32]),
     "dllm_denoise_step": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, C.c_int32]),
+    "dllm_last_step_breakdown": (C.c_int32, [c_vp, c_f32p, c_f32p, c_f32p]),
     "dllm_sample": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, C.c_int32, c_vp]),
+    "dllm_noise_fill": (C.c_int32, [c_vp, C.c_uint64, C.c_uint64, C.c_uint64, c_sz, c_vp]),
+    "dllm_noise_fill_dev": (C.c_int32, [c_vp, C.c_uint64, C.c_uint64, C.c_uint64, c_sz, c_vp]),
+    "dllm_denoise_step_seeded_dev": (C.c_int32, [c_vp, c_vp, c_vp, C.c_uint64, c_sz, c_sz, c_sz, C.c_int32, C.c_int32]),
+    "dllm_sample_seeded": (C.c_int32, [c_vp, c_vp, c_vp, C.c_uint64, c_sz, c_sz, c_sz, C.c_int32, C.c_int32, C.c_int32, c_vp]),
+    "dllm_sample_seeded_dev": (C.c_int32, [c_vp, c_vp, c_vp, C.c_uint64, c_sz, c_sz, c_sz, C.c_int32, C.c_int32, C.c_int32]),
     "dllm_progressive_bits": (C.c_uint8, [c_sz, c_sz, C.c_uint8, C.c_uint8, C.POINTER(C.c_int32)]),
     "dllm_kv_quantize": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_uint8, C.c_int32, C.POINTER(c_vp)]),
     "dllm_kv_quantize_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_uint8, C.c_int32,
                                          C.POINTER(c_vp)]),
+    "dllm_kv_quantize_sharded_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_uint8, C.c_int32,
+                                                 C.POINTER(c_vp)]),
     "dllm_kv_update_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp]),
     "dllm_kv_create": (C.c_int32, [c_vp, c_sz, c_sz, c_sz, C.c_uint8, C.c_int32, C.POINTER(c_vp)]),
     "dllm_kv_append": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz]),
@@ -160,6 +169,7 @@ SIGNATURES = {
     "dllm_tp_unique_id": (C.c_int32, [c_vp]),
     "dllm_tp_init": (C.c_int32, [c_vp, c_vp, C.c_int32, C.c_int32]),
     "dllm_tp_finalize": (C.c_int32, [c_vp]),
+    "dllm_tp_configure": (C.c_int32, [c_vp, C.c_int32, C.c_int32, C.c_int32]),
     "dllm_tp_allreduce_dev": (C.c_int32, [c_vp, c_vp, c_sz]),
     "dllm_tp_allgather_cols_dev": (C.c_int32, [c_vp, c_vp, c_sz, c_sz, c_vp]),
     "dllm_model_set_parallel": (C.c_int32, [c_vp, c_vp, c_vp, c_sz]),

@@ -251,6 +251,22 @@ class DiffuseLLM:
                                                         tt.ctypes.data, batch, feat, out.ctypes.data))
         return out, noise
 
+    def sample_seeded(self, model: QuantizedDiffusionModel, shape, num_steps: Optional[int] = None, seed: int = 42,
+                      x0=None, guard_t0: bool = True, use_graph: bool = True):
+        """DiffuseLLM::sample without cache (lib.rs:853-927) with the noise drawn on the device from the counter-based
+        generator "dllm_noise v1" (timestep t = stream t, initial x = stream num_steps): nothing is uploaded per step and
+        the step is replayed from one CUDA graph.  42 is the one seed the reference uses (examples/diffusion_example.rs:69)."""
+        batch, seq_len = shape
+        num_steps = num_steps if num_steps is not None else self.config.num_timesteps
+        feat = self.config.hidden_size * seq_len
+        x = np.ascontiguousarray(x0, np.float32) if x0 is not None else None
+        out = np.empty((batch, feat), np.float32)
+        with self._ctx.lock:
+            self._ctx._ck(self._ctx._lib.dllm_sample_seeded(self._ctx.h, model.h, x.ctypes.data if x is not None else None,
+                                                            seed, batch, feat, num_steps, int(guard_t0), model.path,
+                                                            int(use_graph), out.ctypes.data))
+        return out
+
     def init_kv_cache(self, batch_size: int) -> KVCacheEntry:
         """lib.rs:958-975: empty [layers, 0, hidden] cache with phase-aware bits"""
         shape = (self.config.num_layers, 0, self.config.hidden_size)

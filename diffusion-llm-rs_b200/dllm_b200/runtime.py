@@ -88,6 +88,20 @@ class Context:
         self._ck(self._lib.dllm_memcpy_d2h(self.h, _ptr(out), C.c_void_p(dptr), out.nbytes))
         return out
 
+    @property
+    def graph_replays(self) -> int:
+        return int(self._lib.dllm_graph_replay_count(self.h))
+
+    # ---- "dllm_noise v1": the seeded loop's counter-based N(0,1) generator (csrc/noise.cuh) ----
+    def noise_fill(self, seed: int, stream: int, n: int, first: int = 0) -> np.ndarray:
+        out = np.empty(int(n), np.float32)
+        with self.lock:
+            self._ck(self._lib.dllm_noise_fill(self.h, seed, stream, first, int(n), _ptr(out)))
+        return out
+
+    def noise_fill_dev(self, seed: int, stream: int, n: int, out_dev: int, first: int = 0):
+        self._ck(self._lib.dllm_noise_fill_dev(self.h, seed, stream, first, int(n), out_dev))
+
     # ---- quantizer B ----
     def quantize_tensor(self, x, bits):
         x = _f32(x).ravel()

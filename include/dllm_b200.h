@@ -88,6 +88,8 @@ DLLM_API void *dllm_ctx_stream(dllm_ctx *ctx);
 DLLM_API const char *dllm_last_error(const dllm_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 DLLM_API uint64_t dllm_launch_count(const dllm_ctx *ctx);
+/* number of CUDA-graph launches this ctx has made (each replays a whole captured denoise step) */
+DLLM_API uint64_t dllm_graph_replay_count(const dllm_ctx *ctx);
 DLLM_API int32_t dllm_sm_count(const dllm_ctx *ctx);
 
 /* per-launch CUDA-event timing of the dominant (tcgen05 linear) kernel on the context's stream.
@@ -272,11 +274,30 @@ DLLM_API int32_t dllm_denoise_step_dev(dllm_ctx *ctx, dllm_model *m, float *x_de
  * of the loop body at lib.rs:924-925 as seen by a host caller) */
 DLLM_API int32_t dllm_denoise_step(dllm_ctx *ctx, dllm_model *m, float *x, const float *z, size_t t, size_t batch,
                                    size_t feat, int32_t guard_t0, int32_t path);
+/* how the last dllm_denoise_step on this ctx spent its time (CUDA events on the compute stream): host->device copy of x,
+ * the step itself (forward + p_sample; the noise upload rides a second stream underneath), device->host copy of x_prev */
+DLLM_API int32_t dllm_last_step_breakdown(const dllm_ctx *ctx, float *h2d_ms, float *compute_ms, float *d2h_ms);
 /* DiffuseLLM::sample without cache, lib.rs:853-927.  x0: initial noise [batch, feat];
  * noises: [num_steps, batch, feat], slice t used at timestep t (slice 0 unused).  Host pointers. */
 DLLM_API int32_t dllm_sample(dllm_ctx *ctx, dllm_model *m, const float *x0, const float *noises,
                              size_t batch, size_t feat, size_t num_steps, int32_t guard_t0,
                              int32_t path, float *x_out);
+/* ---- seeded loop: the noise comes from "dllm_noise v1", a counter-based N(0,1) generator defined by this
+ * build (csrc/noise.cuh: splitmix64 -> Box-Muller with fixed-order f32 polynomials; element i of stream s depends on
+ * (seed, s, i) only; the CPU oracle reproduces it bit for bit).  The reference draws from an unseeded thread_rng
+ * (lib.rs:875-878, :1201), which no implementation can reproduce.  Timestep t uses stream t; the initial x uses stream
+ * num_steps.  Nothing is uploaded per step, and with use_graph != 0 the step is captured once as a CUDA graph and replayed
+ * with t held in device memory (one graph launch per step instead of one launch per kernel). */
+DLLM_API int32_t dllm_noise_fill(dllm_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t first, size_t n, float *out);
+DLLM_API int32_t dllm_noise_fill_dev(dllm_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t first, size_t n, float *out_dev);
+DLLM_API int32_t dllm_denoise_step_seeded_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, uint64_t seed, size_t t,
+                                              size_t batch, size_t feat, int32_t guard_t0, int32_t path);
+/* x0 == NULL: the initial x is drawn from stream num_steps */
+DLLM_API int32_t dllm_sample_seeded(dllm_ctx *ctx, dllm_model *m, const float *x0, uint64_t seed, size_t batch, size_t feat,
+                                    size_t num_steps, int32_t guard_t0, int32_t path, int32_t use_graph, float *x_out);
+/* x_dev: in = x_T, out = the sample; enqueues only */
+DLLM_API int32_t dllm_sample_seeded_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, uint64_t seed, size_t batch, size_t feat,
+                                        size_t num_steps, int32_t guard_t0, int32_t path, int32_t use_graph);
 /* progressive decode precision, lib.rs:886-897 (host arithmetic) */
 DLLM_API uint8_t dllm_progressive_bits(size_t num_steps, size_t t, uint8_t decode_bits,
                                        uint8_t min_decode_bits, int32_t *is_prefill);
@@ -291,6 +312,12 @@ DLLM_API int32_t dllm_kv_quantize(dllm_ctx *ctx, const float *keys, const float 
 DLLM_API int32_t dllm_kv_quantize_dev(dllm_ctx *ctx, const float *keys_dev, const float *values_dev,
                                       size_t layers, size_t seq, size_t hidden, uint8_t bits,
                                       int32_t scheme, dllm_kv **out);
+/* K / V whose token rows are sharded over the ranks of the context's group (dllm_tp_init): this rank's [layers, seq_local,
+ * hidden] slice.  ROW_D / FIXED_C need no exchange; TENSOR_B all-reduces the tensor's min / max (2 floats) so that every
+ * rank encodes with the whole tensor's scale / zero-point: the concatenated codes equal a single-GPU quantization. */
+DLLM_API int32_t dllm_kv_quantize_sharded_dev(dllm_ctx *ctx, const float *keys_dev, const float *values_dev,
+                                              size_t layers, size_t seq_local, size_t hidden, uint8_t bits,
+                                              int32_t scheme, dllm_kv **out);
 /* re-quantize into an existing entry (KVCacheEntry::update, lib.rs:246-276) */
 DLLM_API int32_t dllm_kv_update_dev(dllm_ctx *ctx, dllm_kv *kv, const float *keys_dev,
                                     const float *values_dev);
@@ -327,6 +354,11 @@ DLLM_API void dllm_kv_destroy(dllm_kv *kv);
 DLLM_API int32_t dllm_tp_unique_id(uint8_t id_out[128]);
 DLLM_API int32_t dllm_tp_init(dllm_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t world);
 DLLM_API int32_t dllm_tp_finalize(dllm_ctx *ctx);
+/* overlap of the row-parallel all-reduces with the GEMMs: the tokens are cut into `chunks` pieces (0 = default 2; 1 = no
+ * overlap, collectives on the compute stream) whose all-reduces run on a second stream under the next piece's GEMMs, which
+ * leave `reserve_sms` SMs (-1 = default 8) to the collective.  skip_comm != 0 runs the sharded stack WITHOUT its collectives
+ * (wrong results; measurement of the exposed collective time only). */
+DLLM_API int32_t dllm_tp_configure(dllm_ctx *ctx, int32_t chunks, int32_t reserve_sms, int32_t skip_comm);
 /* sum-all-reduce of a device f32 buffer over the TP group (row-parallel partial sums) */
 DLLM_API int32_t dllm_tp_allreduce_dev(dllm_ctx *ctx, float *buf_dev, size_t n);
 /* all-gather of column shards: in [M, N/world] per rank -> out [M, N] */

@@ -420,6 +420,78 @@ void orc_add_noise(const float *x_start, const float *noise, const size_t *t, si
     }
 }
 
+/* ===================== "dllm_noise v1": the counter-based normal generator of the seeded sampling loop =====================
+ * Defined by this build (the reference's noise is an unseeded thread_rng, lib.rs:875-878/:1201, and cannot be reproduced);
+ * specification in diffusion-llm-rs_b200/csrc/noise.cuh.  Every step is exact or ONE correctly rounded f32 operation in a
+ * fixed order, polynomials are evaluated with fmaf: this restatement and the CUDA kernels agree bit for bit. */
+static uint64_t dn_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static void dn_sincos_poly(float phi, float *s, float *c) {
+    const float p2 = phi * phi;
+    float ps = fmaf(p2, 2.75573192e-6f, -1.98412698e-4f);
+    ps = fmaf(p2, ps, 8.33333333e-3f);
+    ps = fmaf(p2, ps, -1.66666667e-1f);
+    ps = fmaf(p2, ps, 1.0f);
+    *s = phi * ps;
+    float pc = fmaf(p2, -2.75573192e-7f, 2.48015873e-5f);
+    pc = fmaf(p2, pc, -1.38888889e-3f);
+    pc = fmaf(p2, pc, 4.16666667e-2f);
+    pc = fmaf(p2, pc, -0.5f);
+    *c = fmaf(p2, pc, 1.0f);
+}
+static void dn_normal_pair(uint64_t key, uint64_t p, float *z0, float *z1) {
+    const uint64_t r = dn_splitmix64(key + p);
+    const uint32_t a = (uint32_t)(r >> 41), b = (uint32_t)(r >> 17) & 0xFFFFFFu;
+    const uint32_t v = 2u * a + 1u;
+    int e = 31 - __builtin_clz(v);
+    union { uint32_t u; float f; } pw;
+    pw.u = (uint32_t)(127 - e) << 23;
+    float m = (float)v * pw.f;
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
+    const float num = m - 1.0f, den = m + 1.0f;
+    const float t = num / den;
+    const float t2 = t * t;
+    float pl = fmaf(t2, 1.11111111e-1f, 1.42857143e-1f);
+    pl = fmaf(t2, pl, 0.2f);
+    pl = fmaf(t2, pl, 3.33333343e-1f);
+    pl = fmaf(t2, pl, 1.0f);
+    const float tt = 2.0f * t;
+    const float ln_m = tt * pl;
+    const float ln_u = fmaf((float)(e - 24), 6.93147181e-1f, ln_m);
+    const float arg = -2.0f * ln_u;
+    const float radius = sqrtf(arg);
+    const uint32_t quad = b >> 22, f = b & 0x3FFFFFu;
+    const int refl = f >= 0x200000u;
+    const uint32_t g = refl ? 0x3FFFFFu - f : f;
+    const float phi = (float)(2u * g + 1u) * 1.87253514e-7f;
+    float sp, cp;
+    dn_sincos_poly(phi, &sp, &cp);
+    const float sq = refl ? cp : sp, cq = refl ? sp : cp;
+    float cs, sn;
+    switch (quad) {
+        case 0: cs = cq; sn = sq; break;
+        case 1: cs = -sq; sn = cq; break;
+        case 2: cs = -cq; sn = -sq; break;
+        default: cs = sq; sn = -cq; break;
+    }
+    *z0 = radius * cs;
+    *z1 = radius * sn;
+}
+void orc_noise_normal(uint64_t seed, uint64_t stream, uint64_t i0, size_t n, float *out) {
+    const uint64_t key = dn_splitmix64(dn_splitmix64(seed) + stream);
+    for (size_t j = 0; j < n; ++j) {
+        const uint64_t i = i0 + j;
+        float z0, z1;
+        dn_normal_pair(key, i >> 1, &z0, &z1);
+        out[j] = (i & 1) ? z1 : z0;
+    }
+}
+
 uint8_t orc_progressive_bits(size_t num_steps, size_t t, uint8_t decode_bits, uint8_t min_bits,
                              int32_t *is_prefill) {
     *is_prefill = t > num_steps / 2;                          /* :886 */

@@ -118,6 +118,9 @@ void orc_p_sample(const float *x_t, const float *noise_pred, const float *z,
 /* add_noise, lib.rs:1100-1137: noisy = x_start * sqrt(alpha_bar_t) + noise * sqrt(1 - alpha_bar_t), t clamped to T-1 per row */
 void orc_add_noise(const float *x_start, const float *noise, const size_t *t, size_t batch, size_t feat,
                    const float *betas, size_t T, float *noisy);
+/* "dllm_noise v1": elements [i0, i0+n) of stream `stream` under `seed` (spec: diffusion-llm-rs_b200/csrc/noise.cuh).
+ * Not a reference function: the reference's noise (thread_rng) is unseeded; this is the generator the seeded loop uses. */
+void orc_noise_normal(uint64_t seed, uint64_t stream, uint64_t i0, size_t n, float *out);
 /* progressive decode bits, lib.rs:886-897. returns target bits; *is_prefill set. */
 uint8_t orc_progressive_bits(size_t num_steps, size_t t, uint8_t decode_bits, uint8_t min_bits,
                              int32_t *is_prefill);

@@ -306,6 +306,13 @@ def add_noise(x_start, t, noise, betas):
     return out
 
 
+def noise_normal(seed, stream, n, i0=0):
+    """"dllm_noise v1": n standard normals of stream `stream` under `seed`, starting at element i0."""
+    out = np.empty(int(n), np.float32)
+    lib().orc_noise_normal(C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(i0), C.c_size_t(int(n)), _p(out, C.c_float))
+    return out
+
+
 def progressive_bits(num_steps, t, decode_bits=4, min_bits=2):
     pre = C.c_int32()
     b = lib().orc_progressive_bits(C.c_size_t(num_steps), C.c_size_t(t), C.c_uint8(decode_bits),

@@ -15,4 +15,4 @@ with torch.cuda.stream(stream):
     for i in range(20): qw.forward_dev(x.data_ptr(), M, y.data_ptr(), PATH_UMMA)
 nl, ms, fl, by = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
 ctx._ck(ctx._lib.dllm_profile_end(ctx.h, C.byref(nl), C.byref(ms), C.byref(fl), C.byref(by)))
-print(f"dbg={os.environ.get('DLLM_UMMA_DBG','0')} K={K} N={N} bits={bits} M={M}: kernel {ms.value/nl.value*1e3:.1f} us  {fl.value/ms.value/1e9:.0f} TFLOP/s", flush=True)
+print(f"pair={os.environ.get('DLLM_UMMA_PAIR','-')} ntok2={os.environ.get('DLLM_UMMA_NTOK2','-')} dbg={os.environ.get('DLLM_UMMA_DBG','0')} K={K} N={N} bits={bits} M={M}: kernel {ms.value/nl.value*1e3:.1f} us  {fl.value/ms.value/1e9:.0f} TFLOP/s", flush=True)

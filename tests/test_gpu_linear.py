@@ -430,20 +430,71 @@ def test_qlinear_umma_vs_simt_full_width(ctx):
     qw.close()
 
 
-def test_umma_cta_pair_variant_is_bit_identical():
-    """The CTA-pair (tcgen05 cta_group::2) variant of the dense kernel — opt-in with DLLM_UMMA_PAIR=1 — must produce the
-    1-CTA kernel's output bit for bit on a dense, ragged shape with an odd number of column tiles."""
+def _pair_check(mode, shape=None, ntok2=None):
     import os
     import subprocess
     import sys
     import tempfile
     script = os.path.join(os.path.dirname(__file__), "umma_pair_check.py")
-    outs = []
     with tempfile.TemporaryDirectory() as d:
-        for pair in ("0", "1"):
-            out = os.path.join(d, f"y{pair}.npy")
-            env = dict(os.environ, DLLM_UMMA_PAIR=pair)
-            r = subprocess.run([sys.executable, script, out], capture_output=True, text=True, timeout=300, env=env)
-            assert "PAIR_CHECK_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
-            outs.append(np.load(out))
-    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+        out = os.path.join(d, "y.npy")
+        env = dict(os.environ, DLLM_UMMA_PAIR=str(mode))
+        env.pop("DLLM_UMMA_NTOK2", None)
+        if ntok2:
+            env["DLLM_UMMA_NTOK2"] = str(ntok2)
+        cmd = [sys.executable, script, out] + ([str(v) for v in shape] if shape else [])
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        assert "PAIR_CHECK_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+        return np.load(out)
+
+
+def test_umma_cta_pair_variant_is_bit_identical():
+    """The CTA-pair (tcgen05 cta_group::2) kernels — the 256-token pair kernel the denoise step runs (DLLM_UMMA_PAIR=2, the
+    default for dense problems) and round 1's 128-token variant (=1) — must produce the 1-CTA kernel's output (=0) bit for
+    bit on a dense, ragged shape with an odd number of column tiles."""
+    base = _pair_check(0)
+    for mode in (1, 2):
+        assert np.array_equal(base.view(np.uint32), _pair_check(mode).view(np.uint32)), f"pair mode {mode}"
+
+
+@pytest.mark.parametrize("ntok2", [128, 160, 192, 224, 256])
+def test_umma_pair2_tile_widths_bit_identical(ntok2):
+    """Every tile width the 256-token pair kernel may pick (MMA N = ntok/2 = 64..128, token halves of 32..64 rows per CTA),
+    on a shape with an odd k-block count (K = 448 with groups of 64: seven k-blocks, the last stage holds one), ragged tokens and ragged columns."""
+    shape = (448, 7000, 2100, 64)   # >= 4 tiles per SM: the 1-CTA kernel runs whole tiles too (same summation order)
+    base = _pair_check(0, shape)
+    assert np.array_equal(base.view(np.uint32), _pair_check(2, shape, ntok2).view(np.uint32))
+
+
+@pytest.mark.parametrize("KN", [(2048, 2048), (2048, 8192), (8192, 2048)])
+def test_umma_benchmark_shapes_match_oracle(ctx, O, KN):
+    """The launches the headline number is made of: 8192 tokens x the three layer shapes of the 1B-class stack, full size,
+    through the default dense path.  Weight codes / scales / zero-points must equal the oracle's bit for bit; the output is
+    checked against the f64-accumulated oracle on a 256-token x 64-column sample spread over the tile grid, and must be
+    finite everywhere.  Bound: 1e-2 relative (bf16 operands, f32 accumulate — BASELINE.json north_star)."""
+    import torch
+    from dllm_b200 import QWeight, PATH_AUTO
+    K, N = KN
+    M = 8192
+    g = torch.Generator(device="cuda").manual_seed(K + N)
+    w = torch.randn(K, N, device="cuda", generator=g) * (1.0 / K ** 0.5)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    y = torch.empty(M, N, device="cuda")
+    torch.cuda.synchronize()
+    qw = QWeight.quantize_dev(ctx, w.data_ptr(), K, N, 4, 128)
+    qw.forward_dev(x.data_ptr(), M, y.data_ptr(), PATH_AUTO)
+    ctx.sync()
+    codes, scales, zps = qw.export()
+    oc, os_, oz = O.quantize_weight_grouped(w.cpu().numpy(), 4, 128)
+    assert np.array_equal(codes, oc) and np.array_equal(scales.view(np.uint32), os_.view(np.uint32)) and np.array_equal(zps, oz)
+    rng = np.random.default_rng(7)
+    toks = np.unique(np.concatenate([rng.integers(0, M, 250), [0, 127, 128, 223, 224, 255, 256, M - 1]]))
+    cols = np.unique(np.concatenate([rng.integers(0, N, 60), [0, 127, 128, 255, 256, N - 1]]))
+    wd = O.dequantize_weight_grouped(oc, os_, oz, 128)[:, cols].astype(np.float64)
+    y64 = x.cpu().numpy()[toks].astype(np.float64) @ wd
+    ys = y.cpu().numpy()
+    assert np.all(np.isfinite(ys))
+    got = ys[np.ix_(toks, cols)]
+    assert np.linalg.norm(got - y64) <= 1e-2 * np.linalg.norm(y64)
+    assert np.abs(got - y64).max() <= 2e-2 * np.abs(y64).max()
+    qw.close()

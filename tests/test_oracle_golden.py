@@ -281,6 +281,21 @@ def test_add_noise_matches_numpy_restatement():
     assert O.add_noise(np.zeros((0, 8), F), [], np.zeros((0, 8), F), betas).shape == (0, 8)
 
 
+KAT_NOISE_42_3 = [1067104742, 3195617084, 1019446180, 3198130443]   # f32 bit patterns of noise(seed 42, stream 3)[0:4]
+
+
+def test_noise_generator_properties():
+    """"dllm_noise v1": counter-based (element i of stream s depends on (seed, s, i) only), standard normal."""
+    z = O.noise_normal(42, 3, 400_000)
+    assert np.all(np.isfinite(z)) and abs(float(z.mean())) < 6e-3 and abs(float(z.std()) - 1) < 6e-3
+    assert abs(float((z.astype(np.float64) ** 4).mean()) - 3.0) < 0.1                 # kurtosis of N(0,1)
+    assert bits_equal(O.noise_normal(42, 3, 100, i0=1001), z[1001:1101])              # random access
+    assert not np.array_equal(O.noise_normal(42, 4, 64), z[:64]) and not np.array_equal(O.noise_normal(43, 3, 64), z[:64])
+    assert abs(float(np.corrcoef(z[0::2], z[1::2])[0, 1])) < 0.01                     # the two members of a Box-Muller pair
+    # known answers (pin the constants of the specification)
+    assert [int(v) for v in O.noise_normal(42, 3, 4).view(np.uint32)] == KAT_NOISE_42_3
+
+
 def test_progressive_bits():
     # lib.rs:886-897 with defaults decode=4, min=2, num_steps=64
     assert O.progressive_bits(64, 63) == (int(F(4) * (F(1) - F(1 / 32)) + F(2) * F(1 / 32)), True)
