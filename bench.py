@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """bench.py — BASELINE.json metric on the B200-native path, next to the reference's CPU path.
 
-Default workload (BASELINE.json configs[2]): one denoising step of a synthetic 1B-class 4-bit model
+Headline workload (BASELINE.json configs[2]): one denoising step of a synthetic 1B-class 4-bit model
 (120 quantized linears `x·W+b`, group 128), 256-token canvas x batch 32 = 8192 tokens, on one B200.
-  step  = DiffusionModel::forward through the stack (tcgen05 dequant-GEMM) + p_sample
-  value = denoise steps/s, inputs resident in HBM (CUDA events on the launching stream)
-  e2e   = the same step through the host-buffer C ABI call (dllm_denoise_step): x and noise copied
-          H2D from pinned memory and x_prev copied D2H inside the timed region, every step
-N > 1 (torchrun): independent denoising batches, one replica per GPU (data parallel, weak scaling,
-no data-path collective); `--parallelism tp` runs the tensor-parallel 7B-class config instead.
-
-The line also carries the GB/s half of the metric as extras ("gemv": 4-bit 14336^2 dequant-GEMV from a CUDA graph,
-"kv_quant": per-token KV quantize / dequantize), each with its fraction of the measured HBM bandwidth; the full
-sweeps of BASELINE.json configs[1] / [4] are scripts/microbench.py.
+  step     = DiffusionModel::forward through the stack (tcgen05 dequant-GEMM) + p_sample
+  value    = denoise steps/s, inputs resident in HBM; CUDA events on the launching stream, NO per-launch profiling
+  roofline = a second pass over the same steps with every dense-kernel launch bracketed by CUDA events
+  e2e      = the same step through the host-buffer C ABI call (dllm_denoise_step): x and noise copied H2D from pinned
+             memory and x_prev copied D2H inside the timed region, every step; two host threads with one context each
+             keep the GPU busy (one thread's copies run under the other's compute); the single-thread rate and the
+             H2D / compute / D2H breakdown of one call are reported beside it
+N > 1 (torchrun): the headline is one independent replica per GPU (data parallel, weak scaling, no data-path collective).
+Every N (including 1) also carries
+  tp7b  — BASELINE.json configs[3]: the 7B-class stack (H=4096, F=14336, 32 layers) on the same 8192 tokens, sharded
+          column- / row-wise over the N GPUs with the row-parallel all-reduces overlapped on a second stream (strong
+          scaling), the same stack with the tokens split instead (no collective), the exposed collective time, and one
+          64-step seeded sampling loop
+  kv32k — BASELINE.json configs[4]: K and V [32 layers, 32768 tokens, 4096] quantize + dequantize at 8 and 4 bits, per-token
+          (scheme D) and per-tensor (scheme B, min/max all-reduced over the ranks), token rows sharded over the N GPUs
+and, at N = 1, the GB/s half of the metric ("gemv": dequant-GEMV from a CUDA graph at 2/4/8 bits; "kv_quant").
 `--impl reference` times the oracle port of the reference's CPU path on the host cores.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -70,7 +77,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         self.stop_flag = True
@@ -126,6 +133,28 @@ def cpu_denoise_step_seconds(model, threads, sample_tokens):
     return total, ";".join(detail)
 
 
+def cpu_linearity_check(model, threads, sample_tokens):
+    """The CPU arm scales the matmul time of `sample_tokens` tokens linearly to the full 8192.  Checked, not assumed: the
+    smallest layer shape is also run once on ALL tokens; returns measured_full / (sample time x tokens / sample)."""
+    import numpy as np
+    from oracle import pyoracle as O
+    _, shapes = layer_shapes(model)
+    K, N = min(set(shapes), key=lambda s: s[0] * s[1])
+    tokens = BATCH * CANVAS
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((K, N)) * 0.02).astype(np.float32)
+    xs = rng.standard_normal((sample_tokens, K)).astype(np.float32)
+    xf = rng.standard_normal((tokens, K)).astype(np.float32)
+    O.linear_f32(xs, w, None, threads=threads)
+    t0 = time.perf_counter()
+    O.linear_f32(xs, w, None, threads=threads)
+    t1 = time.perf_counter()
+    O.linear_f32(xf, w, None, threads=threads)
+    t2 = time.perf_counter()
+    return {"shape": f"{K}x{N}", "full_tokens_s": t2 - t1, "sample_scaled_s": (t1 - t0) * tokens / sample_tokens,
+            "ratio_full_over_scaled": (t2 - t1) / ((t1 - t0) * tokens / sample_tokens)}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -138,65 +167,112 @@ def run_reference(args, rank):
             t_all.append(secs)
     secs = sum(t_all) / len(t_all)
     val = 1.0 / secs
-    sample_desc = (f"oracle port (C, -O2, no FMA): per step one linear of each distinct shape on {sample} of "
+    secs1, _ = cpu_denoise_step_seconds(args.model, 1, 16)
+    lin = cpu_linearity_check(args.model, threads, sample)
+    sample_desc = (f"oracle port (C, gcc -O3 -mavx2, no FMA contraction): per step one linear of each distinct shape on {sample} of "
                    f"{BATCH * CANVAS} tokens ({detail}), matmul scaled x{BATCH * CANVAS // sample}, + full p_sample; "
-                   f"{threads} threads over output columns")
+                   f"{threads} threads over output columns (the reference itself is single-threaded)")
     print(json.dumps({
         "impl": "reference", "metric": "denoise_steps_per_sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample_desc},
+        "extrapolated": True, "sample_tokens": sample, "full_tokens": BATCH * CANVAS, "threads": threads,
+        "one_thread_value": 1.0 / secs1, "linearity_check": lin,
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
+# --------------------------------------------------------------------------------------------
+# timing helper: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks
+# --------------------------------------------------------------------------------------------
+class Timer:
+    def __init__(self, torch, stream, world):
+        self.torch, self.stream, self.world = torch, stream, world
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, iters, warm):
+        """ms per iteration of fn(i) (max over ranks)."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            for i in range(warm):
+                fn(i)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            e0.record(self.stream)
+            for i in range(iters):
+                fn(warm + i)
+            e1.record(self.stream)
+        e1.synchronize()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / iters
+
+    def max_over_ranks(self, v):
+        if self.world > 1:
+            import torch.distributed as dist
+            t = self.torch.tensor([v], device="cuda", dtype=self.torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return v
+
+
 def secondary_metrics(ctx, stream, pk):
-    """The GB/s half of BASELINE.json's metric, on rank 0 after the timed denoise steps: the 4-bit dequant-GEMV
-    (configs[1] shape K=N=14336, group 128) replayed from a CUDA graph over a pool of weights larger than L2, and
-    the per-token KV quantizer (configs[4] row shape, 4096 hidden).  Algorithmic bytes / CUDA-event
+    """The GB/s half of BASELINE.json's metric, on rank 0 after the timed denoise steps: the dequant-GEMV
+    (configs[1]: 2-, 4- and 8-bit, K=N=14336 and 8192, group 128) replayed from a CUDA graph over a pool of weights larger
+    than L2, and the per-token KV quantizer (configs[4] row shape, 4096 hidden).  Algorithmic bytes / CUDA-event
     time, as a fraction of the measured HBM copy bandwidth."""
     import torch
     import dllm_b200
     from dllm_b200 import QWeight
     out = {}
     hbm = pk["hbm_gbs"]
-    K = N = 14336
-    w = torch.randn(K, N, device="cuda") * 0.02
-    torch.cuda.synchronize()
     gemv = {"kernel": "gemv_mma_kernel (bulk-copy ring + int8 mma.sync: codes as the u8 operand, activations as signed-digit columns)",
-            "K": K, "N": N, "group": 128, "timing": "CUDA-graph replay of 16 calls x 10 over a 4-weight pool (412 MB at 4 bits: every call streams from HBM)"}
-    for bits, Ms in ((4, (1, 4, 16)), (8, (1,))):
-        pool = [QWeight.quantize_dev(ctx, w.data_ptr(), K, N, bits, 128) for _ in range(4)]   # 4 x 103 MB > 126 MB L2
-        ctx.sync()
-        for M in Ms:
-            x = torch.randn(M, K, device="cuda")
-            y = torch.empty(M, N, device="cuda")
-            torch.cuda.synchronize()
-            with torch.cuda.stream(stream):
-                for i in range(4):
-                    pool[i].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
-                stream.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                for i in range(16):
-                    pool[i % 4].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(stream):
-                g.replay()
-                stream.synchronize()
-                e0.record(stream)
-                for _ in range(10):
+            "group": 128, "timing": "CUDA-graph replay of 16 calls x 10 over a pool of weights larger than the 126 MB L2 (every call streams from HBM)"}
+    for KN, cases in ((14336, ((4, (1, 4, 16)), (8, (1,)), (2, (1, 16)))), (8192, ((4, (1,)), (2, (1,)), (8, (1,))))):
+        K = N = KN
+        w = torch.randn(K, N, device="cuda") * 0.02
+        torch.cuda.synchronize()
+        for bits, Ms in cases:
+            wbytes = K * N * bits // 8
+            npool = max(4, -(-400_000_000 // wbytes))                  # >= 400 MB of packed codes in rotation
+            pool = [QWeight.quantize_dev(ctx, w.data_ptr(), K, N, bits, 128) for _ in range(npool)]
+            ctx.sync()
+            for M in Ms:
+                x = torch.randn(M, K, device="cuda")
+                y = torch.empty(M, N, device="cuda")
+                torch.cuda.synchronize()
+                with torch.cuda.stream(stream):
+                    for i in range(npool):
+                        pool[i].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
+                    stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    for i in range(16):
+                        pool[i % npool].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
                     g.replay()
-                e1.record(stream)
-                e1.synchronize()
-            us = e0.elapsed_time(e1) / 160 * 1e3
-            byts = K * N * bits // 8 + (K // 128) * N * 8 + 4 * M * K + 4 * M * N
-            gemv[f"b{bits}_M{M}"] = {"us_per_call": round(us, 2), "GBps": round(byts / us / 1e3, 1), "hbm_frac": round(byts / us / 1e3 / hbm, 3)}
-            del g
-        for p in pool:
-            p.close()
-    del w
+                    stream.synchronize()
+                    e0.record(stream)
+                    for _ in range(10):
+                        g.replay()
+                    e1.record(stream)
+                    e1.synchronize()
+                us = e0.elapsed_time(e1) / 160 * 1e3
+                byts = K * N * bits // 8 + (K // 128) * N * 8 + 4 * M * K + 4 * M * N
+                gemv[f"K{KN}_b{bits}_M{M}"] = {"us_per_call": round(us, 2), "GBps": round(byts / us / 1e3, 1),
+                                               "hbm_frac": round(byts / us / 1e3 / hbm, 3)}
+                del g
+            for p in pool:
+                p.close()
+        del w
     out["gemv"] = gemv
     # exact int8 linear (tcgen05 kind::i8) on the three layer shapes of the 1B-class model at 8192 tokens
     i8 = {"kernel": "umma_qlinear_kernel<.., int8> (tcgen05 kind::i8: u8 codes x s8 activations -> s32, exact)", "tokens": 8192, "bits": 4,
@@ -266,15 +342,226 @@ def workload_config(args, world):
 
 
 # --------------------------------------------------------------------------------------------
+# tp7b: BASELINE.json configs[3] — the 7B-class stack, tensor-parallel over the N GPUs (strong scaling)
+# --------------------------------------------------------------------------------------------
+def tp7b_block(ctx, stream, tm, rank, world, tpg, pk):
+    import torch
+    import dllm_b200
+    from dllm_b200 import QWeight, parallel as PAR
+    from dllm_b200.diffuse_llm import DiffusionConfig, QuantizedDiffusionModel
+    lib = ctx._lib
+    H, shapes = layer_shapes("7b")
+    feat, tokens = CANVAS * H, BATCH * CANVAS
+    params = sum(k * n for k, n in shapes)
+    plan = PAR.tp_plan(shapes, world)
+    wgen = torch.Generator(device="cuda").manual_seed(4242)          # the same full weights on every rank
+    full, shard = [], []
+    for (K, N), mode in zip(shapes, plan):
+        w = torch.randn(K, N, device="cuda", generator=wgen) * (1.0 / K ** 0.5)
+        torch.cuda.synchronize()
+        full.append(QWeight.quantize_dev(ctx, w.data_ptr(), K, N, 4, 128))
+        if world > 1:
+            if mode == PAR.COLUMN:
+                ws = w[:, N * rank // world: N * (rank + 1) // world].contiguous()
+            elif mode == PAR.ROW:
+                ws = w[K * rank // world: K * (rank + 1) // world, :].contiguous()
+            else:
+                ws = w
+            torch.cuda.synchronize()
+            shard.append(QWeight.quantize_dev(ctx, ws.data_ptr(), ws.shape[0], ws.shape[1], 4, 128))
+            del ws
+        ctx.sync()
+        del w
+    cfg = DiffusionConfig(num_timesteps=1000, hidden_size=H, use_kv_cache=False)
+    m_full = QuantizedDiffusionModel(full, H, cfg, ctx, dllm_b200.PATH_AUTO)
+    m_tp = None
+    if world > 1:
+        m_tp = QuantizedDiffusionModel(shard, H, cfg, ctx, dllm_b200.PATH_AUTO)
+        tpg.set_plan(m_tp, plan)
+    gen = torch.Generator(device="cuda").manual_seed(777)            # replicated activations
+    x0 = torch.randn(BATCH, feat, device="cuda", generator=gen)
+    z = torch.randn(BATCH, feat, device="cuda", generator=gen)
+    x = x0.clone()
+    torch.cuda.synchronize()
+    flops = 2.0 * tokens * params
+    out = {"workload": f"7B-class stack ({len(shapes)} quantized linears, {params / 1e9:.2f} G params, 4-bit group 128), {tokens} tokens "
+                       f"(BASELINE.json configs[3]); strong scaling over {world} GPU(s)",
+           "flops_per_step": flops}
+
+    def step_of(model, rows=BATCH, xbuf=None):
+        xb = xbuf if xbuf is not None else x
+        return lambda i: model.denoise_step_dev(xb.data_ptr(), z.data_ptr(), 999 - (i % 900), rows, feat)
+
+    # ---- N = 1 reference: the unsharded stack on one GPU (rank 0 alone when N > 1) ----
+    if rank == 0:
+        t1 = Timer(torch, stream, 1)
+        ms_single = t1.run(step_of(m_full), 3, 1)
+    else:
+        ms_single = 0.0
+    tm.barrier()
+    ms_single = tm.max_over_ranks(ms_single)
+    out["single_gpu"] = {"ms_per_step": ms_single, "steps_per_sec": 1e3 / ms_single, "tflops": flops / ms_single / 1e9}
+    if world == 1:
+        out.update({"ms_per_step": ms_single, "steps_per_sec": 1e3 / ms_single, "tflops_per_gpu": flops / ms_single / 1e9,
+                    "efficiency_vs_single_gpu": 1.0, "parallelism": "single"})
+        model_loop = m_full
+    else:
+        n_ar = sum(1 for p in plan if p == PAR.ROW)
+        ar_bytes = sum(tokens * n * (4 if i + 1 == len(shapes) else 2) for i, ((k, n), p) in enumerate(zip(shapes, plan)) if p == PAR.ROW)
+        # overlapped (default): 2 token chunks, all-reduces on the communication stream
+        ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
+        x.copy_(x0)
+        ms_tp = tm.run(step_of(m_tp), 5, 2)
+        # the same sharded stack WITHOUT its collectives: what is left of the step is GEMM time
+        ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 1))
+        ms_nocomm = tm.run(step_of(m_tp), 3, 1)
+        # collectives on the compute stream, one all-reduce per row-parallel linear (round 1's design)
+        ctx._ck(lib.dllm_tp_configure(ctx.h, 1, 0, 0))
+        x.copy_(x0)
+        ms_serial = tm.run(step_of(m_tp), 3, 1)
+        ctx._ck(lib.dllm_tp_configure(ctx.h, 1, 0, 1))
+        ms_serial_nocomm = tm.run(step_of(m_tp), 3, 1)
+        ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
+        # the collective alone: 64 MiB all-reduces back to back (the size of one [8192, 4096] bf16 boundary tensor)
+        buf = torch.zeros(16 << 20, device="cuda")
+        ms_ar = tm.run(lambda i: tpg.allreduce_dev(buf.data_ptr(), buf.numel()), 20, 3)
+        algbw = buf.numel() * 4 / ms_ar / 1e6
+        # correctness of the sharded stack against the unsharded one (same weights): one forward each
+        p_tp, p_full = torch.empty_like(x0), torch.empty_like(x0)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            m_tp.forward_dev(x0.data_ptr(), BATCH, feat, p_tp.data_ptr())
+            stream.synchronize()
+        if rank == 0:
+            with torch.cuda.stream(stream):
+                m_full.forward_dev(x0.data_ptr(), BATCH, feat, p_full.data_ptr())
+                stream.synchronize()
+            rel = float((p_tp - p_full).norm() / p_full.norm())
+        else:
+            rel = 0.0
+        tm.barrier()
+        # the comm-free split of the same job: tokens (rows of x are independent, lib.rs:860,875) over the N GPUs, weights replicated
+        rows = BATCH // world
+        xs = x0[rank * rows:(rank + 1) * rows].clone()
+        torch.cuda.synchronize()
+        ms_split = tm.run(step_of(m_full, rows, xs), 5, 2)
+        out.update({
+            "parallelism": f"tp{world}", "ms_per_step": ms_tp, "steps_per_sec": 1e3 / ms_tp,
+            "tflops_per_gpu": flops / ms_tp / 1e9 / world, "efficiency_vs_single_gpu": ms_single / (world * ms_tp),
+            "plan": f"{n_ar} column->row pairs, one bf16 all-reduce each at the layer boundary (f32 for the stack's last layer)",
+            "allreduces_per_step": n_ar, "allreduce_bytes_per_step": ar_bytes,
+            "overlap": {"token_chunks": 2, "reserved_sms": 8, "gemm_only_ms": ms_nocomm, "exposed_collective_ms": ms_tp - ms_nocomm},
+            "no_overlap": {"ms_per_step": ms_serial, "gemm_only_ms": ms_serial_nocomm, "exposed_collective_ms": ms_serial - ms_serial_nocomm,
+                           "efficiency_vs_single_gpu": ms_single / (world * ms_serial)},
+            "allreduce_64MiB": {"ms": ms_ar, "algbw_GBps": algbw, "busbw_GBps": algbw * 2 * (world - 1) / world},
+            "limiting_collective": "ncclAllReduce of the row-parallel partial sums ([tokens, N] bf16), "
+                                   f"{ar_bytes / 1e9:.2f} GB per step per GPU",
+            "vs_unsharded_rel_err": rel,
+            "token_split": {"parallelism": f"tokens/{world} per GPU, replicated weights, no collective", "ms_per_step": ms_split,
+                            "steps_per_sec": 1e3 / ms_split, "efficiency_vs_single_gpu": ms_single / (world * ms_split)},
+        })
+        model_loop = m_tp
+    # ---- the full 64-step loop (configs[3]): seeded noise generated on the device, x resident; at N = 1 replayed from a CUDA graph
+    x.copy_(x0)
+    torch.cuda.synchronize()
+    tm.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0 = ctx.graph_replays
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        ctx._ck(lib.dllm_sample_seeded_dev(ctx.h, model_loop.h, x.data_ptr(), 42, BATCH, feat, 64, 1, dllm_b200.PATH_AUTO, 1))
+        e1.record(stream)
+    e1.synchronize()
+    tm.barrier()
+    ms_loop = tm.max_over_ranks(e0.elapsed_time(e1))
+    out["sample_64_steps"] = {"ms": ms_loop, "ms_per_step": ms_loop / 64, "steps_per_sec": 64e3 / ms_loop,
+                              "cuda_graph_replays": ctx.graph_replays - r0, "finite": bool(torch.isfinite(x).all()),
+                              "api": "dllm_sample_seeded_dev (noise from the counter-based generator, nothing uploaded per step)"}
+    if m_tp is not None:
+        m_tp.close()
+    m_full.close()
+    for q in full + shard:
+        q.close()
+    del x, x0, z
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# kv32k: BASELINE.json configs[4] — K and V [32, 32768, 4096], token rows sharded over the N GPUs
+# --------------------------------------------------------------------------------------------
+def kv32k_block(ctx, stream, tm, rank, world, pk):
+    import torch
+    import dllm_b200
+    lib = ctx._lib
+    Lk, S, Hd = 32, 32768, 4096
+    S_loc = S // world
+    n = Lk * S_loc * Hd
+    rows = Lk * S_loc
+    gen = torch.Generator(device="cuda").manual_seed(99 + rank)
+    Kt = torch.randn(Lk, S_loc, Hd, device="cuda", generator=gen)
+    Vt = torch.randn(Lk, S_loc, Hd, device="cuda", generator=gen)
+    deq = torch.empty(Lk, S_loc, Hd, device="cuda")
+    torch.cuda.synchronize()
+    hbm = pk["hbm_gbs"]
+    out = {"workload": f"K and V [{Lk} layers, {S} tokens, {Hd}] f32 (BASELINE.json configs[4]), token rows sharded over {world} GPU(s): "
+                       f"[{Lk}, {S_loc}, {Hd}] per GPU",
+           "elements_per_tensor_per_gpu": n}
+    for scheme, sname in ((dllm_b200.KV_ROW_D, "per_token_D"), (dllm_b200.KV_TENSOR_B, "per_tensor_B")):
+        for bits in (8, 4):
+            h = C.c_void_p()
+            ctx._ck(lib.dllm_kv_quantize_sharded_dev(ctx.h, Kt.data_ptr(), Vt.data_ptr(), Lk, S_loc, Hd, bits, scheme, C.byref(h)))
+            ctx.sync()
+            ms_q = tm.run(lambda i: ctx._ck(lib.dllm_kv_update_dev(ctx.h, h, Kt.data_ptr(), Vt.data_ptr())), 3, 1)
+
+            def dq(i):
+                ctx._ck(lib.dllm_kv_dequantize_dev(ctx.h, h, deq.data_ptr(), None))
+                ctx._ck(lib.dllm_kv_dequantize_dev(ctx.h, h, None, deq.data_ptr()))
+            ms_d = tm.run(dq, 3, 1)
+            # property check at full size (deq holds V): a decoded value is within one quantization step of its input
+            with torch.cuda.stream(stream):
+                worst = 0.0
+                for l in range(0, Lk, 8):
+                    v, d = Vt[l], deq[l]
+                    if scheme == dllm_b200.KV_ROW_D:
+                        step = (v.amax(dim=-1) - v.amin(dim=-1)) / float((1 << bits) - 1)
+                        worst = max(worst, float(((d - v).abs().amax(dim=-1) / step).max()))
+                    else:
+                        worst = max(worst, float((d - v).abs().max()))
+                stream.synchronize()
+            if scheme == dllm_b200.KV_TENSOR_B:
+                gmx, gmn = Vt.max(), Vt.min()
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(gmx, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(gmn, op=dist.ReduceOp.MIN)
+                worst = worst / (float(gmx - gmn) / float((1 << bits) - 1))
+            # algorithmic bytes per GPU for K and V: D reads the tensor once, B twice (min/max pass + encode pass)
+            qb = 2 * ((4 if scheme == dllm_b200.KV_ROW_D else 8) * n + n * bits // 8 + (8 * rows if scheme == dllm_b200.KV_ROW_D else 0))
+            db = 2 * (4 * n + n * bits // 8 + (8 * rows if scheme == dllm_b200.KV_ROW_D else 0))
+            out[f"{sname}_{bits}bit"] = {
+                "quantize_ms": ms_q, "quantize_GBps_per_gpu": qb / ms_q / 1e6, "quantize_hbm_frac": qb / ms_q / 1e6 / hbm,
+                "dequantize_ms": ms_d, "dequantize_GBps_per_gpu": db / ms_d / 1e6, "dequantize_hbm_frac": db / ms_d / 1e6 / hbm,
+                "aggregate_GBps": (qb + db) * world / (ms_q + ms_d) / 1e6,
+                "max_error_in_quantization_steps": worst,
+                "exchange": "none (rows are independent)" if scheme == dllm_b200.KV_ROW_D else
+                            ("none (one GPU)" if world == 1 else "min / max of each tensor all-reduced over the ranks (2 floats)")}
+            lib.dllm_kv_destroy(h)
+    del Kt, Vt, deq
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import dllm_b200
-    from dllm_b200 import QWeight, _lib as L
+    from dllm_b200 import QWeight
     from dllm_b200.diffuse_llm import DiffusionConfig, QuantizedDiffusionModel
-    import ctypes as C
+    from dllm_b200 import parallel as PAR
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -282,14 +569,18 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
     ctx = dllm_b200.Context(local_rank, stream=stream.cuda_stream)   # raises without an sm_100 GPU
+    tm = Timer(torch, stream, world)
     H, shapes = layer_shapes(args.model)
     feat, tokens = CANVAS * H, BATCH * CANVAS
     gen = torch.Generator(device="cuda").manual_seed(42 + rank)
+    tpg = None
+    if world > 1:
+        tpg = PAR.TensorParallelGroup(ctx, rank, world)
+        tpg.init_nccl()
 
     # synthetic weights N(0, 1/K) (unit gain through the stack; the reference's init is N(0,1)*0.02,
     # lib.rs:792-796), quantized on the device with quantizer B per group of 128, zero bias (:798)
     tp = world > 1 and args.parallelism == "tp"
-    from dllm_b200 import parallel as PAR
     plan = PAR.tp_plan(shapes, world) if tp else [PAR.REPLICATED] * len(shapes)
     wgen = torch.Generator(device="cuda").manual_seed(42 if tp else 42 + rank)   # TP: same full weights on every rank
     layers = []
@@ -305,10 +596,7 @@ def run_ours(args, rank, world, local_rank):
         del w
     cfg = DiffusionConfig(num_timesteps=1000, hidden_size=H, use_kv_cache=False)
     model = QuantizedDiffusionModel(layers, H, cfg, ctx, dllm_b200.PATH_AUTO)
-    tpg = None
     if tp:
-        tpg = PAR.TensorParallelGroup(ctx, rank, world)
-        tpg.init_nccl()
         tpg.set_plan(model, plan)
         gen = torch.Generator(device="cuda").manual_seed(4242)                 # TP: replicated activations
 
@@ -320,21 +608,14 @@ def run_ours(args, rank, world, local_rank):
         t = 999 - (i % 999)
         model.denoise_step_dev(x.data_ptr(), zs[i % 4].data_ptr(), t, BATCH, feat)
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- resident-in-HBM timing ----
+    # ---- headline: resident-in-HBM timing, nothing but the step's own launches on the stream ----
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             step(i)
-    barrier()
+    tm.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launches
-    ctx._ck(ctx._lib.dllm_profile_begin(ctx.h))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record(stream)
@@ -342,39 +623,64 @@ def run_ours(args, rank, world, local_rank):
             step(args.warmup + i)
         e1.record(stream)
     e1.synchronize()
-    barrier()
-    secs = e0.elapsed_time(e1) * 1e-3
-    nl, ms, fl, by = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
-    ctx._ck(ctx._lib.dllm_profile_end(ctx.h, C.byref(nl), C.byref(ms), C.byref(fl), C.byref(by)))
+    tm.barrier()
+    secs = tm.max_over_ranks(e0.elapsed_time(e1)) * 1e-3
     launches = ctx.launches - launches0
     clocks = sampler.summary()
     finite = bool(torch.isfinite(x).all())
 
+    # ---- roofline pass: the same steps with every dense-kernel launch bracketed by CUDA events ----
+    prof_steps = max(1, min(args.steps, 5))
+    ctx._ck(ctx._lib.dllm_profile_begin(ctx.h))
+    with torch.cuda.stream(stream):
+        for i in range(prof_steps):
+            step(i)
+    nl, ms, fl, by = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
+    ctx._ck(ctx._lib.dllm_profile_end(ctx.h, C.byref(nl), C.byref(ms), C.byref(fl), C.byref(by)))
+
     # ---- end to end through the host-buffer C ABI call ----
-    xh = torch.randn(BATCH, feat).pin_memory()
-    zh = torch.randn(BATCH, feat).pin_memory()
     e2e_steps = max(2, min(args.steps, 10))
-    for i in range(2):
-        ctx._ck(ctx._lib.dllm_denoise_step(ctx.h, model.h, xh.data_ptr(), zh.data_ptr(), 999 - i, BATCH, feat, 1, 0))
-    barrier()
+    xh = [torch.randn(BATCH, feat).pin_memory() for _ in range(2)]
+    zh = [torch.randn(BATCH, feat).pin_memory() for _ in range(2)]
+    ctx2 = dllm_b200.Context(local_rank)                              # second host thread: its own context / stream
+
+    def host_steps(c, xb, zb, n):
+        for i in range(n):
+            c._ck(c._lib.dllm_denoise_step(c.h, model.h, xb.data_ptr(), zb.data_ptr(), 990 - i, BATCH, feat, 1, 0))
+
+    host_steps(ctx, xh[0], zh[0], 2)
+    host_steps(ctx2, xh[1], zh[1], 2)
+    tm.barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        ctx._ck(ctx._lib.dllm_denoise_step(ctx.h, model.h, xh.data_ptr(), zh.data_ptr(), 990 - i, BATCH, feat, 1, 0))
-    e2e_secs = time.perf_counter() - t0     # the call synchronises before returning
+    host_steps(ctx, xh[0], zh[0], e2e_steps)
+    serial_secs = time.perf_counter() - t0                           # the call synchronises before returning
+    bh, bc, bd = C.c_float(), C.c_float(), C.c_float()
+    ctx._lib.dllm_last_step_breakdown(ctx.h, C.byref(bh), C.byref(bc), C.byref(bd))
+    tm.barrier()
+    th = [threading.Thread(target=host_steps, args=(c, xh[i], zh[i], e2e_steps)) for i, c in enumerate((ctx, ctx2))]
+    t0 = time.perf_counter()
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join()
+    pipe_secs = time.perf_counter() - t0
+    serial_secs = tm.max_over_ranks(serial_secs)
+    pipe_secs = tm.max_over_ranks(pipe_secs)
+    ctx2.close()
+    del xh, zh
 
-    if world > 1:
-        import torch.distributed as dist
-        tt = torch.tensor([secs, e2e_secs], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        secs, e2e_secs = float(tt[0]), float(tt[1])
     # DP: every rank ran its own batch (weak scaling); TP: all ranks share one batch (strong scaling)
-    value = (1 if tp else world) * args.steps / secs
-    e2e_value = (1 if tp else world) * e2e_steps / e2e_secs
+    mult = 1 if tp else world
+    value = mult * args.steps / secs
+    e2e_value = mult * 2 * e2e_steps / pipe_secs
+    e2e_serial = mult * e2e_steps / serial_secs
 
+    line = None
+    pk, src = peaks()
     if rank == 0:
-        pk, src = peaks()
         achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        step_bytes = BATCH * feat * 4
         line = {
             "metric": "denoise_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
@@ -382,34 +688,55 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic", "config": workload_config(args, world),
             "tokens_per_sec": value * tokens,
             "model_tflops_per_gpu": 2.0 * tokens * sum(k * n for k, n in shapes) * value / world / 1e12,
-            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 2 * BATCH * feat * 4,
-                    "d2h_bytes_per_step": BATCH * feat * 4, "steps": e2e_steps,
-                    "api": "dllm_denoise_step (host buffers, pinned)"},
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 2 * step_bytes,
+                    "d2h_bytes_per_step": step_bytes, "steps": 2 * e2e_steps,
+                    "api": "dllm_denoise_step (host buffers, pinned) from two host threads, one context each: one thread's "
+                           "copies run under the other's compute",
+                    "single_thread": {"value": e2e_serial, "steps": e2e_steps},
+                    "breakdown": {"h2d_x_ms": bh.value, "compute_ms": bc.value, "d2h_ms": bd.value,
+                                  "noise_upload": "on a second stream under the forward pass",
+                                  "h2d_GBps": step_bytes / bh.value / 1e6 if bh.value > 0 else None,
+                                  "d2h_GBps": step_bytes / bd.value / 1e6 if bd.value > 0 else None}},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "umma_qlinear_kernel<4,128> (tcgen05 dequant-GEMM)", "bound": "tensor",
+            "roofline": {"kernel": "umma_qlinear_pair2_kernel<4> (tcgen05 cta_group::2 dequant-GEMM, 256-token tiles)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "launches": int(nl.value), "kernel_ms_per_step": ms.value / args.steps,
+                         "traffic": None, "launches": int(nl.value), "kernel_ms_per_step": ms.value / prof_steps,
+                         "timing": f"second pass of {prof_steps} steps, every launch of the kernel between two CUDA events",
                          "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                         "frac_of_burst_peak": achieved / pk["bf16_tflops"],
                          "algorithmic_GBps": by.value / (ms.value * 1e-3) / 1e9 if ms.value > 0 else 0.0},
             "clocks": clocks, "output_finite": finite,
         }
-        traffic = None
         try:   # DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_umma_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_umma_traffic.json")))
             if tj.get("model") == args.model:
-                traffic = tj["dram_bytes_per_launch"]
+                line["roofline"]["traffic"] = tj["dram_bytes_per_launch"]
                 line["roofline"]["traffic_source"] = tj.get("source")
         except Exception:
             pass
-        line["roofline"]["traffic"] = traffic
+    model.close()
+    for q in layers:
+        q.close()
+    del x, zs
+    torch.cuda.empty_cache()
+
+    # ---- configs[3] and configs[4], at every N ----
+    if not args.no_tp7b:
+        blk = tp7b_block(ctx, stream, tm, rank, world, tpg, pk)
+        if line is not None:
+            line["tp7b"] = blk
+    if not args.no_kv32k:
+        blk = kv32k_block(ctx, stream, tm, rank, world, pk)
+        if line is not None:
+            line["kv32k"] = blk
+
+    if rank == 0:
         if not args.no_secondary and world == 1:
             try:
-                model.close()
-                model = None
                 line.update(secondary_metrics(ctx, stream, pk))
             except Exception as e:  # noqa: BLE001  (the headline line must survive a failure of the extras)
                 line["secondary_error"] = str(e)[:200]
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             secs_cpu, detail = cpu_denoise_step_seconds(args.model, 1, 32)
             line["cpu_baseline"] = {
                 "value": 1.0 / secs_cpu, "unit": "steps/s", "cores": 1, "kind": "port",
@@ -418,10 +745,9 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if tpg is not None:
         tpg.close()
-    if model is not None:
-        model.close()
     if world > 1:
         import torch.distributed as dist
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -435,6 +761,8 @@ def main():
     ap.add_argument("--parallelism", default="dp", choices=["dp", "tp"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the GEMV / KV-quant GB/s extras")
+    ap.add_argument("--no-tp7b", action="store_true", help="skip the 7B-class tensor-parallel block (configs[3])")
+    ap.add_argument("--no-kv32k", action="store_true", help="skip the 32k-context KV block (configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -604,18 +604,14 @@ int32_t dllm_qweight_quantize(dllm_ctx *ctx, const float *w_host, size_t K, size
     return sync(ctx);
 }
 
-int32_t dllm_qweight_from_codes(dllm_ctx *ctx, const uint8_t *codes, const float *scales, const float *zero_points,
-                                size_t K, size_t N, uint8_t bits, size_t group, const float *bias,
-                                dllm_qweight **out) {
-    CTX_CHECK(ctx);
-    ARG_CHECK(ctx, codes && scales && zero_points, DLLM_ERR_NULL, "null pointer");
+// adopt canonical codes that are already on the device (one per u8, [K,N]); scales / zero-points / bias are host arrays
+static int32_t qweight_from_codes_dev(dllm_ctx *ctx, const uint8_t *codes_dev, const float *scales, const float *zero_points,
+                                      size_t K, size_t N, uint8_t bits, size_t group, const float *bias, dllm_qweight **out) {
     dllm_qweight *w = nullptr;
     DLLM_TRY(qweight_alloc(ctx, K, N, bits, group, &w));
     const size_t Npad = w->n_tiles * WL_TILE_N;
     int32_t rc = DLLM_OK;
-    void *dc = nullptr;
     do {
-        if ((rc = stage_in(ctx, 1, codes, K * N, &dc)) != DLLM_OK) break;
         if (w->per_tensor) {
             ctx->h_params[0] = scales[0];
             ctx->h_params[1] = zero_points[0];
@@ -632,7 +628,7 @@ int32_t dllm_qweight_from_codes(dllm_ctx *ctx, const uint8_t *codes, const float
             cudaMemcpy2DAsync(w->d_zps, Npad * sizeof(float), zero_points, N * sizeof(float), N * sizeof(float), G,
                               cudaMemcpyHostToDevice, ctx->stream);
         }
-        if ((rc = k_wpack_from_codes(ctx, (const uint8_t *)dc, w)) != DLLM_OK) break;
+        if ((rc = k_wpack_from_codes(ctx, codes_dev, w)) != DLLM_OK) break;
         if ((rc = k_wdq_params(ctx, w)) != DLLM_OK) break;
         if ((rc = qweight_set_bias(ctx, w, bias, false)) != DLLM_OK) break;
         rc = sync(ctx);
@@ -640,6 +636,163 @@ int32_t dllm_qweight_from_codes(dllm_ctx *ctx, const uint8_t *codes, const float
     if (rc != DLLM_OK) { dllm_qweight_destroy(w); return rc; }
     *out = w;
     return DLLM_OK;
+}
+
+int32_t dllm_qweight_from_codes(dllm_ctx *ctx, const uint8_t *codes, const float *scales, const float *zero_points,
+                                size_t K, size_t N, uint8_t bits, size_t group, const float *bias,
+                                dllm_qweight **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, codes && scales && zero_points && out, DLLM_ERR_NULL, "null pointer");
+    ARG_CHECK(ctx, K > 0 && N > 0, DLLM_ERR_SHAPE, "empty weight [%zu, %zu]", K, N);
+    void *dc = nullptr;
+    DLLM_TRY(stage_in(ctx, 1, codes, K * N, &dc));
+    return qweight_from_codes_dev(ctx, (const uint8_t *)dc, scales, zero_points, K, N, bits, group, bias, out);
+}
+
+// ---- packed-weights container: the wire / on-disk form of a quantized linear ----
+//   header  64 B : "DLLMQW01" | u32 version (1) | u32 bits | u64 K | u64 N | u64 group (0 = one scale / zero-point per
+//                  tensor, the reference's scheme) | u32 scheme (0 = quantizer B, `(q - zp) * scale`) | u32 has_bias |
+//                  u64 codes_bytes | u64 reserved (0)
+//   codes        : the [K,N] row-major codes bit-packed LSB first (dllm_pack's layout) at the narrowest width in {1,2,4,8}
+//                  that holds `bits` — QuantizedTensor::data (quantization/src/types.rs:42-47) packed the way its own
+//                  accounting assumes ((len * bits + 7) / 8, diffuse-llm-rs/src/quantization.rs:122)
+//   scales, zps  : f32 [K/group, N] each (or one value each) — QuantizationParams::{scale, zero_point}
+//   bias         : f32 [N] when has_bias
+//   crc32   4 B  : IEEE CRC-32 of everything before it
+// The tile-major layout the kernels read (wlayout.cuh) is private and never serialised.
+namespace {
+struct QwHeader {
+    char magic[8];
+    uint32_t version, bits;
+    uint64_t K, N, group;
+    uint32_t scheme, has_bias;
+    uint64_t codes_bytes, reserved;
+};
+static_assert(sizeof(QwHeader) == 64, "container header is 64 bytes");
+
+uint32_t crc32_ieee(const uint8_t *p, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        init = true;
+    }
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
+int pack_width_for(int bits) { return bits <= 1 ? 1 : (bits <= 2 ? 2 : (bits <= 4 ? 4 : 8)); }
+size_t qw_param_count(const dllm_qweight *w) { return w->per_tensor ? 1 : (w->K / w->group) * w->N; }
+}  // namespace
+
+size_t dllm_qweight_serialized_size(const dllm_qweight *w) {
+    if (!w) return 0;
+    const size_t codes = dllm_packed_len(w->K * w->N, (uint8_t)pack_width_for(w->bits));
+    return sizeof(QwHeader) + codes + 2 * qw_param_count(w) * sizeof(float) + (w->d_bias ? w->N * sizeof(float) : 0) + 4;
+}
+
+int32_t dllm_qweight_serialize(dllm_ctx *ctx, const dllm_qweight *w, uint8_t *buf, size_t cap, size_t *written) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, w && buf, DLLM_ERR_NULL, "null pointer");
+    const size_t total = dllm_qweight_serialized_size(w);
+    ARG_CHECK(ctx, cap >= total, DLLM_ERR_INVALID_PARAMS, "buffer of %zu bytes is too small for %zu", cap, total);
+    const int pw = pack_width_for(w->bits);
+    const size_t n = w->K * w->N, codes_bytes = dllm_packed_len(n, (uint8_t)pw), np = qw_param_count(w);
+    QwHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "DLLMQW01", 8);
+    h.version = 1; h.bits = (uint32_t)w->bits; h.K = w->K; h.N = w->N; h.group = w->per_tensor ? 0 : w->group;
+    h.scheme = 0; h.has_bias = w->d_bias ? 1u : 0u; h.codes_bytes = codes_bytes;
+    memcpy(buf, &h, sizeof(h));
+    uint8_t *p = buf + sizeof(h);
+    void *dc, *dp;
+    DLLM_TRY(stage_out_buf(ctx, 1, n, &dc));
+    DLLM_TRY(stage_out_buf(ctx, 2, codes_bytes, &dp));
+    DLLM_TRY(k_wexport_codes(ctx, w, (uint8_t *)dc));
+    DLLM_TRY(k_pack(ctx, (const uint8_t *)dc, n, pw, (uint8_t *)dp));
+    DLLM_TRY(copy_out(ctx, p, dp, codes_bytes));
+    DLLM_TRY(sync(ctx));
+    p += codes_bytes;
+    DLLM_TRY(dllm_qweight_export(ctx, w, nullptr, (float *)p, (float *)(p + np * sizeof(float))));
+    p += 2 * np * sizeof(float);
+    if (w->d_bias) {
+        DLLM_TRY(copy_out(ctx, p, w->d_bias, w->N * sizeof(float)));
+        DLLM_TRY(sync(ctx));
+        p += w->N * sizeof(float);
+    }
+    const uint32_t crc = crc32_ieee(buf, (size_t)(p - buf));
+    memcpy(p, &crc, 4);
+    if (written) *written = total;
+    return DLLM_OK;
+}
+
+int32_t dllm_qweight_deserialize(dllm_ctx *ctx, const uint8_t *buf, size_t len, dllm_qweight **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, buf && out, DLLM_ERR_NULL, "null pointer");
+    *out = nullptr;
+    ARG_CHECK(ctx, len >= sizeof(QwHeader) + 4, DLLM_ERR_SERIALIZATION, "truncated container (%zu bytes)", len);
+    QwHeader h;
+    memcpy(&h, buf, sizeof(h));
+    ARG_CHECK(ctx, memcmp(h.magic, "DLLMQW01", 8) == 0 && h.version == 1, DLLM_ERR_SERIALIZATION, "not a DLLMQW01 container");
+    ARG_CHECK(ctx, h.bits >= 1 && h.bits <= 8 && h.scheme == 0 && h.K > 0 && h.N > 0 && h.K < ((uint64_t)1 << 32) && h.N < ((uint64_t)1 << 32) &&
+              (h.group == 0 || h.K % h.group == 0), DLLM_ERR_INVALID_DATA_FORMAT, "inconsistent container header");
+    const int pw = pack_width_for((int)h.bits);
+    const size_t n = (size_t)h.K * h.N, codes_bytes = dllm_packed_len(n, (uint8_t)pw);
+    const size_t np = h.group == 0 ? 1 : (size_t)(h.K / h.group) * h.N;
+    const size_t total = sizeof(QwHeader) + codes_bytes + 2 * np * sizeof(float) + (h.has_bias ? h.N * sizeof(float) : 0) + 4;
+    ARG_CHECK(ctx, h.codes_bytes == codes_bytes && len == total, DLLM_ERR_INVALID_DATA_FORMAT, "container size %zu does not match its header (%zu)", len, total);
+    uint32_t crc;
+    memcpy(&crc, buf + total - 4, 4);
+    ARG_CHECK(ctx, crc == crc32_ieee(buf, total - 4), DLLM_ERR_SERIALIZATION, "CRC mismatch: the container is corrupt");
+    const uint8_t *p = buf + sizeof(QwHeader);
+    void *dp, *dc;
+    DLLM_TRY(stage_in(ctx, 2, p, codes_bytes, &dp));
+    DLLM_TRY(stage_out_buf(ctx, 1, n, &dc));
+    DLLM_TRY(k_unpack(ctx, (const uint8_t *)dp, n, pw, (uint8_t *)dc));
+    p += codes_bytes;
+    // (scales / zps / bias may be unaligned inside the caller's buffer: copy them out)
+    std::vector<float> sc(np), zp(np), bias(h.has_bias ? h.N : 0);
+    memcpy(sc.data(), p, np * sizeof(float));
+    memcpy(zp.data(), p + np * sizeof(float), np * sizeof(float));
+    p += 2 * np * sizeof(float);
+    if (h.has_bias) memcpy(bias.data(), p, h.N * sizeof(float));
+    return qweight_from_codes_dev(ctx, (const uint8_t *)dc, sc.data(), zp.data(), (size_t)h.K, (size_t)h.N, (uint8_t)h.bits,
+                                  (size_t)h.group, h.has_bias ? bias.data() : nullptr, out);
+}
+
+int32_t dllm_qweight_save(dllm_ctx *ctx, const dllm_qweight *w, const char *path) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, w && path, DLLM_ERR_NULL, "null pointer");
+    std::vector<uint8_t> buf(dllm_qweight_serialized_size(w));
+    size_t written = 0;
+    DLLM_TRY(dllm_qweight_serialize(ctx, w, buf.data(), buf.size(), &written));
+    FILE *f = fopen(path, "wb");
+    if (!f) DLLM_FAIL(ctx, DLLM_ERR_IO, "cannot open %s for writing", path);
+    const size_t nw = fwrite(buf.data(), 1, written, f);
+    const int rc = fclose(f);
+    if (nw != written || rc != 0) DLLM_FAIL(ctx, DLLM_ERR_IO, "short write to %s", path);
+    return DLLM_OK;
+}
+
+int32_t dllm_qweight_load(dllm_ctx *ctx, const char *path, dllm_qweight **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, path && out, DLLM_ERR_NULL, "null pointer");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) DLLM_FAIL(ctx, DLLM_ERR_IO, "cannot open %s", path);
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (sz < 0) { fclose(f); DLLM_FAIL(ctx, DLLM_ERR_IO, "cannot size %s", path); }
+    std::vector<uint8_t> buf((size_t)sz);
+    const size_t nr = fread(buf.data(), 1, buf.size(), f);
+    fclose(f);
+    if (nr != buf.size()) DLLM_FAIL(ctx, DLLM_ERR_IO, "short read from %s", path);
+    return dllm_qweight_deserialize(ctx, buf.data(), buf.size(), out);
 }
 
 int32_t dllm_qweight_export(dllm_ctx *ctx, const dllm_qweight *w, uint8_t *codes, float *scales, float *zero_points) {
@@ -713,6 +866,9 @@ int32_t dllm_qlinear_forward_dev(dllm_ctx *ctx, const dllm_qweight *w, const flo
     ARG_CHECK(ctx, k_umma_supported(w, M), DLLM_ERR_UNSUPPORTED, "tcgen05 path does not support this shape");
     DLLM_TRY(ensure_buf(ctx, ctx->act[0], M * w->K * 2));
     DLLM_TRY(k_f32_to_bf16(ctx, x_dev, M * w->K, ctx->act[0].p));
+    // timing experiments only (scripts/dense_probe.py): write bf16 into y, as the layers inside a stack do
+    static const bool probe_bf16 = getenv("DLLM_PROBE_BF16_OUT") != nullptr;
+    if (probe_bf16) return k_qlinear_umma(ctx, w, ctx->act[0].p, M, nullptr, y_dev);
     return k_qlinear_umma(ctx, w, ctx->act[0].p, M, y_dev, nullptr);
 }
 
@@ -1436,6 +1592,7 @@ struct dllm_kv {
     float *d_params[2] = {nullptr, nullptr};   // B: {scale, zp, min, max}
     float *d_rows[2] = {nullptr, nullptr};     // D: [rows] scales then [rows] zps
     float c_scale = 0.f;
+    bool sharded = false;             // TENSOR_B: this entry holds one rank's token rows; min / max are all-reduced over the group
     int device = 0;
 };
 
@@ -1466,7 +1623,11 @@ static int32_t kv_quantize_one(dllm_ctx *ctx, dllm_kv *kv, int which, const floa
     switch (kv->scheme) {
         case DLLM_KV_TENSOR_B:
             if (kv->cap != kv->S) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "per-tensor KV entries have no spare capacity");
-            DLLM_TRY(k_minmax(ctx, src_dev, n, kv->bits, kv->d_params[which]));
+            DLLM_TRY(k_minmax(ctx, src_dev, n, kv->bits, kv->d_params[which]));     // (an empty shard leaves {+inf, -inf}: neutral)
+            if (kv->sharded && ctx->tp_world > 1) {
+                DLLM_TRY(tp_allreduce_minmax(ctx, kv->d_params[which]));
+                DLLM_TRY(k_params_from_minmax(ctx, kv->bits, kv->d_params[which]));
+            }
             return k_encode_b(ctx, src_dev, n, kv->bits, pack, kv->d_params[which], 0.f, 0.f, kv->d_codes[which]);
         case DLLM_KV_ROW_D:
         case DLLM_KV_FIXED_C:
@@ -1570,15 +1731,15 @@ int32_t dllm_kv_quantize_sharded_dev(dllm_ctx *ctx, const float *keys_dev, const
         return dllm_kv_quantize_dev(ctx, keys_dev, values_dev, layers, seq_local, hidden, bits, scheme, out);
     dllm_kv *kv = nullptr;
     DLLM_TRY(kv_alloc(ctx, layers, seq_local, seq_local, hidden, bits, scheme, &kv));
-    const size_t n = layers * seq_local * hidden;
-    const float *src[2] = {keys_dev, values_dev};
+    kv->sharded = true;
+    // every rank takes part in the min / max exchange, also one whose shard is empty
     int32_t rc = DLLM_OK;
-    for (int i = 0; i < 2 && rc == DLLM_OK; ++i) {
-        if (n && !src[i]) { rc = DLLM_ERR_NULL; break; }
-        rc = k_minmax(ctx, src[i], n, bits, kv->d_params[i]);                 // an empty shard leaves {+inf, -inf}: neutral
-        if (rc == DLLM_OK) rc = tp_allreduce_minmax(ctx, kv->d_params[i]);
-        if (rc == DLLM_OK) rc = k_params_from_minmax(ctx, bits, kv->d_params[i]);
-        if (rc == DLLM_OK && n) rc = k_encode_b(ctx, src[i], n, bits, kv->packed ? bits : 0, kv->d_params[i], 0.f, 0.f, kv->d_codes[i]);
+    if (layers * seq_local * hidden == 0) {
+        for (int i = 0; i < 2 && rc == DLLM_OK; ++i) rc = kv_quantize_one(ctx, kv, i, nullptr);
+    } else if (!keys_dev || !values_dev) {
+        rc = DLLM_ERR_NULL;
+    } else {
+        rc = dllm_kv_update_dev(ctx, kv, keys_dev, values_dev);
     }
     if (rc != DLLM_OK) { dllm_kv_destroy(kv); return rc; }
     *out = kv;

@@ -1180,6 +1180,53 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 
+__device__ __forceinline__ uint32_t pack_bf16_bias(uint32_t lo, uint32_t hi, float bias) {
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(lo) + bias, __uint_as_float(hi) + bias);
+    return *reinterpret_cast<uint32_t *>(&b2);
+}
+// q (32..64, multiple of 8) accumulator columns of this warp's lanes -> packed bf16 pairs.  Two tensor-memory loads are in
+// flight per wait: a load + wait round trip costs ~500 cycles while the tensor pipe is busy, and the half is only handed
+// back to the MMA warp when its last column is in registers.
+__device__ __forceinline__ void drain_columns(uint32_t t_acc, uint32_t q, float bias, uint32_t *pk) {
+#pragma unroll
+    for (int p2 = 0; p2 < 2; ++p2) {
+        const uint32_t c = (uint32_t)(p2 * 32);
+        uint32_t v[32];
+        const bool a16 = c + 16 <= q, a8 = !a16 && c + 8 <= q, b16 = c + 32 <= q, b8 = !b16 && c + 24 <= q;
+        if (a16) tmem_ld16(t_acc + c, v); else if (a8) tmem_ld8(t_acc + c, v);
+        if (b16) tmem_ld16(t_acc + c + 16, v + 16); else if (b8) tmem_ld8(t_acc + c + 16, v + 16);
+        tmem_ld_wait();
+        if (a16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[p2 * 16 + j] = pack_bf16_bias(v[2 * j], v[2 * j + 1], bias);
+        } else if (a8) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pk[p2 * 16 + j] = pack_bf16_bias(v[2 * j], v[2 * j + 1], bias);
+        }
+        if (b16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[p2 * 16 + 8 + j] = pack_bf16_bias(v[16 + 2 * j], v[16 + 2 * j + 1], bias);
+        } else if (b8) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pk[p2 * 16 + 8 + j] = pack_bf16_bias(v[16 + 2 * j], v[16 + 2 * j + 1], bias);
+        }
+    }
+}
+// packed pairs -> the staging buffer [token][128 columns] (this lane's column), tokens [0, q)
+__device__ __forceinline__ void stage_columns(uint32_t sbase, uint32_t q, const uint32_t *pk) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        if ((uint32_t)(g * 8) < q) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const uint32_t w = pk[(g * 8 + j) >> 1];
+                sts_u16(sbase + (uint32_t)(g * 8 + j) * 256u, w);
+                sts_u16(sbase + (uint32_t)(g * 8 + j + 1) * 256u, w >> 16);
+            }
+        }
+    }
+}
+
 template <int CB, int NDQ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((12 + 4 * NDQ) * 32, 1)
 umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const Pair2Args a) {
@@ -1384,59 +1431,33 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
 #pragma unroll 1
             for (uint32_t h = 0; h < 2; ++h) {
-                mbar_wait(tfull + h, tph);
-                tc_fence_after();
-                if (warp == kEpiWarp0 && lane == 0) TRACE2(4 + h, n_item);
                 const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + part * q;
                 const uint32_t tok0 = mt * ntok + part * half_rows + h * q;     // token of this warp's first column
                 const uint32_t n_tok = tok0 >= a.M ? 0u : (a.M - tok0 < q ? a.M - tok0 : q);   // valid rows among its q
                 if (a.y_f32 == nullptr) {
-                    uint32_t pk[32];
-#pragma unroll
-                    for (int g2 = 0; g2 < 4; ++g2) {
-                        const uint32_t c = (uint32_t)(g2 * 16);
-                        if (c + 16 <= q) {
-                            uint32_t v[16];
-                            tmem_ld16(t_acc + c, v);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[2 * j]) + bias, __uint_as_float(v[2 * j + 1]) + bias);
-                                pk[g2 * 8 + j] = *reinterpret_cast<uint32_t *>(&b2);
-                            }
-                        } else if (c + 8 <= q) {
-                            uint32_t v[8];
-                            tmem_ld8(t_acc + c, v);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[2 * j]) + bias, __uint_as_float(v[2 * j + 1]) + bias);
-                                pk[g2 * 8 + j] = *reinterpret_cast<uint32_t *>(&b2);
-                            }
-                        }
+                    // staging buffer free?  Half 0 checks BEFORE it waits for the accumulator (off the critical path: the previous
+                    // tile's half-1 store has had a whole tile's time), half 1 after it has handed its accumulator back.
+                    if (h == 0 && !(a.dbg & 64)) {
+                        if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        named_bar_sync(1, 256);
                     }
+                    mbar_wait(tfull + h, tph);
+                    tc_fence_after();
+                    if (warp == kEpiWarp0 && lane == 0) TRACE2(4 + h, n_item);
+                    uint32_t pk[32];
+                    drain_columns(t_acc, q, bias, pk);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(tempty_leader + h * 8);   // this warp's columns are out: 16 such arrivals free the half
                     if (warp == kEpiWarp0 && lane == 0) TRACE2(6 + h, n_item);
                     // phase 2: registers -> staging [part][token][128 columns] -> two bulk tensor stores (rows past M and columns past
-                    // N are clipped by the TMA unit).  The staging buffer is reused per half: wait until the previous store has
-                    // read it.
+                    // N are clipped by the TMA unit)
                     if (!(a.dbg & 64)) {
-                        if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        named_bar_sync(1, 256);
-                        const uint32_t sbase = smem_u32(smem + C::kOutOffset) + (part * q) * 256u + (uint32_t)(quarter * 32 + lane) * 2u;
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            if ((uint32_t)(g * 8) < q) {
-#pragma unroll
-                                for (int j = 0; j < 8; j += 2) {
-                                    const uint32_t w = pk[(g * 8 + j) >> 1];
-                                    sts_u16(sbase + (uint32_t)(g * 8 + j) * 256u, w);
-                                    sts_u16(sbase + (uint32_t)(g * 8 + j + 1) * 256u, w >> 16);
-                                }
-                            }
+                        if (h == 1) {
+                            if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            named_bar_sync(1, 256);
                         }
+                        stage_columns(smem_u32(smem + C::kOutOffset) + (part * q) * 256u + (uint32_t)(quarter * 32 + lane) * 2u, q, pk);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         named_bar_sync(1, 256);
                         if (warp == kEpiWarp0 && lane == 0 && nt < a.n_tiles) {
@@ -1449,6 +1470,8 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     }
                 } else {
                     // f32 (and optionally bf16) output: the stack's last layer only.  Columns are stored as they are read.
+                    mbar_wait(tfull + h, tph);
+                    tc_fence_after();
 #pragma unroll 1
                     for (uint32_t c0 = 0; c0 < q; c0 += 8) {
                         uint32_t v[8];

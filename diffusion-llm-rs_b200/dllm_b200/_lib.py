@@ -126,6 +126,11 @@ SIGNATURES = {
     "dllm_qweight_info": (C.c_int32, [c_vp, C.POINTER(c_sz), C.POINTER(c_sz), c_u8p, C.POINTER(c_sz),
                                       C.POINTER(c_sz)]),
     "dllm_qweight_destroy": (None, [c_vp]),
+    "dllm_qweight_serialized_size": (c_sz, [c_vp]),
+    "dllm_qweight_serialize": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, C.POINTER(c_sz)]),
+    "dllm_qweight_deserialize": (C.c_int32, [c_vp, c_vp, c_sz, C.POINTER(c_vp)]),
+    "dllm_qweight_save": (C.c_int32, [c_vp, c_vp, C.c_char_p]),
+    "dllm_qweight_load": (C.c_int32, [c_vp, C.c_char_p, C.POINTER(c_vp)]),
     "dllm_qlinear_forward": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_vp, C.c_int32]),
     "dllm_qlinear_forward_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_vp, C.c_int32]),
     "dllm_qlinear_forward_i8": (C.c_int32, [c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -262,6 +262,41 @@ class QWeight:
                                                      _ptr(b), C.byref(h)))
         return cls(ctx, h, K, N, bits, group)
 
+    # ---- packed-weights container "DLLMQW01" (include/dllm_b200.h) ----
+    def serialize(self) -> bytes:
+        n = int(self.ctx._lib.dllm_qweight_serialized_size(self.h))
+        buf = (C.c_uint8 * n)()
+        wr = C.c_size_t()
+        with self.ctx.lock:
+            self.ctx._ck(self.ctx._lib.dllm_qweight_serialize(self.ctx.h, self.h, buf, n, C.byref(wr)))
+        return bytes(buf[:wr.value])
+
+    @classmethod
+    def deserialize(cls, ctx: "Context", data: bytes):
+        arr = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        h = C.c_void_p()
+        with ctx.lock:
+            ctx._ck(ctx._lib.dllm_qweight_deserialize(ctx.h, arr, len(data), C.byref(h)))
+        return cls._from_handle(ctx, h)
+
+    def save(self, path: str):
+        with self.ctx.lock:
+            self.ctx._ck(self.ctx._lib.dllm_qweight_save(self.ctx.h, self.h, path.encode()))
+
+    @classmethod
+    def load(cls, ctx: "Context", path: str):
+        h = C.c_void_p()
+        with ctx.lock:
+            ctx._ck(ctx._lib.dllm_qweight_load(ctx.h, path.encode(), C.byref(h)))
+        return cls._from_handle(ctx, h)
+
+    @classmethod
+    def _from_handle(cls, ctx, h):
+        K, N, g, pb = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        bits = C.c_uint8()
+        ctx._lib.dllm_qweight_info(h, C.byref(K), C.byref(N), C.byref(bits), C.byref(g), C.byref(pb))
+        return cls(ctx, h, int(K.value), int(N.value), int(bits.value), int(g.value))
+
     def export(self):
         G = 1 if self.group == 0 else self.K // self.group
         codes = np.empty((self.K, self.N), np.uint8)

@@ -219,6 +219,18 @@ DLLM_API int32_t dllm_qweight_info(const dllm_qweight *w, size_t *K, size_t *N, 
                                    size_t *group, size_t *packed_bytes);
 DLLM_API void dllm_qweight_destroy(dllm_qweight *w);
 
+/* Packed-weights container "DLLMQW01" (SURVEY.md 8f-3): the wire / on-disk form of a quantized linear — what the
+ * reference's serde derives on QuantizedTensor { data, shape, params } (quantization/src/types.rs:42-47) would carry, with
+ * the codes bit-packed the way the reference only accounts for ((len * bits + 7) / 8, quantization.rs:122).  64-byte header
+ * (magic, version, bits, K, N, group, scheme, has_bias, codes_bytes), packed codes (dllm_pack layout at the narrowest width
+ * in {1,2,4,8} holding `bits`), f32 scales and zero-points [K/group, N] (or one each), optional f32 bias [N], CRC-32.
+ * Errors: DLLM_ERR_IO (file), DLLM_ERR_SERIALIZATION (magic / CRC / truncation), DLLM_ERR_INVALID_DATA_FORMAT (header). */
+DLLM_API size_t dllm_qweight_serialized_size(const dllm_qweight *w);
+DLLM_API int32_t dllm_qweight_serialize(dllm_ctx *ctx, const dllm_qweight *w, uint8_t *buf, size_t cap, size_t *written);
+DLLM_API int32_t dllm_qweight_deserialize(dllm_ctx *ctx, const uint8_t *buf, size_t len, dllm_qweight **out);
+DLLM_API int32_t dllm_qweight_save(dllm_ctx *ctx, const dllm_qweight *w, const char *path);
+DLLM_API int32_t dllm_qweight_load(dllm_ctx *ctx, const char *path, dllm_qweight **out);
+
 /* y[M,N] = x[M,K] · dequant(W) + b.  path: DLLM_PATH_* */
 DLLM_API int32_t dllm_qlinear_forward(dllm_ctx *ctx, const dllm_qweight *w, const float *x, size_t M,
                                       float *y, int32_t path);

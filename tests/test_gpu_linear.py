@@ -498,3 +498,52 @@ def test_umma_benchmark_shapes_match_oracle(ctx, O, KN):
     assert np.linalg.norm(got - y64) <= 1e-2 * np.linalg.norm(y64)
     assert np.abs(got - y64).max() <= 2e-2 * np.abs(y64).max()
     qw.close()
+
+
+@pytest.mark.parametrize("bits,group,bias", [(4, 128, True), (2, 128, False), (8, 64, True), (3, 0, False), (1, 0, True)])
+def test_qweight_container_round_trip(ctx, O, tmp_path, bits, group, bias):
+    """Packed-weights container "DLLMQW01" (SURVEY.md 8f-3): serialize -> deserialize and save -> load give back the same
+    codes / scales / zero-points (bit for bit, equal to the oracle's quantization) and the same forward result; the header
+    carries K, N, bits, group; a flipped byte or a truncated buffer is refused."""
+    import struct
+    from dllm_b200 import QWeight, PATH_SIMT, DllmError
+    from dllm_b200 import _lib as L
+    rng = np.random.default_rng(bits * 7 + group)
+    K, N = 256, 200                                     # ragged N: codes do not fill whole tiles
+    w = make_w(rng, K, N)
+    b = rng.standard_normal(N).astype(F) if bias else None
+    qw = QWeight.quantize(ctx, w, bits, group, b)
+    blob = qw.serialize()
+    magic, version, hbits, hK, hN, hgroup, scheme, has_bias, codes_bytes, _ = struct.unpack("<8sIIQQQIIQQ", blob[:64])
+    pw = 1 if bits <= 1 else 2 if bits <= 2 else 4 if bits <= 4 else 8
+    assert (magic, version, hbits, hK, hN, hgroup, scheme, has_bias) == (b"DLLMQW01", 1, bits, K, N, group, 0, int(bias))
+    assert codes_bytes == (K * N * pw + 7) // 8
+    G = K // group if group else 1
+    assert len(blob) == 64 + codes_bytes + 2 * 4 * (G * N if group else 1) + (4 * N if bias else 0) + 4
+    # the packed codes in the container are dllm_pack's layout of the oracle's codes
+    if group:
+        oc, os_, oz = O.quantize_weight_grouped(w, bits, group)
+    else:
+        oc, s1, z1 = O.quantize_tensor(w.ravel(), bits)
+        oc, os_, oz = oc.reshape(K, N), np.array([[s1]], F), np.array([[z1]], F)
+    assert np.array_equal(np.frombuffer(blob[64:64 + codes_bytes], np.uint8), O.pack(oc.ravel(), pw))
+    x = rng.standard_normal((5, K)).astype(F)
+    y0 = qw.forward(x, PATH_SIMT)
+    path = str(tmp_path / "w.dllmqw")
+    qw.save(path)
+    for q2 in (QWeight.deserialize(ctx, blob), QWeight.load(ctx, path)):
+        assert (q2.K, q2.N, q2.bits, q2.group) == (K, N, bits, group)
+        c2, s2, z2 = q2.export()
+        assert np.array_equal(c2, oc) and np.array_equal(s2.view(np.uint32), os_.view(np.uint32)) and np.array_equal(z2, oz)
+        assert np.array_equal(q2.forward(x, PATH_SIMT).view(np.uint32), y0.view(np.uint32))
+        q2.close()
+    bad = bytearray(blob)
+    bad[70] ^= 0x10
+    for data in (bytes(bad), blob[:-5], b"NOTAFILE" + blob[8:]):
+        with pytest.raises(DllmError) as ei:
+            QWeight.deserialize(ctx, data)
+        assert ei.value.code in (L.ERR_SERIALIZATION, L.ERR_INVALID_DATA_FORMAT)
+    with pytest.raises(DllmError) as ei:
+        QWeight.load(ctx, str(tmp_path / "missing.dllmqw"))
+    assert ei.value.code == L.ERR_IO
+    qw.close()
