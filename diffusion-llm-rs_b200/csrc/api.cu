@@ -1013,6 +1013,22 @@ int32_t tp_allreduce_on(dllm_ctx *ctx, void *buf, size_t n, bool bf16, cudaStrea
 int32_t tp_allreduce_minmax(dllm_ctx *ctx, float *params_dev);
 int32_t tp_allgather_cols(dllm_ctx *ctx, const float *in, size_t M, size_t n_local, float *out);
 
+// The two ping-pong activation buffers of a tensor-parallel tcgen05 stack: the halves of the peer-to-peer arena when it is
+// enabled and large enough (dllm_tp_p2p_enable: the row-parallel partial sums are then reduced in place by this library's
+// own NVLink kernel), else the context's ordinary buffers (ncclAllReduce).  Same sizes on every rank => same offsets.
+static int32_t tp_act_bufs(dllm_ctx *ctx, size_t bytes_each, char **b0, char **b1) {
+    if (ctx->p2p_arena && ctx->tp_world > 1 && 2 * ((bytes_each + 255) & ~(size_t)255) <= ctx->p2p_bytes) {
+        *b0 = (char *)ctx->p2p_arena;
+        *b1 = (char *)ctx->p2p_arena + ((ctx->p2p_bytes / 2) & ~(size_t)255);
+        return DLLM_OK;
+    }
+    DLLM_TRY(ensure_buf(ctx, ctx->act[0], bytes_each));
+    DLLM_TRY(ensure_buf(ctx, ctx->act[1], bytes_each));
+    *b0 = (char *)ctx->act[0].p;
+    *b1 = (char *)ctx->act[1].p;
+    return DLLM_OK;
+}
+
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -1040,15 +1056,15 @@ static int32_t forward_tp_overlapped(dllm_ctx *ctx, dllm_model *m, const float *
     // every chunk owns one region of each ping-pong buffer ([its tokens, width] dense inside): chunks never overlap,
     // whatever the layers' widths are
     const size_t region = per * maxw * 2;
-    DLLM_TRY(ensure_buf(ctx, ctx->act[0], region * chunks));
-    DLLM_TRY(ensure_buf(ctx, ctx->act[1], region * chunks));
+    char *buf0, *buf1;
+    DLLM_TRY(tp_act_bufs(ctx, region * chunks, &buf0, &buf1));
     for (int c = 0; c < chunks; ++c)
         if (c0[c + 1] > c0[c])
-            DLLM_TRY(k_f32_to_bf16(ctx, x_dev + c0[c] * m->layers[0]->K, (c0[c + 1] - c0[c]) * m->layers[0]->K, (char *)ctx->act[0].p + c * region));
+            DLLM_TRY(k_f32_to_bf16(ctx, x_dev + c0[c] * m->layers[0]->K, (c0[c + 1] - c0[c]) * m->layers[0]->K, buf0 + c * region));
     const int reserve = ctx->sm_reserve >= 0 ? ctx->sm_reserve : env_int("DLLM_TP_RESERVE_SMS", 8);
     ctx->sm_limit = ctx->sm_count - reserve;
     std::vector<char> pending(chunks, 0);          // chunk c's input is still being all-reduced on the comm stream
-    char *cur = (char *)ctx->act[0].p, *nxt = (char *)ctx->act[1].p;
+    char *cur = buf0, *nxt = buf1;
     int32_t rc = DLLM_OK;
     size_t l0 = 0;
     while (l0 < L && rc == DLLM_OK) {
@@ -1136,10 +1152,16 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
     if (all_umma && (!any_parallel || no_gather)) {
         // bf16 activations between layers; the last layer writes f32.  Row-parallel layers leave partial sums:
         // one NCCL all-reduce at the layer boundary, on the bf16 tensor the next linear reads (f32 for the last).
-        DLLM_TRY(ensure_buf(ctx, ctx->act[0], tokens * maxw * 2));
-        DLLM_TRY(ensure_buf(ctx, ctx->act[1], tokens * maxw * 2));
-        DLLM_TRY(k_f32_to_bf16(ctx, x_dev, tokens * m->layers[0]->K, ctx->act[0].p));
-        void *cur = ctx->act[0].p, *nxt = ctx->act[1].p;
+        char *buf0, *buf1;
+        if (any_parallel) {
+            DLLM_TRY(tp_act_bufs(ctx, tokens * maxw * 2, &buf0, &buf1));
+        } else {
+            DLLM_TRY(ensure_buf(ctx, ctx->act[0], tokens * maxw * 2));
+            DLLM_TRY(ensure_buf(ctx, ctx->act[1], tokens * maxw * 2));
+            buf0 = (char *)ctx->act[0].p; buf1 = (char *)ctx->act[1].p;
+        }
+        DLLM_TRY(k_f32_to_bf16(ctx, x_dev, tokens * m->layers[0]->K, buf0));
+        void *cur = buf0, *nxt = buf1;
         for (size_t l = 0; l < L; ++l) {
             const bool last = l + 1 == L;
             DLLM_TRY(k_qlinear_umma(ctx, m->layers[l], cur, tokens, last ? out_dev : nullptr, last ? nullptr : nxt));

@@ -211,6 +211,7 @@ struct GemvArgs {
     uint32_t stages;                 // ring depth (multiple of NG)
     uint32_t prefill;                // stages requested before the activations are resident (XR)
     uint32_t x_off, red_off, bar_off, pre_off;   // shared-memory carve-up (bytes)
+    uint32_t fast;                   // 1: every aligned stage lies in one quantization group, 2: every aligned pair does, 0: neither
     uint32_t bulk;                   // code tiles by one cp.async.bulk per stage (default) or by per-lane cp.async (DLLM_GEMV_BULK=0)
     unsigned long long *trace;       // -DDLLM_GEMV_TRACE: per CTA [32] globaltimer stamps, then [4][256] stage stamps of CTA 0
 };
@@ -253,6 +254,16 @@ struct ItemIter {
     }
 };
 
+// The stages of an item are ALIGNED groups of KBS k-blocks: k-block kb always sits in slot kb % KBS of its stage (the
+// item's first and last stage may be partly empty), so the aligned pairs (2j, 2j + 1) — one quantization group when the
+// group is >= 128 — always meet in one stage whatever k-block the stream-K range starts at.
+template <int KBS>
+__device__ __forceinline__ uint32_t item_stages(const Item &it) {
+    return (it.kb1 - (it.kb0 & ~(uint32_t)(KBS - 1)) + KBS - 1) / KBS;
+}
+// quantization group of a k-block (magic == 0: one k-block per group)
+__device__ __forceinline__ uint32_t kb_group(uint32_t kb, uint32_t magic) { return magic ? __umulhi(kb, magic) : kb; }
+
 // one 64-k block of a 128-column tile, consumed by the 8 warps of one group.
 // Shared-memory addresses, each already offset to this lane's element (lane = 4 g + t, output columns
 // r0 = 16 w + g and r0 + 8):
@@ -262,18 +273,9 @@ struct ItemIter {
 //        last column feed MMA columns that are never stored; they re-read the last one instead of zeroing registers.)
 //   xf : the lane's factor entry of column block 0: + 64 per column block
 // ya[nb] = the lane's f32 accumulators: columns 8 nb + 2 t, + 1 of weight column r0, then the same of r0 + 8.
-template <int CB, int MT>
-__device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_t xw, uint32_t xf, float (*ya)[4]) {
-    constexpr int NB = gemv_nb(MT);
-    // s32 accumulators start at the bits of the float 1.5 * 2^23: while |sum| < 2^22 the integer sum IS the float
-    // 12582912 + sum, so no I2F (a quarter-rate instruction) is needed.  |sum| <= 64 * 128 * 255 < 2^21.
-    constexpr int kMagicBits = 0x4B400000;
-    constexpr float kMagic = 12582912.f;
-    const int cinit[4] = {kMagicBits, kMagicBits, kMagicBits, kMagicBits};
-    const uint2 p0 = lds64(pw), p1 = lds64(pw + 64);
-
-    // A fragments of the k-block's two MMAs: rows r0 / r0 + 8, k positions as gemv_kmap says
-    uint32_t a[2][4];
+// A fragments of one k-block's two MMAs: rows r0 / r0 + 8, k positions as gemv_kmap says
+template <int CB>
+__device__ __forceinline__ void load_a_frags(uint32_t cw, uint32_t (*a)[4]) {
     if (CB == 4) {
         uint32_t q[2][2];
 #pragma unroll
@@ -297,6 +299,19 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
             a[u][2] = lds32(cw + (2 * u + 1) * 2048); a[u][3] = lds32(cw + (2 * u + 1) * 2048 + 128);
         }
     }
+}
+
+template <int CB, int MT>
+__device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_t xw, uint32_t xf, float (*ya)[4]) {
+    constexpr int NB = gemv_nb(MT);
+    // s32 accumulators start at the bits of the float 1.5 * 2^23: while |sum| < 2^22 the integer sum IS the float
+    // 12582912 + sum, so no I2F (a quarter-rate instruction) is needed.  |sum| <= 64 * 128 * 255 < 2^21.
+    constexpr int kMagicBits = 0x4B400000;
+    constexpr float kMagic = 12582912.f;
+    const int cinit[4] = {kMagicBits, kMagicBits, kMagicBits, kMagicBits};
+    const uint2 p0 = lds64(pw), p1 = lds64(pw + 64);
+    uint32_t a[2][4];
+    load_a_frags<CB>(cw, a);
     // dequantize_tensor's `(q - zp) * scale` (quantization.rs:83): sum x q - zp sum x, then * scale, per k-block in f32
     const float s0 = __uint_as_float(p0.x), s1 = __uint_as_float(p1.x);
     const float nz0 = -__uint_as_float(p0.y), nz1 = -__uint_as_float(p1.y);
@@ -309,8 +324,48 @@ __device__ __forceinline__ void consume_kblock(uint32_t cw, uint32_t pw, uint32_
         mma_u8s8(d, a[1][0], a[1][1], a[1][2], a[1][3], b.z, b.w, d);
         const float fac0 = __uint_as_float(f.x), fac1 = __uint_as_float(f.y), sx0 = __uint_as_float(f.z), sx1 = __uint_as_float(f.w);
         // every intermediate is an integer below 2^24: exact
-        const float e0 = fmaf(nz0, sx0, __int_as_float(d[0])) - kMagic, e1 = fmaf(nz0, sx1, __int_as_float(d[1])) - kMagic;
-        const float e2 = fmaf(nz1, sx0, __int_as_float(d[2])) - kMagic, e3 = fmaf(nz1, sx1, __int_as_float(d[3])) - kMagic;
+        const float e0 = fmaf(nz0, sx0, __int_as_float(d[0]) - kMagic), e1 = fmaf(nz0, sx1, __int_as_float(d[1]) - kMagic);
+        const float e2 = fmaf(nz1, sx0, __int_as_float(d[2]) - kMagic), e3 = fmaf(nz1, sx1, __int_as_float(d[3]) - kMagic);
+        ya[nb][0] = fmaf(s0 * fac0, e0, ya[nb][0]);
+        ya[nb][1] = fmaf(s0 * fac1, e1, ya[nb][1]);
+        ya[nb][2] = fmaf(s1 * fac0, e2, ya[nb][2]);
+        ya[nb][3] = fmaf(s1 * fac1, e3, ya[nb][3]);
+    }
+}
+
+// The two k-blocks of an aligned pair (2j, 2j + 1) that share their quantization parameters (group >= 128): their four MMAs
+// chain into ONE int32 sum per accumulator, and the float work — zero-point, scale, the activations' step — is done once for
+// 128 k instead of once per 64.  The activations of an aligned pair share their power-of-two step (prepare_x_tiles), so one
+// factor covers both k-blocks; the digit sums of the two add exactly.  |sum| <= 128 * 128 * 255 < 2^22 still holds, and the
+// magic offset leaves BEFORE the zero-point term joins so that every intermediate stays below 2^24.
+// The second k-block's codes are `cstep` bytes after the first one's, its activations kXTile bytes after.
+template <int CB, int MT>
+__device__ __forceinline__ void consume_pair(uint32_t cw, uint32_t cstep, uint32_t pw, uint32_t xw, uint32_t xf, float (*ya)[4]) {
+    constexpr int NB = gemv_nb(MT);
+    constexpr int kXTile = gemv_x_tile_bytes(MT);
+    constexpr int kMagicBits = 0x4B400000;
+    constexpr float kMagic = 12582912.f;
+    const int cinit[4] = {kMagicBits, kMagicBits, kMagicBits, kMagicBits};
+    const uint2 p0 = lds64(pw), p1 = lds64(pw + 64);
+    uint32_t a[4][4];
+    load_a_frags<CB>(cw, a);
+    load_a_frags<CB>(cw + cstep, a + 2);
+    const float s0 = __uint_as_float(p0.x), s1 = __uint_as_float(p1.x);
+    const float nz0 = -__uint_as_float(p0.y), nz1 = -__uint_as_float(p1.y);
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+        const uint4 b0 = lds128(xw + nb * 512), b1 = lds128(xw + kXTile + nb * 512);
+        const uint4 f0 = lds128(xf + nb * 64);
+        const uint2 f1 = lds64(xf + kXTile + nb * 64 + 8);               // the second k-block's digit sums
+        int d[4];
+        mma_u8s8(d, a[0][0], a[0][1], a[0][2], a[0][3], b0.x, b0.y, cinit);
+        mma_u8s8(d, a[1][0], a[1][1], a[1][2], a[1][3], b0.z, b0.w, d);
+        mma_u8s8(d, a[2][0], a[2][1], a[2][2], a[2][3], b1.x, b1.y, d);
+        mma_u8s8(d, a[3][0], a[3][1], a[3][2], a[3][3], b1.z, b1.w, d);
+        const float fac0 = __uint_as_float(f0.x), fac1 = __uint_as_float(f0.y);
+        const float sx0 = __uint_as_float(f0.z) + __uint_as_float(f1.x), sx1 = __uint_as_float(f0.w) + __uint_as_float(f1.y);
+        const float e0 = fmaf(nz0, sx0, __int_as_float(d[0]) - kMagic), e1 = fmaf(nz0, sx1, __int_as_float(d[1]) - kMagic);
+        const float e2 = fmaf(nz1, sx0, __int_as_float(d[2]) - kMagic), e3 = fmaf(nz1, sx1, __int_as_float(d[3]) - kMagic);
         ya[nb][0] = fmaf(s0 * fac0, e0, ya[nb][0]);
         ya[nb][1] = fmaf(s0 * fac1, e1, ya[nb][1]);
         ya[nb][2] = fmaf(s1 * fac0, e2, ya[nb][2]);
@@ -374,7 +429,10 @@ __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uin
     constexpr int kTop = P == 3 ? 22 : 14;
     constexpr int kMagicBits = 0x4B400000;
     const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    const uint32_t total = n_kb * MT * 4;
+    // work item = (aligned k-block pair, token, half, t): the 8 lanes of a (pair, token) share the step delta, whatever
+    // part of the pair [kb0, kb0 + n_kb) covers — a CTA whose range cuts a pair computes the same delta as its neighbour
+    const uint32_t kbA0 = kb0 & ~1u;
+    const uint32_t total = n_kb ? (((kb0 + n_kb + 1) >> 1) - (kb0 >> 1)) * MT * 8 : 0u;
 #pragma unroll 1
     for (uint32_t base = tid & ~31u; base < total; base += UNR * nthreads) {
         float v[UNR][16];
@@ -382,7 +440,7 @@ __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uin
         for (int j = 0; j < UNR; ++j) {
             const uint32_t idx = base + j * nthreads + (tid & 31);
             if (idx < total) {
-                gemv_x_load<CB>(x, M, K, vec, kb0 + (idx >> 2) / MT, (idx >> 2) % MT, idx & 3, v[j]);
+                gemv_x_load<CB>(x, M, K, vec, kbA0 + 2 * ((idx >> 3) / MT) + ((idx >> 2) & 1), (idx >> 3) % MT, idx & 3, v[j]);
             } else {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[j][e] = 0.f;
@@ -393,14 +451,16 @@ __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uin
         for (int j = 0; j < UNR; ++j) {
             if (base + j * nthreads >= total) break;                      // (warp-uniform) nothing left for this warp
             const uint32_t idx = base + j * nthreads + (tid & 31);
-            const bool valid = idx < total;                               // total % 4 == 0: a quad is all valid or all not
-            const uint32_t t = idx & 3, tok = (idx >> 2) % MT, kb = (idx >> 2) / MT;
-            // block scale: delta = 2^(E - kTop) with max|x| < 2^E
+            const uint32_t t = idx & 3, tok = (idx >> 3) % MT, kb = kbA0 + 2 * ((idx >> 3) / MT) + ((idx >> 2) & 1);
+            // total % 8 == 0: the 8 lanes of a (pair, token) are all inside or all outside; only k-blocks of the range are stored
+            const bool valid = idx < total && kb >= kb0 && kb < kb0 + n_kb;
+            // block scale over the pair's 128 activations: delta = 2^(E - kTop) with max|x| < 2^E
             float m = 0.f;
 #pragma unroll
             for (int e = 0; e < 16; ++e) m = fmaxf(m, fabsf(v[j][e]));
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
             m = fminf(m, 3.0e38f);
             if (j == 0 && m >= 0.f) XTRACE(25);
             int E = (int)(__float_as_uint(m) >> 23) - 126;
@@ -438,7 +498,7 @@ __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uin
                 sum[pp] += __shfl_xor_sync(0xffffffffu, sum[pp], 2);
             }
             if (valid) {
-                uint8_t *tile = dst + (size_t)kb * gemv_x_tile_bytes(MT);
+                uint8_t *tile = dst + (size_t)(kb - kb0) * gemv_x_tile_bytes(MT);
 #pragma unroll
                 for (int pp = 0; pp < P; ++pp) {
                     const uint32_t c = tok * P + pp;
@@ -560,19 +620,23 @@ gemv_mma_kernel(const GemvArgs a) {
         bool x_ready = false;
         const uint64_t w_policy = l2_evict_first_policy();
         while (iter.next(item)) {
-            const uint32_t it1 = it0 + (item.kb1 - item.kb0 + KBS - 1) / KBS;
+            const uint32_t it1 = it0 + item_stages<KBS>(item);
+            const uint32_t kbA = item.kb0 & ~(uint32_t)(KBS - 1);
             const uint8_t *wsrc = a.packed + (size_t)item.nt * a.k_blocks * kWBytes;
             const uint2 *psrc = a.gparams + (size_t)item.nt * 128;
             for (; my_it < it1; my_it += NP) {
-                const uint32_t kb = item.kb0 + (my_it - it0) * KBS;
-                const uint32_t nk = item.kb1 - kb < (uint32_t)KBS ? item.kb1 - kb : (uint32_t)KBS;
+                // the stage's k-blocks [kb, kb + nk) and the slot of the first one
+                const uint32_t sbase = kbA + (my_it - it0) * KBS;
+                const uint32_t kb = sbase > item.kb0 ? sbase : item.kb0;
+                const uint32_t nk = (sbase + KBS < item.kb1 ? sbase + KBS : item.kb1) - kb;
+                const uint32_t sl0 = kb - sbase;
                 // only `prefill` stages are requested before the activations are in shared memory: the loads of the
                 // activation preparation would otherwise queue behind a whole ring of bulk copies on this SM's memory path
                 if (XR && !x_ready && my_it >= a.prefill) { mbar_wait_relaxed(xfull, 0, 1000); x_ready = true; }
                 mbar_wait_relaxed(empty + my_s, my_ph ^ 1, 2000);
                 if (lane == 0) STRACE(0, my_it);
                 uint8_t *st = ring + (size_t)my_s * kStage;
-                // The KBS code tiles are contiguous in HBM: one cp.async.bulk (complete_tx on the stage's mbarrier).
+                // The stage's code tiles are contiguous in HBM: one cp.async.bulk (complete_tx on the stage's mbarrier).
                 // Scales / zero-points (and the activations, when they are not resident) ride on 16-byte cp.async of
                 // the warp's 32 lanes; each lane's arrival on the same mbarrier fires when its copies have landed.
                 // (Measured on 14336^2 4-bit: bulk 33.2 us, all-cp.async 34.6 us — the latter costs the producer
@@ -581,28 +645,34 @@ gemv_mma_kernel(const GemvArgs a) {
                 if (a.bulk) {
                     if (elect_one()) {
                         mbar_arrive_expect_tx(full + my_s, nk * kWBytes);
-                        bulk_load(st, src, nk * kWBytes, full + my_s, w_policy);
+                        bulk_load(st + sl0 * kWBytes, src, nk * kWBytes, full + my_s, w_policy);
                     }
                     __syncwarp();
                 } else {
 #pragma unroll 8
-                    for (uint32_t i = lane; i < nk * (kWBytes / 16); i += 32) cp_async16(st + i * 16, src + (size_t)i * 16);
+                    for (uint32_t i = lane; i < nk * (kWBytes / 16); i += 32) cp_async16(st + sl0 * kWBytes + i * 16, src + (size_t)i * 16);
                     if (lane == 0) mbar_arrive_addr(smem_u32(full + my_s));
                 }
+                // parameters: fetched into the slot of the first k-block of every quantization group the stage touches
+                // (the consumers walk the same way and read that slot for the group's other k-blocks)
+                uint32_t prev_g = 0xffffffffu;
 #pragma unroll
                 for (int sub = 0; sub < KBS; ++sub) {
-                    // (a k-block of the same quantization group as the stage's first one shares its parameters: the
-                    //  consumers read the first slot, nothing is fetched twice)
-                    if ((uint32_t)sub < nk && !(sub > 0 && a.group_magic && __umulhi(kb + sub, a.group_magic) == __umulhi(kb, a.group_magic))) {
-                        const uint2 *pg = psrc + (size_t)(a.group_magic ? __umulhi(kb + sub, a.group_magic) : kb + sub) * a.Npad;
-                        cp_async16(st + KBS * kWBytes + sub * 1024 + lane * 16, pg + lane * 2);
-                        cp_async16(st + KBS * kWBytes + sub * 1024 + 512 + lane * 16, pg + 64 + lane * 2);
+                    if ((uint32_t)sub >= sl0 && (uint32_t)sub < sl0 + nk) {
+                        const uint32_t g = kb_group(sbase + sub, a.group_magic);
+                        if (g != prev_g) {
+                            prev_g = g;
+                            const uint2 *pg = psrc + (size_t)g * a.Npad;
+                            cp_async16(st + KBS * kWBytes + sub * 1024 + lane * 16, pg + lane * 2);
+                            cp_async16(st + KBS * kWBytes + sub * 1024 + 512 + lane * 16, pg + 64 + lane * 2);
+                        }
                     }
                 }
                 if (!XR) {
                     const uint8_t *xsrc = a.xb + (size_t)kb * kXTile;
+                    uint8_t *xdst = st + KBS * (kWBytes + 1024) + sl0 * kXTile;
 #pragma unroll 4
-                    for (uint32_t i = lane; i < nk * (kXTile / 16); i += 32) cp_async16(st + KBS * (kWBytes + 1024) + i * 16, xsrc + (size_t)i * 16);
+                    for (uint32_t i = lane; i < nk * (kXTile / 16); i += 32) cp_async16(xdst + i * 16, xsrc + (size_t)i * 16);
                 }
                 cp_async_arrive(full + my_s);
                 if (lane == 0) STRACE(1, my_it);
@@ -647,24 +717,48 @@ gemv_mma_kernel(const GemvArgs a) {
         // stage counter `it` of the CTA; this group owns the stages with it % NG == grp and walks only those
         uint32_t it0 = 0, my_it = (uint32_t)grp, my_s = (uint32_t)grp, my_ph = 0;
         for (; have_item; have_item = iter.next(item)) {
-            const uint32_t len = item.kb1 - item.kb0;
-            const uint32_t it1 = it0 + (len + KBS - 1) / KBS;
-            uint32_t xa = XR ? xs_lane + (item.kb0 - rg.kb_s0 + (my_it - it0) * KBS) * kXTile : 0u;
+            const uint32_t it1 = it0 + item_stages<KBS>(item);
+            const uint32_t kbA = item.kb0 & ~(uint32_t)(KBS - 1);
             for (; my_it < it1; my_it += NG) {
                 const uint32_t c = cwa + mbar_wait_token(fa, my_ph);
                 if (ctid == 0 && my_it == 0) GTRACE(3);
                 if (w == 0 && lane == 0) STRACE(2, my_it);
-                const uint32_t xk = XR ? xa : c + xs_lane;
-                consume_kblock<CB, MT>(c, c + dpw, xk, xk + dxf, ya);
-                if (KBS == 2 && !(my_it + 1 == it1 && (len & 1))) {             // the item's last stage may hold one k-block
-                    const uint32_t kb = item.kb0 + (my_it - it0) * KBS;
-                    const bool same = a.group_magic && __umulhi(kb + 1, a.group_magic) == __umulhi(kb, a.group_magic);
-                    consume_kblock<CB, MT>(c + kWBytes, c + dpw + (same ? 0u : 1024u), xk + kXTile, xk + kXTile + dxf, ya);
+                // the stage holds the k-blocks [lo, hi) of the aligned group starting at sbase, each in its own slot
+                const uint32_t sbase = kbA + (my_it - it0) * KBS;
+                const uint32_t lo = sbase > item.kb0 ? sbase : item.kb0, hi = sbase + KBS < item.kb1 ? sbase + KBS : item.kb1;
+                const uint32_t xk = XR ? xs_lane + (sbase - rg.kb_s0) * kXTile : c + xs_lane;      // slot 0's activations (may lie before the slice: never read then)
+                if (a.fast && sbase >= item.kb0 && sbase + KBS <= item.kb1) {
+                    // a full stage of a weight whose aligned pairs share their parameters (every stage but an item's first and
+                    // last): straight-line code.  fast == 1: the whole stage is one quantization group (parameters in slot 0),
+                    // fast == 2: one group per pair (slot of the pair's first k-block).
+#pragma unroll
+                    for (int j = 0; j < KBS; j += 2)
+                        consume_pair<CB, MT>(c + j * kWBytes, kWBytes, c + dpw + (a.fast == 1 ? 0u : (uint32_t)j * 1024u), xk + j * kXTile, xk + j * kXTile + dxf, ya);
+                } else {
+                uint32_t prev_g = 0xffffffffu, pslot = 0;
+#pragma unroll 1
+                for (uint32_t j = 0; j < (uint32_t)KBS; j += 2) {
+                    const uint32_t ka = sbase + j;
+                    const bool pa = ka >= lo && ka < hi, pb = KBS > 1 && ka + 1 >= lo && ka + 1 < hi;
+                    const uint32_t ga = kb_group(ka, a.group_magic), gb = kb_group(ka + 1, a.group_magic);
+                    if (pa && pb && ga == gb) {
+                        if (ga != prev_g) { prev_g = ga; pslot = j; }
+                        consume_pair<CB, MT>(c + j * kWBytes, kWBytes, c + dpw + pslot * 1024, xk + j * kXTile, xk + j * kXTile + dxf, ya);
+                    } else {
+#pragma unroll 1
+                        for (uint32_t h = 0; h < 2; ++h) {
+                            if (!(h ? pb : pa)) continue;
+                            const uint32_t g = h ? gb : ga;
+                            if (g != prev_g) { prev_g = g; pslot = j + h; }
+                            consume_kblock<CB, MT>(c + (j + h) * kWBytes, c + dpw + pslot * 1024, xk + (j + h) * kXTile, xk + (j + h) * kXTile + dxf, ya);
+                        }
+                    }
+                }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_addr(fa + bar_bytes);
                 if (w == 0 && lane == 0) STRACE(3, my_it);
-                xa += NG * KBS * kXTile; cwa += NG * kStage; fa += NG * 8; my_s += NG;
+                cwa += NG * kStage; fa += NG * 8; my_s += NG;
                 if (my_s >= a.stages) { my_s -= a.stages; cwa -= ring_bytes; fa -= bar_bytes; my_ph ^= 1; }
             }
             it0 = it1;
@@ -838,11 +932,11 @@ gemv_xprep_kernel(const float *__restrict__ x, uint32_t M, uint32_t K, uint32_t 
     prepare_x_tiles<CB, MT, 1>(x, M, K, 0, k_blocks, xb, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
-template <int CB, int MT, bool XR>
+template <int CB, int MT, bool XR, int KBS>
 int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
     // NP == NG: a ring slot must always be filled by the same producer warp and drained by the same consumer
     // group (the stage count is a multiple of both) — parity waits of different warps on one slot could alias
-    constexpr int NG = 3, NP = 3, KBS = 2;
+    constexpr int NG = 3, NP = 3;
     static_assert(NG % NP == 0 || NP % NG == 0, "ring depth is a multiple of max(NG, NP) only");
     constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
     constexpr int kXTile = gemv_x_tile_bytes(MT);
@@ -878,6 +972,7 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
     if (k_blocks >= 65536 || (uint64_t)n_tiles * k_blocks * (kMaxContrib + 1) >= (1ull << 32)) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "GEMV path: weight too large");
     a.group_magic = group_kb == 1 ? 0u : (uint32_t)(((1ull << 32) + group_kb - 1) / group_kb);   // 0: one k-block per group
     a.S = S; a.P = P;
+    a.fast = (qw->per_tensor || group_kb % KBS == 0) ? 1u : (group_kb % 2 == 0 ? 2u : 0u);
     static const uint32_t bulk_mode = getenv("DLLM_GEMV_BULK") ? (uint32_t)atoi(getenv("DLLM_GEMV_BULK")) : 1u;
     a.bulk = bulk_mode;
     a.trace = nullptr;
@@ -1011,10 +1106,25 @@ int32_t launch_gemv_mma(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
 // the prepared activations of up to kXResident bytes stay resident in shared memory; larger ones ride the ring
 constexpr size_t kXResident = 64 * 1024;
 
+// k-blocks per ring stage.  A stage costs the same hand-offs (two mbarrier round trips, a bulk copy, the consumers' wait)
+// whatever it carries, so narrow codes take four k-blocks per stage where the ring stays >= 9 stages deep
+// (DLLM_GEMV_KBS = 2 / 4 overrides: experiments only)
+template <int CB, int MT, bool XR>
+int32_t launch_gemv_kbs(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
+    static const int kbs_env = getenv("DLLM_GEMV_KBS") ? atoi(getenv("DLLM_GEMV_KBS")) : 0;
+    constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8, kXTile = gemv_x_tile_bytes(MT);
+    constexpr int kStage4 = 4 * (kWBytes + 1024 + (XR ? 0 : kXTile));
+    const size_t fixed = (XR ? qw->k_blocks * (size_t)kXTile : 0) + 3 * MT * kRedStride * 4 + kPreTiles * MT * 512 + 1280;
+    const size_t stages4 = fixed < (size_t)kSmemBudget ? (kSmemBudget - fixed) / kStage4 : 0;
+    const bool want4 = kbs_env ? kbs_env == 4 : CB == 2;
+    if (want4 && stages4 >= 9 && qw->k_blocks >= 8) return launch_gemv_mma<CB, MT, XR, 4>(ctx, qw, x, M, y);
+    return launch_gemv_mma<CB, MT, XR, 2>(ctx, qw, x, M, y);
+}
+
 template <int CB, int MT>
 int32_t launch_gemv_x(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
-    if (qw->k_blocks * (size_t)gemv_x_tile_bytes(MT) <= kXResident) return launch_gemv_mma<CB, MT, true>(ctx, qw, x, M, y);
-    return launch_gemv_mma<CB, MT, false>(ctx, qw, x, M, y);
+    if (qw->k_blocks * (size_t)gemv_x_tile_bytes(MT) <= kXResident) return launch_gemv_kbs<CB, MT, true>(ctx, qw, x, M, y);
+    return launch_gemv_kbs<CB, MT, false>(ctx, qw, x, M, y);
 }
 
 template <int CB>

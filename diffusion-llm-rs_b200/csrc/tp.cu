@@ -3,6 +3,9 @@
 // communicator is created from a 128-byte unique id that the launcher broadcasts
 // (torch.distributed / MPI / a file), so this library needs no process manager of its own.
 #include <nccl.h>
+#include <cuda_bf16.h>
+#include <vector>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -18,9 +21,158 @@
 
 static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
 
+// ==========================================================================================
+// Peer-to-peer all-reduce over NVLink / NVSwitch (this library's own kernel, no NCCL on the data path)
+// ==========================================================================================
+// Every rank allocates one arena of the same size and maps all the others' (CUDA IPC; the 64-byte handles travel over the
+// NCCL communicator once, at set-up).  A tensor at byte offset `off` of the arena is reduced in place, "two-shot":
+//   barrier  — every rank's partial sums are complete (a rank's kernel follows its GEMM in stream order);
+//   reduce   — rank r owns the r-th 1/W of the tensor: it loads that slice from all W arenas (own HBM + W-1 peer loads over
+//              NVLink), sums in f32 in rank order, and stores the result into all W arenas (W-1 peer stores);
+//   barrier  — every slice has landed everywhere.
+// Per GPU and direction that is (W-1)/W of the tensor on NVLink, each way — the same bytes as a ring or an in-switch reduction
+// needs — in one pass with nothing staged.  Every element is summed by exactly one rank, so all ranks hold identical bits.
+// Barriers are per block: block b of rank r raises flag [phase][r][b] in every rank's flag block (st.release.sys) and waits
+// for the W flags [phase][*][b] of its own (ld.acquire.sys on local memory); the generation counter makes the flags
+// reusable without clearing.  A wait that lasts longer than ~4 s (a peer died) gives up and raises ctx->p2p_err instead of
+// hanging the GPU.  The grid must be co-resident (it is: <= 128 blocks of 512 threads, no shared memory, and while it
+// overlaps a dense kernel the latter leaves `sm_reserve` SMs free) and identical on all ranks (same code path).
+namespace {
+constexpr int kP2PMaxBlocks = 256;
+constexpr int kP2PMaxWorld = 16;
+constexpr size_t kP2PFlagBytes = 2 * kP2PMaxWorld * kP2PMaxBlocks * sizeof(uint32_t);
+
+struct P2PArgs {
+    unsigned char *base[kP2PMaxWorld];     // every rank's arena
+    size_t off;                            // byte offset of the tensor
+    size_t n16;                            // 16-byte vectors
+    size_t flag_off;                       // byte offset of the flag block
+    uint32_t epoch;                        // barrier generation of the first barrier (second: + 1)
+    int rank, world;
+    unsigned int *err;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const void *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_v4(void *p, uint4 v) {
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void p2p_barrier(const P2PArgs &a, int phase, uint32_t gen) {
+    __syncthreads();                                   // the block's stores precede thread t's fence below (causality through the barrier)
+    if ((int)threadIdx.x < a.world) {
+        __threadfence_system();
+        const int peer = threadIdx.x;
+        uint32_t *theirs = reinterpret_cast<uint32_t *>(a.base[peer] + a.flag_off) + ((size_t)phase * kP2PMaxWorld + a.rank) * kP2PMaxBlocks + blockIdx.x;
+        st_release_sys(theirs, gen);
+        const uint32_t *mine = reinterpret_cast<const uint32_t *>(a.base[a.rank] + a.flag_off) + ((size_t)phase * kP2PMaxWorld + peer) * kP2PMaxBlocks + blockIdx.x;
+        unsigned long long t0 = 0;
+        uint32_t spins = 0;
+        while ((int32_t)(ld_acquire_sys(mine) - gen) < 0) {
+            if ((++spins & 0x3ff) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ull) { atomicExch(a.err, 1u + (unsigned)peer); break; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <bool BF16>
+__device__ __forceinline__ void p2p_accumulate(float *acc, uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (BF16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // bf16 -> f32 is a 16-bit shift
+            acc[2 * i] += __uint_as_float(w[i] << 16);
+            acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += __uint_as_float(w[i]);
+    }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
+    p2p_barrier(a, 0, a.epoch);
+    const size_t per = (a.n16 + a.world - 1) / a.world;
+    const size_t i0 = per * a.rank < a.n16 ? per * a.rank : a.n16, i1 = i0 + per < a.n16 ? i0 + per : a.n16;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        uint4 v[kP2PMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kP2PMaxWorld; ++r)
+            if (r < a.world) v[r] = ld_relaxed_sys_v4(a.base[r] + a.off + i * 16);      // all loads in flight before the first add
+#pragma unroll
+        for (int r = 0; r < kP2PMaxWorld; ++r)
+            if (r < a.world) p2p_accumulate<BF16>(acc, v[r]);                            // rank order: the same sum on every rank
+        uint4 o;
+        if (BF16) {
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+            o = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
+                           *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
+        } else {
+            o = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+        }
+#pragma unroll
+        for (int r = 0; r < kP2PMaxWorld; ++r)
+            if (r < a.world) st_relaxed_sys_v4(a.base[r] + a.off + i * 16, o);
+    }
+    p2p_barrier(a, 1, a.epoch + 1);
+}
+}  // namespace
+
+// `buf` lies inside the symmetric arena and is 16-byte aligned with a multiple of 16 bytes: reduce it with the kernel above
+static bool p2p_covers(const dllm_ctx *ctx, const void *buf, size_t bytes) {
+    if (!ctx->p2p_arena || ctx->tp_world <= 1) return false;
+    const uintptr_t b = (uintptr_t)buf, a0 = (uintptr_t)ctx->p2p_arena;
+    return b >= a0 && b + bytes <= a0 + ctx->p2p_bytes && ((b - a0) & 15u) == 0 && (bytes & 15u) == 0;
+}
+
+static int32_t p2p_allreduce(dllm_ctx *ctx, void *buf, size_t bytes, bool bf16, cudaStream_t stream, bool overlapped) {
+    P2PArgs a;
+    for (int r = 0; r < kP2PMaxWorld; ++r) a.base[r] = (unsigned char *)(r < ctx->tp_world ? ctx->p2p_peer[r] : nullptr);
+    a.off = (size_t)((uintptr_t)buf - (uintptr_t)ctx->p2p_arena);
+    a.n16 = bytes / 16;
+    a.flag_off = ctx->p2p_bytes;
+    a.epoch = ctx->p2p_epoch + 1;
+    ctx->p2p_epoch += 2;
+    a.rank = ctx->tp_rank; a.world = ctx->tp_world;
+    a.err = ctx->p2p_err;
+    // alone on the GPU: one block per SM up to 128; under a dense kernel: two blocks per SM that kernel leaves free
+    const int reserve = ctx->sm_reserve >= 0 ? ctx->sm_reserve : 8;
+    int blocks = overlapped ? 2 * (reserve > 0 ? reserve : 4) : (ctx->sm_count < 128 ? ctx->sm_count : 128);
+    if (blocks > kP2PMaxBlocks) blocks = kP2PMaxBlocks;
+    if (bf16) p2p_allreduce_kernel<true><<<blocks, 512, 0, stream>>>(a);
+    else p2p_allreduce_kernel<false><<<blocks, 512, 0, stream>>>(a);
+    LAUNCH_CHECK(ctx);
+    ctx->p2p_calls++;
+    return DLLM_OK;
+}
+
 int32_t tp_allreduce(dllm_ctx *ctx, float *buf, size_t n) {
     if (ctx->tp_world <= 1 || n == 0 || ctx->tp_skip_comm) return DLLM_OK;
     if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
+    if (p2p_covers(ctx, buf, n * 4)) return p2p_allreduce(ctx, buf, n * 4, false, ctx->stream, false);
     NCCL_TRY(ctx, ncclAllReduce(buf, buf, n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return DLLM_OK;
 }
@@ -30,6 +182,7 @@ int32_t tp_allreduce(dllm_ctx *ctx, float *buf, size_t n) {
 int32_t tp_allreduce_bf16(dllm_ctx *ctx, void *buf, size_t n) {
     if (ctx->tp_world <= 1 || n == 0 || ctx->tp_skip_comm) return DLLM_OK;
     if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
+    if (p2p_covers(ctx, buf, n * 2)) return p2p_allreduce(ctx, buf, n * 2, true, ctx->stream, false);
     NCCL_TRY(ctx, ncclAllReduce(buf, buf, n, ncclBfloat16, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return DLLM_OK;
 }
@@ -38,6 +191,7 @@ int32_t tp_allreduce_bf16(dllm_ctx *ctx, void *buf, size_t n) {
 int32_t tp_allreduce_on(dllm_ctx *ctx, void *buf, size_t n, bool bf16, cudaStream_t stream) {
     if (ctx->tp_world <= 1 || n == 0 || ctx->tp_skip_comm) return DLLM_OK;
     if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
+    if (p2p_covers(ctx, buf, n * (bf16 ? 2 : 4))) return p2p_allreduce(ctx, buf, n * (bf16 ? 2 : 4), bf16, stream, stream != ctx->stream);
     NCCL_TRY(ctx, ncclAllReduce(buf, buf, n, bf16 ? ncclBfloat16 : ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, stream));
     return DLLM_OK;
 }
@@ -110,8 +264,114 @@ int32_t dllm_tp_init(dllm_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t
     return DLLM_OK;
 }
 
+// tear the arena down: peers' mappings first, then (after everybody has unmapped: the caller's group barrier) the allocation
+static void p2p_release(dllm_ctx *ctx) {
+    if (!ctx->p2p_arena) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+    for (int r = 0; r < ctx->tp_world && r < kP2PMaxWorld; ++r)
+        if (r != ctx->tp_rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+    if (ctx->nccl_comm) {   // nobody frees while a peer still maps it
+        ncclAllReduce(ctx->p2p_err, ctx->p2p_err, 1, ncclUint32, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(ctx->p2p_arena);
+    cudaFree(ctx->p2p_err);
+    ctx->p2p_arena = nullptr; ctx->p2p_err = nullptr; ctx->p2p_bytes = 0;
+    for (auto &q : ctx->p2p_peer) q = nullptr;
+    cudaGetLastError();
+}
+
+int32_t dllm_tp_p2p_enable(dllm_ctx *ctx, size_t arena_bytes) {
+    if (!ctx) return DLLM_ERR_NULL;
+    ctx->err[0] = 0;
+    if (ctx->tp_world <= 1) return DLLM_OK;                       // nothing to exchange
+    if (!ctx->nccl_comm) DLLM_FAIL(ctx, DLLM_ERR_NCCL, "dllm_tp_init has not been called");
+    if (ctx->tp_world > kP2PMaxWorld) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "peer-to-peer all-reduce supports up to %d ranks", kP2PMaxWorld);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    p2p_release(ctx);
+    arena_bytes = (arena_bytes + 4095) & ~(size_t)4095;
+    const int W = ctx->tp_world;
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    // every rank must end up with the same verdict, so failures are agreed on through the communicator before returning
+    void *arena = nullptr;
+    unsigned int *err = nullptr;
+    unsigned char *d_handles = nullptr;
+    uint32_t ok = 1;
+    if (cudaMalloc(&arena, arena_bytes + kP2PFlagBytes) != cudaSuccess) ok = 0;
+    if (ok && cudaMalloc(&err, 2 * sizeof(unsigned int)) != cudaSuccess) ok = 0;
+    if (ok && cudaMalloc(&d_handles, (size_t)W * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) ok = 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine, arena) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    std::vector<cudaIpcMemHandle_t> all((size_t)W);
+    if (ok) {
+        cudaMemsetAsync(arena, 0, arena_bytes + kP2PFlagBytes, ctx->stream);
+        cudaMemsetAsync(err, 0, 2 * sizeof(unsigned int), ctx->stream);
+        cudaMemcpyAsync(d_handles + (size_t)ctx->tp_rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    // (a rank that failed above still takes part in the collectives below with ok = 0)
+    unsigned int *d_ok = nullptr;
+    if (cudaMalloc(&d_ok, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); DLLM_FAIL(ctx, DLLM_ERR_OOM, "cudaMalloc failed"); }
+    auto agree = [&](uint32_t v) -> int {
+        cudaMemcpyAsync(d_ok, &v, sizeof(v), cudaMemcpyHostToDevice, ctx->stream);
+        if (ncclAllReduce(d_ok, d_ok, 1, ncclUint32, ncclMin, comm, ctx->stream) != ncclSuccess) return -1;
+        uint32_t out = 0;
+        cudaMemcpyAsync(&out, d_ok, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+        return (int)out;
+    };
+    int all_ok = agree(ok);
+    if (all_ok == 1) {
+        if (ncclAllGather(d_handles + (size_t)ctx->tp_rank * sizeof(mine), d_handles, sizeof(mine), ncclUint8, comm, ctx->stream) != ncclSuccess) ok = 0;
+        cudaMemcpyAsync(all.data(), d_handles, (size_t)W * sizeof(mine), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = 0;
+        for (int r = 0; r < W && ok; ++r) {
+            if (r == ctx->tp_rank) { ctx->p2p_peer[r] = arena; continue; }
+            void *q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+            ctx->p2p_peer[r] = q;
+        }
+        all_ok = agree(ok);          // also the barrier after which every arena is zeroed and mapped everywhere
+    }
+    cudaFree(d_ok);
+    if (d_handles) cudaFree(d_handles);
+    if (all_ok != 1) {
+        for (int r = 0; r < W; ++r) {
+            if (r != ctx->tp_rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+            ctx->p2p_peer[r] = nullptr;
+        }
+        if (arena) cudaFree(arena);
+        if (err) cudaFree(err);
+        cudaGetLastError();
+        DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "peer-to-peer arena could not be set up on every rank (CUDA IPC / peer access unavailable): the NCCL path stays in use");
+    }
+    ctx->p2p_arena = arena;
+    ctx->p2p_bytes = arena_bytes;
+    ctx->p2p_err = err;
+    ctx->p2p_epoch = 0;
+    return DLLM_OK;
+}
+
+int32_t dllm_tp_p2p_status(dllm_ctx *ctx, size_t *arena_bytes, uint64_t *allreduces, uint32_t *timed_out) {
+    if (!ctx) return DLLM_ERR_NULL;
+    if (arena_bytes) *arena_bytes = ctx->p2p_arena ? ctx->p2p_bytes : 0;
+    if (allreduces) *allreduces = ctx->p2p_calls;
+    if (timed_out) {
+        *timed_out = 0;
+        if (ctx->p2p_err) {
+            cudaSetDevice(ctx->device);
+            if (cudaMemcpy(timed_out, ctx->p2p_err, sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return DLLM_ERR_CUDA;
+        }
+    }
+    return DLLM_OK;
+}
+
 int32_t dllm_tp_finalize(dllm_ctx *ctx) {
     if (!ctx) return DLLM_ERR_NULL;
+    p2p_release(ctx);
     if (ctx->nccl_comm) {
         ncclCommDestroy((ncclComm_t)ctx->nccl_comm);
         ctx->nccl_comm = nullptr;

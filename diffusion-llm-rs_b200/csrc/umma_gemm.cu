@@ -1693,15 +1693,19 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
 }
 
 
-// tokens per pair tile: the candidate that needs the fewest token-columns of MMA time on sms/2 CTA pairs (full waves count;
-// ties go to the wider tile: fewer weight passes)
+// tokens per pair tile: the candidate with the least estimated time on sms/2 CTA pairs — full waves count.  A tile's time is
+// not proportional to its width: the weight tile is dequantized once per tile whatever the width, so a 128-token tile costs
+// 80 % of a 256-token one.  Measured (scripts/ntok_sweep.py, profiles/r2_ntok_sweep.jsonl; [4096,14336] x 8192 tokens, us per
+// wave): 128 -> 22.6, 160 -> 22.9, 192 -> 24.6, 224 -> 26.6, 256 -> 28.4, i.e. max(22.6, 12.6 + 0.0617 ntok): in units of
+// token-columns, waves x max(365, ntok + 205).  (The first version charged ntok + 6 and picked 128- to 160-token tiles whenever
+// they filled the last wave better: up to 1.64x slower than 256 at 4096 tokens.)  Ties go to the wider tile: fewer weight passes.
 static uint32_t pair2_pick_ntok(size_t M, uint32_t n_pairs, uint32_t pairs_hw) {
     uint32_t best = 0;
     uint64_t best_cost = ~0ull;
     for (uint32_t ntok = 256; ntok >= 128; ntok -= 32) {
         const uint64_t m_tiles = (M + ntok - 1) / ntok, tiles = m_tiles * n_pairs;
         const uint64_t waves = (tiles + pairs_hw - 1) / pairs_hw;
-        const uint64_t cost = waves * (ntok + 6);          // + a few columns' worth of per-tile set-up / drain
+        const uint64_t cost = waves * (ntok + 205 > 365 ? ntok + 205 : 365);
         if (cost < best_cost) { best_cost = cost; best = ntok; }
     }
     return best;
@@ -1739,7 +1743,8 @@ int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_b
     a.k_blocks = (uint32_t)qw->k_blocks; a.n_tiles = (uint32_t)qw->n_tiles; a.n_pairs = (a.n_tiles + 1) / 2;
     a.group_kb = (uint32_t)(qw->group / WL_TILE_K);
     const uint32_t pairs_hw = (uint32_t)(ctx->sm_limit > 0 && ctx->sm_limit < ctx->sm_count ? ctx->sm_limit : ctx->sm_count) / 2;
-    static const int ntok_env = getenv("DLLM_UMMA_NTOK2") ? atoi(getenv("DLLM_UMMA_NTOK2")) : 0;     // experiments only
+    const char *ntok_s = getenv("DLLM_UMMA_NTOK2");                                                 // experiments only (read per launch: scripts/ntok_sweep.py)
+    const int ntok_env = ntok_s ? atoi(ntok_s) : 0;
     a.ntok = (ntok_env >= 32 && ntok_env <= 256 && ntok_env % 32 == 0) ? (uint32_t)ntok_env : pair2_pick_ntok(M, a.n_pairs, pairs_hw);
     a.m_tiles = (uint32_t)((M + a.ntok - 1) / a.ntok);
     a.tiles = a.n_pairs * a.m_tiles;

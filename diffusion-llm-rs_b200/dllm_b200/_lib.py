@@ -175,6 +175,8 @@ SIGNATURES = {
     "dllm_tp_init": (C.c_int32, [c_vp, c_vp, C.c_int32, C.c_int32]),
     "dllm_tp_finalize": (C.c_int32, [c_vp]),
     "dllm_tp_configure": (C.c_int32, [c_vp, C.c_int32, C.c_int32, C.c_int32]),
+    "dllm_tp_p2p_enable": (C.c_int32, [c_vp, c_sz]),
+    "dllm_tp_p2p_status": (C.c_int32, [c_vp, C.POINTER(c_sz), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "dllm_tp_allreduce_dev": (C.c_int32, [c_vp, c_vp, c_sz]),
     "dllm_tp_allgather_cols_dev": (C.c_int32, [c_vp, c_vp, c_sz, c_sz, c_vp]),
     "dllm_model_set_parallel": (C.c_int32, [c_vp, c_vp, c_vp, c_sz]),

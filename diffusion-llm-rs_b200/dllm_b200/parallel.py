@@ -116,6 +116,23 @@ class TensorParallelGroup:
         arr = (C.c_int32 * len(plan))(*plan)
         self.ctx._ck(self.ctx._lib.dllm_model_set_parallel(self.ctx.h, model.h, arr, len(plan)))
 
+    def enable_p2p(self, max_tokens: int, max_width: int) -> bool:
+        """Switch the row-parallel all-reduces of tcgen05 stacks to the library's own NVLink kernel: a symmetric arena for
+        the two bf16 activation buffers [max_tokens, max_width] (+ slack for chunk rounding).  Collective.  False (on every
+        rank) when CUDA IPC / peer access is unavailable — the NCCL path then stays in use."""
+        from . import _lib as L
+        need = 2 * ((max_tokens + 512) * max_width * 2 + 4096)
+        try:
+            self.ctx._ck(self.ctx._lib.dllm_tp_p2p_enable(self.ctx.h, need))
+        except L.DllmError:
+            return False
+        return self.world > 1
+
+    def p2p_status(self):
+        b, n, t = C.c_size_t(), C.c_uint64(), C.c_uint32()
+        self.ctx._ck(self.ctx._lib.dllm_tp_p2p_status(self.ctx.h, C.byref(b), C.byref(n), C.byref(t)))
+        return {"arena_bytes": b.value, "allreduces": n.value, "timed_out": t.value}
+
     def allreduce_dev(self, buf_dev: int, n: int):
         self.ctx._ck(self.ctx._lib.dllm_tp_allreduce_dev(self.ctx.h, buf_dev, n))
 

@@ -371,6 +371,16 @@ DLLM_API int32_t dllm_tp_finalize(dllm_ctx *ctx);
  * leave `reserve_sms` SMs (-1 = default 8) to the collective.  skip_comm != 0 runs the sharded stack WITHOUT its collectives
  * (wrong results; measurement of the exposed collective time only). */
 DLLM_API int32_t dllm_tp_configure(dllm_ctx *ctx, int32_t chunks, int32_t reserve_sms, int32_t skip_comm);
+/* This library's own all-reduce over NVLink peer memory (tp.cu: two-shot reduce with peer loads / stores and flag barriers).
+ * Every rank of the group allocates an arena of `arena_bytes` and maps all the others' through CUDA IPC (the handles travel
+ * over the communicator of dllm_tp_init, so no extra rendezvous is needed); a tensor-parallel tcgen05 stack whose two activation
+ * buffers fit into it (2 x tokens x widest shard x 2 bytes) then reduces its row-parallel partial sums in place with that
+ * kernel instead of ncclAllReduce.  Collective: every rank calls it, in the same order relative to other collectives.
+ * DLLM_ERR_UNSUPPORTED (on every rank alike) if some rank cannot map its peers: the NCCL path stays in use.
+ * dllm_tp_p2p_status: arena size (0 = off), all-reduces done by the kernel so far, and whether a barrier ever timed out
+ * (a peer died: results after that are invalid). */
+DLLM_API int32_t dllm_tp_p2p_enable(dllm_ctx *ctx, size_t arena_bytes);
+DLLM_API int32_t dllm_tp_p2p_status(dllm_ctx *ctx, size_t *arena_bytes, uint64_t *allreduces, uint32_t *timed_out);
 /* sum-all-reduce of a device f32 buffer over the TP group (row-parallel partial sums) */
 DLLM_API int32_t dllm_tp_allreduce_dev(dllm_ctx *ctx, float *buf_dev, size_t n);
 /* all-gather of column shards: in [M, N/world] per rank -> out [M, N] */

@@ -167,20 +167,21 @@ def test_dequant_matmul_example_config0(ctx, O):
 
 # ---------------------------------------------------------------- linear, HBM-bound GEMV path (1..16 tokens)
 def gemv_check(y, y64, bound, x=None, wd=None):
-    """int8 tensor path: codes, zero-points and the integer sums are exact; x is rounded to block fixed point per 64
-    activations (error <= 2^-22 of the block's max |x| for 1-2 tokens, 2^-14 for 3-16), scale and accumulation across
-    k-blocks are f32.  With x and the dequantized weight given, every output is checked against
+    """int8 tensor path: codes, zero-points and the integer sums are exact; x is rounded to block fixed point per aligned
+    block of 128 activations (two 64-k blocks share their power-of-two step, so that their integer sums can be added before
+    the float work; error <= 2^-22 of the block's max |x| for 1-2 tokens, 2^-14 for 3-16), scale and accumulation across
+    blocks are f32.  With x and the dequantized weight given, every output is checked against
     B2 = sum over blocks of max|x_block| * sum|w_block|: 2^-14 B2 for 3-16 tokens; for 1-2 tokens the f32 rounding of the
     per-block terms (each up to max|x_block| * sum|w_block|) is of the same order as the 2^-22 digit error: 2^-20 B2.
     Always also against 2^-12 * sum|x||w| (ample for Gaussian x)."""
     err = np.abs(y - y64)
     if x is not None:
         M, K = x.shape
-        kb = (K + 63) // 64
-        xp = np.zeros((M, kb * 64)); xp[:, :K] = np.abs(x)
-        wp = np.zeros((kb * 64, wd.shape[1])); wp[:K] = np.abs(wd)
-        bmax = xp.reshape(M, kb, 64).max(axis=2)                         # [M, kb]
-        wsum = wp.reshape(kb, 64, -1).sum(axis=1)                         # [kb, N]
+        kb = (K + 127) // 128
+        xp = np.zeros((M, kb * 128)); xp[:, :K] = np.abs(x)
+        wp = np.zeros((kb * 128, wd.shape[1])); wp[:K] = np.abs(wd)
+        bmax = xp.reshape(M, kb, 128).max(axis=2)                        # [M, kb]
+        wsum = wp.reshape(kb, 128, -1).sum(axis=1)                        # [kb, N]
         tight = (2.0 ** -20 if M <= 2 else 2.0 ** -14 + 2.0 ** -20) * (bmax @ wsum)
         assert np.all(err <= tight + 1e-6), float((err / (tight + 1e-30)).max())
     else:
@@ -244,6 +245,28 @@ def test_qlinear_gemv_shapes(ctx, O, shape, group):
     gemv_check(y, y64, bound)
     y2 = qw.forward(x, PATH_GEMV)              # tickets re-armed; fixed reduction order
     assert beq(y, y2)
+    qw.close()
+
+
+@pytest.mark.parametrize("bits", [2, 4, 8])
+@pytest.mark.parametrize("group,K", [(64, 448), (192, 1152), (256, 2048), (128, 1408), (0, 1472), (128, 14336)])
+@pytest.mark.parametrize("M", [1, 5, 16])
+def test_qlinear_gemv_stage_shapes(ctx, O, bits, group, K, M):
+    """The ring stages hold aligned groups of 2 or 4 k-blocks and the two k-blocks of an aligned pair are summed in int32
+    when they share their parameters: groups of 64 (never shared), 192 (three k-blocks: pairs straddle groups), 256 and
+    per-tensor parameters (whole stages shared), odd k-block counts, and stream-K ranges that start in the middle of a pair."""
+    from dllm_b200 import QWeight, PATH_GEMV
+    rng = np.random.default_rng(K + M + bits + group)
+    N = 384 if K < 8192 else 256
+    w = make_w(rng, K, N)
+    x = rng.standard_normal((M, K)).astype(F)
+    x[:, 64:128] *= 50.0                         # the two halves of an aligned pair differ in magnitude
+    bias = rng.standard_normal(N).astype(F)
+    qw = QWeight.quantize(ctx, w, bits, group, bias)
+    y = qw.forward(x, PATH_GEMV)
+    wd, y64, bound = ref_linear(O, x, w, bits, group, bias)
+    gemv_check(y, y64, bound, x, wd)
+    assert beq(y, qw.forward(x, PATH_GEMV))
     qw.close()
 
 
