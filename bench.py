@@ -408,20 +408,40 @@ def tp7b_block(ctx, stream, tm, rank, world, tpg, pk):
     else:
         n_ar = sum(1 for p in plan if p == PAR.ROW)
         ar_bytes = sum(tokens * n * (4 if i + 1 == len(shapes) else 2) for i, ((k, n), p) in enumerate(zip(shapes, plan)) if p == PAR.ROW)
-        # overlapped (default): 2 token chunks, all-reduces on the communication stream
-        ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
-        x.copy_(x0)
-        ms_tp = tm.run(step_of(m_tp), 5, 2)
-        # the same sharded stack WITHOUT its collectives: what is left of the step is GEMM time
-        ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 1))
-        ms_nocomm = tm.run(step_of(m_tp), 3, 1)
-        # collectives on the compute stream, one all-reduce per row-parallel linear (round 1's design)
-        ctx._ck(lib.dllm_tp_configure(ctx.h, 1, 0, 0))
-        x.copy_(x0)
-        ms_serial = tm.run(step_of(m_tp), 3, 1)
-        ctx._ck(lib.dllm_tp_configure(ctx.h, 1, 0, 1))
-        ms_serial_nocomm = tm.run(step_of(m_tp), 3, 1)
-        ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
+        maxw = max(max((n // world if p == PAR.COLUMN else n), (k // world if p == PAR.ROW else k)) for (k, n), p in zip(shapes, plan))
+
+        def timed(chunks, reserve):
+            """the step with its collectives, then the same sharded stack WITHOUT them: what is left is GEMM time"""
+            ctx._ck(lib.dllm_tp_configure(ctx.h, chunks, reserve, 0))
+            x.copy_(x0)
+            ms_c = tm.run(step_of(m_tp), 5, 2)
+            ctx._ck(lib.dllm_tp_configure(ctx.h, chunks, reserve, 1))
+            ms_n = tm.run(step_of(m_tp), 3, 1)
+            ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
+            return {"ms_per_step": ms_c, "gemm_only_ms": ms_n, "exposed_collective_ms": ms_c - ms_n,
+                    "efficiency_vs_single_gpu": ms_single / (world * ms_c)}
+
+        modes = {}
+        # (a) NCCL at the layer boundary, on the compute stream (round 1's design) and overlapped on a second stream, 2 token chunks
+        modes["nccl_serial"] = timed(1, 0)
+        modes["nccl_overlapped_2_chunks"] = timed(2, 8)
+        # (b) this library's own all-reduce over NVLink peer memory (csrc/tp.cu), same two placements
+        p2p = tpg.enable_p2p(tokens, max(maxw, H))
+        if p2p:
+            modes["p2p_serial"] = timed(1, 0)
+            modes["p2p_overlapped_2_chunks"] = timed(2, 16)
+            n64 = 16 << 20
+            st = tpg.p2p_status()
+            ms_p2p = tm.run(lambda i: tpg.allreduce_dev(st["arena"], n64), 20, 3)
+        best = min(modes, key=lambda k: modes[k]["ms_per_step"])
+        ms_tp, ms_nocomm = modes[best]["ms_per_step"], modes[best]["gemm_only_ms"]
+        cfg_of = {"nccl_serial": (1, 0), "nccl_overlapped_2_chunks": (2, 8), "p2p_serial": (1, 0), "p2p_overlapped_2_chunks": (2, 16)}
+        if p2p and not best.startswith("p2p"):
+            tpg.disable_p2p()
+            p2p_used = False
+        else:
+            p2p_used = p2p
+        ctx._ck(lib.dllm_tp_configure(ctx.h, cfg_of[best][0], cfg_of[best][1], 0))
         # the collective alone: 64 MiB all-reduces back to back (the size of one [8192, 4096] bf16 boundary tensor)
         buf = torch.zeros(16 << 20, device="cuda")
         ms_ar = tm.run(lambda i: tpg.allreduce_dev(buf.data_ptr(), buf.numel()), 20, 3)
@@ -450,12 +470,16 @@ def tp7b_block(ctx, stream, tm, rank, world, tpg, pk):
             "tflops_per_gpu": flops / ms_tp / 1e9 / world, "efficiency_vs_single_gpu": ms_single / (world * ms_tp),
             "plan": f"{n_ar} column->row pairs, one bf16 all-reduce each at the layer boundary (f32 for the stack's last layer)",
             "allreduces_per_step": n_ar, "allreduce_bytes_per_step": ar_bytes,
-            "overlap": {"token_chunks": 2, "reserved_sms": 8, "gemm_only_ms": ms_nocomm, "exposed_collective_ms": ms_tp - ms_nocomm},
-            "no_overlap": {"ms_per_step": ms_serial, "gemm_only_ms": ms_serial_nocomm, "exposed_collective_ms": ms_serial - ms_serial_nocomm,
-                           "efficiency_vs_single_gpu": ms_single / (world * ms_serial)},
-            "allreduce_64MiB": {"ms": ms_ar, "algbw_GBps": algbw, "busbw_GBps": algbw * 2 * (world - 1) / world},
-            "limiting_collective": "ncclAllReduce of the row-parallel partial sums ([tokens, N] bf16), "
-                                   f"{ar_bytes / 1e9:.2f} GB per step per GPU",
+            "mode": best, "gemm_only_ms": ms_nocomm, "exposed_collective_ms": ms_tp - ms_nocomm,
+            "modes": modes,
+            "allreduce_64MiB": {"nccl_ms": ms_ar, "nccl_algbw_GBps": algbw,
+                                "p2p_ms": ms_p2p if p2p else None,
+                                "p2p_algbw_GBps": (16 << 20) * 4 / ms_p2p / 1e6 if p2p else None,
+                                "p2p_link_GBps_per_direction": (16 << 20) * 4 * 2 * (world - 1) / world / ms_p2p / 1e6 if p2p else None},
+            "p2p": {"available": bool(p2p), "used_for_the_headline": bool(p2p_used),
+                    "kernel": "p2p_allreduce_kernel (two-shot over a CUDA-IPC arena: peer loads / stores + flag barriers)"},
+            "limiting_collective": "all-reduce of the row-parallel partial sums ([tokens, N] bf16, in place), "
+                                   f"{ar_bytes / 1e9:.2f} GB per step per GPU = {2 * (world - 1) / world * ar_bytes / 1e9:.2f} GB on NVLink per direction",
             "vs_unsharded_rel_err": rel,
             "token_split": {"parallelism": f"tokens/{world} per GPU, replicated weights, no collective", "ms_per_step": ms_split,
                             "steps_per_sec": 1e3 / ms_split, "efficiency_vs_single_gpu": ms_single / (world * ms_split)},

@@ -115,6 +115,13 @@ int32_t dllm_ctx_sync(dllm_ctx *ctx) {
 void *dllm_ctx_stream(dllm_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 const char *dllm_last_error(const dllm_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 uint64_t dllm_launch_count(const dllm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int32_t dllm_copy_bytes(const dllm_ctx *ctx, uint64_t *h2d, uint64_t *d2h) {
+    if (!ctx) return DLLM_ERR_NULL;
+    if (h2d) *h2d = ctx->h2d_bytes;
+    if (d2h) *d2h = ctx->d2h_bytes;
+    return DLLM_OK;
+}
+
 uint64_t dllm_graph_replay_count(const dllm_ctx *ctx) { return ctx ? ctx->graph_replays : 0; }
 int32_t dllm_sm_count(const dllm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
@@ -175,11 +182,13 @@ int32_t dllm_free(dllm_ctx *ctx, void *dptr) {
 int32_t dllm_memcpy_h2d(dllm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
     CTX_CHECK(ctx);
     if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += bytes;
     return DLLM_OK;
 }
 int32_t dllm_memcpy_d2h(dllm_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
     CTX_CHECK(ctx);
     if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h_bytes += bytes;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return DLLM_OK;
 }
@@ -199,6 +208,7 @@ static int32_t stage_in(dllm_ctx *ctx, int slot, const void *host, size_t bytes,
     DLLM_TRY(ensure_buf(ctx, ctx->ws[slot], bytes ? bytes : 16));
     *dev = ctx->ws[slot].p;
     if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += bytes;
     return DLLM_OK;
 }
 static int32_t stage_out_buf(dllm_ctx *ctx, int slot, size_t bytes, void **dev) {
@@ -208,6 +218,7 @@ static int32_t stage_out_buf(dllm_ctx *ctx, int slot, size_t bytes, void **dev) 
 }
 static int32_t copy_out(dllm_ctx *ctx, void *host, const void *dev, size_t bytes) {
     if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h_bytes += bytes;
     return DLLM_OK;
 }
 static int32_t sync(dllm_ctx *ctx) {
@@ -1061,7 +1072,9 @@ static int32_t forward_tp_overlapped(dllm_ctx *ctx, dllm_model *m, const float *
     for (int c = 0; c < chunks; ++c)
         if (c0[c + 1] > c0[c])
             DLLM_TRY(k_f32_to_bf16(ctx, x_dev + c0[c] * m->layers[0]->K, (c0[c + 1] - c0[c]) * m->layers[0]->K, buf0 + c * region));
-    const int reserve = ctx->sm_reserve >= 0 ? ctx->sm_reserve : env_int("DLLM_TP_RESERVE_SMS", 8);
+    // SMs left to the collective: NCCL's few CTAs need 8; the library's own all-reduce keeps NVLink busy from 16
+    // (measured at TP2, 7B-class: NCCL 2 chunks / 8 SMs 50.9 ms, own kernel 2 chunks / 16 SMs 49.2 ms per step)
+    const int reserve = ctx->sm_reserve >= 0 ? ctx->sm_reserve : env_int("DLLM_TP_RESERVE_SMS", ctx->p2p_arena ? 16 : 8);
     ctx->sm_limit = ctx->sm_count - reserve;
     std::vector<char> pending(chunks, 0);          // chunk c's input is still being all-reduced on the comm stream
     char *cur = buf0, *nxt = buf1;
@@ -1354,6 +1367,7 @@ static int32_t upload_rowmap(dllm_ctx *ctx, dllm_model *m, const size_t *t, size
     m->h_rowmap.resize(batch);
     for (size_t b = 0; b < batch; ++b) m->h_rowmap[b] = (int)(t[b] < m->T - 1 ? t[b] : m->T - 1);   // lib.rs:1174 clamp
     CUDA_TRY(ctx, cudaMemcpyAsync(m->d_rowmap, m->h_rowmap.data(), batch * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += batch * sizeof(int);
     return DLLM_OK;
 }
 
@@ -1442,10 +1456,12 @@ int32_t dllm_denoise_step(dllm_ctx *ctx, dllm_model *m, float *x, const float *z
     dx = ctx->ws[4].p;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_step[0], ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(dx, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += n * sizeof(float);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_step[1], ctx->stream));
     if (noise) {
         dz = ctx->ws[6].p;
         CUDA_TRY(ctx, cudaMemcpyAsync(dz, z, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+        ctx->h2d_bytes += n * sizeof(float);
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
     }
     DLLM_TRY(dllm_model_forward_dev(ctx, m, (const float *)dx, batch, feat, (float *)dpred, path));   // lib.rs:924
@@ -1506,6 +1522,31 @@ int32_t dllm_denoise_step_seeded_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev,
     ARG_CHECK(ctx, x_dev, DLLM_ERR_NULL, "null device pointer");
     ARG_CHECK(ctx, t <= 0x7fffffffu, DLLM_ERR_INVALID_PARAMS, "timestep out of range");
     return step_seeded(ctx, m, x_dev, nullptr, t, seed, batch, feat, guard_t0, path);
+}
+
+// p_sample alone on device tensors (lib.rs:1152-1215) — for callers that produce noise_pred themselves (the cached branch of
+// the sampling loop, lib.rs:910-921).  x_prev_dev may alias x_t_dev.  z_dev == NULL or t == 0: no noise term.
+int32_t dllm_p_sample_dev(dllm_ctx *ctx, dllm_model *m, const float *x_t_dev, const float *noise_pred_dev, const float *z_dev,
+                          size_t t, size_t batch, size_t feat, int32_t guard_t0, float *x_prev_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    if (batch * feat == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_t_dev && noise_pred_dev && x_prev_dev, DLLM_ERR_NULL, "null device pointer");
+    const int row = (int)(t < m->T - 1 ? t : m->T - 1);
+    return k_p_sample(ctx, x_t_dev, noise_pred_dev, t > 0 ? z_dev : nullptr, m->d_coef_table[guard_t0 ? 1 : 0], nullptr, row, batch,
+                      feat, x_prev_dev);
+}
+
+// the same with the noise of timestep t drawn inside the kernel from the counter-based generator (stream t of `seed`)
+int32_t dllm_p_sample_seeded_dev(dllm_ctx *ctx, dllm_model *m, const float *x_t_dev, const float *noise_pred_dev, uint64_t seed,
+                                 size_t t, size_t batch, size_t feat, int32_t guard_t0, float *x_prev_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, m, DLLM_ERR_NULL, "null model");
+    if (batch * feat == 0) return DLLM_OK;
+    ARG_CHECK(ctx, x_t_dev && noise_pred_dev && x_prev_dev, DLLM_ERR_NULL, "null device pointer");
+    ARG_CHECK(ctx, t <= 0x7fffffffu, DLLM_ERR_INVALID_PARAMS, "timestep out of range");
+    return k_p_sample_seeded(ctx, x_t_dev, noise_pred_dev, m->d_coef_table[guard_t0 ? 1 : 0], nullptr, (int)t, seed, (int)m->T,
+                             batch * feat, x_prev_dev);
 }
 
 int32_t dllm_sample_seeded_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, uint64_t seed, size_t batch, size_t feat,
@@ -1592,6 +1633,7 @@ int32_t dllm_sample(dllm_ctx *ctx, dllm_model *m, const float *x0, const float *
     for (size_t t = num_steps; t-- > 0;) {                           // lib.rs:881 `(0..num_steps).rev()`
         if (noises && t > 0)
             CUDA_TRY(ctx, cudaMemcpyAsync(dz, noises + t * n, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_bytes += n * sizeof(float);
         DLLM_TRY(dllm_denoise_step_dev(ctx, m, (float *)dx, noises ? (const float *)dz : nullptr, t, batch, feat,
                                        guard_t0, path));
     }
@@ -1622,13 +1664,15 @@ static size_t kv_row_bytes(const dllm_kv *kv) { return kv->packed ? kv->H * kv->
 
 // quantize tokens [s0, s0 + t) of every layer from src [L, t, H] (schemes with per-row or fixed parameters: a row's codes
 // depend on that row only, so tokens already in the cache never change)
-static int32_t kv_quantize_rows(dllm_ctx *ctx, dllm_kv *kv, int which, const float *src_dev, size_t s0, size_t t) {
+static int32_t kv_quantize_rows(dllm_ctx *ctx, dllm_kv *kv, int which, const float *src_dev, size_t s0, size_t t,
+                                size_t src_layer_rows = 0) {
     const int pack = kv->packed ? kv->bits : 0;
     const size_t rb = kv_row_bytes(kv), rows_cap = kv->L * kv->cap;
-    const bool contiguous = kv->cap == t && s0 == 0;
+    if (src_layer_rows == 0) src_layer_rows = t;          // rows between two layers of the source (dense by default)
+    const bool contiguous = kv->cap == t && s0 == 0 && src_layer_rows == t;
     const size_t n_l = contiguous ? kv->L : 1, loops = contiguous ? 1 : kv->L;
     for (size_t l = 0; l < loops; ++l) {
-        const float *src = src_dev + l * t * kv->H;
+        const float *src = src_dev + l * src_layer_rows * kv->H;
         const size_t r0 = l * kv->cap + s0;
         if (kv->scheme == DLLM_KV_ROW_D)
             DLLM_TRY(k_quant_d_rows(ctx, src, n_l * t, kv->H, nullptr, 1, kv->bits, pack, kv->d_codes[which] + r0 * rb,
@@ -1890,6 +1934,224 @@ size_t dllm_kv_memory_usage(const dllm_kv *kv) {
     if (!kv) return 0;
     const size_t len = kv->L * kv->S * kv->H;                 // quantized.keys.data.len()
     return 2 * ((len * (size_t)kv->bits + 7) / 8);           // lib.rs:284-285 for keys + values
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// Phase-aware KV cache entry, resident in HBM
+// ==========================================================================================
+// KVCacheEntry (diffuse-llm-rs/src/lib.rs:122-313): the f32 keys / values plus up to two quantized copies — one at the
+// prefill precision, one at the decode precision — and the phase that says which copy get_keys / get_values decode.
+// Everything lives on the device: `update` takes device tensors, the getters decode straight into the consumer's buffer,
+// so the cached branch of the sampling loop (lib.rs:885-921) moves nothing over PCIe.
+// Layout: f32 rows of layer l at [l * capacity, l * capacity + seq) (so tokens can be appended without moving the others);
+// the quantized copies are dllm_kv entries (per tensor: contiguous; per token / fixed scale: the same capacity layout).
+struct dllm_kvcache {
+    size_t L = 0, H = 0, cap = 0, S = 0;
+    int scheme = DLLM_KV_TENSOR_B;
+    int bits[2] = {8, 4};              // prefill, decode
+    bool is_prefill = true;            // lib.rs:166 "Start in prefill phase by default"
+    float *d_f32[2] = {nullptr, nullptr};
+    dllm_kv *q[2] = {nullptr, nullptr};
+    int device = 0;
+};
+
+// the quantized copy `which` (0 prefill, 1 decode) rebuilt from dense device tensors [L, S, H]
+static int32_t kvc_requantize(dllm_ctx *ctx, dllm_kvcache *kc, int which, const float *k_dense, const float *v_dense) {
+    if (kc->bits[which] <= 0) return DLLM_OK;
+    if (!kc->q[which]) {
+        // room for the whole capacity; a per-tensor entry is kept contiguous at its current length (cap == S)
+        DLLM_TRY(kv_alloc(ctx, kc->L, kc->cap, kc->cap, kc->H, (uint8_t)kc->bits[which], kc->scheme, &kc->q[which]));
+        kc->q[which]->S = 0;
+    }
+    dllm_kv *kv = kc->q[which];
+    kv->S = kc->S;
+    if (kc->scheme == DLLM_KV_TENSOR_B) kv->cap = kc->S;
+    if (kc->L * kc->S * kc->H == 0) return DLLM_OK;
+    DLLM_TRY(kv_quantize_one(ctx, kv, 0, k_dense));
+    return kv_quantize_one(ctx, kv, 1, v_dense);
+}
+
+// dense [L, S, H] <-> the capacity layout
+static int32_t kvc_copy_rows(dllm_ctx *ctx, float *dst, size_t dst_layer_rows, const float *src, size_t src_layer_rows,
+                             size_t rows, size_t L, size_t H) {
+    if (rows * L * H == 0) return DLLM_OK;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, dst_layer_rows * H * sizeof(float), src, src_layer_rows * H * sizeof(float),
+                                    rows * H * sizeof(float), L, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DLLM_OK;
+}
+
+// rebuild copy `which` from the cache's own f32 tensors (transition_phase, lib.rs:228-235)
+static int32_t kvc_requantize_from_store(dllm_ctx *ctx, dllm_kvcache *kc, int which) {
+    if (kc->bits[which] <= 0) return DLLM_OK;
+    if (kc->scheme == DLLM_KV_TENSOR_B && kc->cap != kc->S && kc->S > 0) {
+        // one scale per tensor needs the tensor dense: gather the rows first
+        const size_t n = kc->L * kc->S * kc->H;
+        DLLM_TRY(ensure_buf(ctx, ctx->ws[4], n * sizeof(float)));
+        DLLM_TRY(ensure_buf(ctx, ctx->ws[5], n * sizeof(float)));
+        DLLM_TRY(kvc_copy_rows(ctx, (float *)ctx->ws[4].p, kc->S, kc->d_f32[0], kc->cap, kc->S, kc->L, kc->H));
+        DLLM_TRY(kvc_copy_rows(ctx, (float *)ctx->ws[5].p, kc->S, kc->d_f32[1], kc->cap, kc->S, kc->L, kc->H));
+        return kvc_requantize(ctx, kc, which, (const float *)ctx->ws[4].p, (const float *)ctx->ws[5].p);
+    }
+    if (kc->scheme == DLLM_KV_TENSOR_B) return kvc_requantize(ctx, kc, which, kc->d_f32[0], kc->d_f32[1]);
+    if (!kc->q[which]) {
+        DLLM_TRY(kv_alloc(ctx, kc->L, 0, kc->cap, kc->H, (uint8_t)kc->bits[which], kc->scheme, &kc->q[which]));
+    }
+    dllm_kv *kv = kc->q[which];
+    kv->S = kc->S;
+    if (kc->L * kc->S * kc->H == 0) return DLLM_OK;
+    DLLM_TRY(kv_quantize_rows(ctx, kv, 0, kc->d_f32[0], 0, kc->S, kc->cap));
+    return kv_quantize_rows(ctx, kv, 1, kc->d_f32[1], 0, kc->S, kc->cap);
+}
+
+extern "C" {
+
+void dllm_kvcache_destroy(dllm_kvcache *kc) {
+    if (!kc) return;
+    cudaSetDevice(kc->device);
+    for (int i = 0; i < 2; ++i) {
+        if (kc->d_f32[i]) cudaFree(kc->d_f32[i]);
+        if (kc->q[i]) dllm_kv_destroy(kc->q[i]);
+    }
+    delete kc;
+}
+
+int32_t dllm_kvcache_create(dllm_ctx *ctx, size_t layers, size_t hidden, size_t capacity, uint8_t prefill_bits, uint8_t decode_bits,
+                            int32_t scheme, dllm_kvcache **out) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, out, DLLM_ERR_NULL, "null out pointer");
+    *out = nullptr;
+    ARG_CHECK(ctx, scheme >= DLLM_KV_TENSOR_B && scheme <= DLLM_KV_FIXED_C, DLLM_ERR_INVALID_PARAMS, "unknown scheme %d", scheme);
+    ARG_CHECK(ctx, prefill_bits <= 8 && decode_bits <= 8, DLLM_ERR_INVALID_PARAMS, "Bits must be between 1 and 8 (0 = no quantized copy)");
+    dllm_kvcache *kc = new (std::nothrow) dllm_kvcache();
+    if (!kc) return DLLM_ERR_OOM;
+    kc->L = layers; kc->H = hidden; kc->cap = capacity; kc->scheme = scheme; kc->device = ctx->device;
+    kc->bits[0] = prefill_bits; kc->bits[1] = decode_bits;
+    const size_t bytes = layers * capacity * hidden * sizeof(float);
+    for (int i = 0; i < 2; ++i)
+        if (cudaMalloc(&kc->d_f32[i], bytes ? bytes : 16) != cudaSuccess) {
+            cudaGetLastError();
+            dllm_kvcache_destroy(kc);
+            DLLM_FAIL(ctx, DLLM_ERR_OOM, "cudaMalloc failed for the KV cache (%zu bytes per tensor)", bytes);
+        }
+    *out = kc;
+    return DLLM_OK;
+}
+
+// KVCacheEntry::update (lib.rs:246-276): the tensors are replaced and BOTH quantized copies are rebuilt from them
+int32_t dllm_kvcache_update_dev(dllm_ctx *ctx, dllm_kvcache *kc, const float *keys_dev, const float *values_dev, size_t seq) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kc, DLLM_ERR_NULL, "null cache entry");
+    ARG_CHECK(ctx, seq <= kc->cap, DLLM_ERR_INDEX, "%zu tokens > capacity %zu", seq, kc->cap);
+    if (!keys_dev && !values_dev && seq == kc->S) {
+        // the model handed the cache's own tensors back (SimpleDiffusionModel::update_kv_cache, lib.rs:826-835): the copies are
+        // rebuilt from them — which is what re-creates a decode copy dropped by a precision change
+        for (int which = 0; which < 2; ++which) DLLM_TRY(kvc_requantize_from_store(ctx, kc, which));
+        return DLLM_OK;
+    }
+    ARG_CHECK(ctx, kc->L * seq * kc->H == 0 || (keys_dev && values_dev), DLLM_ERR_NULL, "null device pointer");
+    kc->S = seq;
+    DLLM_TRY(kvc_copy_rows(ctx, kc->d_f32[0], kc->cap, keys_dev, seq, seq, kc->L, kc->H));
+    DLLM_TRY(kvc_copy_rows(ctx, kc->d_f32[1], kc->cap, values_dev, seq, seq, kc->L, kc->H));
+    for (int which = 0; which < 2; ++which) {
+        if (kc->bits[which] <= 0) continue;
+        if (kc->scheme == DLLM_KV_TENSOR_B) {
+            DLLM_TRY(kvc_requantize(ctx, kc, which, keys_dev, values_dev));
+        } else {
+            if (!kc->q[which]) DLLM_TRY(kv_alloc(ctx, kc->L, 0, kc->cap, kc->H, (uint8_t)kc->bits[which], kc->scheme, &kc->q[which]));
+            kc->q[which]->S = seq;
+            if (kc->L * seq * kc->H) {
+                DLLM_TRY(kv_quantize_rows(ctx, kc->q[which], 0, keys_dev, 0, seq));
+                DLLM_TRY(kv_quantize_rows(ctx, kc->q[which], 1, values_dev, 0, seq));
+            }
+        }
+    }
+    return DLLM_OK;
+}
+
+// The same update when only t_new tokens per layer are new (per-token / fixed-scale entries: a token's codes depend on that
+// token alone, so the result is bit-identical to dllm_kvcache_update_dev with the concatenated tensors; a per-tensor entry
+// re-quantizes everything, like the reference does, because its one scale changes)
+int32_t dllm_kvcache_append_dev(dllm_ctx *ctx, dllm_kvcache *kc, const float *keys_new_dev, const float *values_new_dev, size_t t_new) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kc, DLLM_ERR_NULL, "null cache entry");
+    ARG_CHECK(ctx, kc->S + t_new <= kc->cap, DLLM_ERR_INDEX, "KV cache is full: %zu + %zu tokens > capacity %zu", kc->S, t_new, kc->cap);
+    if (t_new == 0) return DLLM_OK;
+    ARG_CHECK(ctx, kc->L * kc->H == 0 || (keys_new_dev && values_new_dev), DLLM_ERR_NULL, "null device pointer");
+    const size_t s0 = kc->S;
+    DLLM_TRY(kvc_copy_rows(ctx, kc->d_f32[0] + s0 * kc->H, kc->cap, keys_new_dev, t_new, t_new, kc->L, kc->H));
+    DLLM_TRY(kvc_copy_rows(ctx, kc->d_f32[1] + s0 * kc->H, kc->cap, values_new_dev, t_new, t_new, kc->L, kc->H));
+    kc->S = s0 + t_new;
+    for (int which = 0; which < 2; ++which) {
+        if (kc->bits[which] <= 0) continue;
+        if (kc->scheme == DLLM_KV_TENSOR_B || !kc->q[which]) {
+            DLLM_TRY(kvc_requantize_from_store(ctx, kc, which));
+        } else {
+            dllm_kv *kv = kc->q[which];
+            DLLM_TRY(kv_quantize_rows(ctx, kv, 0, keys_new_dev, s0, t_new));
+            DLLM_TRY(kv_quantize_rows(ctx, kv, 1, values_new_dev, s0, t_new));
+            kv->S = kc->S;
+        }
+    }
+    return DLLM_OK;
+}
+
+// transition_phase (lib.rs:220-238): entering the decode phase creates the decode copy if it is missing
+int32_t dllm_kvcache_set_phase(dllm_ctx *ctx, dllm_kvcache *kc, int32_t is_prefill) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kc, DLLM_ERR_NULL, "null cache entry");
+    const bool p = is_prefill != 0;
+    if (kc->is_prefill == p) return DLLM_OK;
+    kc->is_prefill = p;
+    if (!p && kc->bits[1] > 0 && !kc->q[1]) DLLM_TRY(kvc_requantize_from_store(ctx, kc, 1));
+    return DLLM_OK;
+}
+
+// progressive precision (lib.rs:899-903): a new decode width drops the decode copy; the next update re-creates it
+int32_t dllm_kvcache_set_decode_bits(dllm_ctx *ctx, dllm_kvcache *kc, uint8_t bits) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kc, DLLM_ERR_NULL, "null cache entry");
+    ARG_CHECK(ctx, bits <= 8, DLLM_ERR_INVALID_PARAMS, "Bits must be between 1 and 8 (0 = no quantized copy)");
+    if ((int)bits == kc->bits[1]) return DLLM_OK;
+    kc->bits[1] = bits;
+    if (kc->q[1]) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // its buffers may still be read by enqueued work
+        dllm_kv_destroy(kc->q[1]);
+        kc->q[1] = nullptr;
+    }
+    return DLLM_OK;
+}
+
+// get_keys / get_values (lib.rs:176-205): the active phase's copy decoded into the consumer's dense [L, S, H] buffers
+// (either may be NULL); without a quantized copy, the f32 tensors themselves
+int32_t dllm_kvcache_get_dev(dllm_ctx *ctx, const dllm_kvcache *kc, float *keys_out_dev, float *values_out_dev) {
+    CTX_CHECK(ctx);
+    ARG_CHECK(ctx, kc, DLLM_ERR_NULL, "null cache entry");
+    if (kc->L * kc->S * kc->H == 0) return DLLM_OK;
+    const dllm_kv *q = kc->is_prefill ? kc->q[0] : kc->q[1];
+    if (q) return dllm_kv_dequantize_dev(ctx, q, keys_out_dev, values_out_dev);
+    if (keys_out_dev) DLLM_TRY(kvc_copy_rows(ctx, keys_out_dev, kc->S, kc->d_f32[0], kc->cap, kc->S, kc->L, kc->H));
+    if (values_out_dev) DLLM_TRY(kvc_copy_rows(ctx, values_out_dev, kc->S, kc->d_f32[1], kc->cap, kc->S, kc->L, kc->H));
+    return DLLM_OK;
+}
+
+int32_t dllm_kvcache_info(const dllm_kvcache *kc, size_t *seq_len, int32_t *is_prefill, uint8_t *current_bits, size_t *memory_usage) {
+    if (!kc) return DLLM_ERR_NULL;
+    if (seq_len) *seq_len = kc->S;
+    if (is_prefill) *is_prefill = kc->is_prefill ? 1 : 0;
+    if (current_bits) *current_bits = (uint8_t)(kc->is_prefill ? kc->bits[0] : kc->bits[1]);      // lib.rs:211-217
+    if (memory_usage) {
+        size_t total = 0;                                                                       // lib.rs:279-302
+        for (int i = 0; i < 2; ++i) if (kc->q[i]) total += dllm_kv_memory_usage(kc->q[i]);
+        *memory_usage = total ? total : 2 * kc->L * kc->S * kc->H * sizeof(float);
+    }
+    return DLLM_OK;
+}
+
+// the quantized copy of one phase (NULL if absent) for dllm_kv_export / parity checks; owned by the cache entry
+const dllm_kv *dllm_kvcache_copy(const dllm_kvcache *kc, int32_t prefill) {
+    return kc ? kc->q[prefill ? 0 : 1] : nullptr;
 }
 
 }  // extern "C"

@@ -106,38 +106,54 @@ __device__ __forceinline__ void p2p_accumulate(float *acc, uint4 v) {
     }
 }
 
-template <bool BF16>
+// W = slots of the rank loop (>= world), U = vectors per thread and pass: U x W 16-byte loads are in flight per thread before
+// the first add — what a handful of SMs needs to keep NVLink busy while the rest of the GPU runs a GEMM
+template <bool BF16, int W, int U>
 __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
     p2p_barrier(a, 0, a.epoch);
     const size_t per = (a.n16 + a.world - 1) / a.world;
     const size_t i0 = per * a.rank < a.n16 ? per * a.rank : a.n16, i1 = i0 + per < a.n16 ? i0 + per : a.n16;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride) {
-        float acc[8];
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += U * T) {
+        uint4 v[U][W];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        uint4 v[kP2PMaxWorld];
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int r = 0; r < kP2PMaxWorld; ++r)
-            if (r < a.world) v[r] = ld_relaxed_sys_v4(a.base[r] + a.off + i * 16);      // all loads in flight before the first add
+            for (int r = 0; r < W; ++r)
+                if (r < a.world && i + u * T < i1) v[u][r] = ld_relaxed_sys_v4(a.base[r] + a.off + (i + u * T) * 16);
 #pragma unroll
-        for (int r = 0; r < kP2PMaxWorld; ++r)
-            if (r < a.world) p2p_accumulate<BF16>(acc, v[r]);                            // rank order: the same sum on every rank
-        uint4 o;
-        if (BF16) {
-            __nv_bfloat162 h[4];
+        for (int u = 0; u < U; ++u) {
+            if (i + u * T >= i1) break;
+            float acc[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
-            o = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
-                           *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
-        } else {
-            o = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < a.world) p2p_accumulate<BF16>(acc, v[u][r]);                     // rank order: the same sum on every rank
+            uint4 o;
+            if (BF16) {
+                __nv_bfloat162 h[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+                o = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
+                               *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
+            } else {
+                o = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+            }
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < a.world) st_relaxed_sys_v4(a.base[r] + a.off + (i + u * T) * 16, o);
         }
-#pragma unroll
-        for (int r = 0; r < kP2PMaxWorld; ++r)
-            if (r < a.world) st_relaxed_sys_v4(a.base[r] + a.off + i * 16, o);
     }
     p2p_barrier(a, 1, a.epoch + 1);
+}
+
+template <bool BF16>
+void p2p_launch(const P2PArgs &a, int blocks, cudaStream_t stream) {
+    if (a.world <= 2) p2p_allreduce_kernel<BF16, 2, 4><<<blocks, 512, 0, stream>>>(a);
+    else if (a.world <= 4) p2p_allreduce_kernel<BF16, 4, 2><<<blocks, 512, 0, stream>>>(a);
+    else if (a.world <= 8) p2p_allreduce_kernel<BF16, 8, 1><<<blocks, 512, 0, stream>>>(a);
+    else p2p_allreduce_kernel<BF16, kP2PMaxWorld, 1><<<blocks, 512, 0, stream>>>(a);
 }
 }  // namespace
 
@@ -159,11 +175,13 @@ static int32_t p2p_allreduce(dllm_ctx *ctx, void *buf, size_t bytes, bool bf16, 
     a.rank = ctx->tp_rank; a.world = ctx->tp_world;
     a.err = ctx->p2p_err;
     // alone on the GPU: one block per SM up to 128; under a dense kernel: two blocks per SM that kernel leaves free
-    const int reserve = ctx->sm_reserve >= 0 ? ctx->sm_reserve : 8;
+    const int reserve = ctx->sm_limit > 0 ? ctx->sm_count - ctx->sm_limit : 0;       // what the overlapped forward leaves free right now
     int blocks = overlapped ? 2 * (reserve > 0 ? reserve : 4) : (ctx->sm_count < 128 ? ctx->sm_count : 128);
     if (blocks > kP2PMaxBlocks) blocks = kP2PMaxBlocks;
-    if (bf16) p2p_allreduce_kernel<true><<<blocks, 512, 0, stream>>>(a);
-    else p2p_allreduce_kernel<false><<<blocks, 512, 0, stream>>>(a);
+    static const int blocks_env = getenv("DLLM_P2P_BLOCKS") ? atoi(getenv("DLLM_P2P_BLOCKS")) : 0;      // experiments only
+    if (blocks_env > 0 && blocks_env <= kP2PMaxBlocks) blocks = blocks_env;
+    if (bf16) p2p_launch<true>(a, blocks, stream);
+    else p2p_launch<false>(a, blocks, stream);
     LAUNCH_CHECK(ctx);
     ctx->p2p_calls++;
     return DLLM_OK;
@@ -291,6 +309,7 @@ int32_t dllm_tp_p2p_enable(dllm_ctx *ctx, size_t arena_bytes) {
     if (ctx->tp_world > kP2PMaxWorld) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "peer-to-peer all-reduce supports up to %d ranks", kP2PMaxWorld);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     p2p_release(ctx);
+    if (arena_bytes == 0) return DLLM_OK;                         // switched off: back to ncclAllReduce
     arena_bytes = (arena_bytes + 4095) & ~(size_t)4095;
     const int W = ctx->tp_world;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
@@ -355,8 +374,9 @@ int32_t dllm_tp_p2p_enable(dllm_ctx *ctx, size_t arena_bytes) {
     return DLLM_OK;
 }
 
-int32_t dllm_tp_p2p_status(dllm_ctx *ctx, size_t *arena_bytes, uint64_t *allreduces, uint32_t *timed_out) {
+int32_t dllm_tp_p2p_status(dllm_ctx *ctx, void **arena_dev, size_t *arena_bytes, uint64_t *allreduces, uint32_t *timed_out) {
     if (!ctx) return DLLM_ERR_NULL;
+    if (arena_dev) *arena_dev = ctx->p2p_arena;
     if (arena_bytes) *arena_bytes = ctx->p2p_arena ? ctx->p2p_bytes : 0;
     if (allreduces) *allreduces = ctx->p2p_calls;
     if (timed_out) {

@@ -84,6 +84,7 @@ SIGNATURES = {
     "dllm_launch_count": (C.c_uint64, [c_vp]),
     "dllm_sm_count": (C.c_int32, [c_vp]),
     "dllm_graph_replay_count": (C.c_uint64, [c_vp]),
+    "dllm_copy_bytes": (C.c_int32, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dllm_selftest_division": (C.c_int32, [c_vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "dllm_profile_begin": (C.c_int32, [c_vp]),
     "dllm_profile_end": (C.c_int32, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -153,6 +154,8 @@ SIGNATURES = {
     "dllm_noise_fill": (C.c_int32, [c_vp, C.c_uint64, C.c_uint64, C.c_uint64, c_sz, c_vp]),
     "dllm_noise_fill_dev": (C.c_int32, [c_vp, C.c_uint64, C.c_uint64, C.c_uint64, c_sz, c_vp]),
     "dllm_denoise_step_seeded_dev": (C.c_int32, [c_vp, c_vp, c_vp, C.c_uint64, c_sz, c_sz, c_sz, C.c_int32, C.c_int32]),
+    "dllm_p_sample_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_sz, c_sz, C.c_int32, c_vp]),
+    "dllm_p_sample_seeded_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, C.c_uint64, c_sz, c_sz, c_sz, C.c_int32, c_vp]),
     "dllm_sample_seeded": (C.c_int32, [c_vp, c_vp, c_vp, C.c_uint64, c_sz, c_sz, c_sz, C.c_int32, C.c_int32, C.c_int32, c_vp]),
     "dllm_sample_seeded_dev": (C.c_int32, [c_vp, c_vp, c_vp, C.c_uint64, c_sz, c_sz, c_sz, C.c_int32, C.c_int32, C.c_int32]),
     "dllm_progressive_bits": (C.c_uint8, [c_sz, c_sz, C.c_uint8, C.c_uint8, C.POINTER(C.c_int32)]),
@@ -171,12 +174,21 @@ SIGNATURES = {
     "dllm_kv_export": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dllm_kv_memory_usage": (c_sz, [c_vp]),
     "dllm_kv_destroy": (None, [c_vp]),
+    "dllm_kvcache_create": (C.c_int32, [c_vp, c_sz, c_sz, c_sz, C.c_uint8, C.c_uint8, C.c_int32, C.POINTER(c_vp)]),
+    "dllm_kvcache_update_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz]),
+    "dllm_kvcache_append_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp, c_sz]),
+    "dllm_kvcache_set_phase": (C.c_int32, [c_vp, c_vp, C.c_int32]),
+    "dllm_kvcache_set_decode_bits": (C.c_int32, [c_vp, c_vp, C.c_uint8]),
+    "dllm_kvcache_get_dev": (C.c_int32, [c_vp, c_vp, c_vp, c_vp]),
+    "dllm_kvcache_info": (C.c_int32, [c_vp, C.POINTER(c_sz), C.POINTER(C.c_int32), c_u8p, C.POINTER(c_sz)]),
+    "dllm_kvcache_copy": (c_vp, [c_vp, C.c_int32]),
+    "dllm_kvcache_destroy": (None, [c_vp]),
     "dllm_tp_unique_id": (C.c_int32, [c_vp]),
     "dllm_tp_init": (C.c_int32, [c_vp, c_vp, C.c_int32, C.c_int32]),
     "dllm_tp_finalize": (C.c_int32, [c_vp]),
     "dllm_tp_configure": (C.c_int32, [c_vp, C.c_int32, C.c_int32, C.c_int32]),
     "dllm_tp_p2p_enable": (C.c_int32, [c_vp, c_sz]),
-    "dllm_tp_p2p_status": (C.c_int32, [c_vp, C.POINTER(c_sz), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "dllm_tp_p2p_status": (C.c_int32, [c_vp, C.POINTER(c_vp), C.POINTER(c_sz), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "dllm_tp_allreduce_dev": (C.c_int32, [c_vp, c_vp, c_sz]),
     "dllm_tp_allgather_cols_dev": (C.c_int32, [c_vp, c_vp, c_sz, c_sz, c_vp]),
     "dllm_model_set_parallel": (C.c_int32, [c_vp, c_vp, c_vp, c_sz]),

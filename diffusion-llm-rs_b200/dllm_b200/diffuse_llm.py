@@ -123,6 +123,134 @@ class KVCacheEntry:
         return self.seq_len == 0
 
 
+class DeviceKVCacheEntry:
+    """KVCacheEntry (lib.rs:122-313) resident in HBM (`dllm_kvcache_*`): the f32 keys / values plus the prefill- and the
+    decode-precision quantized copies all live on the device.  `update_dev` / `append_dev` take device pointers, `get_dev`
+    decodes the active phase's copy straight into the consumer's device buffers — the cached branch of the sampling loop
+    (`DiffuseLLM.sample_cached_dev`) copies nothing over PCIe.  `scheme`: L.KV_TENSOR_B is the reference's per-tensor
+    quantizer (quantization.rs:140-157: every update re-quantizes everything); L.KV_ROW_D / L.KV_FIXED_C entries can grow
+    token by token (`append_dev` quantizes only the new tokens)."""
+
+    def __init__(self, ctx: Context, layers: int, hidden: int, capacity: int, prefill_bits: int, decode_bits: int,
+                 scheme: int = L.KV_TENSOR_B):
+        self._ctx = ctx
+        self.layers, self.hidden, self.capacity, self.scheme = layers, hidden, capacity, scheme
+        h = C.c_void_p()
+        ctx._ck(ctx._lib.dllm_kvcache_create(ctx.h, layers, hidden, capacity, prefill_bits, decode_bits, scheme, C.byref(h)))
+        self.h = h
+
+    # -- device-pointer interface --
+    def update_dev(self, keys_dev: int, values_dev: int, seq: int):
+        """:246-276.  Dense [layers, seq, hidden] f32 device tensors."""
+        self._ctx._ck(self._ctx._lib.dllm_kvcache_update_dev(self._ctx.h, self.h, keys_dev, values_dev, seq))
+
+    def refresh_dev(self):
+        """update() with the entry's own tensors (what SimpleDiffusionModel::update_kv_cache hands back, :826-835)."""
+        self._ctx._ck(self._ctx._lib.dllm_kvcache_update_dev(self._ctx.h, self.h, None, None, self.len()))
+
+    def append_dev(self, keys_new_dev: int, values_new_dev: int, t_new: int):
+        self._ctx._ck(self._ctx._lib.dllm_kvcache_append_dev(self._ctx.h, self.h, keys_new_dev, values_new_dev, t_new))
+
+    def get_dev(self, keys_out_dev: Optional[int], values_out_dev: Optional[int]):
+        """get_keys / get_values (:176-205) into dense [layers, seq, hidden] device buffers."""
+        self._ctx._ck(self._ctx._lib.dllm_kvcache_get_dev(self._ctx.h, self.h, keys_out_dev, values_out_dev))
+
+    def set_phase(self, is_prefill: bool):
+        self._ctx._ck(self._ctx._lib.dllm_kvcache_set_phase(self._ctx.h, self.h, int(is_prefill)))
+
+    transition_phase = set_phase
+
+    def set_decode_bits(self, bits: int):
+        """:899-903 — `decode_quant_bits = bits; decode_quantized = None`"""
+        self._ctx._ck(self._ctx._lib.dllm_kvcache_set_decode_bits(self._ctx.h, self.h, bits))
+
+    def _info(self):
+        s, p, b, m = C.c_size_t(), C.c_int32(), C.c_uint8(), C.c_size_t()
+        L.check(self._ctx._lib.dllm_kvcache_info(self.h, C.byref(s), C.byref(p), C.byref(b), C.byref(m)))
+        return s.value, bool(p.value), b.value, m.value
+
+    def len(self) -> int:
+        return self._info()[0]
+
+    def is_empty(self) -> bool:
+        return self.len() == 0
+
+    @property
+    def is_prefill_phase(self) -> bool:
+        return self._info()[1]
+
+    def get_current_quant_bits(self) -> int:
+        return self._info()[2]
+
+    def memory_usage(self) -> int:
+        return self._info()[3]
+
+    # -- host conveniences (tests, interop with the numpy KVCacheEntry) --
+    def _host(self, which: int):
+        shape = (self.layers, self.len(), self.hidden)
+        n = shape[0] * shape[1] * shape[2]
+        if n == 0:
+            return np.empty(shape, np.float32)
+        with self._ctx.lock:
+            d = self._ctx.malloc(n * 4)
+            try:
+                self.get_dev(d if which == 0 else None, d if which == 1 else None)
+                out = self._ctx.d2h(d, shape, np.float32)
+                self._ctx.sync()
+            finally:
+                self._ctx.free(d)
+        return out
+
+    def get_keys(self):
+        return self._host(0)
+
+    def get_values(self):
+        return self._host(1)
+
+    def update(self, new_keys, new_values):
+        k = np.ascontiguousarray(new_keys, np.float32)
+        v = np.ascontiguousarray(new_values, np.float32)
+        n = k.size
+        with self._ctx.lock:
+            dk, dv = self._ctx.malloc(max(n, 1) * 4), self._ctx.malloc(max(n, 1) * 4)
+            try:
+                self._ctx.h2d(dk, k)
+                self._ctx.h2d(dv, v)
+                self.update_dev(dk, dv, k.shape[1])
+                self._ctx.sync()
+            finally:
+                self._ctx.free(dk)
+                self._ctx.free(dv)
+
+    def export_copy(self, prefill: bool):
+        """(key_codes, value_codes, key_scale, key_zp, value_scale, value_zp) of one quantized copy, one code per u8 — the
+        reference's QuantizedTensor view — or None if that copy does not exist."""
+        kv = self._ctx._lib.dllm_kvcache_copy(self.h, int(prefill))
+        if not kv:
+            return None
+        rows = self.layers * self.len()
+        n = rows * self.hidden
+        kc, vc = np.empty(n, np.uint8), np.empty(n, np.uint8)
+        m = rows if self.scheme == L.KV_ROW_D else 1
+        ks, kz, vs, vz = (np.empty(m, np.float32) for _ in range(4))
+        with self._ctx.lock:
+            self._ctx._ck(self._ctx._lib.dllm_kv_export(self._ctx.h, kv, kc.ctypes.data, vc.ctypes.data, ks.ctypes.data,
+                                                        kz.ctypes.data, vs.ctypes.data, vz.ctypes.data))
+        return kc, vc, ks, kz, vs, vz
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._ctx.sync()
+            self._ctx._lib.dllm_kvcache_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DiffusionModel:
     """trait DiffusionModel: Send + Sync (lib.rs:748-772)"""
 
@@ -181,6 +309,17 @@ class QuantizedDiffusionModel(DiffusionModel):
     def update_kv_cache(self, x, t, cache: KVCacheEntry):
         return cache.keys.copy(), cache.values.copy()   # lib.rs:826-835
 
+    # -- the cached branch on device tensors (DiffuseLLM.sample_cached_dev) --
+    def update_kv_cache_dev(self, x_dev: int, t: int, batch: int, feat: int, cache: "DeviceKVCacheEntry"):
+        """lib.rs:826-835: the reference layer hands the cache's own tensors back -> ("same",).  A model that produces keys /
+        values returns ("update", keys_dev, values_dev, seq) (dense [layers, seq, hidden]) or ("append", k_new_dev,
+        v_new_dev, t_new)."""
+        return ("same",)
+
+    def forward_with_cache_dev(self, x_dev: int, t: int, batch: int, feat: int, keys_dev: int, values_dev: int, seq: int,
+                               out_dev: int):
+        self.forward_dev(x_dev, batch, feat, out_dev)     # lib.rs:815-824: the cache is ignored
+
     def denoise_step_dev(self, x_dev: int, z_dev: Optional[int], t: int, batch: int, feat: int, guard_t0=True):
         self._ctx._ck(self._ctx._lib.dllm_denoise_step_dev(self._ctx.h, self.h, x_dev, z_dev, t, batch, feat,
                                                            int(guard_t0), self.path))
@@ -220,6 +359,7 @@ class DiffuseLLM:
         self.config = config or DiffusionConfig()
         self._ctx = ctx or default_context()
         self.kv_cache = {}
+        self.cache_memory_usage = 0          # AtomicUsize of lib.rs:847
 
     # -- p_sample: lib.rs:1152-1215, noise injected --
     def p_sample(self, model: QuantizedDiffusionModel, x_t, t, noise_pred, noise=None, guard_t0=True):
@@ -265,6 +405,124 @@ class DiffuseLLM:
             self._ctx._ck(self._ctx._lib.dllm_sample_seeded(self._ctx.h, model.h, x.ctypes.data if x is not None else None,
                                                             seed, batch, feat, num_steps, int(guard_t0), model.path,
                                                             int(use_graph), out.ctypes.data))
+        return out
+
+    # -- cache management: lib.rs:977-1084 (host-side policy over the entries; the entries' tensors stay where they are) --
+    def get_or_init_cache(self, cache_id: str, batch_size: int = 1):
+        """:977-986"""
+        if cache_id not in self.kv_cache:
+            self.kv_cache[cache_id] = self.init_kv_cache(batch_size)
+        return self.kv_cache[cache_id]
+
+    def update_kv_cache(self, cache_id: str, keys, values):
+        """:988-1043.  Accounting exactly as written there: the incoming entry is charged keys.len()*4*2 bytes against
+        max_cache_size BEFORE it is quantized, eviction frees at least the overshoot, an existing entry is updated in place
+        (usage grows by max(0, f32 size - its previous quantized size)), a new entry is charged its quantized size.
+        (The reference's `KVCacheEntry::new(keys, values, kv_quant_bits)` at :1030 lacks an argument and does not compile;
+        the evident intent — the same width for both phases — is what runs here.)"""
+        if not self.config.use_kv_cache:
+            return
+        keys = np.ascontiguousarray(keys, np.float32)
+        values = np.ascontiguousarray(values, np.float32)
+        entry_size = keys.size * 4 * 2
+        new_usage = self.cache_memory_usage + entry_size
+        if new_usage > self.config.max_cache_size:
+            self.evict_oldest_entries(new_usage - self.config.max_cache_size)
+        entry = self.kv_cache.get(cache_id)
+        if entry is not None:
+            old_size = entry.memory_usage()
+            entry.update(keys, values)
+            self.cache_memory_usage += max(0, entry_size - old_size)              # saturating_sub, :1021-1024
+        else:
+            entry = self._new_entry(keys, values, self.config.kv_quant_bits, self.config.kv_quant_bits)
+            self.kv_cache[cache_id] = entry
+            self.cache_memory_usage += entry.memory_usage()
+
+    def _new_entry(self, keys, values, prefill_bits, decode_bits):
+        return KVCacheEntry(keys, values, prefill_bits, decode_bits, self._ctx)
+
+    def evict_oldest_entries(self, bytes_to_free: int):
+        """:1046-1073 — despite its name the reference evicts the LARGEST entries first (sort by memory usage, descending)
+        until at least bytes_to_free are released."""
+        entries = sorted(((k, e.memory_usage()) for k, e in self.kv_cache.items()), key=lambda kv: -kv[1])
+        freed = 0
+        for key, size in entries:
+            if freed >= bytes_to_free:
+                break
+            e = self.kv_cache.pop(key, None)
+            if e is not None:
+                freed += size
+                if hasattr(e, "close"):
+                    e.close()
+        self.cache_memory_usage = max(0, self.cache_memory_usage - freed)
+        return freed
+
+    def clear_kv_cache(self):
+        """:1076-1079"""
+        for e in self.kv_cache.values():
+            if hasattr(e, "close"):
+                e.close()
+        self.kv_cache.clear()
+        self.cache_memory_usage = 0
+
+    def kv_cache_memory_usage(self) -> int:
+        """:1082-1084"""
+        return self.cache_memory_usage
+
+    def init_kv_cache_dev(self, capacity: int, scheme: int = L.KV_TENSOR_B) -> DeviceKVCacheEntry:
+        """lib.rs:958-975 with the entry resident in HBM: empty [layers, 0, hidden], room for `capacity` tokens per layer"""
+        q = self.config.quant_config
+        pre, dec = (q.prefill_bits, q.decode_bits) if self.config.use_phase_aware_quant else (self.config.kv_quant_bits,) * 2
+        return DeviceKVCacheEntry(self._ctx, self.config.num_layers, self.config.hidden_size, capacity, pre, dec, scheme)
+
+    def sample_cached_dev(self, model: QuantizedDiffusionModel, shape, num_steps: Optional[int] = None, cache_id: str = "default",
+                          seed: int = 42, x0=None, guard_t0: bool = True, capacity: int = 0, scheme: int = L.KV_TENSOR_B):
+        """The cached branch of DiffuseLLM::sample (lib.rs:862-921, :929-936) with x, the cache entry, the keys / values the
+        model reads and the noise all on the device: per step the host only does the phase / precision arithmetic
+        (:886-903) and enqueues kernels — no byte crosses PCIe between the upload of x0 (or nothing, if x0 is drawn from the
+        seeded generator) and the download of the sample.  Noise: the counter-based generator of `sample_seeded`."""
+        batch, seq_len = shape
+        num_steps = num_steps if num_steps is not None else self.config.num_timesteps
+        feat = self.config.hidden_size * seq_len
+        ctx, lib = self._ctx, self._ctx._lib
+        qc = self.config.quant_config
+        n = batch * feat
+        with ctx.lock:
+            cache = self.kv_cache.get(cache_id)
+            if not isinstance(cache, DeviceKVCacheEntry):
+                cache = self.init_kv_cache_dev(max(capacity, 1), scheme)
+            cache.set_phase(True)                                                              # :866-868
+            cap_elems = max(cache.layers * cache.capacity * cache.hidden, 1)
+            x_dev, pred_dev = ctx.malloc(n * 4), ctx.malloc(n * 4)
+            k_dev, v_dev = ctx.malloc(cap_elems * 4), ctx.malloc(cap_elems * 4)
+            try:
+                if x0 is not None:
+                    ctx.h2d(x_dev, np.ascontiguousarray(x0, np.float32))
+                else:
+                    ctx._ck(lib.dllm_noise_fill_dev(ctx.h, seed, num_steps, 0, n, x_dev))      # :875-878
+                for t in range(num_steps - 1, -1, -1):
+                    is_prefill = C.c_int32()
+                    target = lib.dllm_progressive_bits(num_steps, t, qc.decode_bits, qc.min_decode_bits, C.byref(is_prefill))
+                    cache.set_phase(bool(is_prefill.value))                                    # :886-887
+                    if self.config.use_phase_aware_quant and qc.progressive_precision and not is_prefill.value:
+                        cache.set_decode_bits(int(target))                                     # :890-903
+                    upd = model.update_kv_cache_dev(x_dev, t, batch, feat, cache)              # :907
+                    cache.get_dev(k_dev, v_dev)                                                # :913-914
+                    model.forward_with_cache_dev(x_dev, t, batch, feat, k_dev, v_dev, cache.len(), pred_dev)   # :910-915
+                    if upd[0] == "same":                                                       # :918
+                        cache.refresh_dev()
+                    elif upd[0] == "update":
+                        cache.update_dev(upd[1], upd[2], upd[3])
+                    else:
+                        cache.append_dev(upd[1], upd[2], upd[3])
+                    ctx._ck(lib.dllm_p_sample_seeded_dev(ctx.h, model.h, x_dev, pred_dev, seed, t, batch, feat,
+                                                         int(guard_t0), x_dev))                # :921
+                self.kv_cache[cache_id] = cache                                                # :929-936
+                out = ctx.d2h(x_dev, (batch, feat), np.float32)
+            finally:
+                ctx.sync()
+                for d in (x_dev, pred_dev, k_dev, v_dev):
+                    ctx.free(d)
         return out
 
     def init_kv_cache(self, batch_size: int) -> KVCacheEntry:

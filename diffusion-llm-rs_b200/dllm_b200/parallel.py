@@ -128,10 +128,14 @@ class TensorParallelGroup:
             return False
         return self.world > 1
 
+    def disable_p2p(self):
+        """Collective: release the arena; the all-reduces go back to NCCL."""
+        self.ctx._ck(self.ctx._lib.dllm_tp_p2p_enable(self.ctx.h, 0))
+
     def p2p_status(self):
-        b, n, t = C.c_size_t(), C.c_uint64(), C.c_uint32()
-        self.ctx._ck(self.ctx._lib.dllm_tp_p2p_status(self.ctx.h, C.byref(b), C.byref(n), C.byref(t)))
-        return {"arena_bytes": b.value, "allreduces": n.value, "timed_out": t.value}
+        a, b, n, t = C.c_void_p(), C.c_size_t(), C.c_uint64(), C.c_uint32()
+        self.ctx._ck(self.ctx._lib.dllm_tp_p2p_status(self.ctx.h, C.byref(a), C.byref(b), C.byref(n), C.byref(t)))
+        return {"arena": a.value or 0, "arena_bytes": b.value, "allreduces": n.value, "timed_out": t.value}
 
     def allreduce_dev(self, buf_dev: int, n: int):
         self.ctx._ck(self.ctx._lib.dllm_tp_allreduce_dev(self.ctx.h, buf_dev, n))

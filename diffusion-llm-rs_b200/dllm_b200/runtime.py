@@ -89,6 +89,13 @@ class Context:
         return out
 
     @property
+    def copy_bytes(self):
+        """(host->device, device->host) bytes this context has moved so far"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.dllm_copy_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @property
     def graph_replays(self) -> int:
         return int(self._lib.dllm_graph_replay_count(self.h))
 

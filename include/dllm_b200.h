@@ -90,6 +90,9 @@ DLLM_API const char *dllm_last_error(const dllm_ctx *ctx);
 DLLM_API uint64_t dllm_launch_count(const dllm_ctx *ctx);
 /* number of CUDA-graph launches this ctx has made (each replays a whole captured denoise step) */
 DLLM_API uint64_t dllm_graph_replay_count(const dllm_ctx *ctx);
+/* bytes this context has copied host->device / device->host so far (what the host-pointer entry points stage; the *_dev
+ * entry points copy nothing) */
+DLLM_API int32_t dllm_copy_bytes(const dllm_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
 DLLM_API int32_t dllm_sm_count(const dllm_ctx *ctx);
 
 /* per-launch CUDA-event timing of the dominant (tcgen05 linear) kernel on the context's stream.
@@ -304,6 +307,13 @@ DLLM_API int32_t dllm_noise_fill(dllm_ctx *ctx, uint64_t seed, uint64_t stream, 
 DLLM_API int32_t dllm_noise_fill_dev(dllm_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t first, size_t n, float *out_dev);
 DLLM_API int32_t dllm_denoise_step_seeded_dev(dllm_ctx *ctx, dllm_model *m, float *x_dev, uint64_t seed, size_t t,
                                               size_t batch, size_t feat, int32_t guard_t0, int32_t path);
+/* p_sample alone on device tensors (x_prev_dev may alias x_t_dev), with supplied noise or with the seeded generator: for callers
+ * that compute noise_pred themselves, e.g. the cached branch of the sampling loop (lib.rs:910-921) */
+DLLM_API int32_t dllm_p_sample_dev(dllm_ctx *ctx, dllm_model *m, const float *x_t_dev, const float *noise_pred_dev,
+                                   const float *z_dev, size_t t, size_t batch, size_t feat, int32_t guard_t0, float *x_prev_dev);
+DLLM_API int32_t dllm_p_sample_seeded_dev(dllm_ctx *ctx, dllm_model *m, const float *x_t_dev, const float *noise_pred_dev,
+                                          uint64_t seed, size_t t, size_t batch, size_t feat, int32_t guard_t0,
+                                          float *x_prev_dev);
 /* x0 == NULL: the initial x is drawn from stream num_steps */
 DLLM_API int32_t dllm_sample_seeded(dllm_ctx *ctx, dllm_model *m, const float *x0, uint64_t seed, size_t batch, size_t feat,
                                     size_t num_steps, int32_t guard_t0, int32_t path, int32_t use_graph, float *x_out);
@@ -359,6 +369,33 @@ DLLM_API int32_t dllm_kv_export(dllm_ctx *ctx, const dllm_kv *kv, uint8_t *key_c
 DLLM_API size_t dllm_kv_memory_usage(const dllm_kv *kv);
 DLLM_API void dllm_kv_destroy(dllm_kv *kv);
 
+/* Phase-aware cache entry, resident in HBM: KVCacheEntry (lib.rs:122-313) — the f32 keys / values [layers, seq, hidden] plus
+ * a prefill-precision and a decode-precision quantized copy (0 bits = no copy) and the phase that selects which one
+ * get_keys / get_values decode.  All tensors are device pointers, dense [layers, seq, hidden]; nothing crosses PCIe, so the
+ * cached branch of the sampling loop (lib.rs:885-921) runs without host copies.
+ *   update_dev       KVCacheEntry::update (:246-276): replaces the tensors, rebuilds BOTH copies (creating a missing one)
+ *   append_dev       the same update when only t_new tokens per layer are new: ROW_D / FIXED_C entries quantize just those
+ *                    (bit-identical to update_dev with the concatenation); TENSOR_B re-quantizes everything, as the reference does
+ *   set_phase        transition_phase (:220-238): entering decode creates the decode copy from the f32 tensors if it is missing
+ *   set_decode_bits  progressive precision (:899-903): a new width drops the decode copy until the next update / append
+ *   get_dev          get_keys / get_values (:176-205) decoded straight into the consumer's buffers (either may be NULL)
+ *   info             len (:305), phase, get_current_quant_bits (:211-217), memory_usage (:279-302) */
+typedef struct dllm_kvcache dllm_kvcache;
+DLLM_API int32_t dllm_kvcache_create(dllm_ctx *ctx, size_t layers, size_t hidden, size_t capacity, uint8_t prefill_bits,
+                                     uint8_t decode_bits, int32_t scheme, dllm_kvcache **out);
+DLLM_API int32_t dllm_kvcache_update_dev(dllm_ctx *ctx, dllm_kvcache *kc, const float *keys_dev, const float *values_dev,
+                                         size_t seq);
+DLLM_API int32_t dllm_kvcache_append_dev(dllm_ctx *ctx, dllm_kvcache *kc, const float *keys_new_dev,
+                                         const float *values_new_dev, size_t t_new);
+DLLM_API int32_t dllm_kvcache_set_phase(dllm_ctx *ctx, dllm_kvcache *kc, int32_t is_prefill);
+DLLM_API int32_t dllm_kvcache_set_decode_bits(dllm_ctx *ctx, dllm_kvcache *kc, uint8_t bits);
+DLLM_API int32_t dllm_kvcache_get_dev(dllm_ctx *ctx, const dllm_kvcache *kc, float *keys_out_dev, float *values_out_dev);
+DLLM_API int32_t dllm_kvcache_info(const dllm_kvcache *kc, size_t *seq_len, int32_t *is_prefill, uint8_t *current_bits,
+                                   size_t *memory_usage);
+/* the quantized copy of one phase (NULL if absent), for dllm_kv_export / dllm_kv_dequantize; owned by the entry */
+DLLM_API const dllm_kv *dllm_kvcache_copy(const dllm_kvcache *kc, int32_t prefill);
+DLLM_API void dllm_kvcache_destroy(dllm_kvcache *kc);
+
 /* ======================= multi-GPU (one process per GPU) =======================
  * Tensor parallel linears: column-parallel (split N) followed by row-parallel (split K) with
  * one NCCL collective per pair at the layer boundary.  Rank 0 creates the id,
@@ -376,11 +413,14 @@ DLLM_API int32_t dllm_tp_configure(dllm_ctx *ctx, int32_t chunks, int32_t reserv
  * over the communicator of dllm_tp_init, so no extra rendezvous is needed); a tensor-parallel tcgen05 stack whose two activation
  * buffers fit into it (2 x tokens x widest shard x 2 bytes) then reduces its row-parallel partial sums in place with that
  * kernel instead of ncclAllReduce.  Collective: every rank calls it, in the same order relative to other collectives.
+ * arena_bytes == 0 releases the arena (back to ncclAllReduce).
  * DLLM_ERR_UNSUPPORTED (on every rank alike) if some rank cannot map its peers: the NCCL path stays in use.
- * dllm_tp_p2p_status: arena size (0 = off), all-reduces done by the kernel so far, and whether a barrier ever timed out
- * (a peer died: results after that are invalid). */
+ * dllm_tp_p2p_status: this rank's arena (a tensor placed in it is reduced by the kernel when handed to dllm_tp_allreduce_dev),
+ * its size (0 = off), all-reduces done by the kernel so far, and whether a barrier ever timed out (a peer died: results
+ * after that are invalid). */
 DLLM_API int32_t dllm_tp_p2p_enable(dllm_ctx *ctx, size_t arena_bytes);
-DLLM_API int32_t dllm_tp_p2p_status(dllm_ctx *ctx, size_t *arena_bytes, uint64_t *allreduces, uint32_t *timed_out);
+DLLM_API int32_t dllm_tp_p2p_status(dllm_ctx *ctx, void **arena_dev, size_t *arena_bytes, uint64_t *allreduces,
+                                    uint32_t *timed_out);
 /* sum-all-reduce of a device f32 buffer over the TP group (row-parallel partial sums) */
 DLLM_API int32_t dllm_tp_allreduce_dev(dllm_ctx *ctx, float *buf_dev, size_t n);
 /* all-gather of column shards: in [M, N/world] per rank -> out [M, N] */

@@ -33,7 +33,29 @@ ms = tm.run(lambda i: tpg.allreduce_dev(buf.data_ptr(), buf.numel()), 20, 3)
 say(what="nccl_allreduce_64MiB_f32", ms=ms, algbw_GBps=buf.numel() * 4 / ms / 1e6)
 
 ok = tpg.enable_p2p(tokens, max(maxw, H))
-say(what="p2p_enable", ok=ok, status=tpg.p2p_status(), last_error=(lib.dllm_last_error(ctx.h) or b"").decode())
+st = tpg.p2p_status()
+say(what="p2p_enable", ok=ok, status=st, last_error=(lib.dllm_last_error(ctx.h) or b"").decode())
+if ok:
+    # the kernel alone on 64 MiB (f32 elements; the same bytes as one [8192, 4096] bf16 boundary tensor), then correctness
+    n = 16 << 20
+    ms = tm.run(lambda i: tpg.allreduce_dev(st["arena"], n), 20, 3)
+    say(what="p2p_allreduce_64MiB", ms=ms, algbw_GBps=n * 4 / ms / 1e6, link_GBps_per_direction=n * 4 * 2 * (world - 1) / world / ms / 1e6)
+    g = torch.Generator(device="cuda").manual_seed(100 + rank)
+    mine = torch.randn(1 << 20, device="cuda", generator=g)
+    ref = mine.clone(); dist.all_reduce(ref)
+    import numpy as np
+    host = mine.cpu().numpy()
+    ctx._ck(lib.dllm_memcpy_h2d(ctx.h, st["arena"], host.ctypes.data, host.nbytes))
+    ctx.sync()
+    tm.barrier()
+    with torch.cuda.stream(stream):
+        tpg.allreduce_dev(st["arena"], mine.numel()); stream.synchronize()
+    out = np.empty_like(host)
+    ctx._ck(lib.dllm_memcpy_d2h(ctx.h, out.ctypes.data, st["arena"], host.nbytes))
+    ctx.sync()
+    got = torch.from_numpy(out).cuda()
+    tm.barrier()
+    say(what="p2p_vs_nccl_f32", max_abs_diff=float((got - ref).abs().max()), rel=float((got - ref).norm() / ref.norm()))
 
 # ---- the sharded 7B-class stack ----
 wgen = torch.Generator(device="cuda").manual_seed(4242)
@@ -79,7 +101,7 @@ lo, hi = chk.clone(), chk.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 say(what="ranks_bit_identical", same=bool(lo.item() == hi.item()))
 
-for chunks, reserve in ((1, 0), (2, 8), (4, 8), (2, 16), (4, 16), (8, 8)):
+for chunks, reserve in ((1, 0), (2, 8), (2, 12), (2, 16), (2, 24), (4, 16), (4, 24)):
     if tokens < chunks * 512: continue
     ctx._ck(lib.dllm_tp_configure(ctx.h, chunks, reserve if chunks > 1 else 0, 0))
     x.copy_(x0); ms_c = tm.run(step, 4, 2)

@@ -3,7 +3,8 @@
 1. Tensor-parallel stack (NCCL at the layer boundaries) against the ORACLE's f64-accumulated stack built from the oracle's
    own quantization of the unsharded weights (diffuse-llm-rs/src/lib.rs:806-813 composed with quantization.rs:81-85):
    f32 SIMT path, tcgen05 path (bf16 all-reduce), GEMV path; then the tcgen05 path at 2048 tokens with the all-reduces
-   overlapped on the communication stream (token chunks) and with the overlap switched off.
+   overlapped on the communication stream (token chunks) and with the overlap switched off; then the same with the
+   library's own peer-to-peer all-reduce kernel over NVLink instead of NCCL.
 2. A stack whose LAST layer is column-parallel, through dllm_denoise_step_dev: the all-gather lands in the step's own
    noise_pred buffer (it used to be staged in that same buffer).
 3. Row-sharded KV quantize: per-token (D) rows are independent; per-tensor (B) all-reduces min / max — the concatenated
@@ -87,6 +88,25 @@ def main():
         print(f"rank {rank} overlap chunks={chunks} rel-vs-oracle {rel:.3e}", flush=True)
         ok = ok and rel <= 2e-2 and np.all(np.isfinite(y))
     ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
+    # the same stack with the library's own all-reduce over NVLink peer memory (CUDA-IPC arena, csrc/tp.cu) instead of NCCL:
+    # same oracle bound, bit-identical on all ranks (every element is summed by exactly one rank), and identical bits to the
+    # NCCL result of the same placement is NOT required (different summation order is allowed) — only the oracle bound is
+    if tpg.enable_p2p(2048, 1024):
+        for chunks, reserve in ((1, 0), (2, 8)):
+            ctx._ck(lib.dllm_tp_configure(ctx.h, chunks, reserve, 0))
+            y = model.forward(x)
+            rel = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+            st = tpg.p2p_status()
+            t = torch.from_numpy(y.view(np.int32).astype(np.int64)).sum().reshape(1).cuda()
+            lo, hi = t.clone(), t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            print(f"rank {rank} p2p chunks={chunks} rel-vs-oracle {rel:.3e} allreduces {st['allreduces']} same-bits {bool(lo.item() == hi.item())}", flush=True)
+            ok = ok and rel <= 2e-2 and np.all(np.isfinite(y)) and st["allreduces"] > 0 and st["timed_out"] == 0 and lo.item() == hi.item()
+        ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
+        tpg.disable_p2p()
+    else:
+        print(f"rank {rank} p2p arena unavailable (CUDA IPC): NCCL path only", flush=True)
     model.close()
 
     # a stack that ENDS with a column-parallel layer, through dllm_denoise_step_dev: the all-gather's destination is the

@@ -255,6 +255,175 @@ def test_sample_with_phase_aware_cache(ctx, O):
     model.close()
 
 
+def _ref_cache_copy(O, k, v, bits, scheme):
+    """What the reference holds after KVCacheEntry::update(k, v) for one precision (lib.rs:246-276 -> quantization.rs:140-157
+    per tensor; prefill_kv.rs:104-121 per token row): codes and parameters of keys and values."""
+    import dllm_b200
+    out = []
+    for t in (k, v):
+        if scheme == dllm_b200.KV_TENSOR_B:
+            c, s, z = O.quantize_tensor(t.reshape(-1), bits)
+            out.append((c, np.array([s], F), np.array([z], F)))
+        else:
+            c, s, z = O.quantize_d_rows(t.reshape(-1, t.shape[-1]), [bits])
+            out.append((c.reshape(-1), s, z))
+    return out
+
+
+def _assert_copy_equals(entry, prefill, expect):
+    kc, vc, ks, kz, vs, vz = entry.export_copy(prefill)
+    (ekc, eks, ekz), (evc, evs, evz) = expect
+    assert np.array_equal(kc, ekc) and np.array_equal(vc, evc)
+    assert beq(ks, eks) and beq(kz, ekz) and beq(vs, evs) and beq(vz, evz)
+
+
+@pytest.mark.parametrize("scheme_name", ["TENSOR_B", "ROW_D"])
+def test_device_kv_cache_entry_matches_requantize_everything(ctx, O, scheme_name):
+    """The HBM-resident phase-aware entry: after every update / append, BOTH quantized copies equal the reference's
+    re-quantize-everything result on the concatenated tensors, bit for bit (lib.rs:246-276); the getters decode the active
+    phase's copy (:176-205); a decode-precision change drops the decode copy until the next update (:899-903); entering the
+    decode phase re-creates a missing copy from the f32 tensors (:228-235).  Nothing but the test's own uploads crosses PCIe."""
+    import dllm_b200
+    from dllm_b200.diffuse_llm import DeviceKVCacheEntry
+    scheme = getattr(dllm_b200, "KV_" + scheme_name)
+    rng = np.random.default_rng(21)
+    Lk, Hd, cap = 3, 256, 24
+    e = DeviceKVCacheEntry(ctx, Lk, Hd, cap, 8, 4, scheme)
+    assert e.is_empty() and e.is_prefill_phase and e.get_current_quant_bits() == 8
+    assert e.memory_usage() == 0 and e.get_keys().shape == (Lk, 0, Hd)
+    K = np.zeros((Lk, 0, Hd), F)
+    V = np.zeros((Lk, 0, Hd), F)
+    dk, dv = ctx.malloc(Lk * cap * Hd * 4), ctx.malloc(Lk * cap * Hd * 4)
+    for step, t_new in enumerate((5, 1, 7, 3)):
+        kn = (rng.standard_normal((Lk, t_new, Hd)) * (1 + step)).astype(F)
+        vn = rng.standard_normal((Lk, t_new, Hd)).astype(F)
+        K, V = np.concatenate([K, kn], 1), np.concatenate([V, vn], 1)
+        if step % 2 == 0:                                  # the model hands over only the new tokens ...
+            ctx.h2d(dk, kn); ctx.h2d(dv, vn)
+            e.append_dev(dk, dv, t_new)
+        else:                                              # ... or the whole tensors, like the reference's update()
+            ctx.h2d(dk, K); ctx.h2d(dv, V)
+            e.update_dev(dk, dv, K.shape[1])
+        assert e.len() == K.shape[1]
+        for prefill, bits in ((True, 8), (False, 4)):
+            _assert_copy_equals(e, prefill, _ref_cache_copy(O, K, V, bits, scheme))
+        assert e.memory_usage() == 2 * ((K.size * 8 + 7) // 8) + 2 * ((K.size * 4 + 7) // 8)      # lib.rs:279-302
+    # getters: the prefill copy while in prefill, the decode copy after the transition
+    def deq(t, bits):
+        if scheme == dllm_b200.KV_TENSOR_B:
+            c, s, z = O.quantize_tensor(t.reshape(-1), bits)
+            return O.dequantize_tensor(c, s, z).reshape(t.shape)
+        c, s, z = O.quantize_d_rows(t.reshape(-1, Hd), [bits])
+        return O.dequantize_d_rows(c, s, z).reshape(t.shape)
+    assert beq(e.get_keys(), deq(K, 8)) and beq(e.get_values(), deq(V, 8))
+    e.set_phase(False)
+    assert not e.is_prefill_phase and e.get_current_quant_bits() == 4
+    assert beq(e.get_keys(), deq(K, 4)) and beq(e.get_values(), deq(V, 4))
+    # progressive precision: the decode copy is dropped (the getters fall back to the f32 tensors, :190-204) ...
+    e.set_decode_bits(3)
+    assert e.export_copy(False) is None and e.get_current_quant_bits() == 3
+    assert beq(e.get_keys(), K) and beq(e.get_values(), V)
+    # ... and the next update re-creates it at the new width
+    h0, d0 = ctx.copy_bytes
+    e.refresh_dev()
+    ctx.sync()
+    assert ctx.copy_bytes == (h0, d0)
+    _assert_copy_equals(e, False, _ref_cache_copy(O, K, V, 3, scheme))
+    assert beq(e.get_keys(), deq(K, 3))
+    # leaving and re-entering the decode phase with a missing copy re-creates it from the f32 tensors
+    e.set_phase(True)
+    e.set_decode_bits(2)
+    e.set_phase(False)
+    _assert_copy_equals(e, False, _ref_cache_copy(O, K, V, 2, scheme))
+    with pytest.raises(dllm_b200.DllmError):
+        ctx.h2d(dk, K[:, :cap - K.shape[1] + 1]); ctx.h2d(dv, V[:, :cap - K.shape[1] + 1])
+        e.append_dev(dk, dv, cap - K.shape[1] + 1)        # beyond the capacity
+    ctx.free(dk); ctx.free(dv)
+    e.close()
+
+
+class _GrowingCacheModel:
+    """Mixin for the test below: a layer stack whose update_kv_cache appends this step's tokens as new keys / values."""
+
+
+def test_sample_cached_branch_runs_on_the_device(ctx, O):
+    """DiffuseLLM::sample with a cache id (lib.rs:862-936), everything on the device: (1) with the reference layer (which
+    ignores the cache, :815-835) the sample equals the seeded loop without cache bit for bit, the entry goes through the
+    prefill -> decode transition and the progressive decode widths of :886-903, and no byte crosses PCIe between the first
+    and the last step; (2) with a model that appends keys / values every step the entry ends up bit-identical to the
+    reference's re-quantize-everything update of the concatenated tensors."""
+    import dllm_b200
+    from dllm_b200 import PATH_SIMT
+    from dllm_b200.diffuse_llm import DiffuseLLM, DiffusionConfig, QuantizedDiffusionModel
+    rng = np.random.default_rng(33)
+    H, seq, batch, steps, seed = 128, 2, 3, 8, 7
+    layers, ref = build_stack(ctx, O, rng, [H, 256, H])
+    cfg = DiffusionConfig(num_timesteps=50, hidden_size=H, num_layers=2)
+    model = QuantizedDiffusionModel(layers, H, cfg, ctx, PATH_SIMT)
+    llm = DiffuseLLM(cfg, ctx)
+    plain = llm.sample_seeded(model, (batch, seq), steps, seed, use_graph=False)
+    k0 = rng.standard_normal((2, 4, H)).astype(F)
+    entry = llm.init_kv_cache_dev(16)
+    entry.update(k0, -k0)
+    llm.kv_cache["c"] = entry
+    out = llm.sample_cached_dev(model, (batch, seq), steps, "c", seed)
+    assert beq(out, plain)
+    # (:890-897: progress runs up to 2, so the decode width goes 2, 1, 1, 0, 0 over the last five of eight steps — at 0 bits
+    #  the reference keeps no decode copy and get_keys returns the f32 tensors)
+    bits_end = O.progressive_bits(steps, 0)[0]
+    assert bits_end == 0 and O.progressive_bits(steps, 4) == (2, False) and O.progressive_bits(steps, 5)[1]
+    assert not entry.is_prefill_phase and entry.get_current_quant_bits() == bits_end
+    assert entry.export_copy(False) is None and beq(entry.get_keys(), k0) and beq(entry.get_values(), -k0)
+    _assert_copy_equals(entry, True, _ref_cache_copy(O, k0, -k0, 8, dllm_b200.KV_TENSOR_B))
+    # the same loop stopped while the decode width is still 1 bit: 3 of its 8 steps are left out by running a 5-step loop
+    # whose schedule ends at width ... (5 steps: t = 2 -> progress 1.5 -> 1 bit; t = 1, 0 -> 0 bits), so instead drive the
+    # entry by hand through the :886-903 sequence of one decode step and compare the re-created copy
+    entry.set_phase(False)
+    entry.set_decode_bits(1)
+    entry.refresh_dev()
+    _assert_copy_equals(entry, False, _ref_cache_copy(O, k0, -k0, 1, dllm_b200.KV_TENSOR_B))
+
+    class Growing(QuantizedDiffusionModel):
+        """keys = this step's tokens viewed as [1 layer... no: num_layers copies], values = their negation, appended"""
+        def __init__(self, *a, **kw):
+            super().__init__(*a, **kw)
+            self.copies = []
+            self.h2d0 = None
+
+        def update_kv_cache_dev(self, x_dev, t, batch_, feat, cache):
+            if self.h2d0 is None:
+                self.h2d0 = self._ctx.copy_bytes
+            tokens = batch_ * feat // self.hidden
+            # [layers, tokens, hidden]: every layer caches the step's tokens; built with device-to-device copies only
+            n = tokens * self.hidden
+            kd = self._ctx.malloc(cache.layers * n * 4)
+            for l in range(cache.layers):
+                self._ctx._ck(self._ctx._lib.dllm_add_noise_dev(self._ctx.h, self.h, x_dev, x_dev, 0, batch_, feat, kd + l * n * 4))
+            self.copies.append(kd)
+            self.last = self._ctx.copy_bytes
+            return ("append", kd, kd, tokens)
+
+    gmodel = Growing(layers, H, cfg, ctx, PATH_SIMT)
+    llm2 = DiffuseLLM(cfg, ctx)
+    tokens = batch * seq
+    out2 = llm2.sample_cached_dev(gmodel, (batch, seq), steps, "g", seed, capacity=steps * tokens, scheme=dllm_b200.KV_ROW_D)
+    assert beq(out2, plain)                                           # forward still ignores the cache
+    assert gmodel.last == gmodel.h2d0                                 # no PCIe traffic between the first and the last step
+    e2 = llm2.kv_cache["g"]
+    assert e2.len() == steps * tokens
+    Kf = e2.get_keys()                                                # decode width 0 at the end: the f32 history itself
+    assert e2.export_copy(False) is None and np.all(np.isfinite(Kf)) and float(np.abs(Kf).max()) > 0
+    # the prefill copy was built by eight appends of six tokens each: it must equal ONE quantization of the whole history
+    _assert_copy_equals(e2, True, _ref_cache_copy(O, Kf, Kf, 8, dllm_b200.KV_ROW_D))
+    e2.set_decode_bits(3)
+    e2.refresh_dev()
+    _assert_copy_equals(e2, False, _ref_cache_copy(O, Kf, Kf, 3, dllm_b200.KV_ROW_D))
+    for d in gmodel.copies:
+        ctx.free(d)
+    gmodel.close()
+    model.close()
+
+
 def test_cpp_host_mirror_harness():
     """The C++ mirror of the reference interface (host/dllm.hpp) run as the reference's own unit tests."""
     import os

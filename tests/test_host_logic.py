@@ -63,3 +63,43 @@ def test_bitquantizer_scale_and_packed_len():
     for n in (0, 1, 7, 8, 9, 4097):
         for bits in (1, 2, 4, 8):
             assert L.lib().dllm_packed_len(n, bits) == O.packed_len(n, bits) == (n * bits + 7) // 8
+
+
+def test_kv_cache_accounting_and_eviction_policy():
+    """lib.rs:988-1084 on the host: the accounting quirks (f32 size charged before quantization, saturating growth of an
+    updated entry) and the eviction order (largest entry first, despite the function's name) — no GPU involved: the
+    entries are stand-ins that report the reference's memory_usage formula (:279-302)."""
+    from dllm_b200.diffuse_llm import DiffuseLLM, DiffusionConfig
+
+    class Entry:
+        def __init__(self, k, v, pre, dec):
+            self.k, self.bits = k, (pre, dec)
+
+        def memory_usage(self):
+            return sum(2 * ((self.k.size * b + 7) // 8) for b in self.bits if b > 0) or self.k.size * 8
+
+        def update(self, k, v):
+            self.k = k
+
+    class LLM(DiffuseLLM):
+        def _new_entry(self, keys, values, pre, dec):
+            return Entry(keys, values, pre, dec)
+
+    cfg = DiffusionConfig(hidden_size=8, num_layers=2, kv_quant_bits=4, max_cache_size=3000)
+    llm = LLM(cfg, ctx=object())
+    k = lambda seq: np.zeros((2, seq, 8), np.float32)
+    llm.update_kv_cache("a", k(4), k(4))                       # 64 elements: quantized size 2 copies x 2 tensors x 32 B = 128
+    assert llm.kv_cache_memory_usage() == 128
+    llm.update_kv_cache("b", k(16), k(16))                     # 256 elements -> 512 B
+    assert llm.kv_cache_memory_usage() == 640
+    llm.update_kv_cache("a", k(8), k(8))                       # in place: grows by max(0, 128*4*2 - 128) = 896
+    assert llm.kv_cache_memory_usage() == 640 + 896 and llm.kv_cache["a"].k.shape[1] == 8
+    # next insert: 1536 + 32*4*2*... = over the 3000-byte budget -> evict the LARGEST entry ("b", 512 B), not the oldest
+    llm.update_kv_cache("c", k(12), k(12))                     # entry_size = 192*4*2 = 1536 -> new_usage 3072 > 3000
+    assert "b" not in llm.kv_cache and "a" in llm.kv_cache and "c" in llm.kv_cache
+    assert llm.kv_cache_memory_usage() == 1536 - 512 + 384     # 'c' is charged its quantized size (192 el -> 384 B)
+    llm.clear_kv_cache()
+    assert llm.kv_cache == {} and llm.kv_cache_memory_usage() == 0
+    cfg.use_kv_cache = False
+    llm.update_kv_cache("z", k(4), k(4))
+    assert llm.kv_cache == {}
