@@ -426,16 +426,24 @@ def tp7b_block(ctx, stream, tm, rank, world, tpg, pk):
         modes["nccl_serial"] = timed(1, 0)
         modes["nccl_overlapped_2_chunks"] = timed(2, 8)
         # (b) this library's own all-reduce over NVLink peer memory (csrc/tp.cu), same two placements
+        #     fused: the row-parallel GEMM's epilogue pushes its tile rows into the owners' receive buffers (reduce-scatter under
+        #     the GEMM), a reduce + all-gather kernel finishes the exchange; allreduce: plain GEMM, then the two-shot kernel
         p2p = tpg.enable_p2p(tokens, max(maxw, H))
         if p2p:
-            modes["p2p_serial"] = timed(1, 0)
-            modes["p2p_overlapped_2_chunks"] = timed(2, 16)
+            modes["p2p_fused_reduce_scatter"] = timed(1, 0)
+            modes["p2p_fused_reduce_scatter_overlapped_2_chunks"] = timed(2, 8)
+            os.environ["DLLM_TP_FUSED_RS"] = "0"
+            modes["p2p_allreduce"] = timed(1, 0)
+            os.environ.pop("DLLM_TP_FUSED_RS", None)
             n64 = 16 << 20
             st = tpg.p2p_status()
             ms_p2p = tm.run(lambda i: tpg.allreduce_dev(st["arena"], n64), 20, 3)
         best = min(modes, key=lambda k: modes[k]["ms_per_step"])
         ms_tp, ms_nocomm = modes[best]["ms_per_step"], modes[best]["gemm_only_ms"]
-        cfg_of = {"nccl_serial": (1, 0), "nccl_overlapped_2_chunks": (2, 8), "p2p_serial": (1, 0), "p2p_overlapped_2_chunks": (2, 16)}
+        cfg_of = {"nccl_serial": (1, 0), "nccl_overlapped_2_chunks": (2, 8), "p2p_fused_reduce_scatter": (1, 0),
+                  "p2p_fused_reduce_scatter_overlapped_2_chunks": (2, 8), "p2p_allreduce": (1, 0)}
+        if best == "p2p_allreduce":
+            os.environ["DLLM_TP_FUSED_RS"] = "0"
         if p2p and not best.startswith("p2p"):
             tpg.disable_p2p()
             p2p_used = False
@@ -477,7 +485,10 @@ def tp7b_block(ctx, stream, tm, rank, world, tpg, pk):
                                 "p2p_algbw_GBps": (16 << 20) * 4 / ms_p2p / 1e6 if p2p else None,
                                 "p2p_link_GBps_per_direction": (16 << 20) * 4 * 2 * (world - 1) / world / ms_p2p / 1e6 if p2p else None},
             "p2p": {"available": bool(p2p), "used_for_the_headline": bool(p2p_used),
-                    "kernel": "p2p_allreduce_kernel (two-shot over a CUDA-IPC arena: peer loads / stores + flag barriers)"},
+                    "kernels": "umma_qlinear_pair2_kernel with the reduce-scatter fused into its epilogue (bulk tensor stores into the "
+                               "owners' receive buffers over NVLink) + p2p_reduce_gather_kernel (sum of the W partial row blocks, peer "
+                               "stores to every rank); p2p_allreduce_kernel (two-shot) where the shape does not suit the fused form; "
+                               "CUDA-IPC arena, flag barriers with time-out"},
             "limiting_collective": "all-reduce of the row-parallel partial sums ([tokens, N] bf16, in place), "
                                    f"{ar_bytes / 1e9:.2f} GB per step per GPU = {2 * (world - 1) / world * ar_bytes / 1e9:.2f} GB on NVLink per direction",
             "vs_unsharded_rel_err": rel,

@@ -1023,21 +1023,44 @@ int32_t tp_allreduce_bf16(dllm_ctx *ctx, void *buf, size_t n);
 int32_t tp_allreduce_on(dllm_ctx *ctx, void *buf, size_t n, bool bf16, cudaStream_t stream);
 int32_t tp_allreduce_minmax(dllm_ctx *ctx, float *params_dev);
 int32_t tp_allgather_cols(dllm_ctx *ctx, const float *in, size_t M, size_t n_local, float *out);
+bool tp_p2p_regions(const dllm_ctx *ctx, size_t bytes_each, char **b0, char **b1, char **recv);
+void tp_p2p_peer_ptrs(const dllm_ctx *ctx, const void *local, void **out8);
+int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream);
 
 // The two ping-pong activation buffers of a tensor-parallel tcgen05 stack: the halves of the peer-to-peer arena when it is
 // enabled and large enough (dllm_tp_p2p_enable: the row-parallel partial sums are then reduced in place by this library's
 // own NVLink kernel), else the context's ordinary buffers (ncclAllReduce).  Same sizes on every rank => same offsets.
-static int32_t tp_act_bufs(dllm_ctx *ctx, size_t bytes_each, char **b0, char **b1) {
-    if (ctx->p2p_arena && ctx->tp_world > 1 && 2 * ((bytes_each + 255) & ~(size_t)255) <= ctx->p2p_bytes) {
-        *b0 = (char *)ctx->p2p_arena;
-        *b1 = (char *)ctx->p2p_arena + ((ctx->p2p_bytes / 2) & ~(size_t)255);
-        return DLLM_OK;
-    }
+static int32_t tp_act_bufs(dllm_ctx *ctx, size_t bytes_each, char **b0, char **b1, char **recv) {
+    *recv = nullptr;
+    if (tp_p2p_regions(ctx, bytes_each, b0, b1, recv)) return DLLM_OK;
     DLLM_TRY(ensure_buf(ctx, ctx->act[0], bytes_each));
     DLLM_TRY(ensure_buf(ctx, ctx->act[1], bytes_each));
     *b0 = (char *)ctx->act[0].p;
     *b1 = (char *)ctx->act[1].p;
     return DLLM_OK;
+}
+
+// A row-parallel layer that is not the stack's last one, with the reduce-scatter fused into the dense kernel's epilogue and the
+// all-gather done by tp_reduce_gather: possible when the arena has a receive region and the shape suits the CTA-pair kernel.
+// (DLLM_TP_FUSED_RS=0 switches it off: experiments.)
+static bool tp_fused_rs_ok(const dllm_ctx *ctx, const dllm_qweight *w, size_t tokens, const char *recv) {
+    const char *sw = getenv("DLLM_TP_FUSED_RS");                  // read per call: the multi-GPU check toggles it
+    const bool off = sw && atoi(sw) == 0;
+    return !off && recv && !ctx->tp_skip_comm && k_umma_rs_supported(ctx, w, tokens, ctx->tp_world);
+}
+
+// x [tokens, K shard] -> recv buffers of all ranks (fused epilogue); then, on `stream`, recv -> dst [tokens, N] on every rank
+static int32_t tp_row_linear_fused(dllm_ctx *ctx, const dllm_qweight *w, const void *x_bf16, size_t tokens, char *recv, void *dst,
+                                   cudaStream_t reduce_stream, cudaEvent_t gemm_done) {
+    UmmaRs rs;
+    tp_p2p_peer_ptrs(ctx, recv, rs.recv);
+    rs.world = ctx->tp_world; rs.rank = ctx->tp_rank; rs.rows = tokens / (size_t)ctx->tp_world;
+    DLLM_TRY(k_qlinear_umma_rs(ctx, w, x_bf16, tokens, &rs));
+    if (reduce_stream != ctx->stream) {
+        CUDA_TRY(ctx, cudaEventRecord(gemm_done, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(reduce_stream, gemm_done, 0));
+    }
+    return tp_reduce_gather(ctx, recv, dst, rs.rows, w->N, reduce_stream);
 }
 
 static int env_int(const char *name, int dflt) {
@@ -1067,8 +1090,8 @@ static int32_t forward_tp_overlapped(dllm_ctx *ctx, dllm_model *m, const float *
     // every chunk owns one region of each ping-pong buffer ([its tokens, width] dense inside): chunks never overlap,
     // whatever the layers' widths are
     const size_t region = per * maxw * 2;
-    char *buf0, *buf1;
-    DLLM_TRY(tp_act_bufs(ctx, region * chunks, &buf0, &buf1));
+    char *buf0, *buf1, *recv0;
+    DLLM_TRY(tp_act_bufs(ctx, region * chunks, &buf0, &buf1, &recv0));
     for (int c = 0; c < chunks; ++c)
         if (c0[c + 1] > c0[c])
             DLLM_TRY(k_f32_to_bf16(ctx, x_dev + c0[c] * m->layers[0]->K, (c0[c + 1] - c0[c]) * m->layers[0]->K, buf0 + c * region));
@@ -1089,13 +1112,22 @@ static int32_t forward_tp_overlapped(dllm_ctx *ctx, dllm_model *m, const float *
             if (tn == 0) continue;
             if (pending[c]) { rc = cudaStreamWaitEvent(ctx->stream, ctx->tp_ev[2 * c + 1], 0) == cudaSuccess ? DLLM_OK : DLLM_ERR_CUDA; pending[c] = 0; }
             char *a = cur + c * region, *b = nxt + c * region;
+            bool fused = false;
             for (size_t l = l0; l <= l1 && rc == DLLM_OK; ++l) {
                 const dllm_qweight *w = m->layers[l];
                 const bool last = l + 1 == L;
-                rc = k_qlinear_umma(ctx, w, a, tn, last ? out_dev + t0 * w->N : nullptr, last ? nullptr : b);
+                if (l == l1 && reduce && !last && tp_fused_rs_ok(ctx, w, tn, recv0)) {
+                    // reduce-scatter inside the GEMM's epilogue; the all-gather half runs on the communication stream
+                    rc = tp_row_linear_fused(ctx, w, a, tn, recv0 + c * region, b, ctx->comm_stream, ctx->tp_ev[2 * c]);
+                    if (rc == DLLM_OK && cudaEventRecord(ctx->tp_ev[2 * c + 1], ctx->comm_stream) != cudaSuccess) rc = DLLM_ERR_CUDA;
+                    pending[c] = 1;
+                    fused = true;
+                } else {
+                    rc = k_qlinear_umma(ctx, w, a, tn, last ? out_dev + t0 * w->N : nullptr, last ? nullptr : b);
+                }
                 char *t = a; a = b; b = t;
             }
-            if (rc == DLLM_OK && reduce) {
+            if (rc == DLLM_OK && reduce && !fused) {
                 const dllm_qweight *w = m->layers[l1];
                 const bool last = l1 + 1 == L;
                 void *buf = last ? (void *)(out_dev + t0 * w->N) : (void *)a;      // `a` is the last layer's output after the swap
@@ -1159,15 +1191,19 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
     for (size_t l = 0; l < L; ++l)
         if (m->parallel[l] == 1 && (l + 1 == L || m->parallel[l + 1] != 2)) no_gather = false;
     if (all_umma && any_parallel && no_gather && ctx->tp_world > 1) {
-        const int chunks = ctx->tp_chunks > 0 ? ctx->tp_chunks : env_int("DLLM_TP_CHUNKS", 2);
+        // default placement (measured on the 7B-class stack at TP2, ms per step): with the peer-to-peer arena the row layers push
+        // their partial sums from the GEMM epilogue and only the all-gather half is left at the boundary — one launch per
+        // layer, 47.1 (token chunks + overlap: 50.9, chunked GEMMs cost more than the overlap hides); with NCCL the overlap
+        // pays: 2 chunks 50.9 against 53.2
+        const int chunks = ctx->tp_chunks > 0 ? ctx->tp_chunks : env_int("DLLM_TP_CHUNKS", ctx->p2p_arena ? 1 : 2);
         if (chunks > 1 && tokens >= (size_t)chunks * 512) return forward_tp_overlapped(ctx, m, x_dev, tokens, out_dev, chunks);
     }
     if (all_umma && (!any_parallel || no_gather)) {
         // bf16 activations between layers; the last layer writes f32.  Row-parallel layers leave partial sums:
         // one NCCL all-reduce at the layer boundary, on the bf16 tensor the next linear reads (f32 for the last).
-        char *buf0, *buf1;
+        char *buf0, *buf1, *recv0 = nullptr;
         if (any_parallel) {
-            DLLM_TRY(tp_act_bufs(ctx, tokens * maxw * 2, &buf0, &buf1));
+            DLLM_TRY(tp_act_bufs(ctx, tokens * maxw * 2, &buf0, &buf1, &recv0));
         } else {
             DLLM_TRY(ensure_buf(ctx, ctx->act[0], tokens * maxw * 2));
             DLLM_TRY(ensure_buf(ctx, ctx->act[1], tokens * maxw * 2));
@@ -1177,6 +1213,11 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
         void *cur = buf0, *nxt = buf1;
         for (size_t l = 0; l < L; ++l) {
             const bool last = l + 1 == L;
+            if (m->parallel[l] == 2 && !last && tp_fused_rs_ok(ctx, m->layers[l], tokens, recv0)) {
+                DLLM_TRY(tp_row_linear_fused(ctx, m->layers[l], cur, tokens, recv0, nxt, ctx->stream, nullptr));
+                void *t = cur; cur = nxt; nxt = t;
+                continue;
+            }
             DLLM_TRY(k_qlinear_umma(ctx, m->layers[l], cur, tokens, last ? out_dev : nullptr, last ? nullptr : nxt));
             if (m->parallel[l] == 2) {
                 if (last) DLLM_TRY(tp_allreduce(ctx, out_dev, tokens * m->layers[l]->N));

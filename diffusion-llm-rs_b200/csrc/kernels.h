@@ -56,6 +56,11 @@ int32_t k_qlinear_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16
                        float *y_f32_dev, void *y_bf16_dev);
 bool k_umma_supported(const dllm_qweight *qw, size_t M);
 // exact int8 x u8-codes -> int32 linear on tcgen05 kind::i8 (per-tensor quantized weights)
+// the same linear as a tensor-parallel ROW layer with the reduce-scatter fused into the epilogue: tile rows go straight into the
+// receive buffer [M, N] bf16 of the rank that owns those tokens (recv[r]: rank r's buffer as mapped here), row block `rank`
+struct UmmaRs { void *recv[8]; int world, rank; size_t rows; };
+bool k_umma_rs_supported(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, int world);
+int32_t k_qlinear_umma_rs(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M, const UmmaRs *rs);
 int32_t k_qlinear_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq_dev, size_t M, int32_t *y_i32_dev);
 bool k_umma_i8_supported(const dllm_qweight *qw, size_t M);
 

@@ -148,6 +148,45 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
     p2p_barrier(a, 1, a.epoch + 1);
 }
 
+// Second half of the fused reduce-scatter + all-gather: the dense kernel of a row-parallel layer has already pushed every
+// rank's partial sums for MY tokens into my receive buffer (row block s = rank s's partial, csrc/umma_gemm.cu epilogue); this
+// kernel sums the W row blocks (local loads only), and stores the finished rows into every rank's activation buffer (the
+// all-gather: W-1 peer stores per element).  NVLink carries (W-1)/W of the tensor per direction here — the other half went out
+// under the GEMM.  a.off = receive buffer, a.off2 = destination tensor [M, N], a.n16 = 16-byte vectors of one rank's slice.
+template <int W, int U>
+__global__ void __launch_bounds__(512) p2p_reduce_gather_kernel(const P2PArgs a, size_t off2) {
+    p2p_barrier(a, 0, a.epoch);
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    const unsigned char *recv = a.base[a.rank] + a.off;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n16; i += U * T) {
+        uint4 v[U][W];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < a.world && i + u * T < a.n16) v[u][r] = ld_relaxed_sys_v4(recv + ((size_t)r * a.n16 + i + u * T) * 16);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i + u * T >= a.n16) break;
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < a.world) p2p_accumulate<true>(acc, v[u][r]);                     // rank order, as in the two-shot kernel
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+            const uint4 o = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
+                                       *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < a.world) st_relaxed_sys_v4(a.base[r] + off2 + ((size_t)a.rank * a.n16 + i + u * T) * 16, o);
+        }
+    }
+    p2p_barrier(a, 1, a.epoch + 1);
+}
+
 template <bool BF16>
 void p2p_launch(const P2PArgs &a, int blocks, cudaStream_t stream) {
     if (a.world <= 2) p2p_allreduce_kernel<BF16, 2, 4><<<blocks, 512, 0, stream>>>(a);
@@ -164,6 +203,15 @@ static bool p2p_covers(const dllm_ctx *ctx, const void *buf, size_t bytes) {
     return b >= a0 && b + bytes <= a0 + ctx->p2p_bytes && ((b - a0) & 15u) == 0 && (bytes & 15u) == 0;
 }
 
+static int p2p_blocks(const dllm_ctx *ctx, bool overlapped) {
+    // alone on the GPU: one block per SM up to 128; under a dense kernel: two blocks per SM that kernel leaves free
+    const int reserve = ctx->sm_limit > 0 ? ctx->sm_count - ctx->sm_limit : 0;
+    int blocks = overlapped ? 2 * (reserve > 0 ? reserve : 4) : (ctx->sm_count < 128 ? ctx->sm_count : 128);
+    static const int blocks_env = getenv("DLLM_P2P_BLOCKS") ? atoi(getenv("DLLM_P2P_BLOCKS")) : 0;      // experiments only
+    if (blocks_env > 0) blocks = blocks_env;
+    return blocks > kP2PMaxBlocks ? kP2PMaxBlocks : blocks;
+}
+
 static int32_t p2p_allreduce(dllm_ctx *ctx, void *buf, size_t bytes, bool bf16, cudaStream_t stream, bool overlapped) {
     P2PArgs a;
     for (int r = 0; r < kP2PMaxWorld; ++r) a.base[r] = (unsigned char *)(r < ctx->tp_world ? ctx->p2p_peer[r] : nullptr);
@@ -174,14 +222,56 @@ static int32_t p2p_allreduce(dllm_ctx *ctx, void *buf, size_t bytes, bool bf16, 
     ctx->p2p_epoch += 2;
     a.rank = ctx->tp_rank; a.world = ctx->tp_world;
     a.err = ctx->p2p_err;
-    // alone on the GPU: one block per SM up to 128; under a dense kernel: two blocks per SM that kernel leaves free
-    const int reserve = ctx->sm_limit > 0 ? ctx->sm_count - ctx->sm_limit : 0;       // what the overlapped forward leaves free right now
-    int blocks = overlapped ? 2 * (reserve > 0 ? reserve : 4) : (ctx->sm_count < 128 ? ctx->sm_count : 128);
-    if (blocks > kP2PMaxBlocks) blocks = kP2PMaxBlocks;
-    static const int blocks_env = getenv("DLLM_P2P_BLOCKS") ? atoi(getenv("DLLM_P2P_BLOCKS")) : 0;      // experiments only
-    if (blocks_env > 0 && blocks_env <= kP2PMaxBlocks) blocks = blocks_env;
+    const int blocks = p2p_blocks(ctx, overlapped);
     if (bf16) p2p_launch<true>(a, blocks, stream);
     else p2p_launch<false>(a, blocks, stream);
+    LAUNCH_CHECK(ctx);
+    ctx->p2p_calls++;
+    return DLLM_OK;
+}
+
+// The three regions of the arena a tensor-parallel tcgen05 stack uses: two activation buffers and the receive buffer of the
+// fused reduce-scatter (absent when the arena only has room for the first two).
+bool tp_p2p_regions(const dllm_ctx *ctx, size_t bytes_each, char **b0, char **b1, char **recv) {
+    if (!ctx->p2p_arena || ctx->tp_world <= 1) return false;
+    const size_t need = (bytes_each + 255) & ~(size_t)255;
+    if (3 * need <= ctx->p2p_bytes) {
+        const size_t R = (ctx->p2p_bytes / 3) & ~(size_t)255;
+        *b0 = (char *)ctx->p2p_arena; *b1 = *b0 + R; *recv = *b0 + 2 * R;
+        return true;
+    }
+    if (2 * need <= ctx->p2p_bytes) {
+        *b0 = (char *)ctx->p2p_arena; *b1 = *b0 + ((ctx->p2p_bytes / 2) & ~(size_t)255); *recv = nullptr;
+        return true;
+    }
+    return false;
+}
+
+// every rank's view of the address `local` of this rank's arena
+void tp_p2p_peer_ptrs(const dllm_ctx *ctx, const void *local, void **out8) {
+    const size_t off = (size_t)((const char *)local - (const char *)ctx->p2p_arena);
+    for (int r = 0; r < 8; ++r) out8[r] = r < ctx->tp_world ? (void *)((char *)ctx->p2p_peer[r] + off) : nullptr;
+}
+
+// recv (this rank's receive buffer: [world][rows, N] bf16, filled by all ranks' fused epilogues) -> dst [world * rows, N] on every rank
+int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream) {
+    const size_t slice = rows * N * 2;
+    if (!p2p_covers(ctx, recv, slice * ctx->tp_world) || !p2p_covers(ctx, dst, slice * ctx->tp_world))
+        DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "reduce-gather: buffers must lie in the peer-to-peer arena");
+    P2PArgs a;
+    for (int r = 0; r < kP2PMaxWorld; ++r) a.base[r] = (unsigned char *)(r < ctx->tp_world ? ctx->p2p_peer[r] : nullptr);
+    a.off = (size_t)((uintptr_t)recv - (uintptr_t)ctx->p2p_arena);
+    const size_t off2 = (size_t)((uintptr_t)dst - (uintptr_t)ctx->p2p_arena);
+    a.n16 = slice / 16;
+    a.flag_off = ctx->p2p_bytes;
+    a.epoch = ctx->p2p_epoch + 1;
+    ctx->p2p_epoch += 2;
+    a.rank = ctx->tp_rank; a.world = ctx->tp_world;
+    a.err = ctx->p2p_err;
+    const int blocks = p2p_blocks(ctx, stream != ctx->stream);
+    if (a.world <= 2) p2p_reduce_gather_kernel<2, 4><<<blocks, 512, 0, stream>>>(a, off2);
+    else if (a.world <= 4) p2p_reduce_gather_kernel<4, 2><<<blocks, 512, 0, stream>>>(a, off2);
+    else p2p_reduce_gather_kernel<8, 1><<<blocks, 512, 0, stream>>>(a, off2);
     LAUNCH_CHECK(ctx);
     ctx->p2p_calls++;
     return DLLM_OK;

@@ -1110,6 +1110,7 @@ umma_qlinear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaA
 // r = c / q, i = c % q.  ntok is a run-time multiple of 32 (MMA N = ntok/2 is a multiple of 16), chosen per problem so
 // that the tile count fills the 74 CTA pairs evenly (e.g. 8192 tokens x 2048 columns: 224-token tiles = 4 full waves).
 // ------------------------------------------------------------------------------------------
+struct RsMaps { CUtensorMap m[8]; };       // receive buffers [M, N] bf16 of up to 8 ranks (peer-mapped)
 struct Pair2Args {
     const uint8_t *packed;
     const uint2 *dqparams;
@@ -1119,6 +1120,10 @@ struct Pair2Args {
     uint32_t M, N, Npad, k_blocks, n_tiles, n_pairs, m_tiles, group_kb;
     uint32_t ntok;             // tokens per pair tile: multiple of 32, <= 256
     uint32_t tiles;            // n_pairs * m_tiles
+    // fused reduce-scatter (tensor-parallel row layers, tp.cu): rs_world > 0 -> the bf16 tile rows are not stored into y but pushed
+    // over NVLink into the RECEIVE buffer of the rank that owns those tokens (rank o owns tokens [o*rs_rows, (o+1)*rs_rows)), row
+    // block `rs_rank` of it: one bulk tensor store per q-row block, straight from the staging buffer into peer memory
+    uint32_t rs_world, rs_rank, rs_rows;
     uint32_t dbg;              // timing experiments only (DLLM_UMMA_DBG): 1 skip MMAs, 2 skip dequant math, 8 skip activation loads, 64 skip stores
     long long *trace;          // dbg & 128: clock64 stamps of cluster 0's leader CTA: [role 0..7][256]
 };
@@ -1229,7 +1234,8 @@ __device__ __forceinline__ void stage_columns(uint32_t sbase, uint32_t q, const 
 
 template <int CB, int NDQ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((12 + 4 * NDQ) * 32, 1)
-umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const Pair2Args a) {
+umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+                          const __grid_constant__ RsMaps rs, const Pair2Args a) {
     using C = CfgP2<CB>;
     constexpr int KBS = C::KBS, kACols = C::kACols;
     constexpr int SW = C::kWStages, A = C::kSlots;
@@ -1463,8 +1469,22 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                         if (warp == kEpiWarp0 && lane == 0 && nt < a.n_tiles) {
                             const uint32_t src = smem_u32(smem + C::kOutOffset);
                             const int tokA = (int)(mt * ntok + h * q);
-                            tma_store_2d(&tmap_y, src, (int)(nt * 128), tokA);
-                            tma_store_2d(&tmap_y, src + q * 256u, (int)(nt * 128), tokA + (int)half_rows);
+                            if (a.rs_world == 0) {
+                                tma_store_2d(&tmap_y, src, (int)(nt * 128), tokA);
+                                tma_store_2d(&tmap_y, src + q * 256u, (int)(nt * 128), tokA + (int)half_rows);
+                            } else {
+                                // reduce-scatter fused into the epilogue: each q-row block goes to its owner's receive buffer
+                                // (q divides rs_rows, so a block never straddles two owners)
+#pragma unroll
+                                for (int b2 = 0; b2 < 2; ++b2) {
+                                    const uint32_t tk = (uint32_t)tokA + (uint32_t)b2 * half_rows;
+                                    if (tk < a.M) {
+                                        const uint32_t owner = tk / a.rs_rows;
+                                        tma_store_2d(&rs.m[owner], src + (uint32_t)b2 * q * 256u, (int)(nt * 128),
+                                                     (int)(a.rs_rank * a.rs_rows + (tk - owner * a.rs_rows)));
+                                    }
+                                }
+                            }
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                     }
@@ -1731,7 +1751,8 @@ static bool pair2_applicable(const dllm_ctx *ctx, const dllm_qweight *qw, size_t
 }
 
 template <int CB>
-int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, size_t M, float *y_f32, void *y_bf16) {
+int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, size_t M, float *y_f32, void *y_bf16,
+                          const UmmaRs *rsd = nullptr) {
     using C = CfgP2<CB>;
     constexpr int NDQ = kNDQ;
     PFN_encodeTiled enc = get_encode_fn();
@@ -1746,6 +1767,12 @@ int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_b
     const char *ntok_s = getenv("DLLM_UMMA_NTOK2");                                                 // experiments only (read per launch: scripts/ntok_sweep.py)
     const int ntok_env = ntok_s ? atoi(ntok_s) : 0;
     a.ntok = (ntok_env >= 32 && ntok_env <= 256 && ntok_env % 32 == 0) ? (uint32_t)ntok_env : pair2_pick_ntok(M, a.n_pairs, pairs_hw);
+    a.rs_world = 0; a.rs_rank = 0; a.rs_rows = 1;
+    if (rsd) {
+        // fused reduce-scatter: 64-row store blocks must not straddle two owners' token ranges
+        a.ntok = 256;
+        a.rs_world = (uint32_t)rsd->world; a.rs_rank = (uint32_t)rsd->rank; a.rs_rows = (uint32_t)rsd->rows;
+    }
     a.m_tiles = (uint32_t)((M + a.ntok - 1) / a.ntok);
     a.tiles = a.n_pairs * a.m_tiles;
     static const uint32_t dbg_flags = getenv("DLLM_UMMA_DBG") ? (uint32_t)atoi(getenv("DLLM_UMMA_DBG")) : 0u;
@@ -1777,6 +1804,21 @@ int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_b
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
     }
+    RsMaps rsm;
+    memset(&rsm, 0, sizeof(rsm));
+    if (rsd) {
+        // every rank's receive buffer [M, N] bf16 (row block s = the partial sums rank s computed for that rank's tokens), as
+        // mapped into this process; box = one staged part {128 columns, 64 tokens}
+        const cuuint64_t ydim[2] = {(cuuint64_t)qw->N, (cuuint64_t)M};
+        const cuuint64_t ystride[1] = {(cuuint64_t)qw->N * 2};
+        const cuuint32_t ybox[2] = {128, a.ntok / 4};
+        const cuuint32_t yestr[2] = {1, 1};
+        for (int r2 = 0; r2 < rsd->world; ++r2) {
+            r = enc(&rsm.m[r2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rsd->recv[r2], ydim, ystride, ybox, yestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled (receive buffer of rank %d) failed (%d)", r2, (int)r);
+        }
+    }
     DLLM_TRY(ensure_smem_attr(ctx, umma_qlinear_pair2_kernel<CB, NDQ>, C::kTotal));
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1802,7 +1844,7 @@ int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_b
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
-    CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, umma_qlinear_pair2_kernel<CB, NDQ>, tmap, tmap_y, a));
+    CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, umma_qlinear_pair2_kernel<CB, NDQ>, tmap, tmap_y, rsm, a));
     LAUNCH_CHECK(ctx);
     if (a.dbg & 128) {   // dump the timeline of cluster 0's leader (timing experiments only)
         std::vector<long long> hst(8 * 256);
@@ -1940,6 +1982,28 @@ int32_t k_qlinear_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *x
         case 4: return launch_umma_i8_ntok<4>(ctx, qw, xq_dev, M, y_i32_dev);
         default: return launch_umma_i8_ntok<8>(ctx, qw, xq_dev, M, y_i32_dev);
     }
+}
+
+// Row-parallel linear with the reduce-scatter fused into its epilogue (tp.cu): the dense CTA-pair kernel with 256-token tiles,
+// bf16 output, every rank's token slice a multiple of the 64-row store block
+bool k_umma_rs_supported(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, int world) {
+    if (!qw || world < 2 || world > 8 || M % (size_t)world != 0 || (M / world) % 64 != 0 || qw->N % 8 != 0) return false;
+    if (wl_container_bits(qw->bits) == 8 || !(qw->K % 8 == 0 && qw->group % WL_TILE_K == 0 && qw->int_zps)) return false;
+    if (pair2_mode() != 2 || qw->K % WL_TILE_K != 0 || M < 1024) return false;
+    const uint32_t n_pairs = (uint32_t)((qw->n_tiles + 1) / 2);
+    const uint32_t pairs_hw = (uint32_t)(ctx->sm_limit > 0 && ctx->sm_limit < ctx->sm_count ? ctx->sm_limit : ctx->sm_count) / 2;
+    return (uint64_t)((M + 255) / 256) * n_pairs >= pairs_hw / 2;
+}
+
+int32_t k_qlinear_umma_rs(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M, const UmmaRs *rs) {
+    if (!rs || !k_umma_rs_supported(ctx, qw, M, rs->world) || rs->rows * (size_t)rs->world != M)
+        DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "fused reduce-scatter: unsupported shape");
+    if ((reinterpret_cast<uintptr_t>(x_bf16_dev) & 15u) != 0) DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "x must be 16-byte aligned");
+    for (int r = 0; r < rs->world; ++r)
+        if (!rs->recv[r] || (reinterpret_cast<uintptr_t>(rs->recv[r]) & 15u) != 0) DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "receive buffers must be 16-byte aligned");
+    // (y_bf16 = any aligned non-null pointer: nothing is stored through it in this mode)
+    if (wl_container_bits(qw->bits) == 2) return launch_umma_pair2<2>(ctx, qw, x_bf16_dev, M, nullptr, rs->recv[rs->rank], rs);
+    return launch_umma_pair2<4>(ctx, qw, x_bf16_dev, M, nullptr, rs->recv[rs->rank], rs);
 }
 
 bool k_umma_supported(const dllm_qweight *qw, size_t M) {

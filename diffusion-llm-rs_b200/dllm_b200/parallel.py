@@ -121,7 +121,8 @@ class TensorParallelGroup:
         the two bf16 activation buffers [max_tokens, max_width] (+ slack for chunk rounding).  Collective.  False (on every
         rank) when CUDA IPC / peer access is unavailable — the NCCL path then stays in use."""
         from . import _lib as L
-        need = 2 * ((max_tokens + 512) * max_width * 2 + 4096)
+        # three regions: two activation buffers + the receive buffer of the fused reduce-scatter
+        need = 3 * ((max_tokens + 512) * max_width * 2 + 4096)
         try:
             self.ctx._ck(self.ctx._lib.dllm_tp_p2p_enable(self.ctx.h, need))
         except L.DllmError:

@@ -88,26 +88,47 @@ def main():
         print(f"rank {rank} overlap chunks={chunks} rel-vs-oracle {rel:.3e}", flush=True)
         ok = ok and rel <= 2e-2 and np.all(np.isfinite(y))
     ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
-    # the same stack with the library's own all-reduce over NVLink peer memory (CUDA-IPC arena, csrc/tp.cu) instead of NCCL:
+    model.close()
+    # a wider stack with the library's own all-reduce over NVLink peer memory (CUDA-IPC arena, csrc/tp.cu) instead of NCCL:
     # same oracle bound, bit-identical on all ranks (every element is summed by exactly one rank), and identical bits to the
     # NCCL result of the same placement is NOT required (different summation order is allowed) — only the oracle bound is
-    if tpg.enable_p2p(2048, 1024):
-        for chunks, reserve in ((1, 0), (2, 8)):
+    if tpg.enable_p2p(2048, 4096):
+        # wide enough for the dense CTA-pair kernel, so that the row-parallel layers run with the reduce-scatter fused into the
+        # GEMM epilogue (bulk tensor stores into the owners' receive buffers over NVLink) + the reduce / all-gather kernel
+        hid2 = 2048
+        dims2 = [hid2, 4096, hid2, hid2, hid2]
+        shapes2 = list(zip(dims2[:-1], dims2[1:]))
+        ws_b = [(rng.standard_normal(s_) / np.sqrt(s_[0])).astype(F) for s_ in shapes2]
+        bs_b = [(rng.standard_normal(s_[1]) * 0.1).astype(F) for s_ in shapes2]
+        plan_b = P.tp_plan(shapes2, world)
+        assert plan_b == [P.COLUMN, P.ROW, P.COLUMN, P.ROW], plan_b
+        xb = rng.standard_normal((4, hid2 * 512)).astype(F)          # 2048 tokens
+        ref_b = oracle_stack64(xb.reshape(-1, hid2), ws_b, bs_b).reshape(4, -1)
+        layers_b = []
+        for w_, b_, mode in zip(ws_b, bs_b, plan_b):
+            wsh, bsh = P.shard_weight(w_, b_, mode, rank, world)
+            layers_b.append(QWeight.quantize(ctx, np.ascontiguousarray(wsh), 4, 128, bsh))
+        model_b = QuantizedDiffusionModel(layers_b, hid2, ctx=ctx, path=dllm_b200.PATH_UMMA)
+        tpg.set_plan(model_b, plan_b)
+        for fused, chunks, reserve in (("1", 1, 0), ("1", 2, 16), ("0", 1, 0), ("0", 2, 16)):
+            os.environ["DLLM_TP_FUSED_RS"] = fused
             ctx._ck(lib.dllm_tp_configure(ctx.h, chunks, reserve, 0))
-            y = model.forward(x)
-            rel = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+            n0 = tpg.p2p_status()["allreduces"]
+            y = model_b.forward(xb)
+            rel = np.linalg.norm(y - ref_b) / np.linalg.norm(ref_b)
             st = tpg.p2p_status()
             t = torch.from_numpy(y.view(np.int32).astype(np.int64)).sum().reshape(1).cuda()
             lo, hi = t.clone(), t.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-            print(f"rank {rank} p2p chunks={chunks} rel-vs-oracle {rel:.3e} allreduces {st['allreduces']} same-bits {bool(lo.item() == hi.item())}", flush=True)
-            ok = ok and rel <= 2e-2 and np.all(np.isfinite(y)) and st["allreduces"] > 0 and st["timed_out"] == 0 and lo.item() == hi.item()
+            print(f"rank {rank} p2p fused_rs={fused} chunks={chunks} rel-vs-oracle {rel:.3e} kernel calls {st['allreduces'] - n0} same-bits {bool(lo.item() == hi.item())}", flush=True)
+            ok = ok and rel <= 2e-2 and np.all(np.isfinite(y)) and st["allreduces"] > n0 and st["timed_out"] == 0 and lo.item() == hi.item()
         ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
+        os.environ.pop("DLLM_TP_FUSED_RS", None)
+        model_b.close()
         tpg.disable_p2p()
     else:
         print(f"rank {rank} p2p arena unavailable (CUDA IPC): NCCL path only", flush=True)
-    model.close()
 
     # a stack that ENDS with a column-parallel layer, through dllm_denoise_step_dev: the all-gather's destination is the
     # step's noise_pred buffer
