@@ -1095,9 +1095,8 @@ static int32_t forward_tp_overlapped(dllm_ctx *ctx, dllm_model *m, const float *
     for (int c = 0; c < chunks; ++c)
         if (c0[c + 1] > c0[c])
             DLLM_TRY(k_f32_to_bf16(ctx, x_dev + c0[c] * m->layers[0]->K, (c0[c + 1] - c0[c]) * m->layers[0]->K, buf0 + c * region));
-    // SMs left to the collective: NCCL's few CTAs need 8; the library's own all-reduce keeps NVLink busy from 16
-    // (measured at TP2, 7B-class: NCCL 2 chunks / 8 SMs 50.9 ms, own kernel 2 chunks / 16 SMs 49.2 ms per step)
-    const int reserve = ctx->sm_reserve >= 0 ? ctx->sm_reserve : env_int("DLLM_TP_RESERVE_SMS", ctx->p2p_arena ? 16 : 8);
+    // SMs left to the collective's CTAs (NCCL's, or 16 blocks of the library's own reduce / gather kernel)
+    const int reserve = ctx->sm_reserve >= 0 ? ctx->sm_reserve : env_int("DLLM_TP_RESERVE_SMS", 8);
     ctx->sm_limit = ctx->sm_count - reserve;
     std::vector<char> pending(chunks, 0);          // chunk c's input is still being all-reduced on the comm stream
     char *cur = buf0, *nxt = buf1;
@@ -1195,7 +1194,9 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
         // their partial sums from the GEMM epilogue and only the all-gather half is left at the boundary — one launch per
         // layer, 47.1 (token chunks + overlap: 50.9, chunked GEMMs cost more than the overlap hides); with NCCL the overlap
         // pays: 2 chunks 50.9 against 53.2
-        const int chunks = ctx->tp_chunks > 0 ? ctx->tp_chunks : env_int("DLLM_TP_CHUNKS", ctx->p2p_arena ? 1 : 2);
+        //   at TP4 / TP8 the exchange outweighs the GEMMs and two token chunks with the gather half on the second stream win
+        //   (35.3 against 36.7 ms at TP4, 30.5 against 35.5 at TP8)
+        const int chunks = ctx->tp_chunks > 0 ? ctx->tp_chunks : env_int("DLLM_TP_CHUNKS", ctx->p2p_arena && ctx->tp_world <= 2 ? 1 : 2);
         if (chunks > 1 && tokens >= (size_t)chunks * 512) return forward_tp_overlapped(ctx, m, x_dev, tokens, out_dev, chunks);
     }
     if (all_umma && (!any_parallel || no_gather)) {

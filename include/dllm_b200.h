@@ -68,7 +68,8 @@ enum {
     DLLM_PATH_SIMT = 1,  /* f32 CUDA-core dequant-GEMV (exact f32 dequant, f32 accumulate) */
     DLLM_PATH_UMMA = 2,  /* tcgen05 / TMEM path: bf16 operands dequantized on the fly, f32 accumulate */
     DLLM_PATH_GEMV = 3   /* 1..16 tokens, HBM-bound: bulk-copy ring + int8 mma.sync (u8 codes x signed-digit block-fixed-point
-                            activations, exact int32 sums per 64-k block), f32 scale and accumulation across k-blocks */
+                            activations per aligned block of 128 k, exact int32 sums per quantization-group block), f32 scale and
+                            accumulation across blocks */
 };
 
 typedef struct dllm_ctx dllm_ctx;

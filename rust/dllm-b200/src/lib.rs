@@ -403,3 +403,99 @@ impl Drop for GpuKvEntry {
         unsafe { sys::dllm_kv_destroy(self.raw) }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Phase-aware cache entry resident in HBM (KVCacheEntry, lib.rs:122-313): f32 keys / values + a prefill- and a decode-precision
+// quantized copy, all on the device.  The device-pointer methods are what a GPU-resident sampling loop uses (lib.rs:885-921
+// without PCIe traffic); the ndarray methods stage through host memory for drop-in use.
+// ---------------------------------------------------------------------------------------------------------------------
+pub struct GpuKvCacheEntry {
+    raw: *mut sys::dllm_kvcache,
+    layers: usize,
+    hidden: usize,
+}
+unsafe impl Send for GpuKvCacheEntry {}
+unsafe impl Sync for GpuKvCacheEntry {}
+impl GpuKvCacheEntry {
+    /// `KVCacheEntry::new` with room for `capacity` tokens per layer (scheme = DLLM_KV_TENSOR_B is the reference's quantizer)
+    pub fn with_capacity(layers: usize, hidden: usize, capacity: usize, prefill_bits: u8, decode_bits: u8, scheme: i32) -> anyhow::Result<Self> {
+        let g = gpu();
+        let mut raw = std::ptr::null_mut();
+        let rc = g.with(|c| unsafe { sys::dllm_kvcache_create(c, layers, hidden, capacity, prefill_bits, decode_bits, scheme, &mut raw) });
+        if rc != sys::DLLM_OK {
+            anyhow::bail!("dllm_kvcache_create: status {rc}: {}", g.last_error());
+        }
+        Ok(GpuKvCacheEntry { raw, layers, hidden })
+    }
+    fn info(&self) -> (usize, bool, u8, usize) {
+        let (mut s, mut p, mut b, mut m) = (0usize, 0i32, 0u8, 0usize);
+        unsafe { sys::dllm_kvcache_info(self.raw, &mut s, &mut p, &mut b, &mut m) };
+        (s, p != 0, b, m)
+    }
+    pub fn len(&self) -> usize { self.info().0 }
+    pub fn is_empty(&self) -> bool { self.len() == 0 }
+    pub fn get_current_quant_bits(&self) -> u8 { self.info().2 }
+    pub fn memory_usage(&self) -> usize { self.info().3 }
+    /// `transition_phase` / `set_phase` (lib.rs:207-238)
+    pub fn set_phase(&mut self, is_prefill: bool) -> anyhow::Result<()> {
+        let g = gpu();
+        let rc = g.with(|c| unsafe { sys::dllm_kvcache_set_phase(c, self.raw, is_prefill as i32) });
+        if rc != sys::DLLM_OK { anyhow::bail!("dllm_kvcache_set_phase: status {rc}: {}", g.last_error()); }
+        Ok(())
+    }
+    /// `decode_quant_bits = bits; decode_quantized = None` (lib.rs:899-903)
+    pub fn set_decode_bits(&mut self, bits: u8) -> anyhow::Result<()> {
+        let g = gpu();
+        let rc = g.with(|c| unsafe { sys::dllm_kvcache_set_decode_bits(c, self.raw, bits) });
+        if rc != sys::DLLM_OK { anyhow::bail!("dllm_kvcache_set_decode_bits: status {rc}: {}", g.last_error()); }
+        Ok(())
+    }
+    /// `update` on device tensors `[layers, seq, hidden]` (lib.rs:246-276); null pointers + the current length re-quantize the
+    /// entry's own tensors
+    pub unsafe fn update_dev(&mut self, keys_dev: *const f32, values_dev: *const f32, seq: usize) -> anyhow::Result<()> {
+        let g = gpu();
+        let rc = g.with(|c| sys::dllm_kvcache_update_dev(c, self.raw, keys_dev, values_dev, seq));
+        if rc != sys::DLLM_OK { anyhow::bail!("dllm_kvcache_update_dev: status {rc}: {}", g.last_error()); }
+        Ok(())
+    }
+    /// only `t_new` tokens per layer are new (per-token / fixed-scale entries quantize just those)
+    pub unsafe fn append_dev(&mut self, keys_new_dev: *const f32, values_new_dev: *const f32, t_new: usize) -> anyhow::Result<()> {
+        let g = gpu();
+        let rc = g.with(|c| sys::dllm_kvcache_append_dev(c, self.raw, keys_new_dev, values_new_dev, t_new));
+        if rc != sys::DLLM_OK { anyhow::bail!("dllm_kvcache_append_dev: status {rc}: {}", g.last_error()); }
+        Ok(())
+    }
+    /// `get_keys` / `get_values` decoded straight into the consumer's device buffers (either may be null)
+    pub unsafe fn get_dev(&self, keys_out_dev: *mut f32, values_out_dev: *mut f32) -> anyhow::Result<()> {
+        let g = gpu();
+        let rc = g.with(|c| sys::dllm_kvcache_get_dev(c, self.raw, keys_out_dev, values_out_dev));
+        if rc != sys::DLLM_OK { anyhow::bail!("dllm_kvcache_get_dev: status {rc}: {}", g.last_error()); }
+        Ok(())
+    }
+    /// drop-in `update(new_keys, new_values)` from host arrays
+    pub fn update(&mut self, new_keys: &Array3<f32>, new_values: &Array3<f32>) -> anyhow::Result<()> {
+        let g = gpu();
+        let (l, s, h) = new_keys.dim();
+        anyhow::ensure!(l == self.layers && h == self.hidden, "shape mismatch");
+        let (k, v) = (new_keys.as_standard_layout(), new_values.as_standard_layout());
+        let bytes = l * s * h * 4;
+        g.with(|c| unsafe {
+            let (mut dk, mut dv) = (std::ptr::null_mut(), std::ptr::null_mut());
+            let mut rc = sys::dllm_malloc(c, bytes.max(4), &mut dk);
+            if rc == sys::DLLM_OK { rc = sys::dllm_malloc(c, bytes.max(4), &mut dv); }
+            if rc == sys::DLLM_OK { rc = sys::dllm_memcpy_h2d(c, dk, k.as_ptr() as *const _, bytes); }
+            if rc == sys::DLLM_OK { rc = sys::dllm_memcpy_h2d(c, dv, v.as_ptr() as *const _, bytes); }
+            if rc == sys::DLLM_OK { rc = sys::dllm_kvcache_update_dev(c, self.raw, dk as *const f32, dv as *const f32, s); }
+            if rc == sys::DLLM_OK { rc = sys::dllm_ctx_sync(c); }
+            sys::dllm_free(c, dk);
+            sys::dllm_free(c, dv);
+            if rc != sys::DLLM_OK { anyhow::bail!("GpuKvCacheEntry::update: status {rc}"); }
+            Ok(())
+        })
+    }
+}
+impl Drop for GpuKvCacheEntry {
+    fn drop(&mut self) {
+        unsafe { sys::dllm_kvcache_destroy(self.raw) }
+    }
+}
