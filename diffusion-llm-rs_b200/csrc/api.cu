@@ -1025,7 +1025,7 @@ int32_t tp_allreduce_minmax(dllm_ctx *ctx, float *params_dev);
 int32_t tp_allgather_cols(dllm_ctx *ctx, const float *in, size_t M, size_t n_local, float *out);
 bool tp_p2p_regions(const dllm_ctx *ctx, size_t bytes_each, char **b0, char **b1, char **recv);
 void tp_p2p_peer_ptrs(const dllm_ctx *ctx, const void *local, void **out8);
-int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream);
+int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream, bool signal);
 
 // The two ping-pong activation buffers of a tensor-parallel tcgen05 stack: the halves of the peer-to-peer arena when it is
 // enabled and large enough (dllm_tp_p2p_enable: the row-parallel partial sums are then reduced in place by this library's
@@ -1050,8 +1050,10 @@ static bool tp_fused_rs_ok(const dllm_ctx *ctx, const dllm_qweight *w, size_t to
 }
 
 // x [tokens, K shard] -> recv buffers of all ranks (fused epilogue); then, on `stream`, recv -> dst [tokens, N] on every rank
+// gate_next: the reduce / gather kernel ends with per-source signals instead of a barrier and arms the NEXT dense kernel to gate its
+// activation loads on them (serial placement only: the consumer must follow on the same stream)
 static int32_t tp_row_linear_fused(dllm_ctx *ctx, const dllm_qweight *w, const void *x_bf16, size_t tokens, char *recv, void *dst,
-                                   cudaStream_t reduce_stream, cudaEvent_t gemm_done) {
+                                   cudaStream_t reduce_stream, cudaEvent_t gemm_done, bool gate_next = false) {
     UmmaRs rs;
     tp_p2p_peer_ptrs(ctx, recv, rs.recv);
     rs.world = ctx->tp_world; rs.rank = ctx->tp_rank; rs.rows = tokens / (size_t)ctx->tp_world;
@@ -1060,7 +1062,7 @@ static int32_t tp_row_linear_fused(dllm_ctx *ctx, const dllm_qweight *w, const v
         CUDA_TRY(ctx, cudaEventRecord(gemm_done, ctx->stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(reduce_stream, gemm_done, 0));
     }
-    return tp_reduce_gather(ctx, recv, dst, rs.rows, w->N, reduce_stream);
+    return tp_reduce_gather(ctx, recv, dst, rs.rows, w->N, reduce_stream, gate_next);
 }
 
 static int env_int(const char *name, int dflt) {
@@ -1215,7 +1217,12 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
         for (size_t l = 0; l < L; ++l) {
             const bool last = l + 1 == L;
             if (m->parallel[l] == 2 && !last && tp_fused_rs_ok(ctx, m->layers[l], tokens, recv0)) {
-                DLLM_TRY(tp_row_linear_fused(ctx, m->layers[l], cur, tokens, recv0, nxt, ctx->stream, nullptr));
+                // the all-gather half can run under the next GEMM when that one is a dense bf16-output kernel on whole 256-token
+                // tiles per slice (DLLM_TP_GATED=0 keeps the closing barrier: experiments)
+                const char *gsw = getenv("DLLM_TP_GATED");
+                const bool gate_next = !(gsw && atoi(gsw) == 0) && l + 2 < L &&
+                                       k_umma_gate_supported(ctx, m->layers[l + 1], tokens, ctx->tp_world, cur);
+                DLLM_TRY(tp_row_linear_fused(ctx, m->layers[l], cur, tokens, recv0, nxt, ctx->stream, nullptr, gate_next));
                 void *t = cur; cur = nxt; nxt = t;
                 continue;
             }

@@ -433,9 +433,11 @@ __device__ __forceinline__ void prepare_x_tiles(const float *__restrict__ x, uin
     // part of the pair [kb0, kb0 + n_kb) covers — a CTA whose range cuts a pair computes the same delta as its neighbour
     const uint32_t kbA0 = kb0 & ~1u;
     const uint32_t total = n_kb ? (((kb0 + n_kb + 1) >> 1) - (kb0 >> 1)) * MT * 8 : 0u;
+    XTRACE(20);
 #pragma unroll 1
     for (uint32_t base = tid & ~31u; base < total; base += UNR * nthreads) {
         float v[UNR][16];
+        XTRACE(21);
 #pragma unroll
         for (int j = 0; j < UNR; ++j) {
             const uint32_t idx = base + j * nthreads + (tid & 31);
@@ -1123,7 +1125,8 @@ int32_t launch_gemv_kbs(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, s
 
 template <int CB, int MT>
 int32_t launch_gemv_x(dllm_ctx *ctx, const dllm_qweight *qw, const float *x, size_t M, float *y) {
-    if (qw->k_blocks * (size_t)gemv_x_tile_bytes(MT) <= kXResident) return launch_gemv_kbs<CB, MT, true>(ctx, qw, x, M, y);
+    static const bool no_xr = getenv("DLLM_GEMV_XR") && atoi(getenv("DLLM_GEMV_XR")) == 0;      // experiments only
+    if (!no_xr && qw->k_blocks * (size_t)gemv_x_tile_bytes(MT) <= kXResident) return launch_gemv_kbs<CB, MT, true>(ctx, qw, x, M, y);
     return launch_gemv_kbs<CB, MT, false>(ctx, qw, x, M, y);
 }
 

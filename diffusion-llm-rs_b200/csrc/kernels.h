@@ -60,6 +60,8 @@ bool k_umma_supported(const dllm_qweight *qw, size_t M);
 // receive buffer [M, N] bf16 of the rank that owns those tokens (recv[r]: rank r's buffer as mapped here), row block `rank`
 struct UmmaRs { void *recv[8]; int world, rank; size_t rows; };
 bool k_umma_rs_supported(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, int world);
+// can the next k_qlinear_umma(ctx, qw, x, M, nullptr, y_bf16) run with ctx->gate_armed (flag-gated activation loads)?
+bool k_umma_gate_supported(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, int world, const void *y_bf16);
 int32_t k_qlinear_umma_rs(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M, const UmmaRs *rs);
 int32_t k_qlinear_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq_dev, size_t M, int32_t *y_i32_dev);
 bool k_umma_i8_supported(const dllm_qweight *qw, size_t M);

@@ -40,7 +40,8 @@ static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 b
 namespace {
 constexpr int kP2PMaxBlocks = 256;
 constexpr int kP2PMaxWorld = 16;
-constexpr size_t kP2PFlagBytes = 2 * kP2PMaxWorld * kP2PMaxBlocks * sizeof(uint32_t);
+constexpr size_t kP2PBarrierBytes = 2 * kP2PMaxWorld * kP2PMaxBlocks * sizeof(uint32_t);
+constexpr size_t kP2PFlagBytes = kP2PBarrierBytes + 256;      // + [world] arrival counters of the gated all-gather
 
 struct P2PArgs {
     unsigned char *base[kP2PMaxWorld];     // every rank's arena
@@ -153,8 +154,11 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
 // kernel sums the W row blocks (local loads only), and stores the finished rows into every rank's activation buffer (the
 // all-gather: W-1 peer stores per element).  NVLink carries (W-1)/W of the tensor per direction here — the other half went out
 // under the GEMM.  a.off = receive buffer, a.off2 = destination tensor [M, N], a.n16 = 16-byte vectors of one rank's slice.
+// signal != 0: no closing barrier — every block bumps, on every rank, the arrival counter of THIS rank once its rows have been
+// stored there; the consuming GEMM on each rank gates its loads of this rank's token slice on that counter (umma_gemm.cu), so
+// the all-gather runs under that GEMM instead of in front of it.
 template <int W, int U>
-__global__ void __launch_bounds__(512) p2p_reduce_gather_kernel(const P2PArgs a, size_t off2) {
+__global__ void __launch_bounds__(512) p2p_reduce_gather_kernel(const P2PArgs a, size_t off2, int signal) {
     p2p_barrier(a, 0, a.epoch);
     const size_t T = (size_t)gridDim.x * blockDim.x;
     const unsigned char *recv = a.base[a.rank] + a.off;
@@ -184,6 +188,69 @@ __global__ void __launch_bounds__(512) p2p_reduce_gather_kernel(const P2PArgs a,
                 if (r < a.world) st_relaxed_sys_v4(a.base[r] + off2 + ((size_t)a.rank * a.n16 + i + u * T) * 16, o);
         }
     }
+    if (signal) {
+        __syncthreads();
+        if ((int)threadIdx.x < a.world) {
+            __threadfence_system();
+            uint32_t *cnt = reinterpret_cast<uint32_t *>(a.base[threadIdx.x] + a.flag_off + kP2PBarrierBytes) + a.rank;
+            asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(cnt) : "memory");
+        }
+    } else {
+        p2p_barrier(a, 1, a.epoch + 1);
+    }
+}
+
+// The same reduce / all-gather with the peer stores issued as BULK copies: the finished rows are staged in shared memory
+// (2 x 16 KB) and leave as one cp.async.bulk per peer and 16 KB chunk.  16-byte st.global to peer memory travels as 32-byte
+// packets (measured 575 GB/s per direction = 64 % of the link's 900 GB/s, the payload share of a 32-byte packet); bulk copies move
+// full 128-byte lines.  (DLLM_P2P_BULK=0 selects the plain-store kernel above.)
+template <int W>
+__global__ void __launch_bounds__(256, 2) p2p_reduce_gather_bulk_kernel(const P2PArgs a, size_t off2) {
+    constexpr int U = W <= 4 ? 4 : 2, kChunk16 = 256 * U;      // 16-byte vectors per chunk = 16 KB (8 KB at 8 ranks: registers)
+    __shared__ __align__(128) uint4 stage[2][kChunk16];
+    p2p_barrier(a, 0, a.epoch);
+    const unsigned char *recv = a.base[a.rank] + a.off;
+    const size_t n_chunks = (a.n16 + kChunk16 - 1) / kChunk16;
+    uint32_t it = 0;
+    for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+        const uint32_t b = it & 1;
+        // the bulk copies that read this buffer two rounds ago have read it (each issuing thread waits for its own groups)
+        if ((int)threadIdx.x < a.world) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        const size_t i0 = c * kChunk16;
+        const uint32_t n_here = (uint32_t)(a.n16 - i0 < (size_t)kChunk16 ? a.n16 - i0 : (size_t)kChunk16);
+        uint4 v[U][W];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < a.world && u * 256 + threadIdx.x < n_here)
+                    v[u][r] = ld_relaxed_sys_v4(recv + ((size_t)r * a.n16 + i0 + u * 256 + threadIdx.x) * 16);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u * 256 + threadIdx.x >= n_here) break;
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < a.world) p2p_accumulate<true>(acc, v[u][r]);
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+            stage[b][u * 256 + threadIdx.x] = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
+                                                          *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk-copy engine
+        __syncthreads();
+        if ((int)threadIdx.x < a.world) {
+            unsigned char *dst = a.base[threadIdx.x] + off2 + ((size_t)a.rank * a.n16 + i0) * 16;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(&stage[b][0])), "r"(n_here * 16u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if ((int)threadIdx.x < a.world) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // written, not just read
     p2p_barrier(a, 1, a.epoch + 1);
 }
 
@@ -254,7 +321,7 @@ void tp_p2p_peer_ptrs(const dllm_ctx *ctx, const void *local, void **out8) {
 }
 
 // recv (this rank's receive buffer: [world][rows, N] bf16, filled by all ranks' fused epilogues) -> dst [world * rows, N] on every rank
-int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream) {
+int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream, bool signal) {
     const size_t slice = rows * N * 2;
     if (!p2p_covers(ctx, recv, slice * ctx->tp_world) || !p2p_covers(ctx, dst, slice * ctx->tp_world))
         DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "reduce-gather: buffers must lie in the peer-to-peer arena");
@@ -269,9 +336,28 @@ int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows
     a.rank = ctx->tp_rank; a.world = ctx->tp_world;
     a.err = ctx->p2p_err;
     const int blocks = p2p_blocks(ctx, stream != ctx->stream);
-    if (a.world <= 2) p2p_reduce_gather_kernel<2, 4><<<blocks, 512, 0, stream>>>(a, off2);
-    else if (a.world <= 4) p2p_reduce_gather_kernel<4, 2><<<blocks, 512, 0, stream>>>(a, off2);
-    else p2p_reduce_gather_kernel<8, 1><<<blocks, 512, 0, stream>>>(a, off2);
+    // (bulk-copy peer stores measured no faster than 16-byte stores at 2 and 4 ranks: opt-in, DLLM_P2P_BULK=1)
+    static const bool bulk = getenv("DLLM_P2P_BULK") && atoi(getenv("DLLM_P2P_BULK")) == 1;
+    if (signal) {
+        // the consumer is armed with the value the counters reach once every block of this launch has signalled
+        ctx->gate_signals += (uint32_t)blocks;
+        ctx->gate_counters = reinterpret_cast<const uint32_t *>((const char *)ctx->p2p_arena + ctx->p2p_bytes + kP2PBarrierBytes);
+        ctx->gate_target = ctx->gate_signals;
+        ctx->gate_rows = rows;
+        ctx->gate_armed = true;
+    }
+    if (bulk && !signal) {
+        // 256-thread blocks with <= 32 KB of staging, two per SM; every block must be resident at once (a block waits for the
+        // peers' block of the same index): alone on the GPU one per SM, under a dense kernel two per SM that kernel leaves free
+        const int reserve = ctx->sm_limit > 0 ? ctx->sm_count - ctx->sm_limit : 0;
+        int b2 = stream != ctx->stream ? 2 * (reserve > 0 ? reserve : 4) : ctx->sm_count;
+        if (b2 > kP2PMaxBlocks) b2 = kP2PMaxBlocks;
+        if (a.world <= 2) p2p_reduce_gather_bulk_kernel<2><<<b2, 256, 0, stream>>>(a, off2);
+        else if (a.world <= 4) p2p_reduce_gather_bulk_kernel<4><<<b2, 256, 0, stream>>>(a, off2);
+        else p2p_reduce_gather_bulk_kernel<8><<<b2, 256, 0, stream>>>(a, off2);
+    } else if (a.world <= 2) p2p_reduce_gather_kernel<2, 4><<<blocks, 512, 0, stream>>>(a, off2, signal ? 1 : 0);
+    else if (a.world <= 4) p2p_reduce_gather_kernel<4, 2><<<blocks, 512, 0, stream>>>(a, off2, signal ? 1 : 0);
+    else p2p_reduce_gather_kernel<8, 1><<<blocks, 512, 0, stream>>>(a, off2, signal ? 1 : 0);
     LAUNCH_CHECK(ctx);
     ctx->p2p_calls++;
     return DLLM_OK;
@@ -387,6 +473,7 @@ static void p2p_release(dllm_ctx *ctx) {
     cudaFree(ctx->p2p_arena);
     cudaFree(ctx->p2p_err);
     ctx->p2p_arena = nullptr; ctx->p2p_err = nullptr; ctx->p2p_bytes = 0;
+    ctx->gate_armed = false; ctx->gate_counters = nullptr; ctx->gate_signals = 0;
     for (auto &q : ctx->p2p_peer) q = nullptr;
     cudaGetLastError();
 }
@@ -461,6 +548,7 @@ int32_t dllm_tp_p2p_enable(dllm_ctx *ctx, size_t arena_bytes) {
     ctx->p2p_bytes = arena_bytes;
     ctx->p2p_err = err;
     ctx->p2p_epoch = 0;
+    ctx->gate_signals = 0; ctx->gate_armed = false; ctx->gate_counters = nullptr;
     return DLLM_OK;
 }
 

@@ -1124,6 +1124,16 @@ struct Pair2Args {
     // over NVLink into the RECEIVE buffer of the rank that owns those tokens (rank o owns tokens [o*rs_rows, (o+1)*rs_rows)), row
     // block `rs_rank` of it: one bulk tensor store per q-row block, straight from the staging buffer into peer memory
     uint32_t rs_world, rs_rank, rs_rows;
+    // token-tile rotation: tile index t covers token tile (t / n_pairs + mt_rot) % m_tiles.  Under tensor parallelism every rank
+    // starts at its OWN token slice: the fused reduce-scatter then pushes to a different owner from every rank at any time
+    // (no incast on rank 0's links), and a gated consumer works on the rows it already holds while the others' arrive
+    uint32_t mt_rot;
+    // gated activation loads (the all-gather half of the exchange runs UNDER this GEMM): before the first load of a token tile of
+    // slice s != gate_self the loader waits until gate[s] — a counter in this rank's arena that rank s's reduce / gather kernel
+    // bumps once per block after its rows have landed here — has reached gate_target
+    const uint32_t *gate;
+    uint32_t gate_target, gate_rows, gate_self;
+    unsigned int *gate_err;
     uint32_t dbg;              // timing experiments only (DLLM_UMMA_DBG): 1 skip MMAs, 2 skip dequant math, 8 skip activation loads, 64 skip stores
     long long *trace;          // dbg & 128: clock64 stamps of cluster 0's leader CTA: [role 0..7][256]
 };
@@ -1276,8 +1286,31 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         asm volatile("griddepcontrol.wait;" ::: "memory");
         const uint32_t xfull_leader = leader_addr(xfull);
         uint32_t it = 0;
+        uint32_t gate_ok = a.gate_self;
         for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
-            const uint32_t mt = tile / a.n_pairs;
+            const uint32_t mt = (tile / a.n_pairs + a.mt_rot) % a.m_tiles;
+            if (a.gate != nullptr) {
+                const uint32_t slice = (mt * ntok) / a.gate_rows;
+                if (slice != a.gate_self && slice != gate_ok) {
+                    // the rows of this slice are being stored into this GPU's activation buffer by rank `slice` right now
+                    const uint32_t *flag = a.gate + slice;
+                    unsigned long long t0 = 0;
+                    uint32_t spins = 0;
+                    for (;;) {
+                        uint32_t v;
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                        if ((int32_t)(v - a.gate_target) >= 0) break;
+                        if ((++spins & 0xff) == 0) {
+                            unsigned long long now;
+                            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                            if (t0 == 0) t0 = now;
+                            else if (now - t0 > 4000000000ull) { if (lane == 0) atomicExch(a.gate_err, 100u + slice); break; }
+                        }
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");     // the peer's generic-proxy stores -> this CTA's bulk tensor loads
+                    gate_ok = slice;
+                }
+            }
             for (uint32_t kb = 0; kb < KB; kb += KBS, ++it) {
                 const uint32_t s = it % A, ph = (it / A) & 1;
                 mbar_wait(xempty + s, ph ^ 1);
@@ -1429,7 +1462,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         const size_t ldy = a.N;
         uint32_t n_item = 0;
         for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
-            const uint32_t mt = tile / a.n_pairs, nc = tile % a.n_pairs;
+            const uint32_t mt = (tile / a.n_pairs + a.mt_rot) % a.m_tiles, nc = tile % a.n_pairs;
             const uint32_t tph = n_item & 1;
             const uint32_t nt = 2 * nc + rank;
             const uint32_t n = nt * 128 + quarter * 32 + lane;
@@ -1768,10 +1801,23 @@ int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_b
     const int ntok_env = ntok_s ? atoi(ntok_s) : 0;
     a.ntok = (ntok_env >= 32 && ntok_env <= 256 && ntok_env % 32 == 0) ? (uint32_t)ntok_env : pair2_pick_ntok(M, a.n_pairs, pairs_hw);
     a.rs_world = 0; a.rs_rank = 0; a.rs_rows = 1;
+    a.mt_rot = 0;
+    a.gate = nullptr; a.gate_target = 0; a.gate_rows = 1; a.gate_self = 0; a.gate_err = nullptr;
     if (rsd) {
         // fused reduce-scatter: 64-row store blocks must not straddle two owners' token ranges
         a.ntok = 256;
         a.rs_world = (uint32_t)rsd->world; a.rs_rank = (uint32_t)rsd->rank; a.rs_rows = (uint32_t)rsd->rows;
+        a.mt_rot = (uint32_t)(((size_t)rsd->rank * rsd->rows) / 256);
+    }
+    if (ctx->gate_armed) {
+        // the producer of this GEMM's activations is still delivering the other ranks' token slices (tp.cu): whole 256-token
+        // tiles per slice, own slice first
+        ctx->gate_armed = false;
+        if (ctx->gate_rows % 256 != 0 || M % ctx->gate_rows != 0) DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "gated GEMM: slices must be multiples of 256 tokens");
+        a.ntok = 256;
+        a.gate = ctx->gate_counters; a.gate_target = ctx->gate_target; a.gate_rows = (uint32_t)ctx->gate_rows;
+        a.gate_self = (uint32_t)ctx->tp_rank; a.gate_err = ctx->p2p_err;
+        a.mt_rot = (uint32_t)(((size_t)ctx->tp_rank * ctx->gate_rows) / 256);
     }
     a.m_tiles = (uint32_t)((M + a.ntok - 1) / a.ntok);
     a.tiles = a.n_pairs * a.m_tiles;
@@ -1877,6 +1923,10 @@ int32_t launch_umma_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const void *x, s
     static const int ntok_env = getenv("DLLM_UMMA_NTOK") ? atoi(getenv("DLLM_UMMA_NTOK")) : 0;     // experiments only
     if constexpr (CB != 8) {
         if (pair2_applicable(ctx, qw, M, y_f32, y_bf16)) return launch_umma_pair2<CB>(ctx, qw, x, M, y_f32, y_bf16);
+    }
+    if (ctx->gate_armed) {
+        ctx->gate_armed = false;
+        DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "gated activations handed to a kernel that cannot wait for them (k_umma_gate_supported was not consulted)");
     }
     if (M <= 16) return launch_umma<CB, 16, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
     if (M <= 32) return launch_umma<CB, 32, 2, kNDQ>(ctx, qw, x, M, y_f32, y_bf16);
@@ -1993,6 +2043,14 @@ bool k_umma_rs_supported(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, 
     const uint32_t n_pairs = (uint32_t)((qw->n_tiles + 1) / 2);
     const uint32_t pairs_hw = (uint32_t)(ctx->sm_limit > 0 && ctx->sm_limit < ctx->sm_count ? ctx->sm_limit : ctx->sm_count) / 2;
     return (uint64_t)((M + 255) / 256) * n_pairs >= pairs_hw / 2;
+}
+
+// a GEMM whose activation rows of the other ranks' token slices may still be arriving (flag-gated loads): the dense CTA-pair
+// kernel with bf16 output and whole 256-token tiles per slice
+bool k_umma_gate_supported(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, int world, const void *y_bf16) {
+    if (!qw || world < 2 || M % (size_t)world != 0 || (M / world) % 256 != 0 || wl_container_bits(qw->bits) == 8) return false;
+    if (!(qw->K % 8 == 0 && qw->group % WL_TILE_K == 0 && qw->int_zps)) return false;
+    return pair2_applicable(ctx, qw, M, nullptr, y_bf16);
 }
 
 int32_t k_qlinear_umma_rs(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M, const UmmaRs *rs) {

@@ -13,14 +13,15 @@ except Exception:
     hbm = 6650.0
 stream = torch.cuda.Stream()
 ctx = dllm_b200.Context(0, stream=stream.cuda_stream)
-tag = {k: v for k, v in os.environ.items() if k.startswith("DLLM_GEMV")}
+tag = {k: v for k, v in os.environ.items() if k.startswith("DLLM_GEMV") or k.startswith("DLLM_BENCH")}
+PATH = int(os.environ.get("DLLM_BENCH_PATH", dllm_b200.PATH_GEMV))
 for KN in shapes:
     K = N = KN
     w = torch.randn(K, N, device="cuda") * 0.02
     torch.cuda.synchronize()
     for bits in bitss:
         wbytes = K * N * bits // 8
-        npool = max(4, -(-400_000_000 // wbytes))
+        npool = int(os.environ["DLLM_GEMV_POOL"]) if os.environ.get("DLLM_GEMV_POOL") else max(4, -(-400_000_000 // wbytes))
         pool = [QWeight.quantize_dev(ctx, w.data_ptr(), K, N, bits, 128) for _ in range(npool)]
         ctx.sync()
         for M in Ms:
@@ -28,12 +29,12 @@ for KN in shapes:
             torch.cuda.synchronize()
             with torch.cuda.stream(stream):
                 for i in range(npool):
-                    pool[i].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
+                    pool[i].forward_dev(x.data_ptr(), M, y.data_ptr(), PATH)
                 stream.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
                 for i in range(16):
-                    pool[i % npool].forward_dev(x.data_ptr(), M, y.data_ptr(), dllm_b200.PATH_GEMV)
+                    pool[i % npool].forward_dev(x.data_ptr(), M, y.data_ptr(), PATH)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(stream):
                 g.replay(); stream.synchronize()

@@ -101,14 +101,15 @@ lo, hi = chk.clone(), chk.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 say(what="ranks_bit_identical", same=bool(lo.item() == hi.item()))
 
-for fused, chunks, reserve in (("1", 1, 0), ("1", 2, 8), ("1", 2, 16), ("1", 4, 16), ("0", 1, 0), ("0", 2, 16)):
+for fused, gated, chunks, reserve in (("1", "1", 1, 0), ("1", "0", 1, 0), ("1", "0", 2, 8), ("0", "0", 1, 0)):
     if tokens < chunks * 512: continue
     os.environ["DLLM_TP_FUSED_RS"] = fused
+    os.environ["DLLM_TP_GATED"] = gated
     ctx._ck(lib.dllm_tp_configure(ctx.h, chunks, reserve if chunks > 1 else 0, 0))
     x.copy_(x0); ms_c = tm.run(step, 4, 2)
     ctx._ck(lib.dllm_tp_configure(ctx.h, chunks, reserve if chunks > 1 else 0, 1))
     ms_n = tm.run(step, 3, 1)
-    say(what="tp_step", world=world, p2p=ok, fused_rs=fused, chunks=chunks, reserve=reserve, ms=ms_c, gemm_only_ms=ms_n, exposed_ms=ms_c - ms_n,
+    say(what="tp_step", world=world, p2p=ok, fused_rs=fused, gated=gated, chunks=chunks, reserve=reserve, ms=ms_c, gemm_only_ms=ms_n, exposed_ms=ms_c - ms_n,
         efficiency=ms_single / (world * ms_c), finite=bool(torch.isfinite(x).all()))
 ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
 say(what="p2p_status_end", status=tpg.p2p_status())

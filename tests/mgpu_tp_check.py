@@ -96,7 +96,7 @@ def main():
         # wide enough for the dense CTA-pair kernel, so that the row-parallel layers run with the reduce-scatter fused into the
         # GEMM epilogue (bulk tensor stores into the owners' receive buffers over NVLink) + the reduce / all-gather kernel
         hid2 = 2048
-        dims2 = [hid2, 4096, hid2, hid2, hid2]
+        dims2 = [hid2, 4096, hid2, 4096, hid2]
         shapes2 = list(zip(dims2[:-1], dims2[1:]))
         ws_b = [(rng.standard_normal(s_) / np.sqrt(s_[0])).astype(F) for s_ in shapes2]
         bs_b = [(rng.standard_normal(s_[1]) * 0.1).astype(F) for s_ in shapes2]
@@ -110,8 +110,10 @@ def main():
             layers_b.append(QWeight.quantize(ctx, np.ascontiguousarray(wsh), 4, 128, bsh))
         model_b = QuantizedDiffusionModel(layers_b, hid2, ctx=ctx, path=dllm_b200.PATH_UMMA)
         tpg.set_plan(model_b, plan_b)
-        for fused, chunks, reserve in (("1", 1, 0), ("1", 2, 16), ("0", 1, 0), ("0", 2, 16)):
+        # gated = the all-gather half runs under the NEXT GEMM (its activation loads wait on per-source arrival counters)
+        for fused, gated, chunks, reserve in (("1", "1", 1, 0), ("1", "0", 1, 0), ("1", "1", 2, 16), ("0", "0", 1, 0), ("0", "0", 2, 16)):
             os.environ["DLLM_TP_FUSED_RS"] = fused
+            os.environ["DLLM_TP_GATED"] = gated
             ctx._ck(lib.dllm_tp_configure(ctx.h, chunks, reserve, 0))
             n0 = tpg.p2p_status()["allreduces"]
             y = model_b.forward(xb)
@@ -121,10 +123,11 @@ def main():
             lo, hi = t.clone(), t.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-            print(f"rank {rank} p2p fused_rs={fused} chunks={chunks} rel-vs-oracle {rel:.3e} kernel calls {st['allreduces'] - n0} same-bits {bool(lo.item() == hi.item())}", flush=True)
+            print(f"rank {rank} p2p fused_rs={fused} gated={gated} chunks={chunks} rel-vs-oracle {rel:.3e} kernel calls {st['allreduces'] - n0} same-bits {bool(lo.item() == hi.item())}", flush=True)
             ok = ok and rel <= 2e-2 and np.all(np.isfinite(y)) and st["allreduces"] > n0 and st["timed_out"] == 0 and lo.item() == hi.item()
         ctx._ck(lib.dllm_tp_configure(ctx.h, 0, -1, 0))
         os.environ.pop("DLLM_TP_FUSED_RS", None)
+        os.environ.pop("DLLM_TP_GATED", None)
         model_b.close()
         tpg.disable_p2p()
     else:
