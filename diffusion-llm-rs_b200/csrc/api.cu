@@ -1025,7 +1025,7 @@ int32_t tp_allreduce_minmax(dllm_ctx *ctx, float *params_dev);
 int32_t tp_allgather_cols(dllm_ctx *ctx, const float *in, size_t M, size_t n_local, float *out);
 bool tp_p2p_regions(const dllm_ctx *ctx, size_t bytes_each, char **b0, char **b1, char **recv);
 void tp_p2p_peer_ptrs(const dllm_ctx *ctx, const void *local, void **out8);
-int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream, bool signal);
+int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream, int signal);
 
 // The two ping-pong activation buffers of a tensor-parallel tcgen05 stack: the halves of the peer-to-peer arena when it is
 // enabled and large enough (dllm_tp_p2p_enable: the row-parallel partial sums are then reduced in place by this library's
@@ -1053,7 +1053,7 @@ static bool tp_fused_rs_ok(const dllm_ctx *ctx, const dllm_qweight *w, size_t to
 // gate_next: the reduce / gather kernel ends with per-source signals instead of a barrier and arms the NEXT dense kernel to gate its
 // activation loads on them (serial placement only: the consumer must follow on the same stream)
 static int32_t tp_row_linear_fused(dllm_ctx *ctx, const dllm_qweight *w, const void *x_bf16, size_t tokens, char *recv, void *dst,
-                                   cudaStream_t reduce_stream, cudaEvent_t gemm_done, bool gate_next = false) {
+                                   cudaStream_t reduce_stream, cudaEvent_t gemm_done, int gate_next = 0) {
     UmmaRs rs;
     tp_p2p_peer_ptrs(ctx, recv, rs.recv);
     rs.world = ctx->tp_world; rs.rank = ctx->tp_rank; rs.rows = tokens / (size_t)ctx->tp_world;
@@ -1196,9 +1196,8 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
         // their partial sums from the GEMM epilogue and only the all-gather half is left at the boundary — one launch per
         // layer, 47.1 (token chunks + overlap: 50.9, chunked GEMMs cost more than the overlap hides); with NCCL the overlap
         // pays: 2 chunks 50.9 against 53.2
-        //   at TP4 / TP8 the exchange outweighs the GEMMs and two token chunks with the gather half on the second stream win
-        //   (35.3 against 36.7 ms at TP4, 30.5 against 35.5 at TP8)
-        const int chunks = ctx->tp_chunks > 0 ? ctx->tp_chunks : env_int("DLLM_TP_CHUNKS", ctx->p2p_arena && ctx->tp_world <= 2 ? 1 : 2);
+        //   the same holds at TP4 once every rank starts at its own token slice (32.8 against 37.0 ms)
+        const int chunks = ctx->tp_chunks > 0 ? ctx->tp_chunks : env_int("DLLM_TP_CHUNKS", ctx->p2p_arena ? 1 : 2);
         if (chunks > 1 && tokens >= (size_t)chunks * 512) return forward_tp_overlapped(ctx, m, x_dev, tokens, out_dev, chunks);
     }
     if (all_umma && (!any_parallel || no_gather)) {
@@ -1214,25 +1213,53 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
         }
         DLLM_TRY(k_f32_to_bf16(ctx, x_dev, tokens * m->layers[0]->K, buf0));
         void *cur = buf0, *nxt = buf1;
+        bool comm_pending = false;         // a reduce / gather kernel on the communication stream has not been joined yet
         for (size_t l = 0; l < L; ++l) {
             const bool last = l + 1 == L;
             if (m->parallel[l] == 2 && !last && tp_fused_rs_ok(ctx, m->layers[l], tokens, recv0)) {
                 // the all-gather half can run under the next GEMM when that one is a dense bf16-output kernel on whole 256-token
                 // tiles per slice (DLLM_TP_GATED=0 keeps the closing barrier: experiments)
+                // DLLM_TP_GATED: 1 (default) = the reduce / gather kernel runs in front of that GEMM and ends with arrival counters
+                // instead of a barrier: its tail (the peers' rows still in flight) overlaps the GEMM's first tiles; 2 = the kernel
+                // runs on the communication stream UNDER the GEMM, which leaves it 16 SMs and gates its own slice too (measured
+                // no faster at TP2: 49.8 against 48.8-49.5 ms — the GEMM on 132 SMs and the lost dependent-launch overlap cost
+                // what the overlap gains); 0 = closing barrier
                 const char *gsw = getenv("DLLM_TP_GATED");
-                const bool gate_next = !(gsw && atoi(gsw) == 0) && l + 2 < L &&
-                                       k_umma_gate_supported(ctx, m->layers[l + 1], tokens, ctx->tp_world, cur);
-                DLLM_TRY(tp_row_linear_fused(ctx, m->layers[l], cur, tokens, recv0, nxt, ctx->stream, nullptr, gate_next));
+                int gate_next = gsw ? atoi(gsw) : 1;
+                if (gate_next < 0 || gate_next > 2 ||
+                    !(l + 2 < L && m->parallel[l + 1] == 1 && k_umma_gate_supported(ctx, m->layers[l + 1], tokens, ctx->tp_world, cur)))
+                    gate_next = 0;
+                if (gate_next == 2) {
+                    if (!ctx->comm_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+                    while (ctx->tp_ev.size() < 2) {
+                        cudaEvent_t e;
+                        CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                        ctx->tp_ev.push_back(e);
+                    }
+                    DLLM_TRY(tp_row_linear_fused(ctx, m->layers[l], cur, tokens, recv0, nxt, ctx->comm_stream, ctx->tp_ev[0], 2));
+                    CUDA_TRY(ctx, cudaEventRecord(ctx->tp_ev[1], ctx->comm_stream));
+                    comm_pending = true;
+                    ctx->sm_limit = ctx->sm_count - 16;            // for the gated GEMM that follows (reset right after it)
+                } else {
+                    DLLM_TRY(tp_row_linear_fused(ctx, m->layers[l], cur, tokens, recv0, nxt, ctx->stream, nullptr, gate_next));
+                }
                 void *t = cur; cur = nxt; nxt = t;
                 continue;
             }
-            DLLM_TRY(k_qlinear_umma(ctx, m->layers[l], cur, tokens, last ? out_dev : nullptr, last ? nullptr : nxt));
+            {
+                const bool under_gather = ctx->sm_limit != 0;      // this GEMM runs next to the reduce / gather kernel it is gated on
+                const int32_t rc_l = k_qlinear_umma(ctx, m->layers[l], cur, tokens, last ? out_dev : nullptr, last ? nullptr : nxt);
+                ctx->sm_limit = 0;
+                if (under_gather) ctx->no_pdl_once = true;         // the next GEMM must not squat on the SMs left to that kernel
+                DLLM_TRY(rc_l);
+            }
             if (m->parallel[l] == 2) {
                 if (last) DLLM_TRY(tp_allreduce(ctx, out_dev, tokens * m->layers[l]->N));
                 else DLLM_TRY(tp_allreduce_bf16(ctx, nxt, tokens * m->layers[l]->N));
             }
             void *t = cur; cur = nxt; nxt = t;
         }
+        if (comm_pending) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->tp_ev[1], 0));
         return DLLM_OK;
     }
     // General path: f32 activations at the layer boundaries (SIMT layers, and tensor-parallel stacks

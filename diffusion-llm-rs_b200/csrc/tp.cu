@@ -41,7 +41,8 @@ namespace {
 constexpr int kP2PMaxBlocks = 256;
 constexpr int kP2PMaxWorld = 16;
 constexpr size_t kP2PBarrierBytes = 2 * kP2PMaxWorld * kP2PMaxBlocks * sizeof(uint32_t);
-constexpr size_t kP2PFlagBytes = kP2PBarrierBytes + 256;      // + [world] arrival counters of the gated all-gather
+constexpr int kP2PGateSub = 8;                                 // arrival counters per source rank (sub-slices of its token slice)
+constexpr size_t kP2PFlagBytes = kP2PBarrierBytes + kP2PMaxWorld * kP2PGateSub * sizeof(uint32_t);   // + the gated all-gather's counters
 
 struct P2PArgs {
     unsigned char *base[kP2PMaxWorld];     // every rank's arena
@@ -154,50 +155,55 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
 // kernel sums the W row blocks (local loads only), and stores the finished rows into every rank's activation buffer (the
 // all-gather: W-1 peer stores per element).  NVLink carries (W-1)/W of the tensor per direction here — the other half went out
 // under the GEMM.  a.off = receive buffer, a.off2 = destination tensor [M, N], a.n16 = 16-byte vectors of one rank's slice.
-// signal != 0: no closing barrier — every block bumps, on every rank, the arrival counter of THIS rank once its rows have been
-// stored there; the consuming GEMM on each rank gates its loads of this rank's token slice on that counter (umma_gemm.cu), so
-// the all-gather runs under that GEMM instead of in front of it.
+// signal = G > 0: no closing barrier.  The slice is processed in G equal sub-slices; after each one every block bumps, on every
+// rank, arrival counter [this rank][g] — the consuming GEMM on each rank gates its loads of those token rows on it
+// (umma_gemm.cu), so the all-gather runs under that GEMM instead of in front of it, and the GEMM can start on sub-slice 0 while
+// the rest is still being reduced.
 template <int W, int U>
 __global__ void __launch_bounds__(512) p2p_reduce_gather_kernel(const P2PArgs a, size_t off2, int signal) {
     p2p_barrier(a, 0, a.epoch);
     const size_t T = (size_t)gridDim.x * blockDim.x;
     const unsigned char *recv = a.base[a.rank] + a.off;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n16; i += U * T) {
-        uint4 v[U][W];
+    const int G = signal > 0 ? signal : 1;
+    const size_t part = a.n16 / G;                              // (the host picks G so that it divides the slice's rows)
+    for (int g = 0; g < G; ++g) {
+        const size_t p0 = (size_t)g * part, p1 = g + 1 == G ? a.n16 : p0 + part;
+        for (size_t i = p0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p1; i += U * T) {
+            uint4 v[U][W];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+            for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int r = 0; r < W; ++r)
-                if (r < a.world && i + u * T < a.n16) v[u][r] = ld_relaxed_sys_v4(recv + ((size_t)r * a.n16 + i + u * T) * 16);
+                for (int r = 0; r < W; ++r)
+                    if (r < a.world && i + u * T < p1) v[u][r] = ld_relaxed_sys_v4(recv + ((size_t)r * a.n16 + i + u * T) * 16);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (i + u * T >= a.n16) break;
-            float acc[8];
+            for (int u = 0; u < U; ++u) {
+                if (i + u * T >= p1) break;
+                float acc[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
-            for (int r = 0; r < W; ++r)
-                if (r < a.world) p2p_accumulate<true>(acc, v[u][r]);                     // rank order, as in the two-shot kernel
-            __nv_bfloat162 h[4];
+                for (int r = 0; r < W; ++r)
+                    if (r < a.world) p2p_accumulate<true>(acc, v[u][r]);                 // rank order, as in the two-shot kernel
+                __nv_bfloat162 h[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
-            const uint4 o = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
-                                       *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
+                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+                const uint4 o = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
+                                           *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
 #pragma unroll
-            for (int r = 0; r < W; ++r)
-                if (r < a.world) st_relaxed_sys_v4(a.base[r] + off2 + ((size_t)a.rank * a.n16 + i + u * T) * 16, o);
+                for (int r = 0; r < W; ++r)
+                    if (r < a.world) st_relaxed_sys_v4(a.base[r] + off2 + ((size_t)a.rank * a.n16 + i + u * T) * 16, o);
+            }
+        }
+        if (signal > 0) {
+            __syncthreads();
+            if ((int)threadIdx.x < a.world) {
+                __threadfence_system();
+                uint32_t *cnt = reinterpret_cast<uint32_t *>(a.base[threadIdx.x] + a.flag_off + kP2PBarrierBytes) + a.rank * kP2PGateSub + g;
+                asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(cnt) : "memory");
+            }
         }
     }
-    if (signal) {
-        __syncthreads();
-        if ((int)threadIdx.x < a.world) {
-            __threadfence_system();
-            uint32_t *cnt = reinterpret_cast<uint32_t *>(a.base[threadIdx.x] + a.flag_off + kP2PBarrierBytes) + a.rank;
-            asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(cnt) : "memory");
-        }
-    } else {
-        p2p_barrier(a, 1, a.epoch + 1);
-    }
+    if (signal <= 0) p2p_barrier(a, 1, a.epoch + 1);
 }
 
 // The same reduce / all-gather with the peer stores issued as BULK copies: the finished rows are staged in shared memory
@@ -321,7 +327,10 @@ void tp_p2p_peer_ptrs(const dllm_ctx *ctx, const void *local, void **out8) {
 }
 
 // recv (this rank's receive buffer: [world][rows, N] bf16, filled by all ranks' fused epilogues) -> dst [world * rows, N] on every rank
-int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream, bool signal) {
+// signal: 0 = closing barrier; 1 = arrival counters, consumer follows on the same stream (its own slice needs no gate);
+// 2 = arrival counters with the kernel on the communication stream UNDER the consumer (32 blocks on the 16 SMs the consumer leaves
+// free keep NVLink as busy as 128 do: scripts/p2p_blocks_probe.py; the consumer gates its own slice too)
+int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows, size_t N, cudaStream_t stream, int signal) {
     const size_t slice = rows * N * 2;
     if (!p2p_covers(ctx, recv, slice * ctx->tp_world) || !p2p_covers(ctx, dst, slice * ctx->tp_world))
         DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "reduce-gather: buffers must lie in the peer-to-peer arena");
@@ -335,15 +344,20 @@ int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows
     ctx->p2p_epoch += 2;
     a.rank = ctx->tp_rank; a.world = ctx->tp_world;
     a.err = ctx->p2p_err;
-    const int blocks = p2p_blocks(ctx, stream != ctx->stream);
+    const int blocks = signal == 2 ? 32 : p2p_blocks(ctx, stream != ctx->stream);
     // (bulk-copy peer stores measured no faster than 16-byte stores at 2 and 4 ranks: opt-in, DLLM_P2P_BULK=1)
     static const bool bulk = getenv("DLLM_P2P_BULK") && atoi(getenv("DLLM_P2P_BULK")) == 1;
+    int G = 0;
     if (signal) {
+        // sub-slices of whole 256-token tiles: 4 where the slice allows
+        G = rows % 1024 == 0 ? 4 : rows % 512 == 0 ? 2 : 1;
         // the consumer is armed with the value the counters reach once every block of this launch has signalled
         ctx->gate_signals += (uint32_t)blocks;
         ctx->gate_counters = reinterpret_cast<const uint32_t *>((const char *)ctx->p2p_arena + ctx->p2p_bytes + kP2PBarrierBytes);
         ctx->gate_target = ctx->gate_signals;
         ctx->gate_rows = rows;
+        ctx->gate_sub = rows / (size_t)G;
+        ctx->gate_self = signal == 2 ? 0xffffffffu : (uint32_t)ctx->tp_rank;
         ctx->gate_armed = true;
     }
     if (bulk && !signal) {
@@ -355,9 +369,9 @@ int32_t tp_reduce_gather(dllm_ctx *ctx, const void *recv, void *dst, size_t rows
         if (a.world <= 2) p2p_reduce_gather_bulk_kernel<2><<<b2, 256, 0, stream>>>(a, off2);
         else if (a.world <= 4) p2p_reduce_gather_bulk_kernel<4><<<b2, 256, 0, stream>>>(a, off2);
         else p2p_reduce_gather_bulk_kernel<8><<<b2, 256, 0, stream>>>(a, off2);
-    } else if (a.world <= 2) p2p_reduce_gather_kernel<2, 4><<<blocks, 512, 0, stream>>>(a, off2, signal ? 1 : 0);
-    else if (a.world <= 4) p2p_reduce_gather_kernel<4, 2><<<blocks, 512, 0, stream>>>(a, off2, signal ? 1 : 0);
-    else p2p_reduce_gather_kernel<8, 1><<<blocks, 512, 0, stream>>>(a, off2, signal ? 1 : 0);
+    } else if (a.world <= 2) p2p_reduce_gather_kernel<2, 4><<<blocks, 512, 0, stream>>>(a, off2, G);
+    else if (a.world <= 4) p2p_reduce_gather_kernel<4, 2><<<blocks, 512, 0, stream>>>(a, off2, G);
+    else p2p_reduce_gather_kernel<8, 1><<<blocks, 512, 0, stream>>>(a, off2, G);
     LAUNCH_CHECK(ctx);
     ctx->p2p_calls++;
     return DLLM_OK;

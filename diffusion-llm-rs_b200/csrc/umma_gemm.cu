@@ -1131,8 +1131,8 @@ struct Pair2Args {
     // gated activation loads (the all-gather half of the exchange runs UNDER this GEMM): before the first load of a token tile of
     // slice s != gate_self the loader waits until gate[s] — a counter in this rank's arena that rank s's reduce / gather kernel
     // bumps once per block after its rows have landed here — has reached gate_target
-    const uint32_t *gate;
-    uint32_t gate_target, gate_rows, gate_self;
+    const uint32_t *gate;             // [ranks][8] counters: [s][g] covers tokens [s*gate_rows + g*gate_sub, + gate_sub)
+    uint32_t gate_target, gate_rows, gate_sub, gate_self;
     unsigned int *gate_err;
     uint32_t dbg;              // timing experiments only (DLLM_UMMA_DBG): 1 skip MMAs, 2 skip dequant math, 8 skip activation loads, 64 skip stores
     long long *trace;          // dbg & 128: clock64 stamps of cluster 0's leader CTA: [role 0..7][256]
@@ -1286,14 +1286,15 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         asm volatile("griddepcontrol.wait;" ::: "memory");
         const uint32_t xfull_leader = leader_addr(xfull);
         uint32_t it = 0;
-        uint32_t gate_ok = a.gate_self;
+        uint32_t gate_ok = 0xffffffffu;
         for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
             const uint32_t mt = (tile / a.n_pairs + a.mt_rot) % a.m_tiles;
             if (a.gate != nullptr) {
-                const uint32_t slice = (mt * ntok) / a.gate_rows;
-                if (slice != a.gate_self && slice != gate_ok) {
-                    // the rows of this slice are being stored into this GPU's activation buffer by rank `slice` right now
-                    const uint32_t *flag = a.gate + slice;
+                const uint32_t tok = mt * ntok, slice = tok / a.gate_rows;
+                const uint32_t gidx = slice * 8u + (tok - slice * a.gate_rows) / a.gate_sub;
+                if (slice != a.gate_self && gidx != gate_ok) {
+                    // these rows are being stored into this GPU's activation buffer by rank `slice` right now
+                    const uint32_t *flag = a.gate + gidx;
                     unsigned long long t0 = 0;
                     uint32_t spins = 0;
                     for (;;) {
@@ -1308,7 +1309,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                         }
                     }
                     asm volatile("fence.proxy.async;" ::: "memory");     // the peer's generic-proxy stores -> this CTA's bulk tensor loads
-                    gate_ok = slice;
+                    gate_ok = gidx;
                 }
             }
             for (uint32_t kb = 0; kb < KB; kb += KBS, ++it) {
@@ -1714,7 +1715,8 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = no_pdl ? 0 : 1;
+        cfg.numAttrs = (no_pdl || ctx->no_pdl_once) ? 0 : 1;
+        ctx->no_pdl_once = false;
         CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, umma_qlinear_kernel<CB, NTOK, KBS, NDQ>, tmap, a));
     }
     LAUNCH_CHECK(ctx);
@@ -1802,7 +1804,7 @@ int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_b
     a.ntok = (ntok_env >= 32 && ntok_env <= 256 && ntok_env % 32 == 0) ? (uint32_t)ntok_env : pair2_pick_ntok(M, a.n_pairs, pairs_hw);
     a.rs_world = 0; a.rs_rank = 0; a.rs_rows = 1;
     a.mt_rot = 0;
-    a.gate = nullptr; a.gate_target = 0; a.gate_rows = 1; a.gate_self = 0; a.gate_err = nullptr;
+    a.gate = nullptr; a.gate_target = 0; a.gate_rows = 1; a.gate_sub = 1; a.gate_self = 0; a.gate_err = nullptr;
     if (rsd) {
         // fused reduce-scatter: 64-row store blocks must not straddle two owners' token ranges
         a.ntok = 256;
@@ -1816,7 +1818,8 @@ int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_b
         if (ctx->gate_rows % 256 != 0 || M % ctx->gate_rows != 0) DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "gated GEMM: slices must be multiples of 256 tokens");
         a.ntok = 256;
         a.gate = ctx->gate_counters; a.gate_target = ctx->gate_target; a.gate_rows = (uint32_t)ctx->gate_rows;
-        a.gate_self = (uint32_t)ctx->tp_rank; a.gate_err = ctx->p2p_err;
+        a.gate_sub = (uint32_t)ctx->gate_sub;
+        a.gate_self = ctx->gate_self; a.gate_err = ctx->p2p_err;
         a.mt_rot = (uint32_t)(((size_t)ctx->tp_rank * ctx->gate_rows) / 256);
     }
     a.m_tiles = (uint32_t)((M + a.ntok - 1) / a.ntok);
@@ -1889,7 +1892,10 @@ int32_t launch_umma_pair2(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_b
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
+    // (no_pdl_once: the kernel before this one leaves SMs free for a reduce / gather kernel it is waiting for — a dependent
+    //  launched early would occupy exactly those SMs and sit there at its dependency wait: deadlock until the gates time out)
+    cfg.numAttrs = (no_pdl || ctx->no_pdl_once) ? 0 : 1;
+    ctx->no_pdl_once = false;
     CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, umma_qlinear_pair2_kernel<CB, NDQ>, tmap, tmap_y, rsm, a));
     LAUNCH_CHECK(ctx);
     if (a.dbg & 128) {   // dump the timeline of cluster 0's leader (timing experiments only)

@@ -101,7 +101,7 @@ lo, hi = chk.clone(), chk.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 say(what="ranks_bit_identical", same=bool(lo.item() == hi.item()))
 
-for fused, gated, chunks, reserve in (("1", "1", 1, 0), ("1", "0", 1, 0), ("1", "0", 2, 8), ("0", "0", 1, 0)):
+for fused, gated, chunks, reserve in (("1", "2", 1, 0), ("1", "1", 1, 0), ("1", "0", 1, 0), ("0", "0", 1, 0), ("1", "2", 1, 0)):
     if tokens < chunks * 512: continue
     os.environ["DLLM_TP_FUSED_RS"] = fused
     os.environ["DLLM_TP_GATED"] = gated

@@ -111,7 +111,8 @@ def main():
         model_b = QuantizedDiffusionModel(layers_b, hid2, ctx=ctx, path=dllm_b200.PATH_UMMA)
         tpg.set_plan(model_b, plan_b)
         # gated = the all-gather half runs under the NEXT GEMM (its activation loads wait on per-source arrival counters)
-        for fused, gated, chunks, reserve in (("1", "1", 1, 0), ("1", "0", 1, 0), ("1", "1", 2, 16), ("0", "0", 1, 0), ("0", "0", 2, 16)):
+        #         (2: the reduce / gather kernel runs on the communication stream under that GEMM; 1: in front of it; 0: closing barrier)
+        for fused, gated, chunks, reserve in (("1", "2", 1, 0), ("1", "1", 1, 0), ("1", "0", 1, 0), ("1", "2", 2, 16), ("0", "0", 1, 0), ("0", "0", 2, 16)):
             os.environ["DLLM_TP_FUSED_RS"] = fused
             os.environ["DLLM_TP_GATED"] = gated
             ctx._ck(lib.dllm_tp_configure(ctx.h, chunks, reserve, 0))
