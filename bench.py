@@ -58,7 +58,10 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  One long-running
+    `nvidia-smi -lms 50` (a fresh process per sample takes longer than the whole timed region) started before the warm-up;
+    the summary uses the samples between mark_begin() and mark_end() — the timed steps plus the roofline pass, the same steps back
+    to back — and falls back to every sample taken under load (warm-up included) if the marked window caught fewer than two."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -66,34 +69,57 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.t0, self.t1, self.proc = gpu, [], None, None, None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu),
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+        except Exception:
+            pass
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def summary(self):
-        self.stop_flag = True
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        if self.proc is not None:
             try:
-                sm.append(float(r[1]))
-                mx = max(mx, float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                self.proc.terminate()
             except Exception:
-                continue
-        sm.sort()
+                pass
+        def digest(rows):
+            sm, mx, reasons = [], 0, set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1]))
+                    mx = max(mx, float(r[2]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                except Exception:
+                    continue
+            sm.sort()
+            return sm, mx, reasons
+        rows = list(self.rows)
+        inside = [x for x in rows if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1 + 0.05]
+        window = "timed region + roofline pass"
+        if len(inside) < 2:
+            # power draw well above idle = under load (warm-up, timed steps, roofline pass, end-to-end steps)
+            def loaded(r):
+                try:
+                    return float(r[1][3]) > 300.0
+                except Exception:
+                    return False
+            inside = [x for x in rows if loaded(x)] or rows
+            window = "all samples under load (warm-up .. end-to-end steps): the timed region is shorter than two sampling periods"
+        sm, mx, reasons = digest(inside)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------------------------
@@ -644,12 +670,13 @@ def run_ours(args, rank, world, local_rank):
         model.denoise_step_dev(x.data_ptr(), zs[i % 4].data_ptr(), t, BATCH, feat)
 
     # ---- headline: resident-in-HBM timing, nothing but the step's own launches on the stream ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             step(i)
     tm.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_begin()
     launches0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -671,7 +698,7 @@ def run_ours(args, rank, world, local_rank):
             step(i)
     nl, ms, fl, by = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
     ctx._ck(ctx._lib.dllm_profile_end(ctx.h, C.byref(nl), C.byref(ms), C.byref(fl), C.byref(by)))
-    clocks = sampler.summary()          # sampled over the timed region and the roofline pass: the same steps, back to back
+    sampler.mark_end()                  # the timed region and the roofline pass: the same steps, back to back
 
     # ---- end to end through the host-buffer C ABI call ----
     e2e_steps = max(2, min(args.steps, 10))
@@ -699,6 +726,7 @@ def run_ours(args, rank, world, local_rank):
     for t_ in th:
         t_.join()
     pipe_secs = time.perf_counter() - t0
+    clocks = sampler.summary()
     serial_secs = tm.max_over_ranks(serial_secs)
     pipe_secs = tm.max_over_ranks(pipe_secs)
     ctx2.close()

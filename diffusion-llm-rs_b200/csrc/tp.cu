@@ -62,13 +62,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Data accesses of the exchange: WEAK 16-byte loads / stores.  Ordering comes from the barriers
+// alone — a rank's stores precede its st.release.sys of the flag (fence + cumulativity through bar.sync), and loads follow the
+// ld.acquire.sys that observed the peers' flags (which also invalidates L1).  (Strong .sys accesses per 16 bytes — the first
+// version — are each individually coherent: LDG/STG.STRONG.SYS.)
 __device__ __forceinline__ uint4 ld_relaxed_sys_v4(const void *p) {
     uint4 v;
-    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_relaxed_sys_v4(void *p, uint4 v) {
-    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ void p2p_barrier(const P2PArgs &a, int phase, uint32_t gen) {

@@ -354,6 +354,84 @@ private:
     int32_t path_;
 };
 
+// KVCacheEntry (lib.rs:122-313), resident in HBM: f32 keys / values [layers, seq, hidden] + a prefill- and a decode-precision
+// quantized copy.  The host-vector methods stage through device memory; the *_dev methods take device pointers (what a GPU-resident
+// sampling loop uses: the cached branch of DiffuseLLM::sample, :885-921, then moves nothing over PCIe).
+class KVCacheEntry {
+public:
+    KVCacheEntry(Context &ctx, size_t layers, size_t hidden, size_t capacity, uint8_t prefill_bits, uint8_t decode_bits,
+                 int32_t scheme = DLLM_KV_TENSOR_B)
+        : ctx_(ctx), layers_(layers), hidden_(hidden) {
+        std::lock_guard<std::mutex> lk(ctx.mutex());
+        ctx.check(dllm_kvcache_create(ctx.raw(), layers, hidden, capacity, prefill_bits, decode_bits, scheme, &h_));
+    }
+    ~KVCacheEntry() { dllm_kvcache_destroy(h_); }
+    KVCacheEntry(const KVCacheEntry &) = delete;
+    // update(new_keys, new_values), :246-276: both quantized copies are rebuilt
+    void update(const std::vector<float> &keys, const std::vector<float> &values, size_t seq) {
+        std::lock_guard<std::mutex> lk(ctx_.mutex());
+        const size_t bytes = layers_ * seq * hidden_ * sizeof(float);
+        void *dk = nullptr, *dv = nullptr;
+        ctx_.check(dllm_malloc(ctx_.raw(), bytes ? bytes : 4, &dk));
+        ctx_.check(dllm_malloc(ctx_.raw(), bytes ? bytes : 4, &dv));
+        int32_t rc = dllm_memcpy_h2d(ctx_.raw(), dk, keys.data(), bytes);
+        if (rc == DLLM_OK) rc = dllm_memcpy_h2d(ctx_.raw(), dv, values.data(), bytes);
+        if (rc == DLLM_OK) rc = dllm_kvcache_update_dev(ctx_.raw(), h_, (const float *)dk, (const float *)dv, seq);
+        if (rc == DLLM_OK) rc = dllm_ctx_sync(ctx_.raw());
+        dllm_free(ctx_.raw(), dk);
+        dllm_free(ctx_.raw(), dv);
+        ctx_.check(rc);
+    }
+    void update_dev(const float *keys_dev, const float *values_dev, size_t seq) {
+        std::lock_guard<std::mutex> lk(ctx_.mutex());
+        ctx_.check(dllm_kvcache_update_dev(ctx_.raw(), h_, keys_dev, values_dev, seq));
+    }
+    void append_dev(const float *keys_new_dev, const float *values_new_dev, size_t t_new) {
+        std::lock_guard<std::mutex> lk(ctx_.mutex());
+        ctx_.check(dllm_kvcache_append_dev(ctx_.raw(), h_, keys_new_dev, values_new_dev, t_new));
+    }
+    void get_dev(float *keys_out_dev, float *values_out_dev) const {
+        std::lock_guard<std::mutex> lk(ctx_.mutex());
+        ctx_.check(dllm_kvcache_get_dev(ctx_.raw(), h_, keys_out_dev, values_out_dev));
+    }
+    std::vector<float> get_keys() const { return fetch(true); }        // :176-189
+    std::vector<float> get_values() const { return fetch(false); }     // :192-205
+    void set_phase(bool is_prefill) { transition_phase(is_prefill); }  // :207-209
+    void transition_phase(bool is_prefill) {                           // :220-238
+        std::lock_guard<std::mutex> lk(ctx_.mutex());
+        ctx_.check(dllm_kvcache_set_phase(ctx_.raw(), h_, is_prefill ? 1 : 0));
+    }
+    void set_decode_bits(uint8_t bits) {                               // :899-903
+        std::lock_guard<std::mutex> lk(ctx_.mutex());
+        ctx_.check(dllm_kvcache_set_decode_bits(ctx_.raw(), h_, bits));
+    }
+    uint8_t get_current_quant_bits() const { uint8_t b = 0; dllm_kvcache_info(h_, nullptr, nullptr, &b, nullptr); return b; }
+    size_t memory_usage() const { size_t m = 0; dllm_kvcache_info(h_, nullptr, nullptr, nullptr, &m); return m; }
+    size_t len() const { size_t s = 0; dllm_kvcache_info(h_, &s, nullptr, nullptr, nullptr); return s; }
+    bool is_empty() const { return len() == 0; }
+    dllm_kvcache *raw() const { return h_; }
+
+private:
+    std::vector<float> fetch(bool keys) const {
+        std::lock_guard<std::mutex> lk(ctx_.mutex());
+        const size_t n = layers_ * len_unlocked() * hidden_;
+        std::vector<float> out(n);
+        if (n == 0) return out;
+        void *d = nullptr;
+        ctx_.check(dllm_malloc(ctx_.raw(), n * sizeof(float), &d));
+        int32_t rc = dllm_kvcache_get_dev(ctx_.raw(), h_, keys ? (float *)d : nullptr, keys ? nullptr : (float *)d);
+        if (rc == DLLM_OK) rc = dllm_memcpy_d2h(ctx_.raw(), out.data(), d, n * sizeof(float));
+        if (rc == DLLM_OK) rc = dllm_ctx_sync(ctx_.raw());
+        dllm_free(ctx_.raw(), d);
+        ctx_.check(rc);
+        return out;
+    }
+    size_t len_unlocked() const { size_t s = 0; dllm_kvcache_info(h_, &s, nullptr, nullptr, nullptr); return s; }
+    Context &ctx_;
+    size_t layers_, hidden_;
+    dllm_kvcache *h_ = nullptr;
+};
+
 // DiffuseLLM::sample without cache (lib.rs:853-927) and p_sample (:1152-1215), noise injected
 class DiffuseLLM {
 public:

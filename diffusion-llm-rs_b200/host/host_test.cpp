@@ -107,6 +107,33 @@ int main() {
             for (float v : out) CHECK(std::isfinite(v));
             std::printf("launches=%llu\n", (unsigned long long)ctx.launches());
         }
+        // diffuse-llm-rs/src/lib.rs:122-313  KVCacheEntry, resident in HBM: phases, progressive decode width, accounting
+        {
+            const size_t L = 2, S = 4, H = 64;
+            std::vector<float> k(L * S * H), v(L * S * H);
+            for (size_t i = 0; i < k.size(); ++i) { k[i] = std::sin(0.37f * (float)i); v[i] = 2.f * std::cos(0.11f * (float)i); }
+            diffuse_llm::KVCacheEntry e(ctx, L, H, 16, 8, 4);
+            CHECK(e.is_empty() && e.get_current_quant_bits() == 8);
+            e.update(k, v, S);
+            CHECK(e.len() == S);
+            CHECK(e.memory_usage() == 2 * ((k.size() * 8 + 7) / 8) + 2 * ((k.size() * 4 + 7) / 8));   // :279-302
+            // prefill phase decodes the 8-bit copy: equal to QuantizedKVCacheEntry::new(keys, values, 8).dequantize_keys()
+            quantization::QuantizedKVCacheEntry q8(ctx, k, v, L, S, H, 8);
+            auto k8 = e.get_keys(), r8 = q8.dequantize_keys();
+            CHECK(k8.size() == r8.size() && std::memcmp(k8.data(), r8.data(), k8.size() * 4) == 0);
+            e.set_phase(false);
+            CHECK(e.get_current_quant_bits() == 4);
+            quantization::QuantizedKVCacheEntry q4(ctx, k, v, L, S, H, 4);
+            auto v4 = e.get_values(), rv4 = q4.dequantize_values();
+            CHECK(std::memcmp(v4.data(), rv4.data(), v4.size() * 4) == 0);
+            e.set_decode_bits(2);                       // :899-903: the decode copy is dropped; the getters return the f32 tensors
+            auto kf = e.get_keys();
+            CHECK(std::memcmp(kf.data(), k.data(), k.size() * 4) == 0);
+            e.update(k, v, S);                          // ... and re-created at the new width by the next update
+            quantization::QuantizedKVCacheEntry q2(ctx, k, v, L, S, H, 2);
+            auto k2 = e.get_keys(), r2 = q2.dequantize_keys();
+            CHECK(std::memcmp(k2.data(), r2.data(), k2.size() * 4) == 0);
+        }
     } catch (const dllm::Error &e) {
         std::printf("FAIL exception: %s\n", e.what());
         return 2;
