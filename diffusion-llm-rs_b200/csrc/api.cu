@@ -1197,7 +1197,9 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
         // layer, 47.1 (token chunks + overlap: 50.9, chunked GEMMs cost more than the overlap hides); with NCCL the overlap
         // pays: 2 chunks 50.9 against 53.2
         //   the same holds at TP4 once every rank starts at its own token slice (32.8 against 37.0 ms)
-        const int chunks = ctx->tp_chunks > 0 ? ctx->tp_chunks : env_int("DLLM_TP_CHUNKS", ctx->p2p_arena ? 1 : 2);
+        //   (from 4 ranks on the exchange outweighs the GEMMs and two token chunks — the gather half of one chunk under the GEMMs
+        //   of the other — win again: 33.7 against 34.0 ms at TP4, 26.1 against 29.5 at TP8)
+        const int chunks = ctx->tp_chunks > 0 ? ctx->tp_chunks : env_int("DLLM_TP_CHUNKS", ctx->p2p_arena && ctx->tp_world <= 2 ? 1 : 2);
         if (chunks > 1 && tokens >= (size_t)chunks * 512) return forward_tp_overlapped(ctx, m, x_dev, tokens, out_dev, chunks);
     }
     if (all_umma && (!any_parallel || no_gather)) {
@@ -1219,13 +1221,14 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
             if (m->parallel[l] == 2 && !last && tp_fused_rs_ok(ctx, m->layers[l], tokens, recv0)) {
                 // the all-gather half can run under the next GEMM when that one is a dense bf16-output kernel on whole 256-token
                 // tiles per slice (DLLM_TP_GATED=0 keeps the closing barrier: experiments)
-                // DLLM_TP_GATED: 1 (default) = the reduce / gather kernel runs in front of that GEMM and ends with arrival counters
-                // instead of a barrier: its tail (the peers' rows still in flight) overlaps the GEMM's first tiles; 2 = the kernel
-                // runs on the communication stream UNDER the GEMM, which leaves it 16 SMs and gates its own slice too (measured
-                // no faster at TP2: 49.8 against 48.8-49.5 ms — the GEMM on 132 SMs and the lost dependent-launch overlap cost
-                // what the overlap gains); 0 = closing barrier
+                // DLLM_TP_GATED: 0 (default) = the reduce / gather kernel ends with a barrier; 1 = it ends with arrival counters and the
+                // next GEMM gates its activation loads on them, so the peers' rows still in flight overlap its first tiles; 2 = the
+                // kernel runs on the communication stream UNDER that GEMM, which leaves it 16 SMs and gates its own slice too.
+                // Measured (7B-class, ms per step): TP2 47.7 / 46.8 / 49.8 on one box and 48.8 / 49.5 / 49.8 on another, TP4
+                // 33.1 / 34.1 / 34.1 — within the box-to-box spread at TP2 and behind the plain barrier at TP4 (the GEMM on 132 SMs
+                // and the programmatic-launch overlap that has to be given up cost what the overlap gains), so the barrier stays.
                 const char *gsw = getenv("DLLM_TP_GATED");
-                int gate_next = gsw ? atoi(gsw) : 1;
+                int gate_next = gsw ? atoi(gsw) : 0;
                 if (gate_next < 0 || gate_next > 2 ||
                     !(l + 2 < L && m->parallel[l + 1] == 1 && k_umma_gate_supported(ctx, m->layers[l + 1], tokens, ctx->tp_world, cur)))
                     gate_next = 0;
