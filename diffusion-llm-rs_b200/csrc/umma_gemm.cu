@@ -1469,60 +1469,75 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const uint32_t n = nt * 128 + quarter * 32 + lane;
             const bool n_ok = nt < a.n_tiles && n < a.N && !(a.dbg & 64);
             const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
-#pragma unroll 1
-            for (uint32_t h = 0; h < 2; ++h) {
-                const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + part * q;
-                const uint32_t tok0 = mt * ntok + part * half_rows + h * q;     // token of this warp's first column
-                const uint32_t n_tok = tok0 >= a.M ? 0u : (a.M - tok0 < q ? a.M - tok0 : q);   // valid rows among its q
-                if (a.y_f32 == nullptr) {
-                    // staging buffer free?  Half 0 checks BEFORE it waits for the accumulator (off the critical path: the previous
-                    // tile's half-1 store has had a whole tile's time), half 1 after it has handed its accumulator back.
-                    if (h == 0 && !(a.dbg & 64)) {
-                        if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        named_bar_sync(1, 256);
+            if (a.y_f32 == nullptr) {
+                // bf16 output.  Both accumulator halves are on the tensor pipe's critical path (they are single-buffered), so they
+                // are drained back to back: half 0 -> registers -> handed back -> written to the staging buffer (shared-memory
+                // stores only); half 1 -> registers -> handed back; THEN the stores: half 0 leaves as bulk tensor copies, the
+                // staging buffer is re-used for half 1.  (Storing half 0 before draining half 1 — the first version — kept half 1
+                // for 1.9 K cycles longer at every tile boundary: stage timeline, DLLM_UMMA_DBG=128.)
+                const uint32_t stg = smem_u32(smem + C::kOutOffset);
+                const uint32_t stg_mine = stg + (part * q) * 256u + (uint32_t)(quarter * 32 + lane) * 2u;
+                auto store_half = [&](uint32_t h) {                 // one elected thread: the staged half -> global / peer memory
+                    if (warp == kEpiWarp0 && lane == 0 && nt < a.n_tiles) {
+                        const int tokA = (int)(mt * ntok + h * q);
+                        if (a.rs_world == 0) {
+                            tma_store_2d(&tmap_y, stg, (int)(nt * 128), tokA);
+                            tma_store_2d(&tmap_y, stg + q * 256u, (int)(nt * 128), tokA + (int)half_rows);
+                        } else {
+                            // reduce-scatter fused into the epilogue: each q-row block goes to its owner's receive buffer
+                            // (q divides rs_rows, so a block never straddles two owners)
+#pragma unroll
+                            for (int b2 = 0; b2 < 2; ++b2) {
+                                const uint32_t tk = (uint32_t)tokA + (uint32_t)b2 * half_rows;
+                                if (tk < a.M) {
+                                    const uint32_t owner = tk / a.rs_rows;
+                                    tma_store_2d(&rs.m[owner], stg + (uint32_t)b2 * q * 256u, (int)(nt * 128),
+                                                 (int)(a.rs_rank * a.rs_rows + (tk - owner * a.rs_rows)));
+                                }
+                            }
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                };
+                const bool st_on = !(a.dbg & 64);
+                // staging buffer free?  Checked BEFORE the wait for the accumulator (off the critical path: the previous tile's
+                // half-1 store has had a whole tile's time)
+                if (st_on) {
+                    if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    named_bar_sync(1, 256);
+                }
+                uint32_t pk[32];
+#pragma unroll 1
+                for (uint32_t h = 0; h < 2; ++h) {
+                    const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + part * q;
                     mbar_wait(tfull + h, tph);
                     tc_fence_after();
                     if (warp == kEpiWarp0 && lane == 0) TRACE2(4 + h, n_item);
-                    uint32_t pk[32];
                     drain_columns(t_acc, q, bias, pk);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(tempty_leader + h * 8);   // this warp's columns are out: 16 such arrivals free the half
                     if (warp == kEpiWarp0 && lane == 0) TRACE2(6 + h, n_item);
-                    // phase 2: registers -> staging [part][token][128 columns] -> two bulk tensor stores (rows past M and columns past
-                    // N are clipped by the TMA unit)
-                    if (!(a.dbg & 64)) {
-                        if (h == 1) {
-                            if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                            named_bar_sync(1, 256);
-                        }
-                        stage_columns(smem_u32(smem + C::kOutOffset) + (part * q) * 256u + (uint32_t)(quarter * 32 + lane) * 2u, q, pk);
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        named_bar_sync(1, 256);
-                        if (warp == kEpiWarp0 && lane == 0 && nt < a.n_tiles) {
-                            const uint32_t src = smem_u32(smem + C::kOutOffset);
-                            const int tokA = (int)(mt * ntok + h * q);
-                            if (a.rs_world == 0) {
-                                tma_store_2d(&tmap_y, src, (int)(nt * 128), tokA);
-                                tma_store_2d(&tmap_y, src + q * 256u, (int)(nt * 128), tokA + (int)half_rows);
-                            } else {
-                                // reduce-scatter fused into the epilogue: each q-row block goes to its owner's receive buffer
-                                // (q divides rs_rows, so a block never straddles two owners)
-#pragma unroll
-                                for (int b2 = 0; b2 < 2; ++b2) {
-                                    const uint32_t tk = (uint32_t)tokA + (uint32_t)b2 * half_rows;
-                                    if (tk < a.M) {
-                                        const uint32_t owner = tk / a.rs_rows;
-                                        tma_store_2d(&rs.m[owner], src + (uint32_t)b2 * q * 256u, (int)(nt * 128),
-                                                     (int)(a.rs_rank * a.rs_rows + (tk - owner * a.rs_rows)));
-                                    }
-                                }
-                            }
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        }
-                    }
-                } else {
+                    if (h == 0 && st_on) stage_columns(stg_mine, q, pk);          // registers -> staging [part][token][128 columns]
+                }
+                if (st_on) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    named_bar_sync(1, 256);
+                    store_half(0);                                               // rows past M / columns past N are clipped by the TMA unit
+                    if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    named_bar_sync(1, 256);
+                    stage_columns(stg_mine, q, pk);                              // pk still holds half 1
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    named_bar_sync(1, 256);
+                    store_half(1);
+                }
+            } else {
+#pragma unroll 1
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + part * q;
+                const uint32_t tok0 = mt * ntok + part * half_rows + h * q;     // token of this warp's first column
+                const uint32_t n_tok = tok0 >= a.M ? 0u : (a.M - tok0 < q ? a.M - tok0 : q);   // valid rows among its q
+                {
                     // f32 (and optionally bf16) output: the stack's last layer only.  Columns are stored as they are read.
                     mbar_wait(tfull + h, tph);
                     tc_fence_after();
@@ -1548,6 +1563,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                         }
                     }
                 }
+            }
             }
             ++n_item;
         }
