@@ -326,6 +326,60 @@ def secondary_metrics(ctx, stream, pk):
         qt.close()
         del wi, xq, yi
     out["int8_linear"] = i8
+    # int8 denoise mode (DLLM_PATH_I8) of the whole 1B-class stack: the reference's per-tensor 4-bit codes, activations
+    # quantized per token to int8 in front of every linear, kind::i8 with the dequantization fused into the epilogue — next to the
+    # bf16 mode on the SAME per-tensor weights, and both against the f32-faithful SIMT stack on 1024 of the 8192 tokens
+    from dllm_b200.diffuse_llm import DiffusionConfig, QuantizedDiffusionModel
+    H1, shapes1 = layer_shapes("1b")
+    feat1 = CANVAS * H1
+    g1 = torch.Generator(device="cuda").manual_seed(777)
+    lay = []
+    for (K1, N1) in shapes1:
+        w1 = torch.randn(K1, N1, device="cuda", generator=g1) * (1.0 / K1 ** 0.5)
+        torch.cuda.synchronize()
+        lay.append(QWeight.quantize_dev(ctx, w1.data_ptr(), K1, N1, 4, 0))
+        ctx.sync()
+        del w1
+    cfg1 = DiffusionConfig(num_timesteps=1000, hidden_size=H1, use_kv_cache=False)
+    xs = torch.randn(BATCH, feat1, device="cuda", generator=g1)
+    z1 = torch.randn(BATCH, feat1, device="cuda", generator=g1)
+    stack = {"workload": "configs[2] stack with per-tensor 4-bit weights (group_size 0, quantization.rs:38-79), 8192 tokens",
+             "kernels": "rowquant_i8_kernel + umma_qlinear_kernel<.., int8> with fused dequantization epilogue"}
+    preds = {}
+    for name, pth in (("int8", dllm_b200.PATH_I8), ("bf16", dllm_b200.PATH_UMMA), ("f32_simt", dllm_b200.PATH_SIMT)):
+        mdl = QuantizedDiffusionModel(lay, H1, cfg1, ctx, pth)
+        nb = 4 if name == "f32_simt" else BATCH
+        pred = torch.empty(nb, feat1, device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            mdl.forward_dev(xs.data_ptr(), nb, feat1, pred.data_ptr())
+            stream.synchronize()
+        preds[name] = pred[:4].clone()
+        if name != "f32_simt":
+            xw = xs.clone()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ctx.launches
+            with torch.cuda.stream(stream):
+                for i in range(3):
+                    mdl.denoise_step_dev(xw.data_ptr(), z1.data_ptr(), 999 - i, BATCH, feat1)
+                stream.synchronize()
+                l0 = ctx.launches
+                e0.record(stream)
+                for i in range(10):
+                    mdl.denoise_step_dev(xw.data_ptr(), z1.data_ptr(), 900 - i, BATCH, feat1)
+                e1.record(stream)
+                e1.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            stack[name] = {"ms_per_step": round(ms, 3), "steps_per_sec": round(1e3 / ms, 2), "launches_per_step": (ctx.launches - l0) // 10}
+        mdl.close()
+    ref = preds["f32_simt"].double()
+    for name in ("int8", "bf16"):
+        stack[name]["rel_err_vs_f32_stack"] = float(torch.linalg.norm(preds[name].double() - ref) / torch.linalg.norm(ref))
+    stack["tolerance"] = "1e-2 * sqrt(120 linears) relative Frobenius error, as the bf16 stack (tests/test_gpu_model.py)"
+    out["int8_stack"] = stack
+    for q in lay:
+        q.close()
+    del xs, z1, preds
     rows, dim = 1 << 16, 4096
     x = torch.randn(rows, dim, device="cuda")
     codes = torch.empty(rows * dim // 2, dtype=torch.uint8, device="cuda")

@@ -861,14 +861,33 @@ static int resolve_path(const dllm_qweight *w, size_t M, int32_t path) {
     return path;
 }
 
+// int8 denoise mode, one linear: per-token symmetric int8 activations (from the bf16 tensor the stack carries), exact integer
+// contraction, dequantization + bias in the epilogue
+static int32_t i8_linear(dllm_ctx *ctx, const dllm_qweight *w, const void *x_bf16, size_t M, float *y_f32, void *y_bf16) {
+    const size_t aux = (M * 4 + 255) & ~(size_t)255;
+    DLLM_TRY(ensure_buf(ctx, ctx->act[2], M * w->K));
+    DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, 2 * aux));
+    int32_t *rowsum = (int32_t *)ctx->lin_flags.p;
+    float *rowscale = (float *)((char *)ctx->lin_flags.p + aux);
+    DLLM_TRY(k_rowquant_i8(ctx, x_bf16, M, w->K, w->tensor_scale, (int8_t *)ctx->act[2].p, rowscale, rowsum));
+    return k_qlinear_umma_i8_deq(ctx, w, (const int8_t *)ctx->act[2].p, rowsum, rowscale, M, y_f32, y_bf16);
+}
+
 int32_t dllm_qlinear_forward_dev(dllm_ctx *ctx, const dllm_qweight *w, const float *x_dev, size_t M, float *y_dev,
                                  int32_t path) {
     CTX_CHECK(ctx);
     ARG_CHECK(ctx, w, DLLM_ERR_NULL, "null weight");
     ARG_CHECK(ctx, M == 0 || (x_dev && y_dev), DLLM_ERR_NULL, "null device pointer");
-    ARG_CHECK(ctx, path >= DLLM_PATH_AUTO && path <= DLLM_PATH_GEMV, DLLM_ERR_INVALID_PARAMS, "unknown path %d", path);
+    ARG_CHECK(ctx, path >= DLLM_PATH_AUTO && path <= DLLM_PATH_I8, DLLM_ERR_INVALID_PARAMS, "unknown path %d", path);
     if (M == 0) return DLLM_OK;
     const int p = resolve_path(w, M, path);
+    if (p == DLLM_PATH_I8) {
+        ARG_CHECK(ctx, k_umma_i8_supported(w, M), DLLM_ERR_UNSUPPORTED,
+                  "int8 path needs a per-tensor quantized weight (group_size 0) with K %% 64 == 0 and K <= 65536");
+        DLLM_TRY(ensure_buf(ctx, ctx->act[0], M * w->K * 2));
+        DLLM_TRY(k_f32_to_bf16(ctx, x_dev, M * w->K, ctx->act[0].p));
+        return i8_linear(ctx, w, ctx->act[0].p, M, y_dev, nullptr);
+    }
     if (p == DLLM_PATH_SIMT) return k_qlinear_simt(ctx, w, x_dev, M, y_dev);
     if (p == DLLM_PATH_GEMV) {
         ARG_CHECK(ctx, k_gemv_supported(w, M), DLLM_ERR_UNSUPPORTED, "GEMV path needs 1 <= M <= 16 (got %zu)", M);
@@ -1186,6 +1205,23 @@ static int32_t model_forward_tokens(dllm_ctx *ctx, dllm_model *m, const float *x
     bool any_parallel = false;
     for (int p : m->parallel) any_parallel = any_parallel || p != 0;
     if (path == DLLM_PATH_UMMA && !all_umma) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "tcgen05 path does not support this stack");
+    if (path == DLLM_PATH_I8) {
+        // int8 denoise mode: bf16 activations between the layers, each quantized per token in front of its integer linear
+        for (auto *w : m->layers)
+            if (!k_umma_i8_supported(w, tokens))
+                DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "int8 mode needs per-tensor quantized weights (group_size 0) with K %% 64 == 0");
+        if (any_parallel && ctx->tp_world > 1) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "int8 mode runs replicated stacks only");
+        DLLM_TRY(ensure_buf(ctx, ctx->act[0], tokens * maxw * 2));
+        DLLM_TRY(ensure_buf(ctx, ctx->act[1], tokens * maxw * 2));
+        void *cur = ctx->act[0].p, *nxt = ctx->act[1].p;
+        DLLM_TRY(k_f32_to_bf16(ctx, x_dev, tokens * m->layers[0]->K, cur));
+        for (size_t l = 0; l < L; ++l) {
+            const bool last = l + 1 == L;
+            DLLM_TRY(i8_linear(ctx, m->layers[l], cur, tokens, last ? out_dev : nullptr, last ? nullptr : nxt));
+            void *t = cur; cur = nxt; nxt = t;
+        }
+        return DLLM_OK;
+    }
 
     // tensor-parallel stacks whose column-parallel layers all feed a row-parallel one need no all-gather
     bool no_gather = true;

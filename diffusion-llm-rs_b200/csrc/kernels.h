@@ -64,6 +64,13 @@ bool k_umma_rs_supported(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, 
 bool k_umma_gate_supported(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, int world, const void *y_bf16);
 int32_t k_qlinear_umma_rs(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16_dev, size_t M, const UmmaRs *rs);
 int32_t k_qlinear_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq_dev, size_t M, int32_t *y_i32_dev);
+// ... with the dequantization fused into the epilogue (int8 denoise stack): y = (sum - zp rowsum[m]) * rowscale[m] + bias[n]
+int32_t k_qlinear_umma_i8_deq(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq_dev, const int32_t *rowsum_dev,
+                              const float *rowscale_dev, size_t M, float *y_f32_dev, void *y_bf16_dev);
+// per-token symmetric int8 quantization of bf16 activations [M, K] (K % 8 == 0): xq = rint(x * 127 / max|x_row|), rowscale[m] =
+// wscale * max|x_row| / 127 (1 for an all-zero row), rowsum[m] = sum of the row's codes
+int32_t k_rowquant_i8(dllm_ctx *ctx, const void *x_bf16_dev, size_t M, size_t K, float wscale, int8_t *xq_dev, float *rowscale_dev,
+                      int32_t *rowsum_dev);
 bool k_umma_i8_supported(const dllm_qweight *qw, size_t M);
 
 // ---- sample_kernels.cu ----

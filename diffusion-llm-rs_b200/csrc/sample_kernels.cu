@@ -123,6 +123,76 @@ int32_t k_f32_to_bf16(dllm_ctx *ctx, const float *in_dev, size_t n, void *out_bf
     return DLLM_OK;
 }
 
+namespace {
+// one CTA per token row: absmax (first pass), then codes / row sum (second pass: the row comes from L1 / L2)
+__global__ void __launch_bounds__(256) rowquant_i8_kernel(const __nv_bfloat16 *__restrict__ x, uint32_t K, float wscale,
+                                                          int8_t *__restrict__ xq, float *__restrict__ rowscale, int32_t *__restrict__ rowsum) {
+    __shared__ float s_max[8];
+    __shared__ int s_sum[8];
+    const size_t row = blockIdx.x;
+    const uint4 *src = reinterpret_cast<const uint4 *>(x + row * K);
+    const uint32_t n8 = K / 8;
+    float m = 0.f;
+    for (uint32_t i = threadIdx.x; i < n8; i += 256) {
+        const uint4 v = __ldg(src + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            m = fmaxf(m, fabsf(__uint_as_float(w[e] << 16)));
+            m = fmaxf(m, fabsf(__uint_as_float(w[e] & 0xffff0000u)));
+        }
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = s_max[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, s_max[i]);
+    m = fminf(m, 3.0e38f);                                   // (an infinite activation saturates instead of zeroing the row)
+    const float inv = m > 0.f ? 127.f / m : 0.f;
+    int acc = 0;
+    uint2 *dst = reinterpret_cast<uint2 *>(xq + row * K);
+    for (uint32_t i = threadIdx.x; i < n8; i += 256) {
+        const uint4 v = __ldg(src + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        int q[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            q[2 * e] = max(-127, min(127, __float2int_rn(__uint_as_float(w[e] << 16) * inv)));
+            q[2 * e + 1] = max(-127, min(127, __float2int_rn(__uint_as_float(w[e] & 0xffff0000u) * inv)));
+        }
+        uint2 o;
+        o.x = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
+        o.y = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+        dst[i] = o;
+        acc = __dp4a((int)o.x, 0x01010101, acc);
+        acc = __dp4a((int)o.y, 0x01010101, acc);
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_sum[i];
+        rowsum[row] = t;
+        rowscale[row] = wscale * (m > 0.f ? m / 127.f : 1.f);
+    }
+}
+}  // namespace
+
+int32_t k_rowquant_i8(dllm_ctx *ctx, const void *x_bf16_dev, size_t M, size_t K, float wscale, int8_t *xq_dev, float *rowscale_dev,
+                      int32_t *rowsum_dev) {
+    if (M == 0) return DLLM_OK;
+    if (K % 8 != 0 || (reinterpret_cast<uintptr_t>(x_bf16_dev) & 15u) || (reinterpret_cast<uintptr_t>(xq_dev) & 7u))
+        DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "int8 activation quantizer: K %% 8 == 0 and aligned buffers required");
+    rowquant_i8_kernel<<<(unsigned)M, 256, 0, ctx->stream>>>((const __nv_bfloat16 *)x_bf16_dev, (uint32_t)K, wscale, xq_dev, rowscale_dev, rowsum_dev);
+    LAUNCH_CHECK(ctx);
+    return DLLM_OK;
+}
+
 int32_t k_bf16_to_f32(dllm_ctx *ctx, const void *in_bf16_dev, size_t n, float *out_dev) {
     if (n == 0) return DLLM_OK;
     bf16_to_f32_kernel<<<grid1d(ctx, n), 256, 0, ctx->stream>>>((const __nv_bfloat16 *)in_bf16_dev, n, out_dev);

@@ -1030,9 +1030,26 @@ __device__ __forceinline__ void umma_qlinear_body(const CUtensorMap &tmap_x, con
                 if constexpr (I8) {
                     // exact: sum x q - zp sum x  (dequantize_tensor's `- zp`, quantization.rs:83, in the integer domain)
                     if (!n_ok) continue;
-                    int32_t *yp = reinterpret_cast<int32_t *>(a.y_f32) + (size_t)m_base * a.N + n;
                     const int32_t *sx = reinterpret_cast<const int32_t *>(a.partial);
                     const int32_t zp = (int32_t)a.x3d;
+                    if (a.dbg & 256) {
+                        // int8 denoise mode: the exact integer sum leaves as  (sum - zp rowsum) * (weight scale * token scale) + bias
+                        // (dequantize_tensor's `(q - zp) * scale`, quantization.rs:83, composed with the token's own step);
+                        // a.trace = [M] f32 weight scale x token scale, y_f32 / y_bf16 = float outputs
+                        const float *rs = reinterpret_cast<const float *>(a.trace);
+                        const float bn = (a.bias != nullptr) ? __ldg(a.bias + n) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            if (m_base + j < a.M) {
+                                const int32_t e = (int32_t)v[j] - zp * __ldg(sx + m_base + j);
+                                const float f = fmaf((float)e, __ldg(rs + m_base + j), bn);
+                                if (a.y_f32) a.y_f32[(size_t)(m_base + j) * a.N + n] = f;
+                                if (a.y_bf16) a.y_bf16[(size_t)(m_base + j) * a.N + n] = __float2bfloat16_rn(f);
+                            }
+                        }
+                        continue;
+                    }
+                    int32_t *yp = reinterpret_cast<int32_t *>(a.y_f32) + (size_t)m_base * a.N + n;
 #pragma unroll
                     for (int j = 0; j < CH; ++j)
                         if (m_base + j < a.M) yp[(size_t)j * a.N] = (int32_t)v[j] - zp * __ldg(sx + m_base + j);
@@ -1971,8 +1988,12 @@ rowsum_i8_kernel(const int8_t *__restrict__ x, uint32_t M, uint32_t K, int32_t *
     if (lane == 0) sx[row] = acc;
 }
 
+// fused dequantization of the int8 mode (the int8 denoise stack): row sums and (weight scale x token scale) per token come from the
+// activation quantizer, the outputs are floats
+struct I8Deq { const int32_t *rowsum; const float *rowscale; float *y_f32; void *y_bf16; };
+
 template <int CB, int NTOK>
-int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, size_t M, int32_t *y) {
+int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, size_t M, int32_t *y, const I8Deq *dq = nullptr) {
     constexpr int KBS = 2, NDQ = kNDQ;
     using C = Cfg<CB, NTOK, KBS, NDQ, true>;
     PFN_encodeTiled enc = get_encode_fn();
@@ -1988,12 +2009,14 @@ int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
 
-    DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, M * sizeof(int32_t)));
-    rowsum_i8_kernel<<<(unsigned)((M + 7) / 8), 256, 0, ctx->stream>>>(xq, (uint32_t)M, (uint32_t)qw->K, (int32_t *)ctx->lin_flags.p);
-    LAUNCH_CHECK(ctx);
+    if (!dq) {
+        DLLM_TRY(ensure_buf(ctx, ctx->lin_flags, M * sizeof(int32_t)));
+        rowsum_i8_kernel<<<(unsigned)((M + 7) / 8), 256, 0, ctx->stream>>>(xq, (uint32_t)M, (uint32_t)qw->K, (int32_t *)ctx->lin_flags.p);
+        LAUNCH_CHECK(ctx);
+    }
 
     UmmaArgs a;
-    a.packed = qw->d_packed; a.dqparams = qw->d_dqparams; a.bias = nullptr;
+    a.packed = qw->d_packed; a.dqparams = qw->d_dqparams; a.bias = dq ? qw->d_bias : nullptr;
     a.x3d = (uint32_t)(int32_t)qw->tensor_zp;           // (int8 mode: the zero-point)
     a.M = (uint32_t)M; a.N = (uint32_t)qw->N; a.Npad = (uint32_t)(qw->n_tiles * 128);
     a.k_blocks = (uint32_t)qw->k_blocks; a.n_tiles = (uint32_t)qw->n_tiles;
@@ -2004,6 +2027,12 @@ int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, 
     a.y_f32 = reinterpret_cast<float *>(y); a.y_bf16 = nullptr;
     a.partial = reinterpret_cast<float *>(ctx->lin_flags.p);           // (int8 mode: the row sums)
     a.dbg = 0; a.trace = nullptr;
+    if (dq) {
+        a.y_f32 = dq->y_f32; a.y_bf16 = (__nv_bfloat16 *)dq->y_bf16;
+        a.partial = reinterpret_cast<float *>(const_cast<int32_t *>(dq->rowsum));
+        a.trace = reinterpret_cast<long long *>(const_cast<float *>(dq->rowscale));
+        a.dbg = 256;
+    }
     a.stream_k = 0;                                      // whole tiles only: int32 accumulators never leave TMEM half-summed
     const uint32_t sms = (uint32_t)ctx->sm_count;
     const uint32_t grid = tiles < sms ? tiles : sms;
@@ -2031,11 +2060,11 @@ int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, 
 }
 
 template <int CB>
-int32_t launch_umma_i8_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, size_t M, int32_t *y) {
-    if (M <= 16) return launch_umma_i8<CB, 16>(ctx, qw, xq, M, y);
-    if (M <= 32) return launch_umma_i8<CB, 32>(ctx, qw, xq, M, y);
-    if (M <= 64) return launch_umma_i8<CB, 64>(ctx, qw, xq, M, y);
-    return launch_umma_i8<CB, 128>(ctx, qw, xq, M, y);
+int32_t launch_umma_i8_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, size_t M, int32_t *y, const I8Deq *dq = nullptr) {
+    if (M <= 16) return launch_umma_i8<CB, 16>(ctx, qw, xq, M, y, dq);
+    if (M <= 32) return launch_umma_i8<CB, 32>(ctx, qw, xq, M, y, dq);
+    if (M <= 64) return launch_umma_i8<CB, 64>(ctx, qw, xq, M, y, dq);
+    return launch_umma_i8<CB, 128>(ctx, qw, xq, M, y, dq);
 }
 
 }  // namespace
@@ -2084,6 +2113,20 @@ int32_t k_qlinear_umma_rs(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_b
     // (y_bf16 = any aligned non-null pointer: nothing is stored through it in this mode)
     if (wl_container_bits(qw->bits) == 2) return launch_umma_pair2<2>(ctx, qw, x_bf16_dev, M, nullptr, rs->recv[rs->rank], rs);
     return launch_umma_pair2<4>(ctx, qw, x_bf16_dev, M, nullptr, rs->recv[rs->rank], rs);
+}
+
+// the same exact integer linear with the dequantization fused into its epilogue: y = (sum - zp rowsum[m]) * rowscale[m] + bias[n]
+// (rowscale = the weight's scale x the token's activation step; rowsum = the token's int8 row sum): the int8 denoise stack
+int32_t k_qlinear_umma_i8_deq(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq_dev, const int32_t *rowsum_dev,
+                              const float *rowscale_dev, size_t M, float *y_f32_dev, void *y_bf16_dev) {
+    if (!k_umma_i8_supported(qw, M)) DLLM_FAIL(ctx, DLLM_ERR_UNSUPPORTED, "int8 path: per-tensor quantized weight with K %% 64 == 0 and K <= 65536 required");
+    if ((reinterpret_cast<uintptr_t>(xq_dev) & 15u) != 0) DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "xq must be 16-byte aligned");
+    const I8Deq dq = {rowsum_dev, rowscale_dev, y_f32_dev, y_bf16_dev};
+    switch (wl_container_bits(qw->bits)) {
+        case 2: return launch_umma_i8_ntok<2>(ctx, qw, xq_dev, M, nullptr, &dq);
+        case 4: return launch_umma_i8_ntok<4>(ctx, qw, xq_dev, M, nullptr, &dq);
+        default: return launch_umma_i8_ntok<8>(ctx, qw, xq_dev, M, nullptr, &dq);
+    }
 }
 
 bool k_umma_supported(const dllm_qweight *qw, size_t M) {

@@ -9,10 +9,10 @@ behaviour).  Everything computes on the GPU through the C ABI; there is no CPU f
 """
 from . import _lib
 from ._lib import (DllmError, QuantizationError, InvalidParams, UnsupportedOperation, ShapeMismatch,
-                   CalibrationRequired, ReferencePanic, NoDevice, PATH_AUTO, PATH_SIMT, PATH_UMMA, PATH_GEMV,
+                   CalibrationRequired, ReferencePanic, NoDevice, PATH_AUTO, PATH_SIMT, PATH_UMMA, PATH_GEMV, PATH_I8,
                    KV_TENSOR_B, KV_ROW_D, KV_FIXED_C)
 from .runtime import Context, QWeight, dequant_matmul, default_context
 
 __all__ = ["Context", "QWeight", "dequant_matmul", "default_context", "DllmError", "QuantizationError",
            "InvalidParams", "UnsupportedOperation", "ShapeMismatch", "CalibrationRequired", "ReferencePanic",
-           "NoDevice", "PATH_AUTO", "PATH_SIMT", "PATH_UMMA", "PATH_GEMV", "KV_TENSOR_B", "KV_ROW_D", "KV_FIXED_C"]
+           "NoDevice", "PATH_AUTO", "PATH_SIMT", "PATH_UMMA", "PATH_GEMV", "PATH_I8", "KV_TENSOR_B", "KV_ROW_D", "KV_FIXED_C"]

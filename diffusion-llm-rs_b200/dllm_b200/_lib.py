@@ -20,7 +20,7 @@ ERR_CUDA, ERR_NO_DEVICE, ERR_NCCL, ERR_OOM, ERR_NULL = 100, 101, 102, 103, 104
 QT_INT8, QT_INT4, QT_BINARY, QT_FLOAT8 = 0, 1, 2, 3
 BETA_LINEAR, BETA_QUADRATIC, BETA_COSINE = 0, 1, 2
 KV_TENSOR_B, KV_ROW_D, KV_FIXED_C = 0, 1, 2
-PATH_AUTO, PATH_SIMT, PATH_UMMA, PATH_GEMV = 0, 1, 2, 3
+PATH_AUTO, PATH_SIMT, PATH_UMMA, PATH_GEMV, PATH_I8 = 0, 1, 2, 3, 4
 
 
 class DllmError(RuntimeError):

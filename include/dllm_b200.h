@@ -67,9 +67,15 @@ enum {
     DLLM_PATH_AUTO = 0,
     DLLM_PATH_SIMT = 1,  /* f32 CUDA-core dequant-GEMV (exact f32 dequant, f32 accumulate) */
     DLLM_PATH_UMMA = 2,  /* tcgen05 / TMEM path: bf16 operands dequantized on the fly, f32 accumulate */
-    DLLM_PATH_GEMV = 3   /* 1..16 tokens, HBM-bound: bulk-copy ring + int8 mma.sync (u8 codes x signed-digit block-fixed-point
+    DLLM_PATH_GEMV = 3,  /* 1..16 tokens, HBM-bound: bulk-copy ring + int8 mma.sync (u8 codes x signed-digit block-fixed-point
                             activations per aligned block of 128 k, exact int32 sums per quantization-group block), f32 scale and
                             accumulation across blocks */
+    DLLM_PATH_I8 = 4     /* int8 denoise mode (explicit only, never chosen by AUTO): per-tensor quantized weights (group_size 0, the
+                            reference's own scheme, quantization.rs:38-85), activations quantized per token to symmetric int8
+                            (step max|x_row| / 127 on the bf16-rounded row), tcgen05 kind::i8 with exact s32 sums, and
+                            dequantize_tensor's `(q - zp) * scale` (quantization.rs:83) composed with the token step in the epilogue:
+                            y = (sum x_q q - zp sum x_q) * (scale * step) + b.  Error against the f64 stack: the activation rounding
+                            only (<= step / 2 per element), stated in tests/test_gpu_linear.py */
 };
 
 typedef struct dllm_ctx dllm_ctx;

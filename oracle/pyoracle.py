@@ -356,3 +356,52 @@ def linear_i8(xq, codes, zp):
     assert zi == zp, "per-tensor zero-points of quantize_tensor are integers (quantization.rs:55-56)"
     return np.asarray(xq, dtype=np.int64) @ (np.asarray(codes, dtype=np.int64) - zi)
 
+
+
+# ---- int8 denoise mode (DLLM_PATH_I8): an arithmetic mode of this repo, not of the reference -----------------------------
+# The reference's linear is f32 (lib.rs:812 on dequantize_tensor's output, quantization.rs:81-85).  The int8 mode keeps the
+# reference's per-tensor codes, quantizes each token row of the activations to symmetric int8 and contracts exactly in
+# integers; what is restated here is that arithmetic (so that the device result can be held to 1 ulp), and the tests bound its
+# distance to the reference's f64 stack separately.
+def bf16_round(x):
+    """f32 -> bf16 (round to nearest even) -> f32, the activation format between the layers of the tcgen05 stacks."""
+    u = _f32(x).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    nan = np.isnan(_f32(x))
+    out = r.astype(np.uint32).view(np.float32).copy()
+    out[nan] = np.nan
+    return out
+
+
+def rowquant_i8(x_bf16, wscale):
+    """Per-token symmetric int8 activation quantizer: q = clamp(rint(x * (127 / max|x_row|)), -127, 127) in f32 arithmetic,
+    rowscale = wscale * (max|x_row| / 127) (wscale for an all-zero row), rowsum = sum of the row's codes."""
+    x = _f32(x_bf16)
+    m = np.minimum(np.abs(x).max(axis=1), np.float32(3.0e38)).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        inv = np.where(m > 0, np.float32(127.0) / m, np.float32(0)).astype(np.float32)
+    q = np.clip(np.rint(x * inv[:, None]), -127, 127).astype(np.int8)
+    rowscale = (np.float32(wscale) * np.where(m > 0, m / np.float32(127.0), np.float32(1)).astype(np.float32)).astype(np.float32)
+    return q, rowscale, q.astype(np.int64).sum(axis=1)
+
+
+def linear_i8_deq(x, codes, scale, zp, bias=None):
+    """One linear of the int8 mode on f32 activations x[M,K] and per-tensor codes[K,N] (quantize_tensor's, quantization.rs:38-79):
+    y = (sum_k q_x q_w - zp sum_k q_x) * (scale * step_m) + b — `(q - zp) * scale` of quantization.rs:83 with the token's step
+    factored out.  The integer part is exact; the float epilogue is one int->f32 conversion and one fused multiply-add,
+    evaluated here in f64 and rounded once (the device result may differ by 1 ulp of f32)."""
+    q, rowscale, rowsum = rowquant_i8(bf16_round(x), scale)
+    e = q.astype(np.int64) @ np.asarray(codes, dtype=np.int64) - int(zp) * rowsum[:, None]
+    b = 0.0 if bias is None else _f32(bias).astype(np.float64)[None, :]
+    return (e.astype(np.float32).astype(np.float64) * rowscale.astype(np.float64)[:, None] + b).astype(np.float32)
+
+
+def model_forward_i8(x_tokens, layers):
+    """Stack of int8-mode linears; layers: list of (codes[K,N], scale, zp, bias|None); bf16 activations between the layers
+    (the last layer's output stays f32), as dllm_model_forward(path = DLLM_PATH_I8) runs it."""
+    h = _f32(x_tokens)
+    for i, (codes, scale, zp, bias) in enumerate(layers):
+        h = linear_i8_deq(h, codes, scale, zp, bias)
+        if i + 1 < len(layers):
+            h = bf16_round(h)
+    return h

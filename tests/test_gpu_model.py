@@ -191,6 +191,37 @@ def test_stack_forward_umma(ctx, O):
     model.close()
 
 
+@pytest.mark.parametrize("bits", [4, 8])
+def test_stack_forward_i8_mode(ctx, O, bits):
+    """int8 denoise mode of the layer stack (path = DLLM_PATH_I8): per-tensor codes (the reference's scheme,
+    quantization.rs:38-79), bf16 activations between the layers, each quantized per token to int8 in front of its exact
+    integer linear.  Against the oracle's restatement of that arithmetic: 2e-3 relative (a 1-ulp difference in one layer's
+    output can move a bf16 rounding or an int8 code of the next); against the reference's f64 stack:
+    <= 1e-2 * sqrt(n_linears) relative Frobenius error, the bound the bf16 stack is held to."""
+    from dllm_b200 import PATH_I8, QWeight
+    from dllm_b200.diffuse_llm import QuantizedDiffusionModel
+    rng = np.random.default_rng(20 + bits)
+    dims = [256, 256, 512, 256, 256]
+    layers, ref = [], []
+    for K, N in zip(dims[:-1], dims[1:]):
+        w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(F)
+        b = (rng.standard_normal(N) * 0.1).astype(F)
+        layers.append(QWeight.quantize(ctx, w, bits, 0, b))
+        c, s, z = O.quantize_tensor(w, bits)
+        ref.append((c.reshape(K, N), s, z, b))
+    model = QuantizedDiffusionModel(layers, 256, ctx=ctx, path=PATH_I8)
+    x = rng.standard_normal((8, 256 * 40)).astype(F)         # 320 tokens (ragged against the 128-token tiles)
+    y = model.forward(x)
+    exp = O.model_forward_i8(x.reshape(-1, 256), ref).reshape(8, -1)
+    assert np.linalg.norm(y - exp) <= 2e-3 * np.linalg.norm(exp)
+    h = x.reshape(-1, 256).astype(np.float64)
+    for (c, s, z, b) in ref:
+        h = h @ ((c.astype(np.float64) - z) * s) + b
+    rel = np.linalg.norm(y.reshape(-1, 256) - h) / np.linalg.norm(h)
+    assert rel <= 1e-2 * np.sqrt(len(layers)), rel
+    model.close()
+
+
 def test_simple_diffusion_model_is_the_reference_layer(ctx, O):
     """SimpleDiffusionModel: one linear x·W+b, weights N(0,1)*0.02, bias 0 (lib.rs:775-813)."""
     from dllm_b200 import PATH_SIMT

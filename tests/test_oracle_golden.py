@@ -323,3 +323,38 @@ def test_linear_i8_oracle_against_plain_loops_and_the_float_oracle():
     assert np.all(np.abs(yf - np.float64(scale) * y) <= 1e-6 * bound + 1e-12)
     with pytest.raises(AssertionError):
         O.linear_i8(xq, codes, 2.5)                       # quantize_tensor's zero-points are integers
+
+
+def test_int8_mode_restatement_stays_within_the_stated_bound_of_the_f64_stack():
+    """The oracle's restatement of the int8 denoise mode (DLLM_PATH_I8; not a reference mode): bf16 rounding equals torch's,
+    the activation quantizer's codes / sums / steps are self-consistent, and the stack stays within 1e-2 * sqrt(n_linears)
+    relative Frobenius error of the reference's arithmetic in f64 (lib.rs:812 on dequantize_tensor's output)."""
+    import torch
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((64, 1000)) * 3).astype(np.float32)
+    x[0, :3] = [0.0, -0.0, 1e-40]
+    assert np.array_equal(O.bf16_round(x).view(np.uint32), torch.from_numpy(x).bfloat16().float().numpy().view(np.uint32))
+    q, rs, sm = O.rowquant_i8(O.bf16_round(x), 0.5)
+    assert q.dtype == np.int8 and np.abs(q).max() == 127 and np.array_equal(sm, q.astype(np.int64).sum(1))
+    assert np.all(np.abs(q.astype(np.float64) * (rs / 0.5)[:, None] - O.bf16_round(x)) <= 0.5001 * (rs / 0.5)[:, None])
+    q0, rs0, sm0 = O.rowquant_i8(np.zeros((2, 64), np.float32), 0.25)
+    assert not q0.any() and np.all(rs0 == 0.25) and not sm0.any()
+    for bits in (4, 8):
+        dims = [256, 256, 512, 256, 256]
+        layers = []
+        for K, N in zip(dims[:-1], dims[1:]):
+            w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+            b = (rng.standard_normal(N) * 0.1).astype(np.float32)
+            c, s, z = O.quantize_tensor(w, bits)
+            layers.append((c.reshape(K, N), s, z, b))
+        xt = rng.standard_normal((256, 256)).astype(np.float32)
+        h = xt.astype(np.float64)
+        for c, s, z, b in layers:
+            h = h @ ((c.astype(np.float64) - z) * s) + b
+        y = O.model_forward_i8(xt, layers)
+        assert np.linalg.norm(y - h) <= 1e-2 * np.sqrt(len(layers)) * np.linalg.norm(h)
+        c, s, z, b = layers[0]
+        y1 = O.linear_i8_deq(xt, c, s, z, b)
+        h1 = xt.astype(np.float64) @ ((c.astype(np.float64) - z) * s) + b
+        assert np.linalg.norm(y1 - h1) <= 1e-2 * np.linalg.norm(h1)
