@@ -249,6 +249,77 @@ class Timer:
         return v
 
 
+def int8_stack_block(ctx, stream):
+    """configs[2] stack in the int8 denoise mode next to the bf16 mode on the same per-tensor weights (rank 0, N = 1)."""
+    import torch
+    import dllm_b200
+    from dllm_b200 import QWeight
+    # int8 denoise mode (DLLM_PATH_I8) of the whole 1B-class stack: the reference's per-tensor 4-bit codes, activations
+    # quantized per token to int8 in front of every linear, kind::i8 with the dequantization fused into the epilogue — next to the
+    # bf16 mode on the SAME per-tensor weights, and both against the f32-faithful SIMT stack on 1024 of the 8192 tokens
+    from dllm_b200.diffuse_llm import DiffusionConfig, QuantizedDiffusionModel
+    H1, shapes1 = layer_shapes("1b")
+    feat1 = CANVAS * H1
+    g1 = torch.Generator(device="cuda").manual_seed(777)
+    lay = []
+    for (K1, N1) in shapes1:
+        w1 = torch.randn(K1, N1, device="cuda", generator=g1) * (1.0 / K1 ** 0.5)
+        torch.cuda.synchronize()
+        lay.append(QWeight.quantize_dev(ctx, w1.data_ptr(), K1, N1, 4, 0))
+        ctx.sync()
+        del w1
+    cfg1 = DiffusionConfig(num_timesteps=1000, hidden_size=H1, use_kv_cache=False)
+    xs = torch.randn(BATCH, feat1, device="cuda", generator=g1)
+    z1 = torch.randn(BATCH, feat1, device="cuda", generator=g1)
+    stack = {"workload": "configs[2] stack with per-tensor 4-bit weights (group_size 0, quantization.rs:38-79), 8192 tokens",
+             "kernels": "rowquant_i8_kernel + umma_qlinear_pair2_kernel<.., int8> (tcgen05 cta_group::2 kind::i8, 256-token tiles, dequantization fused into the epilogue)"}
+    preds = {}
+    for name, pth in (("int8", dllm_b200.PATH_I8), ("bf16", dllm_b200.PATH_UMMA), ("f32_simt", dllm_b200.PATH_SIMT)):
+        mdl = QuantizedDiffusionModel(lay, H1, cfg1, ctx, pth)
+        nb = 4 if name == "f32_simt" else BATCH
+        pred = torch.empty(nb, feat1, device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            mdl.forward_dev(xs.data_ptr(), nb, feat1, pred.data_ptr())
+            stream.synchronize()
+        preds[name] = pred[:4].clone()
+        if name != "f32_simt":
+            xw = xs.clone()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ctx.launches
+            with torch.cuda.stream(stream):
+                for i in range(3):
+                    mdl.denoise_step_dev(xw.data_ptr(), z1.data_ptr(), 999 - i, BATCH, feat1)
+                stream.synchronize()
+                l0 = ctx.launches
+                e0.record(stream)
+                for i in range(10):
+                    mdl.denoise_step_dev(xw.data_ptr(), z1.data_ptr(), 900 - i, BATCH, feat1)
+                e1.record(stream)
+                e1.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            stack[name] = {"ms_per_step": round(ms, 3), "steps_per_sec": round(1e3 / ms, 2), "launches_per_step": (ctx.launches - l0) // 10}
+            # second pass: every linear of two steps between two CUDA events (what is left of the step is the activation quantizer,
+            # the f32 -> bf16 cast and p_sample)
+            ctx._ck(ctx._lib.dllm_profile_begin(ctx.h))
+            with torch.cuda.stream(stream):
+                for i in range(2):
+                    mdl.denoise_step_dev(xw.data_ptr(), z1.data_ptr(), 800 - i, BATCH, feat1)
+            nl, pms, fl, by = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
+            ctx._ck(ctx._lib.dllm_profile_end(ctx.h, C.byref(nl), C.byref(pms), C.byref(fl), C.byref(by)))
+            if nl.value:
+                stack[name]["linears_ms_per_step"] = round(pms.value / 2, 3)
+                stack[name]["linears_T_ops_per_s"] = round(fl.value / pms.value / 1e9, 1)
+        mdl.close()
+    ref = preds["f32_simt"].double()
+    for name in ("int8", "bf16"):
+        stack[name]["rel_err_vs_f32_stack"] = float(torch.linalg.norm(preds[name].double() - ref) / torch.linalg.norm(ref))
+    stack["tolerance"] = "1e-2 * sqrt(120 linears) relative Frobenius error, as the bf16 stack (tests/test_gpu_model.py)"
+    for q in lay:
+        q.close()
+    return stack
+
+
 def secondary_metrics(ctx, stream, pk):
     """The GB/s half of BASELINE.json's metric, on rank 0 after the timed denoise steps: the dequant-GEMV
     (configs[1]: 2-, 4- and 8-bit, K=N=14336 and 8192, group 128) replayed from a CUDA graph over a pool of weights larger
@@ -326,60 +397,7 @@ def secondary_metrics(ctx, stream, pk):
         qt.close()
         del wi, xq, yi
     out["int8_linear"] = i8
-    # int8 denoise mode (DLLM_PATH_I8) of the whole 1B-class stack: the reference's per-tensor 4-bit codes, activations
-    # quantized per token to int8 in front of every linear, kind::i8 with the dequantization fused into the epilogue — next to the
-    # bf16 mode on the SAME per-tensor weights, and both against the f32-faithful SIMT stack on 1024 of the 8192 tokens
-    from dllm_b200.diffuse_llm import DiffusionConfig, QuantizedDiffusionModel
-    H1, shapes1 = layer_shapes("1b")
-    feat1 = CANVAS * H1
-    g1 = torch.Generator(device="cuda").manual_seed(777)
-    lay = []
-    for (K1, N1) in shapes1:
-        w1 = torch.randn(K1, N1, device="cuda", generator=g1) * (1.0 / K1 ** 0.5)
-        torch.cuda.synchronize()
-        lay.append(QWeight.quantize_dev(ctx, w1.data_ptr(), K1, N1, 4, 0))
-        ctx.sync()
-        del w1
-    cfg1 = DiffusionConfig(num_timesteps=1000, hidden_size=H1, use_kv_cache=False)
-    xs = torch.randn(BATCH, feat1, device="cuda", generator=g1)
-    z1 = torch.randn(BATCH, feat1, device="cuda", generator=g1)
-    stack = {"workload": "configs[2] stack with per-tensor 4-bit weights (group_size 0, quantization.rs:38-79), 8192 tokens",
-             "kernels": "rowquant_i8_kernel + umma_qlinear_kernel<.., int8> with fused dequantization epilogue"}
-    preds = {}
-    for name, pth in (("int8", dllm_b200.PATH_I8), ("bf16", dllm_b200.PATH_UMMA), ("f32_simt", dllm_b200.PATH_SIMT)):
-        mdl = QuantizedDiffusionModel(lay, H1, cfg1, ctx, pth)
-        nb = 4 if name == "f32_simt" else BATCH
-        pred = torch.empty(nb, feat1, device="cuda")
-        torch.cuda.synchronize()
-        with torch.cuda.stream(stream):
-            mdl.forward_dev(xs.data_ptr(), nb, feat1, pred.data_ptr())
-            stream.synchronize()
-        preds[name] = pred[:4].clone()
-        if name != "f32_simt":
-            xw = xs.clone()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            l0 = ctx.launches
-            with torch.cuda.stream(stream):
-                for i in range(3):
-                    mdl.denoise_step_dev(xw.data_ptr(), z1.data_ptr(), 999 - i, BATCH, feat1)
-                stream.synchronize()
-                l0 = ctx.launches
-                e0.record(stream)
-                for i in range(10):
-                    mdl.denoise_step_dev(xw.data_ptr(), z1.data_ptr(), 900 - i, BATCH, feat1)
-                e1.record(stream)
-                e1.synchronize()
-            ms = e0.elapsed_time(e1) / 10
-            stack[name] = {"ms_per_step": round(ms, 3), "steps_per_sec": round(1e3 / ms, 2), "launches_per_step": (ctx.launches - l0) // 10}
-        mdl.close()
-    ref = preds["f32_simt"].double()
-    for name in ("int8", "bf16"):
-        stack[name]["rel_err_vs_f32_stack"] = float(torch.linalg.norm(preds[name].double() - ref) / torch.linalg.norm(ref))
-    stack["tolerance"] = "1e-2 * sqrt(120 linears) relative Frobenius error, as the bf16 stack (tests/test_gpu_model.py)"
-    out["int8_stack"] = stack
-    for q in lay:
-        q.close()
-    del xs, z1, preds
+    out["int8_stack"] = int8_stack_block(ctx, stream)
     rows, dim = 1 << 16, 4096
     x = torch.randn(rows, dim, device="cuda")
     codes = torch.empty(rows * dim // 2, dtype=torch.uint8, device="cuda")
@@ -880,12 +898,19 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the GEMV / KV-quant GB/s extras")
     ap.add_argument("--no-tp7b", action="store_true", help="skip the 7B-class tensor-parallel block (configs[3])")
     ap.add_argument("--no-kv32k", action="store_true", help="skip the 32k-context KV block (configs[4])")
+    ap.add_argument("--only-int8-stack", action="store_true", help="print the int8_stack block alone (development)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.only_int8_stack:
+        import torch
+        import dllm_b200
+        st = torch.cuda.Stream()
+        print(json.dumps(int8_stack_block(dllm_b200.Context(0, stream=st.cuda_stream), st)), flush=True)
         return
     run_ours(args, rank, world, local_rank)
 

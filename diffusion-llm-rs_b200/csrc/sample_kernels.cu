@@ -124,7 +124,9 @@ int32_t k_f32_to_bf16(dllm_ctx *ctx, const float *in_dev, size_t n, void *out_bf
 }
 
 namespace {
-// one CTA per token row: absmax (first pass), then codes / row sum (second pass: the row comes from L1 / L2)
+// one CTA per token row: absmax, then codes / row sum.  V > 0: the row (<= 2048 V elements) stays in registers between the two
+// passes (one HBM read); V == 0: any K, the second pass re-reads the row (from L1 / L2)
+template <int V>
 __global__ void __launch_bounds__(256) rowquant_i8_kernel(const __nv_bfloat16 *__restrict__ x, uint32_t K, float wscale,
                                                           int8_t *__restrict__ xq, float *__restrict__ rowscale, int32_t *__restrict__ rowsum) {
     __shared__ float s_max[8];
@@ -132,15 +134,27 @@ __global__ void __launch_bounds__(256) rowquant_i8_kernel(const __nv_bfloat16 *_
     const size_t row = blockIdx.x;
     const uint4 *src = reinterpret_cast<const uint4 *>(x + row * K);
     const uint32_t n8 = K / 8;
+    constexpr int R = V > 0 ? V : 1;
+    uint4 reg[R];
     float m = 0.f;
-    for (uint32_t i = threadIdx.x; i < n8; i += 256) {
-        const uint4 v = __ldg(src + i);
+    auto absmax8 = [&](const uint4 &v) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             m = fmaxf(m, fabsf(__uint_as_float(w[e] << 16)));
             m = fmaxf(m, fabsf(__uint_as_float(w[e] & 0xffff0000u)));
         }
+    };
+    if constexpr (V > 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const uint32_t idx = threadIdx.x + 256u * i;
+            reg[i] = idx < n8 ? __ldg(src + idx) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) absmax8(reg[i]);
+    } else {
+        for (uint32_t i = threadIdx.x; i < n8; i += 256) absmax8(__ldg(src + i));
     }
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
@@ -153,8 +167,7 @@ __global__ void __launch_bounds__(256) rowquant_i8_kernel(const __nv_bfloat16 *_
     const float inv = m > 0.f ? 127.f / m : 0.f;
     int acc = 0;
     uint2 *dst = reinterpret_cast<uint2 *>(xq + row * K);
-    for (uint32_t i = threadIdx.x; i < n8; i += 256) {
-        const uint4 v = __ldg(src + i);
+    auto encode8 = [&](const uint4 &v, uint32_t idx) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         int q[8];
 #pragma unroll
@@ -165,9 +178,18 @@ __global__ void __launch_bounds__(256) rowquant_i8_kernel(const __nv_bfloat16 *_
         uint2 o;
         o.x = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
         o.y = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
-        dst[i] = o;
+        dst[idx] = o;
         acc = __dp4a((int)o.x, 0x01010101, acc);
         acc = __dp4a((int)o.y, 0x01010101, acc);
+    };
+    if constexpr (V > 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const uint32_t idx = threadIdx.x + 256u * i;
+            if (idx < n8) encode8(reg[i], idx);
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n8; i += 256) encode8(__ldg(src + i), i);
     }
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
@@ -188,7 +210,14 @@ int32_t k_rowquant_i8(dllm_ctx *ctx, const void *x_bf16_dev, size_t M, size_t K,
     if (M == 0) return DLLM_OK;
     if (K % 8 != 0 || (reinterpret_cast<uintptr_t>(x_bf16_dev) & 15u) || (reinterpret_cast<uintptr_t>(xq_dev) & 7u))
         DLLM_FAIL(ctx, DLLM_ERR_INVALID_PARAMS, "int8 activation quantizer: K %% 8 == 0 and aligned buffers required");
-    rowquant_i8_kernel<<<(unsigned)M, 256, 0, ctx->stream>>>((const __nv_bfloat16 *)x_bf16_dev, (uint32_t)K, wscale, xq_dev, rowscale_dev, rowsum_dev);
+    const __nv_bfloat16 *x = (const __nv_bfloat16 *)x_bf16_dev;
+    const uint32_t k = (uint32_t)K;
+    const unsigned g = (unsigned)M;
+    if (K <= 2048) rowquant_i8_kernel<1><<<g, 256, 0, ctx->stream>>>(x, k, wscale, xq_dev, rowscale_dev, rowsum_dev);
+    else if (K <= 4096) rowquant_i8_kernel<2><<<g, 256, 0, ctx->stream>>>(x, k, wscale, xq_dev, rowscale_dev, rowsum_dev);
+    else if (K <= 8192) rowquant_i8_kernel<4><<<g, 256, 0, ctx->stream>>>(x, k, wscale, xq_dev, rowscale_dev, rowsum_dev);
+    else if (K <= 16384) rowquant_i8_kernel<8><<<g, 256, 0, ctx->stream>>>(x, k, wscale, xq_dev, rowscale_dev, rowsum_dev);
+    else rowquant_i8_kernel<0><<<g, 256, 0, ctx->stream>>>(x, k, wscale, xq_dev, rowscale_dev, rowsum_dev);
     LAUNCH_CHECK(ctx);
     return DLLM_OK;
 }

@@ -117,6 +117,11 @@ __device__ __forceinline__ void tma_load_3d_pair(void *smem_dst, const CUtensorM
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         :: "r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t *slot, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -131,6 +136,15 @@ __device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, u
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// the same with kind::i8 (u8 x s8 operands, s32 accumulate: exact)
+__device__ __forceinline__ void umma_ts_pair_i8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t"
         "}\n" :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed
@@ -1153,6 +1167,10 @@ struct Pair2Args {
     unsigned int *gate_err;
     uint32_t dbg;              // timing experiments only (DLLM_UMMA_DBG): 1 skip MMAs, 2 skip dequant math, 8 skip activation loads, 64 skip stores
     long long *trace;          // dbg & 128: clock64 stamps of cluster 0's leader CTA: [role 0..7][256]
+    // int8 variant (the int8 denoise mode): per token the int8 row sum and weight scale x activation step, and the weight's zero-point
+    const int32_t *i8_rowsum;
+    const float *i8_rowscale;
+    int32_t i8_zp;
 };
 #define TRACE2(role, idx) do { if ((a.dbg & 128) && blockIdx.x == 0 && (idx) < 256) a.trace[(role) * 256 + (idx)] = clock64(); } while (0)
 
@@ -1172,13 +1190,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
                  : "r"(taddr) : "memory");
 }
 
-template <int CB>
+template <int CB, bool I8 = false>
 struct CfgP2 {
     static constexpr int KBS = 2;
     static constexpr int kXSlabMax = 128 * 128;                      // one k-block of this CTA's half of the tokens (<= 128 rows x 128 B)
-    static constexpr int kXStage = KBS * kXSlabMax;
-    static constexpr int kACols = 32, kSlotCols = KBS * kACols;
-    static constexpr int kSlots = 4;                                 // X ring (shared memory) and A ring (tensor memory): same depth, one commit frees both
+    // int8: one 128-byte row holds 128 k = BOTH k-blocks of the stage; a k-block of A is 16 tensor-memory columns (64 bytes per row)
+    static constexpr int kXStage = I8 ? kXSlabMax : KBS * kXSlabMax;
+    static constexpr int kACols = I8 ? 16 : 32, kSlotCols = KBS * kACols;
+    // X ring (shared memory) and A ring (tensor memory): same depth, one commit frees both.  (int8: a stage is 512 cycles of MMAs
+    // instead of 1024, so both rings are deeper)
+    static constexpr int kSlots = I8 ? 6 : 4;
     static constexpr int kAccCols = 256;                             // two 128-column halves
     static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
     static constexpr int kPBytes = 128 * 8;
@@ -1193,7 +1214,10 @@ struct CfgP2 {
     static constexpr int kWOffset = kOutOffset + kOutBytes;
     static constexpr int kBarOffset = kWOffset + kWStages * kWStage;
     static constexpr int kNumBars = 2 * kWStages + 3 * kSlots + 4;
-    static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;
+    // int8: {zp x row sum, weight scale x activation step} of the tile's <= 256 tokens, double-buffered by tile parity
+    static constexpr int kTabOffset = kBarOffset + ((kNumBars * 8 + 16 + 15) & ~15);
+    static constexpr int kTabBytes = I8 ? 2 * 256 * 8 : 0;
+    static constexpr int kTotal = kTabOffset + kTabBytes + 1024;
     static_assert(kXStage % 1024 == 0 && kWStage % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned stages");
     static_assert(kWStages >= kSlots, "W ring must be at least as deep as the A ring");
     static_assert(kTotal <= 227 * 1024, "shared memory over-subscribed");
@@ -1219,7 +1243,22 @@ __device__ __forceinline__ uint32_t pack_bf16_bias(uint32_t lo, uint32_t hi, flo
 // q (32..64, multiple of 8) accumulator columns of this warp's lanes -> packed bf16 pairs.  Two tensor-memory loads are in
 // flight per wait: a load + wait round trip costs ~500 cycles while the tensor pipe is busy, and the half is only handed
 // back to the MMA warp when its last column is in registers.
-__device__ __forceinline__ void drain_columns(uint32_t t_acc, uint32_t q, float bias, uint32_t *pk) {
+// int8 variant: the accumulators are exact s32 sums; column j (a token) leaves as (sum - zp rowsum_j) * (scale step_j) + bias with
+// {zp rowsum_j, scale step_j} read from the shared-memory table `tab` (address of this warp's first column's entry)
+__device__ __forceinline__ uint32_t pack_bf16_deq(uint32_t lo, uint32_t hi, float bias, uint32_t tab) {
+    uint32_t z0, s0, z1, s1;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(z0), "=r"(s0), "=r"(z1), "=r"(s1) : "r"(tab));
+    const float f0 = fmaf((float)((int32_t)lo - (int32_t)z0), __uint_as_float(s0), bias);
+    const float f1 = fmaf((float)((int32_t)hi - (int32_t)z1), __uint_as_float(s1), bias);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
+    return *reinterpret_cast<uint32_t *>(&b2);
+}
+template <bool I8 = false>
+__device__ __forceinline__ void drain_columns(uint32_t t_acc, uint32_t q, float bias, uint32_t *pk, uint32_t tab = 0) {
+    auto pack2 = [&](uint32_t lo, uint32_t hi, float b, uint32_t col) -> uint32_t {
+        if constexpr (I8) return pack_bf16_deq(lo, hi, b, tab + col * 8u);
+        else return pack_bf16_bias(lo, hi, b);
+    };
 #pragma unroll
     for (int p2 = 0; p2 < 2; ++p2) {
         const uint32_t c = (uint32_t)(p2 * 32);
@@ -1230,17 +1269,17 @@ __device__ __forceinline__ void drain_columns(uint32_t t_acc, uint32_t q, float 
         tmem_ld_wait();
         if (a16) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) pk[p2 * 16 + j] = pack_bf16_bias(v[2 * j], v[2 * j + 1], bias);
+            for (int j = 0; j < 8; ++j) pk[p2 * 16 + j] = pack2(v[2 * j], v[2 * j + 1], bias, c + 2 * j);
         } else if (a8) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) pk[p2 * 16 + j] = pack_bf16_bias(v[2 * j], v[2 * j + 1], bias);
+            for (int j = 0; j < 4; ++j) pk[p2 * 16 + j] = pack2(v[2 * j], v[2 * j + 1], bias, c + 2 * j);
         }
         if (b16) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) pk[p2 * 16 + 8 + j] = pack_bf16_bias(v[16 + 2 * j], v[16 + 2 * j + 1], bias);
+            for (int j = 0; j < 8; ++j) pk[p2 * 16 + 8 + j] = pack2(v[16 + 2 * j], v[16 + 2 * j + 1], bias, c + 16 + 2 * j);
         } else if (b8) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) pk[p2 * 16 + 8 + j] = pack_bf16_bias(v[16 + 2 * j], v[16 + 2 * j + 1], bias);
+            for (int j = 0; j < 4; ++j) pk[p2 * 16 + 8 + j] = pack2(v[16 + 2 * j], v[16 + 2 * j + 1], bias, c + 16 + 2 * j);
         }
     }
 }
@@ -1259,11 +1298,14 @@ __device__ __forceinline__ void stage_columns(uint32_t sbase, uint32_t q, const 
     }
 }
 
-template <int CB, int NDQ>
+template <int CB, int NDQ, bool I8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((12 + 4 * NDQ) * 32, 1)
 umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                           const __grid_constant__ RsMaps rs, const Pair2Args a) {
-    using C = CfgP2<CB>;
+    // I8: the int8 variant (int8 denoise mode).  tmap_x = the int8 activations [M, K bytes] (box {128 k, ntok/2 tokens}: one
+    // SWIZZLE_128B tile holds both k-blocks of a stage), A = the codes as unsigned bytes (16 tensor-memory columns per k-block),
+    // tcgen05.mma.kind::i8 with K = 32 per instruction, s32 accumulators, and the dequantization in the epilogue.
+    using C = CfgP2<CB, I8>;
     constexpr int KBS = C::KBS, kACols = C::kACols;
     constexpr int SW = C::kWStages, A = C::kSlots;
     constexpr int kEpiWarp0 = 4 + 4 * NDQ;
@@ -1333,7 +1375,11 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 const uint32_t s = it % A, ph = (it / A) & 1;
                 mbar_wait(xempty + s, ph ^ 1);
                 if (elect_one()) {
-                    if (!(a.dbg & 8)) {
+                    if constexpr (I8) {
+                        // box {128 k, ntok/2 tokens}: both k-blocks of the stage; tokens past M and k past K are zero-filled
+                        if (rank == 0) mbar_arrive_expect_tx(xfull + s, 2 * slab);
+                        tma_load_2d_pair(smem + s * C::kXStage, &tmap_x, xfull_leader + s * 8, (int)(kb * WL_TILE_K), (int)(mt * ntok + rank * half_rows));
+                    } else if (!(a.dbg & 8)) {
                         if (rank == 0) mbar_arrive_expect_tx(xfull + s, 2 * KBS * slab);
                         // box {64 k, ntok/2 tokens, KBS k-blocks}; tokens past M and k-blocks past K are zero-filled
                         tma_load_3d_pair(smem + s * C::kXStage, &tmap_x, xfull_leader + s * 8, 0, (int)(mt * ntok + rank * half_rows), (int)kb);
@@ -1372,7 +1418,9 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         }
     } else if (warp == 1 && rank == 0) {
         // ===================== MMA issuer (leader CTA; one elected lane): per stage, half 0 then half 1 =====================
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((nh >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        // c = f32, a = b = bf16 — int8: c = s32 (2 << 4), a = u8 (0 << 7), b = s8 (1 << 10) — K-major A and B, N >> 3 at 17, M >> 4 at 24
+        const uint32_t idesc = (I8 ? ((2u << 4) | (0u << 7) | (1u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10))) |
+                               ((nh >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
         uint32_t it = 0, n_item = 0;
         for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
             const uint32_t tph = n_item & 1;
@@ -1395,10 +1443,18 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 if (elect_one()) {
                     if (!(a.dbg & 1)) {
                         for (uint32_t sub = 0; sub < nk; ++sub) {
-                            const uint64_t bdesc = make_b_desc(stage_addr + sub * slab);
+                            if constexpr (I8) {
+                                // 32 k (32 bytes of the 128-byte row, 8 tensor-memory columns of A) per MMA: two per k-block
+                                const uint64_t bdesc = make_b_desc(stage_addr);
 #pragma unroll
-                            for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
-                                umma_ts_pair(tmem_base, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
+                                for (int k2 = 0; k2 < 2; ++k2)
+                                    umma_ts_pair_i8(tmem_base, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
+                            } else {
+                                const uint64_t bdesc = make_b_desc(stage_addr + sub * slab);
+#pragma unroll
+                                for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                                    umma_ts_pair(tmem_base, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
+                            }
                         }
                     }
                     if (last) umma_commit_pair(tfull + 0);
@@ -1416,10 +1472,17 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 if (elect_one()) {
                     if (!(a.dbg & 1)) {
                         for (uint32_t sub = 0; sub < nk; ++sub) {
-                            const uint64_t bdesc = make_b_desc(stage_addr + sub * slab + q * 128u);
+                            if constexpr (I8) {
+                                const uint64_t bdesc = make_b_desc(stage_addr + q * 128u);
 #pragma unroll
-                            for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
-                                umma_ts_pair(tmem_base + 128, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
+                                for (int k2 = 0; k2 < 2; ++k2)
+                                    umma_ts_pair_i8(tmem_base + 128, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
+                            } else {
+                                const uint64_t bdesc = make_b_desc(stage_addr + sub * slab + q * 128u);
+#pragma unroll
+                                for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                                    umma_ts_pair(tmem_base + 128, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
+                            }
                         }
                     }
                     if (last) umma_commit_pair(tfull + 1);
@@ -1449,14 +1512,21 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 const uint8_t *stage = smem_w + sw * C::kWStage;
                 for (uint32_t sub = 0; sub < nk; ++sub) {
                     const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes);
-                    const uint2 prm = lds64(smem_u32(stage + KBS * C::kWBytes + sub * C::kPBytes) + (uint32_t)n_local * 8u);
-                    uint32_t vals[32];
-                    if (!(a.dbg & 2)) dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
-                    else {
+                    if constexpr (I8) {
+                        // the codes as unsigned bytes in k order: no zero-point, no scale (both leave in the epilogue)
+                        uint32_t vals[16];
+                        unpack_kblock_u8<CB>(wpk, n_local, vals);
+                        tmem_st16(lane_addr + sl * C::kSlotCols + sub * kACols, vals);
+                    } else {
+                        const uint2 prm = lds64(smem_u32(stage + KBS * C::kWBytes + sub * C::kPBytes) + (uint32_t)n_local * 8u);
+                        uint32_t vals[32];
+                        if (!(a.dbg & 2)) dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
+                        else {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) vals[e] = prm.x + e;
+                            for (int e = 0; e < 32; ++e) vals[e] = prm.x + e;
+                        }
+                        tmem_st32(lane_addr + sl * C::kSlotCols + sub * kACols, vals);
                     }
-                    tmem_st32(lane_addr + sl * C::kSlotCols + sub * kACols, vals);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(wempty + sw);
@@ -1486,6 +1556,21 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const uint32_t n = nt * 128 + quarter * 32 + lane;
             const bool n_ok = nt < a.n_tiles && n < a.N && !(a.dbg & 64);
             const float bias = (a.bias != nullptr && n_ok) ? __ldg(a.bias + n) : 0.f;
+            uint32_t tab = 0;
+            if constexpr (I8) {
+                // {zp x row sum, weight scale x activation step} of the tile's tokens, in the order the accumulator columns hold
+                // them (entry part * half_rows + h * q + column); double-buffered by tile parity, so one barrier per tile is enough
+                tab = smem_u32(smem + C::kTabOffset) + (n_item & 1u) * 2048u;
+                const uint32_t e = threadIdx.x - (uint32_t)kEpiWarp0 * 32u;
+                if (e < ntok) {
+                    const uint32_t tok = mt * ntok + e;
+                    int32_t zs = 0;
+                    float sc = 0.f;
+                    if (tok < a.M) { zs = a.i8_zp * __ldg(a.i8_rowsum + tok); sc = __ldg(a.i8_rowscale + tok); }
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(tab + e * 8u), "r"((uint32_t)zs), "r"(__float_as_uint(sc)) : "memory");
+                }
+                named_bar_sync(1, 256);
+            }
             if (a.y_f32 == nullptr) {
                 // bf16 output.  Both accumulator halves are on the tensor pipe's critical path (they are single-buffered), so they
                 // are drained back to back: half 0 -> registers -> handed back -> written to the staging buffer (shared-memory
@@ -1530,7 +1615,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     mbar_wait(tfull + h, tph);
                     tc_fence_after();
                     if (warp == kEpiWarp0 && lane == 0) TRACE2(4 + h, n_item);
-                    drain_columns(t_acc, q, bias, pk);
+                    drain_columns<I8>(t_acc, q, bias, pk, tab + (part * half_rows + h * q) * 8u);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(tempty_leader + h * 8);   // this warp's columns are out: 16 such arrivals free the half
@@ -1573,7 +1658,14 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if (c0 + j < n_tok) {
-                                const float f = __uint_as_float(v[j]) + bias;
+                                float f;
+                                if constexpr (I8) {
+                                    uint32_t zs, sc;
+                                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(zs), "=r"(sc) : "r"(tab + (part * half_rows + h * q + c0 + j) * 8u));
+                                    f = fmaf((float)((int32_t)v[j] - (int32_t)zs), __uint_as_float(sc), bias);
+                                } else {
+                                    f = __uint_as_float(v[j]) + bias;
+                                }
                                 a.y_f32[o + (size_t)j * ldy] = f;
                                 if (a.y_bf16) a.y_bf16[o + (size_t)j * ldy] = __float2bfloat16_rn(f);
                             }
@@ -2059,8 +2151,102 @@ int32_t launch_umma_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, 
     return DLLM_OK;
 }
 
+// ---- int8 variant of the 256-token CTA-pair kernel (the int8 denoise mode's dense linears) ----
+static bool pair2_i8_applicable(const dllm_ctx *ctx, const dllm_qweight *qw, size_t M, const I8Deq *dq) {
+    static const bool off = getenv("DLLM_I8_PAIR") && atoi(getenv("DLLM_I8_PAIR")) == 0;       // experiments: 0 = 1-CTA kernel only
+    if (off || !dq || qw->K % WL_TILE_K != 0 || M < 1024 || wl_container_bits(qw->bits) == 8) return false;
+    if (qw->K % 16 != 0) return false;                                         // row pitch of the int8 activations (TMA)
+    if (!dq->y_f32 && (qw->N % 8 != 0 || (reinterpret_cast<uintptr_t>(dq->y_bf16) & 15u) != 0)) return false;
+    const uint32_t n_pairs = (uint32_t)((qw->n_tiles + 1) / 2);
+    const uint32_t pairs_hw = (uint32_t)ctx->sm_count / 2;
+    const uint32_t ntok = pair2_pick_ntok(M, n_pairs, pairs_hw);
+    return (uint64_t)((M + ntok - 1) / ntok) * n_pairs >= pairs_hw / 2;
+}
+
+template <int CB>
+int32_t launch_umma_pair2_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, size_t M, const I8Deq *dq) {
+    using C = CfgP2<CB, true>;
+    constexpr int NDQ = kNDQ;
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    Pair2Args a;
+    memset(&a, 0, sizeof(a));
+    a.packed = qw->d_packed; a.dqparams = qw->d_dqparams; a.bias = qw->d_bias;
+    a.y_f32 = dq->y_f32; a.y_bf16 = (__nv_bfloat16 *)dq->y_bf16;
+    a.M = (uint32_t)M; a.N = (uint32_t)qw->N; a.Npad = (uint32_t)(qw->n_tiles * 128);
+    a.k_blocks = (uint32_t)qw->k_blocks; a.n_tiles = (uint32_t)qw->n_tiles; a.n_pairs = (a.n_tiles + 1) / 2;
+    a.group_kb = (uint32_t)(qw->group / WL_TILE_K);
+    const uint32_t pairs_hw = (uint32_t)ctx->sm_count / 2;
+    const char *ntok_s = getenv("DLLM_UMMA_NTOK2");                                                 // experiments only
+    const int ntok_env = ntok_s ? atoi(ntok_s) : 0;
+    a.ntok = (ntok_env >= 32 && ntok_env <= 256 && ntok_env % 32 == 0) ? (uint32_t)ntok_env : pair2_pick_ntok(M, a.n_pairs, pairs_hw);
+    a.rs_rows = 1; a.gate_rows = 1; a.gate_sub = 1;
+    a.m_tiles = (uint32_t)((M + a.ntok - 1) / a.ntok);
+    a.tiles = a.n_pairs * a.m_tiles;
+    a.i8_rowsum = dq->rowsum; a.i8_rowscale = dq->rowscale; a.i8_zp = (int32_t)qw->tensor_zp;
+
+    // int8 activations [M tokens, K bytes] row-major; one box = 128 k x ntok/2 tokens in the SWIZZLE_128B K-major layout
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)qw->K, (cuuint64_t)M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)qw->K};
+    const cuuint32_t box[2] = {2 * WL_TILE_K, a.ntok / 2};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(xq), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    CUtensorMap tmap_y = tmap;
+    if (!dq->y_f32) {
+        const cuuint64_t ydim[2] = {(cuuint64_t)qw->N, (cuuint64_t)M};
+        const cuuint64_t ystride[1] = {(cuuint64_t)qw->N * 2};
+        const cuuint32_t ybox[2] = {128, a.ntok / 4};
+        const cuuint32_t yestr[2] = {1, 1};
+        r = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dq->y_bf16, ydim, ystride, ybox, yestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
+    }
+    RsMaps rsm;
+    memset(&rsm, 0, sizeof(rsm));
+    DLLM_TRY(ensure_smem_attr(ctx, umma_qlinear_pair2_kernel<CB, NDQ, true>, C::kTotal));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->prof_on) {
+        while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) {
+            cudaEvent_t e;
+            CUDA_TRY(ctx, cudaEventCreate(&e));
+            ctx->prof_ev.push_back(e);
+        }
+        ev0 = ctx->prof_ev[2 * ctx->prof_n];
+        ev1 = ctx->prof_ev[2 * ctx->prof_n + 1];
+        CUDA_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    const uint32_t pairs = a.tiles < pairs_hw ? a.tiles : pairs_hw;
+    static const bool no_pdl = getenv("DLLM_UMMA_NO_PDL") != nullptr;      // experiments only
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3((12 + 4 * NDQ) * 32);
+    cfg.dynamicSmemBytes = C::kTotal;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, umma_qlinear_pair2_kernel<CB, NDQ, true>, tmap, tmap_y, rsm, a));
+    LAUNCH_CHECK(ctx);
+    if (ev1) {
+        CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
+        ctx->prof_n++;
+        ctx->prof_flops += 2.0 * (double)M * (double)qw->K * (double)qw->N;
+        ctx->prof_bytes += (double)qw->K * qw->N * qw->bits / 8.0 + 1.0 * M * qw->K + (dq->y_f32 ? 4.0 : 2.0) * M * qw->N;
+    }
+    return DLLM_OK;
+}
+
 template <int CB>
 int32_t launch_umma_i8_ntok(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, size_t M, int32_t *y, const I8Deq *dq = nullptr) {
+    if constexpr (CB != 8) {
+        if (pair2_i8_applicable(ctx, qw, M, dq)) return launch_umma_pair2_i8<CB>(ctx, qw, xq, M, dq);
+    }
     if (M <= 16) return launch_umma_i8<CB, 16>(ctx, qw, xq, M, y, dq);
     if (M <= 32) return launch_umma_i8<CB, 32>(ctx, qw, xq, M, y, dq);
     if (M <= 64) return launch_umma_i8<CB, 64>(ctx, qw, xq, M, y, dq);

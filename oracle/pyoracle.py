@@ -391,7 +391,8 @@ def linear_i8_deq(x, codes, scale, zp, bias=None):
     factored out.  The integer part is exact; the float epilogue is one int->f32 conversion and one fused multiply-add,
     evaluated here in f64 and rounded once (the device result may differ by 1 ulp of f32)."""
     q, rowscale, rowsum = rowquant_i8(bf16_round(x), scale)
-    e = q.astype(np.int64) @ np.asarray(codes, dtype=np.int64) - int(zp) * rowsum[:, None]
+    # (every partial sum is an integer below 2^53: the f64 matmul is exact, and BLAS-fast)
+    e = (q.astype(np.float64) @ np.asarray(codes, dtype=np.float64)).astype(np.int64) - int(zp) * rowsum[:, None]
     b = 0.0 if bias is None else _f32(bias).astype(np.float64)[None, :]
     return (e.astype(np.float32).astype(np.float64) * rowscale.astype(np.float64)[:, None] + b).astype(np.float32)
 

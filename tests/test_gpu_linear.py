@@ -392,6 +392,30 @@ def test_qlinear_i8_mode_matches_oracle(ctx, O, bits, shape):
     qw.close()
 
 
+@pytest.mark.parametrize("bits", [2, 4])
+@pytest.mark.parametrize("shape", [(512, 1024, 2560), (576, 1000, 2600), (2048, 2048, 4096), (192, 1536, 1111)])
+def test_qlinear_i8_mode_dense_shapes(ctx, O, bits, shape):
+    """The same on dense shapes (>= 1024 tokens): the CTA-pair kind::i8 kernel (256-token tiles), f32 output.  Ragged token
+    counts and columns, an odd number of k-blocks; same two bounds as above."""
+    from dllm_b200 import QWeight, PATH_I8
+    K, N, M = shape
+    rng = np.random.default_rng(K + N + M + bits)
+    w = make_w(rng, K, N)
+    b = (rng.standard_normal(N) * 0.1).astype(F)
+    qw = QWeight.quantize(ctx, w, bits, 0, b)
+    codes, scales, zps = qw.export()
+    s0, z0 = float(np.ravel(scales)[0]), float(np.ravel(zps)[0])
+    x = (rng.standard_normal((M, K)) * rng.uniform(0.1, 10.0, (M, 1))).astype(F)     # every token its own range
+    x[5] = 0.0
+    y = qw.forward(x, PATH_I8)
+    exp = O.linear_i8_deq(x, codes.reshape(K, N), s0, z0, b)
+    assert np.all(np.abs(y.astype(np.float64) - exp) <= 1.2e-7 * np.abs(exp) + 1e-30)
+    assert beq(y[5], b)
+    y64 = x.astype(np.float64) @ ((codes.reshape(K, N).astype(np.float64) - z0) * s0) + b
+    assert np.linalg.norm(y - y64) <= 1e-2 * np.linalg.norm(y64)
+    qw.close()
+
+
 def test_qlinear_i8_mode_refuses_grouped_weights(ctx):
     import dllm_b200
     from dllm_b200 import QWeight, PATH_I8

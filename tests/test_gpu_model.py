@@ -222,6 +222,34 @@ def test_stack_forward_i8_mode(ctx, O, bits):
     model.close()
 
 
+def test_stack_forward_i8_mode_dense(ctx, O):
+    """The int8 stack at 4096 tokens: every linear runs on the CTA-pair kind::i8 kernel, the inner ones with the staged bf16
+    epilogue.  Same bounds as the small stack."""
+    from dllm_b200 import PATH_I8, QWeight
+    from dllm_b200.diffuse_llm import QuantizedDiffusionModel
+    rng = np.random.default_rng(31)
+    dims = [512, 1024, 512, 512]
+    layers, ref = [], []
+    for K, N in zip(dims[:-1], dims[1:]):
+        w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(F)
+        b = (rng.standard_normal(N) * 0.1).astype(F)
+        layers.append(QWeight.quantize(ctx, w, 4, 0, b))
+        c, s, z = O.quantize_tensor(w, 4)
+        ref.append((c.reshape(K, N), s, z, b))
+    model = QuantizedDiffusionModel(layers, 512, ctx=ctx, path=PATH_I8)
+    x = rng.standard_normal((16, 512 * 256)).astype(F)        # 4096 tokens
+    y = model.forward(x)
+    exp = O.model_forward_i8(x.reshape(-1, 512), ref).reshape(16, -1)
+    assert np.linalg.norm(y - exp) <= 2e-3 * np.linalg.norm(exp)
+    h = x.reshape(-1, 512).astype(np.float64)
+    for (c, s, z, b) in ref:
+        h = h @ ((c.astype(np.float64) - z) * s) + b
+    rel = np.linalg.norm(y.reshape(-1, 512) - h) / np.linalg.norm(h)
+    assert rel <= 1e-2 * np.sqrt(len(layers)), rel
+    assert beq(model.forward(x), y)                            # run-to-run deterministic
+    model.close()
+
+
 def test_simple_diffusion_model_is_the_reference_layer(ctx, O):
     """SimpleDiffusionModel: one linear x·W+b, weights N(0,1)*0.02, bias 0 (lib.rs:775-813)."""
     from dllm_b200 import PATH_SIMT
