@@ -1197,10 +1197,24 @@ struct CfgP2 {
     // int8: one 128-byte row holds 128 k = BOTH k-blocks of the stage; a k-block of A is 16 tensor-memory columns (64 bytes per row)
     static constexpr int kXStage = I8 ? kXSlabMax : KBS * kXSlabMax;
     static constexpr int kACols = I8 ? 16 : 32, kSlotCols = KBS * kACols;
-    // X ring (shared memory) and A ring (tensor memory): same depth, one commit frees both.  (int8: a stage is 512 cycles of MMAs
-    // instead of 1024, so both rings are deeper)
-    static constexpr int kSlots = I8 ? 6 : 4;
-    static constexpr int kAccCols = 256;                             // two 128-column halves
+    // accumulator buffers of 128 columns (one token half each): two — the halves of a tile.  int8: the A ring is half as wide, which
+    // leaves room for a THIRD buffer (-DDLLM_I8_NBUF=3: tile t, half h lives in buffer (2 t + h) % 3, so the next tile's half 0 is
+    // accumulated while this tile's halves are drained) — but only beside a 4-slot A ring, and then the dequant warps' latency
+    // (1.5 K cycles per stage) bounds the stage period at 975 cycles instead of 750: measured slower (85.2 against 87.5 steps/s), so
+    // two buffers and six slots stay.
+#ifndef DLLM_I8_NBUF
+#define DLLM_I8_NBUF 2
+#endif
+    static constexpr int kAccBufs = I8 ? DLLM_I8_NBUF : 2;
+    // X ring (shared memory) and A ring (tensor memory): same depth, one commit frees both
+    static constexpr int kSlots = I8 ? (kAccBufs == 3 ? 4 : 6) : 4;
+    // how many stages half 0 is issued ahead of half 1 (1 = lock step)
+#ifndef DLLM_I8_PRE
+#define DLLM_I8_PRE 2
+#endif
+    static constexpr int kPre = I8 ? DLLM_I8_PRE : 1;
+    static_assert(kPre >= 1 && kPre + 1 < kSlots, "half 0 cannot run further ahead than the rings are deep");
+    static constexpr int kAccCols = kAccBufs * 128;
     static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
     static constexpr int kPBytes = 128 * 8;
     static constexpr int kWStage = KBS * (kWBytes + kPBytes);
@@ -1213,7 +1227,7 @@ struct CfgP2 {
     static constexpr int kOutOffset = kSlots * kXStage;
     static constexpr int kWOffset = kOutOffset + kOutBytes;
     static constexpr int kBarOffset = kWOffset + kWStages * kWStage;
-    static constexpr int kNumBars = 2 * kWStages + 3 * kSlots + 4;
+    static constexpr int kNumBars = 2 * kWStages + 3 * kSlots + 2 * kAccBufs;
     // int8: {zp x row sum, weight scale x activation step} of the tile's <= 256 tokens, double-buffered by tile parity
     static constexpr int kTabOffset = kBarOffset + ((kNumBars * 8 + 16 + 15) & ~15);
     static constexpr int kTabBytes = I8 ? 2 * 256 * 8 : 0;
@@ -1253,8 +1267,16 @@ __device__ __forceinline__ uint32_t pack_bf16_deq(uint32_t lo, uint32_t hi, floa
     __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
     return *reinterpret_cast<uint32_t *>(&b2);
 }
-template <bool I8 = false>
-__device__ __forceinline__ void drain_columns(uint32_t t_acc, uint32_t q, float bias, uint32_t *pk, uint32_t tab = 0) {
+// (Tried for int8: all 64 columns requested before ONE wait, buffer handed back, then the conversion of all of them — half 0 is handed
+//  back after 1.9 K cycles instead of 3.0 K, but the conversion of its 64 columns (spilling) then sits in front of half 1's drain:
+//  8.7 K cycles per tile boundary instead of 6.3 K, 75.8 against 87.5 steps/s.  With two unpack groups instead of three — 640 threads,
+//  96 registers, hardly any spill — the kernel is slower as it stands (83.5 steps/s: the unpack latency of 1.5 K cycles per stage needs
+//  three groups) and slower still with that drain (69.2).  The epilogue warps' 6 K cycles per tile — two tensor-memory round trips and
+//  8 instructions per output pair, on sub-cores they share with the unpack warps — against 12 K cycles of MMAs at K = 2048 are what
+//  is left between this kernel and the tensor pipe.)
+struct NoRelease { __device__ __forceinline__ void operator()() const {} };
+template <bool I8 = false, class Rel = NoRelease>
+__device__ __forceinline__ void drain_columns(uint32_t t_acc, uint32_t q, float bias, uint32_t *pk, uint32_t tab = 0, Rel release = Rel()) {
     auto pack2 = [&](uint32_t lo, uint32_t hi, float b, uint32_t col) -> uint32_t {
         if constexpr (I8) return pack_bf16_deq(lo, hi, b, tab + col * 8u);
         else return pack_bf16_bias(lo, hi, b);
@@ -1267,6 +1289,7 @@ __device__ __forceinline__ void drain_columns(uint32_t t_acc, uint32_t q, float 
         if (a16) tmem_ld16(t_acc + c, v); else if (a8) tmem_ld8(t_acc + c, v);
         if (b16) tmem_ld16(t_acc + c + 16, v + 16); else if (b8) tmem_ld8(t_acc + c + 16, v + 16);
         tmem_ld_wait();
+        if (p2 == (q > 32 ? 1 : 0)) release();           // the last columns are in registers
         if (a16) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) pk[p2 * 16 + j] = pack2(v[2 * j], v[2 * j + 1], bias, c + 2 * j);
@@ -1315,8 +1338,9 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kBarOffset);
     uint64_t *wfull = bars, *wempty = bars + SW;                          // W ring
     uint64_t *xfull = bars + 2 * SW, *xempty = xfull + A, *afull = xempty + A;   // X ring + A ring (xempty frees both)
-    uint64_t *tfull = afull + A, *tempty = tfull + 2;                     // accumulator halves
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    constexpr int NB = C::kAccBufs;
+    uint64_t *tfull = afull + A, *tempty = tfull + NB;                    // accumulator buffers
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + NB);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();                              // 0 = leader: issues the MMAs
@@ -1330,7 +1354,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         if (a.y_f32 == nullptr) prefetch_tmap(&tmap_y);
         for (int s = 0; s < SW; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 4); }
         for (int s = 0; s < A; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); mbar_init(afull + s, 8); }   // afull: dequant warps of both CTAs
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 16); }                            // tempty: the 8 epilogue warps of both CTAs
+        for (int i = 0; i < NB; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 16); }                           // tempty: the 8 epilogue warps of both CTAs
         fence_barrier_init();
     }
     cluster_sync_all();                                                   // barriers of both CTAs exist before anybody signals them
@@ -1340,6 +1364,8 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_col0 = C::kAccCols;
+    // (setmaxnreg — 40 registers for the producer / MMA warps, 56 for the unpack warps, 136 for the epilogue warps — does not help:
+    //  ptxas then allocates the WHOLE kernel for the smallest budget, 1560 bytes of spills.)
     if (warp == 0) {
         // ===================== activation producer: this CTA's half of the tile's tokens, bytes reported to the leader =====================
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1422,8 +1448,68 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         const uint32_t idesc = (I8 ? ((2u << 4) | (0u << 7) | (1u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10))) |
                                ((nh >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
         uint32_t it = 0, n_item = 0;
+        if constexpr (C::kPre > 1) {
+            // Half 0 runs kPre stages AHEAD of half 1: the issue order is h0(0) .. h0(kPre-1), then h1(j), h0(j + kPre) for every j.
+            // At a tile boundary half 0's accumulator is then complete (and being drained) while half 1's last kPre stages still
+            // run, and the next tile's first kPre stages of half 0 are issued as soon as that buffer is back — before half 1's buffer,
+            // which is drained second, has been handed back.  (In lock step the tensor pipe idled for both drains: 6 K cycles per
+            // tile, stage timeline.)  A stage's slot is released after its half-1 MMAs; kPre + 1 slots are held.
+            for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
+                const uint32_t g0 = 2 * n_item, g1 = 2 * n_item + 1;
+                const uint32_t b0 = g0 % NB, b1 = g1 % NB, tp0 = (g0 / NB) & 1, tp1 = (g1 / NB) & 1;
+                ++n_item;
+                const uint32_t n_st = (KB + KBS - 1) / KBS;
+                auto wait_stage = [&](uint32_t j) {
+                    const uint32_t its = it + j, s = its % A, ph = (its / A) & 1;
+                    mbar_wait(xfull + s, ph);          // both CTAs' activation halves landed
+                    mbar_wait(afull + s, ph);          // both CTAs' A slots written to tensor memory
+                    tc_fence_after();
+                };
+                auto issue = [&](uint32_t j, uint32_t h) {
+                    const uint32_t its = it + j, s = its % A;
+                    const uint32_t kb = j * KBS, nk = KB - kb < (uint32_t)KBS ? KB - kb : (uint32_t)KBS;
+                    const uint32_t stage_addr = smem_u32(smem + s * C::kXStage) + h * q * 128u;
+                    const uint32_t a_tmem = tmem_base + a_col0 + s * C::kSlotCols;
+                    const uint32_t d_tmem = tmem_base + (h ? b1 : b0) * 128;
+                    if (lane == 0) TRACE2(1 + h, its);
+                    if (elect_one()) {
+                        if (!(a.dbg & 1)) {
+                            for (uint32_t sub = 0; sub < nk; ++sub) {
+                                if constexpr (I8) {
+                                    const uint64_t bdesc = make_b_desc(stage_addr);
+#pragma unroll
+                                    for (int k2 = 0; k2 < 2; ++k2)
+                                        umma_ts_pair_i8(d_tmem, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (j == 0 && sub == 0 && k2 == 0) ? 0u : 1u);
+                                } else {
+                                    const uint64_t bdesc = make_b_desc(stage_addr + sub * slab);
+#pragma unroll
+                                    for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
+                                        umma_ts_pair(d_tmem, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (j == 0 && sub == 0 && k4 == 0) ? 0u : 1u);
+                                }
+                            }
+                        }
+                        if (j + 1 == n_st) umma_commit_pair(tfull + (h ? b1 : b0));
+                        if (h == 1) umma_commit_pair(xempty + s);      // frees the activation stage and the A slot in both CTAs
+                    }
+                    __syncwarp();
+                };
+                const uint32_t pre = n_st < (uint32_t)C::kPre ? n_st : (uint32_t)C::kPre;
+                mbar_wait(tempty + b0, tp0 ^ 1);                       // the buffer's previous user drained (both CTAs)
+                tc_fence_after();
+                for (uint32_t j = 0; j < pre; ++j) { wait_stage(j); issue(j, 0); }
+                mbar_wait(tempty + b1, tp1 ^ 1);
+                tc_fence_after();
+                for (uint32_t j = 0; j < n_st; ++j) {
+                    issue(j, 1);
+                    if (j + pre < n_st) { wait_stage(j + pre); issue(j + pre, 0); }
+                }
+                it += n_st;
+            }
+        } else
         for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
-            const uint32_t tph = n_item & 1;
+            // tile n, half h: buffer (2 n + h) % NB, in its (2 n + h) / NB-th use
+            const uint32_t g0 = 2 * n_item, g1 = 2 * n_item + 1;
+            const uint32_t b0 = g0 % NB, b1 = g1 % NB, tp0 = (g0 / NB) & 1, tp1 = (g1 / NB) & 1;
             ++n_item;
             bool ready = false;
             for (uint32_t kb = 0; kb < KB; kb += KBS, ++it) {
@@ -1439,7 +1525,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 const bool first = kb == 0, last = kb + KBS >= KB;
                 if (lane == 0) TRACE2(1, it);
                 // ---- token half 0 ----
-                if (first) { mbar_wait(tempty + 0, tph ^ 1); tc_fence_after(); }      // previous tile's half 0 drained (both CTAs)
+                if (first) { mbar_wait(tempty + b0, tp0 ^ 1); tc_fence_after(); }     // the buffer's previous user drained (both CTAs)
                 if (elect_one()) {
                     if (!(a.dbg & 1)) {
                         for (uint32_t sub = 0; sub < nk; ++sub) {
@@ -1448,16 +1534,16 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                                 const uint64_t bdesc = make_b_desc(stage_addr);
 #pragma unroll
                                 for (int k2 = 0; k2 < 2; ++k2)
-                                    umma_ts_pair_i8(tmem_base, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
+                                    umma_ts_pair_i8(tmem_base + b0 * 128, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
                             } else {
                                 const uint64_t bdesc = make_b_desc(stage_addr + sub * slab);
 #pragma unroll
                                 for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
-                                    umma_ts_pair(tmem_base, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
+                                    umma_ts_pair(tmem_base + b0 * 128, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
                             }
                         }
                     }
-                    if (last) umma_commit_pair(tfull + 0);
+                    if (last) umma_commit_pair(tfull + b0);
                 }
                 __syncwarp();
                 // peek at the next stage while those MMAs run (never blocks: half 1 must be issued first)
@@ -1467,7 +1553,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     if (mbar_try(xfull + s2, ph2) && mbar_try(afull + s2, ph2)) { tc_fence_after(); ready = true; }
                 }
                 // ---- token half 1 ----
-                if (first) { mbar_wait(tempty + 1, tph ^ 1); tc_fence_after(); }
+                if (first) { mbar_wait(tempty + b1, tp1 ^ 1); tc_fence_after(); }
                 if (lane == 0) TRACE2(2, it);
                 if (elect_one()) {
                     if (!(a.dbg & 1)) {
@@ -1476,16 +1562,16 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                                 const uint64_t bdesc = make_b_desc(stage_addr + q * 128u);
 #pragma unroll
                                 for (int k2 = 0; k2 < 2; ++k2)
-                                    umma_ts_pair_i8(tmem_base + 128, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
+                                    umma_ts_pair_i8(tmem_base + b1 * 128, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
                             } else {
                                 const uint64_t bdesc = make_b_desc(stage_addr + sub * slab + q * 128u);
 #pragma unroll
                                 for (int k4 = 0; k4 < WL_TILE_K / 16; ++k4)
-                                    umma_ts_pair(tmem_base + 128, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
+                                    umma_ts_pair(tmem_base + b1 * 128, a_tmem + sub * kACols + k4 * 8, bdesc + (uint64_t)(k4 * 2), idesc, (first && sub == 0 && k4 == 0) ? 0u : 1u);
                             }
                         }
                     }
-                    if (last) umma_commit_pair(tfull + 1);
+                    if (last) umma_commit_pair(tfull + b1);
                     umma_commit_pair(xempty + s);      // frees the activation stage and the A slot in both CTAs
                 }
                 __syncwarp();
@@ -1551,7 +1637,6 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         uint32_t n_item = 0;
         for (uint32_t tile = tile0; tile < a.tiles; tile += n_pairs_grid) {
             const uint32_t mt = (tile / a.n_pairs + a.mt_rot) % a.m_tiles, nc = tile % a.n_pairs;
-            const uint32_t tph = n_item & 1;
             const uint32_t nt = 2 * nc + rank;
             const uint32_t n = nt * 128 + quarter * 32 + lane;
             const bool n_ok = nt < a.n_tiles && n < a.N && !(a.dbg & 64);
@@ -1611,15 +1696,32 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 uint32_t pk[32];
 #pragma unroll 1
                 for (uint32_t h = 0; h < 2; ++h) {
-                    const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + part * q;
-                    mbar_wait(tfull + h, tph);
+                    const uint32_t gb = 2 * n_item + h, buf = gb % NB, tph = (gb / NB) & 1;     // buffer of (tile, half) and its use parity
+                    const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128 + part * q;
+                    mbar_wait(tfull + buf, tph);
                     tc_fence_after();
                     if (warp == kEpiWarp0 && lane == 0) TRACE2(4 + h, n_item);
-                    drain_columns<I8>(t_acc, q, bias, pk, tab + (part * half_rows + h * q) * 8u);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty_leader + h * 8);   // this warp's columns are out: 16 such arrivals free the half
-                    if (warp == kEpiWarp0 && lane == 0) TRACE2(6 + h, n_item);
+                    // this warp's columns are out: 16 such arrivals free the buffer
+                    auto release = [&]() {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tempty_leader + buf * 8);
+                        if (warp == kEpiWarp0 && lane == 0) TRACE2(6 + h, n_item);
+                    };
+                    if constexpr (I8) {
+                        // (the buffer is handed back as soon as the last column is in registers, before the last batch is converted)
+#if defined(DLLM_I8_LATE_RELEASE)
+                        drain_columns<true>(t_acc, q, bias, pk, tab + (part * half_rows + h * q) * 8u);
+                        release();
+#else
+                        drain_columns<true>(t_acc, q, bias, pk, tab + (part * half_rows + h * q) * 8u, release);
+#endif
+                    } else {
+                        // (handing the buffer back before the last 32 columns are converted, as the int8 variant may, costs the bf16
+                        //  kernel registers it does not have: 192 instead of 108 bytes spilled, 63.7 against 67.4 steps/s)
+                        drain_columns<false>(t_acc, q, bias, pk);
+                        release();
+                    }
                     if (h == 0 && st_on) stage_columns(stg_mine, q, pk);          // registers -> staging [part][token][128 columns]
                 }
                 if (st_on) {
@@ -1636,12 +1738,13 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             } else {
 #pragma unroll 1
             for (uint32_t h = 0; h < 2; ++h) {
-                const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + part * q;
+                const uint32_t gb = 2 * n_item + h, buf = gb % NB, tph = (gb / NB) & 1;
+                const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128 + part * q;
                 const uint32_t tok0 = mt * ntok + part * half_rows + h * q;     // token of this warp's first column
                 const uint32_t n_tok = tok0 >= a.M ? 0u : (a.M - tok0 < q ? a.M - tok0 : q);   // valid rows among its q
                 {
                     // f32 (and optionally bf16) output: the stack's last layer only.  Columns are stored as they are read.
-                    mbar_wait(tfull + h, tph);
+                    mbar_wait(tfull + buf, tph);
                     tc_fence_after();
 #pragma unroll 1
                     for (uint32_t c0 = 0; c0 < q; c0 += 8) {
@@ -1651,7 +1754,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                         if (c0 + 8 >= q) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(tempty_leader + h * 8);
+                            if (lane == 0) mbar_arrive_cluster(tempty_leader + buf * 8);
                         }
                         if (!n_ok) continue;
                         const size_t o = (size_t)(tok0 + c0) * ldy + n;
@@ -2166,7 +2269,10 @@ static bool pair2_i8_applicable(const dllm_ctx *ctx, const dllm_qweight *qw, siz
 template <int CB>
 int32_t launch_umma_pair2_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t *xq, size_t M, const I8Deq *dq) {
     using C = CfgP2<CB, true>;
-    constexpr int NDQ = kNDQ;
+#ifndef DLLM_I8_NDQ
+#define DLLM_I8_NDQ DLLM_NDQ
+#endif
+    constexpr int NDQ = DLLM_I8_NDQ;          // unpack groups of 4 warps
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) DLLM_FAIL(ctx, DLLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     Pair2Args a;
@@ -2184,6 +2290,13 @@ int32_t launch_umma_pair2_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t
     a.m_tiles = (uint32_t)((M + a.ntok - 1) / a.ntok);
     a.tiles = a.n_pairs * a.m_tiles;
     a.i8_rowsum = dq->rowsum; a.i8_rowscale = dq->rowscale; a.i8_zp = (int32_t)qw->tensor_zp;
+    static const uint32_t dbg_flags = getenv("DLLM_UMMA_DBG") ? (uint32_t)atoi(getenv("DLLM_UMMA_DBG")) : 0u;
+    a.dbg = dbg_flags & (1u | 64u | 128u);                   // timing experiments only: 1 skip MMAs, 64 skip stores, 128 stage timeline
+    if (a.dbg & 128) {
+        DLLM_TRY(ensure_buf(ctx, ctx->lin_ws, 8 * 256 * sizeof(long long)));
+        a.trace = (long long *)ctx->lin_ws.p;
+        cudaMemsetAsync(a.trace, 0, 8 * 256 * sizeof(long long), ctx->stream);
+    }
 
     // int8 activations [M tokens, K bytes] row-major; one box = 128 k x ntok/2 tokens in the SWIZZLE_128B K-major layout
     CUtensorMap tmap;
@@ -2233,6 +2346,24 @@ int32_t launch_umma_pair2_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t
     cfg.numAttrs = no_pdl ? 0 : 1;
     CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, umma_qlinear_pair2_kernel<CB, NDQ, true>, tmap, tmap_y, rsm, a));
     LAUNCH_CHECK(ctx);
+    if (a.dbg & 128) {   // dump the timeline of cluster 0's leader (timing experiments only)
+        std::vector<long long> hst(8 * 256);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(hst.data(), a.trace, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        static int n_dump = 0;
+        char name[64];
+        snprintf(name, sizeof(name), "gpurun_out/pair2_i8_trace_%d.csv", n_dump++ & 3);
+        FILE *f = fopen(name, "w");
+        if (f) {
+            fprintf(f, "i,dq_start(stage),mma_h0(stage),mma_h1(stage),dq_end(stage),epi_h0_ready(tile),epi_h1_ready(tile),epi_h0_released(tile),epi_h1_released(tile)\n");
+            for (int i = 0; i < 256; ++i) {
+                fprintf(f, "%d", i);
+                for (int r = 0; r < 8; ++r) fprintf(f, ",%lld", hst[r * 256 + i]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     if (ev1) {
         CUDA_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
         ctx->prof_n++;
