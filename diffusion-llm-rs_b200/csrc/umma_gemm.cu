@@ -1499,6 +1499,8 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 for (uint32_t j = 0; j < pre; ++j) { wait_stage(j); issue(j, 0); }
                 mbar_wait(tempty + b1, tp1 ^ 1);
                 tc_fence_after();
+                // (interleaving the two halves' MMAs k-step by k-step, so that consecutive MMAs never accumulate into the same
+                //  buffer, changes nothing: 86.7 against 87.6 steps/s)
                 for (uint32_t j = 0; j < n_st; ++j) {
                     issue(j, 1);
                     if (j + pre < n_st) { wait_stage(j + pre); issue(j + pre, 0); }
