@@ -147,6 +147,15 @@ __device__ __forceinline__ void umma_ts_pair_i8(uint32_t d_tmem, uint32_t a_tmem
         "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t"
         "}\n" :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::i8 with A from shared memory (both operands through descriptors)
+__device__ __forceinline__ void umma_ss_pair_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -1205,14 +1214,25 @@ struct CfgP2 {
 #ifndef DLLM_I8_NBUF
 #define DLLM_I8_NBUF 2
 #endif
-    static constexpr int kAccBufs = I8 ? DLLM_I8_NBUF : 2;
-    // X ring (shared memory) and A ring (tensor memory): same depth, one commit frees both
-    static constexpr int kSlots = I8 ? (kAccBufs == 3 ? 4 : 6) : 4;
+    // int8, A ring in SHARED memory (-DDLLM_I8_ASMEM=1): the unpacked codes of a stage are 16 KB per CTA — a SWIZZLE_128B tile like the
+    // activations', written by the unpack warps with plain shared-memory stores and read by the MMA through a descriptor — which
+    // leaves all 512 tensor-memory columns to FOUR accumulator buffers: the halves of tile t + 1 are accumulated while those of tile t
+    // are drained.  Measured: the tile-boundary stall disappears, but shared memory then only holds 4 stages of X + A, and with the
+    // unpack latency at 2 K cycles per stage (the epilogue warps now run all the time on the same sub-cores) the stage period is
+    // 1000 cycles instead of 750: 82.2 against 88.7 steps/s — so the tensor-memory ring stays the default.  Both pass the parity tests.
+#ifndef DLLM_I8_ASMEM
+#define DLLM_I8_ASMEM 0
+#endif
+    static constexpr bool kASmem = I8 && DLLM_I8_ASMEM;
+    static constexpr int kAccBufs = kASmem ? 4 : (I8 ? DLLM_I8_NBUF : 2);
+    // X ring (shared memory) and A ring (tensor memory / shared memory): same depth, one commit frees both
+    static constexpr int kSlots = kASmem ? 4 : (I8 ? (kAccBufs == 3 ? 4 : 6) : 4);
+    static constexpr int kAStage = kASmem ? 128 * 128 : 0;             // 128 columns x 128 k bytes
     // how many stages half 0 is issued ahead of half 1 (1 = lock step)
 #ifndef DLLM_I8_PRE
 #define DLLM_I8_PRE 2
 #endif
-    static constexpr int kPre = I8 ? DLLM_I8_PRE : 1;
+    static constexpr int kPre = (I8 && !kASmem) ? DLLM_I8_PRE : 1;
     static_assert(kPre >= 1 && kPre + 1 < kSlots, "half 0 cannot run further ahead than the rings are deep");
     static constexpr int kAccCols = kAccBufs * 128;
     static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
@@ -1222,9 +1242,10 @@ struct CfgP2 {
     // by the epilogue warps and stored with two bulk tensor copies (the direct 2-byte stores cost 29 % of the kernel)
     static constexpr int kOutBytes = 2 * 64 * 128 * 2;
     static constexpr int kSmemBudget = 220 * 1024;
-    static constexpr int kWStagesRaw = (kSmemBudget - kSlots * kXStage - kOutBytes) / kWStage;
+    static constexpr int kWStagesRaw = (kSmemBudget - kSlots * (kXStage + kAStage) - kOutBytes) / kWStage;
     static constexpr int kWStages = kWStagesRaw > 12 ? 12 : kWStagesRaw;   // 1024 cycles of MMAs per stage: a few stages cover the L2 latency
-    static constexpr int kOutOffset = kSlots * kXStage;
+    static constexpr int kAOffset = kSlots * kXStage;
+    static constexpr int kOutOffset = kAOffset + kSlots * kAStage;
     static constexpr int kWOffset = kOutOffset + kOutBytes;
     static constexpr int kBarOffset = kWOffset + kWStages * kWStage;
     static constexpr int kNumBars = 2 * kWStages + 3 * kSlots + 2 * kAccBufs;
@@ -1235,7 +1256,7 @@ struct CfgP2 {
     static_assert(kXStage % 1024 == 0 && kWStage % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned stages");
     static_assert(kWStages >= kSlots, "W ring must be at least as deep as the A ring");
     static_assert(kTotal <= 227 * 1024, "shared memory over-subscribed");
-    static_assert(kAccCols + kSlots * kSlotCols <= kTmemCols, "TMEM over-subscribed");
+    static_assert(kAccCols + (kASmem ? 0 : kSlots * kSlotCols) <= kTmemCols, "TMEM over-subscribed");
 };
 
 // non-blocking probe (try_wait may suspend the thread for a system-dependent time; test_wait never does)
@@ -1447,6 +1468,14 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         // c = f32, a = b = bf16 — int8: c = s32 (2 << 4), a = u8 (0 << 7), b = s8 (1 << 10) — K-major A and B, N >> 3 at 17, M >> 4 at 24
         const uint32_t idesc = (I8 ? ((2u << 4) | (0u << 7) | (1u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10))) |
                                ((nh >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        // one int8 MMA: 32 k (k-step sub * 2 + k2 of the stage in slot s) into accumulator d
+        auto mma_i8 = [&](uint32_t d, uint32_t s, uint32_t sub, uint32_t k2, uint64_t bdesc, uint32_t acc) {
+            const uint64_t step = (uint64_t)((sub * 2 + k2) * 2);
+            if constexpr (C::kASmem)
+                umma_ss_pair_i8(d, make_b_desc(smem_u32(smem + C::kAOffset + s * C::kAStage)) + step, bdesc + step, idesc, acc);
+            else
+                umma_ts_pair_i8(d, tmem_base + a_col0 + s * C::kSlotCols + sub * kACols + k2 * 8, bdesc + step, idesc, acc);
+        };
         uint32_t it = 0, n_item = 0;
         if constexpr (C::kPre > 1) {
             // Half 0 runs kPre stages AHEAD of half 1: the issue order is h0(0) .. h0(kPre-1), then h1(j), h0(j + kPre) for every j.
@@ -1479,7 +1508,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                                     const uint64_t bdesc = make_b_desc(stage_addr);
 #pragma unroll
                                     for (int k2 = 0; k2 < 2; ++k2)
-                                        umma_ts_pair_i8(d_tmem, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (j == 0 && sub == 0 && k2 == 0) ? 0u : 1u);
+                                        mma_i8(d_tmem, s, sub, (uint32_t)k2, bdesc, (j == 0 && sub == 0 && k2 == 0) ? 0u : 1u);
                                 } else {
                                     const uint64_t bdesc = make_b_desc(stage_addr + sub * slab);
 #pragma unroll
@@ -1536,7 +1565,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                                 const uint64_t bdesc = make_b_desc(stage_addr);
 #pragma unroll
                                 for (int k2 = 0; k2 < 2; ++k2)
-                                    umma_ts_pair_i8(tmem_base + b0 * 128, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
+                                    mma_i8(tmem_base + b0 * 128, s, sub, (uint32_t)k2, bdesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
                             } else {
                                 const uint64_t bdesc = make_b_desc(stage_addr + sub * slab);
 #pragma unroll
@@ -1564,7 +1593,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                                 const uint64_t bdesc = make_b_desc(stage_addr + q * 128u);
 #pragma unroll
                                 for (int k2 = 0; k2 < 2; ++k2)
-                                    umma_ts_pair_i8(tmem_base + b1 * 128, a_tmem + sub * kACols + k2 * 8, bdesc + (uint64_t)((sub * 2 + k2) * 2), idesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
+                                    mma_i8(tmem_base + b1 * 128, s, sub, (uint32_t)k2, bdesc, (first && sub == 0 && k2 == 0) ? 0u : 1u);
                             } else {
                                 const uint64_t bdesc = make_b_desc(stage_addr + sub * slab + q * 128u);
 #pragma unroll
@@ -1598,14 +1627,34 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 tc_fence_after();
                 if (quarter == 0 && lane == 0) TRACE2(0, it);
                 const uint8_t *stage = smem_w + sw * C::kWStage;
+                if constexpr (I8) {
+                    // the codes as unsigned bytes in k order: no zero-point, no scale (both leave in the epilogue).  Both k-blocks of
+                    // the stage in one straight-line block: their loads and unpack interleave
+                    uint32_t vals[KBS][16];
+#pragma unroll
+                    for (uint32_t sub = 0; sub < (uint32_t)KBS; ++sub)
+                        if (sub < nk) unpack_kblock_u8<CB>(reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes), n_local, vals[sub]);
+#pragma unroll
+                    for (uint32_t sub = 0; sub < (uint32_t)KBS; ++sub) {
+                        if (sub >= nk) continue;
+                        if constexpr (C::kASmem) {
+                            // row n_local of the stage's A tile: 128 bytes = both k-blocks, 16-byte chunk c at c ^ (row & 7)
+                            const uint32_t rowa = smem_u32(smem + C::kAOffset + sl * C::kAStage) + (uint32_t)n_local * 128u;
+#pragma unroll
+                            for (uint32_t c4 = 0; c4 < 4; ++c4) {
+                                const uint32_t c = sub * 4 + c4;
+                                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+                                             :: "r"(rowa + ((c ^ ((uint32_t)n_local & 7u)) << 4)), "r"(vals[sub][4 * c4]), "r"(vals[sub][4 * c4 + 1]),
+                                                "r"(vals[sub][4 * c4 + 2]), "r"(vals[sub][4 * c4 + 3]) : "memory");
+                            }
+                        } else {
+                            tmem_st16(lane_addr + sl * C::kSlotCols + sub * kACols, vals[sub]);
+                        }
+                    }
+                } else
                 for (uint32_t sub = 0; sub < nk; ++sub) {
                     const uint4 *wpk = reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes);
-                    if constexpr (I8) {
-                        // the codes as unsigned bytes in k order: no zero-point, no scale (both leave in the epilogue)
-                        uint32_t vals[16];
-                        unpack_kblock_u8<CB>(wpk, n_local, vals);
-                        tmem_st16(lane_addr + sl * C::kSlotCols + sub * kACols, vals);
-                    } else {
+                    {
                         const uint2 prm = lds64(smem_u32(stage + KBS * C::kWBytes + sub * C::kPBytes) + (uint32_t)n_local * 8u);
                         uint32_t vals[32];
                         if (!(a.dbg & 2)) dequant_kblock<CB>(wpk, n_local, prm.x, prm.y, vals);
@@ -1618,8 +1667,12 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(wempty + sw);
-                tmem_st_wait();
-                tc_fence_before();
+                if constexpr (C::kASmem) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // these stores -> the MMA's descriptor reads
+                } else {
+                    tmem_st_wait();
+                    tc_fence_before();
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(afull_leader + sl * 8);
                 if (quarter == 0 && lane == 0) TRACE2(3, it);
