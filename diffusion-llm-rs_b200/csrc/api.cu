@@ -2176,7 +2176,7 @@ int32_t dllm_kvcache_update_dev(dllm_ctx *ctx, dllm_kvcache *kc, const float *ke
         } else {
             if (!kc->q[which]) DLLM_TRY(kv_alloc(ctx, kc->L, 0, kc->cap, kc->H, (uint8_t)kc->bits[which], kc->scheme, &kc->q[which]));
             kc->q[which]->S = seq;
-            if (kc->L * seq * kc->H) {
+            if (kc->L * seq * kc->H != 0) {
                 DLLM_TRY(kv_quantize_rows(ctx, kc->q[which], 0, keys_dev, 0, seq));
                 DLLM_TRY(kv_quantize_rows(ctx, kc->q[which], 1, values_dev, 0, seq));
             }

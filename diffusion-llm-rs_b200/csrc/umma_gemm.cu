@@ -148,7 +148,7 @@ __device__ __forceinline__ void umma_ts_pair_i8(uint32_t d_tmem, uint32_t a_tmem
         "}\n" :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // kind::i8 with A from shared memory (both operands through descriptors)
-__device__ __forceinline__ void umma_ss_pair_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+[[maybe_unused]] __device__ __forceinline__ void umma_ss_pair_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
