@@ -140,9 +140,11 @@ class QuantizedKVCacheEntry:
 
 class AdaptiveQuantizer:
     """quantization.rs:179-235.  The reference feeds a CKMS(0.01) quantile sketch (un-vendored
-    `quantiles` crate) and queries q=0 / q=1; CKMS answers those two queries with the exact
-    extremes it has seen, so the statistics here are a running exact min/max (parity of the
-    sketch itself is unpinned).  The code step runs on the GPU."""
+    `quantiles` crate) and queries q=0 / q=1 only; the published algorithm answers those two
+    queries with the exact extremes it has seen (restated and tested on the checker's side,
+    tests/test_oracle_golden.py), so the statistics here are a running exact
+    min/max — the device reduction per chunk — and the parameters equal the sketch's bit for
+    bit (tests/test_gpu_quantizers.py).  The code step runs on the GPU."""
 
     def __init__(self, bits: int, target_ratio: float, ctx: Context | None = None):
         self.bits, self.target_ratio = int(bits), float(target_ratio)

@@ -406,3 +406,89 @@ def model_forward_i8(x_tokens, layers):
         if i + 1 < len(layers):
             h = bf16_round(h)
     return h
+
+
+# ---- AdaptiveQuantizer's statistics: the CKMS sketch (diffuse-llm-rs/src/quantization.rs:179-216) ------------------------------
+# The reference keeps `quantiles::ckms::CKMS<f32>` (crate `quantiles = "0.7"`, diffuse-llm-rs/Cargo.toml:33 — un-vendored, no
+# Cargo.lock) with error 0.01 and asks it for q = 0.0 and q = 1.0 (:208-209).  What follows restates the PUBLISHED algorithm the
+# crate implements — Cormode, Korn, Muthukrishnan, Srivastava, "Effective Computation of Biased Quantiles over Data Streams"
+# (ICDE 2005), low-biased invariant f(r, n) = 2 eps r: samples (v, g, delta) kept sorted by v; insert with g = 1 and delta =
+# floor(f(r)) - 1 (0 at either end); compress every 1 / (2 eps) inserts, merging sample i into i + 1 when g_i + g_{i+1} +
+# delta_{i+1} <= max(1, floor(f(r_i))); query(q) = the last sample whose successor's maximum rank exceeds q n + f(q n) / 2.
+# Pure Python (small streams only): it is here to show what q = 0 and q = 1 return — the exact extremes seen so far, because a
+# merge always keeps the LARGER value and its rank budget max(1, floor(2 eps r)) is 1 below rank 1 / eps, so neither the last
+# sample nor the first is ever merged away — which is what the product's running min / max computes (parity of the crate's
+# own code stays unpinned: it is not in /root/reference).
+class CKMS:
+    def __init__(self, error=0.01):
+        self.eps = min(max(float(error), 1e-10), 0.99)
+        self.every = max(1, int(1.0 / (2.0 * self.eps)))
+        self.n = 0
+        self.inserts = 0
+        self.samples = []                     # [v, g, delta], sorted by v
+
+    def _f(self, r):
+        return max(1, int(np.floor(2.0 * self.eps * r)))
+
+    def insert(self, v):
+        v = float(np.float32(v))
+        smp = self.samples
+        i = 0
+        r = 0
+        while i < len(smp) and not (v < smp[i][0]):
+            r += smp[i][1]
+            i += 1
+        delta = 0 if (i == 0 or i == len(smp)) else max(0, self._f(r) - 1)
+        smp.insert(i, [v, 1, delta])
+        self.n += 1
+        self.inserts = (self.inserts + 1) % self.every
+        if self.inserts == 0:
+            self.compress()
+
+    def compress(self):
+        smp = self.samples
+        if len(smp) < 3:
+            return
+        ranks = np.cumsum([e[1] for e in smp])          # rank of sample i = sum of g up to and including i
+        i = len(smp) - 2
+        while i >= 1:
+            r_prev = int(ranks[i - 1])
+            if smp[i][1] + smp[i + 1][1] + smp[i + 1][2] <= self._f(r_prev):
+                smp[i + 1][1] += smp[i][1]
+                del smp[i]
+            i -= 1
+
+    def query(self, q):
+        smp = self.samples
+        if not smp:
+            return None
+        nphi = q * self.n
+        rhs = nphi + self._f(nphi) / 2.0
+        r = 0
+        for i in range(1, len(smp)):
+            r += smp[i - 1][1]
+            if r + smp[i][1] + smp[i][2] > rhs:
+                return r, np.float32(smp[i - 1][0])
+        return len(smp), np.float32(smp[-1][0])
+
+
+def adaptive_compute_params(chunks, bits, error=0.01):
+    """AdaptiveQuantizer::update_stats over `chunks` then compute_params (quantization.rs:198-216) with the sketch above:
+    min = query(0.0) or 0.0, max = query(1.0) or 1.0, scale = (max - min) / q_max, zp = clamp(round(-min / scale), 0, q_max),
+    all in f32 with f32::round (half away from zero)."""
+    F32 = np.float32
+    sk = CKMS(error)
+    for c in chunks:
+        for v in np.asarray(c, dtype=np.float32).ravel():
+            sk.insert(v)
+    lo, hi = sk.query(0.0), sk.query(1.0)
+    mn = F32(0.0) if lo is None else lo[1]
+    mx = F32(1.0) if hi is None else hi[1]
+    q_max = F32(F32(1 << bits) - F32(1))
+    with np.errstate(all="ignore"):
+        scale = F32(F32(mx - mn) / q_max)
+        r = F32(F32(-mn) / scale)
+        t = np.trunc(r)
+        r = F32(t + np.copysign(F32(1), r)) if abs(r - t) >= 0.5 else F32(t)
+        zp = F32(min(max(r, F32(0)), q_max))
+    return scale, zp, sk

@@ -373,6 +373,26 @@ def test_adaptive_quantizer(ctx, O):
     assert scale > 0.0 and zp >= 0.0
     codes, s, z = q.quantize(data)
     assert np.array_equal(codes, O.quantize_codes_b(data, 4, s, z))
+    # against the oracle's restatement of the sketch the reference feeds (CKMS(0.01), queried at q = 0 and q = 1 only,
+    # quantization.rs:198-216): the same parameters bit for bit — before any data, after the reference's test data, and after
+    # several chunks with outliers (the device min / max per chunk, the running extremes on the host)
+    s_ref, z_ref, _ = O.adaptive_compute_params([data], 4)
+    assert beq([scale, zp], [s_ref, z_ref])
+    fresh = AdaptiveQuantizer(6, 4.0, ctx)
+    s0, z0, _ = O.adaptive_compute_params([], 6)
+    assert beq(list(fresh.compute_params()), [s0, z0])                    # unwrap_or(0.0) / unwrap_or(1.0), :208-209
+    rng = np.random.default_rng(12)
+    for bits in (2, 4, 8):
+        chunks = [rng.standard_normal(777).astype(F) * 3 - 1, rng.standard_normal(1500).astype(F), np.array([41.5, -17.25], F),
+                  rng.standard_normal(300).astype(F) * 1e-3]
+        aq = AdaptiveQuantizer(bits, 4.0, ctx)
+        for c in chunks:
+            aq.update_stats(c)
+        s_ref, z_ref, _ = O.adaptive_compute_params(chunks, bits)
+        assert beq(list(aq.compute_params()), [s_ref, z_ref])
+        probe = rng.standard_normal(2000).astype(F) * 10
+        cq, sq, zq = aq.quantize(probe)
+        assert np.array_equal(cq, O.quantize_codes_b(probe, bits, s_ref, z_ref)) and beq([sq, zq], [s_ref, z_ref])
 
 
 # ---------------------------------------------------------------- full-size properties

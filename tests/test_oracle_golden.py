@@ -358,3 +358,43 @@ def test_int8_mode_restatement_stays_within_the_stated_bound_of_the_f64_stack():
         y1 = O.linear_i8_deq(xt, c, s, z, b)
         h1 = xt.astype(np.float64) @ ((c.astype(np.float64) - z) * s) + b
         assert np.linalg.norm(y1 - h1) <= 1e-2 * np.linalg.norm(h1)
+
+
+def test_ckms_sketch_answers_q0_and_q1_with_the_exact_extremes():
+    """AdaptiveQuantizer (quantization.rs:179-216) asks its CKMS(0.01) sketch for q = 0.0 and q = 1.0 only.  The oracle's
+    restatement of the published algorithm returns the exact minimum / maximum of everything inserted so far — for random,
+    sorted, reverse-sorted, constant, duplicate-heavy and outlier streams, at every prefix checked — while it does compress
+    (far fewer samples than inserts) and stays within its rank error in between."""
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(7)
+    streams = {
+        "normal": rng.standard_normal(6000),
+        "sorted": np.sort(rng.standard_normal(4000)),
+        "reverse": np.sort(rng.standard_normal(4000))[::-1],
+        "constant": np.full(1500, 0.25),
+        "duplicates": rng.integers(-3, 4, 5000).astype(np.float64),
+        "outliers": np.concatenate([rng.standard_normal(3000), [1e30, -1e30], rng.standard_normal(1000) * 1e-20]),
+        "ramp": np.arange(1000) / 1000.0,                       # the reference's own test data (quantization.rs:267-277)
+    }
+    for name, data in streams.items():
+        data = data.astype(np.float32)
+        sk = O.CKMS(0.01)
+        for i, v in enumerate(data):
+            sk.insert(v)
+            if i % 397 == 0 or i + 1 == len(data):
+                assert sk.query(0.0)[1] == data[: i + 1].min(), name
+                assert sk.query(1.0)[1] == data[: i + 1].max(), name
+        assert sk.n == len(data) and sum(e[1] for e in sk.samples) == len(data)
+        if name in ("normal", "sorted", "reverse"):
+            assert len(sk.samples) < len(data) // 4, (name, len(sk.samples))          # it does compress
+            srt = np.sort(data)
+            for q in (0.1, 0.5, 0.9):                                                    # and stays a quantile sketch
+                _, v = sk.query(q)
+                rank = np.searchsorted(srt, v, side="left")
+                assert abs(rank - q * len(data)) <= 0.01 * 2 * q * len(data) + 2, (name, q, rank)
+    assert O.CKMS(0.01).query(0.0) is None                                                # -> unwrap_or(0.0) / unwrap_or(1.0)
+    # compute_params on the reference's test data: scale = (0.999 - 0) / 15, zero-point 0
+    scale, zp, _ = O.adaptive_compute_params([streams["ramp"]], 4)
+    assert scale == np.float32(np.float32(0.999) / np.float32(15)) and zp == 0.0
+    s0, z0, _ = O.adaptive_compute_params([], 4)
+    assert s0 == np.float32(np.float32(1.0) / np.float32(15)) and z0 == 0.0
