@@ -1233,6 +1233,14 @@ struct CfgP2 {
 #define DLLM_I8_PRE 2
 #endif
     static constexpr int kPre = (I8 && !kASmem) ? DLLM_I8_PRE : 1;
+    // epilogue warps per CTA: 8 (two per tensor-memory lane quarter, q <= 64 columns each per half).  -DDLLM_I8_EPI16=1: 16 for int8,
+    // four per lane quarter with q / 2 <= 32 columns each, i.e. one tensor-memory round trip and 16 output pairs per warp and half
+    // instead of two and 32 — measured slower: 1024 threads leave 64 registers, half 0 is handed back after 1.9 K cycles instead
+    // of 2.6 K but its conversion and staging then take 4.9 K (8.4 K per tile boundary instead of 6.1 K; 81.9 against 88.4 steps/s).
+#ifndef DLLM_I8_EPI16
+#define DLLM_I8_EPI16 0
+#endif
+    static constexpr int kEpiWarps = (I8 && DLLM_I8_EPI16) ? 16 : 8;
     static_assert(kPre >= 1 && kPre + 1 < kSlots, "half 0 cannot run further ahead than the rings are deep");
     static constexpr int kAccCols = kAccBufs * 128;
     static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
@@ -1343,7 +1351,7 @@ __device__ __forceinline__ void stage_columns(uint32_t sbase, uint32_t q, const 
 }
 
 template <int CB, int NDQ, bool I8 = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((12 + 4 * NDQ) * 32, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 4 * NDQ + CfgP2<CB, I8>::kEpiWarps) * 32, 1)
 umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                           const __grid_constant__ RsMaps rs, const Pair2Args a) {
     // I8: the int8 variant (int8 denoise mode).  tmap_x = the int8 activations [M, K bytes] (box {128 k, ntok/2 tokens}: one
@@ -1375,7 +1383,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         if (a.y_f32 == nullptr) prefetch_tmap(&tmap_y);
         for (int s = 0; s < SW; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 4); }
         for (int s = 0; s < A; ++s) { mbar_init(xfull + s, 1); mbar_init(xempty + s, 1); mbar_init(afull + s, 8); }   // afull: dequant warps of both CTAs
-        for (int i = 0; i < NB; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 16); }                           // tempty: the 8 epilogue warps of both CTAs
+        for (int i = 0; i < NB; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 2 * C::kEpiWarps); }            // tempty: the epilogue warps of both CTAs
         fence_barrier_init();
     }
     cluster_sync_all();                                                   // barriers of both CTAs exist before anybody signals them
@@ -1422,7 +1430,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 const uint32_t s = it % A, ph = (it / A) & 1;
                 mbar_wait(xempty + s, ph ^ 1);
                 if (elect_one()) {
-                    if constexpr (I8) {
+                    if (I8 && !(a.dbg & 8)) {
                         // box {128 k, ntok/2 tokens}: both k-blocks of the stage; tokens past M and k past K are zero-filled
                         if (rank == 0) mbar_arrive_expect_tx(xfull + s, 2 * slab);
                         tma_load_2d_pair(smem + s * C::kXStage, &tmap_x, xfull_leader + s * 8, (int)(kb * WL_TILE_K), (int)(mt * ntok + rank * half_rows));
@@ -1632,8 +1640,14 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     // the stage in one straight-line block: their loads and unpack interleave
                     uint32_t vals[KBS][16];
 #pragma unroll
-                    for (uint32_t sub = 0; sub < (uint32_t)KBS; ++sub)
-                        if (sub < nk) unpack_kblock_u8<CB>(reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes), n_local, vals[sub]);
+                    for (uint32_t sub = 0; sub < (uint32_t)KBS; ++sub) {
+                        if (sub >= nk) continue;
+                        if (!(a.dbg & 2)) unpack_kblock_u8<CB>(reinterpret_cast<const uint4 *>(stage + sub * C::kWBytes), n_local, vals[sub]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) vals[sub][e] = (uint32_t)(e + n_local);
+                        }
+                    }
 #pragma unroll
                     for (uint32_t sub = 0; sub < (uint32_t)KBS; ++sub) {
                         if (sub >= nk) continue;
@@ -1686,7 +1700,9 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         // handed back to the MMA warp BEFORE anything is stored.  Phase 2, the stores, then overlaps the next MMAs.
         asm volatile("griddepcontrol.wait;" ::: "memory");
         const int quarter = warp & 3;
-        const uint32_t part = (uint32_t)(warp - kEpiWarp0) >> 2;
+        constexpr uint32_t SPLIT = C::kEpiWarps / 8, kEpiThreads = C::kEpiWarps * 32;      // warps per (lane quarter, CTA part)
+        const uint32_t part4 = (uint32_t)(warp - kEpiWarp0) >> 2;
+        const uint32_t part = part4 / SPLIT, wsub = part4 % SPLIT, wq = q / SPLIT;          // this warp: columns [wsub * wq, + wq) of its part
         const uint32_t tempty_leader = leader_addr(tempty);
         const size_t ldy = a.N;
         uint32_t n_item = 0;
@@ -1709,7 +1725,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     if (tok < a.M) { zs = a.i8_zp * __ldg(a.i8_rowsum + tok); sc = __ldg(a.i8_rowscale + tok); }
                     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(tab + e * 8u), "r"((uint32_t)zs), "r"(__float_as_uint(sc)) : "memory");
                 }
-                named_bar_sync(1, 256);
+                named_bar_sync(1, kEpiThreads);
             }
             if (a.y_f32 == nullptr) {
                 // bf16 output.  Both accumulator halves are on the tensor pipe's critical path (they are single-buffered), so they
@@ -1718,7 +1734,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 // staging buffer is re-used for half 1.  (Storing half 0 before draining half 1 — the first version — kept half 1
                 // for 1.9 K cycles longer at every tile boundary: stage timeline, DLLM_UMMA_DBG=128.)
                 const uint32_t stg = smem_u32(smem + C::kOutOffset);
-                const uint32_t stg_mine = stg + (part * q) * 256u + (uint32_t)(quarter * 32 + lane) * 2u;
+                const uint32_t stg_mine = stg + (part * q + wsub * wq) * 256u + (uint32_t)(quarter * 32 + lane) * 2u;
                 auto store_half = [&](uint32_t h) {                 // one elected thread: the staged half -> global / peer memory
                     if (warp == kEpiWarp0 && lane == 0 && nt < a.n_tiles) {
                         const int tokA = (int)(mt * ntok + h * q);
@@ -1746,13 +1762,13 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 // half-1 store has had a whole tile's time)
                 if (st_on) {
                     if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    named_bar_sync(1, 256);
+                    named_bar_sync(1, kEpiThreads);
                 }
                 uint32_t pk[32];
 #pragma unroll 1
                 for (uint32_t h = 0; h < 2; ++h) {
                     const uint32_t gb = 2 * n_item + h, buf = gb % NB, tph = (gb / NB) & 1;     // buffer of (tile, half) and its use parity
-                    const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128 + part * q;
+                    const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128 + part * q + wsub * wq;
                     mbar_wait(tfull + buf, tph);
                     tc_fence_after();
                     if (warp == kEpiWarp0 && lane == 0) TRACE2(4 + h, n_item);
@@ -1766,47 +1782,47 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     if constexpr (I8) {
                         // (the buffer is handed back as soon as the last column is in registers, before the last batch is converted)
 #if defined(DLLM_I8_LATE_RELEASE)
-                        drain_columns<true>(t_acc, q, bias, pk, tab + (part * half_rows + h * q) * 8u);
+                        drain_columns<true>(t_acc, wq, bias, pk, tab + (part * half_rows + h * q + wsub * wq) * 8u);
                         release();
 #else
-                        drain_columns<true>(t_acc, q, bias, pk, tab + (part * half_rows + h * q) * 8u, release);
+                        drain_columns<true>(t_acc, wq, bias, pk, tab + (part * half_rows + h * q + wsub * wq) * 8u, release);
 #endif
                     } else {
                         // (handing the buffer back before the last 32 columns are converted, as the int8 variant may, costs the bf16
                         //  kernel registers it does not have: 192 instead of 108 bytes spilled, 63.7 against 67.4 steps/s)
-                        drain_columns<false>(t_acc, q, bias, pk);
+                        drain_columns<false>(t_acc, wq, bias, pk);
                         release();
                     }
-                    if (h == 0 && st_on) stage_columns(stg_mine, q, pk);          // registers -> staging [part][token][128 columns]
+                    if (h == 0 && st_on) stage_columns(stg_mine, wq, pk);         // registers -> staging [part][token][128 columns]
                 }
                 if (st_on) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    named_bar_sync(1, 256);
+                    named_bar_sync(1, kEpiThreads);
                     store_half(0);                                               // rows past M / columns past N are clipped by the TMA unit
                     if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    named_bar_sync(1, 256);
-                    stage_columns(stg_mine, q, pk);                              // pk still holds half 1
+                    named_bar_sync(1, kEpiThreads);
+                    stage_columns(stg_mine, wq, pk);                             // pk still holds half 1
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    named_bar_sync(1, 256);
+                    named_bar_sync(1, kEpiThreads);
                     store_half(1);
                 }
             } else {
 #pragma unroll 1
             for (uint32_t h = 0; h < 2; ++h) {
                 const uint32_t gb = 2 * n_item + h, buf = gb % NB, tph = (gb / NB) & 1;
-                const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128 + part * q;
-                const uint32_t tok0 = mt * ntok + part * half_rows + h * q;     // token of this warp's first column
-                const uint32_t n_tok = tok0 >= a.M ? 0u : (a.M - tok0 < q ? a.M - tok0 : q);   // valid rows among its q
+                const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128 + part * q + wsub * wq;
+                const uint32_t tok0 = mt * ntok + part * half_rows + h * q + wsub * wq;     // token of this warp's first column
+                const uint32_t n_tok = tok0 >= a.M ? 0u : (a.M - tok0 < wq ? a.M - tok0 : wq);   // valid rows among its wq
                 {
                     // f32 (and optionally bf16) output: the stack's last layer only.  Columns are stored as they are read.
                     mbar_wait(tfull + buf, tph);
                     tc_fence_after();
 #pragma unroll 1
-                    for (uint32_t c0 = 0; c0 < q; c0 += 8) {
+                    for (uint32_t c0 = 0; c0 < wq; c0 += 8) {
                         uint32_t v[8];
                         tmem_ld8(t_acc + c0, v);
                         tmem_ld_wait();
-                        if (c0 + 8 >= q) {
+                        if (c0 + 8 >= wq) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(tempty_leader + buf * 8);
@@ -1819,7 +1835,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                                 float f;
                                 if constexpr (I8) {
                                     uint32_t zs, sc;
-                                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(zs), "=r"(sc) : "r"(tab + (part * half_rows + h * q + c0 + j) * 8u));
+                                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(zs), "=r"(sc) : "r"(tab + (part * half_rows + h * q + wsub * wq + c0 + j) * 8u));
                                     f = fmaf((float)((int32_t)v[j] - (int32_t)zs), __uint_as_float(sc), bias);
                                 } else {
                                     f = __uint_as_float(v[j]) + bias;
@@ -2037,10 +2053,10 @@ int32_t launch_umma(dllm_ctx *ctx, const dllm_qweight *qw, const void *x_bf16, s
 // wave): 128 -> 22.6, 160 -> 22.9, 192 -> 24.6, 224 -> 26.6, 256 -> 28.4, i.e. max(22.6, 12.6 + 0.0617 ntok): in units of
 // token-columns, waves x max(365, ntok + 205).  (The first version charged ntok + 6 and picked 128- to 160-token tiles whenever
 // they filled the last wave better: up to 1.64x slower than 256 at 4096 tokens.)  Ties go to the wider tile: fewer weight passes.
-static uint32_t pair2_pick_ntok(size_t M, uint32_t n_pairs, uint32_t pairs_hw) {
+static uint32_t pair2_pick_ntok(size_t M, uint32_t n_pairs, uint32_t pairs_hw, uint32_t step = 32) {
     uint32_t best = 0;
     uint64_t best_cost = ~0ull;
-    for (uint32_t ntok = 256; ntok >= 128; ntok -= 32) {
+    for (uint32_t ntok = 256; ntok >= 128; ntok -= step) {
         const uint64_t m_tiles = (M + ntok - 1) / ntok, tiles = m_tiles * n_pairs;
         const uint64_t waves = (tiles + pairs_hw - 1) / pairs_hw;
         const uint64_t cost = waves * (ntok + 205 > 365 ? ntok + 205 : 365);
@@ -2317,7 +2333,7 @@ static bool pair2_i8_applicable(const dllm_ctx *ctx, const dllm_qweight *qw, siz
     if (!dq->y_f32 && (qw->N % 8 != 0 || (reinterpret_cast<uintptr_t>(dq->y_bf16) & 15u) != 0)) return false;
     const uint32_t n_pairs = (uint32_t)((qw->n_tiles + 1) / 2);
     const uint32_t pairs_hw = (uint32_t)ctx->sm_count / 2;
-    const uint32_t ntok = pair2_pick_ntok(M, n_pairs, pairs_hw);
+    const uint32_t ntok = pair2_pick_ntok(M, n_pairs, pairs_hw, DLLM_I8_EPI16 ? 64 : 32);
     return (uint64_t)((M + ntok - 1) / ntok) * n_pairs >= pairs_hw / 2;
 }
 
@@ -2340,13 +2356,15 @@ int32_t launch_umma_pair2_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t
     const uint32_t pairs_hw = (uint32_t)ctx->sm_count / 2;
     const char *ntok_s = getenv("DLLM_UMMA_NTOK2");                                                 // experiments only
     const int ntok_env = ntok_s ? atoi(ntok_s) : 0;
-    a.ntok = (ntok_env >= 32 && ntok_env <= 256 && ntok_env % 32 == 0) ? (uint32_t)ntok_env : pair2_pick_ntok(M, a.n_pairs, pairs_hw);
+    // (16 epilogue warps: each drains q / 2 columns, a multiple of 8 -> token tiles in multiples of 64)
+    constexpr uint32_t kStep = C::kEpiWarps == 16 ? 64 : 32;
+    a.ntok = (ntok_env >= 64 && ntok_env <= 256 && ntok_env % kStep == 0) ? (uint32_t)ntok_env : pair2_pick_ntok(M, a.n_pairs, pairs_hw, kStep);
     a.rs_rows = 1; a.gate_rows = 1; a.gate_sub = 1;
     a.m_tiles = (uint32_t)((M + a.ntok - 1) / a.ntok);
     a.tiles = a.n_pairs * a.m_tiles;
     a.i8_rowsum = dq->rowsum; a.i8_rowscale = dq->rowscale; a.i8_zp = (int32_t)qw->tensor_zp;
     static const uint32_t dbg_flags = getenv("DLLM_UMMA_DBG") ? (uint32_t)atoi(getenv("DLLM_UMMA_DBG")) : 0u;
-    a.dbg = dbg_flags & (1u | 64u | 128u);                   // timing experiments only: 1 skip MMAs, 64 skip stores, 128 stage timeline
+    a.dbg = dbg_flags & (1u | 2u | 8u | 64u | 128u);         // timing experiments only: 1 skip MMAs, 2 skip the unpack, 8 skip the activation loads, 64 skip stores, 128 stage timeline
     if (a.dbg & 128) {
         DLLM_TRY(ensure_buf(ctx, ctx->lin_ws, 8 * 256 * sizeof(long long)));
         a.trace = (long long *)ctx->lin_ws.p;
@@ -2391,7 +2409,7 @@ int32_t launch_umma_pair2_i8(dllm_ctx *ctx, const dllm_qweight *qw, const int8_t
     static const bool no_pdl = getenv("DLLM_UMMA_NO_PDL") != nullptr;      // experiments only
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3((12 + 4 * NDQ) * 32);
+    cfg.blockDim = dim3((4 + 4 * NDQ + C::kEpiWarps) * 32);
     cfg.dynamicSmemBytes = C::kTotal;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
