@@ -107,6 +107,26 @@ int main() {
             for (float v : out) CHECK(std::isfinite(v));
             std::printf("launches=%llu\n", (unsigned long long)ctx.launches());
         }
+        // the int8 denoise mode through the same interface: per-tensor codes (group 0, the reference's scheme), DLLM_PATH_I8
+        {
+            const size_t H = 256, batch = 2, seq = 8, feat = H * seq;
+            std::vector<float> w(H * H);
+            for (size_t i = 0; i < w.size(); ++i) w[i] = 0.05f * std::sin(0.37f * (float)i);
+            auto layer = std::make_shared<diffuse_llm::QWeight>(ctx, w, H, H, 8, 0);
+            diffuse_llm::QuantizedDiffusionModel model(ctx, {layer}, H, 50, DLLM_BETA_LINEAR, 1e-4f, 0.02f, DLLM_PATH_I8);
+            std::vector<float> x(batch * feat);
+            for (size_t i = 0; i < x.size(); ++i) x[i] = std::cos(0.11f * (float)i);
+            auto y = model.forward(x, {0, 0}, batch, feat);
+            double num = 0, den = 0;
+            for (size_t tok = 0; tok < batch * seq; ++tok)
+                for (size_t n = 0; n < H; ++n) {
+                    double acc = 0;
+                    for (size_t k = 0; k < H; ++k) acc += (double)x[tok * H + k] * (double)w[k * H + n];
+                    num += (acc - (double)y[tok * H + n]) * (acc - (double)y[tok * H + n]);
+                    den += acc * acc;
+                }
+            CHECK(std::sqrt(num / den) < 2e-2);         // 8-bit weights + int8 activations: <= 1e-2 each (stated bound)
+        }
         // diffuse-llm-rs/src/lib.rs:122-313  KVCacheEntry, resident in HBM: phases, progressive decode width, accounting
         {
             const size_t L = 2, S = 4, H = 64;

@@ -265,6 +265,8 @@ pub struct GpuQuantizedModel {
     layers: Vec<QWeight>,
     model: *mut sys::dllm_model,
     hidden: usize,
+    /// which kernel family the linears run on (`sys::DLLM_PATH_*`); `DLLM_PATH_I8` = the int8 denoise mode (per-tensor weights only)
+    path: i32,
 }
 unsafe impl Send for GpuQuantizedModel {}
 unsafe impl Sync for GpuQuantizedModel {}
@@ -279,7 +281,12 @@ impl GpuQuantizedModel {
         if rc != sys::DLLM_OK {
             anyhow::bail!("dllm_model_create: status {rc}: {}", g.last_error());
         }
-        Ok(GpuQuantizedModel { layers, model, hidden })
+        Ok(GpuQuantizedModel { layers, model, hidden, path: sys::DLLM_PATH_AUTO })
+    }
+    /// Select the kernel family, e.g. `sys::DLLM_PATH_I8` for the int8 denoise mode (weights quantized per tensor, `group = 0`).
+    pub fn with_path(mut self, path: i32) -> Self {
+        self.path = path;
+        self
     }
     pub fn hidden(&self) -> usize {
         self.hidden
@@ -293,7 +300,7 @@ impl GpuQuantizedModel {
         let (batch, feat) = x0.dim();
         let mut out = Array2::<f32>::zeros((batch, feat));
         let (x, z) = (x0.as_standard_layout(), noises.as_standard_layout());
-        let rc = g.with(|c| unsafe { sys::dllm_sample(c, self.model, x.as_ptr(), z.as_ptr(), batch, feat, num_steps, 1, sys::DLLM_PATH_AUTO, out.as_mut_ptr()) });
+        let rc = g.with(|c| unsafe { sys::dllm_sample(c, self.model, x.as_ptr(), z.as_ptr(), batch, feat, num_steps, 1, self.path, out.as_mut_ptr()) });
         if rc != sys::DLLM_OK {
             anyhow::bail!("dllm_sample: status {rc}: {}", g.last_error());
         }
@@ -305,7 +312,7 @@ impl GpuQuantizedModel {
         let g = gpu();
         let mut out = Array2::<f32>::zeros((batch, feat));
         let rc = g.with(|c| unsafe {
-            sys::dllm_sample_seeded(c, self.model, std::ptr::null(), seed, batch, feat, num_steps, 1, sys::DLLM_PATH_AUTO, 1, out.as_mut_ptr())
+            sys::dllm_sample_seeded(c, self.model, std::ptr::null(), seed, batch, feat, num_steps, 1, self.path, 1, out.as_mut_ptr())
         });
         if rc != sys::DLLM_OK {
             anyhow::bail!("dllm_sample_seeded: status {rc}: {}", g.last_error());
@@ -327,7 +334,7 @@ impl DiffusionModel for GpuQuantizedModel {
         let xs = x.as_standard_layout();
         let mut out = Array2::<f32>::zeros((batch, feat));
         let rc = g.with(|c| unsafe {
-            sys::dllm_model_forward(c, self.model, xs.as_ptr(), t.as_ptr(), batch, feat, out.as_mut_ptr(), sys::DLLM_PATH_AUTO)
+            sys::dllm_model_forward(c, self.model, xs.as_ptr(), t.as_ptr(), batch, feat, out.as_mut_ptr(), self.path)
         });
         assert_eq!(rc, sys::DLLM_OK, "{}", g.last_error()); // forward() is infallible in the trait
         out
