@@ -1226,11 +1226,17 @@ struct CfgP2 {
     static constexpr bool kASmem = I8 && DLLM_I8_ASMEM;
     static constexpr int kAccBufs = kASmem ? 4 : (I8 ? DLLM_I8_NBUF : 2);
     // X ring (shared memory) and A ring (tensor memory / shared memory): same depth, one commit frees both
-    static constexpr int kSlots = kASmem ? 4 : (I8 ? (kAccBufs == 3 ? 4 : 6) : 4);
+    // (int8: SEVEN slots — eight would fill tensor memory, but shared memory then only holds 7 weight stages beside them.  The empty-pipeline timeline showed a slot's round
+    //  trip — commit -> both CTAs' unpack warps -> tensor-memory store -> remote arrive -> MMA — at 3.2 K cycles before any work, so
+    //  the stage period is (3.2 K + work) / slots: 774 cycles with six slots where the MMAs need 512)
+#ifndef DLLM_I8_SLOTS
+#define DLLM_I8_SLOTS 7
+#endif
+    static constexpr int kSlots = kASmem ? 4 : (I8 ? (kAccBufs == 3 ? 4 : DLLM_I8_SLOTS) : 4);
     static constexpr int kAStage = kASmem ? 128 * 128 : 0;             // 128 columns x 128 k bytes
     // how many stages half 0 is issued ahead of half 1 (1 = lock step)
 #ifndef DLLM_I8_PRE
-#define DLLM_I8_PRE 2
+#define DLLM_I8_PRE 3
 #endif
     static constexpr int kPre = (I8 && !kASmem) ? DLLM_I8_PRE : 1;
     // epilogue warps per CTA: 8 (two per tensor-memory lane quarter, q <= 64 columns each per half).  -DDLLM_I8_EPI16=1: 16 for int8,
@@ -1244,7 +1250,7 @@ struct CfgP2 {
     static_assert(kPre >= 1 && kPre + 1 < kSlots, "half 0 cannot run further ahead than the rings are deep");
     static constexpr int kAccCols = kAccBufs * 128;
     static constexpr int kWBytes = WL_TILE_N * WL_TILE_K * CB / 8;
-    static constexpr int kPBytes = 128 * 8;
+    static constexpr int kPBytes = I8 ? 0 : 128 * 8;                // (int8: no per-group parameters — scale and zero-point leave in the epilogue)
     static constexpr int kWStage = KBS * (kWBytes + kPBytes);
     // output staging: one accumulator half of this CTA as bf16, [2 parts][q <= 64 tokens][128 columns] = 32 KB, written
     // by the epilogue warps and stored with two bulk tensor copies (the direct 2-byte stores cost 29 % of the kernel)
@@ -1463,9 +1469,11 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     uint8_t *stage = smem_w + s * C::kWStage;
                     mbar_arrive_expect_tx(wfull + s, nk * (C::kWBytes + C::kPBytes));
                     bulk_load(stage, wsrc + (size_t)kb * C::kWBytes, nk * C::kWBytes, wfull + s);
-                    for (uint32_t sub = 0; sub < nk; ++sub) {
-                        const uint32_t g = (kb + sub) / a.group_kb;
-                        bulk_load(stage + KBS * C::kWBytes + sub * C::kPBytes, psrc + (size_t)g * a.Npad, C::kPBytes, wfull + s);
+                    if constexpr (C::kPBytes != 0) {
+                        for (uint32_t sub = 0; sub < nk; ++sub) {
+                            const uint32_t g = (kb + sub) / a.group_kb;
+                            bulk_load(stage + KBS * C::kWBytes + sub * C::kPBytes, psrc + (size_t)g * a.Npad, C::kPBytes, wfull + s);
+                        }
                     }
                 }
                 __syncwarp();
