@@ -265,7 +265,7 @@ pub struct GpuQuantizedModel {
     layers: Vec<QWeight>,
     model: *mut sys::dllm_model,
     hidden: usize,
-    /// which kernel family the linears run on (`sys::DLLM_PATH_*`); `DLLM_PATH_I8` = the int8 denoise mode (per-tensor weights only)
+    /// which kernel family the linears run on (one of the path constants of the -sys crate); `DLLM_PATH_I8` = the int8 denoise mode (per-tensor weights only)
     path: i32,
 }
 unsafe impl Send for GpuQuantizedModel {}
