@@ -1207,7 +1207,7 @@ struct CfgP2 {
     static constexpr int kXStage = I8 ? kXSlabMax : KBS * kXSlabMax;
     static constexpr int kACols = I8 ? 16 : 32, kSlotCols = KBS * kACols;
     // accumulator buffers of 128 columns (one token half each): two — the halves of a tile.  int8: the A ring is half as wide, which
-    // leaves room for a THIRD buffer (-DDLLM_I8_NBUF=3: tile t, half h lives in buffer (2 t + h) % 3, so the next tile's half 0 is
+    // leaves room for a THIRD buffer (-DDLLM_I8_NBUF=3 -DDLLM_I8_PRE=2: tile t, half h lives in buffer (2 t + h) % 3, so the next tile's half 0 is
     // accumulated while this tile's halves are drained) — but only beside a 4-slot A ring, and then the dequant warps' latency
     // (1.5 K cycles per stage) bounds the stage period at 975 cycles instead of 750: measured slower (85.2 against 87.5 steps/s), so
     // two buffers and six slots stay.
