@@ -250,6 +250,38 @@ def test_stack_forward_i8_mode_dense(ctx, O):
     model.close()
 
 
+def test_sample_seeded_int8_mode_graph_equals_eager(ctx, O):
+    """The seeded loop in the int8 denoise mode: the step captured into a CUDA graph (activation quantizers and int8 linears
+    launched with programmatic dependent launch inside the capture) is bit-identical to the eager launches, on a dense shape
+    (CTA-pair kernel) and a small one (1-CTA kernel), and stays within the stack bound of the oracle's f32 loop."""
+    from dllm_b200 import PATH_I8, QWeight
+    from dllm_b200.diffuse_llm import DiffuseLLM, DiffusionConfig, QuantizedDiffusionModel
+    rng = np.random.default_rng(77)
+    for H, seq, batch, steps in ((512, 256, 8, 4), (128, 3, 5, 5)):
+        dims = [H, 2 * H, H]
+        layers, ref = [], []
+        for K, N in zip(dims[:-1], dims[1:]):
+            w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(F)
+            layers.append(QWeight.quantize(ctx, w, 8, 0))
+            c, s, z = O.quantize_tensor(w, 8)
+            ref.append((c.reshape(K, N), np.full((1, N), s, F), np.full((1, N), z, F), None, K))
+        cfg = DiffusionConfig(num_timesteps=50, hidden_size=H, use_kv_cache=False)
+        model = QuantizedDiffusionModel(layers, H, cfg, ctx, PATH_I8)
+        llm = DiffuseLLM(cfg, ctx)
+        eager = llm.sample_seeded(model, (batch, seq), steps, 42, use_graph=False)
+        r0 = ctx.graph_replays
+        graph = llm.sample_seeded(model, (batch, seq), steps, 42, use_graph=True)
+        assert ctx.graph_replays - r0 == steps - 1
+        assert np.all(np.isfinite(eager)) and beq(eager, graph)
+        if H == 128:
+            n = batch * seq * H
+            x0 = O.noise_normal(42, steps, n).reshape(batch, -1)
+            noises = [O.noise_normal(42, t, n).reshape(batch, -1) for t in range(steps)]
+            exp = O.sample(x0, ref, H, steps, O.beta_schedule(O.BETA_LINEAR, 50), noises, True)
+            assert np.linalg.norm(eager - exp) <= 1e-2 * np.sqrt(len(layers) * steps) * np.linalg.norm(exp)
+        model.close()
+
+
 def test_simple_diffusion_model_is_the_reference_layer(ctx, O):
     """SimpleDiffusionModel: one linear x·W+b, weights N(0,1)*0.02, bias 0 (lib.rs:775-813)."""
     from dllm_b200 import PATH_SIMT
