@@ -111,6 +111,12 @@ __device__ __forceinline__ uint32_t leader_addr(const void *p) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
 }
+// The same arrive without the cluster-scope release (which compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive): for hand-offs
+// whose payload lives in tensor memory only — the tcgen05.wait / tcgen05.fence::before_thread_sync in front of it order the tensor-
+// memory accesses, and no generic-proxy write has to be published.  (int8 variant of the CTA-pair kernel.)
+__device__ __forceinline__ void mbar_arrive_cluster_tmem(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
+}
 // both CTAs load their half of the tile into their own shared memory; the bytes are reported to the LEADER's barrier
 __device__ __forceinline__ void tma_load_3d_pair(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1, int c2) {
     asm volatile(
@@ -1696,7 +1702,10 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     tc_fence_before();
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(afull_leader + sl * 8);
+                if (lane == 0) {
+                    if constexpr (I8 && !C::kASmem) mbar_arrive_cluster_tmem(afull_leader + sl * 8);
+                    else mbar_arrive_cluster(afull_leader + sl * 8);
+                }
                 if (quarter == 0 && lane == 0) TRACE2(3, it);
             }
         }
@@ -1784,7 +1793,10 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     auto release = [&]() {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(tempty_leader + buf * 8);
+                        if (lane == 0) {
+                            if constexpr (I8) mbar_arrive_cluster_tmem(tempty_leader + buf * 8);
+                            else mbar_arrive_cluster(tempty_leader + buf * 8);
+                        }
                         if (warp == kEpiWarp0 && lane == 0) TRACE2(6 + h, n_item);
                     };
                     if constexpr (I8) {
@@ -1833,7 +1845,10 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                         if (c0 + 8 >= wq) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(tempty_leader + buf * 8);
+                            if (lane == 0) {
+                                if constexpr (I8) mbar_arrive_cluster_tmem(tempty_leader + buf * 8);
+                                else mbar_arrive_cluster(tempty_leader + buf * 8);
+                            }
                         }
                         if (!n_ok) continue;
                         const size_t o = (size_t)(tok0 + c0) * ldy + n;
