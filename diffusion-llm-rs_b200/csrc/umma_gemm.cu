@@ -113,7 +113,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
 }
 // The same arrive without the cluster-scope release (which compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive): for hand-offs
 // whose payload lives in tensor memory only — the tcgen05.wait / tcgen05.fence::before_thread_sync in front of it order the tensor-
-// memory accesses, and no generic-proxy write has to be published.  (int8 variant of the CTA-pair kernel.)
+// memory accesses, and no generic-proxy write has to be published.  (Both variants of the 256-token CTA-pair kernel.)
 __device__ __forceinline__ void mbar_arrive_cluster_tmem(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
 }
@@ -1703,7 +1703,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    if constexpr (I8 && !C::kASmem) mbar_arrive_cluster_tmem(afull_leader + sl * 8);
+                    if constexpr (!C::kASmem) mbar_arrive_cluster_tmem(afull_leader + sl * 8);
                     else mbar_arrive_cluster(afull_leader + sl * 8);
                 }
                 if (quarter == 0 && lane == 0) TRACE2(3, it);
@@ -1794,8 +1794,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
-                            if constexpr (I8) mbar_arrive_cluster_tmem(tempty_leader + buf * 8);
-                            else mbar_arrive_cluster(tempty_leader + buf * 8);
+                            mbar_arrive_cluster_tmem(tempty_leader + buf * 8);
                         }
                         if (warp == kEpiWarp0 && lane == 0) TRACE2(6 + h, n_item);
                     };
@@ -1846,8 +1845,7 @@ umma_qlinear_pair2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) {
-                                if constexpr (I8) mbar_arrive_cluster_tmem(tempty_leader + buf * 8);
-                                else mbar_arrive_cluster(tempty_leader + buf * 8);
+                                mbar_arrive_cluster_tmem(tempty_leader + buf * 8);
                             }
                         }
                         if (!n_ok) continue;
